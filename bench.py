@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""bench.py — the driver-facing benchmark of the B200 state-root engine.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Headline workload (BASELINE.json configs[1], "C2"): batch keccak256 of 10M 32-byte keys per GPU — the
+AccountHashing / StorageHashing inner loop.  One step = one pass over the batch.
+  value : digests/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e   : same metric through the C-ABI with HOST (page-locked) buffers, H2D + hash + D2H inside the region
+Secondary object "state_root" (BASELINE.json configs[2], "C3"): StateRoot over 1M accounts x 16 slots per GPU,
+leaves/s; at N>1 the accounts are sharded by top key nibble and the 16-entry subtrie frontier is all-gathered
+over NCCL (the only collective of the path).
+Also printed in the same JSON line: roofline (dominant kernel vs measured HBM peak), cpu_baseline (the oracle's
+keccak on the host cores, bounded sample), clocks, gpu_launches.
+
+--impl reference times the CPU restatement of reth's algorithm (oracle/, all host threads) on a bounded sample
+of the same workload: reth itself cannot be built in this image (no Rust toolchain; its keccak/HashBuilder live
+in external crates), see DESIGN.md.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2_KEYS = 10_000_000
+C3_ACCOUNTS = 1_000_000
+C3_SLOTS = 16
+METRIC = "keccak256_digests_per_sec"
+UNIT = "digests/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------------------------------------ synthetic data
+def splitmix64_torch(seed: int, n: int, device):
+    """n 64-bit words of the splitmix64 stream (C2 = seed 2, C3 = seed 3) as int64."""
+    import torch
+    M = (1 << 64) - 1
+
+    def s64(x):  # python int -> wrapped signed 64
+        x &= M
+        return x - (1 << 64) if x >= (1 << 63) else x
+
+    idx = torch.arange(1, n + 1, dtype=torch.int64, device=device)
+    z = idx * s64(0x9E3779B97F4A7C15) + s64(seed)
+
+    def lsr(v, k):
+        return (v >> k) & ((1 << (64 - k)) - 1)
+
+    z = (z ^ lsr(z, 30)) * s64(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * s64(0x94D049BB133111EB)
+    return z ^ lsr(z, 31)
+
+
+def random_keys_torch(seed: int, n: int, device):
+    return splitmix64_torch(seed, 4 * n, device).view(n, 4)
+
+
+def be_sort_key(words):
+    """int64 [n] whose signed order equals the bytewise order of the first 8 bytes of each 32-byte row."""
+    import torch
+    b = words[:, 0].contiguous().view(torch.uint8).view(-1, 8).to(torch.int64)
+    k = torch.zeros(b.shape[0], dtype=torch.int64, device=words.device)
+    for i in range(8):
+        k = (k << 8) | b[:, i]
+    return k ^ (-(1 << 63))
+
+
+def make_c3_shard(seed: int, n_accounts: int, slots: int, nibble_lo: int, nibble_hi: int, device):
+    """C3-shaped shard resident on `device`: uniform random account keys inside top nibbles
+    [nibble_lo, nibble_hi), `slots` random slots each, everything sorted as the C ABI requires."""
+    import torch
+    akeys = random_keys_torch(seed, n_accounts, device)
+    ab = akeys.view(torch.uint8).view(n_accounts, 32)
+    span = nibble_hi - nibble_lo
+    top = (ab[:, 0] >> 4).to(torch.int64) % span + nibble_lo
+    ab[:, 0] = (top.to(torch.uint8) << 4) | (ab[:, 0] & 0x0F)
+    order = torch.sort(be_sort_key(akeys), stable=True).indices
+    akeys = akeys[order].contiguous()
+    w = splitmix64_torch(seed ^ 0xACC0, 8 * n_accounts, device).view(n_accounts, 8)
+    accts = torch.zeros((n_accounts, 72), dtype=torch.uint8, device=device)
+    accts[:, 0:2] = (w[:, 0] & 0xFFFF).contiguous().view(torch.uint8).view(n_accounts, 8)[:, 0:2]  # nonce < 2^16
+    accts[:, 8 + 22:8 + 32] = w[:, 1:3].contiguous().view(torch.uint8).view(n_accounts, 16)[:, :10]  # balance < 2^80
+    accts[:, 40:72] = w[:, 4:8].contiguous().view(torch.uint8).view(n_accounts, 32)  # code hash (contracts)
+    m = n_accounts * slots
+    skeys = random_keys_torch(seed ^ 0x5107, m, device)
+    seg = torch.arange(m, dtype=torch.int64, device=device) // slots
+    o1 = torch.sort(be_sort_key(skeys), stable=True).indices
+    o2 = torch.sort(seg[o1], stable=True).indices
+    skeys = skeys[o1[o2]].contiguous()
+    vals = torch.zeros((m, 32), dtype=torch.uint8, device=device)
+    v = splitmix64_torch(seed ^ 0x7A1, m, device) | 1  # uniform in [1, 2^64): RLP 1..9 bytes
+    vals[:, 24:32] = v.view(torch.uint8).view(m, 8).flip(1)  # big-endian
+    offs = torch.arange(0, n_accounts + 1, dtype=torch.int64, device=device) * slots
+    return dict(akeys=akeys.view(torch.uint8).view(-1), accts=accts.view(-1), skeys=skeys.view(torch.uint8).view(-1),
+                svals=vals.view(-1), offs=offs, n_accounts=n_accounts, n_slots=m)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region (pynvml)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_keccak_baseline(target_seconds: float = 12.0):
+    """oracle keccak over 32-byte keys on all host cores; bounded sample of the C2 workload."""
+    import oracle
+    cores = os.cpu_count() or 1
+    n = 2_000_000
+    from tests.util import random_keys
+    keys = random_keys(2, n)
+    oracle.keccak256_fixed(keys[:100_000], threads=cores)  # warm
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        oracle.keccak256_fixed(keys, threads=cores)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= target_seconds or reps >= 64:
+            break
+    return {"value": n * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{reps} x {n} of the 10M 32-byte keys (splitmix64 seed 2), scalar C keccak, {cores} threads, chunks of 100"}
+
+
+def cpu_state_root_baseline(n_accounts: int = 40_000, slots: int = 16):
+    """oracle ParallelStateRoot-shaped build on all host cores over a C3-shaped sample."""
+    import oracle
+    from tests.util import synth_accounts, synth_storage
+    cores = os.cpu_count() or 1
+    akeys, accs = synth_accounts(3, n_accounts)
+    skeys, svals, offs = synth_storage(3, np.full(n_accounts, slots))
+    leaves = n_accounts * (slots + 1)
+    t0 = time.perf_counter()
+    oracle.state_root_full(akeys, accs, skeys, svals, offs, threads=cores)
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    oracle.state_root_full(akeys, accs, skeys, svals, offs, threads=1)
+    dt1 = time.perf_counter() - t1
+    return {"value": leaves / dt, "unit": "leaves/s", "cores": cores, "kind": "port",
+            "single_thread_value": leaves / dt1,
+            "sample": f"{n_accounts} accounts x {slots} slots ({leaves} leaves): storage tries on {cores} threads, "
+                      "account trie serial (ParallelStateRoot shape); single_thread_value = StateRoot shape"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement timed on the host cores, same metric/config, bounded sample."""
+    if rank != 0:
+        return
+    import oracle
+    from tests.util import random_keys
+    cores = os.cpu_count() or 1
+    n = 1_000_000
+    keys = random_keys(2, n)
+    for _ in range(args.warmup):
+        oracle.keccak256_fixed(keys[:200_000], threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.keccak256_fixed(keys, threads=cores)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    sample = f"each step hashes {n} of the 10M 32-byte keys on {cores} host threads (scalar C keccak, chunks of 100)"
+    sr = cpu_state_root_baseline()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "C2: batch keccak256 of 10M 32-byte keys per GPU (AccountHashing/StorageHashing inner loop)",
+                   "reference": "CPU restatement of reth's algorithm (oracle/); reth cannot be built here (no Rust toolchain)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "state_root": {"value": sr["value"], "unit": "leaves/s", "cores": cores, "sample": sr["sample"],
+                       "single_thread_value": sr["single_thread_value"]},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--keys", type=int, default=C2_KEYS, help="keys per GPU for the keccak workload")
+    ap.add_argument("--accounts", type=int, default=C3_ACCOUNTS, help="accounts per GPU for the state-root workload")
+    ap.add_argument("--skip-state-root", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from reth_b200 import Engine
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Engine(local_rank)
+    eng.use_torch_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------------------------------------------------------- C2: keccak, inputs resident in HBM
+    n = args.keys
+    d_keys = random_keys_torch(2 + 1000 * rank, n, dev).view(torch.uint8).view(-1)
+    d_out = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+    for _ in range(args.warmup):
+        eng.keccak256_fixed_dev(d_keys, 32, 32, n, d_out)
+    barrier()
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            eng.keccak256_fixed_dev(d_keys, 32, 32, n, d_out)
+        e1.record()
+        barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    gpu_launches = eng.launch_count() - launches0
+    ms_per_step = ms_total / args.steps
+    value = world * n * args.steps / (ms_total * 1e-3)
+
+    # spot-check the timed output against the oracle (checker only)
+    import oracle
+    idx = torch.randint(0, n, (64,), device=dev)
+    got = d_out.view(n, 32)[idx].cpu().numpy()
+    exp = oracle.keccak256_fixed(d_keys.view(n, 32)[idx].cpu().numpy())
+    parity_ok = bool((got == exp).all())
+
+    # ---------------------------------------------------------------- C2 e2e: host buffers through the C ABI
+    h_in = eng.pinned_empty((n, 32))
+    h_out = eng.pinned_empty((n, 32))
+    h_in[:] = d_keys.view(n, 32).cpu().numpy()
+    eng.set_stream(None)
+    for _ in range(2):
+        eng.keccak256_fixed(h_in, 32, out=h_out)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.keccak256_fixed(h_in, 32, out=h_out)
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = {"value": world * n * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * 32,
+           "d2h_bytes_per_step": n * 32, "steps": e2e_steps,
+           "api": "b200_keccak256_fixed (host pointers, page-locked, chunked double-buffered H2D/kernel/D2H)"}
+    eng.use_torch_stream()
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "of measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
+    algo_bytes = 64 * n  # 32 B key read + 32 B digest written per digest
+    achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(prof):
+        traffic = json.load(open(prof)).get("keccak256_fixed32_kernel_dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "keccak256_fixed32_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "note": "Keccak-f is ALU-bound (~4.3k LOP3/SHF per digest on the 64-lane/clk/SM ALU pipe): "
+                        "see alu_frac for the binding roofline",
+                "alu_frac": None}
+    if clk.summary()["sm_mhz"]:
+        alu_peak = 148 * 64 * clk.summary()["sm_mhz"] * 1e6 / 4254.0  # digests/s if every ALU slot did keccak work
+        roofline["alu_frac"] = (n / (ms_per_step * 1e-3)) / alu_peak
+        roofline["alu_peak_digests_per_s"] = alu_peak
+
+    # ---------------------------------------------------------------- C3: state root
+    state_root = None
+    if not args.skip_state_root:
+        state_root = bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu = cpu_keccak_baseline()
+        if state_root is not None:
+            state_root["cpu_baseline"] = cpu_state_root_baseline()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "C2: batch keccak256 of 10M 32-byte keys per GPU (AccountHashing/StorageHashing inner loop)",
+                       "keys_per_gpu": n, "msg_len": 32, "parallelism": f"keys sharded over {world} GPU(s), no collective",
+                       "l2": "input 320 MB + output 320 MB per step exceed the 126 MB L2; no flush needed"},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
+            "cpu_baseline": cpu, "state_root": state_root, "parity_spot_check": parity_ok,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks):
+    import torch
+    import torch.distributed as dist
+    n_acc = args.accounts
+    lo, hi = rank * 16 // world, (rank + 1) * 16 // world
+    if world > 16:
+        raise SystemExit("top-nibble sharding supports at most 16 ranks")
+    sh = make_c3_shard(3 + 1000 * rank, n_acc, C3_SLOTS, lo, hi, dev)
+    leaves = n_acc * (C3_SLOTS + 1)
+    d_root = torch.zeros(32, dtype=torch.uint8, device=dev)
+    d_front = torch.zeros(16 * 68, dtype=torch.uint8, device=dev)
+    gathered = [torch.zeros(16 * 68, dtype=torch.uint8, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step():
+        if world == 1:
+            eng.state_root_full_dev(sh["akeys"], sh["accts"], n_acc, sh["skeys"], sh["svals"], sh["offs"],
+                                    sh["n_slots"], d_root)
+        else:
+            eng.subtrie_frontier_dev(sh["akeys"], sh["accts"], n_acc, sh["skeys"], sh["svals"], sh["offs"],
+                                     sh["n_slots"], d_front)
+            dist.all_gather(gathered, d_front)  # 16 x 68 B per rank: the one collective of the path
+            merged = torch.stack(gathered).view(world, 16, 68)
+            pick = torch.arange(16, device=dev) * world // 16  # owner rank of each top nibble
+            front = merged[pick, torch.arange(16, device=dev)].contiguous().view(-1)
+            eng.root_from_frontier_dev(front, d_root)
+            step.front = front  # keep alive until the stream has consumed it
+
+    for _ in range(max(2, args.warmup - 1)):
+        step()
+    barrier()
+    eng.dev_status()
+    steps = max(3, min(args.steps, 10))
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    eng.dev_status()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    stats = eng.last_stats()
+    res = {"metric": "state_root_leaves_per_sec", "value": world * leaves / (ms * 1e-3), "unit": "leaves/s",
+           "ms_per_step": ms, "steps": steps, "gpu_launches": int(eng.launch_count() - l0),
+           "config": {"workload": f"C3: StateRoot over {n_acc} accounts x {C3_SLOTS} storage slots per GPU, "
+                                  "level-by-level node-hash frontier", "leaves_per_gpu": leaves,
+                      "parallelism": "single GPU" if world == 1 else
+                      f"accounts sharded by top key nibble over {world} GPUs, one NCCL all-gather of 16 frontier entries"},
+           "root": bytes(d_root.cpu().numpy()).hex(),
+           "node_digests_per_sec": world * stats["hashed_nodes"] / (ms * 1e-3) if world == 1 else None,
+           "stats": stats,
+           "algorithmic_gb_per_s": world * (n_acc * C3_SLOTS * 64 + n_acc * 104) / (ms * 1e-3) / 1e9}
+    if world == 1:
+        # e2e: host (page-locked) buffers through b200_state_root_full
+        h = {k: eng.pinned_empty(tuple(v.shape), np.uint8 if v.dtype == torch.uint8 else np.int64)
+             for k, v in sh.items() if hasattr(v, "shape")}
+        for k in h:
+            h[k][...] = sh[k].cpu().numpy()
+        eng.set_stream(None)
+        accts = h["accts"].view(eng_account_dtype())
+        for _ in range(2):
+            root = eng.state_root_full(h["akeys"], accts, h["skeys"], h["svals"], h["offs"].view(np.uint64))
+        t0 = time.perf_counter()
+        e2e_steps = 3
+        for _ in range(e2e_steps):
+            root = eng.state_root_full(h["akeys"], accts, h["skeys"], h["svals"], h["offs"].view(np.uint64))
+        dt = time.perf_counter() - t0
+        eng.use_torch_stream()
+        res["e2e"] = {"value": leaves * e2e_steps / dt, "unit": "leaves/s",
+                      "h2d_bytes_per_step": int(sum(v.nbytes for v in h.values())), "d2h_bytes_per_step": 32,
+                      "root_matches_device_run": root.hex() == res["root"],
+                      "api": "b200_state_root_full (host pointers, page-locked)"}
+    return res
+
+
+def eng_account_dtype():
+    from reth_b200 import ACCOUNT_DTYPE
+    return ACCOUNT_DTYPE
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,211 @@
+/*
+ * b200trie.h — C ABI of the B200-native state-root engine (libb200trie.so).
+ *
+ * This is the drop-in boundary for reth's Merkle-Patricia-Trie commitment path.  reth has no FFI for this
+ * path (it is all Rust traits/closures); each entry point below names the reference interface a thin Rust
+ * shim would route to it (paths relative to the reth workspace; the shim itself is shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all multi-byte integers little-endian host order unless a field says BE
+ *   - every function returns B200_OK (0) or a negative b200_status; b200_last_error(ctx) gives the text
+ *   - the library never aborts/throws across the boundary and never falls back to a CPU path: without a
+ *     usable CUDA device b200_create fails with B200_ERR_NO_DEVICE
+ *   - a b200_ctx is internally locked: calls on one ctx are serialised, different ctxs run concurrently
+ *     (ParallelStateRoot calls StorageRoot from many threads: crates/trie/parallel/src/root.rs:111-125)
+ *   - host-pointer entry points copy inputs to the device and results back (these are what the e2e
+ *     benchmark times); *_dev entry points take device pointers, enqueue on the ctx stream and return
+ *     without synchronising (b200_sync to wait)
+ *   - hashed keys are 32-byte big-endian strings exactly as reth's B256; sorted means ascending bytewise
+ */
+#ifndef B200TRIE_H
+#define B200TRIE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_ctx b200_ctx;
+
+typedef enum {
+    B200_OK = 0,
+    B200_ERR_NO_DEVICE = -1,   /* no CUDA device / driver */
+    B200_ERR_CUDA = -2,        /* CUDA runtime error (text in b200_last_error) */
+    B200_ERR_INVALID_ARG = -3, /* null pointer, bad length, offsets not monotone ... */
+    B200_ERR_UNSORTED = -4,    /* keys not strictly ascending inside a trie (HashBuilder::add_leaf asserts this) */
+    B200_ERR_ZERO_VALUE = -5,  /* a storage slot with value 0: reth treats zero as deletion
+                                  (crates/trie/common/src/hashed_state.rs:423-455), it is never a leaf */
+    B200_ERR_OOM = -6,
+    B200_ERR_INLINE_HASH_CHILD = -7 /* a <32-byte branch child under a hash_mask bit while retaining updates:
+                                       alloy-trie's child_hashes would panic here; unreachable for keccak keys */
+} b200_status;
+
+/* ------------------------------------------------------------------------------------------------ lifecycle */
+/* Number of usable CUDA devices (0 when there is no driver). */
+B200_API int32_t b200_device_count(void);
+/* One context per device ordinal (one process per GPU in the multi-GPU layout). NULL on failure;
+ * b200_create_status() then tells why. */
+B200_API b200_ctx *b200_create(int32_t device_ordinal);
+B200_API int32_t b200_create_status(void);
+B200_API void b200_destroy(b200_ctx *);
+B200_API const char *b200_last_error(const b200_ctx *);
+B200_API const char *b200_version(void);
+/* Use an existing CUDA stream (cudaStream_t passed as void*) instead of the context's own stream, so that a
+ * host runtime (torch, the Rust shim's stream) can order and time the work. NULL restores the own stream. */
+B200_API int32_t b200_set_stream(b200_ctx *, void *cuda_stream);
+B200_API int32_t b200_sync(b200_ctx *);
+/* Page-locked host buffers for the host-pointer entry points (pageable memory works too, but is slower). */
+B200_API void *b200_host_alloc(size_t bytes);
+B200_API void b200_host_free(void *);
+/* Scratch the context currently holds on the device, bytes. */
+B200_API uint64_t b200_device_bytes(const b200_ctx *);
+/* Kernel launches issued through this context so far (what bench.py reports as gpu_launches). */
+B200_API uint64_t b200_launch_count(const b200_ctx *);
+
+/* ------------------------------------------------------------------------------------------------ key hashing
+ * Replaces the per-key `keccak256` of KeccakKeyHasher::hash_key (crates/trie/common/src/key.rs:4-18) as
+ * batched by AccountHashingStage (crates/stages/stages/src/stages/hashing_account.rs:192-211, 20-byte
+ * addresses), StorageHashingStage (hashing_storage.rs:121-148, 20-byte address + 32-byte slot),
+ * HashedPostState::from_bundle_state (crates/trie/common/src/hashed_state.rs:49-69) and
+ * load_prefix_sets_with_provider (crates/trie/db/src/prefix_set.rs:42-60).
+ *
+ * in: n messages of msg_len bytes, message i at in + i*stride (stride >= msg_len). out32: n*32 bytes. */
+B200_API int32_t b200_keccak256_fixed(b200_ctx *, const uint8_t *in, uint32_t msg_len, uint32_t stride, uint64_t n,
+                             uint8_t *out32);
+B200_API int32_t b200_keccak256_fixed_dev(b200_ctx *, const void *d_in, uint32_t msg_len, uint32_t stride, uint64_t n,
+                                 void *d_out32);
+/* Variable-length messages (contract code -> code hash, arbitrary RLP): message i is
+ * data[offsets[i] .. offsets[i+1]). */
+B200_API int32_t b200_keccak256_var(b200_ctx *, const uint8_t *data, const uint64_t *offsets, uint64_t n, uint8_t *out32);
+B200_API int32_t b200_keccak256_var_dev(b200_ctx *, const void *d_data, const void *d_offsets, uint64_t n, void *d_out32);
+
+/* Hash then sort: what the hashing stages feed to the ETL collector (crates/etl/src/lib.rs:31-60,
+ * hashing_account.rs:207-230).  out_sorted32 receives the digests in ascending order, out_perm[i] is the
+ * input index whose digest landed at position i (the shim permutes the values with it). */
+B200_API int32_t b200_hash_sort_keys(b200_ctx *, const uint8_t *in, uint32_t msg_len, uint32_t stride, uint64_t n,
+                            uint8_t *out_sorted32, uint32_t *out_perm);
+B200_API int32_t b200_hash_sort_keys_dev(b200_ctx *, const void *d_in, uint32_t msg_len, uint32_t stride, uint64_t n,
+                                void *d_sorted32, void *d_perm_u32);
+/* The sort half alone: n 32-byte keys (already digests) -> ascending order + permutation. */
+B200_API int32_t b200_sort_keys32_dev(b200_ctx *, const void *d_keys32, uint64_t n, void *d_sorted32, void *d_perm_u32);
+
+/* ------------------------------------------------------------------------------------------------ trie inputs
+ * reth's Account (reth-primitives-traits: nonce u64, balance U256, bytecode_hash Option<B256>) flattened;
+ * the shim writes KECCAK_EMPTY when bytecode_hash is None (crates/trie/common/src/account.rs:16-31). */
+typedef struct {
+    uint64_t nonce;
+    uint8_t balance_be[32];
+    uint8_t code_hash[32];
+} b200_account; /* 72 bytes */
+
+/* TrieUpdates / StorageTrieUpdates after finalize (crates/trie/common/src/updates.rs:17-26,140-158,235-245):
+ * one record per stored BranchNodeCompact, empty path excluded.  Record order is deterministic (by path
+ * length, then key order) but carries no meaning: reth keeps these in hash maps.  All arrays are owned by the library (pinned host memory); release with b200_updates_release. */
+typedef struct {
+    uint64_t n_nodes;
+    uint32_t *trie_id;     /* storage tries: index of the account (segment); account trie: 0 */
+    uint8_t *path_len;     /* nibbles, 1..63 */
+    uint8_t *path_packed;  /* [n_nodes][32] nibbles packed high-first, zero padded */
+    uint16_t *state_mask, *tree_mask, *hash_mask;
+    uint64_t *hash_offset; /* [n_nodes+1] into hashes */
+    uint8_t *hashes;       /* [hash_offset[n_nodes]][32] child hashes, ascending nibble */
+    void *_owner;
+} b200_updates;
+B200_API void b200_updates_release(b200_updates *);
+
+/* TrieStats / TrieRootMetrics (crates/trie/trie/src/stats.rs, metrics.rs:22-40) plus device timing. */
+typedef struct {
+    uint64_t leaves_added;
+    uint64_t branches_added;   /* branch nodes built (reth counts add_branch calls; a from-scratch build has none) */
+    uint64_t extension_nodes;
+    uint64_t hashed_nodes;     /* keccak digests produced (node RLP >= 32 bytes, plus roots) */
+    uint64_t levels;           /* populated trie levels processed */
+    double device_ms;          /* stream time of the build, measured with CUDA events */
+} b200_stats;
+
+/* ------------------------------------------------------------------------------------------------ roots
+ * StorageRoot::calculate for n_accounts tries in one call (crates/trie/trie/src/trie.rs:615-721; the
+ * fan-out of ParallelStateRoot, crates/trie/parallel/src/root.rs:101-127).  Segment a holds slots
+ * seg_offsets[a] .. seg_offsets[a+1]: slot_keys32 = keccak(slot) sorted ascending inside the segment,
+ * values32_be = U256 big-endian, non-zero.  Empty segment -> EMPTY_ROOT_HASH (trie.rs:622-629).
+ * roots32: n_accounts*32. opt_updates may be NULL (root(): no updates retained). */
+B200_API int32_t b200_storage_roots(b200_ctx *, const uint8_t *slot_keys32, const uint8_t *values32_be,
+                           const uint64_t *seg_offsets, uint64_t n_accounts, uint8_t *roots32,
+                           b200_updates *opt_updates, b200_stats *opt_stats);
+
+/* The account-trie fold of StateRoot::calculate (trie.rs:247-309): leaf i = rlp(TrieAccount{nonce, balance,
+ * storage_roots32[i], code_hash}) under key acct_keys32[i] (trie.rs:429-432).  storage_roots32 may be NULL
+ * (all EMPTY_ROOT_HASH).  n == 0 -> EMPTY_ROOT_HASH. */
+B200_API int32_t b200_state_root(b200_ctx *, const uint8_t *acct_keys32, const b200_account *accts,
+                        const uint8_t *storage_roots32, uint64_t n, uint8_t root32[32],
+                        b200_updates *opt_updates, b200_stats *opt_stats);
+
+/* StateRoot::root_with_updates / ParallelStateRoot::incremental_root_with_updates over a complete
+ * HashedPostStateSorted-shaped input (crates/trie/common/src/hashed_state.rs:519-524,710-715): all storage
+ * tries, then all account leaves, then the account trie, without leaving the device.
+ * seg_offsets has n_accounts+1 entries (segment a = storage of account a). */
+B200_API int32_t b200_state_root_full(b200_ctx *, const uint8_t *acct_keys32, const b200_account *accts,
+                             uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
+                             const uint64_t *seg_offsets, uint8_t root32[32],
+                             b200_updates *opt_account_updates, b200_updates *opt_storage_updates,
+                             b200_stats *opt_stats);
+
+/* Device-resident variants: every pointer is a device pointer (seg_offsets included), results are written
+ * to device memory, nothing is copied or synchronised.  d_root32 / d_roots32 are device buffers.
+ * Input violations (unsorted keys, zero values) are reported by the next b200_sync / b200_dev_status. */
+B200_API int32_t b200_storage_roots_dev(b200_ctx *, const void *d_slot_keys32, const void *d_values32_be,
+                               const void *d_seg_offsets, uint64_t n_accounts, uint64_t n_slots,
+                               void *d_roots32);
+B200_API int32_t b200_state_root_dev(b200_ctx *, const void *d_acct_keys32, const void *d_accts,
+                            const void *d_storage_roots32, uint64_t n, void *d_root32);
+B200_API int32_t b200_state_root_full_dev(b200_ctx *, const void *d_acct_keys32, const void *d_accts, uint64_t n_accounts,
+                                 const void *d_slot_keys32, const void *d_values32_be, const void *d_seg_offsets,
+                                 uint64_t n_slots, void *d_root32);
+/* Sticky status of the asynchronous entry points (B200_OK / B200_ERR_UNSORTED / ...); synchronises. */
+B200_API int32_t b200_dev_status(b200_ctx *);
+/* Stats of the last build on this ctx (synchronises). */
+B200_API int32_t b200_last_stats(b200_ctx *, b200_stats *out);
+
+/* ------------------------------------------------------------------------------------------------ multi-GPU
+ * Key-range sharding of the account trie: a rank owns whole top-nibble buckets of the hashed
+ * address space together with the storage tries of its accounts.  It builds its buckets with
+ * b200_subtrie_frontier, the 16 frontier entries of all ranks are all-gathered (NCCL, 16 x 2 x 34 bytes), and
+ * every rank finishes the root with b200_root_from_frontier.
+ *
+ * Each bucket yields two RlpNode candidates (len byte + up to 33 bytes):
+ *   as_child: the node as child `nibble` of a depth-0 root branch (used when >= 2 buckets are non-empty)
+ *   as_root : the bucket alone as the whole trie (used when it is the only non-empty bucket)
+ * len == 0 means the bucket is empty. */
+typedef struct {
+    uint8_t as_child_len;
+    uint8_t as_child[33];
+    uint8_t as_root_len; /* 0 or 32: root hash */
+    uint8_t as_root[33];
+} b200_frontier_entry; /* 68 bytes */
+
+/* acct_keys32/accts/storage as in b200_state_root_full but holding only this rank's accounts (any subset of
+ * top nibbles). frontier: 16 entries, entries of nibbles this rank does not own are zeroed. */
+B200_API int32_t b200_subtrie_frontier(b200_ctx *, const uint8_t *acct_keys32, const b200_account *accts,
+                              uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
+                              const uint64_t *seg_offsets, b200_frontier_entry frontier[16],
+                              b200_stats *opt_stats);
+B200_API int32_t b200_subtrie_frontier_dev(b200_ctx *, const void *d_acct_keys32, const void *d_accts, uint64_t n_accounts,
+                                  const void *d_slot_keys32, const void *d_values32_be, const void *d_seg_offsets,
+                                  uint64_t n_slots, void *d_frontier /* 16 x b200_frontier_entry */);
+/* Combine the gathered frontier (entry i = bucket of top nibble i, from whichever rank owns it). Host-side,
+ * 17 node hashes at most; runs on the device like everything else. */
+B200_API int32_t b200_root_from_frontier(b200_ctx *, const b200_frontier_entry frontier[16], uint8_t root32[32]);
+B200_API int32_t b200_root_from_frontier_dev(b200_ctx *, const void *d_frontier, void *d_root32);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TRIE_H */

@@ -1,0 +1,7 @@
+"""reth_b200 — B200-native state-root engine behind reth's StateRoot / StorageRoot / HashedPostState surface.
+
+The product is libb200trie.so (hand-written sm_100a CUDA behind the C ABI of include/b200trie.h); this
+package is the host-side mirror of the reference interface used by tests and benchmarks.
+"""
+from ._lib import B200Error, LIB_PATH  # noqa: F401
+from .engine import ACCOUNT_DTYPE, EMPTY_ROOT_HASH, KECCAK_EMPTY, Engine  # noqa: F401

@@ -1,0 +1,119 @@
+"""ctypes loader for libb200trie.so (the C-ABI of include/b200trie.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is usable, the error is raised
+to the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200trie.so")
+
+# b200_status (include/b200trie.h)
+OK, ERR_NO_DEVICE, ERR_CUDA, ERR_INVALID_ARG, ERR_UNSORTED, ERR_ZERO_VALUE, ERR_OOM, ERR_INLINE_HASH_CHILD = (
+    0, -1, -2, -3, -4, -5, -6, -7)
+
+
+class B200Error(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"b200 status {status}: {message}")
+        self.status = status
+
+
+class Updates(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_uint64),
+        ("trie_id", C.POINTER(C.c_uint32)),
+        ("path_len", C.POINTER(C.c_uint8)),
+        ("path_packed", C.POINTER(C.c_uint8)),
+        ("state_mask", C.POINTER(C.c_uint16)),
+        ("tree_mask", C.POINTER(C.c_uint16)),
+        ("hash_mask", C.POINTER(C.c_uint16)),
+        ("hash_offset", C.POINTER(C.c_uint64)),
+        ("hashes", C.POINTER(C.c_uint8)),
+        ("_owner", C.c_void_p),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("leaves_added", C.c_uint64),
+        ("branches_added", C.c_uint64),
+        ("extension_nodes", C.c_uint64),
+        ("hashed_nodes", C.c_uint64),
+        ("levels", C.c_uint64),
+        ("device_ms", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class FrontierEntry(C.Structure):
+    _fields_ = [
+        ("as_child_len", C.c_uint8),
+        ("as_child", C.c_uint8 * 33),
+        ("as_root_len", C.c_uint8),
+        ("as_root", C.c_uint8 * 33),
+    ]
+
+
+assert C.sizeof(FrontierEntry) == 68
+
+_lib = None
+
+
+def load():
+    """Returns the loaded library; raises if libb200trie.so has not been built (python -c 'import
+    __graft_entry__ as g; g.build()' or make -C reth_b200/csrc)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `make -C reth_b200/csrc` (needs nvcc). "
+                          "reth_b200 has no CPU path.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u32, u64 = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64
+    PU, PS = C.POINTER(Updates), C.POINTER(Stats)
+
+    def sig(name, res, *args):
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = list(args)
+
+    sig("b200_device_count", i32)
+    sig("b200_create", vp, i32)
+    sig("b200_create_status", i32)
+    sig("b200_destroy", None, vp)
+    sig("b200_last_error", C.c_char_p, vp)
+    sig("b200_version", C.c_char_p)
+    sig("b200_set_stream", i32, vp, vp)
+    sig("b200_sync", i32, vp)
+    sig("b200_host_alloc", vp, C.c_size_t)
+    sig("b200_host_free", None, vp)
+    sig("b200_device_bytes", u64, vp)
+    sig("b200_launch_count", u64, vp)
+    sig("b200_keccak256_fixed", i32, vp, vp, u32, u32, u64, vp)
+    sig("b200_keccak256_fixed_dev", i32, vp, vp, u32, u32, u64, vp)
+    sig("b200_keccak256_var", i32, vp, vp, vp, u64, vp)
+    sig("b200_keccak256_var_dev", i32, vp, vp, vp, u64, vp)
+    sig("b200_hash_sort_keys", i32, vp, vp, u32, u32, u64, vp, vp)
+    sig("b200_hash_sort_keys_dev", i32, vp, vp, u32, u32, u64, vp, vp)
+    sig("b200_sort_keys32_dev", i32, vp, vp, u64, vp, vp)
+    sig("b200_updates_release", None, PU)
+    sig("b200_storage_roots", i32, vp, vp, vp, vp, u64, vp, PU, PS)
+    sig("b200_state_root", i32, vp, vp, vp, vp, u64, vp, PU, PS)
+    sig("b200_state_root_full", i32, vp, vp, vp, u64, vp, vp, vp, vp, PU, PU, PS)
+    sig("b200_storage_roots_dev", i32, vp, vp, vp, vp, u64, u64, vp)
+    sig("b200_state_root_dev", i32, vp, vp, vp, vp, u64, vp)
+    sig("b200_state_root_full_dev", i32, vp, vp, vp, u64, vp, vp, vp, u64, vp)
+    sig("b200_dev_status", i32, vp)
+    sig("b200_last_stats", i32, vp, PS)
+    sig("b200_subtrie_frontier", i32, vp, vp, vp, u64, vp, vp, vp, C.POINTER(FrontierEntry), PS)
+    sig("b200_subtrie_frontier_dev", i32, vp, vp, vp, u64, vp, vp, vp, u64, vp)
+    sig("b200_root_from_frontier", i32, vp, C.POINTER(FrontierEntry), vp)
+    sig("b200_root_from_frontier_dev", i32, vp, vp, vp)
+    _lib = L
+    return L

@@ -1,0 +1,823 @@
+// engine.cu — context, HBM scratch arena, build orchestration and the extern "C" B200_API boundary of
+// libb200trie.so (include/b200trie.h).  No CPU fallback exists: every entry point needs a CUDA device.
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+#include "kernels.h"
+#include "trie_kernels.h"
+
+using namespace b200;
+
+#define B200_VERSION_STR "reth_b200 0.1.0 (sm_100a)"
+
+static thread_local int g_create_status = 0;
+
+// layout of the `small` device buffer (uint32 units)
+enum : int { SM_BUCKET_OFF = 0, SM_LEVEL_LO = 80, SM_NNODES = 160, SM_ERR = 164, SM_NSTORED = 168, SM_COUNTERS = 176 /* 4 x u64 */, SM_WORDS = 256 };
+
+static uint32_t *small_u32(b200_ctx *c) { return static_cast<uint32_t *>(c->small.p); }
+
+extern "C" B200_API int32_t b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" B200_API int32_t b200_create_status(void) { return g_create_status; }
+
+extern "C" B200_API b200_ctx *b200_create(int32_t device_ordinal) {
+    int n = b200_device_count();
+    if (n <= 0 || device_ordinal < 0 || device_ordinal >= n) {
+        g_create_status = n <= 0 ? B200_ERR_NO_DEVICE : B200_ERR_INVALID_ARG;
+        return nullptr;
+    }
+    b200_ctx *c = new b200_ctx();
+    c->device = device_ordinal;
+    auto bail = [&](cudaError_t e) -> b200_ctx * {
+        (void)e;
+        g_create_status = B200_ERR_CUDA;
+        delete c;
+        return nullptr;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return bail(e);
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    c->stream = c->own_stream;
+    for (int i = 0; i < 2; i++)
+        if ((e = cudaStreamCreateWithFlags(&c->copy_streams[i], cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail(e);
+    if ((e = cudaMallocHost(&c->pinned_small, 4096)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&c->small.p, SM_WORDS * 4)) != cudaSuccess) return bail(e);
+    c->small.cap = SM_WORDS * 4;
+    c->dev_bytes += c->small.cap;
+    if ((e = cudaMemset(c->small.p, 0, SM_WORDS * 4)) != cudaSuccess) return bail(e);
+    g_create_status = B200_OK;
+    return c;
+}
+
+extern "C" B200_API void b200_destroy(b200_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    DevBuf *bufs[] = {&c->Lp, &c->nibs, &c->leaf_ref, &c->leaf_meta, &c->S, &c->E, &c->iota, &c->depth_sorted,
+                      &c->gap_sorted, &c->bound_rank, &c->head, &c->node_start, &c->node_ref, &c->node_meta,
+                      &c->node_l, &c->node_r, &c->node_masks, &c->cub_temp, &c->small, &c->sroots, &c->buckets,
+                      &c->upd_flags, &c->upd_nh, &c->upd_ids, &c->upd_prefix, &c->in_a, &c->in_b, &c->in_c,
+                      &c->in_d, &c->in_e, &c->out_a, &c->chunk_in[0], &c->chunk_in[1], &c->chunk_out[0],
+                      &c->chunk_out[1], &c->sort_ka, &c->sort_kb, &c->sort_ia, &c->sort_flag, &c->sort_perm,
+                      &c->sort_out};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (c->pinned_small) cudaFreeHost(c->pinned_small);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    for (int i = 0; i < 2; i++)
+        if (c->copy_streams[i]) cudaStreamDestroy(c->copy_streams[i]);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" B200_API const char *b200_last_error(const b200_ctx *c) { return c ? c->err.c_str() : "null context"; }
+extern "C" B200_API const char *b200_version(void) { return B200_VERSION_STR; }
+extern "C" B200_API uint64_t b200_device_bytes(const b200_ctx *c) { return c ? c->dev_bytes : 0; }
+
+extern "C" B200_API int32_t b200_set_stream(b200_ctx *c, void *cuda_stream) {
+    if (!c) return B200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(c->mu);
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return B200_OK;
+}
+
+extern "C" B200_API void *b200_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" B200_API void b200_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+static int32_t map_dev_error(b200_ctx *c, int code) {
+    switch (code) {
+        case B200_DEVERR_NONE: return B200_OK;
+        case B200_DEVERR_UNSORTED: return fail(c, B200_ERR_UNSORTED, "keys are not strictly ascending inside a trie");
+        case B200_DEVERR_ZERO_VALUE: return fail(c, B200_ERR_ZERO_VALUE, "storage slot with zero value (zero means deleted)");
+        case B200_DEVERR_INLINE_HASH_CHILD:
+            return fail(c, B200_ERR_INLINE_HASH_CHILD, "inline (<32 byte) branch child under a hash_mask bit");
+        case B200_DEVERR_BAD_OFFSETS: return fail(c, B200_ERR_INVALID_ARG, "seg_offsets must start at 0, end at n and be monotone");
+        default: return fail(c, B200_ERR_CUDA, "unknown device error %d", code);
+    }
+}
+
+// waits for the stream, folds the timing / counters of the last build into stats, returns the sticky status
+static int32_t sync_and_status(b200_ctx *c) {
+    CU(cudaStreamSynchronize(c->stream));
+    uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
+    CU(cudaMemcpyAsync(ps, small_u32(c) + SM_ERR, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(ps + 8, small_u32(c) + SM_COUNTERS, 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->stats_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->stats.device_ms = ms;
+        else cudaGetLastError();
+        const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(ps + 8);
+        c->stats.hashed_nodes = cnt[CNT_HASHED];
+        c->stats.extension_nodes = cnt[CNT_EXT];
+        c->stats_pending = false;
+    }
+    return map_dev_error(c, (int)ps[0]);
+}
+
+static int32_t reset_build_state(b200_ctx *c) {
+    CU(cudaMemsetAsync(small_u32(c) + SM_ERR, 0, 4, c->stream));
+    CU(cudaMemsetAsync(small_u32(c) + SM_COUNTERS, 0, 32, c->stream));
+    c->stats = b200_stats{};
+    CU(cudaEventRecord(c->ev0, c->stream));
+    return B200_OK;
+}
+static int32_t finish_build_state(b200_ctx *c) {
+    CU(cudaEventRecord(c->ev1, c->stream));
+    c->stats_pending = true;
+    return B200_OK;
+}
+
+extern "C" B200_API int32_t b200_sync(b200_ctx *c) {
+    if (!c) return B200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    return sync_and_status(c);
+}
+extern "C" B200_API int32_t b200_dev_status(b200_ctx *c) { return b200_sync(c); }
+extern "C" B200_API int32_t b200_last_stats(b200_ctx *c, b200_stats *out) {
+    if (!c || !out) return B200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    int32_t r = sync_and_status(c);
+    *out = c->stats;
+    return r;
+}
+// number of kernel launches issued through this context (bench.py reports it as gpu_launches)
+extern "C" B200_API uint64_t b200_launch_count(const b200_ctx *c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ keccak
+extern "C" B200_API int32_t b200_keccak256_fixed_dev(b200_ctx *c, const void *d_in, uint32_t msg_len, uint32_t stride,
+                                            uint64_t n, void *d_out32) {
+    if (!c || (n && (!d_in || !d_out32)) || stride < msg_len) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(launch_keccak256_fixed(d_in, msg_len, stride, n, d_out32, c->stream, &c->launches));
+    return B200_OK;
+}
+
+extern "C" B200_API int32_t b200_keccak256_var_dev(b200_ctx *c, const void *d_data, const void *d_offsets, uint64_t n,
+                                          void *d_out32) {
+    if (!c || (n && (!d_offsets || !d_out32))) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(launch_keccak256_var(d_data, d_offsets, n, d_out32, c->stream, &c->launches));
+    return B200_OK;
+}
+
+// Host buffers: chunked and double-buffered so that H2D, hashing and D2H of consecutive chunks overlap
+// (fully asynchronous when the caller's buffers are page-locked, see b200_host_alloc).
+extern "C" B200_API int32_t b200_keccak256_fixed(b200_ctx *c, const uint8_t *in, uint32_t msg_len, uint32_t stride, uint64_t n,
+                                        uint8_t *out32) {
+    if (!c || (n && (!in || !out32)) || stride < msg_len) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    if (n == 0) return B200_OK;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    const uint64_t CHUNK = 1ull << 20;  // messages per chunk
+    uint64_t chunk = n < CHUNK ? n : CHUNK;
+    for (int i = 0; i < 2; i++) {
+        TRY(ensure(c, c->chunk_in[i], chunk * stride));
+        TRY(ensure(c, c->chunk_out[i], chunk * 32));
+    }
+    int slot = 0;
+    for (uint64_t lo = 0; lo < n; lo += chunk, slot ^= 1) {
+        uint64_t m = n - lo < chunk ? n - lo : chunk;
+        cudaStream_t st = c->copy_streams[slot];
+        size_t in_bytes = (m - 1) * (size_t)stride + msg_len;
+        CU(cudaMemcpyAsync(c->chunk_in[slot].p, in + lo * stride, in_bytes, cudaMemcpyHostToDevice, st));
+        CU(launch_keccak256_fixed(c->chunk_in[slot].p, msg_len, stride, m, c->chunk_out[slot].p, st, &c->launches));
+        CU(cudaMemcpyAsync(out32 + lo * 32, c->chunk_out[slot].p, m * 32, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(c->copy_streams[0]));
+    CU(cudaStreamSynchronize(c->copy_streams[1]));
+    return B200_OK;
+}
+
+extern "C" B200_API int32_t b200_keccak256_var(b200_ctx *c, const uint8_t *data, const uint64_t *offsets, uint64_t n,
+                                      uint8_t *out32) {
+    if (!c || (n && (!offsets || !out32))) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    if (n == 0) return B200_OK;
+    for (uint64_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(c, B200_ERR_INVALID_ARG, "offsets must be monotone");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    uint64_t base = offsets[0], total = offsets[n] - base;
+    if (total && !data) return fail(c, B200_ERR_INVALID_ARG, "data is null");
+    ENSURE(in_a, total ? total : 1);
+    ENSURE(in_b, (n + 1) * 8);
+    ENSURE(out_a, n * 32);
+    std::vector<uint64_t> rel;
+    const uint64_t *offs = offsets;
+    if (base) {
+        rel.resize(n + 1);
+        for (uint64_t i = 0; i <= n; i++) rel[i] = offsets[i] - base;
+        offs = rel.data();
+    }
+    if (total) CU(cudaMemcpyAsync(c->in_a.p, data + base, total, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->in_b.p, offs, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // `rel` must outlive the copy
+    CU(launch_keccak256_var(c->in_a.p, c->in_b.p, n, c->out_a.p, c->stream, &c->launches));
+    CU(cudaMemcpyAsync(out32, c->out_a.p, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ hash + sort
+int32_t sort_digests_on_device(b200_ctx *c, const void *d_digests, uint64_t n, void *d_sorted, uint32_t *d_perm,
+                               DevBuf &keys_a, DevBuf &keys_b, DevBuf &idx_a, DevBuf &flag);
+
+// Device-resident: d_in -> d_sorted32 (n x 32), d_perm (n x u32).  Synchronises once (tie check).
+extern "C" B200_API int32_t b200_hash_sort_keys_dev(b200_ctx *c, const void *d_in, uint32_t msg_len, uint32_t stride,
+                                           uint64_t n, void *d_sorted32, void *d_perm) {
+    if (!c || (n && (!d_in || !d_sorted32 || !d_perm)) || stride < msg_len)
+        return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ENSURE(out_a, (n ? n : 1) * 32);
+    CU(launch_keccak256_fixed(d_in, msg_len, stride, n, c->out_a.p, c->stream, &c->launches));
+    return sort_digests_on_device(c, c->out_a.p, n, d_sorted32, static_cast<uint32_t *>(d_perm), c->sort_ka,
+                                  c->sort_kb, c->sort_ia, c->sort_flag);
+}
+
+// Sorts 32-byte keys that are already digests (no hashing): the ETL-replacement half on its own.
+extern "C" B200_API int32_t b200_sort_keys32_dev(b200_ctx *c, const void *d_keys32, uint64_t n, void *d_sorted32,
+                                        void *d_perm) {
+    if (!c || (n && (!d_keys32 || !d_sorted32 || !d_perm))) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    return sort_digests_on_device(c, d_keys32, n, d_sorted32, static_cast<uint32_t *>(d_perm), c->sort_ka,
+                                  c->sort_kb, c->sort_ia, c->sort_flag);
+}
+
+extern "C" B200_API int32_t b200_hash_sort_keys(b200_ctx *c, const uint8_t *in, uint32_t msg_len, uint32_t stride, uint64_t n,
+                                       uint8_t *out_sorted32, uint32_t *out_perm) {
+    if (!c || (n && (!in || !out_sorted32 || !out_perm)) || stride < msg_len)
+        return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    if (n == 0) return B200_OK;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    size_t in_bytes = (n - 1) * (size_t)stride + msg_len;
+    ENSURE(in_a, in_bytes);
+    ENSURE(out_a, n * 32);
+    ENSURE(sort_out, n * 32);
+    ENSURE(sort_perm, n * 4);
+    CU(cudaMemcpyAsync(c->in_a.p, in, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(launch_keccak256_fixed(c->in_a.p, msg_len, stride, n, c->out_a.p, c->stream, &c->launches));
+    TRY(sort_digests_on_device(c, c->out_a.p, n, c->sort_out.p, static_cast<uint32_t *>(c->sort_perm.p), c->sort_ka,
+                               c->sort_kb, c->sort_ia, c->sort_flag));
+    CU(cudaMemcpyAsync(out_sorted32, c->sort_out.p, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(out_perm, c->sort_perm.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ forest build
+struct IsBoundary {
+    __host__ __device__ uint32_t operator()(uint8_t v) const { return v == 0xFF ? 1u : 0u; }
+};
+
+struct Built {
+    ForestDev f{};
+    uint32_t n_nodes = 0;
+    uint32_t levels = 0;
+};
+
+// Builds every trie of a forest over d_keys (n leaves).  d_seg_offsets == nullptr: one trie.
+// account: leaves are accounts (d_values = b200_account[n], d_sroots = storage roots or null); else storage
+// slots (d_values = U256 BE [n][32]).
+static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, const uint64_t *d_seg_offsets,
+                            uint64_t n_segs, bool account, const uint8_t *d_values, const uint8_t *d_sroots,
+                            bool retain_updates, Built &out) {
+    if (n >= (1ull << 31)) return fail(c, B200_ERR_INVALID_ARG, "at most 2^31-1 leaves per build");
+    cudaStream_t st = c->stream;
+    ForestDev &f = out.f;
+    f.n = n;
+    f.keys = d_keys;
+    f.err = reinterpret_cast<int *>(small_u32(c) + SM_ERR);
+    f.counters = reinterpret_cast<unsigned long long *>(small_u32(c) + SM_COUNTERS);
+    f.retain_updates = retain_updates ? 1 : 0;
+    out.n_nodes = 0;
+    out.levels = 0;
+    if (n == 0) return B200_OK;
+
+    ENSURE(Lp, n + 1);
+    ENSURE(nibs, n + 1);
+    ENSURE(leaf_ref, n * 32);
+    ENSURE(leaf_meta, n);
+    ENSURE(S, n * 4);
+    ENSURE(E, n * 4);
+    f.Lp = static_cast<uint8_t *>(c->Lp.p);
+    f.nibs = static_cast<uint8_t *>(c->nibs.p);
+    f.leaf_ref = static_cast<uint8_t *>(c->leaf_ref.p);
+    f.leaf_meta = static_cast<uint8_t *>(c->leaf_meta.p);
+    f.S = static_cast<uint32_t *>(c->S.p);
+    f.E = static_cast<uint32_t *>(c->E.p);
+
+    CU(cudaMemsetAsync(f.Lp, 0, n + 1, st));
+    if (d_seg_offsets) {
+        CU(launch_mark_boundaries(d_seg_offsets, n_segs, n, f.Lp, f.err, st));
+        c->launches++;
+    }
+    CU(launch_lcp(d_keys, n, f.Lp, f.nibs, f.err, st));
+    CU(launch_leaves(f, account, d_values, d_sroots, st));
+    c->launches += 2;
+    if (n < 2) return B200_OK;
+
+    // ---- gaps sorted by depth (stable: position order inside a depth) -> branch nodes in CSR form
+    const uint64_t G = n - 1;
+    ENSURE(iota, G * 4);
+    ENSURE(depth_sorted, G);
+    ENSURE(gap_sorted, G * 4);
+    ENSURE(head, G);
+    ENSURE(node_start, (G + 1) * 4);
+    uint32_t *bucket_off = small_u32(c) + SM_BUCKET_OFF;
+    uint32_t *level_lo = small_u32(c) + SM_LEVEL_LO;
+    uint32_t *n_nodes_p = small_u32(c) + SM_NNODES;
+    uint8_t *depth_sorted = static_cast<uint8_t *>(c->depth_sorted.p);
+    uint32_t *gap_sorted = static_cast<uint32_t *>(c->gap_sorted.p);
+    uint8_t *head = static_cast<uint8_t *>(c->head.p);
+    uint32_t *node_start = static_cast<uint32_t *>(c->node_start.p);
+
+    CU(launch_iota(static_cast<uint32_t *>(c->iota.p), G, 1, st));
+    c->launches++;
+    size_t t_sort = 0, t_sel = 0, t_scan = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, f.Lp + 1, depth_sorted, static_cast<uint32_t *>(c->iota.p),
+                                       gap_sorted, (int64_t)G, 0, 8, st));
+    thrust::counting_iterator<uint32_t> counting(0);
+    CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, head, node_start, n_nodes_p, (int64_t)G, st));
+    auto bflags = thrust::make_transform_iterator(static_cast<const uint8_t *>(f.Lp), IsBoundary());
+    uint32_t *bound_rank = nullptr;
+    if (d_seg_offsets) {
+        ENSURE(bound_rank, (n + 1) * 4);
+        bound_rank = static_cast<uint32_t *>(c->bound_rank.p);
+        CU(cub::DeviceScan::InclusiveSum(nullptr, t_scan, bflags, bound_rank, (int64_t)(n + 1), st));
+    }
+    size_t t_max = std::max(t_sort, std::max(t_sel, t_scan));
+    ENSURE(cub_temp, t_max);
+    CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_sort, f.Lp + 1, depth_sorted,
+                                       static_cast<uint32_t *>(c->iota.p), gap_sorted, (int64_t)G, 0, 8, st));
+    CU(launch_bucket_offsets(depth_sorted, G, bucket_off, st));
+    if (d_seg_offsets)
+        CU(cub::DeviceScan::InclusiveSum(c->cub_temp.p, t_scan, bflags, bound_rank, (int64_t)(n + 1), st));
+    CU(cudaMemsetAsync(head, 0, G, st));
+    CU(launch_head_flags(d_keys, depth_sorted, gap_sorted, bound_rank, bucket_off + 64, G, head, st));
+    CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, head, node_start, n_nodes_p, (int64_t)G, st));
+    CU(launch_level_ranges(node_start, n_nodes_p, bucket_off, level_lo, st));
+    c->launches += 8;
+    uint32_t *h_level = static_cast<uint32_t *>(c->pinned_small) + 64;
+    CU(cudaMemcpyAsync(h_level, level_lo, 66 * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));  // the only host round trip of a build: 66 integers
+    const uint32_t B = h_level[65];
+    out.n_nodes = B;
+    f.gap_sorted = gap_sorted;
+    f.node_start = node_start;
+    if (B == 0) return B200_OK;  // every trie has at most one leaf
+
+    ENSURE(node_ref, (size_t)B * 32);
+    ENSURE(node_meta, B);
+    ENSURE(node_l, (size_t)B * 4);
+    ENSURE(node_r, (size_t)B * 4);
+    ENSURE(node_masks, (size_t)B * 8);
+    f.node_ref = static_cast<uint8_t *>(c->node_ref.p);
+    f.node_meta = static_cast<uint8_t *>(c->node_meta.p);
+    f.node_l = static_cast<uint32_t *>(c->node_l.p);
+    f.node_r = static_cast<uint32_t *>(c->node_r.p);
+    f.node_masks = static_cast<ushort4 *>(c->node_masks.p);
+
+    // ---- deepest level first: one launch per populated level, the per-level frontier stays in HBM
+    for (int d = 63; d >= 0; d--) {
+        uint32_t lo = h_level[d], hi = h_level[d + 1];
+        if (hi > lo) {
+            CU(launch_branch_level(f, lo, hi, d, st));
+            c->launches++;
+            out.levels++;
+        }
+    }
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ updates
+struct UpdatesOwner {
+    void *host = nullptr;  // one page-locked block holding every array
+};
+
+extern "C" B200_API void b200_updates_release(b200_updates *u) {
+    if (!u) return;
+    if (u->_owner) {
+        UpdatesOwner *o = static_cast<UpdatesOwner *>(u->_owner);
+        if (o->host) cudaFreeHost(o->host);
+        delete o;
+    }
+    memset(u, 0, sizeof *u);
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Collects the stored BranchNodeCompact records of a finished build into `u` (host, page-locked).
+static int32_t collect_updates(b200_ctx *c, const Built &b, const uint64_t *d_seg_offsets, uint64_t n_segs,
+                               b200_updates *u) {
+    memset(u, 0, sizeof *u);
+    UpdatesOwner *owner = new UpdatesOwner();
+    u->_owner = owner;
+    cudaStream_t st = c->stream;
+    const uint32_t B = b.n_nodes;
+    uint32_t n_stored = 0, n_hashes = 0;
+    uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
+    if (B) {
+        ENSURE(upd_flags, B);
+        ENSURE(upd_nh, (size_t)B * 4);
+        ENSURE(upd_ids, (size_t)B * 4);
+        ENSURE(upd_prefix, (size_t)(B + 1) * 4);
+        uint8_t *flags = static_cast<uint8_t *>(c->upd_flags.p);
+        uint32_t *nh = static_cast<uint32_t *>(c->upd_nh.p);
+        uint32_t *ids = static_cast<uint32_t *>(c->upd_ids.p);
+        uint32_t *prefix = static_cast<uint32_t *>(c->upd_prefix.p);
+        uint32_t *n_stored_p = small_u32(c) + SM_NSTORED;
+        CU(launch_stored_flags(b.f, B, flags, nh, st));
+        size_t t_sel = 0, t_scan = 0;
+        thrust::counting_iterator<uint32_t> counting(0);
+        CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, flags, ids, n_stored_p, (int64_t)B, st));
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, t_scan, nh, prefix, (int64_t)B, st));
+        ENSURE(cub_temp, std::max(t_sel, t_scan));
+        CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, flags, ids, n_stored_p, (int64_t)B, st));
+        CU(cub::DeviceScan::ExclusiveSum(c->cub_temp.p, t_scan, nh, prefix, (int64_t)B, st));
+        c->launches += 3;
+        CU(cudaMemcpyAsync(ps + 200, n_stored_p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ps + 201, prefix + (B - 1), 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ps + 202, nh + (B - 1), 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        n_stored = ps[200];
+        n_hashes = ps[201] + ps[202];
+    }
+    // one device block + one pinned host block, same layout
+    size_t o_tid = 0;
+    size_t o_plen = align_up(o_tid + (size_t)n_stored * 4, 16);
+    size_t o_path = align_up(o_plen + n_stored, 16);
+    size_t o_sm = align_up(o_path + (size_t)n_stored * 32, 16);
+    size_t o_tm = align_up(o_sm + (size_t)n_stored * 2, 16);
+    size_t o_hm = align_up(o_tm + (size_t)n_stored * 2, 16);
+    size_t o_ho32 = align_up(o_hm + (size_t)n_stored * 2, 16);
+    size_t o_hash = align_up(o_ho32 + (size_t)n_stored * 4, 16);
+    size_t o_ho64 = align_up(o_hash + (size_t)n_hashes * 32, 16);
+    size_t dev_total = o_ho64;
+    size_t host_total = o_ho64 + ((size_t)n_stored + 1) * 8;
+    CU(cudaMallocHost(&owner->host, host_total ? host_total : 16));
+    uint8_t *h = static_cast<uint8_t *>(owner->host);
+    u->n_nodes = n_stored;
+    u->trie_id = reinterpret_cast<uint32_t *>(h + o_tid);
+    u->path_len = h + o_plen;
+    u->path_packed = h + o_path;
+    u->state_mask = reinterpret_cast<uint16_t *>(h + o_sm);
+    u->tree_mask = reinterpret_cast<uint16_t *>(h + o_tm);
+    u->hash_mask = reinterpret_cast<uint16_t *>(h + o_hm);
+    u->hashes = h + o_hash;
+    u->hash_offset = reinterpret_cast<uint64_t *>(h + o_ho64);
+    if (n_stored) {
+        ENSURE(out_a, dev_total);
+        uint8_t *d = static_cast<uint8_t *>(c->out_a.p);
+        UpdatesDev ud;
+        ud.trie_id = reinterpret_cast<uint32_t *>(d + o_tid);
+        ud.path_len = d + o_plen;
+        ud.path_packed = d + o_path;
+        ud.state_mask = reinterpret_cast<uint16_t *>(d + o_sm);
+        ud.tree_mask = reinterpret_cast<uint16_t *>(d + o_tm);
+        ud.hash_mask = reinterpret_cast<uint16_t *>(d + o_hm);
+        ud.hash_offset = reinterpret_cast<uint32_t *>(d + o_ho32);
+        ud.hashes = d + o_hash;
+        CU(launch_gather_updates(b.f, static_cast<uint32_t *>(c->upd_ids.p), n_stored,
+                                 static_cast<uint32_t *>(c->upd_prefix.p), d_seg_offsets, n_segs, ud, st));
+        c->launches++;
+        CU(cudaMemcpyAsync(h, d, dev_total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const uint32_t *ho32 = reinterpret_cast<const uint32_t *>(h + o_ho32);
+        for (uint32_t i = 0; i < n_stored; i++) u->hash_offset[i] = ho32[i];
+    }
+    u->hash_offset[n_stored] = n_hashes;
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ device-level drivers
+static int32_t storage_roots_on_device(b200_ctx *c, const uint8_t *d_keys, const uint8_t *d_vals,
+                                       const uint64_t *d_offs, uint64_t n_accounts, uint64_t n_slots,
+                                       uint8_t *d_roots, bool retain, Built &b) {
+    TRY(build_forest(c, d_keys, n_slots, d_offs, n_accounts, false, d_vals, nullptr, retain, b));
+    CU(launch_segment_roots(b.f, d_offs, n_accounts, d_roots, c->stream));
+    c->launches++;
+    c->stats.leaves_added += n_slots;
+    c->stats.branches_added += b.n_nodes;
+    c->stats.levels += b.levels;
+    return B200_OK;
+}
+
+static int32_t account_root_on_device(b200_ctx *c, const uint8_t *d_keys, const uint8_t *d_accts,
+                                      const uint8_t *d_sroots, uint64_t n, uint8_t *d_root, bool retain, Built &b) {
+    TRY(build_forest(c, d_keys, n, nullptr, 0, true, d_accts, d_sroots, retain, b));
+    CU(launch_segment_roots(b.f, nullptr, 1, d_root, c->stream));
+    c->launches++;
+    c->stats.leaves_added += n;
+    c->stats.branches_added += b.n_nodes;
+    c->stats.levels += b.levels;
+    return B200_OK;
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" B200_API int32_t b200_storage_roots_dev(b200_ctx *c, const void *d_slot_keys32, const void *d_values32_be,
+                                          const void *d_seg_offsets, uint64_t n_accounts, uint64_t n_slots,
+                                          void *d_roots32) {
+    if (!c || !d_seg_offsets || (n_accounts && !d_roots32) || (n_slots && (!d_slot_keys32 || !d_values32_be)))
+        return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    if (!aligned16(d_slot_keys32) || !aligned16(d_values32_be) || !aligned16(d_roots32))
+        return fail(c, B200_ERR_INVALID_ARG, "device buffers must be 16-byte aligned");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    TRY(reset_build_state(c));
+    Built b;
+    TRY(storage_roots_on_device(c, static_cast<const uint8_t *>(d_slot_keys32),
+                                static_cast<const uint8_t *>(d_values32_be),
+                                static_cast<const uint64_t *>(d_seg_offsets), n_accounts, n_slots,
+                                static_cast<uint8_t *>(d_roots32), false, b));
+    return finish_build_state(c);
+}
+
+extern "C" B200_API int32_t b200_state_root_dev(b200_ctx *c, const void *d_acct_keys32, const void *d_accts,
+                                       const void *d_storage_roots32, uint64_t n, void *d_root32) {
+    if (!c || !d_root32 || (n && (!d_acct_keys32 || !d_accts))) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    if (!aligned16(d_acct_keys32) || !aligned16(d_root32) || !aligned16(d_storage_roots32) ||
+        (reinterpret_cast<uintptr_t>(d_accts) & 7))
+        return fail(c, B200_ERR_INVALID_ARG, "device buffers must be 16-byte aligned (accounts: 8)");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    TRY(reset_build_state(c));
+    Built b;
+    TRY(account_root_on_device(c, static_cast<const uint8_t *>(d_acct_keys32), static_cast<const uint8_t *>(d_accts),
+                               static_cast<const uint8_t *>(d_storage_roots32), n, static_cast<uint8_t *>(d_root32),
+                               false, b));
+    return finish_build_state(c);
+}
+
+extern "C" B200_API int32_t b200_state_root_full_dev(b200_ctx *c, const void *d_acct_keys32, const void *d_accts,
+                                            uint64_t n_accounts, const void *d_slot_keys32, const void *d_values32_be,
+                                            const void *d_seg_offsets, uint64_t n_slots, void *d_root32) {
+    if (!c || !d_root32 || !d_seg_offsets || (n_accounts && (!d_acct_keys32 || !d_accts)) ||
+        (n_slots && (!d_slot_keys32 || !d_values32_be)))
+        return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    TRY(reset_build_state(c));
+    ENSURE(sroots, (n_accounts ? n_accounts : 1) * 32);
+    Built bs, ba;
+    TRY(storage_roots_on_device(c, static_cast<const uint8_t *>(d_slot_keys32),
+                                static_cast<const uint8_t *>(d_values32_be),
+                                static_cast<const uint64_t *>(d_seg_offsets), n_accounts, n_slots,
+                                static_cast<uint8_t *>(c->sroots.p), false, bs));
+    TRY(account_root_on_device(c, static_cast<const uint8_t *>(d_acct_keys32), static_cast<const uint8_t *>(d_accts),
+                               static_cast<const uint8_t *>(c->sroots.p), n_accounts,
+                               static_cast<uint8_t *>(d_root32), false, ba));
+    return finish_build_state(c);
+}
+
+// ------------------------------------------------------------------------------------------------ host-pointer drivers
+static int32_t h2d(b200_ctx *c, DevBuf &b, const void *src, size_t bytes) {
+    TRY(ensure(c, b, bytes ? bytes : 16));
+    if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return B200_OK;
+}
+
+static int32_t check_offsets_host(b200_ctx *c, const uint64_t *offs, uint64_t n_segs) {
+    if (offs[0] != 0) return fail(c, B200_ERR_INVALID_ARG, "seg_offsets[0] must be 0");
+    for (uint64_t i = 0; i < n_segs; i++)
+        if (offs[i + 1] < offs[i]) return fail(c, B200_ERR_INVALID_ARG, "seg_offsets must be monotone");
+    return B200_OK;
+}
+
+extern "C" B200_API int32_t b200_storage_roots(b200_ctx *c, const uint8_t *slot_keys32, const uint8_t *values32_be,
+                                      const uint64_t *seg_offsets, uint64_t n_accounts, uint8_t *roots32,
+                                      b200_updates *opt_updates, b200_stats *opt_stats) {
+    if (!c || !seg_offsets || (n_accounts && !roots32)) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    TRY(check_offsets_host(c, seg_offsets, n_accounts));
+    uint64_t n_slots = seg_offsets[n_accounts];
+    if (n_slots && (!slot_keys32 || !values32_be)) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    if (opt_updates) memset(opt_updates, 0, sizeof *opt_updates);
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    TRY(h2d(c, c->in_a, slot_keys32, n_slots * 32));
+    TRY(h2d(c, c->in_b, values32_be, n_slots * 32));
+    TRY(h2d(c, c->in_c, seg_offsets, (n_accounts + 1) * 8));
+    ENSURE(sroots, (n_accounts ? n_accounts : 1) * 32);
+    TRY(reset_build_state(c));
+    Built b;
+    TRY(storage_roots_on_device(c, static_cast<const uint8_t *>(c->in_a.p), static_cast<const uint8_t *>(c->in_b.p),
+                                static_cast<const uint64_t *>(c->in_c.p), n_accounts, n_slots,
+                                static_cast<uint8_t *>(c->sroots.p), opt_updates != nullptr, b));
+    TRY(finish_build_state(c));
+    if (n_accounts) CU(cudaMemcpyAsync(roots32, c->sroots.p, n_accounts * 32, cudaMemcpyDeviceToHost, c->stream));
+    int32_t r = sync_and_status(c);
+    if (r == B200_OK && opt_updates)
+        r = collect_updates(c, b, static_cast<const uint64_t *>(c->in_c.p), n_accounts, opt_updates);
+    if (r != B200_OK && opt_updates) b200_updates_release(opt_updates);
+    if (opt_stats) *opt_stats = c->stats;
+    return r;
+}
+
+extern "C" B200_API int32_t b200_state_root(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
+                                   const uint8_t *storage_roots32, uint64_t n, uint8_t root32[32],
+                                   b200_updates *opt_updates, b200_stats *opt_stats) {
+    if (!c || !root32 || (n && (!acct_keys32 || !accts))) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    if (opt_updates) memset(opt_updates, 0, sizeof *opt_updates);
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    TRY(h2d(c, c->in_a, acct_keys32, n * 32));
+    TRY(h2d(c, c->in_b, accts, n * sizeof(b200_account)));
+    if (storage_roots32) TRY(h2d(c, c->in_c, storage_roots32, n * 32));
+    ENSURE(in_e, 32);
+    TRY(reset_build_state(c));
+    Built b;
+    TRY(account_root_on_device(c, static_cast<const uint8_t *>(c->in_a.p), static_cast<const uint8_t *>(c->in_b.p),
+                               storage_roots32 ? static_cast<const uint8_t *>(c->in_c.p) : nullptr, n,
+                               static_cast<uint8_t *>(c->in_e.p), opt_updates != nullptr, b));
+    TRY(finish_build_state(c));
+    CU(cudaMemcpyAsync(root32, c->in_e.p, 32, cudaMemcpyDeviceToHost, c->stream));
+    int32_t r = sync_and_status(c);
+    if (r == B200_OK && opt_updates) r = collect_updates(c, b, nullptr, 0, opt_updates);
+    if (r != B200_OK && opt_updates) b200_updates_release(opt_updates);
+    if (opt_stats) *opt_stats = c->stats;
+    return r;
+}
+
+extern "C" B200_API int32_t b200_state_root_full(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
+                                        uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
+                                        const uint64_t *seg_offsets, uint8_t root32[32],
+                                        b200_updates *opt_account_updates, b200_updates *opt_storage_updates,
+                                        b200_stats *opt_stats) {
+    if (!c || !root32 || !seg_offsets || (n_accounts && (!acct_keys32 || !accts)))
+        return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    TRY(check_offsets_host(c, seg_offsets, n_accounts));
+    uint64_t n_slots = seg_offsets[n_accounts];
+    if (n_slots && (!slot_keys32 || !values32_be)) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    if (opt_account_updates) memset(opt_account_updates, 0, sizeof *opt_account_updates);
+    if (opt_storage_updates) memset(opt_storage_updates, 0, sizeof *opt_storage_updates);
+    const bool retain = opt_account_updates || opt_storage_updates;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    TRY(h2d(c, c->in_a, slot_keys32, n_slots * 32));
+    TRY(h2d(c, c->in_b, values32_be, n_slots * 32));
+    TRY(h2d(c, c->in_c, seg_offsets, (n_accounts + 1) * 8));
+    TRY(h2d(c, c->in_d, acct_keys32, n_accounts * 32));
+    TRY(h2d(c, c->in_e, accts, n_accounts * sizeof(b200_account)));
+    ENSURE(sroots, (n_accounts ? n_accounts : 1) * 32 + 32);
+    uint8_t *d_root = static_cast<uint8_t *>(c->sroots.p) + (n_accounts ? n_accounts : 1) * 32;
+    TRY(reset_build_state(c));
+    Built bs, ba;
+    int32_t r = storage_roots_on_device(c, static_cast<const uint8_t *>(c->in_a.p),
+                                        static_cast<const uint8_t *>(c->in_b.p),
+                                        static_cast<const uint64_t *>(c->in_c.p), n_accounts, n_slots,
+                                        static_cast<uint8_t *>(c->sroots.p), retain, bs);
+    // the storage forest's scratch is reused by the account build: gather its updates first
+    if (r == B200_OK && opt_storage_updates) {
+        r = sync_and_status(c);
+        if (r == B200_OK)
+            r = collect_updates(c, bs, static_cast<const uint64_t *>(c->in_c.p), n_accounts, opt_storage_updates);
+    }
+    if (r == B200_OK)
+        r = account_root_on_device(c, static_cast<const uint8_t *>(c->in_d.p), static_cast<const uint8_t *>(c->in_e.p),
+                                   static_cast<const uint8_t *>(c->sroots.p), n_accounts, d_root, retain, ba);
+    if (r == B200_OK) r = finish_build_state(c);
+    if (r == B200_OK) {
+        cudaError_t e = cudaMemcpyAsync(root32, d_root, 32, cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) r = fail(c, B200_ERR_CUDA, "root copy: %s", cudaGetErrorString(e));
+    }
+    if (r == B200_OK) r = sync_and_status(c);
+    if (r == B200_OK && opt_account_updates) r = collect_updates(c, ba, nullptr, 0, opt_account_updates);
+    if (r != B200_OK) {
+        if (opt_account_updates) b200_updates_release(opt_account_updates);
+        if (opt_storage_updates) b200_updates_release(opt_storage_updates);
+    }
+    if (opt_stats) *opt_stats = c->stats;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU frontier
+static int32_t frontier_on_device(b200_ctx *c, const uint8_t *d_akeys, const uint8_t *d_accts, uint64_t n_accounts,
+                                  const uint8_t *d_skeys, const uint8_t *d_svals, const uint64_t *d_offs,
+                                  uint64_t n_slots, FrontierEntryDev *d_out) {
+    ENSURE(sroots, (n_accounts ? n_accounts : 1) * 32);
+    ENSURE(buckets, 17 * 8);
+    Built bs, ba;
+    TRY(storage_roots_on_device(c, d_skeys, d_svals, d_offs, n_accounts, n_slots, static_cast<uint8_t *>(c->sroots.p),
+                                false, bs));
+    uint64_t *d_buckets = static_cast<uint64_t *>(c->buckets.p);
+    CU(launch_nibble_buckets(d_akeys, n_accounts, d_buckets, c->stream));
+    // every top-nibble bucket is built as a trie of its own (16 segments)
+    TRY(build_forest(c, d_akeys, n_accounts, d_buckets, 16, true, d_accts, static_cast<const uint8_t *>(c->sroots.p),
+                     false, ba));
+    CU(launch_frontier(ba.f, d_buckets, d_accts, static_cast<const uint8_t *>(c->sroots.p), d_out, c->stream));
+    c->launches += 2;
+    c->stats.leaves_added += n_accounts;
+    c->stats.branches_added += ba.n_nodes;
+    c->stats.levels += ba.levels;
+    return B200_OK;
+}
+
+extern "C" B200_API int32_t b200_subtrie_frontier_dev(b200_ctx *c, const void *d_acct_keys32, const void *d_accts,
+                                             uint64_t n_accounts, const void *d_slot_keys32,
+                                             const void *d_values32_be, const void *d_seg_offsets, uint64_t n_slots,
+                                             void *d_frontier) {
+    if (!c || !d_frontier || !d_seg_offsets || (n_accounts && (!d_acct_keys32 || !d_accts)))
+        return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    TRY(reset_build_state(c));
+    TRY(frontier_on_device(c, static_cast<const uint8_t *>(d_acct_keys32), static_cast<const uint8_t *>(d_accts),
+                           n_accounts, static_cast<const uint8_t *>(d_slot_keys32),
+                           static_cast<const uint8_t *>(d_values32_be), static_cast<const uint64_t *>(d_seg_offsets),
+                           n_slots, static_cast<FrontierEntryDev *>(d_frontier)));
+    return finish_build_state(c);
+}
+
+extern "C" B200_API int32_t b200_subtrie_frontier(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
+                                         uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
+                                         const uint64_t *seg_offsets, b200_frontier_entry frontier[16],
+                                         b200_stats *opt_stats) {
+    if (!c || !frontier || !seg_offsets || (n_accounts && (!acct_keys32 || !accts)))
+        return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    TRY(check_offsets_host(c, seg_offsets, n_accounts));
+    uint64_t n_slots = seg_offsets[n_accounts];
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    TRY(h2d(c, c->in_a, slot_keys32, n_slots * 32));
+    TRY(h2d(c, c->in_b, values32_be, n_slots * 32));
+    TRY(h2d(c, c->in_c, seg_offsets, (n_accounts + 1) * 8));
+    TRY(h2d(c, c->in_d, acct_keys32, n_accounts * 32));
+    TRY(h2d(c, c->in_e, accts, n_accounts * sizeof(b200_account)));
+    ENSURE(out_a, 16 * sizeof(FrontierEntryDev));
+    TRY(reset_build_state(c));
+    TRY(frontier_on_device(c, static_cast<const uint8_t *>(c->in_d.p), static_cast<const uint8_t *>(c->in_e.p),
+                           n_accounts, static_cast<const uint8_t *>(c->in_a.p),
+                           static_cast<const uint8_t *>(c->in_b.p), static_cast<const uint64_t *>(c->in_c.p), n_slots,
+                           static_cast<FrontierEntryDev *>(c->out_a.p)));
+    TRY(finish_build_state(c));
+    CU(cudaMemcpyAsync(frontier, c->out_a.p, 16 * sizeof(FrontierEntryDev), cudaMemcpyDeviceToHost, c->stream));
+    int32_t r = sync_and_status(c);
+    if (opt_stats) *opt_stats = c->stats;
+    return r;
+}
+
+extern "C" B200_API int32_t b200_root_from_frontier(b200_ctx *c, const b200_frontier_entry frontier[16], uint8_t root32[32]) {
+    if (!c || !frontier || !root32) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    for (int i = 0; i < 16; i++)
+        if (frontier[i].as_child_len > 33 || (frontier[i].as_root_len != 0 && frontier[i].as_root_len != 32))
+            return fail(c, B200_ERR_INVALID_ARG, "malformed frontier entry %d", i);
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ENSURE(out_a, 16 * sizeof(FrontierEntryDev) + 64);
+    uint8_t *d = static_cast<uint8_t *>(c->out_a.p);
+    uint8_t *d_root = d + align_up(16 * sizeof(FrontierEntryDev), 16);
+    CU(cudaMemcpyAsync(d, frontier, 16 * sizeof(FrontierEntryDev), cudaMemcpyHostToDevice, c->stream));
+    CU(launch_root_from_frontier(reinterpret_cast<const FrontierEntryDev *>(d), d_root, c->stream));
+    c->launches++;
+    CU(cudaMemcpyAsync(root32, d_root, 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B200_OK;
+}
+
+// device-resident variant used by the multi-GPU host after the NCCL all-gather
+extern "C" B200_API int32_t b200_root_from_frontier_dev(b200_ctx *c, const void *d_frontier, void *d_root32) {
+    if (!c || !d_frontier || !d_root32) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(launch_root_from_frontier(static_cast<const FrontierEntryDev *>(d_frontier), static_cast<uint8_t *>(d_root32),
+                                 c->stream));
+    c->launches++;
+    return B200_OK;
+}

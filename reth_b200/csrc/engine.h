@@ -1,0 +1,83 @@
+// engine.h — context and scratch-arena definitions shared by the translation units of libb200trie.so.
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "../../include/b200trie.h"
+
+// ------------------------------------------------------------------------------------------------ context
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct b200_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_streams[2] = {nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+    std::string err;
+    uint64_t dev_bytes = 0;
+    unsigned launches = 0;
+    b200_stats stats{};
+    bool stats_pending = false;
+    // scratch (grow-only)
+    DevBuf Lp, nibs, leaf_ref, leaf_meta, S, E, iota, depth_sorted, gap_sorted, bound_rank, head, node_start,
+        node_ref, node_meta, node_l, node_r, node_masks, cub_temp, small, sroots, buckets;
+    DevBuf upd_flags, upd_nh, upd_ids, upd_prefix;
+    DevBuf sort_ka, sort_kb, sort_ia, sort_flag, sort_perm, sort_out;
+    // staging for host-pointer entry points
+    DevBuf in_a, in_b, in_c, in_d, in_e, out_a, chunk_in[2], chunk_out[2];
+    void *pinned_small = nullptr;  // 4 KiB page-locked readback area
+};
+
+inline int32_t fail(b200_ctx *c, int32_t code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(c, e__ == cudaErrorMemoryAllocation ? B200_ERR_OOM : B200_ERR_CUDA, "%s: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e__), __FILE__, __LINE__);                                  \
+    } while (0)
+
+inline int32_t ensure(b200_ctx *c, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return B200_OK;
+    if (b.p) {
+        CU(cudaStreamSynchronize(c->stream));  // buffer may still be in use by queued work
+        CU(cudaFree(b.p));
+        c->dev_bytes -= b.cap;
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;  // slack so that slowly growing inputs do not re-allocate every call
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    c->dev_bytes += want;
+    return B200_OK;
+}
+#define ENSURE(buf, bytes)                                   \
+    do {                                                     \
+        int32_t r__ = ensure(c, c->buf, (size_t)(bytes));    \
+        if (r__ != B200_OK) return r__;                      \
+    } while (0)
+#define TRY(expr)                         \
+    do {                                  \
+        int32_t r__ = (expr);             \
+        if (r__ != B200_OK) return r__;   \
+    } while (0)
+

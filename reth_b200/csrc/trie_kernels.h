@@ -1,0 +1,98 @@
+// trie_kernels.h — device-side data layout of one forest build and the kernel launch interface
+// (internal to libb200trie.so).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+// sticky device error codes (mapped to b200_status by the engine)
+enum : int {
+    B200_DEVERR_NONE = 0,
+    B200_DEVERR_UNSORTED = 1,
+    B200_DEVERR_ZERO_VALUE = 2,
+    B200_DEVERR_INLINE_HASH_CHILD = 3,
+    B200_DEVERR_BAD_OFFSETS = 4,
+};
+
+// node / leaf meta byte
+enum : uint32_t { META_LEN = 31u, META_EXT = 32u, META_STORED = 64u };
+
+enum : int { CNT_HASHED = 0, CNT_EXT = 1, CNT_COUNT = 4 };
+
+struct b200_account_dev {  // == b200_account (include/b200trie.h), 72 bytes
+    uint64_t nonce;
+    uint8_t balance_be[32];
+    uint8_t code_hash[32];
+};
+static_assert(sizeof(b200_account_dev) == 72, "account layout");
+
+struct FrontierEntryDev {  // == b200_frontier_entry
+    uint8_t as_child_len;
+    uint8_t as_child[33];
+    uint8_t as_root_len;
+    uint8_t as_root[33];
+};
+static_assert(sizeof(FrontierEntryDev) == 68, "frontier layout");
+
+// All arrays live in HBM for the duration of one build (and stay resident afterwards: the node-hash
+// frontier of every level is exactly node_ref/leaf_ref).
+//
+//   per leaf  (n)    : keys 32 B (input) | Lp 1 | nibs 1 | leaf_ref 32 | leaf_meta 1 | S 4 | E 4
+//   per gap   (n-1)  : depth_sorted 1 | gap_sorted 4            (gaps ordered by (depth, position))
+//   per branch (B)   : node_start 4 (CSR into gap_sorted) | node_ref 32 | node_meta 1 | node_l 4 | node_r 4 |
+//                      node_masks 8 (state, tree, hash, depth)
+struct ForestDev {
+    uint64_t n;             // leaves
+    const uint8_t *keys;    // [n][32] sorted inside each trie
+    uint8_t *Lp;            // [n+1] gap depth; Lp[0] = Lp[n] = 0xFF; 0xFF = trie boundary
+    uint8_t *nibs;          // [n+1] (left nibble << 4) | right nibble at depth Lp
+    uint8_t *leaf_ref;      // [n][32] digest, or inline RLP (< 32 bytes)
+    uint8_t *leaf_meta;     // [n] 0 = hashed, else inline length
+    uint32_t *S, *E;        // [n] frontier item starting / ending at this leaf (< n leaf, else n + node id)
+    const uint32_t *gap_sorted;   // [n-1]
+    const uint32_t *node_start;   // [B+1]
+    uint8_t *node_ref;      // [B][32]
+    uint8_t *node_meta;     // [B] inline length | META_EXT | META_STORED
+    uint32_t *node_l, *node_r;    // [B] leaf extent
+    ushort4 *node_masks;    // [B]
+    int *err;               // sticky error code
+    unsigned long long *counters;  // [CNT_COUNT]
+    int retain_updates;
+};
+
+struct UpdatesDev {
+    uint32_t *trie_id;
+    uint8_t *path_len;
+    uint8_t *path_packed;
+    uint16_t *state_mask, *tree_mask, *hash_mask;
+    uint32_t *hash_offset;  // [n_stored] (exclusive); the engine appends the total
+    uint8_t *hashes;
+};
+
+cudaError_t launch_mark_boundaries(const uint64_t *d_seg_offsets, uint64_t n_segs, uint64_t n, uint8_t *Lp, int *err,
+                                   cudaStream_t st);
+cudaError_t launch_lcp(const uint8_t *keys, uint64_t n, uint8_t *Lp, uint8_t *nibs, int *err, cudaStream_t st);
+cudaError_t launch_iota(uint32_t *out, uint64_t n, uint32_t first, cudaStream_t st);
+cudaError_t launch_bucket_offsets(const uint8_t *depth_sorted, uint64_t G, uint32_t *bucket_off, cudaStream_t st);
+cudaError_t launch_head_flags(const uint8_t *keys, const uint8_t *depth_sorted, const uint32_t *gap_sorted,
+                              const uint32_t *bound_rank, const uint32_t *G_real_p, uint64_t G, uint8_t *head,
+                              cudaStream_t st);
+cudaError_t launch_level_ranges(uint32_t *node_start, const uint32_t *n_nodes_p, const uint32_t *bucket_off,
+                                uint32_t *level_lo, cudaStream_t st);
+cudaError_t launch_leaves(const ForestDev &f, bool account, const uint8_t *values, const uint8_t *storage_roots,
+                          cudaStream_t st);
+cudaError_t launch_branch_level(const ForestDev &f, uint32_t node_lo, uint32_t node_hi, int d, cudaStream_t st);
+cudaError_t launch_segment_roots(const ForestDev &f, const uint64_t *d_seg_offsets, uint64_t n_segs, uint8_t *roots,
+                                 cudaStream_t st);
+cudaError_t launch_stored_flags(const ForestDev &f, uint32_t n_nodes, uint8_t *flags, uint32_t *n_hashes,
+                                cudaStream_t st);
+cudaError_t launch_gather_updates(const ForestDev &f, const uint32_t *stored_ids, uint32_t n_stored,
+                                  const uint32_t *hash_prefix, const uint64_t *d_seg_offsets, uint64_t n_segs,
+                                  const UpdatesDev &out, cudaStream_t st);
+cudaError_t launch_nibble_buckets(const uint8_t *keys, uint64_t n, uint64_t *offs, cudaStream_t st);
+cudaError_t launch_frontier(const ForestDev &f, const uint64_t *bucket_offsets, const uint8_t *values,
+                            const uint8_t *storage_roots, FrontierEntryDev *out, cudaStream_t st);
+cudaError_t launch_root_from_frontier(const FrontierEntryDev *fr, uint8_t *root, cudaStream_t st);
+
+}  // namespace b200

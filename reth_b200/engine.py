@@ -1,0 +1,262 @@
+"""Engine — thin Python handle on a b200_ctx (one per GPU / per process).
+
+numpy arrays go through the host-pointer entry points (H2D + compute + D2H inside the call: the e2e path);
+torch CUDA tensors go through the *_dev entry points (inputs resident in HBM, asynchronous on the ctx stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import B200Error, FrontierEntry, Stats, Updates
+
+ACCOUNT_DTYPE = np.dtype([("nonce", "<u8"), ("balance", "u1", (32,)), ("code_hash", "u1", (32,))])
+KECCAK_EMPTY = bytes.fromhex("c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470")
+EMPTY_ROOT_HASH = bytes.fromhex("56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421")
+
+
+def _np(a, dtype=np.uint8):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _unpack_nibbles(packed: bytes, n: int) -> bytes:
+    return bytes(x for b in packed for x in (b >> 4, b & 15))[:n]
+
+
+def updates_to_records(u: Updates, lib) -> list:
+    """-> [(trie_id, path_nibbles, state_mask, tree_mask, hash_mask, [hashes])] sorted by (trie_id, path);
+    releases the library-owned buffers."""
+    n = int(u.n_nodes)
+    res = []
+    if n:
+        tid = np.ctypeslib.as_array(u.trie_id, (n,))
+        pl = np.ctypeslib.as_array(u.path_len, (n,))
+        pp = np.ctypeslib.as_array(u.path_packed, (n, 32))
+        sm = np.ctypeslib.as_array(u.state_mask, (n,))
+        tm = np.ctypeslib.as_array(u.tree_mask, (n,))
+        hm = np.ctypeslib.as_array(u.hash_mask, (n,))
+        ho = np.ctypeslib.as_array(u.hash_offset, (n + 1,))
+        nh = int(ho[n])
+        hs = np.ctypeslib.as_array(u.hashes, (max(nh, 1), 32))
+        for i in range(n):
+            res.append((int(tid[i]), _unpack_nibbles(pp[i].tobytes(), int(pl[i])), int(sm[i]), int(tm[i]),
+                        int(hm[i]), [hs[j].tobytes() for j in range(int(ho[i]), int(ho[i + 1]))]))
+    lib.b200_updates_release(C.byref(u))
+    res.sort(key=lambda r: (r[0], r[1]))
+    return res
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        if self.lib.b200_device_count() <= 0:
+            raise B200Error(_lib.ERR_NO_DEVICE, "no CUDA device: reth_b200 has no CPU path")
+        self.ctx = self.lib.b200_create(device)
+        if not self.ctx:
+            raise B200Error(self.lib.b200_create_status(), f"b200_create({device}) failed")
+        self.device = device
+        self._pinned = []
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.b200_destroy(self.ctx)
+            self.ctx = None
+            for p in self._pinned:
+                self.lib.b200_host_free(p)
+            self._pinned = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise B200Error(rc, self.lib.b200_last_error(self.ctx).decode())
+
+    # ------------------------------------------------------------------ plumbing
+    def version(self) -> str:
+        return self.lib.b200_version().decode()
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self.lib.b200_set_stream(self.ctx, cuda_stream))
+
+    def use_torch_stream(self):
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sync(self):
+        self._check(self.lib.b200_sync(self.ctx))
+
+    def launch_count(self) -> int:
+        return int(self.lib.b200_launch_count(self.ctx))
+
+    def device_bytes(self) -> int:
+        return int(self.lib.b200_device_bytes(self.ctx))
+
+    def last_stats(self) -> dict:
+        s = Stats()
+        self._check(self.lib.b200_last_stats(self.ctx, C.byref(s)))
+        return s.as_dict()
+
+    def pinned_empty(self, shape, dtype=np.uint8) -> np.ndarray:
+        """numpy array over page-locked memory from b200_host_alloc; released by close()."""
+        count = int(np.prod(shape))
+        nbytes = max(count * np.dtype(dtype).itemsize, 1)
+        p = self.lib.b200_host_alloc(nbytes)
+        if not p:
+            raise B200Error(_lib.ERR_OOM, "b200_host_alloc failed")
+        self._pinned.append(p)
+        buf = (C.c_uint8 * nbytes).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    # ------------------------------------------------------------------ keccak
+    def keccak256_fixed(self, msgs: np.ndarray, msg_len: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
+        """msgs: uint8[n, stride]; digest of the first msg_len bytes of every row -> uint8[n, 32]."""
+        if msgs.dtype != np.uint8 or msgs.ndim != 2 or not msgs.flags.c_contiguous:
+            msgs = _np(msgs)
+        n, stride = msgs.shape
+        if out is None:
+            out = np.empty((n, 32), np.uint8)
+        self._check(self.lib.b200_keccak256_fixed(self.ctx, _ptr(msgs), msg_len or stride, stride, n, _ptr(out)))
+        return out
+
+    def keccak256_var(self, data: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+        data = _np(data)
+        offsets = _np(offsets, np.uint64)
+        n = len(offsets) - 1
+        out = np.empty((n, 32), np.uint8)
+        self._check(self.lib.b200_keccak256_var(self.ctx, _ptr(data), _ptr(offsets), n, _ptr(out)))
+        return out
+
+    def keccak256(self, data: bytes) -> bytes:
+        d = np.frombuffer(bytes(data) or b"\0", np.uint8)
+        return self.keccak256_var(d, np.array([0, len(data)], np.uint64))[0].tobytes()
+
+    def hash_sort_keys(self, msgs: np.ndarray, msg_len: int | None = None):
+        """-> (sorted digests uint8[n,32], perm uint32[n]): digest[perm[i]] is the i-th smallest."""
+        msgs = _np(msgs)
+        n, stride = msgs.shape
+        out = np.empty((n, 32), np.uint8)
+        perm = np.empty(n, np.uint32)
+        self._check(self.lib.b200_hash_sort_keys(self.ctx, _ptr(msgs), msg_len or stride, stride, n, _ptr(out), _ptr(perm)))
+        return out, perm
+
+    # device-resident (torch) variants ------------------------------------------------------------
+    def keccak256_fixed_dev(self, t_in, msg_len: int, stride: int, n: int, t_out):
+        self._check(self.lib.b200_keccak256_fixed_dev(self.ctx, t_in.data_ptr(), msg_len, stride, n, t_out.data_ptr()))
+
+    def hash_sort_keys_dev(self, t_in, msg_len: int, stride: int, n: int, t_sorted, t_perm):
+        self._check(self.lib.b200_hash_sort_keys_dev(self.ctx, t_in.data_ptr(), msg_len, stride, n,
+                                                     t_sorted.data_ptr(), t_perm.data_ptr()))
+
+    def sort_keys32_dev(self, t_keys, n: int, t_sorted, t_perm):
+        self._check(self.lib.b200_sort_keys32_dev(self.ctx, t_keys.data_ptr(), n, t_sorted.data_ptr(), t_perm.data_ptr()))
+
+    # ------------------------------------------------------------------ roots (host buffers)
+    def storage_roots(self, slot_keys, values, seg_offsets, want_updates=False, want_stats=False):
+        slot_keys = _np(slot_keys).reshape(-1, 32)
+        values = _np(values).reshape(-1, 32)
+        seg_offsets = _np(seg_offsets, np.uint64)
+        m = len(seg_offsets) - 1
+        roots = np.empty((m, 32), np.uint8)
+        u, s = Updates(), Stats()
+        self._check(self.lib.b200_storage_roots(self.ctx, _ptr(slot_keys), _ptr(values), _ptr(seg_offsets), m,
+                                                _ptr(roots), C.byref(u) if want_updates else None, C.byref(s)))
+        res = [roots]
+        if want_updates:
+            res.append(updates_to_records(u, self.lib))
+        if want_stats:
+            res.append(s.as_dict())
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def state_root(self, acct_keys, accounts, storage_roots32=None, want_updates=False, want_stats=False):
+        acct_keys = _np(acct_keys).reshape(-1, 32)
+        accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
+        sr = None if storage_roots32 is None else _np(storage_roots32).reshape(-1, 32)
+        root = np.empty(32, np.uint8)
+        u, s = Updates(), Stats()
+        self._check(self.lib.b200_state_root(self.ctx, _ptr(acct_keys), _ptr(accounts), _ptr(sr), len(acct_keys),
+                                             _ptr(root), C.byref(u) if want_updates else None, C.byref(s)))
+        res = [root.tobytes()]
+        if want_updates:
+            res.append(updates_to_records(u, self.lib))
+        if want_stats:
+            res.append(s.as_dict())
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def state_root_full(self, acct_keys, accounts, slot_keys, values, seg_offsets, want_updates=False,
+                        want_stats=False):
+        acct_keys = _np(acct_keys).reshape(-1, 32)
+        accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
+        slot_keys = _np(slot_keys).reshape(-1, 32)
+        values = _np(values).reshape(-1, 32)
+        seg_offsets = _np(seg_offsets, np.uint64)
+        if len(seg_offsets) != len(acct_keys) + 1:
+            raise ValueError("seg_offsets must have n_accounts+1 entries")
+        root = np.empty(32, np.uint8)
+        ua, us, s = Updates(), Updates(), Stats()
+        self._check(self.lib.b200_state_root_full(
+            self.ctx, _ptr(acct_keys), _ptr(accounts), len(acct_keys), _ptr(slot_keys), _ptr(values),
+            _ptr(seg_offsets), _ptr(root), C.byref(ua) if want_updates else None,
+            C.byref(us) if want_updates else None, C.byref(s)))
+        res = [root.tobytes()]
+        if want_updates:
+            res += [updates_to_records(ua, self.lib), updates_to_records(us, self.lib)]
+        if want_stats:
+            res.append(s.as_dict())
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def subtrie_frontier(self, acct_keys, accounts, slot_keys, values, seg_offsets) -> np.ndarray:
+        """This rank's 16-entry frontier as uint8[16, 68] (b200_frontier_entry records)."""
+        acct_keys = _np(acct_keys).reshape(-1, 32)
+        accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
+        slot_keys = _np(slot_keys).reshape(-1, 32)
+        values = _np(values).reshape(-1, 32)
+        seg_offsets = _np(seg_offsets, np.uint64)
+        fr = (FrontierEntry * 16)()
+        s = Stats()
+        self._check(self.lib.b200_subtrie_frontier(self.ctx, _ptr(acct_keys), _ptr(accounts), len(acct_keys),
+                                                   _ptr(slot_keys), _ptr(values), _ptr(seg_offsets), fr, C.byref(s)))
+        return np.frombuffer(bytes(fr), np.uint8).reshape(16, 68).copy()
+
+    def root_from_frontier(self, frontier: np.ndarray) -> bytes:
+        frontier = _np(frontier).reshape(16, 68)
+        fr = (FrontierEntry * 16).from_buffer_copy(frontier.tobytes())
+        root = np.empty(32, np.uint8)
+        self._check(self.lib.b200_root_from_frontier(self.ctx, fr, _ptr(root)))
+        return root.tobytes()
+
+    # ------------------------------------------------------------------ roots (device buffers, torch tensors)
+    def storage_roots_dev(self, t_keys, t_vals, t_offs, n_accounts: int, n_slots: int, t_roots):
+        self._check(self.lib.b200_storage_roots_dev(self.ctx, t_keys.data_ptr(), t_vals.data_ptr(), t_offs.data_ptr(),
+                                                    n_accounts, n_slots, t_roots.data_ptr()))
+
+    def state_root_dev(self, t_keys, t_accts, t_sroots, n: int, t_root):
+        self._check(self.lib.b200_state_root_dev(self.ctx, t_keys.data_ptr(), t_accts.data_ptr(),
+                                                 t_sroots.data_ptr() if t_sroots is not None else None, n,
+                                                 t_root.data_ptr()))
+
+    def state_root_full_dev(self, t_akeys, t_accts, n_accounts: int, t_skeys, t_svals, t_offs, n_slots: int, t_root):
+        self._check(self.lib.b200_state_root_full_dev(self.ctx, t_akeys.data_ptr(), t_accts.data_ptr(), n_accounts,
+                                                      t_skeys.data_ptr(), t_svals.data_ptr(), t_offs.data_ptr(),
+                                                      n_slots, t_root.data_ptr()))
+
+    def subtrie_frontier_dev(self, t_akeys, t_accts, n_accounts: int, t_skeys, t_svals, t_offs, n_slots: int,
+                             t_frontier):
+        self._check(self.lib.b200_subtrie_frontier_dev(self.ctx, t_akeys.data_ptr(), t_accts.data_ptr(), n_accounts,
+                                                       t_skeys.data_ptr(), t_svals.data_ptr(), t_offs.data_ptr(),
+                                                       n_slots, t_frontier.data_ptr()))
+
+    def root_from_frontier_dev(self, t_frontier, t_root):
+        self._check(self.lib.b200_root_from_frontier_dev(self.ctx, t_frontier.data_ptr(), t_root.data_ptr()))
+
+    def dev_status(self):
+        self._check(self.lib.b200_dev_status(self.ctx))

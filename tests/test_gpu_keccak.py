@@ -1,0 +1,121 @@
+"""GPU parity: batched keccak256 through the C ABI (include/b200trie.h) against the oracle and the
+reference's known-answer vectors.  Bit-exact (byte work)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle
+from tests.util import random_keys, sort_rows
+
+H = bytes.fromhex
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from reth_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def test_known_answers(eng):
+    """KECCAK_EMPTY / EMPTY_ROOT_HASH / HASHED_ZERO_ADDRESS (hashing_storage.rs:34-35) and the address table of
+    crates/trie/db/tests/proof.rs:23-29."""
+    assert eng.keccak256(b"") == H("c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470")
+    assert eng.keccak256(b"\x80") == H("56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421")
+    z = eng.keccak256_fixed(np.zeros((1, 20), np.uint8))
+    assert z[0].tobytes() == H("5380c7b7ae81a58eb98d9c78de4a1fd7fd9535fc953ed2be602daaa41767312a")
+    table = {
+        "2031f89b3ea8014eb51a78c316e42af3e0d7695f": "a711355ec1c8f7e26bb3ccbcb0b75d870d15846c0b98e5cc452db46c37faea40",
+        "33f0fc440b8477fcfbe9d0bf8649e7dea9baedb2": "a77d337781e762f3577784bab7491fcc43e291ce5a356b9bc517ac52eed3a37a",
+        "62b0dd4aab2b1a0a04e279e2b828791a10755528": "a7f936599f93b769acf90c7178fd2ddcac1b5b4bc9949ee5a04b7e0823c2446e",
+        "1ed9b1dd266b607ee278726d324b855a093394a6": "a77d397a32b8ab5eb4b043c65b1f00c93f517bc8883c5cd31baf8e8a279475e3",
+        "000d836201318ec6899a67540690382780743280": "cf67b71c90b0d523dd5004cf206f325748da347685071b34812e21801f5270c4",
+    }
+    addrs = np.frombuffer(b"".join(H(a) for a in table), np.uint8).reshape(-1, 20)
+    got = eng.keccak256_fixed(addrs)
+    assert [g.tobytes().hex() for g in got] == list(table.values())
+
+
+@pytest.mark.parametrize("msg_len,stride", [(32, 32), (20, 20), (20, 32), (32, 48), (32, 33), (7, 7), (64, 64),
+                                            (135, 136), (136, 136), (137, 140), (300, 300)])
+def test_fixed_matches_oracle(eng, msg_len, stride):
+    n = 20_011
+    msgs = random_keys(msg_len * 1000 + stride, (n * stride + 31) // 32)[:].reshape(-1)[: n * stride].reshape(n, stride)
+    got = eng.keccak256_fixed(msgs, msg_len)
+    exp = oracle.keccak256_fixed(msgs, msg_len, threads=4)
+    assert (got == exp).all()
+
+
+def test_fixed_large_multi_chunk(eng):
+    """> 1 Mi messages exercises the chunked double-buffered host path."""
+    n = (1 << 21) + 12345
+    keys = random_keys(2, n)
+    got = eng.keccak256_fixed(keys)
+    idx = np.random.default_rng(0).integers(0, n, 5000)
+    exp = oracle.keccak256_fixed(keys[idx], threads=4)
+    assert (got[idx] == exp).all()
+    assert (got[-1] == oracle.keccak256_fixed(keys[-1:])[0]).all()
+
+
+def test_var_matches_oracle(eng):
+    rng = np.random.default_rng(5)
+    lens = np.concatenate([np.arange(0, 300), rng.integers(0, 1200, 700),
+                           np.array([135, 136, 137, 271, 272, 273, 407, 408, 409, 543, 544])])
+    offs = np.zeros(len(lens) + 1, np.uint64)
+    offs[1:] = np.cumsum(lens)
+    data = rng.integers(0, 256, int(offs[-1]), dtype=np.uint8)
+    got = eng.keccak256_var(data, offs)
+    exp = oracle.keccak256_var(data, offs, threads=2)
+    assert (got == exp).all()
+
+
+def test_empty_batches(eng):
+    assert eng.keccak256_fixed(np.zeros((0, 32), np.uint8)).shape == (0, 32)
+    assert eng.keccak256_var(np.zeros(0, np.uint8), np.zeros(1, np.uint64)).shape == (0, 32)
+
+
+def test_hash_sort_keys(eng):
+    """AccountHashing full pass: digests sorted ascending + permutation (hashing_account.rs:192-230)."""
+    n = 300_007
+    addrs = random_keys(77, n)[:, :20].copy()
+    sorted_d, perm = eng.hash_sort_keys(addrs)
+    exp = oracle.keccak256_fixed(addrs, threads=4)
+    order = sort_rows(exp)
+    assert (sorted_d == exp[order]).all()
+    assert (perm.astype(np.int64) == order).all()
+
+
+def test_sort_keys32_equal_prefix_fallback(eng):
+    """Keys sharing their first 8..31 bytes force the full-key LSD fallback."""
+    import torch
+    rng = np.random.default_rng(9)
+    n = 50_000
+    keys = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    keys[:, :8] = keys[0, :8]            # identical 64-bit prefix everywhere
+    keys[: n // 2, 8:24] = keys[1, 8:24]  # half of them also share the next 16 bytes
+    keys = np.unique(keys, axis=0)
+    rng.shuffle(keys)
+    n = len(keys)
+    t = torch.from_numpy(keys).cuda()
+    out = torch.empty_like(t)
+    perm = torch.empty(n, dtype=torch.int32, device="cuda")
+    eng.sort_keys32_dev(t, n, out, perm)
+    eng.sync()
+    order = sort_rows(keys)
+    assert (out.cpu().numpy() == keys[order]).all()
+    assert (perm.cpu().numpy().astype(np.int64) == order).all()
+
+
+def test_device_resident_path(eng):
+    import torch
+    n = 100_000
+    keys = random_keys(21, n)
+    t = torch.from_numpy(keys).cuda()
+    out = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
+    eng.use_torch_stream()
+    eng.keccak256_fixed_dev(t, 32, 32, n, out)
+    torch.cuda.synchronize()
+    eng.set_stream(None)
+    assert (out.cpu().numpy() == oracle.keccak256_fixed(keys, threads=4)).all()

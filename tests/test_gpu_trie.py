@@ -1,0 +1,282 @@
+"""GPU parity: storage roots / state roots / TrieUpdates through the C ABI against the reference's golden
+vectors and the CPU oracle.  Bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle
+from tests.test_oracle_golden import EXT_KEYS, _check_ext_updates, _flat_from_hashed, _vector5, ETHER
+from tests.util import alloc_to_flat, random_keys, sort_rows, synth_accounts, synth_storage, u256_be
+
+H = bytes.fromhex
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from reth_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+# ---------------------------------------------------------------- golden vectors through the C ABI
+@pytest.mark.parametrize("chain", ["mainnet", "sepolia", "holesky", "goerli"])
+def test_genesis_state_roots(eng, golden_allocs, chain):
+    """stateRoot of crates/chainspec/res/genesis/<chain>.json; addresses and slots hashed on the GPU too."""
+    g = golden_allocs[chain]
+    flat = alloc_to_flat(g["alloc"], keccak_rows=eng.keccak256_fixed)
+    assert eng.state_root_full(*flat).hex() == g["state_root"]
+
+
+def test_testspec_root(eng, golden_allocs):
+    """crates/trie/db/tests/proof.rs:55 — root = keccak(extension node e48200a7a0...)."""
+    flat = alloc_to_flat(golden_allocs["testspec"]["alloc"], keccak_rows=eng.keccak256_fixed)
+    ext = H("e48200a7a040f916999be583c572cc4dd369ec53b0a99f7de95f13880cf203d98f935ed1b3")
+    assert eng.state_root_full(*flat) == oracle.keccak256(ext)
+
+
+def test_account_and_storage_trie(eng):
+    """crates/trie/db/tests/trie.rs:357-477."""
+    flat = _flat_from_hashed(_vector5())
+    root, au, su = eng.state_root_full(*flat, want_updates=True)
+    assert root.hex() == "72861041bc90cd2f93777956f058a545412b56de79af5eb6b8075fe2eabbe015"
+    assert [(list(p), s, t, h, len(hs)) for (_, p, s, t, h, hs) in au] == [
+        ([0xB], 0b1011, 0b0001, 0b1001, 2), ([0xB, 0], 0b10001, 0, 0b10000, 1)]
+    o_root, o_au, o_su = oracle.state_root_full(*flat, want_updates=True)
+    assert (root, au, su) == (o_root, o_au, o_su)
+
+
+def test_account_and_storage_trie_after_insert(eng):
+    """crates/trie/db/tests/trie.rs:479-522 (root of the full rebuild)."""
+    accounts = _vector5()
+    accounts.append((oracle.keccak256(H("4f61f2d5ebd991b85aa1677db97307caf5215c91")), 0, 5 * ETHER, None, []))
+    root, au, _ = eng.state_root_full(*_flat_from_hashed(accounts), want_updates=True)
+    assert root.hex() == "8e263cd4eefb0c3cbbb14e5541a66a755cad25bcfab1e10dd9d706263e811b28"
+    assert [(list(p), s, t, h, len(hs)) for (_, p, s, t, h, hs) in au] == [
+        ([0xB], 0b1011, 0b0001, 0b1011, 3), ([0xB, 0], 0b10001, 0, 0b10000, 1)]
+
+
+def test_known_bundle_root(eng):
+    """crates/trie/db/src/state.rs:408-437."""
+    alloc = {
+        "00" * 19 + "01": {"nonce": "0x1", "balance": "0x0", "storage": {"0x" + (1015).to_bytes(32, "big").hex(): hex(10)}},
+        "00" * 19 + "02": {"nonce": "0x2", "balance": "0x0", "storage": {"0x" + (2015).to_bytes(32, "big").hex(): hex(20)}},
+    }
+    flat = alloc_to_flat(alloc, keccak_rows=eng.keccak256_fixed)
+    assert eng.state_root_full(*flat).hex() == "b464525710cafcf5d4044ac85b72c08b1e76231b8d91f288fe438cc41d8eaafd"
+
+
+def test_extension_node_tries(eng):
+    """crates/trie/db/tests/trie.rs:719-805: stored nodes [3] and [3,0,A,F]."""
+    keys = np.frombuffer(b"".join(H(k) for k in EXT_KEYS), np.uint8).reshape(-1, 32)
+    roots, upd = eng.storage_roots(keys, u256_be([1] * 6), [0, 6], want_updates=True)
+    _check_ext_updates(upd)
+    o_roots, o_upd = oracle.storage_roots(keys, u256_be([1] * 6), [0, 6], want_updates=True)
+    assert (roots == o_roots).all() and upd == o_upd
+    accs = oracle.make_accounts([(0, 1, bytes(range(32)))] * 6)
+    root, upd = eng.state_root(keys, accs, want_updates=True)
+    _check_ext_updates(upd)
+    assert (root, upd) == oracle.state_root(keys, accs, want_updates=True)
+
+
+# ---------------------------------------------------------------- edge cases
+def test_empty_and_single(eng):
+    assert eng.state_root(np.zeros((0, 32), np.uint8), np.zeros(0, oracle.ACCOUNT_DTYPE)) == oracle.EMPTY_ROOT_HASH
+    roots = eng.storage_roots(np.zeros((0, 32), np.uint8), np.zeros((0, 32), np.uint8), [0, 0, 0])
+    assert all(r.tobytes() == oracle.EMPTY_ROOT_HASH for r in roots)
+    k, a = synth_accounts(1, 1)
+    assert eng.state_root(k, a) == oracle.state_root(k, a)
+    sk, sv, so = synth_storage(2, [1])
+    assert (eng.storage_roots(sk, sv, so) == oracle.storage_roots(sk, sv, so)).all()
+    k, a = synth_accounts(3, 2)
+    assert eng.state_root(k, a, want_updates=True) == oracle.state_root(k, a, want_updates=True)
+
+
+def _shared_prefix_keys(rng, n, max_share=63):
+    keys = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    for i in range(1, n):
+        if rng.random() < 0.6:
+            share = int(rng.integers(0, max_share + 1))
+            src = keys[int(rng.integers(0, i))]
+            nb = share // 2
+            keys[i, :nb] = src[:nb]
+            if share & 1:
+                keys[i, nb] = (src[nb] & 0xF0) | (keys[i, nb] & 0x0F)
+    keys = np.unique(keys, axis=0)
+    return keys[sort_rows(keys)]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_forest_with_deep_shared_prefixes(eng, seed):
+    """Many small tries whose keys share up to 63 nibbles: every level 0..63 populated, extension nodes at all
+    depths, inline (<32 byte) leaves and branches.  Roots must equal the oracle's.  (Updates are not retained
+    here: an inline branch child under a hash bit makes alloy-trie itself panic.)"""
+    rng = np.random.default_rng(100 + seed)
+    segs, vals = [], []
+    for _ in range(60):
+        n = int(rng.choice([1, 2, 3, 5, 8, 17, 40]))
+        k = _shared_prefix_keys(rng, n)
+        segs.append(k)
+        v = np.zeros((len(k), 32), np.uint8)
+        for i in range(len(k)):
+            if rng.random() < 0.5:
+                v[i, 31] = rng.integers(1, 0x80)  # tiny values -> inline leaves when the suffix is short
+            else:
+                ln = int(rng.integers(1, 33))
+                v[i, 32 - ln:] = rng.integers(0, 256, ln, dtype=np.uint8)
+                v[i, 32 - ln] |= 1
+        vals.append(v)
+    offs = np.zeros(len(segs) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(s) for s in segs])
+    keys, values = np.concatenate(segs), np.concatenate(vals)
+    got = eng.storage_roots(keys, values, offs)
+    exp = oracle.storage_roots(keys, values, offs, threads=2)
+    assert (got == exp).all()
+
+
+@pytest.mark.parametrize("mode", ["u64", "mixed"])
+def test_storage_forest_random(eng, mode):
+    rng = np.random.default_rng(4)
+    counts = rng.choice([0, 1, 2, 3, 16, 17, 100, 1000], 3000, p=[.2, .2, .1, .1, .2, .1, .09, .01])
+    keys, vals, offs = synth_storage(31, counts, value_mode=mode)
+    roots, upd, stats = eng.storage_roots(keys, vals, offs, want_updates=True, want_stats=True)
+    o_roots, o_upd = oracle.storage_roots(keys, vals, offs, want_updates=True, threads=4)
+    assert (roots == o_roots).all()
+    assert upd == o_upd
+    assert stats["leaves_added"] == len(keys)
+
+
+def test_account_trie_random_with_updates(eng):
+    keys, accs = synth_accounts(8, 200_000)
+    sroots = random_keys(99, len(keys))
+    root, upd, stats = eng.state_root(keys, accs, sroots, want_updates=True, want_stats=True)
+    o_root, o_upd = oracle.state_root(keys, accs, sroots, want_updates=True)
+    assert root == o_root
+    assert upd == o_upd
+    oracle.stats_reset()
+    oracle.state_root(keys, accs, sroots)
+    s = oracle.stats()
+    assert stats["branches_added"] == s["branch_nodes"]
+    assert stats["extension_nodes"] == s["extension_nodes"]
+    assert stats["hashed_nodes"] == s["hashed_nodes"]
+
+
+def test_c1_config(eng):
+    """BASELINE.json configs[0]: 10k synthetic accounts, no storage."""
+    n = 10_000
+    seed_msgs = np.zeros((n, 16), np.uint8)
+    seed_msgs[:, 0] = 1
+    seed_msgs[:, 8:16] = np.arange(n, dtype="<u8").view(np.uint8).reshape(n, 8)
+    addrs = oracle.keccak256_fixed(seed_msgs)[:, :20].copy()
+    hashed = eng.keccak256_fixed(addrs)
+    assert (hashed == oracle.keccak256_fixed(addrs)).all()
+    order = sort_rows(hashed)
+    accs = oracle.make_accounts([(int(i) % 7, (int(i) + 1) * 10**15, None) for i in order])
+    root = eng.state_root(hashed[order], accs)
+    assert root == oracle.state_root(hashed[order], accs)
+
+
+def test_full_state_random(eng):
+    n = 30_000
+    akeys, accs = synth_accounts(12, n)
+    counts = np.where(np.arange(n) % 5 == 0, 16, 0) + np.where(np.arange(n) % 997 == 0, 3000, 0)
+    skeys, svals, offs = synth_storage(13, counts, value_mode="mixed")
+    root, au, su = eng.state_root_full(akeys, accs, skeys, svals, offs, want_updates=True)
+    o_root, o_au, o_su = oracle.state_root_full(akeys, accs, skeys, svals, offs, want_updates=True, threads=4)
+    assert root == o_root
+    assert au == o_au
+    assert su == o_su
+
+
+def test_one_million_leaves(eng):
+    """Size-independent check at scale: 1M-account trie root equals the oracle's."""
+    keys, accs = synth_accounts(77, 1_000_000)
+    root, stats = eng.state_root(keys, accs, want_stats=True)
+    assert root == oracle.state_root(keys, accs)
+    assert stats["leaves_added"] == 1_000_000
+
+
+# ---------------------------------------------------------------- error behaviour
+def test_rejects_unsorted_and_zero(eng):
+    from reth_b200 import B200Error
+    from reth_b200 import _lib
+    keys, accs = synth_accounts(5, 100)
+    bad = keys.copy()
+    bad[[10, 11]] = bad[[11, 10]]
+    with pytest.raises(B200Error) as e:
+        eng.state_root(bad, accs)
+    assert e.value.status == _lib.ERR_UNSORTED
+    dup = keys.copy()
+    dup[11] = dup[10]
+    with pytest.raises(B200Error) as e:
+        eng.state_root(dup, accs)
+    assert e.value.status == _lib.ERR_UNSORTED
+    sk, sv, so = synth_storage(6, [4, 4])
+    sv[5] = 0
+    with pytest.raises(B200Error) as e:
+        eng.storage_roots(sk, sv, so)
+    assert e.value.status == _lib.ERR_ZERO_VALUE
+    with pytest.raises(B200Error) as e:
+        eng.storage_roots(sk, np.ones_like(sv), np.array([0, 5, 3], np.uint64))
+    assert e.value.status == _lib.ERR_INVALID_ARG
+    # the context stays usable after an error
+    assert eng.state_root(keys, accs) == oracle.state_root(keys, accs)
+
+
+# ---------------------------------------------------------------- multi-GPU frontier (emulated shards on one GPU)
+@pytest.mark.parametrize("world", [1, 2, 4, 8, 16])
+def test_frontier_sharding_matches_full_root(eng, world):
+    n = 20_000
+    akeys, accs = synth_accounts(41, n)
+    counts = np.where(np.arange(n) % 11 == 0, 5, 0)
+    skeys, svals, offs = synth_storage(42, counts)
+    full = oracle.state_root_full(akeys, accs, skeys, svals, offs, threads=4)
+    merged = np.zeros((16, 68), np.uint8)
+    top = akeys[:, 0] >> 4
+    for rank in range(world):
+        lo_n, hi_n = rank * 16 // world, (rank + 1) * 16 // world
+        sel = np.nonzero((top >= lo_n) & (top < hi_n))[0]
+        a0, a1 = (int(sel[0]), int(sel[-1]) + 1) if len(sel) else (0, 0)
+        s0, s1 = int(offs[a0]), int(offs[a1])
+        fr = eng.subtrie_frontier(akeys[a0:a1], accs[a0:a1], skeys[s0:s1], svals[s0:s1], offs[a0:a1 + 1] - offs[a0])
+        for b in range(lo_n, hi_n):
+            merged[b] = fr[b]
+        others = [b for b in range(16) if not lo_n <= b < hi_n]
+        assert not fr[others].any()
+    assert eng.root_from_frontier(merged) == full
+
+
+def test_frontier_degenerate_shapes(eng):
+    # all accounts in one top-nibble bucket: the root is not a depth-0 branch
+    keys, accs = synth_accounts(51, 500)
+    keys[:, 0] = (keys[:, 0] & 0x0F) | 0x70
+    keys = keys[sort_rows(keys)]
+    z = np.zeros((0, 32), np.uint8)
+    offs = np.zeros(len(keys) + 1, np.uint64)
+    fr = eng.subtrie_frontier(keys, accs, z, z, offs)
+    assert eng.root_from_frontier(fr) == oracle.state_root(keys, accs)
+    # a single account; and nothing at all
+    fr = eng.subtrie_frontier(keys[:1], accs[:1], z, z, offs[:2])
+    assert eng.root_from_frontier(fr) == oracle.state_root(keys[:1], accs[:1])
+    fr = eng.subtrie_frontier(keys[:0], accs[:0], z, z, offs[:1])
+    assert eng.root_from_frontier(fr) == oracle.EMPTY_ROOT_HASH
+    # two buckets with one account each
+    k2 = np.zeros((2, 32), np.uint8)
+    k2[0, 0], k2[1, 0] = 0x10, 0xF0
+    fr = eng.subtrie_frontier(k2, accs[:2], z, z, offs[:3])
+    assert eng.root_from_frontier(fr) == oracle.state_root(k2, accs[:2])
+
+
+def test_device_resident_full_state(eng):
+    import torch
+    n = 50_000
+    akeys, accs = synth_accounts(61, n)
+    skeys, svals, offs = synth_storage(62, np.full(n, 4))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
+    d_root = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    eng.use_torch_stream()
+    eng.state_root_full_dev(t(akeys), t(accs), n, t(skeys), t(svals), t(offs), len(skeys), d_root)
+    eng.dev_status()
+    eng.set_stream(None)
+    assert d_root.cpu().numpy().tobytes() == oracle.state_root_full(akeys, accs, skeys, svals, offs, threads=4)
