@@ -39,6 +39,25 @@ METRIC = "keccak256_digests_per_sec"
 UNIT = "digests/s"
 
 
+def effective_cpus() -> int:
+    """Host threads this process can really run: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return n
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -168,7 +187,7 @@ class ClockSampler:
 def cpu_keccak_baseline(target_seconds: float = 12.0):
     """oracle keccak over 32-byte keys on all host cores; bounded sample of the C2 workload."""
     import oracle
-    cores = os.cpu_count() or 1
+    cores = effective_cpus()
     n = 2_000_000
     from tests.util import random_keys
     keys = random_keys(2, n)
@@ -189,7 +208,7 @@ def cpu_state_root_baseline(n_accounts: int = 40_000, slots: int = 16):
     """oracle ParallelStateRoot-shaped build on all host cores over a C3-shaped sample."""
     import oracle
     from tests.util import synth_accounts, synth_storage
-    cores = os.cpu_count() or 1
+    cores = effective_cpus()
     akeys, accs = synth_accounts(3, n_accounts)
     skeys, svals, offs = synth_storage(3, np.full(n_accounts, slots))
     leaves = n_accounts * (slots + 1)
@@ -211,7 +230,7 @@ def run_reference(args, rank, world):
         return
     import oracle
     from tests.util import random_keys
-    cores = os.cpu_count() or 1
+    cores = effective_cpus()
     n = 1_000_000
     keys = random_keys(2, n)
     for _ in range(args.warmup):
@@ -267,6 +286,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     eng = Engine(local_rank)
+    # a dedicated (non-default) stream: torch events, NCCL and the engine's kernels are all ordered on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     eng.use_torch_stream()
 
     def barrier():

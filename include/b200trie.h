@@ -59,7 +59,8 @@ B200_API void b200_destroy(b200_ctx *);
 B200_API const char *b200_last_error(const b200_ctx *);
 B200_API const char *b200_version(void);
 /* Use an existing CUDA stream (cudaStream_t passed as void*) instead of the context's own stream, so that a
- * host runtime (torch, the Rust shim's stream) can order and time the work. NULL restores the own stream. */
+ * host runtime (torch, the Rust shim's stream) can order and time the work.  NULL is the CUDA legacy default
+ * stream (what a cudaStream_t of 0 means everywhere); (void*)-1 restores the context's own stream. */
 B200_API int32_t b200_set_stream(b200_ctx *, void *cuda_stream);
 B200_API int32_t b200_sync(b200_ctx *);
 /* Page-locked host buffers for the host-pointer entry points (pageable memory works too, but is slower). */

@@ -5,3 +5,9 @@ package is the host-side mirror of the reference interface used by tests and ben
 """
 from ._lib import B200Error, LIB_PATH  # noqa: F401
 from .engine import ACCOUNT_DTYPE, EMPTY_ROOT_HASH, KECCAK_EMPTY, Engine  # noqa: F401
+from .hashed_state import (Account, HashedPostState, HashedPostStateSorted, HashedStorage,  # noqa: F401,E402
+                           HashedStorageSorted, KeccakKeyHasher, PrefixSet, PrefixSetMut, TriePrefixSets,
+                           TriePrefixSetsMut, unpack_nibbles)
+from .stages import AccountHashingStage, MerkleStage, StageError, StorageHashingStage, Tables  # noqa: F401,E402
+from .trie import (BranchNodeCompact, ParallelStateRoot, StateRoot, StateRootError, StateRootProgress,  # noqa: F401,E402
+                   StorageRoot, StorageTrieUpdates, TrieUpdates)

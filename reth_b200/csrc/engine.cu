@@ -79,7 +79,7 @@ extern "C" B200_API void b200_destroy(b200_ctx *c) {
                       &c->upd_flags, &c->upd_nh, &c->upd_ids, &c->upd_prefix, &c->in_a, &c->in_b, &c->in_c,
                       &c->in_d, &c->in_e, &c->out_a, &c->chunk_in[0], &c->chunk_in[1], &c->chunk_out[0],
                       &c->chunk_out[1], &c->sort_ka, &c->sort_kb, &c->sort_ia, &c->sort_flag, &c->sort_perm,
-                      &c->sort_out};
+                      &c->sort_out, &c->node_key, &c->node_key2, &c->node_ids, &c->node_order};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->pinned_small) cudaFreeHost(c->pinned_small);
@@ -98,7 +98,10 @@ extern "C" B200_API uint64_t b200_device_bytes(const b200_ctx *c) { return c ? c
 extern "C" B200_API int32_t b200_set_stream(b200_ctx *c, void *cuda_stream) {
     if (!c) return B200_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(c->mu);
-    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    // 0 is the CUDA legacy default stream; "no stream given" is spelled b200_set_stream(ctx, (void*)-1)
+    c->stream = cuda_stream == reinterpret_cast<void *>(-1) ? c->own_stream
+                : cuda_stream == nullptr                    ? cudaStreamLegacy
+                                                            : static_cast<cudaStream_t>(cuda_stream);
     return B200_OK;
 }
 
@@ -414,13 +417,29 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
     f.node_r = static_cast<uint32_t *>(c->node_r.p);
     f.node_masks = static_cast<ushort4 *>(c->node_masks.p);
 
+    // ---- node visiting order: (depth descending, child-count class); ids stay what they are
+    ENSURE(node_key, B);
+    ENSURE(node_key2, B);
+    ENSURE(node_ids, (size_t)B * 4);
+    ENSURE(node_order, (size_t)B * 4);
+    uint8_t *nk = static_cast<uint8_t *>(c->node_key.p), *nk2 = static_cast<uint8_t *>(c->node_key2.p);
+    uint32_t *nids = static_cast<uint32_t *>(c->node_ids.p), *norder = static_cast<uint32_t *>(c->node_order.p);
+    CU(launch_node_class_keys(node_start, depth_sorted, B, nk, nids, st));
+    size_t t_ns = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, t_ns, nk, nk2, nids, norder, (int64_t)B, 0, 8, st));
+    ENSURE(cub_temp, t_ns);
+    CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_ns, nk, nk2, nids, norder, (int64_t)B, 0, 8, st));
+    c->launches += 2;
+
     // ---- deepest level first: one launch per populated level, the per-level frontier stays in HBM
+    uint32_t pos = 0;
     for (int d = 63; d >= 0; d--) {
-        uint32_t lo = h_level[d], hi = h_level[d + 1];
-        if (hi > lo) {
-            CU(launch_branch_level(f, lo, hi, d, st));
+        uint32_t cnt = h_level[d + 1] - h_level[d];
+        if (cnt) {
+            CU(launch_branch_level(f, norder, pos, pos + cnt, d, st));
             c->launches++;
             out.levels++;
+            pos += cnt;
         }
     }
     return B200_OK;

@@ -32,6 +32,7 @@ struct b200_ctx {
         node_ref, node_meta, node_l, node_r, node_masks, cub_temp, small, sroots, buckets;
     DevBuf upd_flags, upd_nh, upd_ids, upd_prefix;
     DevBuf sort_ka, sort_kb, sort_ia, sort_flag, sort_perm, sort_out;
+    DevBuf node_key, node_key2, node_ids, node_order;
     // staging for host-pointer entry points
     DevBuf in_a, in_b, in_c, in_d, in_e, out_a, chunk_in[2], chunk_out[2];
     void *pinned_small = nullptr;  // 4 KiB page-locked readback area

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(BLOCK) keccak256_fixed32_kernel(const uint8_t 
 #pragma unroll
         for (int l = 5; l < 25; l++) a[l] = 0;
         a[16] = 0x8000000000000000ULL;  // last byte of the 136-byte rate block
-        keccak_f1600_final(a);
+        keccak_f1600_sparse_final(a);
         uint4 d0 = make_uint4((uint32_t)a[0], (uint32_t)(a[0] >> 32), (uint32_t)a[1], (uint32_t)(a[1] >> 32));
         uint4 d1 = make_uint4((uint32_t)a[2], (uint32_t)(a[2] >> 32), (uint32_t)a[3], (uint32_t)(a[3] >> 32));
         out[2 * i] = d0;
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(BLOCK) keccak256_fixed20_kernel(const uint8_t 
 #pragma unroll
         for (int l = 3; l < 25; l++) a[l] = 0;
         a[16] = 0x8000000000000000ULL;
-        keccak_f1600_final(a);
+        keccak_f1600_sparse_final(a);
         uint4 d0 = make_uint4((uint32_t)a[0], (uint32_t)(a[0] >> 32), (uint32_t)a[1], (uint32_t)(a[1] >> 32));
         uint4 d1 = make_uint4((uint32_t)a[2], (uint32_t)(a[2] >> 32), (uint32_t)a[3], (uint32_t)(a[3] >> 32));
         out[2 * i] = d0;

@@ -117,4 +117,13 @@ __device__ __forceinline__ void keccak_f1600_final(uint64_t (&a)[25]) {
     keccak_round(a, 0x8000000080008008ULL);
 }
 
+// Single-block message whose state is mostly compile-time zeros (a 20/32-byte key): round 0 is peeled too, so
+// that the compiler folds the XORs with the 20 zero lanes and the constant pad lanes.
+__device__ __forceinline__ void keccak_f1600_sparse_final(uint64_t (&a)[25]) {
+    keccak_round(a, 0x0000000000000001ULL);
+#pragma unroll 1
+    for (int r = 1; r < 23; r++) keccak_round(a, KECCAK_RC[r]);
+    keccak_round(a, 0x8000000080008008ULL);
+}
+
 }  // namespace b200

@@ -200,8 +200,12 @@ __global__ void lcp_kernel(const uint8_t *__restrict__ keys, uint64_t n, uint8_t
             ascending = x < y;
         }
     }
-    if (!ascending) atomicExch(err, B200_DEVERR_UNSORTED);  // equal or descending keys inside one trie
-    Lp[g] = (uint8_t)(lcp & 63);
+    if (!ascending) {  // equal or descending keys inside one trie: flag it; later kernels of the build bail out
+        atomicExch(err, B200_DEVERR_UNSORTED);
+        Lp[g] = 0xFF;
+        return;
+    }
+    Lp[g] = (uint8_t)lcp;
     nibs[g] = (uint8_t)((na << 4) | nbb);
 }
 
@@ -411,6 +415,7 @@ template <int BLOCK, bool ACCOUNT>
 __global__ void __launch_bounds__(BLOCK) leaf_kernel(ForestDev f, const uint8_t *__restrict__ values,
                                                      const uint8_t *__restrict__ storage_roots) {
     extern __shared__ uint32_t smem[];
+    if (*(volatile int *)f.err == B200_DEVERR_UNSORTED || *(volatile int *)f.err == B200_DEVERR_BAD_OFFSETS) return;
     Strip<BLOCK> s;
     uint32_t hashed = 0;
     const uint64_t step = (uint64_t)gridDim.x * BLOCK;
@@ -543,13 +548,17 @@ __device__ __forceinline__ uint32_t encode_extension(Strip<BLOCK> &s, const uint
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) branch_kernel(ForestDev f, uint32_t node_lo, uint32_t node_hi, int d) {
+__global__ void __launch_bounds__(BLOCK) branch_kernel(ForestDev f, const uint32_t *__restrict__ node_order,
+                                                       uint32_t pos_lo, uint32_t pos_hi, int d) {
     extern __shared__ uint32_t smem[];
+    if (*(volatile int *)f.err != B200_DEVERR_NONE) return;  // malformed input: the structure arrays are not trustworthy
     Strip<BLOCK> s;
     uint32_t hashed = 0, exts = 0;
     const uint32_t step = gridDim.x * BLOCK;
-    for (uint64_t v64 = (uint64_t)node_lo + blockIdx.x * BLOCK + threadIdx.x; v64 < node_hi; v64 += step) {
-        uint32_t v = (uint32_t)v64;
+    for (uint64_t p64 = (uint64_t)pos_lo + blockIdx.x * BLOCK + threadIdx.x; p64 < pos_hi; p64 += step) {
+        // nodes of a level are visited grouped by child-count class, so the lanes of a warp absorb the same
+        // number of rate blocks (1..4) and do not wait on each other
+        uint32_t v = __ldg(node_order + p64);
         s.init(smem);
         uint32_t j0 = f.node_start[v], k = f.node_start[v + 1] - j0;
         uint32_t state_mask, tree_mask, hash_mask, l, r;
@@ -593,6 +602,7 @@ __global__ void segment_roots_kernel(ForestDev f, const uint64_t *__restrict__ s
                                      uint8_t *__restrict__ roots) {
     uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_segs) return;
+    if (*(volatile int *)f.err != B200_DEVERR_NONE) return;
     uint32_t ref[8];
     uint64_t lo = seg_offsets ? seg_offsets[s] : 0, hi = seg_offsets ? seg_offsets[s + 1] : f.n;
     if (lo == hi) {  // StorageRoot::calculate short circuit, trie.rs:622-629
@@ -680,7 +690,7 @@ __global__ void frontier_kernel(ForestDev f, const uint64_t *__restrict__ bucket
     uint32_t b = threadIdx.x;
     Strip<BLOCK> s;
     s.init(smem);
-    if (b >= 16) return;
+    if (b >= 16 || *(volatile int *)f.err != B200_DEVERR_NONE) return;
     FrontierEntryDev e;
     for (int i = 0; i < 33; i++) e.as_child[i] = e.as_root[i] = 0;
     e.as_child_len = e.as_root_len = 0;
@@ -867,11 +877,31 @@ cudaError_t launch_leaves(const ForestDev &f, bool account, const uint8_t *value
     return cudaGetLastError();
 }
 
-cudaError_t launch_branch_level(const ForestDev &f, uint32_t node_lo, uint32_t node_hi, int d, cudaStream_t st) {
-    if (node_hi <= node_lo) return cudaSuccess;
+cudaError_t launch_branch_level(const ForestDev &f, const uint32_t *node_order, uint32_t pos_lo, uint32_t pos_hi,
+                                int d, cudaStream_t st) {
+    if (pos_hi <= pos_lo) return cudaSuccess;
     auto k = branch_kernel<BRANCH_BLOCK>;
     size_t smem = (size_t)BRANCH_WORDS * BRANCH_BLOCK * 4;
-    k<<<persistent_grid(k, BRANCH_BLOCK, smem, node_hi - node_lo), BRANCH_BLOCK, smem, st>>>(f, node_lo, node_hi, d);
+    k<<<persistent_grid(k, BRANCH_BLOCK, smem, pos_hi - pos_lo), BRANCH_BLOCK, smem, st>>>(f, node_order, pos_lo,
+                                                                                          pos_hi, d);
+    return cudaGetLastError();
+}
+
+// sort key of node v: deepest level first, then by the number of rate blocks its RLP needs when every child
+// is a 33-byte hash reference (children <= 3 -> 1 block, <= 7 -> 2, <= 12 -> 3, else 4)
+__global__ void node_class_keys_kernel(const uint32_t *__restrict__ node_start, const uint8_t *__restrict__ depth_sorted,
+                                       uint32_t n_nodes, uint8_t *__restrict__ keys, uint32_t *__restrict__ ids) {
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    uint32_t j0 = node_start[v], children = node_start[v + 1] - j0 + 1;
+    uint32_t cls = children <= 3 ? 0 : (children <= 7 ? 1 : (children <= 12 ? 2 : 3));
+    keys[v] = (uint8_t)(((63u - depth_sorted[j0]) << 2) | cls);
+    ids[v] = v;
+}
+cudaError_t launch_node_class_keys(const uint32_t *node_start, const uint8_t *depth_sorted, uint32_t n_nodes,
+                                   uint8_t *keys, uint32_t *ids, cudaStream_t st) {
+    if (n_nodes == 0) return cudaSuccess;
+    node_class_keys_kernel<<<blocks_for(n_nodes, 256), 256, 0, st>>>(node_start, depth_sorted, n_nodes, keys, ids);
     return cudaGetLastError();
 }
 

@@ -86,7 +86,9 @@ class Engine:
         return self.lib.b200_version().decode()
 
     def set_stream(self, cuda_stream: int | None):
-        self._check(self.lib.b200_set_stream(self.ctx, cuda_stream))
+        """cuda_stream: a cudaStream_t handle (0 = legacy default stream); None = the context's own stream."""
+        handle = C.c_void_p(-1) if cuda_stream is None else C.c_void_p(cuda_stream)
+        self._check(self.lib.b200_set_stream(self.ctx, handle))
 
     def use_torch_stream(self):
         import torch

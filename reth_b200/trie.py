@@ -1,0 +1,205 @@
+"""Host-side mirror of reth's root calculators (crates/trie/trie/src/trie.rs, crates/trie/parallel/src/root.rs,
+crates/trie/common/src/updates.rs) over the C ABI.
+
+The calculators take the hashed state itself where reth takes cursor factories over it: with no stored trie nodes
+underneath (from-scratch build: MerkleStage's rebuild path `merkle.rs:210-254`, `StateRootProvider::state_root`
+on a full state, every test that uses `MockHashedCursorFactory` + `NoopTrieCursor`) the walk degenerates to
+"stream all leaves in key order" (SURVEY.md §3.2), which is what the device consumes.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .engine import EMPTY_ROOT_HASH, Engine
+from .hashed_state import HashedPostStateSorted, HashedStorageSorted, TriePrefixSets
+
+B256 = bytes
+Nibbles = bytes
+
+
+@dataclass(frozen=True)
+class BranchNodeCompact:
+    """alloy_trie::BranchNodeCompact as reth stores it (crates/storage/db-api/src/tables/mod.rs:484-494)."""
+    state_mask: int
+    tree_mask: int
+    hash_mask: int
+    hashes: Tuple[bytes, ...]
+    root_hash: Optional[bytes] = None
+
+
+@dataclass
+class StorageTrieUpdates:
+    """crates/trie/common/src/updates.rs:235-245."""
+    is_deleted: bool = False
+    storage_nodes: Dict[Nibbles, BranchNodeCompact] = field(default_factory=dict)
+    removed_nodes: set = field(default_factory=set)
+
+    @classmethod
+    def deleted(cls):
+        return cls(is_deleted=True)
+
+    def is_empty(self) -> bool:
+        return not self.is_deleted and not self.storage_nodes and not self.removed_nodes
+
+    def __len__(self):
+        return int(self.is_deleted) + len(self.storage_nodes) + len(self.removed_nodes)
+
+
+@dataclass
+class TrieUpdates:
+    """crates/trie/common/src/updates.rs:17-26."""
+    account_nodes: Dict[Nibbles, BranchNodeCompact] = field(default_factory=dict)
+    removed_nodes: set = field(default_factory=set)
+    storage_tries: Dict[B256, StorageTrieUpdates] = field(default_factory=dict)
+
+    def insert_storage_updates(self, hashed_address: B256, updates: StorageTrieUpdates):
+        if updates.is_empty():  # updates.rs:132-134
+            return
+        assert hashed_address not in self.storage_tries
+        self.storage_tries[hashed_address] = updates
+
+    def is_empty(self) -> bool:
+        return not self.account_nodes and not self.removed_nodes and not self.storage_tries
+
+
+@dataclass
+class StateRootProgress:
+    """crates/trie/trie/src/progress.rs:12-21.  A device build never pauses: always `Complete`."""
+    root: bytes
+    hashed_entries_walked: int
+    updates: TrieUpdates
+    complete: bool = True
+
+
+class StateRootError(RuntimeError):
+    """StateRootError::Database(DatabaseError::Other(msg)) in the Rust shim."""
+
+
+def _records_to_nodes(records) -> Dict[int, Dict[Nibbles, BranchNodeCompact]]:
+    out: Dict[int, Dict[Nibbles, BranchNodeCompact]] = {}
+    for tid, path, sm, tm, hm, hashes in records:
+        out.setdefault(tid, {})[bytes(path)] = BranchNodeCompact(sm, tm, hm, tuple(hashes))
+    return out
+
+
+class StorageRoot:
+    """StorageRoot::new_hashed(..).root() / root_with_updates() — crates/trie/trie/src/trie.rs:479-615."""
+
+    def __init__(self, engine: Engine, hashed_address: B256, storage: HashedStorageSorted):
+        self.engine, self.hashed_address, self.storage = engine, hashed_address, storage
+        self.prefix_set = None
+        self.threshold = 100_000
+
+    def with_prefix_set(self, prefix_set):
+        self.prefix_set = prefix_set
+        return self
+
+    def with_threshold(self, threshold: int):
+        self.threshold = threshold
+        return self
+
+    def with_no_threshold(self):
+        self.threshold = 2**64 - 1
+        return self
+
+    def _flat(self):
+        slots = [(k, v) for k, v in self.storage.storage_slots if v != 0]
+        m = len(slots)
+        keys = np.frombuffer(b"".join(k for k, _ in slots), np.uint8).reshape(m, 32) if m else np.zeros((0, 32), np.uint8)
+        vals = np.frombuffer(b"".join(int(v).to_bytes(32, "big") for _, v in slots), np.uint8).reshape(m, 32) \
+            if m else np.zeros((0, 32), np.uint8)
+        return keys, vals, np.array([0, m], np.uint64)
+
+    def root(self) -> bytes:
+        return self.calculate(False)[0]
+
+    def root_with_updates(self) -> Tuple[bytes, int, StorageTrieUpdates]:
+        return self.calculate(True)
+
+    def calculate(self, retain_updates: bool) -> Tuple[bytes, int, StorageTrieUpdates]:
+        """-> (root, storage_slots_walked, updates) like StorageRootProgress::Complete (trie.rs:615-721)."""
+        keys, vals, offs = self._flat()
+        if len(keys) == 0:  # trie.rs:622-629
+            return EMPTY_ROOT_HASH, 0, StorageTrieUpdates.deleted()
+        try:
+            if retain_updates:
+                roots, recs = self.engine.storage_roots(keys, vals, offs, want_updates=True)
+                upd = StorageTrieUpdates(storage_nodes=_records_to_nodes(recs).get(0, {}))
+            else:
+                roots, upd = self.engine.storage_roots(keys, vals, offs), StorageTrieUpdates()
+        except Exception as e:  # noqa: BLE001 - mapped like the shim maps native errors
+            raise StateRootError(str(e)) from e
+        return roots[0].tobytes(), len(keys), upd
+
+
+class StateRoot:
+    """StateRoot::{root, root_with_updates, root_with_progress} — crates/trie/trie/src/trie.rs:54-158."""
+
+    def __init__(self, engine: Engine, hashed_state: HashedPostStateSorted):
+        self.engine, self.state = engine, hashed_state
+        self.prefix_sets = TriePrefixSets()
+        self.threshold = 100_000  # DEFAULT_INTERMEDIATE_THRESHOLD, trie.rs:25
+
+    def with_prefix_sets(self, prefix_sets: TriePrefixSets):
+        self.prefix_sets = prefix_sets
+        return self
+
+    def with_threshold(self, threshold: int):
+        self.threshold = threshold
+        return self
+
+    def with_no_threshold(self):
+        self.threshold = 2**64 - 1
+        return self
+
+    def root(self) -> bytes:
+        return self._calculate(False).root
+
+    def root_with_updates(self) -> Tuple[bytes, TrieUpdates]:
+        p = self._calculate(True)
+        return p.root, p.updates
+
+    def root_with_progress(self) -> StateRootProgress:
+        return self._calculate(True)
+
+    def _calculate(self, retain_updates: bool) -> StateRootProgress:
+        keys, accts, skeys, svals, offs = self.state.to_flat()
+        try:
+            if retain_updates:
+                root, acct_recs, stor_recs = self.engine.state_root_full(keys, accts, skeys, svals, offs,
+                                                                         want_updates=True)
+            else:
+                root = self.engine.state_root_full(keys, accts, skeys, svals, offs)
+                acct_recs = stor_recs = []
+        except Exception as e:  # noqa: BLE001
+            raise StateRootError(str(e)) from e
+        updates = TrieUpdates()
+        if retain_updates:
+            updates.account_nodes = _records_to_nodes(acct_recs).get(0, {})
+            per_trie = _records_to_nodes(stor_recs)
+            for i in range(len(keys)):
+                addr = keys[i].tobytes()
+                if offs[i + 1] == offs[i]:
+                    # StorageRoot::calculate returns StorageTrieUpdates::deleted() for empty storage (trie.rs:622-629)
+                    updates.insert_storage_updates(addr, StorageTrieUpdates.deleted())
+                else:
+                    updates.insert_storage_updates(addr, StorageTrieUpdates(storage_nodes=per_trie.get(i, {})))
+            # TrieUpdates::finalize (updates.rs:140-158): destroyed accounts -> is_deleted
+            for destroyed in self.prefix_sets.destroyed_accounts:
+                updates.storage_tries.setdefault(destroyed, StorageTrieUpdates()).is_deleted = True
+        walked = int(len(keys) + len(skeys))
+        return StateRootProgress(root, walked, updates)
+
+
+class ParallelStateRoot(StateRoot):
+    """ParallelStateRoot::{incremental_root, incremental_root_with_updates} — crates/trie/parallel/src/root.rs:35-77.
+    On the device the storage-root fan-out and the account fold are the same launches."""
+
+    def incremental_root(self) -> bytes:
+        return self.root()
+
+    def incremental_root_with_updates(self) -> Tuple[bytes, TrieUpdates]:
+        return self.root_with_updates()

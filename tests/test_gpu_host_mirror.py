@@ -1,0 +1,117 @@
+"""GPU tests written against the host mirror of reth's interface (StateRoot / StorageRoot / ParallelStateRoot /
+HashedPostState / the hashing + merkle stages) so they read like the reference's own tests."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle
+from reth_b200 import (Account, AccountHashingStage, Engine, HashedPostState, HashedStorage, MerkleStage,
+                       ParallelStateRoot, StageError, StateRoot, StorageHashingStage, StorageRoot, Tables,
+                       EMPTY_ROOT_HASH)
+from tests.util import alloc_to_flat
+
+H = bytes.fromhex
+ETHER = 10**18
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def test_from_bundle_state_known_root(eng):
+    """from_bundle_state_with_rayon — crates/trie/db/src/state.rs:408-437."""
+    a1, a2 = bytes(19) + b"\x01", bytes(19) + b"\x02"
+    bundle = [
+        (a1, {"info": Account(nonce=1), "storage": {1015: 10}}),
+        (a2, {"info": Account(nonce=2), "storage": {2015: 20}}),
+    ]
+    post_state = HashedPostState.from_bundle_state(eng, bundle)
+    assert len(post_state.accounts) == 2 and len(post_state.storages) == 2
+    root = StateRoot(eng, post_state.into_sorted()).root()
+    assert root.hex() == "b464525710cafcf5d4044ac85b72c08b1e76231b8d91f288fe438cc41d8eaafd"
+
+
+def test_account_and_storage_trie_via_mirror(eng):
+    """account_and_storage_trie — crates/trie/db/tests/trie.rs:357-477 (root, two stored account nodes)."""
+    storage = {H("12" + "00" * 31): 0x42, H("14" + "00" * 31): 0x01,
+               H("30" + "00" * 28 + "E00000"): 0x127A89, H("30" + "00" * 28 + "E00001"): 0x05}
+    key3 = oracle.keccak256(H("16b07afd1c635f77172e842a000ead9a2a222459"))
+    state = HashedPostState(
+        accounts={
+            H("b0" + "00" * 31): Account(0, 3 * ETHER),
+            oracle.keccak256(H("7db3e81b72d2695e19764583f6d219dbee0f35ca")): Account(0, ETHER),
+            key3: Account(0, 2 * ETHER, H("5be74cad16203c4905c068b012a2e9fb6d19d036c410f16fd177f337541440dd")),
+            H("B1A0" + "00" * 30): Account(0, 4 * ETHER),
+            H("B310" + "00" * 30): Account(0, 8 * ETHER),
+            H("B340" + "00" * 30): Account(0, 1 * ETHER),
+        },
+        storages={key3: HashedStorage(False, storage)},
+    ).into_sorted()
+    root, updates = StateRoot(eng, state).root_with_updates()
+    assert root.hex() == "72861041bc90cd2f93777956f058a545412b56de79af5eb6b8075fe2eabbe015"
+    nodes = sorted(updates.account_nodes.items())
+    assert [list(p) for p, _ in nodes] == [[0xB], [0xB, 0x0]]
+    n1, n2 = nodes[0][1], nodes[1][1]
+    assert (n1.state_mask, n1.tree_mask, n1.hash_mask, len(n1.hashes), n1.root_hash) == (0b1011, 0b0001, 0b1001, 2, None)
+    assert (n2.state_mask, n2.tree_mask, n2.hash_mask, len(n2.hashes)) == (0b10001, 0, 0b10000, 1)
+    # every account without storage carries StorageTrieUpdates::deleted() (trie.rs:622-629 + updates.rs:126-137)
+    assert sum(u.is_deleted for u in updates.storage_tries.values()) == 5
+    assert key3 not in updates.storage_tries  # its 4-leaf trie stores no branch node
+    # ParallelStateRoot and the storage root on its own agree
+    assert ParallelStateRoot(eng, state).incremental_root() == root
+    sroot = StorageRoot(eng, key3, state.storages[key3]).root()
+    o = oracle.storage_roots(np.frombuffer(b"".join(sorted(storage)), np.uint8).reshape(-1, 32),
+                             np.frombuffer(b"".join(int(storage[k]).to_bytes(32, "big") for k in sorted(storage)),
+                                           np.uint8).reshape(-1, 32), [0, 4])
+    assert sroot == o[0].tobytes()
+
+
+def test_storage_root_empty_and_zero_values(eng):
+    from reth_b200 import HashedStorageSorted
+    r, walked, upd = StorageRoot(eng, b"\x01" * 32, HashedStorageSorted([])).root_with_updates()
+    assert r == EMPTY_ROOT_HASH and walked == 0 and upd.is_deleted
+    # zero-valued slots are deletions: a storage holding only zeros is empty
+    r2, _, _ = StorageRoot(eng, b"\x01" * 32, HashedStorageSorted([(b"\x05" * 32, 0)])).root_with_updates()
+    assert r2 == EMPTY_ROOT_HASH
+
+
+def test_hashing_and_merkle_stages_on_genesis(eng, golden_allocs):
+    """The three stages of HashingStages (crates/stages/stages/src/sets.rs:427-442) over the holesky genesis alloc
+    (contract code + storage); MerkleStage validates against the stateRoot of the genesis file and fails loudly on
+    a wrong expectation (merkle.rs:437-453)."""
+    g = golden_allocs["holesky"]
+    t = Tables()
+    for addr, e in g["alloc"].items():
+        code = bytes.fromhex(e["code"][2:]) if e.get("code") else b""
+        t.plain_accounts[bytes.fromhex(addr)] = Account(
+            int(e.get("nonce", "0x0"), 16), int(e["balance"], 16), eng.keccak256(code) if code else None)
+        if e.get("storage"):
+            t.plain_storage[bytes.fromhex(addr)] = {int(k, 16): int(v, 16) for k, v in e["storage"].items()}
+    assert AccountHashingStage(eng).execute(t) == len(g["alloc"])
+    keys = [k for k, _ in t.hashed_accounts]
+    assert keys == sorted(keys)
+    StorageHashingStage(eng).execute(t)
+    root = MerkleStage(eng).execute(t, expected_state_root=bytes.fromhex(g["state_root"]))
+    assert root.hex() == g["state_root"]
+    assert t.trie_updates is not None and len(t.trie_updates.account_nodes) > 0
+    with pytest.raises(StageError):
+        MerkleStage(eng).execute(t, expected_state_root=b"\x00" * 32)
+    # same state through the flat path
+    assert eng.state_root_full(*alloc_to_flat(g["alloc"], keccak_rows=eng.keccak256_fixed)).hex() == g["state_root"]
+
+
+def test_destroyed_accounts_and_wiped_storage(eng):
+    """A destroyed account (None) disappears from the trie; construct_prefix_sets reports it and finalize marks its
+    storage trie deleted (updates.rs:153-157)."""
+    k1, k2 = b"\x11" * 32, b"\x22" * 32
+    st = HashedPostState(accounts={k1: Account(1, 1), k2: None},
+                         storages={k2: HashedStorage(True, {})})
+    sets = st.construct_prefix_sets().freeze()
+    root, updates = StateRoot(eng, st.into_sorted()).with_prefix_sets(sets).root_with_updates()
+    only = HashedPostState(accounts={k1: Account(1, 1)}).into_sorted()
+    assert root == StateRoot(eng, only).root()
+    assert updates.storage_tries[k2].is_deleted
