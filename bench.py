@@ -284,6 +284,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     eng = Engine(local_rank)
     # a dedicated (non-default) stream: torch events, NCCL and the engine's kernels are all ordered on it

@@ -23,7 +23,7 @@ using namespace b200;
 static thread_local int g_create_status = 0;
 
 // layout of the `small` device buffer (uint32 units)
-enum : int { SM_BUCKET_OFF = 0, SM_LEVEL_LO = 80, SM_NNODES = 160, SM_ERR = 164, SM_NSTORED = 168, SM_COUNTERS = 176 /* 4 x u64 */, SM_WORDS = 256 };
+enum : int { SM_BUCKET_OFF = 0, SM_LEVEL_LO = 80, SM_NNODES = 160, SM_ERR = 164, SM_NSTORED = 168, SM_COUNTERS = 176 /* 4 x u64 */, SM_HIST = 256 /* 256 x u32 */, SM_WORDS = 512 };
 
 static uint32_t *small_u32(b200_ctx *c) { return static_cast<uint32_t *>(c->small.p); }
 
@@ -396,10 +396,20 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
     CU(launch_head_flags(d_keys, depth_sorted, gap_sorted, bound_rank, bucket_off + 64, G, head, st));
     CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, head, node_start, n_nodes_p, (int64_t)G, st));
     CU(launch_level_ranges(node_start, n_nodes_p, bucket_off, level_lo, st));
-    c->launches += 8;
+    // (depth, child-count class) of every node + histogram, still without knowing the node count on the host
+    ENSURE(node_key, G);
+    ENSURE(node_ids, G * 4);
+    uint8_t *nk = static_cast<uint8_t *>(c->node_key.p);
+    uint32_t *nids = static_cast<uint32_t *>(c->node_ids.p);
+    uint32_t *hist = small_u32(c) + SM_HIST;
+    CU(cudaMemsetAsync(hist, 0, 256 * 4, st));
+    CU(launch_node_class_keys(node_start, depth_sorted, n_nodes_p, G, nk, nids, hist, st));
+    c->launches += 9;
     uint32_t *h_level = static_cast<uint32_t *>(c->pinned_small) + 64;
+    uint32_t *h_hist = static_cast<uint32_t *>(c->pinned_small) + 256;
     CU(cudaMemcpyAsync(h_level, level_lo, 66 * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));  // the only host round trip of a build: 66 integers
+    CU(cudaMemcpyAsync(h_hist, hist, 256 * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));  // the only host round trip of a build: 322 integers
     const uint32_t B = h_level[65];
     out.n_nodes = B;
     f.gap_sorted = gap_sorted;
@@ -418,30 +428,38 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
     f.node_masks = static_cast<ushort4 *>(c->node_masks.p);
 
     // ---- node visiting order: (depth descending, child-count class); ids stay what they are
-    ENSURE(node_key, B);
     ENSURE(node_key2, B);
-    ENSURE(node_ids, (size_t)B * 4);
     ENSURE(node_order, (size_t)B * 4);
-    uint8_t *nk = static_cast<uint8_t *>(c->node_key.p), *nk2 = static_cast<uint8_t *>(c->node_key2.p);
-    uint32_t *nids = static_cast<uint32_t *>(c->node_ids.p), *norder = static_cast<uint32_t *>(c->node_order.p);
-    CU(launch_node_class_keys(node_start, depth_sorted, B, nk, nids, st));
+    uint8_t *nk2 = static_cast<uint8_t *>(c->node_key2.p);
+    uint32_t *norder = static_cast<uint32_t *>(c->node_order.p);
     size_t t_ns = 0;
     CU(cub::DeviceRadixSort::SortPairs(nullptr, t_ns, nk, nk2, nids, norder, (int64_t)B, 0, 8, st));
     ENSURE(cub_temp, t_ns);
     CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_ns, nk, nk2, nids, norder, (int64_t)B, 0, 8, st));
-    c->launches += 2;
+    c->launches += 1;
 
-    // ---- deepest level first: one launch per populated level, the per-level frontier stays in HBM
+    // ---- deepest level first; the per-level frontier stays in HBM.  Big levels get one launch per child-count
+    // class (strip size and unrolling fit the class), small ones a single launch.
     uint32_t pos = 0;
     for (int d = 63; d >= 0; d--) {
-        uint32_t cnt = h_level[d + 1] - h_level[d];
-        if (cnt) {
-            CU(launch_branch_level(f, norder, pos, pos + cnt, d, st));
+        const uint32_t *hc = h_hist + 4 * (63 - d);
+        uint32_t cnt = hc[0] + hc[1] + hc[2] + hc[3];
+        if (!cnt) continue;
+        out.levels++;
+        if (cnt < 4096) {
+            CU(launch_branch_level(f, norder, pos, pos + cnt, d, 3, st));
             c->launches++;
-            out.levels++;
             pos += cnt;
+        } else {
+            for (int cls = 0; cls < 4; cls++) {
+                if (!hc[cls]) continue;
+                CU(launch_branch_level(f, norder, pos, pos + hc[cls], d, cls, st));
+                c->launches++;
+                pos += hc[cls];
+            }
         }
     }
+    if (pos != B) return fail(c, B200_ERR_CUDA, "internal: level histogram (%u) != node count (%u)", pos, B);
     return B200_OK;
 }
 

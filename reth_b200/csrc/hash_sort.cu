@@ -84,7 +84,7 @@ int32_t sort_digests_on_device(b200_ctx *c, const void *d_digests, uint64_t n, v
     CU(cudaMemsetAsync(flag.p, 0, 4, st));
     check_sorted_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const uint64_t *>(d_sorted), n, static_cast<int *>(flag.p));
     c->launches += 4;
-    int *h_flag = reinterpret_cast<int *>(static_cast<uint8_t *>(c->pinned_small) + 1024);
+    int *h_flag = reinterpret_cast<int *>(static_cast<uint8_t *>(c->pinned_small) + 3072);
     CU(cudaMemcpyAsync(h_flag, flag.p, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (*h_flag == 0) return B200_OK;

@@ -547,7 +547,82 @@ __device__ __forceinline__ uint32_t encode_extension(Strip<BLOCK> &s, const uint
     return list_header_len(payload) + payload;
 }
 
-template <int BLOCK>
+// Class-specialised variant of encode_branch: at most MAXC children, every per-child quantity lives in registers
+// and all the dependent global loads of a phase (gap -> S/E -> meta -> ref) are issued back to back for the
+// whole node before any of them is consumed, so one thread keeps up to MAXC requests in flight.
+template <int BLOCK, int MAXC>
+__device__ __forceinline__ uint32_t encode_branch_u(Strip<BLOCK> &s, const ForestDev &f, uint32_t j0, uint32_t k,
+                                                    uint32_t &state_mask, uint32_t &tree_mask, uint32_t &hash_mask,
+                                                    uint32_t &l, uint32_t &r) {
+    const uint32_t n = (uint32_t)f.n;
+    uint32_t g[MAXC - 1];
+#pragma unroll
+    for (int c = 0; c < MAXC - 1; c++) g[c] = (uint32_t)c < k ? f.gap_sorted[j0 + c] : 0u;
+    uint32_t id[MAXC], nm[MAXC];  // nm = nibble | meta << 8
+    id[0] = f.E[g[0] - 1];
+    nm[0] = f.nibs[g[0]] >> 4;
+#pragma unroll
+    for (int c = 1; c < MAXC; c++) {
+        id[c] = 0;
+        nm[c] = 0;
+        if ((uint32_t)c <= k) {
+            id[c] = f.S[g[c - 1]];
+            nm[c] = f.nibs[g[c - 1]] & 15;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; c++)
+        if ((uint32_t)c <= k) nm[c] |= (uint32_t)(id[c] < n ? f.leaf_meta[id[c]] : f.node_meta[id[c] - n]) << 8;
+    uint32_t payload = 17;
+    state_mask = tree_mask = hash_mask = 0;
+    uint32_t last = id[0];
+#pragma unroll
+    for (int c = 0; c < MAXC; c++) {
+        if ((uint32_t)c <= k) {
+            uint32_t meta = nm[c] >> 8;
+            payload += ((meta & META_LEN) ? (meta & META_LEN) : 33u) - 1;
+            uint32_t bit = 1u << (nm[c] & 15);
+            state_mask |= bit;
+            if (id[c] >= n) {
+                if (!(meta & META_EXT)) {
+                    hash_mask |= bit;
+                    if ((meta & META_LEN) && f.retain_updates) atomicExch(f.err, B200_DEVERR_INLINE_HASH_CHILD);
+                }
+                if (meta & META_STORED) tree_mask |= bit;
+            }
+            last = id[c];
+        }
+    }
+    l = id[0] < n ? id[0] : f.node_l[id[0] - n];
+    r = last < n ? last : f.node_r[last - n];
+    put_list_header(s, payload);
+    uint32_t cur = 0;
+#pragma unroll
+    for (int c = 0; c < MAXC; c++) {
+        if ((uint32_t)c <= k) {
+            const uint8_t *rp = id[c] < n ? f.leaf_ref + 32 * (uint64_t)id[c] : f.node_ref + 32 * (uint64_t)(id[c] - n);
+            uint32_t ref[8];
+            load32_nc(rp, ref);
+            uint32_t nibble = nm[c] & 15;
+            for (; cur < nibble; cur++) s.byte(0x80);
+            uint32_t clen = (nm[c] >> 8) & META_LEN;
+            if (clen == 0) {
+                s.byte(0xa0);
+                s.words8(ref);
+            } else {
+                for (uint32_t b = 0; b < clen; b++) s.byte(byte_at(ref, b));
+            }
+            cur++;
+        }
+    }
+    for (; cur < 16; cur++) s.byte(0x80);
+    s.byte(0x80);  // value slot
+    return list_header_len(payload) + payload;
+}
+
+// One thread per branch node of depth d.  MAXC bounds the children of every node in [pos_lo, pos_hi) (the level's
+// nodes are grouped by child-count class); the strip is sized for that class, which is what sets the occupancy.
+template <int BLOCK, int MAXC>
 __global__ void __launch_bounds__(BLOCK) branch_kernel(ForestDev f, const uint32_t *__restrict__ node_order,
                                                        uint32_t pos_lo, uint32_t pos_hi, int d) {
     extern __shared__ uint32_t smem[];
@@ -556,13 +631,12 @@ __global__ void __launch_bounds__(BLOCK) branch_kernel(ForestDev f, const uint32
     uint32_t hashed = 0, exts = 0;
     const uint32_t step = gridDim.x * BLOCK;
     for (uint64_t p64 = (uint64_t)pos_lo + blockIdx.x * BLOCK + threadIdx.x; p64 < pos_hi; p64 += step) {
-        // nodes of a level are visited grouped by child-count class, so the lanes of a warp absorb the same
-        // number of rate blocks (1..4) and do not wait on each other
         uint32_t v = __ldg(node_order + p64);
         s.init(smem);
         uint32_t j0 = f.node_start[v], k = f.node_start[v + 1] - j0;
+        if (k + 1 > (uint32_t)MAXC) k = MAXC - 1;  // cannot happen for well-formed input; keeps the strip in bounds
         uint32_t state_mask, tree_mask, hash_mask, l, r;
-        uint32_t len = encode_branch(s, f, j0, k, state_mask, tree_mask, hash_mask, l, r);
+        uint32_t len = encode_branch_u<BLOCK, MAXC>(s, f, j0, k, state_mask, tree_mask, hash_mask, l, r);
         int pdl = depth_of(f.Lp[l]), pdr = depth_of(f.Lp[(uint64_t)r + 1]);
         int pd = pdl > pdr ? pdl : pdr;
         bool is_root = pd < 0;
@@ -877,31 +951,57 @@ cudaError_t launch_leaves(const ForestDev &f, bool account, const uint8_t *value
     return cudaGetLastError();
 }
 
-cudaError_t launch_branch_level(const ForestDev &f, const uint32_t *node_order, uint32_t pos_lo, uint32_t pos_hi,
-                                int d, cudaStream_t st) {
-    if (pos_hi <= pos_lo) return cudaSuccess;
-    auto k = branch_kernel<BRANCH_BLOCK>;
-    size_t smem = (size_t)BRANCH_WORDS * BRANCH_BLOCK * 4;
+template <int MAXC, int WORDS>
+static cudaError_t launch_branch_class(const ForestDev &f, const uint32_t *node_order, uint32_t pos_lo, uint32_t pos_hi,
+                                       int d, cudaStream_t st) {
+    auto k = branch_kernel<BRANCH_BLOCK, MAXC>;
+    size_t smem = (size_t)WORDS * BRANCH_BLOCK * 4;
     k<<<persistent_grid(k, BRANCH_BLOCK, smem, pos_hi - pos_lo), BRANCH_BLOCK, smem, st>>>(f, node_order, pos_lo,
                                                                                           pos_hi, d);
     return cudaGetLastError();
 }
 
+// cls: child-count class of every node in the range (0: <=3, 1: <=7, 2: <=12, 3: <=16 children), or 3 for a
+// mixed range.  The extension wrapper (<= 70 bytes) fits the smallest strip.
+cudaError_t launch_branch_level(const ForestDev &f, const uint32_t *node_order, uint32_t pos_lo, uint32_t pos_hi,
+                                int d, int cls, cudaStream_t st) {
+    if (pos_hi <= pos_lo) return cudaSuccess;
+    switch (cls) {
+        case 0: return launch_branch_class<3, 34>(f, node_order, pos_lo, pos_hi, d, st);
+        case 1: return launch_branch_class<7, 68>(f, node_order, pos_lo, pos_hi, d, st);
+        case 2: return launch_branch_class<12, 102>(f, node_order, pos_lo, pos_hi, d, st);
+        default: return launch_branch_class<16, BRANCH_WORDS>(f, node_order, pos_lo, pos_hi, d, st);
+    }
+}
+
 // sort key of node v: deepest level first, then by the number of rate blocks its RLP needs when every child
 // is a 33-byte hash reference (children <= 3 -> 1 block, <= 7 -> 2, <= 12 -> 3, else 4)
+// hist[key] counts the nodes of every (depth, class); runs before the host knows the node count, hence the
+// device-side bound.
 __global__ void node_class_keys_kernel(const uint32_t *__restrict__ node_start, const uint8_t *__restrict__ depth_sorted,
-                                       uint32_t n_nodes, uint8_t *__restrict__ keys, uint32_t *__restrict__ ids) {
-    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_nodes) return;
-    uint32_t j0 = node_start[v], children = node_start[v + 1] - j0 + 1;
-    uint32_t cls = children <= 3 ? 0 : (children <= 7 ? 1 : (children <= 12 ? 2 : 3));
-    keys[v] = (uint8_t)(((63u - depth_sorted[j0]) << 2) | cls);
-    ids[v] = v;
+                                       const uint32_t *__restrict__ n_nodes_p, uint8_t *__restrict__ keys,
+                                       uint32_t *__restrict__ ids, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n_nodes = *n_nodes_p;
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_nodes; v += gridDim.x * blockDim.x) {
+        uint32_t j0 = node_start[v], children = node_start[v + 1] - j0 + 1;
+        uint32_t cls = children <= 3 ? 0 : (children <= 7 ? 1 : (children <= 12 ? 2 : 3));
+        uint32_t key = ((63u - depth_sorted[j0]) << 2) | cls;
+        keys[v] = (uint8_t)key;
+        ids[v] = v;
+        atomicAdd(&sh[key], 1u);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
-cudaError_t launch_node_class_keys(const uint32_t *node_start, const uint8_t *depth_sorted, uint32_t n_nodes,
-                                   uint8_t *keys, uint32_t *ids, cudaStream_t st) {
-    if (n_nodes == 0) return cudaSuccess;
-    node_class_keys_kernel<<<blocks_for(n_nodes, 256), 256, 0, st>>>(node_start, depth_sorted, n_nodes, keys, ids);
+cudaError_t launch_node_class_keys(const uint32_t *node_start, const uint8_t *depth_sorted, const uint32_t *n_nodes_p,
+                                   uint64_t max_nodes, uint8_t *keys, uint32_t *ids, uint32_t *hist, cudaStream_t st) {
+    if (max_nodes == 0) return cudaSuccess;
+    unsigned blocks = blocks_for(max_nodes, 256);
+    if (blocks > (unsigned)sms() * 8) blocks = (unsigned)sms() * 8;
+    node_class_keys_kernel<<<blocks, 256, 0, st>>>(node_start, depth_sorted, n_nodes_p, keys, ids, hist);
     return cudaGetLastError();
 }
 

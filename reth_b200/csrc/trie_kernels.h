@@ -83,9 +83,9 @@ cudaError_t launch_level_ranges(uint32_t *node_start, const uint32_t *n_nodes_p,
 cudaError_t launch_leaves(const ForestDev &f, bool account, const uint8_t *values, const uint8_t *storage_roots,
                           cudaStream_t st);
 cudaError_t launch_branch_level(const ForestDev &f, const uint32_t *node_order, uint32_t pos_lo, uint32_t pos_hi,
-                                int d, cudaStream_t st);
-cudaError_t launch_node_class_keys(const uint32_t *node_start, const uint8_t *depth_sorted, uint32_t n_nodes,
-                                   uint8_t *keys, uint32_t *ids, cudaStream_t st);
+                                int d, int cls, cudaStream_t st);
+cudaError_t launch_node_class_keys(const uint32_t *node_start, const uint8_t *depth_sorted, const uint32_t *n_nodes_p,
+                                   uint64_t max_nodes, uint8_t *keys, uint32_t *ids, uint32_t *hist, cudaStream_t st);
 cudaError_t launch_segment_roots(const ForestDev &f, const uint64_t *d_seg_offsets, uint64_t n_segs, uint8_t *roots,
                                  cudaStream_t st);
 cudaError_t launch_stored_flags(const ForestDev &f, uint32_t n_nodes, uint8_t *flags, uint32_t *n_hashes,

@@ -54,6 +54,8 @@ __global__ void probe(uint32_t *out, unsigned long long *cycles, int ITER) {
 #define RIb(i) asm volatile("lop3.b32 %0, %0, %1, 0x0f0f4321, 0xd2;" : "+r"(b[i]) : "r"(a[i]))
 #define X2a(i) asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i]))
 #define X2b(i) asm volatile("xor.b32 %0, %0, %1;" : "+r"(b[i]) : "r"(a[i]))
+#define H3(i) asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(c[i]) : "r"(a[i]), "r"(m0))
+#define M4(i) asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(c[i]) : "r"(b[i]), "r"(m1), "r"(c[i]))
 #define ALL(X) X(0); X(1); X(2); X(3); X(4); X(5); X(6); X(7)
         if (MODE == 0) { ALL(L1); ALL(L2); }
         else if (MODE == 1) { ALL(S1); ALL(S2); }
@@ -70,6 +72,9 @@ __global__ void probe(uint32_t *out, unsigned long long *cycles, int ITER) {
         else if (MODE == 12) { ALL(L1); ALL(F1); ALL(L2); ALL(F1); }
         else if (MODE == 13) { ALL(F1); ALL(F1); }
         else if (MODE == 14) { ALL(L1); ALL(S1); ALL(L2); ALL(M3); }
+        else if (MODE == 15) { ALL(L1); ALL(H3); ALL(L2); }
+        else if (MODE == 16) { ALL(L1); ALL(L2); ALL(H3); ALL(L1); ALL(L2); ALL(M4); }
+        else if (MODE == 17) { ALL(L1); ALL(L2); ALL(H3); ALL(L1); ALL(M4); }
         else if (MODE == 20) { ALL(R3a); ALL(R3b); }
         else if (MODE == 21) { ALL(R2a); ALL(R2b); }
         else if (MODE == 22) { ALL(RIa); ALL(RIb); }
@@ -128,7 +133,7 @@ int main() {
     uint32_t mul[8] = {8, 1u << 13, 3, 5, 7, 9, 11, 13};
     cudaMemcpyToSymbol(MUL, mul, sizeof mul);
     printf("SMs=%d\n", sms);
-    for (int w : {8, 16, 32, 64}) {
+    for (int w : {8, 16, 24}) {
         run<0>("LOP3 (2 reg + uniform)", 2, sms, w);
         run<20>("LOP3 (3 distinct regs)", 2, sms, w);
         run<21>("LOP3 (2 distinct regs)", 2, sms, w);
@@ -148,6 +153,9 @@ int main() {
         run<12>("2 LOP3 + 2 FFMA", 4, sms, w);
         run<14>("2 LOP3 + 1 SHF + 1 IMAD", 4, sms, w);
         run<3>("2 LOP3 + 1 IMAD.WIDE", 3, sms, w);
+        run<15>("2 LOP3 + 1 IMAD.HI", 3, sms, w);
+        run<16>("4 LOP3 + 1 IMAD.HI + 1 IMAD", 6, sms, w);
+        run<17>("3 LOP3 + 1 IMAD.HI + 1 IMAD", 5, sms, w);
     }
     return 0;
 }
