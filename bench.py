@@ -267,6 +267,9 @@ def main():
     ap.add_argument("--keys", type=int, default=C2_KEYS, help="keys per GPU for the keccak workload")
     ap.add_argument("--accounts", type=int, default=C3_ACCOUNTS, help="accounts per GPU for the state-root workload")
     ap.add_argument("--skip-state-root", action="store_true")
+    ap.add_argument("--base-accounts", type=int, default=100_000_000, help="resident base trie of the incremental (C5) leg")
+    ap.add_argument("--dirty", type=int, default=10_000, help="dirty accounts per incremental update")
+    ap.add_argument("--skip-incremental", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -378,6 +381,10 @@ def main():
     if not args.skip_state_root:
         state_root = bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks)
 
+    incremental = None
+    if not args.skip_incremental and world == 1:
+        incremental = bench_incremental(args, eng, dev)
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_keccak_baseline()
@@ -393,7 +400,8 @@ def main():
                        "keys_per_gpu": n, "msg_len": 32, "parallelism": f"keys sharded over {world} GPU(s), no collective",
                        "l2": "input 320 MB + output 320 MB per step exceed the 126 MB L2; no flush needed"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
-            "cpu_baseline": cpu, "state_root": state_root, "parity_spot_check": parity_ok,
+            "cpu_baseline": cpu, "state_root": state_root, "incremental": incremental,
+            "parity_spot_check": parity_ok,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -472,6 +480,83 @@ def bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks):
                       "h2d_bytes_per_step": int(sum(v.nbytes for v in h.values())), "d2h_bytes_per_step": 32,
                       "root_matches_device_run": root.hex() == res["root"],
                       "api": "b200_state_root_full (host pointers, page-locked)"}
+    return res
+
+
+def bench_incremental(args, eng, dev):
+    """BASELINE config 5: a resident base trie of --base-accounts accounts (no storage), then updates of --dirty random
+    existing accounts (new balance + nonce).  Reports the root latency of one update (device-resident dirty set) and
+    the same through the host-pointer C ABI."""
+    import torch
+    from reth_b200 import ResidentTrie
+    n, m = args.base_accounts, args.dirty
+    try:
+        keys = random_keys_torch(5, n, dev)
+        order = torch.sort(be_sort_key(keys), stable=True).indices
+        keys = keys[order].contiguous()
+        del order
+        accts = torch.zeros((n, 72), dtype=torch.uint8, device=dev)
+        w = splitmix64_torch(5 ^ 0xACC0, n, dev)
+        accts[:, 8 + 24:8 + 32] = w.view(torch.uint8).view(n, 8)  # balance < 2^64
+        accts[:, 40:72] = torch.frombuffer(bytearray(bytes.fromhex(
+            "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470")), dtype=torch.uint8).to(dev)
+        del w
+        d_root = torch.zeros(32, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        trie = ResidentTrie.create_dev(eng, keys.view(torch.uint8).view(-1), accts.view(-1), None, n, d_root)
+        torch.cuda.synchronize()
+        build_s = time.perf_counter() - t0
+    except (RuntimeError, Exception) as e:  # noqa: BLE001 - out of memory on a smaller part: report, do not die
+        return {"error": f"{type(e).__name__}: {e}"[:300], "base_leaves": n}
+    base_root = bytes(d_root.cpu().numpy()).hex()
+    g = torch.Generator(device=dev)
+    g.manual_seed(55)
+    lat = []
+    d_new_root = torch.zeros(32, dtype=torch.uint8, device=dev)
+    reps = 12
+    for it in range(reps):
+        idx = torch.randperm(n, generator=g, device=dev)[:m] if n < 50_000_000 else \
+            torch.unique(torch.randint(0, n, (m + m // 8,), generator=g, device=dev))[:m]
+        mm = int(idx.numel())
+        dk = keys[idx].contiguous().view(torch.uint8).view(-1)
+        da = accts[idx].clone()
+        da[:, 0] = it + 1                       # nonce
+        da[:, 8 + 24:8 + 32] = torch.randint(0, 255, (mm, 8), generator=g, device=dev, dtype=torch.uint8)
+        da = da.view(-1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        trie.update_dev(dk, da, None, mm, d_new_root)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if it >= 2:
+            lat.append((e0.elapsed_time(e1) * 1e3, wall * 1e6))
+    stats = eng.last_stats()
+    dev_us = float(np.median([a for a, _ in lat]))
+    wall_us = float(np.median([b for _, b in lat]))
+    # host-pointer path (H2D of the dirty set + D2H of the root inside the call)
+    hk = dk.view(mm, 32).cpu().numpy()
+    ha = da.view(mm, 72).cpu().numpy().view(eng_account_dtype()).reshape(-1)
+    eng.set_stream(None)
+    trie.update(hk, ha)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        root = trie.update(hk, ha)
+    e2e_us = (time.perf_counter() - t0) / 5 * 1e6
+    eng.use_torch_stream()
+    res = {"metric": "incremental_root_latency_us", "value": wall_us, "unit": "us", "device_us": dev_us,
+           "e2e_us": e2e_us, "base_leaves": n, "dirty_accounts": mm, "dirty_leaves_per_sec": mm / (wall_us * 1e-6),
+           "base_build_ms": build_s * 1e3, "base_root": base_root, "root_after": root.hex(),
+           "rehashed_branch_nodes": stats["branches_added"], "levels": stats["levels"],
+           "resident_bytes": trie.device_bytes(),
+           "config": {"workload": f"C5: {mm}-account dirty set against a resident {n}-leaf base trie, "
+                                  "value changes of existing accounts, root path re-hash only"}}
+    trie.close()
+    del keys, accts
+    torch.cuda.empty_cache()
     return res
 
 

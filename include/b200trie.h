@@ -44,8 +44,9 @@ typedef enum {
     B200_ERR_ZERO_VALUE = -5,  /* a storage slot with value 0: reth treats zero as deletion
                                   (crates/trie/common/src/hashed_state.rs:423-455), it is never a leaf */
     B200_ERR_OOM = -6,
-    B200_ERR_INLINE_HASH_CHILD = -7 /* a <32-byte branch child under a hash_mask bit while retaining updates:
-                                       alloy-trie's child_hashes would panic here; unreachable for keccak keys */
+    B200_ERR_INLINE_HASH_CHILD = -7, /* a <32-byte branch child under a hash_mask bit while retaining updates:
+                                        alloy-trie's child_hashes would panic here; unreachable for keccak keys */
+    B200_ERR_NOT_FOUND = -8 /* b200_trie_update: a dirty key is not in the resident trie */
 } b200_status;
 
 /* ------------------------------------------------------------------------------------------------ lifecycle */
@@ -205,6 +206,34 @@ B200_API int32_t b200_subtrie_frontier_dev(b200_ctx *, const void *d_acct_keys32
  * 17 node hashes at most; runs on the device like everything else. */
 B200_API int32_t b200_root_from_frontier(b200_ctx *, const b200_frontier_entry frontier[16], uint8_t root32[32]);
 B200_API int32_t b200_root_from_frontier_dev(b200_ctx *, const void *d_frontier, void *d_root32);
+
+/* ------------------------------------------------------------------------------------------------ resident trie
+ * Incremental state root (BASELINE config 5; reth: StateRoot::with_prefix_sets over stored branch nodes,
+ * crates/trie/trie/src/walker.rs:172-202, node_iter.rs:205-300, DatabaseStateRoot::incremental_root_with_updates
+ * crates/trie/db/src/state.rs:184-193).  The whole account trie — keys, accounts, storage roots and the node-hash
+ * frontier of every level — stays in HBM; an update re-hashes only the root paths of the dirty accounts.
+ *
+ * Scope: value changes of EXISTING accounts (nonce / balance / code hash / storage root).  A key that is not in the
+ * trie yields B200_ERR_NOT_FOUND and leaves the trie untouched (inserts and deletes change the trie shape: rebuild).
+ * Dirty keys of one call must be distinct.  Storage roots of dirty accounts are computed by the caller with
+ * b200_storage_roots over their complete post-state storage. */
+typedef struct b200_trie b200_trie;
+B200_API int32_t b200_trie_create(b200_ctx *, const uint8_t *acct_keys32, const b200_account *accts,
+                                  const uint8_t *storage_roots32 /* nullable: all EMPTY_ROOT_HASH, not updatable */,
+                                  uint64_t n, b200_trie **out, uint8_t root32[32]);
+B200_API int32_t b200_trie_create_dev(b200_ctx *, const void *d_acct_keys32, const void *d_accts,
+                                      const void *d_storage_roots32, uint64_t n, b200_trie **out, void *d_root32);
+/* opt_updates: the stored BranchNodeCompact records on the dirty paths (what HashBuilder re-emits when reth
+ * re-walks them), same format as above. */
+B200_API int32_t b200_trie_update(b200_trie *, const uint8_t *dirty_keys32, const b200_account *new_accts,
+                                  const uint8_t *new_storage_roots32 /* nullable: unchanged */, uint64_t m,
+                                  uint8_t root32[32], b200_updates *opt_updates, b200_stats *opt_stats);
+B200_API int32_t b200_trie_update_dev(b200_trie *, const void *d_dirty_keys32, const void *d_new_accts,
+                                      const void *d_new_storage_roots32, uint64_t m, void *d_root32);
+B200_API int32_t b200_trie_root(b200_trie *, uint8_t root32[32]);
+B200_API uint64_t b200_trie_device_bytes(const b200_trie *);
+B200_API uint64_t b200_trie_leaves(const b200_trie *);
+B200_API void b200_trie_destroy(b200_trie *);
 
 #ifdef __cplusplus
 }

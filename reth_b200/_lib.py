@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200trie.so")
 
 # b200_status (include/b200trie.h)
-OK, ERR_NO_DEVICE, ERR_CUDA, ERR_INVALID_ARG, ERR_UNSORTED, ERR_ZERO_VALUE, ERR_OOM, ERR_INLINE_HASH_CHILD = (
-    0, -1, -2, -3, -4, -5, -6, -7)
+OK, ERR_NO_DEVICE, ERR_CUDA, ERR_INVALID_ARG, ERR_UNSORTED, ERR_ZERO_VALUE, ERR_OOM, ERR_INLINE_HASH_CHILD, \
+    ERR_NOT_FOUND = (0, -1, -2, -3, -4, -5, -6, -7, -8)
 
 
 class B200Error(RuntimeError):
@@ -115,5 +115,13 @@ def load():
     sig("b200_subtrie_frontier_dev", i32, vp, vp, vp, u64, vp, vp, vp, u64, vp)
     sig("b200_root_from_frontier", i32, vp, C.POINTER(FrontierEntry), vp)
     sig("b200_root_from_frontier_dev", i32, vp, vp, vp)
+    sig("b200_trie_create", i32, vp, vp, vp, vp, u64, C.POINTER(vp), vp)
+    sig("b200_trie_create_dev", i32, vp, vp, vp, vp, u64, C.POINTER(vp), vp)
+    sig("b200_trie_update", i32, vp, vp, vp, vp, u64, vp, PU, PS)
+    sig("b200_trie_update_dev", i32, vp, vp, vp, vp, u64, vp)
+    sig("b200_trie_root", i32, vp, vp)
+    sig("b200_trie_device_bytes", u64, vp)
+    sig("b200_trie_leaves", u64, vp)
+    sig("b200_trie_destroy", None, vp)
     _lib = L
     return L

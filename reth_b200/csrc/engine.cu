@@ -85,6 +85,7 @@ extern "C" B200_API void b200_destroy(b200_ctx *c) {
     if (c->pinned_small) cudaFreeHost(c->pinned_small);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : c->chunk_events) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++)
         if (c->copy_streams[i]) cudaStreamDestroy(c->copy_streams[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -125,6 +126,7 @@ static int32_t map_dev_error(b200_ctx *c, int code) {
         case B200_DEVERR_INLINE_HASH_CHILD:
             return fail(c, B200_ERR_INLINE_HASH_CHILD, "inline (<32 byte) branch child under a hash_mask bit");
         case B200_DEVERR_BAD_OFFSETS: return fail(c, B200_ERR_INVALID_ARG, "seg_offsets must start at 0, end at n and be monotone");
+        case B200_DEVERR_NOT_FOUND: return fail(c, B200_ERR_NOT_FOUND, "key not found in the resident trie");
         default: return fail(c, B200_ERR_CUDA, "unknown device error %d", code);
     }
 }
@@ -480,6 +482,58 @@ extern "C" B200_API void b200_updates_release(b200_updates *u) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Gathers the records of `n_stored` stored nodes (ids on the device) into `u` (host, page-locked).
+static int32_t gather_and_copy(b200_ctx *c, const ForestDev &f, const uint32_t *d_stored_ids, uint32_t n_stored,
+                               uint32_t n_hashes, const uint32_t *d_prefix_by_node, const uint32_t *d_prefix_by_record,
+                               const uint64_t *d_seg_offsets, uint64_t n_segs, b200_updates *u, UpdatesOwner *owner) {
+    cudaStream_t st = c->stream;
+    // one device block + one pinned host block, same layout
+    size_t o_tid = 0;
+    size_t o_plen = align_up(o_tid + (size_t)n_stored * 4, 16);
+    size_t o_path = align_up(o_plen + n_stored, 16);
+    size_t o_sm = align_up(o_path + (size_t)n_stored * 32, 16);
+    size_t o_tm = align_up(o_sm + (size_t)n_stored * 2, 16);
+    size_t o_hm = align_up(o_tm + (size_t)n_stored * 2, 16);
+    size_t o_ho32 = align_up(o_hm + (size_t)n_stored * 2, 16);
+    size_t o_hash = align_up(o_ho32 + (size_t)n_stored * 4, 16);
+    size_t o_ho64 = align_up(o_hash + (size_t)n_hashes * 32, 16);
+    size_t dev_total = o_ho64;
+    size_t host_total = o_ho64 + ((size_t)n_stored + 1) * 8;
+    CU(cudaMallocHost(&owner->host, host_total ? host_total : 16));
+    uint8_t *h = static_cast<uint8_t *>(owner->host);
+    u->n_nodes = n_stored;
+    u->trie_id = reinterpret_cast<uint32_t *>(h + o_tid);
+    u->path_len = h + o_plen;
+    u->path_packed = h + o_path;
+    u->state_mask = reinterpret_cast<uint16_t *>(h + o_sm);
+    u->tree_mask = reinterpret_cast<uint16_t *>(h + o_tm);
+    u->hash_mask = reinterpret_cast<uint16_t *>(h + o_hm);
+    u->hashes = h + o_hash;
+    u->hash_offset = reinterpret_cast<uint64_t *>(h + o_ho64);
+    if (n_stored) {
+        ENSURE(out_a, dev_total);
+        uint8_t *d = static_cast<uint8_t *>(c->out_a.p);
+        UpdatesDev ud;
+        ud.trie_id = reinterpret_cast<uint32_t *>(d + o_tid);
+        ud.path_len = d + o_plen;
+        ud.path_packed = d + o_path;
+        ud.state_mask = reinterpret_cast<uint16_t *>(d + o_sm);
+        ud.tree_mask = reinterpret_cast<uint16_t *>(d + o_tm);
+        ud.hash_mask = reinterpret_cast<uint16_t *>(d + o_hm);
+        ud.hash_offset = reinterpret_cast<uint32_t *>(d + o_ho32);
+        ud.hashes = d + o_hash;
+        CU(launch_gather_updates(f, d_stored_ids, n_stored, d_prefix_by_node, d_prefix_by_record, d_seg_offsets, n_segs,
+                                 ud, st));
+        c->launches++;
+        CU(cudaMemcpyAsync(h, d, dev_total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const uint32_t *ho32 = reinterpret_cast<const uint32_t *>(h + o_ho32);
+        for (uint32_t i = 0; i < n_stored; i++) u->hash_offset[i] = ho32[i];
+    }
+    u->hash_offset[n_stored] = n_hashes;
+    return B200_OK;
+}
+
 // Collects the stored BranchNodeCompact records of a finished build into `u` (host, page-locked).
 static int32_t collect_updates(b200_ctx *c, const Built &b, const uint64_t *d_seg_offsets, uint64_t n_segs,
                                b200_updates *u) {
@@ -516,51 +570,49 @@ static int32_t collect_updates(b200_ctx *c, const Built &b, const uint64_t *d_se
         n_stored = ps[200];
         n_hashes = ps[201] + ps[202];
     }
-    // one device block + one pinned host block, same layout
-    size_t o_tid = 0;
-    size_t o_plen = align_up(o_tid + (size_t)n_stored * 4, 16);
-    size_t o_path = align_up(o_plen + n_stored, 16);
-    size_t o_sm = align_up(o_path + (size_t)n_stored * 32, 16);
-    size_t o_tm = align_up(o_sm + (size_t)n_stored * 2, 16);
-    size_t o_hm = align_up(o_tm + (size_t)n_stored * 2, 16);
-    size_t o_ho32 = align_up(o_hm + (size_t)n_stored * 2, 16);
-    size_t o_hash = align_up(o_ho32 + (size_t)n_stored * 4, 16);
-    size_t o_ho64 = align_up(o_hash + (size_t)n_hashes * 32, 16);
-    size_t dev_total = o_ho64;
-    size_t host_total = o_ho64 + ((size_t)n_stored + 1) * 8;
-    CU(cudaMallocHost(&owner->host, host_total ? host_total : 16));
-    uint8_t *h = static_cast<uint8_t *>(owner->host);
-    u->n_nodes = n_stored;
-    u->trie_id = reinterpret_cast<uint32_t *>(h + o_tid);
-    u->path_len = h + o_plen;
-    u->path_packed = h + o_path;
-    u->state_mask = reinterpret_cast<uint16_t *>(h + o_sm);
-    u->tree_mask = reinterpret_cast<uint16_t *>(h + o_tm);
-    u->hash_mask = reinterpret_cast<uint16_t *>(h + o_hm);
-    u->hashes = h + o_hash;
-    u->hash_offset = reinterpret_cast<uint64_t *>(h + o_ho64);
-    if (n_stored) {
-        ENSURE(out_a, dev_total);
-        uint8_t *d = static_cast<uint8_t *>(c->out_a.p);
-        UpdatesDev ud;
-        ud.trie_id = reinterpret_cast<uint32_t *>(d + o_tid);
-        ud.path_len = d + o_plen;
-        ud.path_packed = d + o_path;
-        ud.state_mask = reinterpret_cast<uint16_t *>(d + o_sm);
-        ud.tree_mask = reinterpret_cast<uint16_t *>(d + o_tm);
-        ud.hash_mask = reinterpret_cast<uint16_t *>(d + o_hm);
-        ud.hash_offset = reinterpret_cast<uint32_t *>(d + o_ho32);
-        ud.hashes = d + o_hash;
-        CU(launch_gather_updates(b.f, static_cast<uint32_t *>(c->upd_ids.p), n_stored,
-                                 static_cast<uint32_t *>(c->upd_prefix.p), d_seg_offsets, n_segs, ud, st));
-        c->launches++;
-        CU(cudaMemcpyAsync(h, d, dev_total, cudaMemcpyDeviceToHost, st));
+    return gather_and_copy(c, b.f, static_cast<uint32_t *>(c->upd_ids.p), n_stored, n_hashes,
+                           static_cast<uint32_t *>(c->upd_prefix.p), nullptr, d_seg_offsets, n_segs, u, owner);
+}
+
+// Same for a subset of nodes given by id (the dirty nodes of an incremental update), in list order.
+static int32_t collect_updates_subset(b200_ctx *c, const ForestDev &f, const uint32_t *d_ids, uint32_t count,
+                                      b200_updates *u) {
+    memset(u, 0, sizeof *u);
+    UpdatesOwner *owner = new UpdatesOwner();
+    u->_owner = owner;
+    cudaStream_t st = c->stream;
+    uint32_t n_stored = 0, n_hashes = 0;
+    uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
+    if (count) {
+        ENSURE(upd_flags, count);
+        ENSURE(upd_nh, (size_t)count * 4);
+        ENSURE(upd_ids, (size_t)count * 4 * 3);  // selected positions | picked ids | picked prefixes
+        ENSURE(upd_prefix, (size_t)(count + 1) * 4);
+        uint8_t *flags = static_cast<uint8_t *>(c->upd_flags.p);
+        uint32_t *nh = static_cast<uint32_t *>(c->upd_nh.p);
+        uint32_t *sel = static_cast<uint32_t *>(c->upd_ids.p), *pick_ids = sel + count, *pick_prefix = sel + 2 * (size_t)count;
+        uint32_t *prefix = static_cast<uint32_t *>(c->upd_prefix.p);
+        uint32_t *n_stored_p = small_u32(c) + SM_NSTORED;
+        CU(launch_stored_flags_subset(f, d_ids, count, flags, nh, st));
+        size_t t_sel = 0, t_scan = 0;
+        thrust::counting_iterator<uint32_t> counting(0);
+        CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, flags, sel, n_stored_p, (int64_t)count, st));
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, t_scan, nh, prefix, (int64_t)count, st));
+        ENSURE(cub_temp, std::max(t_sel, t_scan));
+        CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, flags, sel, n_stored_p, (int64_t)count, st));
+        CU(cub::DeviceScan::ExclusiveSum(c->cub_temp.p, t_scan, nh, prefix, (int64_t)count, st));
+        c->launches += 3;
+        CU(cudaMemcpyAsync(ps + 200, n_stored_p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ps + 201, prefix + (count - 1), 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ps + 202, nh + (count - 1), 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        const uint32_t *ho32 = reinterpret_cast<const uint32_t *>(h + o_ho32);
-        for (uint32_t i = 0; i < n_stored; i++) u->hash_offset[i] = ho32[i];
+        n_stored = ps[200];
+        n_hashes = ps[201] + ps[202];
+        CU(launch_pick_subset(d_ids, prefix, sel, n_stored, pick_ids, pick_prefix, st));
+        c->launches++;
+        return gather_and_copy(c, f, pick_ids, n_stored, n_hashes, nullptr, pick_prefix, nullptr, 0, u, owner);
     }
-    u->hash_offset[n_stored] = n_hashes;
-    return B200_OK;
+    return gather_and_copy(c, f, nullptr, 0, 0, nullptr, nullptr, nullptr, 0, u, owner);
 }
 
 // ------------------------------------------------------------------------------------------------ device-level drivers
@@ -712,6 +764,87 @@ extern "C" B200_API int32_t b200_state_root(b200_ctx *c, const uint8_t *acct_key
     return r;
 }
 
+// Host-pointer full state root without retained updates: the storage forest is cut into account ranges so that the
+// H2D copy of range k+1 (copy stream) overlaps the build of range k (compute stream).  PCIe moves ~1.1 GB for the C3
+// workload (≈20 ms) against ≈9 ms of hashing: the transfer is the critical path and the hashing hides under it.
+static int32_t state_root_full_pipelined(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
+                                         uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
+                                         const uint64_t *seg_offsets, uint64_t n_slots, uint8_t root32[32]) {
+    // chunk boundaries: ~n_slots/12 slots each, at least 1M
+    const uint64_t target = std::max<uint64_t>(n_slots / 12, 1ull << 20);
+    std::vector<uint64_t> cut{0};
+    for (uint64_t a = 1; a <= n_accounts; a++)
+        if (a == n_accounts || seg_offsets[a] - seg_offsets[cut.back()] >= target) cut.push_back(a);
+    const size_t n_chunks = cut.size() - 1;
+    // per-chunk offsets rebased to 0
+    std::vector<uint64_t> rel(n_accounts + n_chunks);
+    std::vector<uint64_t> rel_start(n_chunks);
+    {
+        uint64_t w = 0;
+        for (size_t k = 0; k < n_chunks; k++) {
+            rel_start[k] = w;
+            uint64_t s0 = seg_offsets[cut[k]];
+            for (uint64_t a = cut[k]; a <= cut[k + 1]; a++) rel[w++] = seg_offsets[a] - s0;
+        }
+    }
+    ENSURE(in_a, n_slots * 32);
+    ENSURE(in_b, n_slots * 32);
+    ENSURE(in_c, rel.size() * 8);
+    ENSURE(in_d, n_accounts * 32);
+    ENSURE(in_e, n_accounts * sizeof(b200_account));
+    ENSURE(sroots, n_accounts * 32 + 32);
+    while (c->chunk_events.size() < n_chunks + 1) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->chunk_events.push_back(e);
+    }
+    cudaStream_t cs = c->copy_streams[0];
+    CU(cudaStreamSynchronize(c->stream));  // scratch of an earlier call may still be in use
+    CU(cudaMemcpyAsync(c->in_c.p, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, cs));
+    uint8_t *d_keys = static_cast<uint8_t *>(c->in_a.p), *d_vals = static_cast<uint8_t *>(c->in_b.p);
+    for (size_t k = 0; k < n_chunks; k++) {
+        uint64_t s0 = seg_offsets[cut[k]], s1 = seg_offsets[cut[k + 1]];
+        if (s1 > s0) {
+            CU(cudaMemcpyAsync(d_keys + 32 * s0, slot_keys32 + 32 * s0, (s1 - s0) * 32, cudaMemcpyHostToDevice, cs));
+            CU(cudaMemcpyAsync(d_vals + 32 * s0, values32_be + 32 * s0, (s1 - s0) * 32, cudaMemcpyHostToDevice, cs));
+        }
+        CU(cudaEventRecord(c->chunk_events[k], cs));
+    }
+    CU(cudaMemcpyAsync(c->in_d.p, acct_keys32, n_accounts * 32, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(c->in_e.p, accts, n_accounts * sizeof(b200_account), cudaMemcpyHostToDevice, cs));
+    CU(cudaEventRecord(c->chunk_events[n_chunks], cs));
+
+    TRY(reset_build_state(c));
+    uint8_t *d_sroots = static_cast<uint8_t *>(c->sroots.p);
+    uint8_t *d_root = d_sroots + n_accounts * 32;
+    const uint64_t *d_rel = static_cast<const uint64_t *>(c->in_c.p);
+    int32_t r = B200_OK;
+    for (size_t k = 0; k < n_chunks && r == B200_OK; k++) {
+        uint64_t a0 = cut[k], a1 = cut[k + 1], s0 = seg_offsets[a0], s1 = seg_offsets[a1];
+        CU(cudaStreamWaitEvent(c->stream, c->chunk_events[k], 0));
+        Built b;
+        r = build_forest(c, d_keys + 32 * s0, s1 - s0, d_rel + rel_start[k], a1 - a0, false, d_vals + 32 * s0, nullptr,
+                         false, b);
+        if (r != B200_OK) break;
+        CU(launch_segment_roots(b.f, d_rel + rel_start[k], a1 - a0, d_sroots + 32 * a0, c->stream));
+        c->launches++;
+        c->stats.leaves_added += s1 - s0;
+        c->stats.branches_added += b.n_nodes;
+        c->stats.levels += b.levels;
+    }
+    if (r != B200_OK) {
+        cudaStreamSynchronize(cs);  // do not leave copies in flight into buffers a later call may resize
+        return r;
+    }
+    CU(cudaStreamWaitEvent(c->stream, c->chunk_events[n_chunks], 0));
+    Built ba;
+    TRY(account_root_on_device(c, static_cast<const uint8_t *>(c->in_d.p), static_cast<const uint8_t *>(c->in_e.p),
+                               d_sroots, n_accounts, d_root, false, ba));
+    TRY(finish_build_state(c));
+    CU(cudaMemcpyAsync(root32, d_root, 32, cudaMemcpyDeviceToHost, c->stream));
+    return sync_and_status(c);
+}
+
 extern "C" B200_API int32_t b200_state_root_full(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
                                         uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
                                         const uint64_t *seg_offsets, uint8_t root32[32],
@@ -727,6 +860,12 @@ extern "C" B200_API int32_t b200_state_root_full(b200_ctx *c, const uint8_t *acc
     const bool retain = opt_account_updates || opt_storage_updates;
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
+    if (!retain && n_slots >= (2ull << 20) && n_accounts >= 16) {
+        int32_t pr = state_root_full_pipelined(c, acct_keys32, accts, n_accounts, slot_keys32, values32_be, seg_offsets,
+                                               n_slots, root32);
+        if (opt_stats) *opt_stats = c->stats;
+        return pr;
+    }
     TRY(h2d(c, c->in_a, slot_keys32, n_slots * 32));
     TRY(h2d(c, c->in_b, values32_be, n_slots * 32));
     TRY(h2d(c, c->in_c, seg_offsets, (n_accounts + 1) * 8));
@@ -856,5 +995,292 @@ extern "C" B200_API int32_t b200_root_from_frontier_dev(b200_ctx *c, const void 
     CU(launch_root_from_frontier(static_cast<const FrontierEntryDev *>(d_frontier), static_cast<uint8_t *>(d_root32),
                                  c->stream));
     c->launches++;
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ resident trie (C5)
+// The account trie of a whole state kept in HBM — keys, accounts, storage roots and the node-hash frontier of every
+// level — so that a block's dirty accounts are committed by re-hashing only their root paths.  This is what reth
+// gets from stored branch nodes + prefix sets (crates/trie/trie/src/walker.rs:172-202, node_iter.rs:205-300):
+// untouched subtries are not revisited.  Scope: value changes of existing accounts (balance / nonce / code hash /
+// storage root); inserting or deleting a key changes the trie shape and is reported as B200_ERR_NOT_FOUND so the
+// caller rebuilds.
+struct b200_trie {
+    b200_ctx *c = nullptr;
+    uint64_t n = 0;
+    uint32_t B = 0;
+    ForestDev f{};
+    bool has_sroots = false;
+    uint64_t bytes = 0;
+    DevBuf keys, accts, sroots, Lp, nibs, leaf_ref, leaf_meta, S, E, gap_sorted, node_start, node_ref, node_meta, node_l,
+        node_r, node_masks, leaf_parent, node_parent, dirty, dirty_ids, dirty_key, dirty_key2, dirty_order, idx, in_keys,
+        in_accts, in_sroots, root;
+};
+
+static void steal(b200_trie *t, DevBuf &dst, DevBuf &src) {
+    dst = src;
+    src = DevBuf{};
+    t->c->dev_bytes -= dst.cap;
+    t->bytes += dst.cap;
+}
+static int32_t trie_alloc(b200_trie *t, DevBuf &b, size_t bytes) {
+    b200_ctx *c = t->c;
+    if (bytes <= b.cap) return B200_OK;
+    if (b.p) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(b.p));
+        t->bytes -= b.cap;
+        b = DevBuf{};
+    }
+    size_t want = bytes + 256;
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    t->bytes += want;
+    return B200_OK;
+}
+
+extern "C" B200_API void b200_trie_destroy(b200_trie *t) {
+    if (!t) return;
+    cudaSetDevice(t->c->device);
+    cudaStreamSynchronize(t->c->stream);
+    DevBuf *bufs[] = {&t->keys, &t->accts, &t->sroots, &t->Lp, &t->nibs, &t->leaf_ref, &t->leaf_meta, &t->S, &t->E,
+                      &t->gap_sorted, &t->node_start, &t->node_ref, &t->node_meta, &t->node_l, &t->node_r, &t->node_masks,
+                      &t->leaf_parent, &t->node_parent, &t->dirty, &t->dirty_ids, &t->dirty_key, &t->dirty_key2,
+                      &t->dirty_order, &t->idx, &t->in_keys, &t->in_accts, &t->in_sroots, &t->root};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    delete t;
+}
+extern "C" B200_API uint64_t b200_trie_device_bytes(const b200_trie *t) { return t ? t->bytes : 0; }
+extern "C" B200_API uint64_t b200_trie_leaves(const b200_trie *t) { return t ? t->n : 0; }
+
+// builds from device-resident inputs that the trie already owns (t->keys / accts / sroots)
+static int32_t trie_build_owned(b200_trie *t) {
+    b200_ctx *c = t->c;
+    TRY(reset_build_state(c));
+    Built b;
+    TRY(trie_alloc(t, t->root, 64));
+    TRY(account_root_on_device(c, static_cast<const uint8_t *>(t->keys.p), static_cast<const uint8_t *>(t->accts.p),
+                               t->has_sroots ? static_cast<const uint8_t *>(t->sroots.p) : nullptr, t->n,
+                               static_cast<uint8_t *>(t->root.p), true, b));
+    TRY(finish_build_state(c));
+    TRY(sync_and_status(c));
+    t->f = b.f;
+    t->B = b.n_nodes;
+    // the build's arrays become the trie's: same pointers, new owner; the context re-allocates on its next build
+    steal(t, t->Lp, c->Lp);
+    steal(t, t->nibs, c->nibs);
+    steal(t, t->leaf_ref, c->leaf_ref);
+    steal(t, t->leaf_meta, c->leaf_meta);
+    steal(t, t->S, c->S);
+    steal(t, t->E, c->E);
+    if (t->n >= 2) {
+        steal(t, t->gap_sorted, c->gap_sorted);
+        steal(t, t->node_start, c->node_start);
+    }
+    if (t->B) {
+        steal(t, t->node_ref, c->node_ref);
+        steal(t, t->node_meta, c->node_meta);
+        steal(t, t->node_l, c->node_l);
+        steal(t, t->node_r, c->node_r);
+        steal(t, t->node_masks, c->node_masks);
+    }
+    TRY(trie_alloc(t, t->leaf_parent, (t->n ? t->n : 1) * 4));
+    TRY(trie_alloc(t, t->node_parent, ((size_t)t->B + 1) * 4));
+    TRY(trie_alloc(t, t->dirty, ((size_t)t->B + 1) * 4));
+    CU(cudaMemsetAsync(t->leaf_parent.p, 0xFF, (t->n ? t->n : 1) * 4, c->stream));
+    CU(cudaMemsetAsync(t->node_parent.p, 0xFF, ((size_t)t->B + 1) * 4, c->stream));
+    CU(cudaMemsetAsync(t->dirty.p, 0, ((size_t)t->B + 1) * 4, c->stream));
+    CU(launch_parent_links(t->f, t->B, static_cast<uint32_t *>(t->leaf_parent.p),
+                           static_cast<uint32_t *>(t->node_parent.p), c->stream));
+    c->launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    return B200_OK;
+}
+
+static int32_t trie_create_common(b200_ctx *c, const void *keys, const void *accts, const void *sroots, uint64_t n,
+                                  cudaMemcpyKind kind, b200_trie **out, void *root_out) {
+    if (!c || !out || (n && (!keys || !accts))) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    b200_trie *t = new b200_trie();
+    t->c = c;
+    t->n = n;
+    t->has_sroots = sroots != nullptr;
+    int32_t r = B200_OK;
+    auto put = [&](DevBuf &b, const void *src, size_t bytes) -> int32_t {
+        TRY(trie_alloc(t, b, bytes ? bytes : 16));
+        if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, kind, c->stream));
+        return B200_OK;
+    };
+    r = put(t->keys, keys, n * 32);
+    if (r == B200_OK) r = put(t->accts, accts, n * 72);
+    if (r == B200_OK && sroots) r = put(t->sroots, sroots, n * 32);
+    if (r == B200_OK) r = trie_build_owned(t);
+    if (r == B200_OK && root_out) {
+        cudaError_t e = cudaMemcpyAsync(root_out, t->root.p, 32,
+                                        kind == cudaMemcpyHostToDevice ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                                        c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) r = fail(c, B200_ERR_CUDA, "root copy: %s", cudaGetErrorString(e));
+    }
+    if (r != B200_OK) {
+        b200_trie_destroy(t);  // does not take the context lock
+        return r;
+    }
+    *out = t;
+    return B200_OK;
+}
+
+extern "C" B200_API int32_t b200_trie_create(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
+                                             const uint8_t *storage_roots32, uint64_t n, b200_trie **out,
+                                             uint8_t root32[32]) {
+    return trie_create_common(c, acct_keys32, accts, storage_roots32, n, cudaMemcpyHostToDevice, out, root32);
+}
+extern "C" B200_API int32_t b200_trie_create_dev(b200_ctx *c, const void *d_acct_keys32, const void *d_accts,
+                                                 const void *d_storage_roots32, uint64_t n, b200_trie **out,
+                                                 void *d_root32) {
+    return trie_create_common(c, d_acct_keys32, d_accts, d_storage_roots32, n, cudaMemcpyDeviceToDevice, out, d_root32);
+}
+
+// dirty inputs already on the device; result root in t->root
+static int32_t trie_update_on_device(b200_trie *t, const uint8_t *d_keys, const uint8_t *d_accts, const uint8_t *d_sroots,
+                                     uint64_t m, uint32_t *n_dirty_out) {
+    b200_ctx *c = t->c;
+    cudaStream_t st = c->stream;
+    *n_dirty_out = 0;
+    TRY(reset_build_state(c));
+    if (m == 0 || t->n == 0) {
+        if (m && t->n == 0) return fail(c, B200_ERR_NOT_FOUND, "the resident trie is empty");
+        return finish_build_state(c);
+    }
+    if (d_sroots && !t->has_sroots) return fail(c, B200_ERR_INVALID_ARG, "trie was created without storage roots");
+    ForestDev f = t->f;
+    f.retain_updates = 1;
+    TRY(trie_alloc(t, t->idx, m * 4));
+    uint32_t *idx = static_cast<uint32_t *>(t->idx.p);
+    uint32_t *dirty = static_cast<uint32_t *>(t->dirty.p);
+    CU(launch_locate(static_cast<const uint8_t *>(t->keys.p), t->n, d_keys, m, idx, f.err, st));
+    CU(launch_leaf_rehash(f, static_cast<uint8_t *>(t->accts.p),
+                          t->has_sroots ? static_cast<uint8_t *>(t->sroots.p) : nullptr, d_accts, d_sroots, idx, m,
+                          static_cast<uint32_t *>(t->leaf_parent.p), static_cast<uint32_t *>(t->node_parent.p), dirty,
+                          st));
+    c->launches += 2;
+    c->stats.leaves_added += m;
+    uint32_t D = 0;
+    uint32_t *h_hist = static_cast<uint32_t *>(c->pinned_small) + 256;
+    if (t->B) {
+        TRY(trie_alloc(t, t->dirty_ids, (size_t)t->B * 4));
+        TRY(trie_alloc(t, t->dirty_key, t->B));
+        uint32_t *ids = static_cast<uint32_t *>(t->dirty_ids.p);
+        uint32_t *count_p = small_u32(c) + SM_NSTORED;
+        uint32_t *hist = small_u32(c) + SM_HIST;
+        size_t t_sel = 0;
+        thrust::counting_iterator<uint32_t> counting(0);
+        CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, dirty, ids, count_p, (int64_t)t->B, st));
+        ENSURE(cub_temp, t_sel);
+        CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, dirty, ids, count_p, (int64_t)t->B, st));
+        CU(cudaMemsetAsync(hist, 0, 64 * 4, st));
+        // an update touches at most 64 ancestors per dirty leaf
+        uint64_t max_dirty = std::min<uint64_t>(t->B, m * 64);
+        CU(launch_dirty_keys(ids, count_p, max_dirty, t->f.node_masks, static_cast<uint8_t *>(t->dirty_key.p), hist, dirty,
+                             st));
+        c->launches += 2;
+        uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
+        CU(cudaMemcpyAsync(ps + 200, count_p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_hist, hist, 64 * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ps, small_u32(c) + SM_ERR, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (ps[0] == B200_DEVERR_NOT_FOUND)
+            return fail(c, B200_ERR_NOT_FOUND, "a dirty key is not in the resident trie (inserts/deletes need a rebuild)");
+        if (ps[0] != B200_DEVERR_NONE) return map_dev_error(c, (int)ps[0]);
+        D = ps[200];
+    }
+    if (D) {
+        TRY(trie_alloc(t, t->dirty_key2, D));
+        TRY(trie_alloc(t, t->dirty_order, (size_t)D * 4));
+        uint32_t *order = static_cast<uint32_t *>(t->dirty_order.p);
+        size_t t_sort = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, static_cast<uint8_t *>(t->dirty_key.p),
+                                           static_cast<uint8_t *>(t->dirty_key2.p),
+                                           static_cast<uint32_t *>(t->dirty_ids.p), order, (int64_t)D, 0, 8, st));
+        ENSURE(cub_temp, t_sort);
+        CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_sort, static_cast<uint8_t *>(t->dirty_key.p),
+                                           static_cast<uint8_t *>(t->dirty_key2.p),
+                                           static_cast<uint32_t *>(t->dirty_ids.p), order, (int64_t)D, 0, 8, st));
+        c->launches++;
+        uint32_t pos = 0;
+        for (int d = 63; d >= 0; d--) {
+            uint32_t cnt = h_hist[63 - d];
+            if (!cnt) continue;
+            CU(launch_branch_level(f, order, pos, pos + cnt, d, 3, st));
+            c->launches++;
+            c->stats.levels++;
+            pos += cnt;
+        }
+        c->stats.branches_added += D;
+    }
+    CU(launch_segment_roots(f, nullptr, 1, static_cast<uint8_t *>(t->root.p), st));
+    c->launches++;
+    *n_dirty_out = D;
+    return finish_build_state(c);
+}
+
+extern "C" B200_API int32_t b200_trie_update_dev(b200_trie *t, const void *d_dirty_keys32, const void *d_new_accts,
+                                                 const void *d_new_storage_roots32, uint64_t m, void *d_root32) {
+    if (!t || (m && (!d_dirty_keys32 || !d_new_accts))) return fail(t ? t->c : nullptr, B200_ERR_INVALID_ARG, "bad argument");
+    b200_ctx *c = t->c;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    uint32_t D = 0;
+    TRY(trie_update_on_device(t, static_cast<const uint8_t *>(d_dirty_keys32), static_cast<const uint8_t *>(d_new_accts),
+                              static_cast<const uint8_t *>(d_new_storage_roots32), m, &D));
+    if (d_root32) CU(cudaMemcpyAsync(d_root32, t->root.p, 32, cudaMemcpyDeviceToDevice, c->stream));
+    return B200_OK;
+}
+
+extern "C" B200_API int32_t b200_trie_update(b200_trie *t, const uint8_t *dirty_keys32, const b200_account *new_accts,
+                                             const uint8_t *new_storage_roots32, uint64_t m, uint8_t root32[32],
+                                             b200_updates *opt_updates, b200_stats *opt_stats) {
+    if (!t || !root32 || (m && (!dirty_keys32 || !new_accts)))
+        return fail(t ? t->c : nullptr, B200_ERR_INVALID_ARG, "bad argument");
+    b200_ctx *c = t->c;
+    if (opt_updates) memset(opt_updates, 0, sizeof *opt_updates);
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    TRY(trie_alloc(t, t->in_keys, (m ? m : 1) * 32));
+    TRY(trie_alloc(t, t->in_accts, (m ? m : 1) * 72));
+    if (m) {
+        CU(cudaMemcpyAsync(t->in_keys.p, dirty_keys32, m * 32, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(t->in_accts.p, new_accts, m * 72, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (new_storage_roots32 && m) {
+        TRY(trie_alloc(t, t->in_sroots, m * 32));
+        CU(cudaMemcpyAsync(t->in_sroots.p, new_storage_roots32, m * 32, cudaMemcpyHostToDevice, c->stream));
+    }
+    uint32_t D = 0;
+    int32_t r = trie_update_on_device(t, static_cast<const uint8_t *>(t->in_keys.p),
+                                      static_cast<const uint8_t *>(t->in_accts.p),
+                                      new_storage_roots32 ? static_cast<const uint8_t *>(t->in_sroots.p) : nullptr, m, &D);
+    if (r == B200_OK) {
+        cudaError_t e = cudaMemcpyAsync(root32, t->root.p, 32, cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) r = fail(c, B200_ERR_CUDA, "root copy: %s", cudaGetErrorString(e));
+    }
+    if (r == B200_OK) r = sync_and_status(c);
+    if (r == B200_OK && opt_updates)
+        r = collect_updates_subset(c, t->f, static_cast<const uint32_t *>(t->dirty_order.p), D, opt_updates);
+    if (r != B200_OK && opt_updates) b200_updates_release(opt_updates);
+    if (opt_stats) *opt_stats = c->stats;
+    return r;
+}
+
+extern "C" B200_API int32_t b200_trie_root(b200_trie *t, uint8_t root32[32]) {
+    if (!t || !root32) return B200_ERR_INVALID_ARG;
+    b200_ctx *c = t->c;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(root32, t->root.p, 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return B200_OK;
 }

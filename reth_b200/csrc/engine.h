@@ -5,6 +5,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -21,6 +22,7 @@ struct b200_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_streams[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
     std::mutex mu;
     std::string err;
     uint64_t dev_bytes = 0;

@@ -703,9 +703,31 @@ __global__ void stored_flags_kernel(ForestDev f, uint32_t n_nodes, uint8_t *__re
     n_hashes[v] = st ? __popc((uint32_t)f.node_masks[v].z) : 0;
 }
 
+// Same over a list of node ids (the dirty nodes of an incremental update).
+__global__ void stored_flags_subset_kernel(ForestDev f, const uint32_t *__restrict__ ids, uint32_t count,
+                                           uint8_t *__restrict__ flags, uint32_t *__restrict__ n_hashes) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    uint32_t v = ids[t];
+    bool st = (f.node_meta[v] & META_STORED) && f.node_masks[v].w != 0;
+    flags[t] = st ? 1 : 0;
+    n_hashes[t] = st ? __popc((uint32_t)f.node_masks[v].z) : 0;
+}
+// compacts (node id, hash prefix) of the selected positions
+__global__ void pick_subset_kernel(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ prefix,
+                                   const uint32_t *__restrict__ sel_pos, uint32_t n_sel, uint32_t *__restrict__ out_ids,
+                                   uint32_t *__restrict__ out_prefix) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_sel) return;
+    uint32_t p = sel_pos[t];
+    out_ids[t] = ids[p];
+    out_prefix[t] = prefix[p];
+}
+
 // One thread per stored node: path, masks and the child hashes under hash_mask, ascending nibble.
 __global__ void gather_updates_kernel(ForestDev f, const uint32_t *__restrict__ stored_ids, uint32_t n_stored,
                                       const uint32_t *__restrict__ hash_prefix /* exclusive, over all nodes */,
+                                      const uint32_t *__restrict__ prefix_by_record /* or null */,
                                       const uint64_t *__restrict__ seg_offsets, uint64_t n_segs,
                                       UpdatesDev out) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -737,7 +759,7 @@ __global__ void gather_updates_kernel(ForestDev f, const uint32_t *__restrict__ 
     out.state_mask[t] = mk.x;
     out.tree_mask[t] = mk.y;
     out.hash_mask[t] = mk.z;
-    uint32_t ho = hash_prefix[v];
+    uint32_t ho = prefix_by_record ? prefix_by_record[t] : hash_prefix[v];
     out.hash_offset[t] = ho;
     uint32_t j0 = f.node_start[v], k = f.node_start[v + 1] - j0;
     for (uint32_t c = 0; c <= k; c++) {
@@ -749,6 +771,132 @@ __global__ void gather_updates_kernel(ForestDev f, const uint32_t *__restrict__ 
             ho++;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------ resident trie (C5)
+// Parent links of a finished build: one thread per branch node tells its children who their parent is.
+__global__ void parent_links_kernel(ForestDev f, uint32_t n_nodes, uint32_t *__restrict__ leaf_parent,
+                                    uint32_t *__restrict__ node_parent) {
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    uint32_t j0 = f.node_start[v], k = f.node_start[v + 1] - j0;
+    for (uint32_t c = 0; c <= k; c++) {
+        ChildInfo ci = fetch_child(f, j0, c);
+        if (ci.id < f.n) leaf_parent[ci.id] = v;
+        else node_parent[ci.id - (uint32_t)f.n] = v;
+    }
+}
+
+// Finds every dirty key in the resident sorted key array (nothing is written to the trie: if any key is missing
+// the error flag makes every later kernel of the update a no-op, so the resident trie stays consistent).
+__global__ void locate_kernel(const uint8_t *__restrict__ keys, uint64_t n, const uint8_t *__restrict__ dirty_keys,
+                              uint64_t m, uint32_t *__restrict__ idx_out, int *__restrict__ err) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    uint32_t q[8];
+    load32(dirty_keys + 32 * t, q);
+#pragma unroll
+    for (int i = 0; i < 8; i++) q[i] = __byte_perm(q[i], 0, 0x0123);
+    uint64_t lo = 0, hi = n;  // first key >= q
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        uint32_t kx[8];
+        load32_nc(keys + 32 * mid, kx);
+        bool less = false, decided = false;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t x = __byte_perm(kx[i], 0, 0x0123);
+            if (!decided && x != q[i]) {
+                decided = true;
+                less = x < q[i];
+            }
+        }
+        if (less) lo = mid + 1;
+        else hi = mid;
+    }
+    bool found = false;
+    if (lo < n) {
+        uint32_t kx[8];
+        load32_nc(keys + 32 * lo, kx);
+        found = true;
+#pragma unroll
+        for (int i = 0; i < 8; i++) found = found && __byte_perm(kx[i], 0, 0x0123) == q[i];
+    }
+    if (!found) {
+        atomicExch(err, B200_DEVERR_NOT_FOUND);
+        idx_out[t] = 0xFFFFFFFFu;
+        return;
+    }
+    idx_out[t] = (uint32_t)lo;
+}
+
+// Re-encodes the dirty leaves and marks their ancestor chains (stops at the first already-marked ancestor).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) leaf_rehash_kernel(ForestDev f, uint8_t *__restrict__ accts,
+                                                            uint8_t *__restrict__ sroots,
+                                                            const uint8_t *__restrict__ new_accts,
+                                                            const uint8_t *__restrict__ new_sroots,
+                                                            const uint32_t *__restrict__ idx, uint64_t m,
+                                                            const uint32_t *__restrict__ leaf_parent,
+                                                            const uint32_t *__restrict__ node_parent,
+                                                            uint32_t *__restrict__ dirty) {
+    extern __shared__ uint32_t smem[];
+    if (*(volatile int *)f.err != B200_DEVERR_NONE) return;
+    Strip<BLOCK> s;
+    uint32_t hashed = 0;
+    for (uint64_t t = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; t < m; t += (uint64_t)gridDim.x * BLOCK) {
+        uint32_t i = idx[t];
+        s.init(smem);
+        {  // overwrite the resident account (and storage root) with the new value
+            const uint64_t *src = reinterpret_cast<const uint64_t *>(new_accts + 72 * t);
+            uint64_t *dst = reinterpret_cast<uint64_t *>(accts + 72 * (uint64_t)i);
+#pragma unroll
+            for (int w = 0; w < 9; w++) dst[w] = src[w];
+            if (new_sroots && sroots) {
+                uint32_t r[8];
+                load32(new_sroots + 32 * t, r);
+                store32(sroots + 32 * (uint64_t)i, r);
+            }
+        }
+        uint32_t k[8];
+        load32(f.keys + 32 * (uint64_t)i, k);
+        int pdl = depth_of(f.Lp[i]), pdr = depth_of(f.Lp[(uint64_t)i + 1]);
+        int pd = pdl > pdr ? pdl : pdr;
+        // plain loads: the account was written by this thread a moment ago
+        uint32_t len = encode_leaf<BLOCK, true>(s, k, pd, new_accts + 72 * t,
+                                                sroots ? (new_sroots ? new_sroots + 32 * t : sroots + 32 * (uint64_t)i) : nullptr,
+                                                f.err);
+        uint32_t ref[8];
+        uint32_t meta = strip_to_ref(s, len, pd < 0, ref, hashed);
+        store32(f.leaf_ref + 32 * (uint64_t)i, ref);
+        f.leaf_meta[i] = (uint8_t)meta;
+        uint32_t p = leaf_parent[i];
+        while (p != 0xFFFFFFFFu) {
+            if (atomicExch(&dirty[p], 1u) != 0u) break;
+            p = node_parent[p];
+        }
+    }
+    for (int o = 16; o; o >>= 1) hashed += __shfl_xor_sync(0xffffffffu, hashed, o);
+    if ((threadIdx.x & 31) == 0 && hashed) atomicAdd(&f.counters[CNT_HASHED], (unsigned long long)hashed);
+}
+
+// depth keys + per-depth histogram of the dirty nodes (count known only on the device)
+__global__ void dirty_keys_kernel(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ count_p,
+                                  const ushort4 *__restrict__ node_masks, uint8_t *__restrict__ keys,
+                                  uint32_t *__restrict__ hist, uint32_t *__restrict__ dirty) {
+    __shared__ uint32_t sh[64];
+    if (threadIdx.x < 64) sh[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t cnt = *count_p;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += gridDim.x * blockDim.x) {
+        uint32_t v = ids[t];
+        uint32_t d = node_masks[v].w;
+        keys[t] = (uint8_t)(63u - d);
+        atomicAdd(&sh[63u - d], 1u);
+        dirty[v] = 0;  // consumed
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------ multi-GPU frontier
@@ -1019,11 +1167,12 @@ cudaError_t launch_stored_flags(const ForestDev &f, uint32_t n_nodes, uint8_t *f
     return cudaGetLastError();
 }
 cudaError_t launch_gather_updates(const ForestDev &f, const uint32_t *stored_ids, uint32_t n_stored,
-                                  const uint32_t *hash_prefix, const uint64_t *d_seg_offsets, uint64_t n_segs,
-                                  const UpdatesDev &out, cudaStream_t st) {
+                                  const uint32_t *hash_prefix, const uint32_t *prefix_by_record,
+                                  const uint64_t *d_seg_offsets, uint64_t n_segs, const UpdatesDev &out,
+                                  cudaStream_t st) {
     if (n_stored == 0) return cudaSuccess;
     gather_updates_kernel<<<blocks_for(n_stored, 128), 128, 0, st>>>(f, stored_ids, n_stored, hash_prefix,
-                                                                     d_seg_offsets, n_segs, out);
+                                                                     prefix_by_record, d_seg_offsets, n_segs, out);
     return cudaGetLastError();
 }
 
@@ -1045,6 +1194,51 @@ cudaError_t launch_root_from_frontier(const FrontierEntryDev *fr, uint8_t *root,
     auto k = root_from_frontier_kernel<B>;
     size_t smem = (size_t)BRANCH_WORDS * B * 4;
     k<<<1, B, smem, st>>>(fr, root);
+    return cudaGetLastError();
+}
+
+// ---- resident trie launchers
+cudaError_t launch_stored_flags_subset(const ForestDev &f, const uint32_t *ids, uint32_t count, uint8_t *flags,
+                                       uint32_t *n_hashes, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    stored_flags_subset_kernel<<<blocks_for(count, 256), 256, 0, st>>>(f, ids, count, flags, n_hashes);
+    return cudaGetLastError();
+}
+cudaError_t launch_pick_subset(const uint32_t *ids, const uint32_t *prefix, const uint32_t *sel_pos, uint32_t n_sel,
+                               uint32_t *out_ids, uint32_t *out_prefix, cudaStream_t st) {
+    if (n_sel == 0) return cudaSuccess;
+    pick_subset_kernel<<<blocks_for(n_sel, 256), 256, 0, st>>>(ids, prefix, sel_pos, n_sel, out_ids, out_prefix);
+    return cudaGetLastError();
+}
+cudaError_t launch_parent_links(const ForestDev &f, uint32_t n_nodes, uint32_t *leaf_parent, uint32_t *node_parent,
+                                cudaStream_t st) {
+    if (n_nodes == 0) return cudaSuccess;
+    parent_links_kernel<<<blocks_for(n_nodes, 256), 256, 0, st>>>(f, n_nodes, leaf_parent, node_parent);
+    return cudaGetLastError();
+}
+cudaError_t launch_locate(const uint8_t *keys, uint64_t n, const uint8_t *dirty_keys, uint64_t m, uint32_t *idx_out,
+                          int *err, cudaStream_t st) {
+    if (m == 0) return cudaSuccess;
+    locate_kernel<<<blocks_for(m, 128), 128, 0, st>>>(keys, n, dirty_keys, m, idx_out, err);
+    return cudaGetLastError();
+}
+cudaError_t launch_leaf_rehash(const ForestDev &f, uint8_t *accts, uint8_t *sroots, const uint8_t *new_accts,
+                               const uint8_t *new_sroots, const uint32_t *idx, uint64_t m, const uint32_t *leaf_parent,
+                               const uint32_t *node_parent, uint32_t *dirty, cudaStream_t st) {
+    if (m == 0) return cudaSuccess;
+    constexpr int B = 64;
+    auto k = leaf_rehash_kernel<B>;
+    size_t smem = (size_t)68 * B * 4;
+    k<<<persistent_grid(k, B, smem, m), B, smem, st>>>(f, accts, sroots, new_accts, new_sroots, idx, m, leaf_parent,
+                                                       node_parent, dirty);
+    return cudaGetLastError();
+}
+cudaError_t launch_dirty_keys(const uint32_t *ids, const uint32_t *count_p, uint64_t max_count, const ushort4 *node_masks,
+                              uint8_t *keys, uint32_t *hist, uint32_t *dirty, cudaStream_t st) {
+    if (max_count == 0) return cudaSuccess;
+    unsigned blocks = blocks_for(max_count, 256);
+    if (blocks > (unsigned)sms() * 4) blocks = (unsigned)sms() * 4;
+    dirty_keys_kernel<<<blocks, 256, 0, st>>>(ids, count_p, node_masks, keys, hist, dirty);
     return cudaGetLastError();
 }
 

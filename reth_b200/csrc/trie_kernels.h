@@ -13,6 +13,7 @@ enum : int {
     B200_DEVERR_ZERO_VALUE = 2,
     B200_DEVERR_INLINE_HASH_CHILD = 3,
     B200_DEVERR_BAD_OFFSETS = 4,
+    B200_DEVERR_NOT_FOUND = 5,
 };
 
 // node / leaf meta byte
@@ -91,11 +92,26 @@ cudaError_t launch_segment_roots(const ForestDev &f, const uint64_t *d_seg_offse
 cudaError_t launch_stored_flags(const ForestDev &f, uint32_t n_nodes, uint8_t *flags, uint32_t *n_hashes,
                                 cudaStream_t st);
 cudaError_t launch_gather_updates(const ForestDev &f, const uint32_t *stored_ids, uint32_t n_stored,
-                                  const uint32_t *hash_prefix, const uint64_t *d_seg_offsets, uint64_t n_segs,
-                                  const UpdatesDev &out, cudaStream_t st);
+                                  const uint32_t *hash_prefix, const uint32_t *prefix_by_record,
+                                  const uint64_t *d_seg_offsets, uint64_t n_segs, const UpdatesDev &out,
+                                  cudaStream_t st);
 cudaError_t launch_nibble_buckets(const uint8_t *keys, uint64_t n, uint64_t *offs, cudaStream_t st);
 cudaError_t launch_frontier(const ForestDev &f, const uint64_t *bucket_offsets, const uint8_t *values,
                             const uint8_t *storage_roots, FrontierEntryDev *out, cudaStream_t st);
 cudaError_t launch_root_from_frontier(const FrontierEntryDev *fr, uint8_t *root, cudaStream_t st);
+
+cudaError_t launch_parent_links(const ForestDev &f, uint32_t n_nodes, uint32_t *leaf_parent, uint32_t *node_parent,
+                                cudaStream_t st);
+cudaError_t launch_locate(const uint8_t *keys, uint64_t n, const uint8_t *dirty_keys, uint64_t m, uint32_t *idx_out,
+                          int *err, cudaStream_t st);
+cudaError_t launch_leaf_rehash(const ForestDev &f, uint8_t *accts, uint8_t *sroots, const uint8_t *new_accts,
+                               const uint8_t *new_sroots, const uint32_t *idx, uint64_t m, const uint32_t *leaf_parent,
+                               const uint32_t *node_parent, uint32_t *dirty, cudaStream_t st);
+cudaError_t launch_stored_flags_subset(const ForestDev &f, const uint32_t *ids, uint32_t count, uint8_t *flags,
+                                       uint32_t *n_hashes, cudaStream_t st);
+cudaError_t launch_pick_subset(const uint32_t *ids, const uint32_t *prefix, const uint32_t *sel_pos, uint32_t n_sel,
+                               uint32_t *out_ids, uint32_t *out_prefix, cudaStream_t st);
+cudaError_t launch_dirty_keys(const uint32_t *ids, const uint32_t *count_p, uint64_t max_count, const ushort4 *node_masks,
+                              uint8_t *keys, uint32_t *hist, uint32_t *dirty, cudaStream_t st);
 
 }  // namespace b200

@@ -262,3 +262,70 @@ class Engine:
 
     def dev_status(self):
         self._check(self.lib.b200_dev_status(self.ctx))
+
+
+class ResidentTrie:
+    """Handle on a b200_trie: the account trie of a whole state kept in HBM for incremental roots (BASELINE config 5).
+    `update` commits value changes of existing accounts by re-hashing only their root paths."""
+
+    def __init__(self, engine: Engine, handle, root: bytes):
+        self.engine, self.handle, self._root = engine, handle, root
+
+    # -- construction
+    @classmethod
+    def create(cls, engine: Engine, acct_keys, accounts, storage_roots32=None) -> "ResidentTrie":
+        acct_keys = _np(acct_keys).reshape(-1, 32)
+        accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
+        sr = None if storage_roots32 is None else _np(storage_roots32).reshape(-1, 32)
+        h = C.c_void_p()
+        root = np.empty(32, np.uint8)
+        engine._check(engine.lib.b200_trie_create(engine.ctx, _ptr(acct_keys), _ptr(accounts), _ptr(sr), len(acct_keys),
+                                                  C.byref(h), _ptr(root)))
+        return cls(engine, h, root.tobytes())
+
+    @classmethod
+    def create_dev(cls, engine: Engine, t_keys, t_accts, t_sroots, n: int, t_root=None) -> "ResidentTrie":
+        h = C.c_void_p()
+        engine._check(engine.lib.b200_trie_create_dev(engine.ctx, t_keys.data_ptr(), t_accts.data_ptr(),
+                                                      t_sroots.data_ptr() if t_sroots is not None else None, n,
+                                                      C.byref(h), t_root.data_ptr() if t_root is not None else None))
+        return cls(engine, h, b"")
+
+    # -- updates
+    def update(self, dirty_keys, new_accounts, new_storage_roots32=None, want_updates=False, want_stats=False):
+        dirty_keys = _np(dirty_keys).reshape(-1, 32)
+        new_accounts = np.ascontiguousarray(new_accounts, ACCOUNT_DTYPE)
+        sr = None if new_storage_roots32 is None else _np(new_storage_roots32).reshape(-1, 32)
+        root = np.empty(32, np.uint8)
+        u, s = Updates(), Stats()
+        self.engine._check(self.engine.lib.b200_trie_update(self.handle, _ptr(dirty_keys), _ptr(new_accounts), _ptr(sr),
+                                                            len(dirty_keys), _ptr(root),
+                                                            C.byref(u) if want_updates else None, C.byref(s)))
+        self._root = root.tobytes()
+        res = [self._root]
+        if want_updates:
+            res.append(updates_to_records(u, self.engine.lib))
+        if want_stats:
+            res.append(s.as_dict())
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def update_dev(self, t_keys, t_accts, t_sroots, m: int, t_root=None):
+        self.engine._check(self.engine.lib.b200_trie_update_dev(
+            self.handle, t_keys.data_ptr(), t_accts.data_ptr(), t_sroots.data_ptr() if t_sroots is not None else None, m,
+            t_root.data_ptr() if t_root is not None else None))
+
+    def root(self) -> bytes:
+        out = np.empty(32, np.uint8)
+        self.engine._check(self.engine.lib.b200_trie_root(self.handle, _ptr(out)))
+        return out.tobytes()
+
+    def device_bytes(self) -> int:
+        return int(self.engine.lib.b200_trie_device_bytes(self.handle))
+
+    def __len__(self):
+        return int(self.engine.lib.b200_trie_leaves(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.engine.lib.b200_trie_destroy(self.handle)
+            self.handle = None
