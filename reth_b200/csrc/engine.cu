@@ -22,6 +22,9 @@ using namespace b200;
 
 static thread_local int g_create_status = 0;
 
+// levels with at most this many nodes run one warp per node (shuffle-based Keccak): beyond ~3-4k nodes the 14x higher instruction count of the shuffle formulation outweighs its ~5x shorter latency
+static constexpr uint32_t WARP_LEVEL_MAX = 4096;
+
 // layout of the `small` device buffer (uint32 units)
 enum : int { SM_BUCKET_OFF = 0, SM_LEVEL_LO = 80, SM_NNODES = 160, SM_ERR = 164, SM_NSTORED = 168, SM_COUNTERS = 176 /* 4 x u64 */, SM_HIST = 256 /* 256 x u32 */, SM_WORDS = 512 };
 
@@ -137,8 +140,10 @@ static int32_t sync_and_status(b200_ctx *c) {
     uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
     CU(cudaMemcpyAsync(ps, small_u32(c) + SM_ERR, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(ps + 8, small_u32(c) + SM_COUNTERS, 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(ps + 4, small_u32(c) + SM_NSTORED, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (c->stats_pending) {
+        if (c->stats_wavefront) c->stats.branches_added = ps[4];
         float ms = 0;
         if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->stats.device_ms = ms;
         else cudaGetLastError();
@@ -154,6 +159,7 @@ static int32_t reset_build_state(b200_ctx *c) {
     CU(cudaMemsetAsync(small_u32(c) + SM_ERR, 0, 4, c->stream));
     CU(cudaMemsetAsync(small_u32(c) + SM_COUNTERS, 0, 32, c->stream));
     c->stats = b200_stats{};
+    c->stats_wavefront = false;
     CU(cudaEventRecord(c->ev0, c->stream));
     return B200_OK;
 }
@@ -448,8 +454,8 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
         uint32_t cnt = hc[0] + hc[1] + hc[2] + hc[3];
         if (!cnt) continue;
         out.levels++;
-        if (cnt < 4096) {
-            CU(launch_branch_level(f, norder, pos, pos + cnt, d, 3, st));
+        if (cnt <= WARP_LEVEL_MAX) {  // about one wave of warps: latency-bound, one warp per node
+            CU(launch_branch_level(f, norder, pos, pos + cnt, d, -1, st));
             c->launches++;
             pos += cnt;
         } else {
@@ -1144,12 +1150,12 @@ extern "C" B200_API int32_t b200_trie_create_dev(b200_ctx *c, const void *d_acct
     return trie_create_common(c, d_acct_keys32, d_accts, d_storage_roots32, n, cudaMemcpyDeviceToDevice, out, d_root32);
 }
 
-// dirty inputs already on the device; result root in t->root
+// dirty inputs already on the device; result root in t->root.  Three launches, no host round trip:
+// locate (binary search) -> mark_pending (count dirty children per ancestor) -> wavefront (leaf + root-path re-hash).
 static int32_t trie_update_on_device(b200_trie *t, const uint8_t *d_keys, const uint8_t *d_accts, const uint8_t *d_sroots,
-                                     uint64_t m, uint32_t *n_dirty_out) {
+                                     uint64_t m) {
     b200_ctx *c = t->c;
     cudaStream_t st = c->stream;
-    *n_dirty_out = 0;
     TRY(reset_build_state(c));
     if (m == 0 || t->n == 0) {
         if (m && t->n == 0) return fail(c, B200_ERR_NOT_FOUND, "the resident trie is empty");
@@ -1159,72 +1165,32 @@ static int32_t trie_update_on_device(b200_trie *t, const uint8_t *d_keys, const 
     ForestDev f = t->f;
     f.retain_updates = 1;
     TRY(trie_alloc(t, t->idx, m * 4));
+    uint64_t max_dirty = std::min<uint64_t>((uint64_t)t->B, m * 64) + 1;  // at most 64 ancestors per dirty leaf
+    TRY(trie_alloc(t, t->dirty_ids, max_dirty * 4));
     uint32_t *idx = static_cast<uint32_t *>(t->idx.p);
-    uint32_t *dirty = static_cast<uint32_t *>(t->dirty.p);
+    uint32_t *count_p = small_u32(c) + SM_NSTORED;
+    CU(cudaMemsetAsync(count_p, 0, 4, st));
     CU(launch_locate(static_cast<const uint8_t *>(t->keys.p), t->n, d_keys, m, idx, f.err, st));
-    CU(launch_leaf_rehash(f, static_cast<uint8_t *>(t->accts.p),
-                          t->has_sroots ? static_cast<uint8_t *>(t->sroots.p) : nullptr, d_accts, d_sroots, idx, m,
-                          static_cast<uint32_t *>(t->leaf_parent.p), static_cast<uint32_t *>(t->node_parent.p), dirty,
-                          st));
-    c->launches += 2;
+    CU(launch_mark_pending(f, idx, m, static_cast<uint32_t *>(t->leaf_parent.p), static_cast<uint32_t *>(t->node_parent.p),
+                           static_cast<uint32_t *>(t->dirty.p), st));
+    CU(launch_wavefront(f, static_cast<uint8_t *>(t->accts.p), t->has_sroots ? static_cast<uint8_t *>(t->sroots.p) : nullptr,
+                        d_accts, d_sroots, idx, m, static_cast<uint32_t *>(t->leaf_parent.p),
+                        static_cast<uint32_t *>(t->node_parent.p), static_cast<uint32_t *>(t->dirty.p),
+                        static_cast<uint32_t *>(t->dirty_ids.p), count_p, static_cast<uint8_t *>(t->root.p), st));
+    c->launches += 3;
     c->stats.leaves_added += m;
-    uint32_t D = 0;
-    uint32_t *h_hist = static_cast<uint32_t *>(c->pinned_small) + 256;
-    if (t->B) {
-        TRY(trie_alloc(t, t->dirty_ids, (size_t)t->B * 4));
-        TRY(trie_alloc(t, t->dirty_key, t->B));
-        uint32_t *ids = static_cast<uint32_t *>(t->dirty_ids.p);
-        uint32_t *count_p = small_u32(c) + SM_NSTORED;
-        uint32_t *hist = small_u32(c) + SM_HIST;
-        size_t t_sel = 0;
-        thrust::counting_iterator<uint32_t> counting(0);
-        CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, dirty, ids, count_p, (int64_t)t->B, st));
-        ENSURE(cub_temp, t_sel);
-        CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, dirty, ids, count_p, (int64_t)t->B, st));
-        CU(cudaMemsetAsync(hist, 0, 64 * 4, st));
-        // an update touches at most 64 ancestors per dirty leaf
-        uint64_t max_dirty = std::min<uint64_t>(t->B, m * 64);
-        CU(launch_dirty_keys(ids, count_p, max_dirty, t->f.node_masks, static_cast<uint8_t *>(t->dirty_key.p), hist, dirty,
-                             st));
-        c->launches += 2;
-        uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
-        CU(cudaMemcpyAsync(ps + 200, count_p, 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h_hist, hist, 64 * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(ps, small_u32(c) + SM_ERR, 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if (ps[0] == B200_DEVERR_NOT_FOUND)
-            return fail(c, B200_ERR_NOT_FOUND, "a dirty key is not in the resident trie (inserts/deletes need a rebuild)");
-        if (ps[0] != B200_DEVERR_NONE) return map_dev_error(c, (int)ps[0]);
-        D = ps[200];
-    }
-    if (D) {
-        TRY(trie_alloc(t, t->dirty_key2, D));
-        TRY(trie_alloc(t, t->dirty_order, (size_t)D * 4));
-        uint32_t *order = static_cast<uint32_t *>(t->dirty_order.p);
-        size_t t_sort = 0;
-        CU(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, static_cast<uint8_t *>(t->dirty_key.p),
-                                           static_cast<uint8_t *>(t->dirty_key2.p),
-                                           static_cast<uint32_t *>(t->dirty_ids.p), order, (int64_t)D, 0, 8, st));
-        ENSURE(cub_temp, t_sort);
-        CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_sort, static_cast<uint8_t *>(t->dirty_key.p),
-                                           static_cast<uint8_t *>(t->dirty_key2.p),
-                                           static_cast<uint32_t *>(t->dirty_ids.p), order, (int64_t)D, 0, 8, st));
-        c->launches++;
-        uint32_t pos = 0;
-        for (int d = 63; d >= 0; d--) {
-            uint32_t cnt = h_hist[63 - d];
-            if (!cnt) continue;
-            CU(launch_branch_level(f, order, pos, pos + cnt, d, 3, st));
-            c->launches++;
-            c->stats.levels++;
-            pos += cnt;
-        }
-        c->stats.branches_added += D;
-    }
-    CU(launch_segment_roots(f, nullptr, 1, static_cast<uint8_t *>(t->root.p), st));
-    c->launches++;
-    *n_dirty_out = D;
+    c->stats_wavefront = true;
     return finish_build_state(c);
+}
+
+// number of re-hashed branch nodes of the last update (after a sync)
+static int32_t trie_read_dirty_count(b200_trie *t, uint32_t *out) {
+    b200_ctx *c = t->c;
+    uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
+    CU(cudaMemcpyAsync(ps + 200, small_u32(c) + SM_NSTORED, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = ps[200];
+    return B200_OK;
 }
 
 extern "C" B200_API int32_t b200_trie_update_dev(b200_trie *t, const void *d_dirty_keys32, const void *d_new_accts,
@@ -1233,11 +1199,10 @@ extern "C" B200_API int32_t b200_trie_update_dev(b200_trie *t, const void *d_dir
     b200_ctx *c = t->c;
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
-    uint32_t D = 0;
     TRY(trie_update_on_device(t, static_cast<const uint8_t *>(d_dirty_keys32), static_cast<const uint8_t *>(d_new_accts),
-                              static_cast<const uint8_t *>(d_new_storage_roots32), m, &D));
+                              static_cast<const uint8_t *>(d_new_storage_roots32), m));
     if (d_root32) CU(cudaMemcpyAsync(d_root32, t->root.p, 32, cudaMemcpyDeviceToDevice, c->stream));
-    return B200_OK;
+    return B200_OK;  // asynchronous: B200_ERR_NOT_FOUND etc. surface at the next b200_sync / b200_dev_status
 }
 
 extern "C" B200_API int32_t b200_trie_update(b200_trie *t, const uint8_t *dirty_keys32, const b200_account *new_accts,
@@ -1262,14 +1227,17 @@ extern "C" B200_API int32_t b200_trie_update(b200_trie *t, const uint8_t *dirty_
     uint32_t D = 0;
     int32_t r = trie_update_on_device(t, static_cast<const uint8_t *>(t->in_keys.p),
                                       static_cast<const uint8_t *>(t->in_accts.p),
-                                      new_storage_roots32 ? static_cast<const uint8_t *>(t->in_sroots.p) : nullptr, m, &D);
+                                      new_storage_roots32 ? static_cast<const uint8_t *>(t->in_sroots.p) : nullptr, m);
     if (r == B200_OK) {
         cudaError_t e = cudaMemcpyAsync(root32, t->root.p, 32, cudaMemcpyDeviceToHost, c->stream);
         if (e != cudaSuccess) r = fail(c, B200_ERR_CUDA, "root copy: %s", cudaGetErrorString(e));
     }
     if (r == B200_OK) r = sync_and_status(c);
-    if (r == B200_OK && opt_updates)
-        r = collect_updates_subset(c, t->f, static_cast<const uint32_t *>(t->dirty_order.p), D, opt_updates);
+    if (r == B200_OK) r = trie_read_dirty_count(t, &D);
+    if (r == B200_OK) {
+        c->stats.branches_added = D;
+        if (opt_updates) r = collect_updates_subset(c, t->f, static_cast<const uint32_t *>(t->dirty_ids.p), D, opt_updates);
+    }
     if (r != B200_OK && opt_updates) b200_updates_release(opt_updates);
     if (opt_stats) *opt_stats = c->stats;
     return r;

@@ -29,6 +29,7 @@ struct b200_ctx {
     unsigned launches = 0;
     b200_stats stats{};
     bool stats_pending = false;
+    bool stats_wavefront = false;  // branches_added of the last build comes from the wavefront's node counter
     // scratch (grow-only)
     DevBuf Lp, nibs, leaf_ref, leaf_meta, S, E, iota, depth_sorted, gap_sorted, bound_rank, head, node_start,
         node_ref, node_meta, node_l, node_r, node_masks, cub_temp, small, sroots, buckets;

@@ -154,8 +154,8 @@ static __device__ __forceinline__ uint32_t byte_at(const uint32_t (&x)[8], uint3
 }
 
 // RLP list header for a payload < 65536 bytes
-template <int BLOCK>
-static __device__ __forceinline__ void put_list_header(Strip<BLOCK> &s, uint32_t payload) {
+template <class W>
+static __device__ __forceinline__ void put_list_header(W &s, uint32_t payload) {
     if (payload < 56) {
         s.byte(0xc0 + payload);
     } else if (payload < 256) {
@@ -294,8 +294,8 @@ __global__ void level_ranges_kernel(const uint32_t *__restrict__ node_start, con
 // One leaf -> RlpNode.  ACCOUNT: value = rlp(TrieAccount) built on the fly (crates/trie/trie/src/trie.rs:429-432,
 // crates/trie/common/src/account.rs:16-31); else value = rlp(U256) (trie.rs:668-671).
 // Encodes with parent depth `pd` (suffix starts at nibble pd+1); `force_hash` for a leaf that is a whole trie.
-template <int BLOCK, bool ACCOUNT>
-__device__ __forceinline__ uint32_t encode_leaf(Strip<BLOCK> &s, const uint32_t (&k)[8], int pd, const uint8_t *val_ptr,
+template <class W, bool ACCOUNT>
+__device__ __forceinline__ uint32_t encode_leaf(W &s, const uint32_t (&k)[8], int pd, const uint8_t *val_ptr,
                                                 const uint8_t *sroot_ptr, int *err) {
     uint32_t p = (uint32_t)(pd + 1);  // first suffix nibble
     uint32_t m = 64 - p;              // suffix nibbles (1..64)
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(BLOCK) leaf_kernel(ForestDev f, const uint8_t 
         int pd = pdl > pdr ? pdl : pdr;
         const uint8_t *vp = ACCOUNT ? values + (uint64_t)sizeof(b200_account_dev) * i : values + 32 * i;
         const uint8_t *sp = (ACCOUNT && storage_roots) ? storage_roots + 32 * i : nullptr;
-        uint32_t len = encode_leaf<BLOCK, ACCOUNT>(s, k, pd, vp, sp, f.err);
+        uint32_t len = encode_leaf<Strip<BLOCK>, ACCOUNT>(s, k, pd, vp, sp, f.err);
         uint32_t ref[8];
         uint32_t meta = strip_to_ref(s, len, pd < 0, ref, hashed);
         store32(f.leaf_ref + 32 * i, ref);
@@ -463,8 +463,8 @@ __device__ __forceinline__ ChildInfo fetch_child(const ForestDev &f, uint32_t j0
 }
 
 // hex-prefix string of key nibbles [from, to) (extension flag), as an RLP string
-template <int BLOCK>
-__device__ __forceinline__ uint32_t put_ext_path(Strip<BLOCK> &s, const uint8_t *key, uint32_t from, uint32_t to) {
+template <class W>
+__device__ __forceinline__ uint32_t put_ext_path(W &s, const uint8_t *key, uint32_t from, uint32_t to) {
     uint32_t m = to - from;
     uint32_t hp_len = 1 + (m >> 1);
     uint32_t i = from;
@@ -528,8 +528,8 @@ __device__ __forceinline__ uint32_t encode_branch(Strip<BLOCK> &s, const ForestD
 }
 
 // Wraps `child` (ref words + inline length, 0 = hashed) into an extension over key nibbles [from,to).
-template <int BLOCK>
-__device__ __forceinline__ uint32_t encode_extension(Strip<BLOCK> &s, const uint8_t *key, uint32_t from, uint32_t to,
+template <class W>
+__device__ __forceinline__ uint32_t encode_extension(W &s, const uint8_t *key, uint32_t from, uint32_t to,
                                                      const uint32_t (&child)[8], uint32_t child_inline_len) {
     uint32_t m = to - from;
     uint32_t hp_len = 1 + (m >> 1);
@@ -665,6 +665,378 @@ __global__ void __launch_bounds__(BLOCK) branch_kernel(ForestDev f, const uint32
         exts += __shfl_xor_sync(0xffffffffu, exts, o);
     }
     if ((threadIdx.x & 31) == 0) {
+        if (hashed) atomicAdd(&f.counters[CNT_HASHED], (unsigned long long)hashed);
+        if (exts) atomicAdd(&f.counters[CNT_EXT], (unsigned long long)exts);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ warp-per-node
+// Small levels (the top of every trie, the dirty paths of an incremental update) hold too few nodes to fill the
+// machine; there the cost is the LATENCY of one node: 1-4 dependent Keccak-f on one thread is 20-40 us.  Here one
+// warp builds one node: the 16 child slots are assembled by 16 lanes in parallel, and the permutation runs with
+// the 25 lanes of the sponge state spread over 25 threads (theta/pi/chi as warp shuffles) — the layout the task
+// statement sketches.  It is ~5x less ALU-efficient than the register-resident sponge but ~5x shorter in latency,
+// so it is used only where a level fits in about one wave of warps.
+__constant__ uint8_t KW_ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+__constant__ uint8_t KW_SRC[25] = {0, 6, 12, 18, 24, 3, 9, 10, 16, 22, 1, 7, 13, 19, 20, 4, 5, 11, 17, 23, 2, 8, 14, 15, 21};
+
+static __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+    uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+static __device__ __forceinline__ uint64_t rotl64_var(uint64_t x, uint32_t n) {
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    if (n & 32) {
+        uint32_t t = lo;
+        lo = hi;
+        hi = t;
+    }
+    n &= 31;
+    return ((uint64_t)__funnelshift_l(lo, hi, n) << 32) | __funnelshift_l(hi, lo, n);
+}
+
+struct WarpKeccak {
+    int l5, l10, l15, l20, xm1, xp1, src, n1, n2;
+    uint32_t rot;
+    bool lane0;
+    __device__ __forceinline__ void init(int lane) {
+        int i = lane % 25, x = i % 5, y = i / 5;
+        l5 = (i + 5) % 25; l10 = (i + 10) % 25; l15 = (i + 15) % 25; l20 = (i + 20) % 25;
+        xm1 = (x + 4) % 5; xp1 = (x + 1) % 5;
+        src = KW_SRC[i]; rot = KW_ROT[i];
+        n1 = 5 * y + (x + 1) % 5; n2 = 5 * y + (x + 2) % 5;
+        lane0 = lane == 0;
+    }
+    __device__ __forceinline__ void permute(uint64_t &a) const {
+#pragma unroll 1
+        for (int r = 0; r < 24; r++) {
+            uint64_t c = a ^ shfl64(a, l5) ^ shfl64(a, l10) ^ shfl64(a, l15) ^ shfl64(a, l20);
+            uint64_t d = shfl64(c, xm1) ^ rotl64<1>(shfl64(c, xp1));
+            uint64_t b = shfl64(rotl64_var(a ^ d, rot), src);
+            a = b ^ (~shfl64(b, n1) & shfl64(b, n2));
+            if (lane0) a ^= KECCAK_RC[r];
+        }
+    }
+    // keccak256 of buf[0 .. blocks*136) (already padded); digest word i ends up in lane i (i < 4)
+    __device__ __forceinline__ uint64_t hash(const uint8_t *buf, uint32_t blocks, int lane) const {
+        uint64_t a = 0;
+        const uint64_t *w = reinterpret_cast<const uint64_t *>(buf);
+        for (uint32_t b = 0; b < blocks; b++) {
+            if (lane < 17) a ^= w[17 * b + lane];
+            permute(a);
+        }
+        return a;
+    }
+};
+
+// byte writer over a warp's linear shared buffer (single-lane use)
+struct LinBuf {
+    uint8_t *p;
+    uint32_t n;
+    __device__ __forceinline__ void byte(uint32_t b) { p[n++] = (uint8_t)b; }
+    __device__ __forceinline__ void tail32(const uint32_t (&x)[8], uint32_t b0) {
+        for (uint32_t b = b0; b < 32; b++) byte(byte_at(x, b));
+    }
+    __device__ __forceinline__ void words8(const uint32_t (&x)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            p[n++] = (uint8_t)x[i];
+            p[n++] = (uint8_t)(x[i] >> 8);
+            p[n++] = (uint8_t)(x[i] >> 16);
+            p[n++] = (uint8_t)(x[i] >> 24);
+        }
+    }
+};
+
+constexpr int WARP_BUF = 560;  // 4 rate blocks + slack, 16-byte multiple
+
+// fetch_child with loads that bypass L1 (data produced by other SMs earlier in the SAME kernel: the wavefront)
+template <bool COHERENT>
+__device__ __forceinline__ ChildInfo fetch_child_c(const ForestDev &f, uint32_t j0, uint32_t c) {
+    if (!COHERENT) return fetch_child(f, j0, c);
+    ChildInfo ci;
+    if (c == 0) {
+        uint32_t g = f.gap_sorted[j0];
+        ci.id = f.E[g - 1];
+        ci.nib = f.nibs[g] >> 4;
+    } else {
+        uint32_t g = f.gap_sorted[j0 + c - 1];
+        ci.id = f.S[g];
+        ci.nib = f.nibs[g] & 15;
+    }
+    ci.meta = ci.id < f.n ? __ldcg(f.leaf_meta + ci.id) : __ldcg(f.node_meta + (ci.id - (uint32_t)f.n));
+    return ci;
+}
+
+// One warp builds branch node v of depth d (all 32 lanes must call).  Returns through lane 0's stores.
+template <bool COHERENT>
+__device__ __forceinline__ void warp_build_node(const ForestDev &f, uint32_t v, int d, uint8_t *buf, const WarpKeccak &kw,
+                                                int lane, uint32_t &hashed, uint32_t &exts, uint32_t (&out)[8]) {
+    uint32_t *bufw = reinterpret_cast<uint32_t *>(buf);
+    const uint32_t n = (uint32_t)f.n;
+    uint32_t j0 = f.node_start[v], k = f.node_start[v + 1] - j0;
+    if (k > 15) k = 15;
+    // ---- lane c <= k owns child c
+    const bool has = (uint32_t)lane <= k;
+    ChildInfo ci{0, 0, 0};
+    uint32_t ref[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t lext = 0, rext = 0;
+    if (has) {
+        ci = fetch_child_c<COHERENT>(f, j0, (uint32_t)lane);
+        const uint8_t *rp = ci.id < n ? f.leaf_ref + 32 * (uint64_t)ci.id : f.node_ref + 32 * (uint64_t)(ci.id - n);
+        if (COHERENT) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(rp);
+            uint4 x = __ldcg(q), y = __ldcg(q + 1);
+            ref[0] = x.x; ref[1] = x.y; ref[2] = x.z; ref[3] = x.w;
+            ref[4] = y.x; ref[5] = y.y; ref[6] = y.z; ref[7] = y.w;
+        } else {
+            load32_nc(rp, ref);
+        }
+        if (lane == 0) lext = ci.id < n ? ci.id : f.node_l[ci.id - n];
+        if ((uint32_t)lane == k) rext = ci.id < n ? ci.id : f.node_r[ci.id - n];
+    }
+    uint32_t clen = has ? ((ci.meta & META_LEN) ? (ci.meta & META_LEN) : 33u) : 0u;
+    uint32_t bit = has ? (1u << ci.nib) : 0u;
+    bool is_branch = has && ci.id >= n;
+    uint32_t hbit = (is_branch && !(ci.meta & META_EXT)) ? bit : 0u;
+    uint32_t tbit = (is_branch && (ci.meta & META_STORED)) ? bit : 0u;
+    if (hbit && (ci.meta & META_LEN) && f.retain_updates) atomicExch(f.err, B200_DEVERR_INLINE_HASH_CHILD);
+    uint32_t state_mask = __reduce_or_sync(0xffffffffu, bit);
+    uint32_t hash_mask = __reduce_or_sync(0xffffffffu, hbit);
+    uint32_t tree_mask = __reduce_or_sync(0xffffffffu, tbit);
+    uint32_t incl = clen;  // inclusive prefix sum of child lengths
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    uint32_t children_len = __shfl_sync(0xffffffffu, incl, (int)k);
+    uint32_t l = __shfl_sync(0xffffffffu, lext, 0), r = __shfl_sync(0xffffffffu, rext, (int)k);
+    uint32_t payload = children_len + (15 - k) + 1;
+    uint32_t hdr = list_header_len(payload), total = hdr + payload;
+    uint32_t blocks = total / 136 + 1;
+    for (uint32_t w = lane; w < blocks * 34; w += 32) bufw[w] = 0;
+    __syncwarp();
+    if (lane == 0) {
+        LinBuf lb{buf, 0};
+        put_list_header(lb, payload);
+    }
+    if (has) {  // child bytes at hdr + (lengths of earlier children) + (empty slots before this nibble)
+        uint32_t off = hdr + (incl - clen) + (ci.nib - (uint32_t)lane);
+        if ((ci.meta & META_LEN) == 0) {
+            buf[off++] = 0xa0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                buf[off++] = (uint8_t)ref[i];
+                buf[off++] = (uint8_t)(ref[i] >> 8);
+                buf[off++] = (uint8_t)(ref[i] >> 16);
+                buf[off++] = (uint8_t)(ref[i] >> 24);
+            }
+        } else {
+            for (uint32_t b = 0; b < clen; b++) buf[off++] = (uint8_t)byte_at(ref, b);
+        }
+    }
+    {  // empty slots: lane e < 16 owns nibble e
+        uint32_t cb = __popc(state_mask & ((1u << (lane & 15)) - 1));
+        uint32_t before = __shfl_sync(0xffffffffu, incl, cb ? (int)cb - 1 : 0);
+        if (lane < 16 && !((state_mask >> lane) & 1)) buf[hdr + (cb ? before : 0u) + ((uint32_t)lane - cb)] = 0x80;
+    }
+    if (lane == 16) {
+        buf[total - 1] = 0x80;  // value slot
+        buf[total] |= 0x01;     // pad10*1
+        buf[blocks * 136 - 1] |= 0x80;
+    }
+    __syncwarp();
+    // ---- parent depth, extension, hash (uniform control flow)
+    int pdl = depth_of(f.Lp[l]), pdr = depth_of(f.Lp[(uint64_t)r + 1]);
+    int pd = pdl > pdr ? pdl : pdr;
+    bool is_root = pd < 0, need_ext = pd + 1 < d;
+    uint32_t meta;
+    if (total >= 32 || (is_root && !need_ext)) {
+        uint64_t a = kw.hash(buf, blocks, lane);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint64_t w = shfl64(a, i);
+            out[2 * i] = (uint32_t)w;
+            out[2 * i + 1] = (uint32_t)(w >> 32);
+        }
+        meta = 0;
+        hashed += lane == 0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) out[i] = bufw[i];
+        meta = total;
+    }
+    if (need_ext) {
+        __syncwarp();
+        for (uint32_t w = lane; w < 34; w += 32) bufw[w] = 0;
+        __syncwarp();
+        uint32_t elen = 0;
+        if (lane == 0) {
+            LinBuf lb{buf, 0};
+            elen = encode_extension(lb, f.keys + 32 * (uint64_t)l, (uint32_t)(pd + 1), (uint32_t)d, out, meta);
+            buf[elen] |= 0x01;
+            buf[135] |= 0x80;
+        }
+        elen = __shfl_sync(0xffffffffu, elen, 0);
+        __syncwarp();
+        if (elen >= 32 || is_root) {
+            uint64_t a = kw.hash(buf, 1, lane);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint64_t w = shfl64(a, i);
+                out[2 * i] = (uint32_t)w;
+                out[2 * i + 1] = (uint32_t)(w >> 32);
+            }
+            meta = META_EXT;
+            hashed += lane == 0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) out[i] = bufw[i];
+            meta = elen | META_EXT;
+        }
+        exts += lane == 0;
+    }
+    if (lane == 0) {
+        if ((tree_mask | hash_mask) != 0) meta |= META_STORED;
+        store32(f.node_ref + 32 * (uint64_t)v, out);
+        f.node_meta[v] = (uint8_t)meta;
+        f.node_l[v] = l;
+        f.node_r[v] = r;
+        f.node_masks[v] = make_ushort4((unsigned short)state_mask, (unsigned short)tree_mask,
+                                       (unsigned short)hash_mask, (unsigned short)d);
+        f.S[l] = n + v;
+        f.E[r] = n + v;
+    }
+    __syncwarp();
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) branch_warp_kernel(ForestDev f, const uint32_t *__restrict__ node_order,
+                                                                uint32_t pos_lo, uint32_t pos_hi, int d) {
+    __shared__ __align__(16) uint8_t sbuf[WARPS][WARP_BUF];
+    if (*(volatile int *)f.err != B200_DEVERR_NONE) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpKeccak kw;
+    kw.init(lane);
+    uint32_t hashed = 0, exts = 0;
+    const uint32_t stride = gridDim.x * WARPS;
+    for (uint64_t p64 = (uint64_t)pos_lo + blockIdx.x * WARPS + warp; p64 < pos_hi; p64 += stride) {
+        uint32_t out[8];
+        warp_build_node<false>(f, __ldg(node_order + p64), d, sbuf[warp], kw, lane, hashed, exts, out);
+    }
+    if (lane == 0) {
+        if (hashed) atomicAdd(&f.counters[CNT_HASHED], (unsigned long long)hashed);
+        if (exts) atomicAdd(&f.counters[CNT_EXT], (unsigned long long)exts);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ incremental wavefront
+// pending[p] = number of dirty children of node p (dirty leaves and dirty branches), counted by walking up from
+// every dirty leaf and stopping at the first ancestor somebody else already reached.
+__global__ void mark_pending_kernel(ForestDev f, const uint32_t *__restrict__ idx, uint64_t m,
+                                    const uint32_t *__restrict__ leaf_parent, const uint32_t *__restrict__ node_parent,
+                                    uint32_t *__restrict__ pending) {
+    if (*(volatile int *)f.err != B200_DEVERR_NONE) return;
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    uint32_t p = leaf_parent[idx[t]];
+    while (p != 0xFFFFFFFFu) {
+        if (atomicAdd(&pending[p], 1u) != 0u) break;
+        p = node_parent[p];
+    }
+}
+
+// One warp per dirty leaf: overwrite + re-hash the leaf, then climb: whoever is the LAST dirty child to arrive at a
+// node re-hashes it and continues to its parent; everybody else retires.  The whole dirty-path re-hash of an update
+// is this single launch: its latency is (levels) x (one warp-built node), with no host round trip in between.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) wavefront_kernel(ForestDev f, uint8_t *__restrict__ accts,
+                                                              uint8_t *__restrict__ sroots,
+                                                              const uint8_t *__restrict__ new_accts,
+                                                              const uint8_t *__restrict__ new_sroots,
+                                                              const uint32_t *__restrict__ idx, uint64_t m,
+                                                              const uint32_t *__restrict__ leaf_parent,
+                                                              const uint32_t *__restrict__ node_parent,
+                                                              uint32_t *__restrict__ pending, uint32_t *__restrict__ dirty_list,
+                                                              uint32_t *__restrict__ dirty_count, uint8_t *__restrict__ root_out) {
+    __shared__ __align__(16) uint8_t sbuf[WARPS][WARP_BUF];
+    if (*(volatile int *)f.err != B200_DEVERR_NONE) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *buf = sbuf[warp];
+    uint32_t *bufw = reinterpret_cast<uint32_t *>(buf);
+    WarpKeccak kw;
+    kw.init(lane);
+    uint32_t hashed = 0, exts = 0;
+    const uint64_t t = (uint64_t)blockIdx.x * WARPS + warp;
+    if (t >= m) return;
+    const uint32_t i = idx[t];
+    // ---- the leaf
+    for (uint32_t w = lane; w < 68; w += 32) bufw[w] = 0;
+    __syncwarp();
+    int pdl = depth_of(f.Lp[i]), pdr = depth_of(f.Lp[(uint64_t)i + 1]);
+    int pd = pdl > pdr ? pdl : pdr;
+    uint32_t len = 0;
+    if (lane == 0) {
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(new_accts + 72 * t);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(accts + 72 * (uint64_t)i);
+#pragma unroll
+        for (int w = 0; w < 9; w++) dst[w] = src[w];
+        if (new_sroots && sroots) {
+            uint32_t r[8];
+            load32(new_sroots + 32 * t, r);
+            store32(sroots + 32 * (uint64_t)i, r);
+        }
+        uint32_t k[8];
+        load32(f.keys + 32 * (uint64_t)i, k);
+        LinBuf lb{buf, 0};
+        len = encode_leaf<LinBuf, true>(lb, k, pd, new_accts + 72 * t,
+                                        sroots ? (new_sroots ? new_sroots + 32 * t : sroots + 32 * (uint64_t)i) : nullptr,
+                                        f.err);
+        buf[len] |= 0x01;
+        buf[(len / 136 + 1) * 136 - 1] |= 0x80;
+    }
+    len = __shfl_sync(0xffffffffu, len, 0);
+    __syncwarp();
+    uint32_t out[8];
+    {
+        uint64_t a = kw.hash(buf, len / 136 + 1, lane);  // account leaves are >= 70 bytes: always hashed
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint64_t w = shfl64(a, q);
+            out[2 * q] = (uint32_t)w;
+            out[2 * q + 1] = (uint32_t)(w >> 32);
+        }
+        hashed += lane == 0;
+    }
+    if (lane == 0) {
+        store32(f.leaf_ref + 32 * (uint64_t)i, out);
+        f.leaf_meta[i] = 0;
+    }
+    __syncwarp();
+    // ---- climb
+    uint32_t p = leaf_parent[i];
+    bool top = true;  // true while `out` is the reference of the highest item this warp finished
+    while (p != 0xFFFFFFFFu) {
+        uint32_t last = 0;
+        if (lane == 0) {
+            __threadfence();  // publish what this warp wrote before announcing arrival
+            last = atomicSub(&pending[p], 1u) == 1u;
+            __threadfence();
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) {
+            top = false;
+            break;
+        }
+        int d = f.node_masks[p].w;
+        warp_build_node<true>(f, p, d, buf, kw, lane, hashed, exts, out);
+        if (lane == 0) dirty_list[atomicAdd(dirty_count, 1u)] = p;
+        p = node_parent[p];
+    }
+    if (top && lane == 0) store32(root_out, out);  // this warp re-hashed the root (or the only leaf)
+    if (lane == 0) {
         if (hashed) atomicAdd(&f.counters[CNT_HASHED], (unsigned long long)hashed);
         if (exts) atomicAdd(&f.counters[CNT_EXT], (unsigned long long)exts);
     }
@@ -863,7 +1235,7 @@ __global__ void __launch_bounds__(BLOCK) leaf_rehash_kernel(ForestDev f, uint8_t
         int pdl = depth_of(f.Lp[i]), pdr = depth_of(f.Lp[(uint64_t)i + 1]);
         int pd = pdl > pdr ? pdl : pdr;
         // plain loads: the account was written by this thread a moment ago
-        uint32_t len = encode_leaf<BLOCK, true>(s, k, pd, new_accts + 72 * t,
+        uint32_t len = encode_leaf<Strip<BLOCK>, true>(s, k, pd, new_accts + 72 * t,
                                                 sroots ? (new_sroots ? new_sroots + 32 * t : sroots + 32 * (uint64_t)i) : nullptr,
                                                 f.err);
         uint32_t ref[8];
@@ -930,7 +1302,7 @@ __global__ void frontier_kernel(ForestDev f, const uint64_t *__restrict__ bucket
             load32(f.keys + 32 * (uint64_t)item, k);
             const uint8_t *vp = ACCOUNT ? values + (uint64_t)sizeof(b200_account_dev) * item : values + 32 * (uint64_t)item;
             const uint8_t *sp = (ACCOUNT && storage_roots) ? storage_roots + 32 * (uint64_t)item : nullptr;
-            uint32_t len = encode_leaf<BLOCK, ACCOUNT>(s, k, 0, vp, sp, f.err);
+            uint32_t len = encode_leaf<Strip<BLOCK>, ACCOUNT>(s, k, 0, vp, sp, f.err);
             meta = strip_to_ref(s, len, false, ref, hashed);
         } else {
             uint32_t v = item - (uint32_t)f.n;
@@ -1114,6 +1486,14 @@ static cudaError_t launch_branch_class(const ForestDev &f, const uint32_t *node_
 cudaError_t launch_branch_level(const ForestDev &f, const uint32_t *node_order, uint32_t pos_lo, uint32_t pos_hi,
                                 int d, int cls, cudaStream_t st) {
     if (pos_hi <= pos_lo) return cudaSuccess;
+    if (cls < 0) {  // latency path: one warp per node
+        constexpr int WARPS = 4;
+        uint32_t cnt = pos_hi - pos_lo;
+        unsigned blocks = (cnt + WARPS - 1) / WARPS;
+        unsigned cap = (unsigned)sms() * 16;
+        branch_warp_kernel<WARPS><<<blocks < cap ? blocks : cap, WARPS * 32, 0, st>>>(f, node_order, pos_lo, pos_hi, d);
+        return cudaGetLastError();
+    }
     switch (cls) {
         case 0: return launch_branch_class<3, 34>(f, node_order, pos_lo, pos_hi, d, st);
         case 1: return launch_branch_class<7, 68>(f, node_order, pos_lo, pos_hi, d, st);
@@ -1198,6 +1578,23 @@ cudaError_t launch_root_from_frontier(const FrontierEntryDev *fr, uint8_t *root,
 }
 
 // ---- resident trie launchers
+cudaError_t launch_mark_pending(const ForestDev &f, const uint32_t *idx, uint64_t m, const uint32_t *leaf_parent,
+                                const uint32_t *node_parent, uint32_t *pending, cudaStream_t st) {
+    if (m == 0) return cudaSuccess;
+    mark_pending_kernel<<<blocks_for(m, 128), 128, 0, st>>>(f, idx, m, leaf_parent, node_parent, pending);
+    return cudaGetLastError();
+}
+cudaError_t launch_wavefront(const ForestDev &f, uint8_t *accts, uint8_t *sroots, const uint8_t *new_accts,
+                             const uint8_t *new_sroots, const uint32_t *idx, uint64_t m, const uint32_t *leaf_parent,
+                             const uint32_t *node_parent, uint32_t *pending, uint32_t *dirty_list, uint32_t *dirty_count,
+                             uint8_t *root_out, cudaStream_t st) {
+    if (m == 0) return cudaSuccess;
+    constexpr int WARPS = 4;
+    wavefront_kernel<WARPS><<<blocks_for(m, WARPS), WARPS * 32, 0, st>>>(f, accts, sroots, new_accts, new_sroots, idx, m,
+                                                                        leaf_parent, node_parent, pending, dirty_list,
+                                                                        dirty_count, root_out);
+    return cudaGetLastError();
+}
 cudaError_t launch_stored_flags_subset(const ForestDev &f, const uint32_t *ids, uint32_t count, uint8_t *flags,
                                        uint32_t *n_hashes, cudaStream_t st) {
     if (count == 0) return cudaSuccess;
