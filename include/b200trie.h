@@ -96,6 +96,12 @@ B200_API int32_t b200_hash_sort_keys(b200_ctx *, const uint8_t *in, uint32_t msg
                             uint8_t *out_sorted32, uint32_t *out_perm);
 B200_API int32_t b200_hash_sort_keys_dev(b200_ctx *, const void *d_in, uint32_t msg_len, uint32_t stride, uint64_t n,
                                 void *d_sorted32, void *d_perm_u32);
+/* StorageHashingStage full pass (hashing_storage.rs:106-178): entry i is (addresses20[addr_index[i]], slots32[i]).
+ * Every address is hashed once, every slot key once, and the entries are sorted by the 64-byte composite key
+ * keccak(address) || keccak(slot): out_sorted64[i] is the i-th smallest composite key, out_perm[i] the entry it
+ * came from.  A duplicate (address, slot) pair yields B200_ERR_UNSORTED. */
+B200_API int32_t b200_hash_sort_storage(b200_ctx *, const uint8_t *addresses20, uint32_t n_addr, const uint32_t *addr_index,
+                                        const uint8_t *slots32, uint64_t n, uint8_t *out_sorted64, uint32_t *out_perm);
 /* The sort half alone: n 32-byte keys (already digests) -> ascending order + permutation. */
 B200_API int32_t b200_sort_keys32_dev(b200_ctx *, const void *d_keys32, uint64_t n, void *d_sorted32, void *d_perm_u32);
 

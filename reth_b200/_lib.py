@@ -102,6 +102,7 @@ def load():
     sig("b200_hash_sort_keys", i32, vp, vp, u32, u32, u64, vp, vp)
     sig("b200_hash_sort_keys_dev", i32, vp, vp, u32, u32, u64, vp, vp)
     sig("b200_sort_keys32_dev", i32, vp, vp, u64, vp, vp)
+    sig("b200_hash_sort_storage", i32, vp, vp, u32, vp, vp, u64, vp, vp)
     sig("b200_updates_release", None, PU)
     sig("b200_storage_roots", i32, vp, vp, vp, vp, u64, vp, PU, PS)
     sig("b200_state_root", i32, vp, vp, vp, vp, u64, vp, PU, PS)

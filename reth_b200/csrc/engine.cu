@@ -312,6 +312,40 @@ extern "C" B200_API int32_t b200_hash_sort_keys(b200_ctx *c, const uint8_t *in, 
     return B200_OK;
 }
 
+int32_t sort_composite_on_device(b200_ctx *c, const void *d_ha, uint32_t n_addr, const uint32_t *d_addr_index,
+                                 const void *d_hs, uint64_t n, void *d_sorted, uint32_t *d_perm, DevBuf &keys_a,
+                                 DevBuf &keys_b, DevBuf &idx_a, DevBuf &flag);
+
+// StorageHashingStage full pass: hash n_addr addresses once, n slot keys, sort entries by keccak(address) || keccak(slot).
+extern "C" B200_API int32_t b200_hash_sort_storage(b200_ctx *c, const uint8_t *addresses20, uint32_t n_addr,
+                                                   const uint32_t *addr_index, const uint8_t *slots32, uint64_t n,
+                                                   uint8_t *out_sorted64, uint32_t *out_perm) {
+    if (!c || (n && (!addresses20 || !addr_index || !slots32 || !out_sorted64 || !out_perm)) || (n && !n_addr))
+        return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    if (n == 0) return B200_OK;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ENSURE(in_a, (size_t)n_addr * 20);
+    ENSURE(in_b, n * 32);
+    ENSURE(in_c, n * 4);
+    ENSURE(in_d, (size_t)n_addr * 32);  // address digests
+    ENSURE(out_a, n * 32);              // slot digests
+    ENSURE(sort_out, n * 64);
+    ENSURE(sort_perm, n * 4);
+    CU(cudaMemcpyAsync(c->in_a.p, addresses20, (size_t)n_addr * 20, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->in_b.p, slots32, n * 32, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->in_c.p, addr_index, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(launch_keccak256_fixed(c->in_a.p, 20, 20, n_addr, c->in_d.p, c->stream, &c->launches));
+    CU(launch_keccak256_fixed(c->in_b.p, 32, 32, n, c->out_a.p, c->stream, &c->launches));
+    TRY(sort_composite_on_device(c, c->in_d.p, n_addr, static_cast<const uint32_t *>(c->in_c.p), c->out_a.p, n,
+                                 c->sort_out.p, static_cast<uint32_t *>(c->sort_perm.p), c->sort_ka, c->sort_kb,
+                                 c->sort_ia, c->sort_flag));
+    CU(cudaMemcpyAsync(out_sorted64, c->sort_out.p, n * 64, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(out_perm, c->sort_perm.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B200_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ forest build
 struct IsBoundary {
     __host__ __device__ uint32_t operator()(uint8_t v) const { return v == 0xFF ? 1u : 0u; }
@@ -321,6 +355,7 @@ struct Built {
     ForestDev f{};
     uint32_t n_nodes = 0;
     uint32_t levels = 0;
+    uint32_t level_count[64] = {};  // branch nodes per depth
 };
 
 // Builds every trie of a forest over d_keys (n leaves).  d_seg_offsets == nullptr: one trie.
@@ -454,6 +489,7 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
         uint32_t cnt = hc[0] + hc[1] + hc[2] + hc[3];
         if (!cnt) continue;
         out.levels++;
+        out.level_count[d] = cnt;
         if (cnt <= WARP_LEVEL_MAX) {  // about one wave of warps: latency-bound, one warp per node
             CU(launch_branch_level(f, norder, pos, pos + cnt, d, -1, st));
             c->launches++;
@@ -1018,6 +1054,7 @@ struct b200_trie {
     ForestDev f{};
     bool has_sroots = false;
     uint64_t bytes = 0;
+    uint32_t level_count[64] = {};
     DevBuf keys, accts, sroots, Lp, nibs, leaf_ref, leaf_meta, S, E, gap_sorted, node_start, node_ref, node_meta, node_l,
         node_r, node_masks, leaf_parent, node_parent, dirty, dirty_ids, dirty_key, dirty_key2, dirty_order, idx, in_keys,
         in_accts, in_sroots, root;
@@ -1073,6 +1110,7 @@ static int32_t trie_build_owned(b200_trie *t) {
     TRY(sync_and_status(c));
     t->f = b.f;
     t->B = b.n_nodes;
+    memcpy(t->level_count, b.level_count, sizeof t->level_count);
     // the build's arrays become the trie's: same pointers, new owner; the context re-allocates on its next build
     steal(t, t->Lp, c->Lp);
     steal(t, t->nibs, c->nibs);
@@ -1173,10 +1211,31 @@ static int32_t trie_update_on_device(b200_trie *t, const uint8_t *d_keys, const 
     CU(launch_locate(static_cast<const uint8_t *>(t->keys.p), t->n, d_keys, m, idx, f.err, st));
     CU(launch_mark_pending(f, idx, m, static_cast<uint32_t *>(t->leaf_parent.p), static_cast<uint32_t *>(t->node_parent.p),
                            static_cast<uint32_t *>(t->dirty.p), st));
-    CU(launch_wavefront(f, static_cast<uint8_t *>(t->accts.p), t->has_sroots ? static_cast<uint8_t *>(t->sroots.p) : nullptr,
-                        d_accts, d_sroots, idx, m, static_cast<uint32_t *>(t->leaf_parent.p),
-                        static_cast<uint32_t *>(t->node_parent.p), static_cast<uint32_t *>(t->dirty.p),
-                        static_cast<uint32_t *>(t->dirty_ids.p), count_p, static_cast<uint8_t *>(t->root.p), st));
+    // Populous deep levels (more dirty nodes than a wave of warps can absorb cheaply) are climbed by one thread per
+    // leaf with the register-resident sponge; the sparse levels above by one warp per node (shuffle sponge).
+    int split = 65;  // 65: everything warp-cooperative
+    if (m > WARP_LEVEL_MAX)
+        for (int d = 0; d < 64; d++)
+            if (std::min<uint64_t>(m, t->level_count[d]) > WARP_LEVEL_MAX) {
+                split = d;
+                break;
+            }
+    uint8_t *accts = static_cast<uint8_t *>(t->accts.p);
+    uint8_t *sroots = t->has_sroots ? static_cast<uint8_t *>(t->sroots.p) : nullptr;
+    uint32_t *lp = static_cast<uint32_t *>(t->leaf_parent.p), *np = static_cast<uint32_t *>(t->node_parent.p);
+    uint32_t *pending = static_cast<uint32_t *>(t->dirty.p), *dlist = static_cast<uint32_t *>(t->dirty_ids.p);
+    if (split == 65) {
+        CU(launch_wavefront(f, accts, sroots, d_accts, d_sroots, idx, m, lp, np, pending, dlist, count_p,
+                            static_cast<uint8_t *>(t->root.p), st));
+    } else {
+        TRY(trie_alloc(t, t->dirty_order, m * 4));  // hand-over list: at most one entry per dirty leaf
+        uint32_t *hcount = small_u32(c) + SM_NNODES + 1;
+        CU(cudaMemsetAsync(hcount, 0, 4, st));
+        CU(launch_wavefront_two_stage(f, accts, sroots, d_accts, d_sroots, idx, m, lp, np, pending, dlist, count_p,
+                                      static_cast<uint32_t *>(t->dirty_order.p), hcount, m,
+                                      static_cast<uint8_t *>(t->root.p), split, st));
+        c->launches++;
+    }
     c->launches += 3;
     c->stats.leaves_added += m;
     c->stats_wavefront = true;

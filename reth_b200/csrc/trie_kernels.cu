@@ -550,7 +550,7 @@ __device__ __forceinline__ uint32_t encode_extension(W &s, const uint8_t *key, u
 // Class-specialised variant of encode_branch: at most MAXC children, every per-child quantity lives in registers
 // and all the dependent global loads of a phase (gap -> S/E -> meta -> ref) are issued back to back for the
 // whole node before any of them is consumed, so one thread keeps up to MAXC requests in flight.
-template <int BLOCK, int MAXC>
+template <int BLOCK, int MAXC, bool COHERENT = false>
 __device__ __forceinline__ uint32_t encode_branch_u(Strip<BLOCK> &s, const ForestDev &f, uint32_t j0, uint32_t k,
                                                     uint32_t &state_mask, uint32_t &tree_mask, uint32_t &hash_mask,
                                                     uint32_t &l, uint32_t &r) {
@@ -572,7 +572,10 @@ __device__ __forceinline__ uint32_t encode_branch_u(Strip<BLOCK> &s, const Fores
     }
 #pragma unroll
     for (int c = 0; c < MAXC; c++)
-        if ((uint32_t)c <= k) nm[c] |= (uint32_t)(id[c] < n ? f.leaf_meta[id[c]] : f.node_meta[id[c] - n]) << 8;
+        if ((uint32_t)c <= k) {
+            const uint8_t *mp = id[c] < n ? f.leaf_meta + id[c] : f.node_meta + (id[c] - n);
+            nm[c] |= (uint32_t)(COHERENT ? __ldcg(mp) : *mp) << 8;
+        }
     uint32_t payload = 17;
     state_mask = tree_mask = hash_mask = 0;
     uint32_t last = id[0];
@@ -602,7 +605,14 @@ __device__ __forceinline__ uint32_t encode_branch_u(Strip<BLOCK> &s, const Fores
         if ((uint32_t)c <= k) {
             const uint8_t *rp = id[c] < n ? f.leaf_ref + 32 * (uint64_t)id[c] : f.node_ref + 32 * (uint64_t)(id[c] - n);
             uint32_t ref[8];
-            load32_nc(rp, ref);
+            if (COHERENT) {
+                const uint4 *q = reinterpret_cast<const uint4 *>(rp);
+                uint4 x = __ldcg(q), y = __ldcg(q + 1);
+                ref[0] = x.x; ref[1] = x.y; ref[2] = x.z; ref[3] = x.w;
+                ref[4] = y.x; ref[5] = y.y; ref[6] = y.z; ref[7] = y.w;
+            } else {
+                load32_nc(rp, ref);
+            }
             uint32_t nibble = nm[c] & 15;
             for (; cur < nibble; cur++) s.byte(0x80);
             uint32_t clen = (nm[c] >> 8) & META_LEN;
@@ -620,6 +630,38 @@ __device__ __forceinline__ uint32_t encode_branch_u(Strip<BLOCK> &s, const Fores
     return list_header_len(payload) + payload;
 }
 
+// One thread builds branch node v of depth d into its strip, hashes it and publishes it (node arrays, S/E).
+template <int BLOCK, int MAXC, bool COHERENT>
+__device__ __forceinline__ void thread_build_node(Strip<BLOCK> &s, uint32_t *smem, const ForestDev &f, uint32_t v, int d,
+                                                  uint32_t &hashed, uint32_t &exts, uint32_t (&ref)[8]) {
+    s.init(smem);
+    uint32_t j0 = f.node_start[v], k = f.node_start[v + 1] - j0;
+    if (k + 1 > (uint32_t)MAXC) k = MAXC - 1;  // cannot happen for well-formed input; keeps the strip in bounds
+    uint32_t state_mask, tree_mask, hash_mask, l, r;
+    uint32_t len = encode_branch_u<BLOCK, MAXC, COHERENT>(s, f, j0, k, state_mask, tree_mask, hash_mask, l, r);
+    int pdl = depth_of(f.Lp[l]), pdr = depth_of(f.Lp[(uint64_t)r + 1]);
+    int pd = pdl > pdr ? pdl : pdr;
+    bool is_root = pd < 0;
+    bool need_ext = pd + 1 < d;
+    uint32_t meta = strip_to_ref(s, len, is_root && !need_ext, ref, hashed);
+    if (need_ext) {
+        s.reset();
+        uint32_t elen = encode_extension(s, f.keys + 32 * (uint64_t)l, (uint32_t)(pd + 1), (uint32_t)d, ref, meta);
+        meta = strip_to_ref(s, elen, is_root, ref, hashed) | META_EXT;
+        exts++;
+    }
+    bool stored = (tree_mask | hash_mask) != 0;
+    if (stored) meta |= META_STORED;
+    store32(f.node_ref + 32 * (uint64_t)v, ref);
+    f.node_meta[v] = (uint8_t)meta;
+    f.node_l[v] = l;
+    f.node_r[v] = r;
+    f.node_masks[v] = make_ushort4((unsigned short)state_mask, (unsigned short)tree_mask, (unsigned short)hash_mask,
+                                   (unsigned short)d);
+    f.S[l] = (uint32_t)f.n + v;
+    f.E[r] = (uint32_t)f.n + v;
+}
+
 // One thread per branch node of depth d.  MAXC bounds the children of every node in [pos_lo, pos_hi) (the level's
 // nodes are grouped by child-count class); the strip is sized for that class, which is what sets the occupancy.
 template <int BLOCK, int MAXC>
@@ -631,34 +673,8 @@ __global__ void __launch_bounds__(BLOCK) branch_kernel(ForestDev f, const uint32
     uint32_t hashed = 0, exts = 0;
     const uint32_t step = gridDim.x * BLOCK;
     for (uint64_t p64 = (uint64_t)pos_lo + blockIdx.x * BLOCK + threadIdx.x; p64 < pos_hi; p64 += step) {
-        uint32_t v = __ldg(node_order + p64);
-        s.init(smem);
-        uint32_t j0 = f.node_start[v], k = f.node_start[v + 1] - j0;
-        if (k + 1 > (uint32_t)MAXC) k = MAXC - 1;  // cannot happen for well-formed input; keeps the strip in bounds
-        uint32_t state_mask, tree_mask, hash_mask, l, r;
-        uint32_t len = encode_branch_u<BLOCK, MAXC>(s, f, j0, k, state_mask, tree_mask, hash_mask, l, r);
-        int pdl = depth_of(f.Lp[l]), pdr = depth_of(f.Lp[(uint64_t)r + 1]);
-        int pd = pdl > pdr ? pdl : pdr;
-        bool is_root = pd < 0;
-        bool need_ext = pd + 1 < d;
         uint32_t ref[8];
-        uint32_t meta = strip_to_ref(s, len, is_root && !need_ext, ref, hashed);
-        if (need_ext) {
-            s.reset();
-            uint32_t elen = encode_extension(s, f.keys + 32 * (uint64_t)l, (uint32_t)(pd + 1), (uint32_t)d, ref, meta);
-            meta = strip_to_ref(s, elen, is_root, ref, hashed) | META_EXT;
-            exts++;
-        }
-        bool stored = (tree_mask | hash_mask) != 0;
-        if (stored) meta |= META_STORED;
-        store32(f.node_ref + 32 * (uint64_t)v, ref);
-        f.node_meta[v] = (uint8_t)meta;
-        f.node_l[v] = l;
-        f.node_r[v] = r;
-        f.node_masks[v] = make_ushort4((unsigned short)state_mask, (unsigned short)tree_mask,
-                                       (unsigned short)hash_mask, (unsigned short)d);
-        f.S[l] = (uint32_t)f.n + v;
-        f.E[r] = (uint32_t)f.n + v;
+        thread_build_node<BLOCK, MAXC, false>(s, smem, f, __ldg(node_order + p64), d, hashed, exts, ref);
     }
     for (int o = 16; o; o >>= 1) {
         hashed += __shfl_xor_sync(0xffffffffu, hashed, o);
@@ -948,6 +964,29 @@ __global__ void mark_pending_kernel(ForestDev f, const uint32_t *__restrict__ id
     }
 }
 
+// A warp that just finished a dirty item climbs from its parent p: whoever is the LAST dirty child to arrive at a
+// node re-hashes it and goes on; everybody else retires.  Returns true iff this warp finished the root.
+__device__ __forceinline__ bool warp_climb(const ForestDev &f, uint32_t p, const uint32_t *__restrict__ node_parent,
+                                           uint32_t *__restrict__ pending, uint32_t *__restrict__ dirty_list,
+                                           uint32_t *__restrict__ dirty_count, uint8_t *buf, const WarpKeccak &kw, int lane,
+                                           uint32_t &hashed, uint32_t &exts, uint32_t (&out)[8]) {
+    while (p != 0xFFFFFFFFu) {
+        uint32_t last = 0;
+        if (lane == 0) {
+            __threadfence();  // publish what this warp wrote before announcing arrival
+            last = atomicSub(&pending[p], 1u) == 1u;
+            __threadfence();
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) return false;
+        int d = f.node_masks[p].w;
+        warp_build_node<true>(f, p, d, buf, kw, lane, hashed, exts, out);
+        if (lane == 0) dirty_list[atomicAdd(dirty_count, 1u)] = p;
+        p = node_parent[p];
+    }
+    return true;
+}
+
 // One warp per dirty leaf: overwrite + re-hash the leaf, then climb: whoever is the LAST dirty child to arrive at a
 // node re-hashes it and continues to its parent; everybody else retires.  The whole dirty-path re-hash of an update
 // is this single launch: its latency is (levels) x (one warp-built node), with no host round trip in between.
@@ -1016,26 +1055,108 @@ __global__ void __launch_bounds__(WARPS * 32) wavefront_kernel(ForestDev f, uint
     }
     __syncwarp();
     // ---- climb
-    uint32_t p = leaf_parent[i];
-    bool top = true;  // true while `out` is the reference of the highest item this warp finished
-    while (p != 0xFFFFFFFFu) {
-        uint32_t last = 0;
-        if (lane == 0) {
-            __threadfence();  // publish what this warp wrote before announcing arrival
-            last = atomicSub(&pending[p], 1u) == 1u;
-            __threadfence();
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (!last) {
-            top = false;
-            break;
-        }
-        int d = f.node_masks[p].w;
-        warp_build_node<true>(f, p, d, buf, kw, lane, hashed, exts, out);
-        if (lane == 0) dirty_list[atomicAdd(dirty_count, 1u)] = p;
-        p = node_parent[p];
-    }
+    bool top = warp_climb(f, leaf_parent[i], node_parent, pending, dirty_list, dirty_count, buf, kw, lane, hashed, exts, out);
     if (top && lane == 0) store32(root_out, out);  // this warp re-hashed the root (or the only leaf)
+    if (lane == 0) {
+        if (hashed) atomicAdd(&f.counters[CNT_HASHED], (unsigned long long)hashed);
+        if (exts) atomicAdd(&f.counters[CNT_EXT], (unsigned long long)exts);
+    }
+}
+
+// ---- two-stage variant for large dirty sets -----------------------------------------------------------------------
+// Stage A: one THREAD per dirty leaf (register-resident sponge: the ALU-efficient formulation) hashes the leaf and
+// climbs through the populous deep levels (depth >= split_depth); when the next ancestor is shallower it hands the
+// parent over.  Stage B (climb_kernel): one WARP per hand-over finishes the sparse upper levels with the
+// latency-optimised warp-cooperative node builder.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) wavefront_thread_kernel(
+    ForestDev f, uint8_t *__restrict__ accts, uint8_t *__restrict__ sroots, const uint8_t *__restrict__ new_accts,
+    const uint8_t *__restrict__ new_sroots, const uint32_t *__restrict__ idx, uint64_t m,
+    const uint32_t *__restrict__ leaf_parent, const uint32_t *__restrict__ node_parent, uint32_t *__restrict__ pending,
+    uint32_t *__restrict__ dirty_list, uint32_t *__restrict__ dirty_count, uint32_t *__restrict__ handoff_list,
+    uint32_t *__restrict__ handoff_count, uint8_t *__restrict__ root_out, int split_depth) {
+    extern __shared__ uint32_t smem[];
+    if (*(volatile int *)f.err != B200_DEVERR_NONE) return;
+    Strip<BLOCK> s;
+    uint32_t hashed = 0, exts = 0;
+    uint64_t t = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (t < m) {
+        const uint32_t i = idx[t];
+        s.init(smem);
+        {
+            const uint64_t *src = reinterpret_cast<const uint64_t *>(new_accts + 72 * t);
+            uint64_t *dst = reinterpret_cast<uint64_t *>(accts + 72 * (uint64_t)i);
+#pragma unroll
+            for (int w = 0; w < 9; w++) dst[w] = src[w];
+            if (new_sroots && sroots) {
+                uint32_t r[8];
+                load32(new_sroots + 32 * t, r);
+                store32(sroots + 32 * (uint64_t)i, r);
+            }
+        }
+        uint32_t k[8];
+        load32(f.keys + 32 * (uint64_t)i, k);
+        int pdl = depth_of(f.Lp[i]), pdr = depth_of(f.Lp[(uint64_t)i + 1]);
+        int pd = pdl > pdr ? pdl : pdr;
+        uint32_t len = encode_leaf<Strip<BLOCK>, true>(
+            s, k, pd, new_accts + 72 * t, sroots ? (new_sroots ? new_sroots + 32 * t : sroots + 32 * (uint64_t)i) : nullptr,
+            f.err);
+        uint32_t ref[8];
+        uint32_t meta = strip_to_ref(s, len, pd < 0, ref, hashed);
+        store32(f.leaf_ref + 32 * (uint64_t)i, ref);
+        f.leaf_meta[i] = (uint8_t)meta;
+        uint32_t p = leaf_parent[i];
+        bool top = true;
+        while (p != 0xFFFFFFFFu) {
+            int d = f.node_masks[p].w;
+            if (d < split_depth) {
+                __threadfence();
+                handoff_list[atomicAdd(handoff_count, 1u)] = p;
+                top = false;
+                break;
+            }
+            __threadfence();
+            bool last = atomicSub(&pending[p], 1u) == 1u;
+            __threadfence();
+            if (!last) {
+                top = false;
+                break;
+            }
+            thread_build_node<BLOCK, 16, true>(s, smem, f, p, d, hashed, exts, ref);
+            dirty_list[atomicAdd(dirty_count, 1u)] = p;
+            p = node_parent[p];
+        }
+        if (top) store32(root_out, ref);
+    }
+    for (int o = 16; o; o >>= 1) {
+        hashed += __shfl_xor_sync(0xffffffffu, hashed, o);
+        exts += __shfl_xor_sync(0xffffffffu, exts, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (hashed) atomicAdd(&f.counters[CNT_HASHED], (unsigned long long)hashed);
+        if (exts) atomicAdd(&f.counters[CNT_EXT], (unsigned long long)exts);
+    }
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) climb_kernel(ForestDev f, const uint32_t *__restrict__ start_list,
+                                                          const uint32_t *__restrict__ start_count_p,
+                                                          const uint32_t *__restrict__ node_parent,
+                                                          uint32_t *__restrict__ pending, uint32_t *__restrict__ dirty_list,
+                                                          uint32_t *__restrict__ dirty_count, uint8_t *__restrict__ root_out) {
+    __shared__ __align__(16) uint8_t sbuf[WARPS][WARP_BUF];
+    if (*(volatile int *)f.err != B200_DEVERR_NONE) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpKeccak kw;
+    kw.init(lane);
+    uint32_t hashed = 0, exts = 0;
+    const uint32_t count = *start_count_p;
+    for (uint32_t e = blockIdx.x * WARPS + warp; e < count; e += gridDim.x * WARPS) {
+        uint32_t out[8];
+        bool top = warp_climb(f, start_list[e], node_parent, pending, dirty_list, dirty_count, sbuf[warp], kw, lane, hashed,
+                              exts, out);
+        if (top && lane == 0) store32(root_out, out);
+    }
     if (lane == 0) {
         if (hashed) atomicAdd(&f.counters[CNT_HASHED], (unsigned long long)hashed);
         if (exts) atomicAdd(&f.counters[CNT_EXT], (unsigned long long)exts);
@@ -1578,6 +1699,32 @@ cudaError_t launch_root_from_frontier(const FrontierEntryDev *fr, uint8_t *root,
 }
 
 // ---- resident trie launchers
+cudaError_t launch_wavefront_two_stage(const ForestDev &f, uint8_t *accts, uint8_t *sroots, const uint8_t *new_accts,
+                                       const uint8_t *new_sroots, const uint32_t *idx, uint64_t m,
+                                       const uint32_t *leaf_parent, const uint32_t *node_parent, uint32_t *pending,
+                                       uint32_t *dirty_list, uint32_t *dirty_count, uint32_t *handoff_list,
+                                       uint32_t *handoff_count, uint64_t max_handoff, uint8_t *root_out, int split_depth,
+                                       cudaStream_t st) {
+    if (m == 0) return cudaSuccess;
+    constexpr int TB = 64;
+    auto ka = wavefront_thread_kernel<TB>;
+    size_t smem = (size_t)BRANCH_WORDS * TB * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    ka<<<blocks_for(m, TB), TB, smem, st>>>(f, accts, sroots, new_accts, new_sroots, idx, m, leaf_parent, node_parent, pending,
+                                            dirty_list, dirty_count, handoff_list, handoff_count, root_out, split_depth);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    constexpr int WARPS = 4;
+    unsigned blocks = blocks_for(max_handoff ? max_handoff : 1, WARPS);
+    unsigned cap = (unsigned)sms() * 16;
+    climb_kernel<WARPS><<<blocks < cap ? blocks : cap, WARPS * 32, 0, st>>>(f, handoff_list, handoff_count, node_parent, pending,
+                                                                         dirty_list, dirty_count, root_out);
+    return cudaGetLastError();
+}
 cudaError_t launch_mark_pending(const ForestDev &f, const uint32_t *idx, uint64_t m, const uint32_t *leaf_parent,
                                 const uint32_t *node_parent, uint32_t *pending, cudaStream_t st) {
     if (m == 0) return cudaSuccess;

@@ -113,6 +113,12 @@ cudaError_t launch_wavefront(const ForestDev &f, uint8_t *accts, uint8_t *sroots
                              const uint8_t *new_sroots, const uint32_t *idx, uint64_t m, const uint32_t *leaf_parent,
                              const uint32_t *node_parent, uint32_t *pending, uint32_t *dirty_list, uint32_t *dirty_count,
                              uint8_t *root_out, cudaStream_t st);
+cudaError_t launch_wavefront_two_stage(const ForestDev &f, uint8_t *accts, uint8_t *sroots, const uint8_t *new_accts,
+                                       const uint8_t *new_sroots, const uint32_t *idx, uint64_t m,
+                                       const uint32_t *leaf_parent, const uint32_t *node_parent, uint32_t *pending,
+                                       uint32_t *dirty_list, uint32_t *dirty_count, uint32_t *handoff_list,
+                                       uint32_t *handoff_count, uint64_t max_handoff, uint8_t *root_out, int split_depth,
+                                       cudaStream_t st);
 cudaError_t launch_stored_flags_subset(const ForestDev &f, const uint32_t *ids, uint32_t count, uint8_t *flags,
                                        uint32_t *n_hashes, cudaStream_t st);
 cudaError_t launch_pick_subset(const uint32_t *ids, const uint32_t *prefix, const uint32_t *sel_pos, uint32_t n_sel,

@@ -151,6 +151,19 @@ class Engine:
         self._check(self.lib.b200_hash_sort_keys(self.ctx, _ptr(msgs), msg_len or stride, stride, n, _ptr(out), _ptr(perm)))
         return out, perm
 
+    def hash_sort_storage(self, addresses: np.ndarray, addr_index: np.ndarray, slots: np.ndarray):
+        """StorageHashing full pass: entry i = (addresses[addr_index[i]], slots[i]) -> (composite keys uint8[n,64]
+        sorted ascending, perm uint32[n])."""
+        addresses = _np(addresses).reshape(-1, 20)
+        addr_index = _np(addr_index, np.uint32)
+        slots = _np(slots).reshape(-1, 32)
+        n = len(slots)
+        out = np.empty((n, 64), np.uint8)
+        perm = np.empty(n, np.uint32)
+        self._check(self.lib.b200_hash_sort_storage(self.ctx, _ptr(addresses), len(addresses), _ptr(addr_index),
+                                                    _ptr(slots), n, _ptr(out), _ptr(perm)))
+        return out, perm
+
     # device-resident (torch) variants ------------------------------------------------------------
     def keccak256_fixed_dev(self, t_in, msg_len: int, stride: int, n: int, t_out):
         self._check(self.lib.b200_keccak256_fixed_dev(self.ctx, t_in.data_ptr(), msg_len, stride, n, t_out.data_ptr()))

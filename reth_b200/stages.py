@@ -62,8 +62,6 @@ class StorageHashingStage:
         t.hashed_storages = {}
         if not addrs:
             return 0
-        ha = self.engine.keccak256_fixed(np.frombuffer(b"".join(addrs), np.uint8).reshape(len(addrs), 20))
-        total = 0
         slot_rows, owners, values = [], [], []
         for i, a in enumerate(addrs):
             for slot, val in t.plain_storage[a].items():
@@ -72,13 +70,15 @@ class StorageHashingStage:
                 slot_rows.append(int(slot).to_bytes(32, "big"))
                 owners.append(i)
                 values.append(val)
-        if slot_rows:
-            hs = self.engine.keccak256_fixed(np.frombuffer(b"".join(slot_rows), np.uint8).reshape(len(slot_rows), 32))
-            for h, o, v in zip(hs, owners, values):
-                t.hashed_storages.setdefault(ha[o].tobytes(), []).append((h.tobytes(), v))
-                total += 1
-        for k in t.hashed_storages:
-            t.hashed_storages[k].sort()
+        total = len(slot_rows)
+        if total:
+            # one device call: hash each address once, each slot once, sort by keccak(address) || keccak(slot)
+            keys, perm = self.engine.hash_sort_storage(
+                np.frombuffer(b"".join(addrs), np.uint8).reshape(len(addrs), 20), np.array(owners, np.uint32),
+                np.frombuffer(b"".join(slot_rows), np.uint8).reshape(total, 32))
+            for i in range(total):  # rows arrive in table order (append_dup, hashing_storage.rs:150-170)
+                t.hashed_storages.setdefault(keys[i, :32].tobytes(), []).append(
+                    (keys[i, 32:].tobytes(), values[int(perm[i])]))
         return total
 
 

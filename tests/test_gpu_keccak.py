@@ -119,3 +119,36 @@ def test_device_resident_path(eng):
     torch.cuda.synchronize()
     eng.set_stream(None)
     assert (out.cpu().numpy() == oracle.keccak256_fixed(keys, threads=4)).all()
+
+
+def test_hash_sort_storage_composite(eng):
+    """StorageHashing full pass (hashing_storage.rs:106-178): rows sorted by keccak(address) || keccak(slot)."""
+    rng = np.random.default_rng(3)
+    n_addr, n = 5000, 120_000
+    addrs = random_keys(5, n_addr)[:, :20].copy()
+    owner = rng.integers(0, n_addr, n).astype(np.uint32)
+    owner[:40_000] = 7                      # one contract with a large storage: identical address prefix everywhere
+    slots = random_keys(6, n)
+    keys, perm = eng.hash_sort_storage(addrs, owner, slots)
+    ha = oracle.keccak256_fixed(addrs, threads=4)
+    hs = oracle.keccak256_fixed(slots, threads=4)
+    comp = np.concatenate([ha[owner], hs], axis=1)
+    v = comp.view(">u8")
+    order = np.lexsort(tuple(v[:, i] for i in range(7, -1, -1)))
+    assert (keys == comp[order]).all()
+    assert (perm.astype(np.int64) == order).all()
+
+
+def test_hash_sort_storage_rejects_duplicates_and_bad_index(eng):
+    from reth_b200 import B200Error, _lib
+    addrs = random_keys(5, 4)[:, :20].copy()
+    slots = random_keys(6, 8)
+    slots[5] = slots[2]
+    owner = np.array([0, 1, 2, 3, 0, 2, 1, 3], np.uint32)
+    with pytest.raises(B200Error) as e:
+        eng.hash_sort_storage(addrs, owner, slots)
+    assert e.value.status == _lib.ERR_UNSORTED
+    owner[0] = 9
+    with pytest.raises(B200Error) as e:
+        eng.hash_sort_storage(addrs, owner, random_keys(7, 8))
+    assert e.value.status == _lib.ERR_INVALID_ARG
