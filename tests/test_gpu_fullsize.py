@@ -1,0 +1,135 @@
+"""Size-independent properties at BASELINE.json's full sizes (C2: 10M keys, C3: 1M accounts x 16 slots, C5: resident
+trie updates), where the oracle is too slow to recompute everything: sampled digests against the oracle,
+permutation equivariance, sharded == monolithic == pipelined roots, update/revert round trips."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from reth_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def test_c2_ten_million_keys(eng):
+    import torch
+    from bench import random_keys_torch
+    n = 10_000_000
+    dev = torch.device("cuda", 0)
+    keys = random_keys_torch(2, n, dev).view(torch.uint8).view(n, 32)
+    out = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    eng.use_torch_stream()
+    eng.keccak256_fixed_dev(keys, 32, 32, n, out)
+    # permutation equivariance: hashing a permuted batch permutes the digests (no cross-talk between messages)
+    perm = torch.randperm(n, device=dev)
+    out2 = torch.empty_like(out)
+    eng.keccak256_fixed_dev(keys[perm].contiguous(), 32, 32, n, out2)
+    torch.cuda.synchronize()
+    assert torch.equal(out[perm], out2)
+    # a sample of 20k digests against the oracle
+    idx = torch.randint(0, n, (20_000,), device=dev)
+    assert (out[idx].cpu().numpy() == oracle.keccak256_fixed(keys[idx].cpu().numpy(), threads=4)).all()
+    # the 20-byte address variant on the same scale (stride 32, first 20 bytes hashed)
+    eng.keccak256_fixed_dev(keys, 20, 32, n, out2)
+    torch.cuda.synchronize()
+    assert (out2[idx].cpu().numpy() == oracle.keccak256_fixed(keys[idx].cpu().numpy(), 20, threads=4)).all()
+    eng.set_stream(None)
+
+
+def test_c3_sharded_monolithic_and_host_paths_agree(eng):
+    import torch
+    from bench import make_c3_shard
+    dev = torch.device("cuda", 0)
+    n_acc, slots = 1_000_000, 16
+    sh = make_c3_shard(3, n_acc, slots, 0, 16, dev)
+    eng.use_torch_stream()
+    d_root = torch.zeros(32, dtype=torch.uint8, device=dev)
+    eng.state_root_full_dev(sh["akeys"], sh["accts"], n_acc, sh["skeys"], sh["svals"], sh["offs"], sh["n_slots"], d_root)
+    eng.dev_status()
+    mono = bytes(d_root.cpu().numpy())
+    stats = eng.last_stats()
+    assert stats["leaves_added"] == n_acc * (slots + 1)
+    assert 1.30 < stats["hashed_nodes"] / stats["leaves_added"] < 1.45      # SURVEY.md Appendix C structure factor
+    # 4 emulated ranks by top nibble -> frontier merge -> same root
+    akeys = sh["akeys"].view(n_acc, 32)
+    top = (akeys[:, 0] >> 4).cpu().numpy()
+    merged = torch.zeros(16 * 68, dtype=torch.uint8, device=dev)
+    for rank in range(4):
+        lo_n, hi_n = rank * 4, rank * 4 + 4
+        sel = np.nonzero((top >= lo_n) & (top < hi_n))[0]
+        a0, a1 = int(sel[0]), int(sel[-1]) + 1
+        s0, s1 = a0 * slots, a1 * slots
+        fr = torch.zeros(16 * 68, dtype=torch.uint8, device=dev)
+        offs = (sh["offs"][a0:a1 + 1] - sh["offs"][a0]).contiguous()
+        eng.subtrie_frontier_dev(akeys[a0:a1].contiguous().view(-1), sh["accts"].view(n_acc, 72)[a0:a1].contiguous().view(-1),
+                                 a1 - a0, sh["skeys"].view(-1, 32)[s0:s1].contiguous().view(-1),
+                                 sh["svals"].view(-1, 32)[s0:s1].contiguous().view(-1), offs, s1 - s0, fr)
+        merged.view(16, 68)[lo_n:hi_n] = fr.view(16, 68)[lo_n:hi_n]
+    eng.root_from_frontier_dev(merged, d_root)
+    eng.dev_status()
+    assert bytes(d_root.cpu().numpy()) == mono
+    eng.set_stream(None)
+    # host-pointer path (chunked H2D/compute pipeline) on the same data
+    from reth_b200 import ACCOUNT_DTYPE
+    h = lambda t: t.cpu().numpy()
+    root = eng.state_root_full(h(sh["akeys"]).reshape(-1, 32), h(sh["accts"]).view(ACCOUNT_DTYPE).reshape(-1),
+                               h(sh["skeys"]).reshape(-1, 32), h(sh["svals"]).reshape(-1, 32),
+                               h(sh["offs"]).astype(np.uint64))
+    assert root == mono
+    # a 30k-account prefix of the same data against the oracle (exact)
+    m = 30_000
+    exp = oracle.state_root_full(h(akeys[:m]), h(sh["accts"].view(n_acc, 72)[:m]).view(ACCOUNT_DTYPE).reshape(-1),
+                                 h(sh["skeys"].view(-1, 32)[:m * slots]), h(sh["svals"].view(-1, 32)[:m * slots]),
+                                 h(sh["offs"][:m + 1]).astype(np.uint64), threads=8)
+    got = eng.state_root_full(h(akeys[:m]), h(sh["accts"].view(n_acc, 72)[:m]).view(ACCOUNT_DTYPE).reshape(-1),
+                              h(sh["skeys"].view(-1, 32)[:m * slots]), h(sh["svals"].view(-1, 32)[:m * slots]),
+                              h(sh["offs"][:m + 1]).astype(np.uint64))
+    assert got == exp
+
+
+def test_c5_update_revert_round_trip(eng):
+    """10M-leaf resident trie: update 10k accounts, then write the old values back -> the original root; the updated
+    root equals a from-scratch build of the modified state on the device."""
+    import torch
+    from bench import be_sort_key, random_keys_torch, splitmix64_torch
+    from reth_b200 import ResidentTrie
+    dev = torch.device("cuda", 0)
+    n, m = 10_000_000, 10_000
+    keys = random_keys_torch(5, n, dev)
+    keys = keys[torch.sort(be_sort_key(keys), stable=True).indices].contiguous()
+    accts = torch.zeros((n, 72), dtype=torch.uint8, device=dev)
+    accts[:, 32:40] = splitmix64_torch(9, n, dev).view(torch.uint8).view(n, 8)
+    eng.use_torch_stream()
+    root0 = torch.zeros(32, dtype=torch.uint8, device=dev)
+    trie = ResidentTrie.create_dev(eng, keys.view(torch.uint8).view(-1), accts.view(-1), None, n, root0)
+    idx = torch.unique(torch.randint(0, n, (m + 2000,), device=dev))[:m]
+    mm = int(idx.numel())
+    dk = keys[idx].contiguous().view(torch.uint8).view(-1)
+    old = accts[idx].clone()
+    new = old.clone()
+    new[:, 0] = 7
+    new[:, 33] ^= 0x5A
+    root1 = torch.zeros(32, dtype=torch.uint8, device=dev)
+    trie.update_dev(dk, new.view(-1), None, mm, root1)
+    eng.dev_status()
+    assert not torch.equal(root0, root1)
+    # from-scratch build of the modified state
+    accts2 = accts.clone()
+    accts2[idx] = new
+    root_full = torch.zeros(32, dtype=torch.uint8, device=dev)
+    eng.state_root_dev(keys.view(torch.uint8).view(-1), accts2.view(-1), None, n, root_full)
+    eng.dev_status()
+    assert torch.equal(root1, root_full)
+    # revert
+    root2 = torch.zeros(32, dtype=torch.uint8, device=dev)
+    trie.update_dev(dk, old.view(-1), None, mm, root2)
+    eng.dev_status()
+    assert torch.equal(root2, root0)
+    trie.close()
+    eng.set_stream(None)
