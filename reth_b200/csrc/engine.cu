@@ -497,7 +497,8 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
         } else {
             for (int cls = 0; cls < 4; cls++) {
                 if (!hc[cls]) continue;
-                CU(launch_branch_level(f, norder, pos, pos + hc[cls], d, cls, st));
+                // a sparsely populated class of a big level is latency-bound too: one warp per node
+                CU(launch_branch_level(f, norder, pos, pos + hc[cls], d, hc[cls] <= WARP_LEVEL_MAX / 4 ? -1 : cls, st));
                 c->launches++;
                 pos += hc[cls];
             }
