@@ -1,0 +1,460 @@
+// reth_b200.hpp — C++17 host-side mirror of reth's commitment interface over the C ABI (include/b200trie.h).
+//
+// reth is Rust and this image has no Rust toolchain, so the layer a reth maintainer would write in Rust
+//  is written here in C++ with the same type names, method names, argument meaning and error
+// behaviour:  HashedPostState / HashedStorage / HashedPostStateSorted (crates/trie/common/src/hashed_state.rs),
+// PrefixSetMut / PrefixSet (prefix_set.rs), TrieUpdates / StorageTrieUpdates / BranchNodeCompact (updates.rs),
+// KeccakKeyHasher (key.rs), StateRoot / StorageRoot (crates/trie/trie/src/trie.rs), ParallelStateRoot
+// (crates/trie/parallel/src/root.rs).  Header-only; link with -lb200trie.  There is no CPU path: Engine's
+// constructor throws B200Error when no CUDA device is usable.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <optional>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/b200trie.h"
+
+namespace reth_b200 {
+
+using B256 = std::array<uint8_t, 32>;
+using Address = std::array<uint8_t, 20>;
+using U256 = std::array<uint8_t, 32>;  // big-endian
+using Nibbles = std::vector<uint8_t>;  // one nibble per byte
+
+inline const B256 KECCAK_EMPTY = {0xc5, 0xd2, 0x46, 0x01, 0x86, 0xf7, 0x23, 0x3c, 0x92, 0x7e, 0x7d, 0xb2, 0xdc, 0xc7, 0x03, 0xc0,
+                                  0xe5, 0x00, 0xb6, 0x53, 0xca, 0x82, 0x27, 0x3b, 0x7b, 0xfa, 0xd8, 0x04, 0x5d, 0x85, 0xa4, 0x70};
+inline const B256 EMPTY_ROOT_HASH = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55, 0xa6, 0xff, 0x83, 0x45, 0xe6, 0x92, 0xc0, 0xf8, 0x6e,
+                                     0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c, 0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
+
+inline U256 u256_from_u64(uint64_t v) {
+    U256 r{};
+    for (int i = 0; i < 8; i++) r[31 - i] = (uint8_t)(v >> (8 * i));
+    return r;
+}
+inline bool is_zero(const U256 &v) {
+    for (uint8_t b : v)
+        if (b) return false;
+    return true;
+}
+inline Nibbles unpack_nibbles(const B256 &k) {
+    Nibbles n(64);
+    for (int i = 0; i < 32; i++) {
+        n[2 * i] = k[i] >> 4;
+        n[2 * i + 1] = k[i] & 15;
+    }
+    return n;
+}
+
+/// StateRootError::Database(DatabaseError::Other(msg)) in the Rust shim.
+struct B200Error : std::runtime_error {
+    int status;
+    B200Error(int s, const std::string &m) : std::runtime_error("b200 status " + std::to_string(s) + ": " + m), status(s) {}
+};
+
+/// reth_primitives_traits::Account
+struct Account {
+    uint64_t nonce = 0;
+    U256 balance{};
+    std::optional<B256> bytecode_hash;
+};
+
+/// One b200_ctx (one GPU).  Internally locked by the library; share it freely between threads.
+class Engine {
+  public:
+    explicit Engine(int device = 0) : ctx_(b200_create(device)) {
+        if (!ctx_) throw B200Error(b200_create_status(), "b200_create failed (no CUDA device? reth_b200 has no CPU path)");
+    }
+    ~Engine() { b200_destroy(ctx_); }
+    Engine(const Engine &) = delete;
+    Engine &operator=(const Engine &) = delete;
+    b200_ctx *raw() const { return ctx_; }
+    void check(int32_t rc) const {
+        if (rc != B200_OK) throw B200Error(rc, b200_last_error(ctx_));
+    }
+    /// n fixed-length messages -> n digests
+    std::vector<B256> keccak256_fixed(const uint8_t *msgs, uint32_t msg_len, uint64_t n) const {
+        std::vector<B256> out(n);
+        check(b200_keccak256_fixed(ctx_, msgs, msg_len, msg_len, n, n ? out[0].data() : nullptr));
+        return out;
+    }
+
+  private:
+    b200_ctx *ctx_;
+};
+
+/// crates/trie/common/src/key.rs:4-18, plus the batch form the device wants
+struct KeccakKeyHasher {
+    static B256 hash_key(const Engine &e, const uint8_t *bytes, uint32_t len) { return e.keccak256_fixed(bytes, len, 1)[0]; }
+    template <size_t N>
+    static std::vector<B256> hash_keys(const Engine &e, const std::vector<std::array<uint8_t, N>> &keys) {
+        return e.keccak256_fixed(keys.empty() ? nullptr : keys[0].data(), (uint32_t)N, keys.size());
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- prefix sets
+/// crates/trie/common/src/prefix_set.rs:182-231
+class PrefixSet {
+  public:
+    PrefixSet() = default;
+    PrefixSet(std::vector<Nibbles> keys, bool all) : all_(all), keys_(std::move(keys)) {}
+    bool contains(const Nibbles &prefix) {
+        if (all_) return true;
+        while (index_ > 0 && keys_[index_] > prefix) index_--;
+        for (size_t i = index_; i < keys_.size(); i++) {
+            const Nibbles &k = keys_[i];
+            if (k.size() >= prefix.size() && std::equal(prefix.begin(), prefix.end(), k.begin())) {
+                index_ = i;
+                return true;
+            }
+            if (k > prefix) {
+                index_ = i;
+                return false;
+            }
+        }
+        return false;
+    }
+    size_t len() const { return keys_.size(); }
+    bool is_all() const { return all_; }
+
+  private:
+    bool all_ = false;
+    size_t index_ = 0;
+    std::vector<Nibbles> keys_;
+};
+
+/// prefix_set.rs:100-177
+class PrefixSetMut {
+  public:
+    static PrefixSetMut all() {
+        PrefixSetMut p;
+        p.all_ = true;
+        return p;
+    }
+    void insert(Nibbles n) { keys_.push_back(std::move(n)); }
+    void extend(const PrefixSetMut &o) {
+        all_ |= o.all_;
+        keys_.insert(keys_.end(), o.keys_.begin(), o.keys_.end());
+    }
+    bool is_empty() const { return !all_ && keys_.empty(); }
+    PrefixSet freeze() const {
+        if (all_) return PrefixSet({}, true);
+        std::set<Nibbles> s(keys_.begin(), keys_.end());
+        return PrefixSet(std::vector<Nibbles>(s.begin(), s.end()), false);
+    }
+
+  private:
+    bool all_ = false;
+    std::vector<Nibbles> keys_;
+};
+
+struct TriePrefixSets {
+    PrefixSet account_prefix_set;
+    std::map<B256, PrefixSet> storage_prefix_sets;
+    std::set<B256> destroyed_accounts;
+};
+struct TriePrefixSetsMut {
+    PrefixSetMut account_prefix_set;
+    std::map<B256, PrefixSetMut> storage_prefix_sets;
+    std::set<B256> destroyed_accounts;
+    TriePrefixSets freeze() const {
+        TriePrefixSets f;
+        f.account_prefix_set = account_prefix_set.freeze();
+        for (auto &kv : storage_prefix_sets) f.storage_prefix_sets.emplace(kv.first, kv.second.freeze());
+        f.destroyed_accounts = destroyed_accounts;
+        return f;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- hashed state
+/// hashed_state.rs:710-715
+struct HashedStorageSorted {
+    std::vector<std::pair<B256, U256>> storage_slots;  // sorted by hashed slot; zero value = deletion
+    bool wiped = false;
+};
+
+/// hashed_state.rs:423-428
+struct HashedStorage {
+    bool wiped = false;
+    std::map<B256, U256> storage;
+    bool is_empty() const { return !wiped && storage.empty(); }
+    PrefixSetMut construct_prefix_set() const {
+        if (wiped) return PrefixSetMut::all();
+        PrefixSetMut p;
+        for (auto &kv : storage) p.insert(unpack_nibbles(kv.first));
+        return p;
+    }
+    HashedStorageSorted into_sorted() const {
+        return HashedStorageSorted{std::vector<std::pair<B256, U256>>(storage.begin(), storage.end()), wiped};
+    }
+};
+
+/// The flat layout of include/b200trie.h.
+struct FlatState {
+    std::vector<uint8_t> acct_keys;  // n x 32
+    std::vector<b200_account> accts;
+    std::vector<uint8_t> slot_keys, slot_values;  // m x 32
+    std::vector<uint64_t> seg_offsets{0};
+    uint64_t n_accounts() const { return accts.size(); }
+};
+
+/// hashed_state.rs:519-524
+struct HashedPostStateSorted {
+    std::vector<std::pair<B256, std::optional<Account>>> accounts;
+    std::map<B256, HashedStorageSorted> storages;
+
+    /// Destroyed accounts (None) and zero-valued slots are dropped where the reference's cursors skip them
+    /// (crates/trie/trie/src/hashed_cursor/post_state.rs:260-297); storage without an account entry is never
+    /// visited by StateRoot::calculate.
+    FlatState to_flat() const {
+        FlatState f;
+        for (auto &ka : accounts) {
+            if (!ka.second) continue;
+            const Account &a = *ka.second;
+            f.acct_keys.insert(f.acct_keys.end(), ka.first.begin(), ka.first.end());
+            b200_account ba;
+            ba.nonce = a.nonce;
+            std::memcpy(ba.balance_be, a.balance.data(), 32);
+            const B256 &ch = a.bytecode_hash ? *a.bytecode_hash : KECCAK_EMPTY;  // account.rs:16-31
+            std::memcpy(ba.code_hash, ch.data(), 32);
+            f.accts.push_back(ba);
+            uint64_t cnt = 0;
+            auto it = storages.find(ka.first);
+            if (it != storages.end())
+                for (auto &sv : it->second.storage_slots)
+                    if (!is_zero(sv.second)) {
+                        f.slot_keys.insert(f.slot_keys.end(), sv.first.begin(), sv.first.end());
+                        f.slot_values.insert(f.slot_values.end(), sv.second.begin(), sv.second.end());
+                        cnt++;
+                    }
+            f.seg_offsets.push_back(f.seg_offsets.back() + cnt);
+        }
+        return f;
+    }
+};
+
+/// One account of a BundleState as from_bundle_state sees it.
+struct BundleAccount {
+    std::optional<Account> info;
+    bool was_destroyed = false;
+    std::vector<std::pair<U256, U256>> storage;  // slot -> present value
+};
+
+/// hashed_state.rs:29-34
+struct HashedPostState {
+    std::map<B256, std::optional<Account>> accounts;
+    std::map<B256, HashedStorage> storages;
+
+    /// from_bundle_state (hashed_state.rs:49-69): all addresses in one device batch, all slots in another.
+    static HashedPostState from_bundle_state(const Engine &e, const std::vector<std::pair<Address, BundleAccount>> &state) {
+        std::vector<Address> addrs;
+        std::vector<U256> slots;
+        for (auto &kv : state) {
+            addrs.push_back(kv.first);
+            for (auto &sv : kv.second.storage) slots.push_back(sv.first);
+        }
+        auto ha = KeccakKeyHasher::hash_keys(e, addrs);
+        auto hs = KeccakKeyHasher::hash_keys(e, slots);
+        HashedPostState out;
+        size_t si = 0;
+        for (size_t i = 0; i < state.size(); i++) {
+            const BundleAccount &b = state[i].second;
+            out.accounts[ha[i]] = b.info;
+            HashedStorage st;
+            st.wiped = b.was_destroyed;
+            for (auto &sv : b.storage) st.storage[hs[si++]] = sv.second;
+            if (!st.is_empty()) out.storages[ha[i]] = std::move(st);
+        }
+        return out;
+    }
+    bool is_empty() const { return accounts.empty() && storages.empty(); }
+    /// hashed_state.rs:105-126
+    TriePrefixSetsMut construct_prefix_sets() const {
+        TriePrefixSetsMut ps;
+        for (auto &ka : accounts) {
+            ps.account_prefix_set.insert(unpack_nibbles(ka.first));
+            if (!ka.second) ps.destroyed_accounts.insert(ka.first);
+        }
+        for (auto &ks : storages) {
+            ps.account_prefix_set.insert(unpack_nibbles(ks.first));
+            ps.storage_prefix_sets.emplace(ks.first, ks.second.construct_prefix_set());
+        }
+        return ps;
+    }
+    /// hashed_state.rs:329-340
+    HashedPostStateSorted into_sorted() const {
+        HashedPostStateSorted s;
+        s.accounts.assign(accounts.begin(), accounts.end());
+        for (auto &ks : storages) s.storages.emplace(ks.first, ks.second.into_sorted());
+        return s;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- updates
+struct BranchNodeCompact {
+    uint16_t state_mask = 0, tree_mask = 0, hash_mask = 0;
+    std::vector<B256> hashes;
+    std::optional<B256> root_hash;
+    bool operator==(const BranchNodeCompact &o) const {
+        return state_mask == o.state_mask && tree_mask == o.tree_mask && hash_mask == o.hash_mask && hashes == o.hashes &&
+               root_hash == o.root_hash;
+    }
+};
+/// updates.rs:235-245
+struct StorageTrieUpdates {
+    bool is_deleted = false;
+    std::map<Nibbles, BranchNodeCompact> storage_nodes;
+    std::set<Nibbles> removed_nodes;
+    static StorageTrieUpdates deleted() {
+        StorageTrieUpdates u;
+        u.is_deleted = true;
+        return u;
+    }
+    bool is_empty() const { return !is_deleted && storage_nodes.empty() && removed_nodes.empty(); }
+    size_t len() const { return (is_deleted ? 1 : 0) + storage_nodes.size() + removed_nodes.size(); }
+};
+/// updates.rs:17-26
+struct TrieUpdates {
+    std::map<Nibbles, BranchNodeCompact> account_nodes;
+    std::set<Nibbles> removed_nodes;
+    std::map<B256, StorageTrieUpdates> storage_tries;
+    void insert_storage_updates(const B256 &addr, StorageTrieUpdates u) {
+        if (u.is_empty()) return;  // updates.rs:132-134
+        storage_tries.emplace(addr, std::move(u));
+    }
+};
+
+namespace detail {
+inline std::pair<Nibbles, BranchNodeCompact> branch_node(const b200_updates &u, uint64_t i) {
+    Nibbles path(u.path_len[i]);
+    const uint8_t *pp = u.path_packed + 32 * i;
+    for (size_t j = 0; j < path.size(); j++) path[j] = (j & 1) ? (pp[j >> 1] & 15) : (pp[j >> 1] >> 4);
+    BranchNodeCompact n;
+    n.state_mask = u.state_mask[i];
+    n.tree_mask = u.tree_mask[i];
+    n.hash_mask = u.hash_mask[i];
+    for (uint64_t h = u.hash_offset[i]; h < u.hash_offset[i + 1]; h++) {
+        B256 x;
+        std::memcpy(x.data(), u.hashes + 32 * h, 32);
+        n.hashes.push_back(x);
+    }
+    return {std::move(path), std::move(n)};
+}
+}  // namespace detail
+
+/// crates/trie/trie/src/progress.rs:12-21 — a device build never pauses: always Complete.
+struct StateRootProgress {
+    B256 root;
+    size_t hashed_entries_walked;
+    TrieUpdates updates;
+};
+
+/// StorageRoot::{root, root_with_updates, calculate} — trie.rs:479-721
+class StorageRoot {
+  public:
+    StorageRoot(const Engine &e, B256 hashed_address, HashedStorageSorted storage)
+        : e_(e), hashed_address_(hashed_address), storage_(std::move(storage)) {}
+    B256 root() const { return std::get<0>(calculate(false)); }
+    std::tuple<B256, size_t, StorageTrieUpdates> root_with_updates() const { return calculate(true); }
+    std::tuple<B256, size_t, StorageTrieUpdates> calculate(bool retain_updates) const {
+        std::vector<uint8_t> keys, vals;
+        for (auto &sv : storage_.storage_slots)
+            if (!is_zero(sv.second)) {
+                keys.insert(keys.end(), sv.first.begin(), sv.first.end());
+                vals.insert(vals.end(), sv.second.begin(), sv.second.end());
+            }
+        uint64_t m = keys.size() / 32;
+        if (m == 0) return {EMPTY_ROOT_HASH, 0, StorageTrieUpdates::deleted()};  // trie.rs:622-629
+        uint64_t offs[2] = {0, m};
+        B256 root;
+        b200_updates u{};
+        e_.check(b200_storage_roots(e_.raw(), keys.data(), vals.data(), offs, 1, root.data(), retain_updates ? &u : nullptr,
+                                    nullptr));
+        StorageTrieUpdates upd;
+        if (retain_updates) {
+            for (uint64_t i = 0; i < u.n_nodes; i++) upd.storage_nodes.insert(detail::branch_node(u, i));
+            b200_updates_release(&u);
+        }
+        return {root, (size_t)m, std::move(upd)};
+    }
+
+  private:
+    const Engine &e_;
+    B256 hashed_address_;
+    HashedStorageSorted storage_;
+};
+
+/// StateRoot::{root, root_with_updates, root_with_progress, with_prefix_sets, with_threshold} — trie.rs:54-330.
+/// Takes the hashed state where reth takes cursor factories over it (no stored trie nodes underneath:
+/// MerkleStage's rebuild path, StateRootProvider::state_root on a full state, MockHashedCursorFactory tests).
+class StateRoot {
+  public:
+    StateRoot(const Engine &e, HashedPostStateSorted state) : e_(e), state_(std::move(state)) {}
+    StateRoot &with_prefix_sets(TriePrefixSets ps) {
+        prefix_sets_ = std::move(ps);
+        return *this;
+    }
+    StateRoot &with_threshold(uint64_t t) {
+        threshold_ = t;
+        return *this;
+    }
+    StateRoot &with_no_threshold() {
+        threshold_ = UINT64_MAX;
+        return *this;
+    }
+    B256 root() const { return calculate(false).root; }
+    std::pair<B256, TrieUpdates> root_with_updates() const {
+        auto p = calculate(true);
+        return {p.root, std::move(p.updates)};
+    }
+    StateRootProgress root_with_progress() const { return calculate(true); }
+
+  protected:
+    StateRootProgress calculate(bool retain_updates) const {
+        FlatState f = state_.to_flat();
+        StateRootProgress out;
+        b200_updates au{}, su{};
+        e_.check(b200_state_root_full(e_.raw(), f.acct_keys.data(), f.accts.data(), f.n_accounts(), f.slot_keys.data(),
+                                      f.slot_values.data(), f.seg_offsets.data(), out.root.data(),
+                                      retain_updates ? &au : nullptr, retain_updates ? &su : nullptr, nullptr));
+        out.hashed_entries_walked = f.n_accounts() + f.slot_keys.size() / 32;
+        if (retain_updates) {
+            for (uint64_t i = 0; i < au.n_nodes; i++) out.updates.account_nodes.insert(detail::branch_node(au, i));
+            std::map<uint32_t, StorageTrieUpdates> per_trie;
+            for (uint64_t i = 0; i < su.n_nodes; i++) per_trie[su.trie_id[i]].storage_nodes.insert(detail::branch_node(su, i));
+            for (uint64_t a = 0; a < f.n_accounts(); a++) {
+                B256 addr;
+                std::memcpy(addr.data(), f.acct_keys.data() + 32 * a, 32);
+                if (f.seg_offsets[a + 1] == f.seg_offsets[a])
+                    out.updates.insert_storage_updates(addr, StorageTrieUpdates::deleted());  // trie.rs:622-629
+                else
+                    out.updates.insert_storage_updates(addr, per_trie[(uint32_t)a]);
+            }
+            for (auto &d : prefix_sets_.destroyed_accounts) out.updates.storage_tries[d].is_deleted = true;  // updates.rs:153-157
+            b200_updates_release(&au);
+            b200_updates_release(&su);
+        }
+        return out;
+    }
+    const Engine &e_;
+    HashedPostStateSorted state_;
+    TriePrefixSets prefix_sets_;
+    uint64_t threshold_ = 100000;  // DEFAULT_INTERMEDIATE_THRESHOLD, trie.rs:25
+};
+
+/// ParallelStateRoot::{incremental_root, incremental_root_with_updates} — crates/trie/parallel/src/root.rs:35-77.
+/// The storage-root fan-out and the account fold are the same device launches.
+class ParallelStateRoot : public StateRoot {
+  public:
+    using StateRoot::StateRoot;
+    B256 incremental_root() const { return root(); }
+    std::pair<B256, TrieUpdates> incremental_root_with_updates() const { return root_with_updates(); }
+};
+
+}  // namespace reth_b200

@@ -1,0 +1,215 @@
+// host_test.cpp — the reference's own trie tests, restated against the C++ host mirror (reth_b200/host/reth_b200.hpp)
+// and checked against the CPU oracle.  Built by __graft_entry__.build(), run by tests/test_gpu_cpp_host.py.
+//   account_and_storage_trie          crates/trie/db/tests/trie.rs:357-477
+//   from_bundle_state_with_rayon      crates/trie/db/src/state.rs:408-437
+//   storage_trie_around_extension_node crates/trie/db/tests/trie.rs:719-805
+//   prefix set semantics              crates/trie/common/src/prefix_set.rs:292-305
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+
+#include "../../oracle/oracle.h"
+#include "../../reth_b200/host/reth_b200.hpp"
+
+using namespace reth_b200;
+
+static int failures = 0;
+#define CHECK(cond)                                                       \
+    do {                                                                  \
+        if (!(cond)) {                                                    \
+            std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond);  \
+            failures++;                                                   \
+        }                                                                 \
+    } while (0)
+
+static B256 b256(const char *hex) {
+    B256 r{};
+    for (int i = 0; i < 32; i++) {
+        unsigned v;
+        std::sscanf(hex + 2 * i, "%2x", &v);
+        r[i] = (uint8_t)v;
+    }
+    return r;
+}
+static Address addr(const char *hex) {
+    Address r{};
+    for (int i = 0; i < 20; i++) {
+        unsigned v;
+        std::sscanf(hex + 2 * i, "%2x", &v);
+        r[i] = (uint8_t)v;
+    }
+    return r;
+}
+static std::string hex(const B256 &b) {
+    char s[65];
+    for (int i = 0; i < 32; i++) std::snprintf(s + 2 * i, 3, "%02x", b[i]);
+    return s;
+}
+static U256 ether(uint64_t n) {  // n * 1e18
+    unsigned __int128 v = (unsigned __int128)n * 1000000000000000000ULL;
+    U256 r{};
+    for (int i = 0; i < 16; i++) r[31 - i] = (uint8_t)(v >> (8 * i));
+    return r;
+}
+
+static void account_and_storage_trie(const Engine &e) {
+    HashedPostState st;
+    Address a2 = addr("7db3e81b72d2695e19764583f6d219dbee0f35ca"), a3 = addr("16b07afd1c635f77172e842a000ead9a2a222459");
+    B256 key2 = KeccakKeyHasher::hash_key(e, a2.data(), 20), key3 = KeccakKeyHasher::hash_key(e, a3.data(), 20);
+    CHECK(key2[0] == 0xB0 && key2[1] == 0x40 && key3[0] == 0xB0 && key3[1] == 0x41);
+    st.accounts[b256("b000000000000000000000000000000000000000000000000000000000000000")] = Account{0, ether(3), std::nullopt};
+    st.accounts[key2] = Account{0, ether(1), std::nullopt};
+    st.accounts[key3] = Account{0, ether(2), b256("5be74cad16203c4905c068b012a2e9fb6d19d036c410f16fd177f337541440dd")};
+    st.accounts[b256("B1A0000000000000000000000000000000000000000000000000000000000000")] = Account{0, ether(4), std::nullopt};
+    st.accounts[b256("B310000000000000000000000000000000000000000000000000000000000000")] = Account{0, ether(8), std::nullopt};
+    st.accounts[b256("B340000000000000000000000000000000000000000000000000000000000000")] = Account{0, ether(1), std::nullopt};
+    HashedStorage hs;
+    hs.storage[b256("1200000000000000000000000000000000000000000000000000000000000000")] = u256_from_u64(0x42);
+    hs.storage[b256("1400000000000000000000000000000000000000000000000000000000000000")] = u256_from_u64(0x01);
+    hs.storage[b256("3000000000000000000000000000000000000000000000000000000000E00000")] = u256_from_u64(0x127a89);
+    hs.storage[b256("3000000000000000000000000000000000000000000000000000000000E00001")] = u256_from_u64(0x05);
+    st.storages[key3] = hs;
+    auto [root, updates] = StateRoot(e, st.into_sorted()).root_with_updates();
+    CHECK(hex(root) == "72861041bc90cd2f93777956f058a545412b56de79af5eb6b8075fe2eabbe015");
+    CHECK(updates.account_nodes.size() == 2);
+    auto it = updates.account_nodes.begin();
+    CHECK(it->first == Nibbles({0xB}));
+    CHECK(it->second.state_mask == 0b1011 && it->second.tree_mask == 0b0001 && it->second.hash_mask == 0b1001);
+    CHECK(it->second.hashes.size() == 2 && !it->second.root_hash);
+    ++it;
+    CHECK(it->first == Nibbles({0xB, 0x0}));
+    CHECK(it->second.state_mask == 0b10001 && it->second.tree_mask == 0 && it->second.hash_mask == 0b10000);
+    CHECK(it->second.hashes.size() == 1);
+    size_t deleted = 0;
+    for (auto &kv : updates.storage_tries) deleted += kv.second.is_deleted;
+    CHECK(deleted == 5);  // StorageTrieUpdates::deleted() for every account without storage
+    CHECK(ParallelStateRoot(e, st.into_sorted()).incremental_root() == root);
+    CHECK(StateRoot(e, st.into_sorted()).root() == root);
+    // add the account at keccak(0x4f61..5c91): crates/trie/db/tests/trie.rs:479-491
+    Address a4b = addr("4f61f2d5ebd991b85aa1677db97307caf5215c91");
+    st.accounts[KeccakKeyHasher::hash_key(e, a4b.data(), 20)] = Account{0, ether(5), std::nullopt};
+    CHECK(hex(StateRoot(e, st.into_sorted()).root()) == "8e263cd4eefb0c3cbbb14e5541a66a755cad25bcfab1e10dd9d706263e811b28");
+}
+
+static void from_bundle_state(const Engine &e) {
+    Address a1{}, a2{};
+    a1[19] = 1;
+    a2[19] = 2;
+    BundleAccount b1, b2;
+    b1.info = Account{1, {}, std::nullopt};
+    b1.storage.push_back({u256_from_u64(1015), u256_from_u64(10)});
+    b2.info = Account{2, {}, std::nullopt};
+    b2.storage.push_back({u256_from_u64(2015), u256_from_u64(20)});
+    auto post = HashedPostState::from_bundle_state(e, {{a1, b1}, {a2, b2}});
+    CHECK(post.accounts.size() == 2 && post.storages.size() == 2);
+    CHECK(hex(StateRoot(e, post.into_sorted()).root()) == "b464525710cafcf5d4044ac85b72c08b1e76231b8d91f288fe438cc41d8eaafd");
+}
+
+static void extension_node_storage_trie(const Engine &e) {
+    const char *keys[6] = {"30af561000000000000000000000000000000000000000000000000000000000",
+                           "30af569000000000000000000000000000000000000000000000000000000000",
+                           "30af650000000000000000000000000000000000000000000000000000000000",
+                           "30af6f0000000000000000000000000000000000000000000000000000000000",
+                           "30af8f0000000000000000000000000000000000000000000000000000000000",
+                           "3100000000000000000000000000000000000000000000000000000000000000"};
+    HashedStorage hs;
+    for (auto k : keys) hs.storage[b256(k)] = u256_from_u64(1);
+    auto [root, walked, upd] = StorageRoot(e, B256{}, hs.into_sorted()).root_with_updates();
+    CHECK(walked == 6 && upd.storage_nodes.size() == 2 && !upd.is_deleted);
+    auto &n3 = upd.storage_nodes.at(Nibbles({3}));
+    CHECK(n3.state_mask == 0b0011 && n3.tree_mask == 0b0001 && n3.hash_mask == 0 && n3.hashes.empty());
+    auto &n30af = upd.storage_nodes.at(Nibbles({3, 0, 0xA, 0xF}));
+    CHECK(n30af.state_mask == 0b101100000 && n30af.tree_mask == 0 && n30af.hash_mask == 0b001000000 && n30af.hashes.size() == 1);
+    // oracle agrees on the root
+    std::vector<uint8_t> k, v;
+    for (auto &sv : hs.storage) {
+        k.insert(k.end(), sv.first.begin(), sv.first.end());
+        v.insert(v.end(), sv.second.begin(), sv.second.end());
+    }
+    uint64_t offs[2] = {0, 6};
+    B256 oroot;
+    CHECK(orc_storage_roots(k.data(), v.data(), offs, 1, oroot.data(), nullptr, 1) == 0 && oroot == root);
+    // empty storage and all-zero storage
+    auto [r0, w0, u0] = StorageRoot(e, B256{}, HashedStorageSorted{}).root_with_updates();
+    CHECK(r0 == EMPTY_ROOT_HASH && w0 == 0 && u0.is_deleted);
+    HashedStorage z;
+    z.storage[b256(keys[0])] = U256{};
+    CHECK(StorageRoot(e, B256{}, z.into_sorted()).root() == EMPTY_ROOT_HASH);
+}
+
+static void prefix_sets_and_destroyed(const Engine &e) {
+    PrefixSetMut m;
+    m.insert({1, 2, 3});
+    m.insert({1, 2, 4});
+    m.insert({4, 5, 6});
+    m.insert({1, 2, 3});
+    PrefixSet ps = m.freeze();
+    CHECK(ps.contains({1, 2}) && ps.contains({4, 5}) && !ps.contains({7, 8}) && ps.len() == 3);
+    B256 k1, k2;
+    k1.fill(0x11);
+    k2.fill(0x22);
+    HashedPostState st;
+    st.accounts[k1] = Account{1, u256_from_u64(1), std::nullopt};
+    st.accounts[k2] = std::nullopt;  // destroyed
+    st.storages[k2].wiped = true;
+    auto sets = st.construct_prefix_sets().freeze();
+    CHECK(sets.destroyed_accounts.count(k2) == 1 && sets.storage_prefix_sets.at(k2).is_all());
+    auto [root, upd] = StateRoot(e, st.into_sorted()).with_prefix_sets(sets).root_with_updates();
+    HashedPostState only;
+    only.accounts[k1] = st.accounts[k1];
+    CHECK(root == StateRoot(e, only.into_sorted()).root());
+    CHECK(upd.storage_tries.at(k2).is_deleted);
+    CHECK(StateRoot(e, HashedPostStateSorted{}).root() == EMPTY_ROOT_HASH);
+}
+
+static void random_state_vs_oracle(const Engine &e) {
+    std::mt19937_64 rng(42);
+    HashedPostState st;
+    for (int i = 0; i < 3000; i++) {
+        B256 k;
+        for (auto &b : k) b = (uint8_t)rng();
+        Account a{rng() & 0xffff, u256_from_u64(rng()), std::nullopt};
+        if (i % 3 == 0) {
+            B256 ch;
+            for (auto &b : ch) b = (uint8_t)rng();
+            a.bytecode_hash = ch;
+        }
+        st.accounts[k] = a;
+        if (i % 5 == 0)
+            for (int s = 0; s < 1 + (int)(rng() % 40); s++) {
+                B256 sk;
+                for (auto &b : sk) b = (uint8_t)rng();
+                st.storages[k].storage[sk] = u256_from_u64(rng() | 1);
+            }
+    }
+    auto sorted = st.into_sorted();
+    FlatState f = sorted.to_flat();
+    B256 oroot;
+    orc_updates oa{}, os{};
+    CHECK(orc_state_root_full(f.acct_keys.data(), reinterpret_cast<const orc_account *>(f.accts.data()), f.n_accounts(),
+                              f.slot_keys.data(), f.slot_values.data(), f.seg_offsets.data(), oroot.data(), &oa, &os, 4) == 0);
+    auto [root, upd] = StateRoot(e, sorted).root_with_updates();
+    CHECK(root == oroot);
+    CHECK(upd.account_nodes.size() == oa.n_nodes);
+    size_t storage_nodes = 0;
+    for (auto &kv : upd.storage_tries) storage_nodes += kv.second.storage_nodes.size();
+    CHECK(storage_nodes == os.n_nodes);
+    orc_updates_free(&oa);
+    orc_updates_free(&os);
+}
+
+int main() {
+    try {
+        Engine e(0);
+        account_and_storage_trie(e);
+        from_bundle_state(e);
+        extension_node_storage_trie(e);
+        prefix_sets_and_destroyed(e);
+        random_state_vs_oracle(e);
+    } catch (const B200Error &err) {
+        std::printf("B200Error: %s\n", err.what());
+        return err.status == B200_ERR_NO_DEVICE ? 77 : 2;
+    }
+    std::printf(failures ? "host_test: %d FAILURES\n" : "host_test: all checks passed\n", failures);
+    return failures ? 1 : 0;
+}
