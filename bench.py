@@ -287,8 +287,20 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "WARN")  # NCCL prints its version banner to stdout
+        # stdout carries exactly one JSON line: park fd 1 on stderr while NCCL initialises (it writes to fd 1 directly)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     eng = Engine(local_rank)
     # a dedicated (non-default) stream: torch events, NCCL and the engine's kernels are all ordered on it
     stream = torch.cuda.Stream(device=dev)
@@ -372,7 +384,7 @@ def main():
                         "see alu_frac for the binding roofline",
                 "alu_frac": None}
     if clk.summary()["sm_mhz"]:
-        alu_peak = 148 * 64 * clk.summary()["sm_mhz"] * 1e6 / 4254.0  # digests/s if every ALU slot did keccak work
+        alu_peak = 148 * 64 * clk.summary()["sm_mhz"] * 1e6 / 4150.0  # measured 64 lanes/clk/SM ALU pipe, ~4150 ALU instr/digest
         roofline["alu_frac"] = (n / (ms_per_step * 1e-3)) / alu_peak
         roofline["alu_peak_digests_per_s"] = alu_peak
 
