@@ -270,6 +270,9 @@ def main():
     ap.add_argument("--base-accounts", type=int, default=100_000_000, help="resident base trie of the incremental (C5) leg")
     ap.add_argument("--dirty", type=int, default=10_000, help="dirty accounts per incremental update")
     ap.add_argument("--skip-incremental", action="store_true")
+    ap.add_argument("--c4", action="store_true", help="also run the mainnet-shape leg (BASELINE config 4): per GPU "
+                    "--c4-leaves leaves, 80%% EOAs, Zipf(1.2) storage sizes")
+    ap.add_argument("--c4-leaves", type=int, default=31_250_000, help="leaves per GPU (250M over 8 GPUs)")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -393,6 +396,10 @@ def main():
     if not args.skip_state_root:
         state_root = bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks)
 
+    c4 = None
+    if args.c4:
+        c4 = bench_c4(args, eng, dev, rank, world, barrier, max_over_ranks)
+
     incremental = None
     if not args.skip_incremental and world == 1:
         incremental = bench_incremental(args, eng, dev)
@@ -412,7 +419,7 @@ def main():
                        "keys_per_gpu": n, "msg_len": 32, "parallelism": f"keys sharded over {world} GPU(s), no collective",
                        "l2": "input 320 MB + output 320 MB per step exceed the 126 MB L2; no flush needed"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
-            "cpu_baseline": cpu, "state_root": state_root, "incremental": incremental,
+            "cpu_baseline": cpu, "state_root": state_root, "mainnet_shape": c4, "incremental": incremental,
             "parity_spot_check": parity_ok,
         }
         print(json.dumps(line), flush=True)
@@ -492,6 +499,102 @@ def bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks):
                       "h2d_bytes_per_step": int(sum(v.nbytes for v in h.values())), "d2h_bytes_per_step": 32,
                       "root_matches_device_run": root.hex() == res["root"],
                       "api": "b200_state_root_full (host pointers, page-locked)"}
+    return res
+
+
+def make_c4_shard(seed: int, leaves: int, nibble_lo: int, nibble_hi: int, device):
+    """Mainnet-shaped shard: 20% of the leaves are accounts, 80% of the accounts are EOAs without
+    storage, the contracts' slot counts follow Zipf(s=1.2) (a few huge tries, a long tail of tiny ones)."""
+    import torch
+    n_acc = leaves // 5
+    n_slots = leaves - n_acc
+    n_contracts = n_acc // 5
+    ranks = np.arange(1, n_contracts + 1, dtype=np.float64) ** -1.2
+    lo, hi = 1.0, float(n_slots)
+    for _ in range(60):  # scale so that the sizes sum to n_slots
+        c = 0.5 * (lo + hi)
+        tot = np.maximum(1, np.floor(c * ranks)).sum()
+        lo, hi = (c, hi) if tot < n_slots else (lo, c)
+    sizes = np.maximum(1, np.floor(lo * ranks)).astype(np.int64)
+    sizes[0] += n_slots - int(sizes.sum())
+    rng = np.random.default_rng(seed)
+    counts = np.zeros(n_acc, np.int64)
+    counts[rng.choice(n_acc, n_contracts, replace=False)] = sizes  # contracts scattered over the key space
+    akeys = random_keys_torch(seed, n_acc, device)
+    ab = akeys.view(torch.uint8).view(n_acc, 32)
+    span = nibble_hi - nibble_lo
+    top = (ab[:, 0] >> 4).to(torch.int64) % span + nibble_lo
+    ab[:, 0] = (top.to(torch.uint8) << 4) | (ab[:, 0] & 0x0F)
+    akeys = akeys[torch.sort(be_sort_key(akeys), stable=True).indices].contiguous()
+    w = splitmix64_torch(seed ^ 0xACC0, 8 * n_acc, device).view(n_acc, 8)
+    accts = torch.zeros((n_acc, 72), dtype=torch.uint8, device=device)
+    accts[:, 0:2] = (w[:, 0] & 0xFFFF).contiguous().view(torch.uint8).view(n_acc, 8)[:, 0:2]
+    accts[:, 8 + 22:8 + 32] = w[:, 1:3].contiguous().view(torch.uint8).view(n_acc, 16)[:, :10]
+    accts[:, 40:72] = w[:, 4:8].contiguous().view(torch.uint8).view(n_acc, 32)
+    t_counts = torch.from_numpy(counts).to(device)
+    offs = torch.zeros(n_acc + 1, dtype=torch.int64, device=device)
+    offs[1:] = torch.cumsum(t_counts, 0)
+    m = int(offs[-1].item())
+    seg = torch.repeat_interleave(torch.arange(n_acc, dtype=torch.int64, device=device), t_counts)
+    skeys = random_keys_torch(seed ^ 0x5107, m, device)
+    o1 = torch.sort(be_sort_key(skeys), stable=True).indices
+    o2 = torch.sort(seg[o1], stable=True).indices
+    skeys = skeys[o1[o2]].contiguous()
+    del o1, o2, seg
+    vals = torch.zeros((m, 32), dtype=torch.uint8, device=device)
+    v = splitmix64_torch(seed ^ 0x7A1, m, device) | 1
+    vals[:, 24:32] = v.view(torch.uint8).view(m, 8).flip(1)
+    return dict(akeys=akeys.view(torch.uint8).view(-1), accts=accts.view(-1), skeys=skeys.view(torch.uint8).view(-1),
+                svals=vals.view(-1), offs=offs, n_accounts=n_acc, n_slots=m, max_trie=int(sizes[0]),
+                contracts=n_contracts)
+
+
+def bench_c4(args, eng, dev, rank, world, barrier, max_over_ranks):
+    """BASELINE config 4: MerkleExecute-style full build of a mainnet-shaped state, subtries sharded over the GPUs."""
+    import torch
+    import torch.distributed as dist
+    lo, hi = rank * 16 // world, (rank + 1) * 16 // world
+    sh = make_c4_shard(4 + 1000 * rank, args.c4_leaves, lo, hi, dev)
+    n_acc, leaves = sh["n_accounts"], sh["n_accounts"] + sh["n_slots"]
+    d_root = torch.zeros(32, dtype=torch.uint8, device=dev)
+    d_front = torch.zeros(16 * 68, dtype=torch.uint8, device=dev)
+    gathered = [torch.zeros(16 * 68, dtype=torch.uint8, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step():
+        if world == 1:
+            eng.state_root_full_dev(sh["akeys"], sh["accts"], n_acc, sh["skeys"], sh["svals"], sh["offs"], sh["n_slots"], d_root)
+        else:
+            eng.subtrie_frontier_dev(sh["akeys"], sh["accts"], n_acc, sh["skeys"], sh["svals"], sh["offs"], sh["n_slots"], d_front)
+            dist.all_gather(gathered, d_front)
+            merged = torch.stack(gathered).view(world, 16, 68)
+            pick = torch.arange(16, device=dev) * world // 16
+            step.front = merged[pick, torch.arange(16, device=dev)].contiguous().view(-1)
+            eng.root_from_frontier_dev(step.front, d_root)
+
+    for _ in range(2):
+        step()
+    barrier()
+    eng.dev_status()
+    steps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    eng.dev_status()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    stats = eng.last_stats()
+    res = {"metric": "state_root_leaves_per_sec", "value": world * leaves / (ms * 1e-3), "unit": "leaves/s", "ms_per_step": ms,
+           "steps": steps, "root": bytes(d_root.cpu().numpy()).hex(),
+           "config": {"workload": f"C4: mainnet-shape full build, {leaves} leaves per GPU ({world * leaves} total): "
+                                  f"{n_acc} accounts (80% EOAs), {sh['contracts']} contracts with Zipf(1.2) storage sizes, "
+                                  f"largest trie {sh['max_trie']} slots",
+                      "parallelism": "single GPU" if world == 1 else
+                      f"accounts sharded by top key nibble over {world} GPUs, one NCCL all-gather of 16 frontier entries"},
+           "stats_rank0": stats}
+    del sh
+    torch.cuda.empty_cache()
     return res
 
 

@@ -133,3 +133,20 @@ def test_c5_update_revert_round_trip(eng):
     assert torch.equal(root2, root0)
     trie.close()
     eng.set_stream(None)
+
+
+def test_c4_mainnet_shape_small_vs_oracle(eng):
+    """The mainnet-shaped generator of bench.py (80% EOAs, Zipf(1.2) storage sizes: one huge trie, a long tail of
+    1-slot tries) at 300k leaves: root and TrieUpdates against the oracle."""
+    import torch
+    from bench import make_c4_shard
+    from reth_b200 import ACCOUNT_DTYPE
+    dev = torch.device("cuda", 0)
+    sh = make_c4_shard(4, 300_000, 0, 16, dev)
+    h = lambda t: t.cpu().numpy()
+    args = (h(sh["akeys"]).reshape(-1, 32), h(sh["accts"]).view(ACCOUNT_DTYPE).reshape(-1), h(sh["skeys"]).reshape(-1, 32),
+            h(sh["svals"]).reshape(-1, 32), h(sh["offs"]).astype(np.uint64))
+    assert sh["max_trie"] > 20_000 and int((np.diff(args[4]) == 1).sum()) > 10_000
+    root, au, su = eng.state_root_full(*args, want_updates=True)
+    o_root, o_au, o_su = oracle.state_root_full(*args, want_updates=True, threads=8)
+    assert root == o_root and au == o_au and su == o_su
