@@ -236,6 +236,15 @@ B200_API int32_t b200_trie_update(b200_trie *, const uint8_t *dirty_keys32, cons
                                   uint8_t root32[32], b200_updates *opt_updates, b200_stats *opt_stats);
 B200_API int32_t b200_trie_update_dev(b200_trie *, const void *d_dirty_keys32, const void *d_new_accts,
                                       const void *d_new_storage_roots32, uint64_t m, void *d_root32);
+/* General commit of a dirty set with HashedPostStateSorted semantics (crates/trie/common/src/hashed_state.rs:519-524):
+ * keys32 strictly ascending; present[i] != 0 (or present == NULL) = upsert accts[i], present[i] == 0 = delete (a delete
+ * of an absent key is a no-op).  Value changes of existing accounts take the in-place path of b200_trie_update; any
+ * insert or delete merges the keys on the device and rebuilds the trie there (*out_rebuilt = 1; opt_updates then holds
+ * the complete node set of the new trie, to be written after clearing AccountsTrie as MerkleStage's rebuild path does,
+ * crates/stages/stages/src/stages/merkle.rs:237-238). */
+B200_API int32_t b200_trie_apply(b200_trie *, const uint8_t *keys32, const b200_account *accts, const uint8_t *present,
+                                 const uint8_t *storage_roots32, uint64_t m, uint8_t root32[32], int32_t *out_rebuilt,
+                                 b200_updates *opt_updates, b200_stats *opt_stats);
 B200_API int32_t b200_trie_root(b200_trie *, uint8_t root32[32]);
 B200_API uint64_t b200_trie_device_bytes(const b200_trie *);
 B200_API uint64_t b200_trie_leaves(const b200_trie *);

@@ -120,6 +120,7 @@ def load():
     sig("b200_trie_create_dev", i32, vp, vp, vp, vp, u64, C.POINTER(vp), vp)
     sig("b200_trie_update", i32, vp, vp, vp, vp, u64, vp, PU, PS)
     sig("b200_trie_update_dev", i32, vp, vp, vp, vp, u64, vp)
+    sig("b200_trie_apply", i32, vp, vp, vp, vp, vp, u64, vp, C.POINTER(i32), PU, PS)
     sig("b200_trie_root", i32, vp, vp)
     sig("b200_trie_device_bytes", u64, vp)
     sig("b200_trie_leaves", u64, vp)

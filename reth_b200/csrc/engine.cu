@@ -59,7 +59,7 @@ extern "C" B200_API b200_ctx *b200_create(int32_t device_ordinal) {
     if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return bail(e);
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     c->stream = c->own_stream;
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 3; i++)
         if ((e = cudaStreamCreateWithFlags(&c->copy_streams[i], cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail(e);
@@ -80,8 +80,8 @@ extern "C" B200_API void b200_destroy(b200_ctx *c) {
                       &c->gap_sorted, &c->bound_rank, &c->head, &c->node_start, &c->node_ref, &c->node_meta,
                       &c->node_l, &c->node_r, &c->node_masks, &c->cub_temp, &c->small, &c->sroots, &c->buckets,
                       &c->upd_flags, &c->upd_nh, &c->upd_ids, &c->upd_prefix, &c->in_a, &c->in_b, &c->in_c,
-                      &c->in_d, &c->in_e, &c->out_a, &c->chunk_in[0], &c->chunk_in[1], &c->chunk_out[0],
-                      &c->chunk_out[1], &c->sort_ka, &c->sort_kb, &c->sort_ia, &c->sort_flag, &c->sort_perm,
+                      &c->in_d, &c->in_e, &c->out_a, &c->chunk_in[0], &c->chunk_in[1], &c->chunk_in[2], &c->chunk_out[0],
+                      &c->chunk_out[1], &c->chunk_out[2], &c->sort_ka, &c->sort_kb, &c->sort_ia, &c->sort_flag, &c->sort_perm,
                       &c->sort_out, &c->node_key, &c->node_key2, &c->node_ids, &c->node_order};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -89,7 +89,7 @@ extern "C" B200_API void b200_destroy(b200_ctx *c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->chunk_events) cudaEventDestroy(e);
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 3; i++)
         if (c->copy_streams[i]) cudaStreamDestroy(c->copy_streams[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -206,22 +206,23 @@ extern "C" B200_API int32_t b200_keccak256_var_dev(b200_ctx *c, const void *d_da
     return B200_OK;
 }
 
-// Host buffers: chunked and double-buffered so that H2D, hashing and D2H of consecutive chunks overlap
-// (fully asynchronous when the caller's buffers are page-locked, see b200_host_alloc).
+// Host buffers: chunked over three streams so that the H2D copy of chunk k+2, the hashing of chunk k+1 and the D2H
+// copy of chunk k overlap (both DMA directions stay busy; fully asynchronous when the caller's buffers are
+// page-locked, see b200_host_alloc).
 extern "C" B200_API int32_t b200_keccak256_fixed(b200_ctx *c, const uint8_t *in, uint32_t msg_len, uint32_t stride, uint64_t n,
                                         uint8_t *out32) {
     if (!c || (n && (!in || !out32)) || stride < msg_len) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
     if (n == 0) return B200_OK;
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
-    const uint64_t CHUNK = 1ull << 20;  // messages per chunk
+    const uint64_t CHUNK = 1ull << 19;  // messages per chunk
     uint64_t chunk = n < CHUNK ? n : CHUNK;
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 3; i++) {
         TRY(ensure(c, c->chunk_in[i], chunk * stride));
         TRY(ensure(c, c->chunk_out[i], chunk * 32));
     }
     int slot = 0;
-    for (uint64_t lo = 0; lo < n; lo += chunk, slot ^= 1) {
+    for (uint64_t lo = 0; lo < n; lo += chunk, slot = (slot + 1) % 3) {
         uint64_t m = n - lo < chunk ? n - lo : chunk;
         cudaStream_t st = c->copy_streams[slot];
         size_t in_bytes = (m - 1) * (size_t)stride + msg_len;
@@ -229,8 +230,7 @@ extern "C" B200_API int32_t b200_keccak256_fixed(b200_ctx *c, const uint8_t *in,
         CU(launch_keccak256_fixed(c->chunk_in[slot].p, msg_len, stride, m, c->chunk_out[slot].p, st, &c->launches));
         CU(cudaMemcpyAsync(out32 + lo * 32, c->chunk_out[slot].p, m * 32, cudaMemcpyDeviceToHost, st));
     }
-    CU(cudaStreamSynchronize(c->copy_streams[0]));
-    CU(cudaStreamSynchronize(c->copy_streams[1]));
+    for (int i = 0; i < 3; i++) CU(cudaStreamSynchronize(c->copy_streams[i]));
     return B200_OK;
 }
 
@@ -1297,6 +1297,151 @@ extern "C" B200_API int32_t b200_trie_update(b200_trie *t, const uint8_t *dirty_
     if (r == B200_OK) {
         c->stats.branches_added = D;
         if (opt_updates) r = collect_updates_subset(c, t->f, static_cast<const uint32_t *>(t->dirty_ids.p), D, opt_updates);
+    }
+    if (r != B200_OK && opt_updates) b200_updates_release(opt_updates);
+    if (opt_stats) *opt_stats = c->stats;
+    return r;
+}
+
+static void trie_free(b200_trie *t, DevBuf &b) {
+    if (b.p) {
+        cudaFree(b.p);
+        t->bytes -= b.cap;
+        b = DevBuf{};
+    }
+}
+
+// General commit of a sorted dirty set (HashedPostStateSorted semantics: present = upsert, absent = delete).  If every
+// entry is a value change of an existing account the dirty paths are re-hashed in place; otherwise the keys are
+// merged on the device (two scans + two scatters) and the trie is rebuilt from the merged arrays — the state never
+// travels back to the host.  *out_rebuilt tells which one happened: after a rebuild opt_updates holds the COMPLETE
+// node set of the new trie (the caller clears AccountsTrie first, like MerkleStage's rebuild path, merkle.rs:237-238).
+extern "C" B200_API int32_t b200_trie_apply(b200_trie *t, const uint8_t *keys32, const b200_account *accts,
+                                            const uint8_t *present, const uint8_t *storage_roots32, uint64_t m,
+                                            uint8_t root32[32], int32_t *out_rebuilt, b200_updates *opt_updates,
+                                            b200_stats *opt_stats) {
+    if (!t || !root32 || (m && (!keys32 || !accts))) return fail(t ? t->c : nullptr, B200_ERR_INVALID_ARG, "bad argument");
+    b200_ctx *c = t->c;
+    if (opt_updates) memset(opt_updates, 0, sizeof *opt_updates);
+    if (out_rebuilt) *out_rebuilt = 0;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    if (storage_roots32 && !t->has_sroots) return fail(c, B200_ERR_INVALID_ARG, "trie was created without storage roots");
+    TRY(trie_alloc(t, t->in_keys, (m ? m : 1) * 32));
+    TRY(trie_alloc(t, t->in_accts, (m ? m : 1) * 72));
+    TRY(trie_alloc(t, t->idx, (m ? m : 1) * 4));
+    TRY(trie_alloc(t, t->dirty_key, (m ? m : 1) * 2));  // kind[m] | present[m]
+    uint8_t *d_kind = static_cast<uint8_t *>(t->dirty_key.p), *d_present = d_kind + (m ? m : 1);
+    if (m) {
+        CU(cudaMemcpyAsync(t->in_keys.p, keys32, m * 32, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(t->in_accts.p, accts, m * 72, cudaMemcpyHostToDevice, st));
+        if (present) CU(cudaMemcpyAsync(d_present, present, m, cudaMemcpyHostToDevice, st));
+        if (storage_roots32) {
+            TRY(trie_alloc(t, t->in_sroots, m * 32));
+            CU(cudaMemcpyAsync(t->in_sroots.p, storage_roots32, m * 32, cudaMemcpyHostToDevice, st));
+        }
+    }
+    const uint8_t *d_keys = static_cast<const uint8_t *>(t->in_keys.p), *d_accts = static_cast<const uint8_t *>(t->in_accts.p);
+    const uint8_t *d_sr = storage_roots32 ? static_cast<const uint8_t *>(t->in_sroots.p) : nullptr;
+    TRY(reset_build_state(c));
+    uint32_t *counts = small_u32(c) + SM_HIST;  // [0] inserts [1] deletes [2] value updates
+    CU(cudaMemsetAsync(counts, 0, 16, st));
+    uint32_t *lb = static_cast<uint32_t *>(t->idx.p);
+    CU(launch_locate_classify(static_cast<const uint8_t *>(t->keys.p), t->n, d_keys, present ? d_present : nullptr, m, lb, d_kind,
+                              counts, reinterpret_cast<int *>(small_u32(c) + SM_ERR), st));
+    c->launches++;
+    uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
+    CU(cudaMemcpyAsync(ps + 300, counts, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ps, small_u32(c) + SM_ERR, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (ps[0] != B200_DEVERR_NONE) return map_dev_error(c, (int)ps[0]);
+    const uint64_t n_ins = ps[300], n_del = ps[301], n_upd = ps[302];
+    int32_t r = B200_OK;
+    if (n_ins == 0 && n_del == 0 && n_upd == m) {
+        // ---- value changes only: wavefront re-hash of the dirty paths
+        r = trie_update_on_device(t, d_keys, d_accts, d_sr, m);
+        if (r == B200_OK) {
+            cudaError_t e = cudaMemcpyAsync(root32, t->root.p, 32, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) r = fail(c, B200_ERR_CUDA, "root copy: %s", cudaGetErrorString(e));
+        }
+        if (r == B200_OK) r = sync_and_status(c);
+        uint32_t D = 0;
+        if (r == B200_OK) r = trie_read_dirty_count(t, &D);
+        if (r == B200_OK) {
+            c->stats.branches_added = D;
+            if (opt_updates) r = collect_updates_subset(c, t->f, static_cast<const uint32_t *>(t->dirty_ids.p), D, opt_updates);
+        }
+    } else {
+        // ---- shape changes: merge on the device, rebuild
+        const uint64_t n = t->n, n2 = n + n_ins - n_del;
+        if (n2 >= (1ull << 31)) return fail(c, B200_ERR_INVALID_ARG, "merged trie exceeds 2^31-1 leaves");
+        DevBuf marks{}, nk{}, na{}, ns{};
+        auto cleanup = [&]() {
+            trie_free(t, marks);
+            trie_free(t, nk);
+            trie_free(t, na);
+            trie_free(t, ns);
+        };
+        // marks: ins_at[n+1] | del[n+1] | ins_incl[n+1] | del_excl[n+1] | ins_flag[m] | ins_rank[m]
+        size_t w = n + 1;
+        r = trie_alloc(t, marks, (4 * w + 2 * (m ? m : 1)) * 4);
+        if (r == B200_OK) r = trie_alloc(t, nk, (n2 ? n2 : 1) * 32);
+        if (r == B200_OK) r = trie_alloc(t, na, (n2 ? n2 : 1) * 72);
+        if (r == B200_OK && t->has_sroots) r = trie_alloc(t, ns, (n2 ? n2 : 1) * 32);
+        if (r != B200_OK) {
+            cleanup();
+            return r;
+        }
+        uint32_t *ins_at = static_cast<uint32_t *>(marks.p), *del = ins_at + w, *ins_incl = del + w, *del_excl = ins_incl + w,
+                 *ins_flag = del_excl + w, *ins_rank = ins_flag + (m ? m : 1);
+        auto run = [&]() -> int32_t {
+            CU(cudaMemsetAsync(ins_at, 0, 2 * w * 4, st));
+            CU(launch_merge_marks(lb, d_kind, m, ins_at, del, ins_flag, st));
+            size_t t1 = 0, t2 = 0, t3 = 0;
+            CU(cub::DeviceScan::InclusiveSum(nullptr, t1, ins_at, ins_incl, (int64_t)w, st));
+            CU(cub::DeviceScan::ExclusiveSum(nullptr, t2, del, del_excl, (int64_t)w, st));
+            CU(cub::DeviceScan::ExclusiveSum(nullptr, t3, ins_flag, ins_rank, (int64_t)(m ? m : 1), st));
+            ENSURE(cub_temp, std::max(t1, std::max(t2, t3)));
+            CU(cub::DeviceScan::InclusiveSum(c->cub_temp.p, t1, ins_at, ins_incl, (int64_t)w, st));
+            CU(cub::DeviceScan::ExclusiveSum(c->cub_temp.p, t2, del, del_excl, (int64_t)w, st));
+            if (m) CU(cub::DeviceScan::ExclusiveSum(c->cub_temp.p, t3, ins_flag, ins_rank, (int64_t)m, st));
+            CU(launch_merge_scatter(static_cast<const uint8_t *>(t->keys.p), static_cast<const uint8_t *>(t->accts.p),
+                                    t->has_sroots ? static_cast<const uint8_t *>(t->sroots.p) : nullptr, n, ins_incl, del_excl, del,
+                                    d_keys, d_accts, d_sr, lb, d_kind, ins_rank, m, static_cast<uint8_t *>(nk.p),
+                                    static_cast<uint8_t *>(na.p), t->has_sroots ? static_cast<uint8_t *>(ns.p) : nullptr, st));
+            c->launches += 6;
+            CU(cudaStreamSynchronize(st));
+            return B200_OK;
+        };
+        r = run();
+        if (r != B200_OK) {
+            cleanup();
+            return r;
+        }
+        // the merged arrays become the trie's inputs; the old structure is dropped and rebuilt
+        trie_free(t, marks);
+        std::swap(t->keys, nk);
+        std::swap(t->accts, na);
+        if (t->has_sroots) std::swap(t->sroots, ns);
+        cleanup();
+        DevBuf *old[] = {&t->Lp, &t->nibs, &t->leaf_ref, &t->leaf_meta, &t->S, &t->E, &t->gap_sorted, &t->node_start,
+                         &t->node_ref, &t->node_meta, &t->node_l, &t->node_r, &t->node_masks, &t->leaf_parent,
+                         &t->node_parent, &t->dirty, &t->dirty_ids, &t->dirty_order};
+        for (DevBuf *b : old) trie_free(t, *b);
+        t->n = n2;
+        r = trie_build_owned(t);
+        if (r == B200_OK) {
+            cudaError_t e = cudaMemcpy(root32, t->root.p, 32, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) r = fail(c, B200_ERR_CUDA, "root copy: %s", cudaGetErrorString(e));
+        }
+        if (out_rebuilt) *out_rebuilt = 1;
+        if (r == B200_OK && opt_updates) {
+            Built b;
+            b.f = t->f;
+            b.n_nodes = t->B;
+            r = collect_updates(c, b, nullptr, 0, opt_updates);
+        }
     }
     if (r != B200_OK && opt_updates) b200_updates_release(opt_updates);
     if (opt_stats) *opt_stats = c->stats;

@@ -20,7 +20,7 @@ struct DevBuf {
 struct b200_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaStream_t copy_streams[2] = {nullptr, nullptr};
+    cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> chunk_events;
     std::mutex mu;
@@ -37,7 +37,7 @@ struct b200_ctx {
     DevBuf sort_ka, sort_kb, sort_ia, sort_flag, sort_perm, sort_out;
     DevBuf node_key, node_key2, node_ids, node_order;
     // staging for host-pointer entry points
-    DevBuf in_a, in_b, in_c, in_d, in_e, out_a, chunk_in[2], chunk_out[2];
+    DevBuf in_a, in_b, in_c, in_d, in_e, out_a, chunk_in[3], chunk_out[3];
     void *pinned_small = nullptr;  // 4 KiB page-locked readback area
 };
 

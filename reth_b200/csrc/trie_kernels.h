@@ -119,6 +119,15 @@ cudaError_t launch_wavefront_two_stage(const ForestDev &f, uint8_t *accts, uint8
                                        uint32_t *dirty_list, uint32_t *dirty_count, uint32_t *handoff_list,
                                        uint32_t *handoff_count, uint64_t max_handoff, uint8_t *root_out, int split_depth,
                                        cudaStream_t st);
+cudaError_t launch_locate_classify(const uint8_t *keys, uint64_t n, const uint8_t *dirty_keys, const uint8_t *present,
+                                   uint64_t m, uint32_t *lb, uint8_t *kind, uint32_t *counts, int *err, cudaStream_t st);
+cudaError_t launch_merge_marks(const uint32_t *lb, const uint8_t *kind, uint64_t m, uint32_t *ins_at, uint32_t *del,
+                               uint32_t *ins_flag, cudaStream_t st);
+cudaError_t launch_merge_scatter(const uint8_t *keys, const uint8_t *accts, const uint8_t *sroots, uint64_t n,
+                                 const uint32_t *ins_incl, const uint32_t *del_excl, const uint32_t *del,
+                                 const uint8_t *dirty_keys, const uint8_t *new_accts, const uint8_t *new_sroots,
+                                 const uint32_t *lb, const uint8_t *kind, const uint32_t *ins_rank, uint64_t m, uint8_t *nkeys,
+                                 uint8_t *naccts, uint8_t *nsroots, cudaStream_t st);
 cudaError_t launch_stored_flags_subset(const ForestDev &f, const uint32_t *ids, uint32_t count, uint8_t *flags,
                                        uint32_t *n_hashes, cudaStream_t st);
 cudaError_t launch_pick_subset(const uint32_t *ids, const uint32_t *prefix, const uint32_t *sel_pos, uint32_t n_sel,

@@ -322,6 +322,23 @@ class ResidentTrie:
             res.append(s.as_dict())
         return res[0] if len(res) == 1 else tuple(res)
 
+    def apply(self, keys, accounts, present=None, storage_roots32=None, want_updates=False):
+        """HashedPostStateSorted semantics: keys strictly ascending, present[i] False = delete.  -> (root, rebuilt[, updates])."""
+        keys = _np(keys).reshape(-1, 32)
+        accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
+        pres = None if present is None else _np(np.asarray(present, dtype=np.uint8))
+        sr = None if storage_roots32 is None else _np(storage_roots32).reshape(-1, 32)
+        root = np.empty(32, np.uint8)
+        rebuilt = C.c_int32(0)
+        u, s = Updates(), Stats()
+        self.engine._check(self.engine.lib.b200_trie_apply(self.handle, _ptr(keys), _ptr(accounts), _ptr(pres), _ptr(sr),
+                                                           len(keys), _ptr(root), C.byref(rebuilt),
+                                                           C.byref(u) if want_updates else None, C.byref(s)))
+        self._root = root.tobytes()
+        if want_updates:
+            return self._root, bool(rebuilt.value), updates_to_records(u, self.engine.lib)
+        return self._root, bool(rebuilt.value)
+
     def update_dev(self, t_keys, t_accts, t_sroots, m: int, t_root=None):
         self.engine._check(self.engine.lib.b200_trie_update_dev(
             self.handle, t_keys.data_ptr(), t_accts.data_ptr(), t_sroots.data_ptr() if t_sroots is not None else None, m,

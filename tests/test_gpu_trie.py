@@ -365,3 +365,66 @@ def test_pipelined_host_path_large_state(eng):
     # the monolithic path (updates retained) agrees
     root2, _, _ = eng.state_root_full(akeys, accs, skeys, svals, offs, want_updates=True)
     assert root2 == root
+
+
+def test_resident_trie_apply_inserts_deletes_updates(eng):
+    """b200_trie_apply with HashedPostStateSorted semantics (upsert / delete, keys ascending): after every batch the
+    resident root equals a from-scratch oracle build of the model state — fuzz_state_root_incremental
+    (crates/trie/db/tests/trie.rs:680-717) restated.  Pure value batches must take the in-place path."""
+    from reth_b200 import ResidentTrie
+    rng = np.random.default_rng(5)
+    keys0, accs0 = synth_accounts(400, 4000)
+    model = {keys0[i].tobytes(): accs0[i].copy() for i in range(len(keys0))}
+    t = ResidentTrie.create(eng, keys0, accs0)
+
+    def model_root():
+        ks = sorted(model)
+        k = np.frombuffer(b"".join(ks), np.uint8).reshape(-1, 32) if ks else np.zeros((0, 32), np.uint8)
+        a = np.array([model[x] for x in ks], oracle.ACCOUNT_DTYPE) if ks else np.zeros(0, oracle.ACCOUNT_DTYPE)
+        return oracle.state_root(k, a), k, a
+
+    for batch in range(6):
+        existing = sorted(model)
+        upd = [existing[i] for i in rng.choice(len(existing), 150, replace=False)]
+        dele = [existing[i] for i in rng.choice(len(existing), 60 if batch % 2 == 0 else 0, replace=False)] if batch < 5 else []
+        ins = [bytes(r) for r in random_keys(9000 + batch, 80 if batch % 3 != 2 else 0)]
+        absent_del = [bytes(r) for r in random_keys(9900 + batch, 5)]          # deleting what is not there: no-op
+        entries = {}
+        for k in upd + ins:
+            a = np.zeros((), oracle.ACCOUNT_DTYPE)
+            a["nonce"] = rng.integers(0, 1000)
+            a["balance"][20:] = rng.integers(0, 256, 12, dtype=np.uint8)
+            a["code_hash"] = np.frombuffer(oracle.KECCAK_EMPTY, np.uint8)
+            entries[k] = (True, a)
+        for k in dele + (absent_del if batch % 2 == 0 else []):
+            entries[k] = (False, np.zeros((), oracle.ACCOUNT_DTYPE))
+        ks = sorted(entries)
+        kk = np.frombuffer(b"".join(ks), np.uint8).reshape(-1, 32)
+        aa = np.array([entries[k][1] for k in ks], oracle.ACCOUNT_DTYPE)
+        pres = np.array([entries[k][0] for k in ks], np.uint8)
+        root, rebuilt, updates = t.apply(kk, aa, pres, want_updates=True)
+        for k in ks:
+            if entries[k][0]:
+                model[k] = entries[k][1]
+            else:
+                model.pop(k, None)
+        exp_root, mk, ma = model_root()
+        assert root == exp_root and len(t) == len(model)
+        structural = bool(ins) or bool(dele) or (batch % 2 == 0)
+        assert rebuilt == structural
+        if rebuilt:
+            assert updates == oracle.state_root(mk, ma, want_updates=True)[1]      # complete node set of the new trie
+    # unsorted dirty keys are rejected, nothing changes
+    from reth_b200 import B200Error, _lib
+    before = t.root()
+    with pytest.raises(B200Error) as e:
+        t.apply(kk[::-1].copy(), aa[::-1].copy(), pres[::-1].copy())
+    assert e.value.status == _lib.ERR_UNSORTED and t.root() == before
+    # delete everything -> empty trie; then re-insert
+    ks = sorted(model)
+    kk = np.frombuffer(b"".join(ks), np.uint8).reshape(-1, 32)
+    root, rebuilt = t.apply(kk, np.zeros(len(ks), oracle.ACCOUNT_DTYPE), np.zeros(len(ks), np.uint8))
+    assert root == oracle.EMPTY_ROOT_HASH and rebuilt and len(t) == 0
+    root, rebuilt = t.apply(keys0[:10], accs0[:10])
+    assert root == oracle.state_root(keys0[:10], accs0[:10]) and len(t) == 10
+    t.close()
