@@ -203,3 +203,87 @@ class ParallelStateRoot(StateRoot):
 
     def incremental_root_with_updates(self) -> Tuple[bytes, TrieUpdates]:
         return self.root_with_updates()
+
+
+class ResidentStateRoot:
+    """Live-path commitment with the account trie resident in HBM (BASELINE config 5).
+
+    Plays the part of `StateRoot::overlay_root_with_updates` / `ParallelStateRoot::incremental_root_with_updates`
+    (crates/trie/db/src/state.rs:184-230, crates/trie/parallel/src/root.rs:35-77): `commit(HashedPostState)` folds one
+    block's hashed post state into the committed state and returns the new root.  The hashed tables the reference
+    reads through cursors (`HashedAccounts`, `HashedStorages`) are kept here as host dictionaries; the trie itself —
+    every node hash of every level — lives on the device and only the dirty paths are re-hashed
+    (`b200_trie_apply`).  Storage roots of the touched accounts are recomputed from their complete post-block storage
+    in one `b200_storage_roots` call."""
+
+    def __init__(self, engine: Engine, state: HashedPostStateSorted):
+        from .engine import ACCOUNT_DTYPE, ResidentTrie
+        self.engine = engine
+        self.accounts = {k: a for k, a in state.accounts if a is not None}
+        self.storages = {k: {s: v for s, v in st.storage_slots if v != 0} for k, st in state.storages.items()
+                         if k in self.accounts}
+        keys, accts, skeys, svals, offs = state.to_flat()
+        sroots = engine.storage_roots(skeys, svals, offs) if len(keys) else np.zeros((0, 32), np.uint8)
+        self.trie = ResidentTrie.create(engine, keys, accts, sroots)
+        self._dtype = ACCOUNT_DTYPE
+
+    def root(self) -> bytes:
+        return self.trie.root()
+
+    def commit(self, post) -> Tuple[bytes, bool]:
+        """post: HashedPostState.  -> (new root, rebuilt) where rebuilt tells whether the trie shape changed."""
+        from .hashed_state import Account
+        touched = set(post.accounts) | set(post.storages)
+        # 1. storage overlay: wiped hides everything older, zero deletes (hashed_cursor/post_state.rs:185-195,260-297)
+        for addr, hs in post.storages.items():
+            cur = {} if hs.wiped else dict(self.storages.get(addr, {}))
+            for slot, val in hs.storage.items():
+                if val == 0:
+                    cur.pop(slot, None)
+                else:
+                    cur[slot] = val
+            self.storages[addr] = cur
+        # 2. account overlay
+        for addr, acc in post.accounts.items():
+            if acc is None:
+                self.accounts.pop(addr, None)
+                self.storages.pop(addr, None)
+            else:
+                self.accounts[addr] = acc
+        dirty = sorted(touched)
+        if not dirty:
+            return self.trie.root(), False
+        live = [k for k in dirty if k in self.accounts]
+        # 3. storage roots of the live touched accounts, all tries in one device call
+        slot_keys, slot_vals, offs = [], [], [0]
+        for k in live:
+            st = sorted(self.storages.get(k, {}).items())
+            slot_keys += [s for s, _ in st]
+            slot_vals += [int(v).to_bytes(32, "big") for _, v in st]
+            offs.append(offs[-1] + len(st))
+        m = len(slot_keys)
+        sk = np.frombuffer(b"".join(slot_keys), np.uint8).reshape(m, 32) if m else np.zeros((0, 32), np.uint8)
+        sv = np.frombuffer(b"".join(slot_vals), np.uint8).reshape(m, 32) if m else np.zeros((0, 32), np.uint8)
+        roots = self.engine.storage_roots(sk, sv, np.array(offs, np.uint64)) if live else np.zeros((0, 32), np.uint8)
+        root_of = {k: roots[i] for i, k in enumerate(live)}
+        # 4. one sorted dirty set for the device: upserts and deletes
+        keys = np.frombuffer(b"".join(dirty), np.uint8).reshape(len(dirty), 32)
+        accts = np.zeros(len(dirty), self._dtype)
+        present = np.zeros(len(dirty), np.uint8)
+        sroots = np.zeros((len(dirty), 32), np.uint8)
+        for i, k in enumerate(dirty):
+            a = self.accounts.get(k)
+            if a is None:
+                continue  # destroyed (or storage of an account that does not exist): delete / no-op
+            present[i] = 1
+            accts[i]["nonce"] = a.nonce
+            accts[i]["balance"] = np.frombuffer(int(a.balance).to_bytes(32, "big"), np.uint8)
+            accts[i]["code_hash"] = np.frombuffer(a.code_hash(), np.uint8)
+            sroots[i] = root_of[k]
+        try:
+            return self.trie.apply(keys, accts, present, sroots)
+        except Exception as e:  # noqa: BLE001
+            raise StateRootError(str(e)) from e
+
+    def close(self):
+        self.trie.close()

@@ -115,3 +115,60 @@ def test_destroyed_accounts_and_wiped_storage(eng):
     only = HashedPostState(accounts={k1: Account(1, 1)}).into_sorted()
     assert root == StateRoot(eng, only).root()
     assert updates.storage_tries[k2].is_deleted
+
+
+def test_resident_state_root_commits_blocks(eng):
+    """Live path: fold a sequence of per-block HashedPostStates (balance changes, new accounts, destroyed accounts,
+    storage writes / zeroing / wipes) into a resident state; after every block the root equals a from-scratch
+    StateRoot over the merged state — the reference's incremental == full criterion
+    (crates/trie/db/tests/trie.rs:680-717, crates/trie/parallel/src/root.rs:287-400)."""
+    from reth_b200 import ResidentStateRoot
+    rng = np.random.default_rng(77)
+    rk = lambda: bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+    base = HashedPostState()
+    for _ in range(800):
+        k = rk()
+        base.accounts[k] = Account(int(rng.integers(0, 50)), int(rng.integers(1, 2**62)))
+        if rng.random() < 0.25:
+            base.storages[k] = HashedStorage(False, {rk(): int(rng.integers(1, 2**62)) for _ in range(int(rng.integers(1, 30)))})
+    merged = HashedPostState(dict(base.accounts), {k: HashedStorage(False, dict(v.storage)) for k, v in base.storages.items()})
+    rs = ResidentStateRoot(eng, base.into_sorted())
+    assert rs.root() == StateRoot(eng, base.into_sorted()).root()
+    for block in range(5):
+        post = HashedPostState()
+        live = [k for k, a in merged.accounts.items() if a is not None]
+        for k in rng.choice(len(live), 40, replace=False):
+            a = merged.accounts[live[k]]
+            post.accounts[live[k]] = Account(a.nonce + 1, a.balance + 7, a.bytecode_hash)
+        if block % 2 == 0:
+            for _ in range(10):
+                post.accounts[rk()] = Account(0, int(rng.integers(1, 10**18)))               # new accounts
+            for k in rng.choice(len(live), 5, replace=False):
+                post.accounts[live[k]] = None                                                 # destroyed
+                post.storages[live[k]] = HashedStorage(True, {})
+        with_storage = [k for k in merged.storages if merged.accounts.get(k) is not None and k not in post.accounts]
+        for k in with_storage[:6]:
+            st = merged.storages[k].storage
+            slots = list(st)
+            changes = {slots[0]: 0} if slots else {}                                          # zero = delete
+            changes[rk()] = int(rng.integers(1, 2**60))
+            post.storages[k] = HashedStorage(block == 3, changes)                             # one block wipes
+        root, rebuilt = rs.commit(post)
+        # model: merge like HashedPostState::extend + deletion rules
+        for k, hs in post.storages.items():
+            cur = {} if hs.wiped else dict(merged.storages.get(k, HashedStorage()).storage)
+            for s, v in hs.storage.items():
+                if v == 0:
+                    cur.pop(s, None)
+                else:
+                    cur[s] = v
+            merged.storages[k] = HashedStorage(False, cur)
+        for k, a in post.accounts.items():
+            if a is None:
+                merged.accounts.pop(k, None)
+                merged.storages.pop(k, None)
+            else:
+                merged.accounts[k] = a
+        assert root == StateRoot(eng, merged.into_sorted()).root(), block
+        assert rebuilt == (block % 2 == 0)
+    rs.close()
