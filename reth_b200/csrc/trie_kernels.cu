@@ -54,6 +54,14 @@ struct Strip {
 #pragma unroll
         for (int i = 0; i < 8; i++) word(x[i]);
     }
+    // `cnt` empty-slot markers (0x80), four at a time whatever the current byte alignment
+    __device__ __forceinline__ void fill80(uint32_t cnt) {
+        while (cnt >= 4) {
+            word(0x80808080u);
+            cnt -= 4;
+        }
+        while (cnt--) byte(0x80);
+    }
     // bytes [b0, 32) of a 32-byte string held as 8 little-endian words
     __device__ __forceinline__ void tail32(const uint32_t (&x)[8], uint32_t b0) {
 #pragma unroll
@@ -614,7 +622,8 @@ __device__ __forceinline__ uint32_t encode_branch_u(Strip<BLOCK> &s, const Fores
                 load32_nc(rp, ref);
             }
             uint32_t nibble = nm[c] & 15;
-            for (; cur < nibble; cur++) s.byte(0x80);
+            s.fill80(nibble - cur);
+            cur = nibble;
             uint32_t clen = (nm[c] >> 8) & META_LEN;
             if (clen == 0) {
                 s.byte(0xa0);
@@ -625,8 +634,7 @@ __device__ __forceinline__ uint32_t encode_branch_u(Strip<BLOCK> &s, const Fores
             cur++;
         }
     }
-    for (; cur < 16; cur++) s.byte(0x80);
-    s.byte(0x80);  // value slot
+    s.fill80(16 - cur + 1);  // trailing empty slots + the value slot
     return list_header_len(payload) + payload;
 }
 
@@ -1323,75 +1331,6 @@ __global__ void locate_kernel(const uint8_t *__restrict__ keys, uint64_t n, cons
     idx_out[t] = (uint32_t)lo;
 }
 
-// Re-encodes the dirty leaves and marks their ancestor chains (stops at the first already-marked ancestor).
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) leaf_rehash_kernel(ForestDev f, uint8_t *__restrict__ accts,
-                                                            uint8_t *__restrict__ sroots,
-                                                            const uint8_t *__restrict__ new_accts,
-                                                            const uint8_t *__restrict__ new_sroots,
-                                                            const uint32_t *__restrict__ idx, uint64_t m,
-                                                            const uint32_t *__restrict__ leaf_parent,
-                                                            const uint32_t *__restrict__ node_parent,
-                                                            uint32_t *__restrict__ dirty) {
-    extern __shared__ uint32_t smem[];
-    if (*(volatile int *)f.err != B200_DEVERR_NONE) return;
-    Strip<BLOCK> s;
-    uint32_t hashed = 0;
-    for (uint64_t t = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; t < m; t += (uint64_t)gridDim.x * BLOCK) {
-        uint32_t i = idx[t];
-        s.init(smem);
-        {  // overwrite the resident account (and storage root) with the new value
-            const uint64_t *src = reinterpret_cast<const uint64_t *>(new_accts + 72 * t);
-            uint64_t *dst = reinterpret_cast<uint64_t *>(accts + 72 * (uint64_t)i);
-#pragma unroll
-            for (int w = 0; w < 9; w++) dst[w] = src[w];
-            if (new_sroots && sroots) {
-                uint32_t r[8];
-                load32(new_sroots + 32 * t, r);
-                store32(sroots + 32 * (uint64_t)i, r);
-            }
-        }
-        uint32_t k[8];
-        load32(f.keys + 32 * (uint64_t)i, k);
-        int pdl = depth_of(f.Lp[i]), pdr = depth_of(f.Lp[(uint64_t)i + 1]);
-        int pd = pdl > pdr ? pdl : pdr;
-        // plain loads: the account was written by this thread a moment ago
-        uint32_t len = encode_leaf<Strip<BLOCK>, true>(s, k, pd, new_accts + 72 * t,
-                                                sroots ? (new_sroots ? new_sroots + 32 * t : sroots + 32 * (uint64_t)i) : nullptr,
-                                                f.err);
-        uint32_t ref[8];
-        uint32_t meta = strip_to_ref(s, len, pd < 0, ref, hashed);
-        store32(f.leaf_ref + 32 * (uint64_t)i, ref);
-        f.leaf_meta[i] = (uint8_t)meta;
-        uint32_t p = leaf_parent[i];
-        while (p != 0xFFFFFFFFu) {
-            if (atomicExch(&dirty[p], 1u) != 0u) break;
-            p = node_parent[p];
-        }
-    }
-    for (int o = 16; o; o >>= 1) hashed += __shfl_xor_sync(0xffffffffu, hashed, o);
-    if ((threadIdx.x & 31) == 0 && hashed) atomicAdd(&f.counters[CNT_HASHED], (unsigned long long)hashed);
-}
-
-// depth keys + per-depth histogram of the dirty nodes (count known only on the device)
-__global__ void dirty_keys_kernel(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ count_p,
-                                  const ushort4 *__restrict__ node_masks, uint8_t *__restrict__ keys,
-                                  uint32_t *__restrict__ hist, uint32_t *__restrict__ dirty) {
-    __shared__ uint32_t sh[64];
-    if (threadIdx.x < 64) sh[threadIdx.x] = 0;
-    __syncthreads();
-    uint32_t cnt = *count_p;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += gridDim.x * blockDim.x) {
-        uint32_t v = ids[t];
-        uint32_t d = node_masks[v].w;
-        keys[t] = (uint8_t)(63u - d);
-        atomicAdd(&sh[63u - d], 1u);
-        dirty[v] = 0;  // consumed
-    }
-    __syncthreads();
-    if (threadIdx.x < 64 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
-}
-
 // ------------------------------------------------------------------------------------------------ structural updates
 // lb[t] = lower bound of dirty key t in the resident keys, found[t] = exact match; classifies every entry and counts
 // inserts (present && !found), deletes (!present && found) and value updates (present && found).
@@ -1918,25 +1857,6 @@ cudaError_t launch_locate(const uint8_t *keys, uint64_t n, const uint8_t *dirty_
                           int *err, cudaStream_t st) {
     if (m == 0) return cudaSuccess;
     locate_kernel<<<blocks_for(m, 128), 128, 0, st>>>(keys, n, dirty_keys, m, idx_out, err);
-    return cudaGetLastError();
-}
-cudaError_t launch_leaf_rehash(const ForestDev &f, uint8_t *accts, uint8_t *sroots, const uint8_t *new_accts,
-                               const uint8_t *new_sroots, const uint32_t *idx, uint64_t m, const uint32_t *leaf_parent,
-                               const uint32_t *node_parent, uint32_t *dirty, cudaStream_t st) {
-    if (m == 0) return cudaSuccess;
-    constexpr int B = 64;
-    auto k = leaf_rehash_kernel<B>;
-    size_t smem = (size_t)68 * B * 4;
-    k<<<persistent_grid(k, B, smem, m), B, smem, st>>>(f, accts, sroots, new_accts, new_sroots, idx, m, leaf_parent,
-                                                       node_parent, dirty);
-    return cudaGetLastError();
-}
-cudaError_t launch_dirty_keys(const uint32_t *ids, const uint32_t *count_p, uint64_t max_count, const ushort4 *node_masks,
-                              uint8_t *keys, uint32_t *hist, uint32_t *dirty, cudaStream_t st) {
-    if (max_count == 0) return cudaSuccess;
-    unsigned blocks = blocks_for(max_count, 256);
-    if (blocks > (unsigned)sms() * 4) blocks = (unsigned)sms() * 4;
-    dirty_keys_kernel<<<blocks, 256, 0, st>>>(ids, count_p, node_masks, keys, hist, dirty);
     return cudaGetLastError();
 }
 

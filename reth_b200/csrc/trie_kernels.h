@@ -104,9 +104,6 @@ cudaError_t launch_parent_links(const ForestDev &f, uint32_t n_nodes, uint32_t *
                                 cudaStream_t st);
 cudaError_t launch_locate(const uint8_t *keys, uint64_t n, const uint8_t *dirty_keys, uint64_t m, uint32_t *idx_out,
                           int *err, cudaStream_t st);
-cudaError_t launch_leaf_rehash(const ForestDev &f, uint8_t *accts, uint8_t *sroots, const uint8_t *new_accts,
-                               const uint8_t *new_sroots, const uint32_t *idx, uint64_t m, const uint32_t *leaf_parent,
-                               const uint32_t *node_parent, uint32_t *dirty, cudaStream_t st);
 cudaError_t launch_mark_pending(const ForestDev &f, const uint32_t *idx, uint64_t m, const uint32_t *leaf_parent,
                                 const uint32_t *node_parent, uint32_t *pending, cudaStream_t st);
 cudaError_t launch_wavefront(const ForestDev &f, uint8_t *accts, uint8_t *sroots, const uint8_t *new_accts,
@@ -132,7 +129,5 @@ cudaError_t launch_stored_flags_subset(const ForestDev &f, const uint32_t *ids, 
                                        uint32_t *n_hashes, cudaStream_t st);
 cudaError_t launch_pick_subset(const uint32_t *ids, const uint32_t *prefix, const uint32_t *sel_pos, uint32_t n_sel,
                                uint32_t *out_ids, uint32_t *out_prefix, cudaStream_t st);
-cudaError_t launch_dirty_keys(const uint32_t *ids, const uint32_t *count_p, uint64_t max_count, const ushort4 *node_masks,
-                              uint8_t *keys, uint32_t *hist, uint32_t *dirty, cudaStream_t st);
 
 }  // namespace b200
