@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -215,7 +216,11 @@ extern "C" B200_API int32_t b200_keccak256_fixed(b200_ctx *c, const uint8_t *in,
     if (n == 0) return B200_OK;
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
-    const uint64_t CHUNK = 1ull << 19;  // messages per chunk
+    static const uint64_t CHUNK = [] {  // messages per chunk (B200_KECCAK_CHUNK overrides, for tuning)
+        const char *e = getenv("B200_KECCAK_CHUNK");
+        uint64_t v = e ? strtoull(e, nullptr, 10) : 0;
+        return v >= 1024 ? v : (1ull << 19);
+    }();
     uint64_t chunk = n < CHUNK ? n : CHUNK;
     for (int i = 0; i < 3; i++) {
         TRY(ensure(c, c->chunk_in[i], chunk * stride));

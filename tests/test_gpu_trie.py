@@ -428,3 +428,51 @@ def test_resident_trie_apply_inserts_deletes_updates(eng):
     root, rebuilt = t.apply(keys0[:10], accs0[:10])
     assert root == oracle.state_root(keys0[:10], accs0[:10]) and len(t) == 10
     t.close()
+
+
+def test_reentrancy_two_contexts_and_shared_context(eng):
+    """ParallelStateRoot calls StorageRoot::calculate from many blocking threads (crates/trie/parallel/src/root.rs:
+    111-125): the library must be re-entrant.  Two contexts run concurrently; one context shared by several threads
+    serialises internally.  Every thread checks its own results against the oracle."""
+    import threading
+    from reth_b200 import Engine
+    other = Engine(0)
+    errors = []
+
+    def worker(e, seed):
+        try:
+            for it in range(4):
+                keys, accs = synth_accounts(seed * 10 + it, 20_000 + 1000 * seed)
+                sk, sv, so = synth_storage(seed * 10 + it, np.full(50, 30))
+                assert e.state_root(keys, accs) == oracle.state_root(keys, accs)
+                assert (e.storage_roots(sk, sv, so) == oracle.storage_roots(sk, sv, so)).all()
+                msgs = random_keys(seed * 100 + it, 50_000)
+                assert (e.keccak256_fixed(msgs) == oracle.keccak256_fixed(msgs)).all()
+        except Exception as ex:  # noqa: BLE001
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=worker, args=(eng if i % 2 == 0 else other, i)) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    other.close()
+    assert not errors, errors
+
+
+def test_null_and_bad_arguments_are_rejected(eng):
+    """The boundary never crashes on bad input: null pointers / inconsistent sizes give B200_ERR_INVALID_ARG."""
+    import ctypes as C
+    from reth_b200 import _lib
+    L = eng.lib
+    out = np.zeros(32, np.uint8)
+    assert L.b200_keccak256_fixed(eng.ctx, None, 32, 32, 5, out.ctypes.data) == _lib.ERR_INVALID_ARG
+    assert L.b200_keccak256_fixed(eng.ctx, out.ctypes.data, 32, 16, 1, out.ctypes.data) == _lib.ERR_INVALID_ARG  # stride < len
+    assert L.b200_state_root(eng.ctx, None, None, None, 3, out.ctypes.data, None, None) == _lib.ERR_INVALID_ARG
+    assert L.b200_storage_roots(eng.ctx, None, None, None, 1, out.ctypes.data, None, None) == _lib.ERR_INVALID_ARG
+    assert L.b200_keccak256_fixed(None, out.ctypes.data, 32, 32, 1, out.ctypes.data) == _lib.ERR_INVALID_ARG
+    assert b"bad argument" in L.b200_last_error(eng.ctx)
+    # n == 0 is fine everywhere
+    assert L.b200_keccak256_fixed(eng.ctx, None, 32, 32, 0, None) == 0
+    assert L.b200_state_root(eng.ctx, None, None, None, 0, out.ctypes.data, None, None) == 0
+    assert out.tobytes() == oracle.EMPTY_ROOT_HASH
