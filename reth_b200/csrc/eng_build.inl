@@ -1,0 +1,164 @@
+// eng_build.inl — one forest build: structure pass, leaf pass, level-by-level branch passes.
+// Part of the single translation unit engine.cu (textually included, in this order).
+
+// ------------------------------------------------------------------------------------------------ forest build
+struct IsBoundary {
+    __host__ __device__ uint32_t operator()(uint8_t v) const { return v == 0xFF ? 1u : 0u; }
+};
+
+struct Built {
+    ForestDev f{};
+    uint32_t n_nodes = 0;
+    uint32_t levels = 0;
+    uint32_t level_count[64] = {};  // branch nodes per depth
+};
+
+// Builds every trie of a forest over d_keys (n leaves).  d_seg_offsets == nullptr: one trie.
+// account: leaves are accounts (d_values = b200_account[n], d_sroots = storage roots or null); else storage
+// slots (d_values = U256 BE [n][32]).
+static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, const uint64_t *d_seg_offsets,
+                            uint64_t n_segs, bool account, const uint8_t *d_values, const uint8_t *d_sroots,
+                            bool retain_updates, Built &out) {
+    if (n >= (1ull << 31)) return fail(c, B200_ERR_INVALID_ARG, "at most 2^31-1 leaves per build");
+    cudaStream_t st = c->stream;
+    ForestDev &f = out.f;
+    f.n = n;
+    f.keys = d_keys;
+    f.err = reinterpret_cast<int *>(small_u32(c) + SM_ERR);
+    f.counters = reinterpret_cast<unsigned long long *>(small_u32(c) + SM_COUNTERS);
+    f.retain_updates = retain_updates ? 1 : 0;
+    out.n_nodes = 0;
+    out.levels = 0;
+    if (n == 0) return B200_OK;
+
+    ENSURE(Lp, n + 1);
+    ENSURE(nibs, n + 1);
+    ENSURE(leaf_ref, n * 32);
+    ENSURE(leaf_meta, n);
+    ENSURE(S, n * 4);
+    ENSURE(E, n * 4);
+    f.Lp = static_cast<uint8_t *>(c->Lp.p);
+    f.nibs = static_cast<uint8_t *>(c->nibs.p);
+    f.leaf_ref = static_cast<uint8_t *>(c->leaf_ref.p);
+    f.leaf_meta = static_cast<uint8_t *>(c->leaf_meta.p);
+    f.S = static_cast<uint32_t *>(c->S.p);
+    f.E = static_cast<uint32_t *>(c->E.p);
+
+    CU(cudaMemsetAsync(f.Lp, 0, n + 1, st));
+    if (d_seg_offsets) {
+        CU(launch_mark_boundaries(d_seg_offsets, n_segs, n, f.Lp, f.err, st));
+        c->launches++;
+    }
+    CU(launch_lcp(d_keys, n, f.Lp, f.nibs, f.err, st));
+    CU(launch_leaves(f, account, d_values, d_sroots, st));
+    c->launches += 2;
+    if (n < 2) return B200_OK;
+
+    // ---- gaps sorted by depth (stable: position order inside a depth) -> branch nodes in CSR form
+    const uint64_t G = n - 1;
+    ENSURE(iota, G * 4);
+    ENSURE(depth_sorted, G);
+    ENSURE(gap_sorted, G * 4);
+    ENSURE(head, G);
+    ENSURE(node_start, (G + 1) * 4);
+    uint32_t *bucket_off = small_u32(c) + SM_BUCKET_OFF;
+    uint32_t *level_lo = small_u32(c) + SM_LEVEL_LO;
+    uint32_t *n_nodes_p = small_u32(c) + SM_NNODES;
+    uint8_t *depth_sorted = static_cast<uint8_t *>(c->depth_sorted.p);
+    uint32_t *gap_sorted = static_cast<uint32_t *>(c->gap_sorted.p);
+    uint8_t *head = static_cast<uint8_t *>(c->head.p);
+    uint32_t *node_start = static_cast<uint32_t *>(c->node_start.p);
+
+    CU(launch_iota(static_cast<uint32_t *>(c->iota.p), G, 1, st));
+    c->launches++;
+    size_t t_sort = 0, t_sel = 0, t_scan = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, f.Lp + 1, depth_sorted, static_cast<uint32_t *>(c->iota.p),
+                                       gap_sorted, (int64_t)G, 0, 8, st));
+    thrust::counting_iterator<uint32_t> counting(0);
+    CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, head, node_start, n_nodes_p, (int64_t)G, st));
+    auto bflags = thrust::make_transform_iterator(static_cast<const uint8_t *>(f.Lp), IsBoundary());
+    uint32_t *bound_rank = nullptr;
+    if (d_seg_offsets) {
+        ENSURE(bound_rank, (n + 1) * 4);
+        bound_rank = static_cast<uint32_t *>(c->bound_rank.p);
+        CU(cub::DeviceScan::InclusiveSum(nullptr, t_scan, bflags, bound_rank, (int64_t)(n + 1), st));
+    }
+    size_t t_max = std::max(t_sort, std::max(t_sel, t_scan));
+    ENSURE(cub_temp, t_max);
+    CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_sort, f.Lp + 1, depth_sorted,
+                                       static_cast<uint32_t *>(c->iota.p), gap_sorted, (int64_t)G, 0, 8, st));
+    CU(launch_bucket_offsets(depth_sorted, G, bucket_off, st));
+    if (d_seg_offsets)
+        CU(cub::DeviceScan::InclusiveSum(c->cub_temp.p, t_scan, bflags, bound_rank, (int64_t)(n + 1), st));
+    CU(cudaMemsetAsync(head, 0, G, st));
+    CU(launch_head_flags(d_keys, depth_sorted, gap_sorted, bound_rank, bucket_off + 64, G, head, st));
+    CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, head, node_start, n_nodes_p, (int64_t)G, st));
+    CU(launch_level_ranges(node_start, n_nodes_p, bucket_off, level_lo, st));
+    // (depth, child-count class) of every node + histogram, still without knowing the node count on the host
+    ENSURE(node_key, G);
+    ENSURE(node_ids, G * 4);
+    uint8_t *nk = static_cast<uint8_t *>(c->node_key.p);
+    uint32_t *nids = static_cast<uint32_t *>(c->node_ids.p);
+    uint32_t *hist = small_u32(c) + SM_HIST;
+    CU(cudaMemsetAsync(hist, 0, 256 * 4, st));
+    CU(launch_node_class_keys(node_start, depth_sorted, n_nodes_p, G, nk, nids, hist, st));
+    c->launches += 9;
+    uint32_t *h_level = static_cast<uint32_t *>(c->pinned_small) + 64;
+    uint32_t *h_hist = static_cast<uint32_t *>(c->pinned_small) + 256;
+    CU(cudaMemcpyAsync(h_level, level_lo, 66 * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_hist, hist, 256 * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));  // the only host round trip of a build: 322 integers
+    const uint32_t B = h_level[65];
+    out.n_nodes = B;
+    f.gap_sorted = gap_sorted;
+    f.node_start = node_start;
+    if (B == 0) return B200_OK;  // every trie has at most one leaf
+
+    ENSURE(node_ref, (size_t)B * 32);
+    ENSURE(node_meta, B);
+    ENSURE(node_l, (size_t)B * 4);
+    ENSURE(node_r, (size_t)B * 4);
+    ENSURE(node_masks, (size_t)B * 8);
+    f.node_ref = static_cast<uint8_t *>(c->node_ref.p);
+    f.node_meta = static_cast<uint8_t *>(c->node_meta.p);
+    f.node_l = static_cast<uint32_t *>(c->node_l.p);
+    f.node_r = static_cast<uint32_t *>(c->node_r.p);
+    f.node_masks = static_cast<ushort4 *>(c->node_masks.p);
+
+    // ---- node visiting order: (depth descending, child-count class); ids stay what they are
+    ENSURE(node_key2, B);
+    ENSURE(node_order, (size_t)B * 4);
+    uint8_t *nk2 = static_cast<uint8_t *>(c->node_key2.p);
+    uint32_t *norder = static_cast<uint32_t *>(c->node_order.p);
+    size_t t_ns = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, t_ns, nk, nk2, nids, norder, (int64_t)B, 0, 8, st));
+    ENSURE(cub_temp, t_ns);
+    CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_ns, nk, nk2, nids, norder, (int64_t)B, 0, 8, st));
+    c->launches += 1;
+
+    // ---- deepest level first; the per-level frontier stays in HBM.  Big levels get one launch per child-count
+    // class (strip size and unrolling fit the class), small ones a single launch.
+    uint32_t pos = 0;
+    for (int d = 63; d >= 0; d--) {
+        const uint32_t *hc = h_hist + 4 * (63 - d);
+        uint32_t cnt = hc[0] + hc[1] + hc[2] + hc[3];
+        if (!cnt) continue;
+        out.levels++;
+        out.level_count[d] = cnt;
+        if (cnt <= WARP_LEVEL_MAX) {  // about one wave of warps: latency-bound, one warp per node
+            CU(launch_branch_level(f, norder, pos, pos + cnt, d, -1, st));
+            c->launches++;
+            pos += cnt;
+        } else {
+            for (int cls = 0; cls < 4; cls++) {
+                if (!hc[cls]) continue;
+                // a sparsely populated class of a big level is latency-bound too: one warp per node
+                CU(launch_branch_level(f, norder, pos, pos + hc[cls], d, hc[cls] <= WARP_LEVEL_MAX / 4 ? -1 : cls, st));
+                c->launches++;
+                pos += hc[cls];
+            }
+        }
+    }
+    if (pos != B) return fail(c, B200_ERR_CUDA, "internal: level histogram (%u) != node count (%u)", pos, B);
+    return B200_OK;
+}

@@ -1,0 +1,152 @@
+// eng_updates.inl — TrieUpdates collection (stored BranchNodeCompact records) into page-locked host memory.
+// Part of the single translation unit engine.cu (textually included, in this order).
+
+// ------------------------------------------------------------------------------------------------ updates
+struct UpdatesOwner {
+    void *host = nullptr;  // one page-locked block holding every array
+};
+
+extern "C" B200_API void b200_updates_release(b200_updates *u) {
+    if (!u) return;
+    if (u->_owner) {
+        UpdatesOwner *o = static_cast<UpdatesOwner *>(u->_owner);
+        if (o->host) cudaFreeHost(o->host);
+        delete o;
+    }
+    memset(u, 0, sizeof *u);
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Gathers the records of `n_stored` stored nodes (ids on the device) into `u` (host, page-locked).
+static int32_t gather_and_copy(b200_ctx *c, const ForestDev &f, const uint32_t *d_stored_ids, uint32_t n_stored,
+                               uint32_t n_hashes, const uint32_t *d_prefix_by_node, const uint32_t *d_prefix_by_record,
+                               const uint64_t *d_seg_offsets, uint64_t n_segs, b200_updates *u, UpdatesOwner *owner) {
+    cudaStream_t st = c->stream;
+    // one device block + one pinned host block, same layout
+    size_t o_tid = 0;
+    size_t o_plen = align_up(o_tid + (size_t)n_stored * 4, 16);
+    size_t o_path = align_up(o_plen + n_stored, 16);
+    size_t o_sm = align_up(o_path + (size_t)n_stored * 32, 16);
+    size_t o_tm = align_up(o_sm + (size_t)n_stored * 2, 16);
+    size_t o_hm = align_up(o_tm + (size_t)n_stored * 2, 16);
+    size_t o_ho32 = align_up(o_hm + (size_t)n_stored * 2, 16);
+    size_t o_hash = align_up(o_ho32 + (size_t)n_stored * 4, 16);
+    size_t o_ho64 = align_up(o_hash + (size_t)n_hashes * 32, 16);
+    size_t dev_total = o_ho64;
+    size_t host_total = o_ho64 + ((size_t)n_stored + 1) * 8;
+    CU(cudaMallocHost(&owner->host, host_total ? host_total : 16));
+    uint8_t *h = static_cast<uint8_t *>(owner->host);
+    u->n_nodes = n_stored;
+    u->trie_id = reinterpret_cast<uint32_t *>(h + o_tid);
+    u->path_len = h + o_plen;
+    u->path_packed = h + o_path;
+    u->state_mask = reinterpret_cast<uint16_t *>(h + o_sm);
+    u->tree_mask = reinterpret_cast<uint16_t *>(h + o_tm);
+    u->hash_mask = reinterpret_cast<uint16_t *>(h + o_hm);
+    u->hashes = h + o_hash;
+    u->hash_offset = reinterpret_cast<uint64_t *>(h + o_ho64);
+    if (n_stored) {
+        ENSURE(out_a, dev_total);
+        uint8_t *d = static_cast<uint8_t *>(c->out_a.p);
+        UpdatesDev ud;
+        ud.trie_id = reinterpret_cast<uint32_t *>(d + o_tid);
+        ud.path_len = d + o_plen;
+        ud.path_packed = d + o_path;
+        ud.state_mask = reinterpret_cast<uint16_t *>(d + o_sm);
+        ud.tree_mask = reinterpret_cast<uint16_t *>(d + o_tm);
+        ud.hash_mask = reinterpret_cast<uint16_t *>(d + o_hm);
+        ud.hash_offset = reinterpret_cast<uint32_t *>(d + o_ho32);
+        ud.hashes = d + o_hash;
+        CU(launch_gather_updates(f, d_stored_ids, n_stored, d_prefix_by_node, d_prefix_by_record, d_seg_offsets, n_segs,
+                                 ud, st));
+        c->launches++;
+        CU(cudaMemcpyAsync(h, d, dev_total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const uint32_t *ho32 = reinterpret_cast<const uint32_t *>(h + o_ho32);
+        for (uint32_t i = 0; i < n_stored; i++) u->hash_offset[i] = ho32[i];
+    }
+    u->hash_offset[n_stored] = n_hashes;
+    return B200_OK;
+}
+
+// Collects the stored BranchNodeCompact records of a finished build into `u` (host, page-locked).
+static int32_t collect_updates(b200_ctx *c, const Built &b, const uint64_t *d_seg_offsets, uint64_t n_segs,
+                               b200_updates *u) {
+    memset(u, 0, sizeof *u);
+    UpdatesOwner *owner = new UpdatesOwner();
+    u->_owner = owner;
+    cudaStream_t st = c->stream;
+    const uint32_t B = b.n_nodes;
+    uint32_t n_stored = 0, n_hashes = 0;
+    uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
+    if (B) {
+        ENSURE(upd_flags, B);
+        ENSURE(upd_nh, (size_t)B * 4);
+        ENSURE(upd_ids, (size_t)B * 4);
+        ENSURE(upd_prefix, (size_t)(B + 1) * 4);
+        uint8_t *flags = static_cast<uint8_t *>(c->upd_flags.p);
+        uint32_t *nh = static_cast<uint32_t *>(c->upd_nh.p);
+        uint32_t *ids = static_cast<uint32_t *>(c->upd_ids.p);
+        uint32_t *prefix = static_cast<uint32_t *>(c->upd_prefix.p);
+        uint32_t *n_stored_p = small_u32(c) + SM_NSTORED;
+        CU(launch_stored_flags(b.f, B, flags, nh, st));
+        size_t t_sel = 0, t_scan = 0;
+        thrust::counting_iterator<uint32_t> counting(0);
+        CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, flags, ids, n_stored_p, (int64_t)B, st));
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, t_scan, nh, prefix, (int64_t)B, st));
+        ENSURE(cub_temp, std::max(t_sel, t_scan));
+        CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, flags, ids, n_stored_p, (int64_t)B, st));
+        CU(cub::DeviceScan::ExclusiveSum(c->cub_temp.p, t_scan, nh, prefix, (int64_t)B, st));
+        c->launches += 3;
+        CU(cudaMemcpyAsync(ps + 200, n_stored_p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ps + 201, prefix + (B - 1), 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ps + 202, nh + (B - 1), 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        n_stored = ps[200];
+        n_hashes = ps[201] + ps[202];
+    }
+    return gather_and_copy(c, b.f, static_cast<uint32_t *>(c->upd_ids.p), n_stored, n_hashes,
+                           static_cast<uint32_t *>(c->upd_prefix.p), nullptr, d_seg_offsets, n_segs, u, owner);
+}
+
+// Same for a subset of nodes given by id (the dirty nodes of an incremental update), in list order.
+static int32_t collect_updates_subset(b200_ctx *c, const ForestDev &f, const uint32_t *d_ids, uint32_t count,
+                                      b200_updates *u) {
+    memset(u, 0, sizeof *u);
+    UpdatesOwner *owner = new UpdatesOwner();
+    u->_owner = owner;
+    cudaStream_t st = c->stream;
+    uint32_t n_stored = 0, n_hashes = 0;
+    uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
+    if (count) {
+        ENSURE(upd_flags, count);
+        ENSURE(upd_nh, (size_t)count * 4);
+        ENSURE(upd_ids, (size_t)count * 4 * 3);  // selected positions | picked ids | picked prefixes
+        ENSURE(upd_prefix, (size_t)(count + 1) * 4);
+        uint8_t *flags = static_cast<uint8_t *>(c->upd_flags.p);
+        uint32_t *nh = static_cast<uint32_t *>(c->upd_nh.p);
+        uint32_t *sel = static_cast<uint32_t *>(c->upd_ids.p), *pick_ids = sel + count, *pick_prefix = sel + 2 * (size_t)count;
+        uint32_t *prefix = static_cast<uint32_t *>(c->upd_prefix.p);
+        uint32_t *n_stored_p = small_u32(c) + SM_NSTORED;
+        CU(launch_stored_flags_subset(f, d_ids, count, flags, nh, st));
+        size_t t_sel = 0, t_scan = 0;
+        thrust::counting_iterator<uint32_t> counting(0);
+        CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, flags, sel, n_stored_p, (int64_t)count, st));
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, t_scan, nh, prefix, (int64_t)count, st));
+        ENSURE(cub_temp, std::max(t_sel, t_scan));
+        CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, flags, sel, n_stored_p, (int64_t)count, st));
+        CU(cub::DeviceScan::ExclusiveSum(c->cub_temp.p, t_scan, nh, prefix, (int64_t)count, st));
+        c->launches += 3;
+        CU(cudaMemcpyAsync(ps + 200, n_stored_p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ps + 201, prefix + (count - 1), 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ps + 202, nh + (count - 1), 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        n_stored = ps[200];
+        n_hashes = ps[201] + ps[202];
+        CU(launch_pick_subset(d_ids, prefix, sel, n_stored, pick_ids, pick_prefix, st));
+        c->launches++;
+        return gather_and_copy(c, f, pick_ids, n_stored, n_hashes, nullptr, pick_prefix, nullptr, 0, u, owner);
+    }
+    return gather_and_copy(c, f, nullptr, 0, 0, nullptr, nullptr, nullptr, 0, u, owner);
+}

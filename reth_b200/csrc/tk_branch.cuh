@@ -1,0 +1,249 @@
+// tk_branch.cuh — branch / extension encoding, the thread-per-node builder and the class-specialised branch kernel.
+// Part of the single translation unit trie_kernels.cu (included inside namespace b200, in this order: the later
+// files use the device functions of the earlier ones).
+
+// ------------------------------------------------------------------------------------------------ branches
+struct ChildInfo {
+    uint32_t id;    // < n: leaf, else n + node
+    uint32_t nib;
+    uint32_t meta;  // low 5 bits inline length (0 = hashed), META_EXT, META_STORED
+};
+
+__device__ __forceinline__ ChildInfo fetch_child(const ForestDev &f, uint32_t j0, uint32_t c) {
+    ChildInfo ci;
+    if (c == 0) {
+        uint32_t g = f.gap_sorted[j0];
+        ci.id = f.E[g - 1];
+        ci.nib = f.nibs[g] >> 4;
+    } else {
+        uint32_t g = f.gap_sorted[j0 + c - 1];
+        ci.id = f.S[g];
+        ci.nib = f.nibs[g] & 15;
+    }
+    ci.meta = ci.id < f.n ? f.leaf_meta[ci.id] : f.node_meta[ci.id - (uint32_t)f.n];
+    return ci;
+}
+
+// hex-prefix string of key nibbles [from, to) (extension flag), as an RLP string
+template <class W>
+__device__ __forceinline__ uint32_t put_ext_path(W &s, const uint8_t *key, uint32_t from, uint32_t to) {
+    uint32_t m = to - from;
+    uint32_t hp_len = 1 + (m >> 1);
+    uint32_t i = from;
+    uint32_t first = 0;
+    if (m & 1) {
+        first = 0x10u | key_nibble_mem(key, i);
+        i++;
+    }
+    if (hp_len > 1) s.byte(0x80 + hp_len);
+    s.byte(first);  // 0x00 or 0x1n: a lone byte < 0x80 is its own RLP
+    for (; i < to; i += 2) s.byte((key_nibble_mem(key, i) << 4) | key_nibble_mem(key, i + 1));
+    return hp_len == 1 ? 1 : 1 + hp_len;
+}
+
+// Builds branch node v (depth d) into the strip; returns RLP length and the node's masks / extent.
+template <int BLOCK>
+__device__ __forceinline__ uint32_t encode_branch(Strip<BLOCK> &s, const ForestDev &f, uint32_t j0, uint32_t k,
+                                                  uint32_t &state_mask, uint32_t &tree_mask, uint32_t &hash_mask,
+                                                  uint32_t &l, uint32_t &r) {
+    // pass 1: lengths and masks
+    uint32_t payload = 17;
+    state_mask = tree_mask = hash_mask = 0;
+    for (uint32_t c = 0; c <= k; c++) {
+        ChildInfo ci = fetch_child(f, j0, c);
+        uint32_t clen = (ci.meta & META_LEN) ? (ci.meta & META_LEN) : 33;
+        payload += clen - 1;
+        uint32_t bit = 1u << ci.nib;
+        state_mask |= bit;
+        if (ci.id >= f.n) {
+            if (!(ci.meta & META_EXT)) {
+                hash_mask |= bit;
+                if ((ci.meta & META_LEN) && f.retain_updates) atomicExch(f.err, B200_DEVERR_INLINE_HASH_CHILD);
+            }
+            if (ci.meta & META_STORED) tree_mask |= bit;
+        }
+        if (c == 0) l = ci.id < f.n ? ci.id : f.node_l[ci.id - (uint32_t)f.n];
+        if (c == k) r = ci.id < f.n ? ci.id : f.node_r[ci.id - (uint32_t)f.n];
+    }
+    // pass 2: bytes
+    put_list_header(s, payload);
+    uint32_t cur = 0;
+    for (uint32_t c = 0; c <= k; c++) {
+        ChildInfo ci = fetch_child(f, j0, c);
+        for (; cur < ci.nib; cur++) s.byte(0x80);
+        const uint8_t *rp = ci.id < f.n ? f.leaf_ref + 32 * (uint64_t)ci.id
+                                        : f.node_ref + 32 * (uint64_t)(ci.id - (uint32_t)f.n);
+        uint32_t ref[8];
+        load32_nc(rp, ref);
+        uint32_t clen = ci.meta & META_LEN;
+        if (clen == 0) {
+            s.byte(0xa0);
+            s.words8(ref);
+        } else {
+            for (uint32_t b = 0; b < clen; b++) s.byte(byte_at(ref, b));
+        }
+        cur++;
+    }
+    for (; cur < 16; cur++) s.byte(0x80);
+    s.byte(0x80);  // value slot
+    return list_header_len(payload) + payload;
+}
+
+// Wraps `child` (ref words + inline length, 0 = hashed) into an extension over key nibbles [from,to).
+template <class W>
+__device__ __forceinline__ uint32_t encode_extension(W &s, const uint8_t *key, uint32_t from, uint32_t to,
+                                                     const uint32_t (&child)[8], uint32_t child_inline_len) {
+    uint32_t m = to - from;
+    uint32_t hp_len = 1 + (m >> 1);
+    uint32_t path_str = hp_len == 1 ? 1 : 1 + hp_len;
+    uint32_t clen = child_inline_len ? child_inline_len : 33;
+    uint32_t payload = path_str + clen;
+    put_list_header(s, payload);
+    put_ext_path(s, key, from, to);
+    if (child_inline_len == 0) {
+        s.byte(0xa0);
+        s.words8(child);
+    } else {
+        for (uint32_t b = 0; b < child_inline_len; b++) s.byte(byte_at(child, b));
+    }
+    return list_header_len(payload) + payload;
+}
+
+// Class-specialised variant of encode_branch: at most MAXC children, every per-child quantity lives in registers
+// and all the dependent global loads of a phase (gap -> S/E -> meta -> ref) are issued back to back for the
+// whole node before any of them is consumed, so one thread keeps up to MAXC requests in flight.
+template <int BLOCK, int MAXC, bool COHERENT = false>
+__device__ __forceinline__ uint32_t encode_branch_u(Strip<BLOCK> &s, const ForestDev &f, uint32_t j0, uint32_t k,
+                                                    uint32_t &state_mask, uint32_t &tree_mask, uint32_t &hash_mask,
+                                                    uint32_t &l, uint32_t &r) {
+    const uint32_t n = (uint32_t)f.n;
+    uint32_t g[MAXC - 1];
+#pragma unroll
+    for (int c = 0; c < MAXC - 1; c++) g[c] = (uint32_t)c < k ? f.gap_sorted[j0 + c] : 0u;
+    uint32_t id[MAXC], nm[MAXC];  // nm = nibble | meta << 8
+    id[0] = f.E[g[0] - 1];
+    nm[0] = f.nibs[g[0]] >> 4;
+#pragma unroll
+    for (int c = 1; c < MAXC; c++) {
+        id[c] = 0;
+        nm[c] = 0;
+        if ((uint32_t)c <= k) {
+            id[c] = f.S[g[c - 1]];
+            nm[c] = f.nibs[g[c - 1]] & 15;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; c++)
+        if ((uint32_t)c <= k) {
+            const uint8_t *mp = id[c] < n ? f.leaf_meta + id[c] : f.node_meta + (id[c] - n);
+            nm[c] |= (uint32_t)(COHERENT ? __ldcg(mp) : *mp) << 8;
+        }
+    uint32_t payload = 17;
+    state_mask = tree_mask = hash_mask = 0;
+    uint32_t last = id[0];
+#pragma unroll
+    for (int c = 0; c < MAXC; c++) {
+        if ((uint32_t)c <= k) {
+            uint32_t meta = nm[c] >> 8;
+            payload += ((meta & META_LEN) ? (meta & META_LEN) : 33u) - 1;
+            uint32_t bit = 1u << (nm[c] & 15);
+            state_mask |= bit;
+            if (id[c] >= n) {
+                if (!(meta & META_EXT)) {
+                    hash_mask |= bit;
+                    if ((meta & META_LEN) && f.retain_updates) atomicExch(f.err, B200_DEVERR_INLINE_HASH_CHILD);
+                }
+                if (meta & META_STORED) tree_mask |= bit;
+            }
+            last = id[c];
+        }
+    }
+    l = id[0] < n ? id[0] : f.node_l[id[0] - n];
+    r = last < n ? last : f.node_r[last - n];
+    put_list_header(s, payload);
+    uint32_t cur = 0;
+#pragma unroll
+    for (int c = 0; c < MAXC; c++) {
+        if ((uint32_t)c <= k) {
+            const uint8_t *rp = id[c] < n ? f.leaf_ref + 32 * (uint64_t)id[c] : f.node_ref + 32 * (uint64_t)(id[c] - n);
+            uint32_t ref[8];
+            if (COHERENT) {
+                const uint4 *q = reinterpret_cast<const uint4 *>(rp);
+                uint4 x = __ldcg(q), y = __ldcg(q + 1);
+                ref[0] = x.x; ref[1] = x.y; ref[2] = x.z; ref[3] = x.w;
+                ref[4] = y.x; ref[5] = y.y; ref[6] = y.z; ref[7] = y.w;
+            } else {
+                load32_nc(rp, ref);
+            }
+            uint32_t nibble = nm[c] & 15;
+            s.fill80(nibble - cur);
+            cur = nibble;
+            uint32_t clen = (nm[c] >> 8) & META_LEN;
+            if (clen == 0) {
+                s.byte(0xa0);
+                s.words8(ref);
+            } else {
+                for (uint32_t b = 0; b < clen; b++) s.byte(byte_at(ref, b));
+            }
+            cur++;
+        }
+    }
+    s.fill80(16 - cur + 1);  // trailing empty slots + the value slot
+    return list_header_len(payload) + payload;
+}
+
+// One thread builds branch node v of depth d into its strip, hashes it and publishes it (node arrays, S/E).
+template <int BLOCK, int MAXC, bool COHERENT>
+__device__ __forceinline__ void thread_build_node(Strip<BLOCK> &s, uint32_t *smem, const ForestDev &f, uint32_t v, int d,
+                                                  uint32_t &hashed, uint32_t &exts, uint32_t (&ref)[8]) {
+    s.init(smem);
+    uint32_t j0 = f.node_start[v], k = f.node_start[v + 1] - j0;
+    if (k + 1 > (uint32_t)MAXC) k = MAXC - 1;  // cannot happen for well-formed input; keeps the strip in bounds
+    uint32_t state_mask, tree_mask, hash_mask, l, r;
+    uint32_t len = encode_branch_u<BLOCK, MAXC, COHERENT>(s, f, j0, k, state_mask, tree_mask, hash_mask, l, r);
+    int pdl = depth_of(f.Lp[l]), pdr = depth_of(f.Lp[(uint64_t)r + 1]);
+    int pd = pdl > pdr ? pdl : pdr;
+    bool is_root = pd < 0;
+    bool need_ext = pd + 1 < d;
+    uint32_t meta = strip_to_ref(s, len, is_root && !need_ext, ref, hashed);
+    if (need_ext) {
+        s.reset();
+        uint32_t elen = encode_extension(s, f.keys + 32 * (uint64_t)l, (uint32_t)(pd + 1), (uint32_t)d, ref, meta);
+        meta = strip_to_ref(s, elen, is_root, ref, hashed) | META_EXT;
+        exts++;
+    }
+    bool stored = (tree_mask | hash_mask) != 0;
+    if (stored) meta |= META_STORED;
+    store32(f.node_ref + 32 * (uint64_t)v, ref);
+    f.node_meta[v] = (uint8_t)meta;
+    f.node_l[v] = l;
+    f.node_r[v] = r;
+    f.node_masks[v] = make_ushort4((unsigned short)state_mask, (unsigned short)tree_mask, (unsigned short)hash_mask,
+                                   (unsigned short)d);
+    f.S[l] = (uint32_t)f.n + v;
+    f.E[r] = (uint32_t)f.n + v;
+}
+
+// One thread per branch node of depth d.  MAXC bounds the children of every node in [pos_lo, pos_hi) (the level's
+// nodes are grouped by child-count class); the strip is sized for that class, which is what sets the occupancy.
+template <int BLOCK, int MAXC>
+__global__ void __launch_bounds__(BLOCK) branch_kernel(ForestDev f, const uint32_t *__restrict__ node_order,
+                                                       uint32_t pos_lo, uint32_t pos_hi, int d) {
+    extern __shared__ uint32_t smem[];
+    if (*(volatile int *)f.err != B200_DEVERR_NONE) return;  // malformed input: the structure arrays are not trustworthy
+    Strip<BLOCK> s;
+    uint32_t hashed = 0, exts = 0;
+    const uint32_t step = gridDim.x * BLOCK;
+    for (uint64_t p64 = (uint64_t)pos_lo + blockIdx.x * BLOCK + threadIdx.x; p64 < pos_hi; p64 += step) {
+        uint32_t ref[8];
+        thread_build_node<BLOCK, MAXC, false>(s, smem, f, __ldg(node_order + p64), d, hashed, exts, ref);
+    }
+    for (int o = 16; o; o >>= 1) {
+        hashed += __shfl_xor_sync(0xffffffffu, hashed, o);
+        exts += __shfl_xor_sync(0xffffffffu, exts, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (hashed) atomicAdd(&f.counters[CNT_HASHED], (unsigned long long)hashed);
+        if (exts) atomicAdd(&f.counters[CNT_EXT], (unsigned long long)exts);
+    }
+}
