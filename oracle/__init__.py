@@ -27,7 +27,8 @@ EMPTY_ROOT_HASH = bytes.fromhex("56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc
 
 def build(force: bool = False) -> str:
     """Compile liboracle.so with gcc (oracle/Makefile)."""
-    srcs = [os.path.join(_HERE, f) for f in ("keccak.c", "hash_builder.c", "state_root.c", "oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("keccak.c", "keccak_avx512.c", "hash_builder.c", "state_root.c", "oracle.h",
+                                             "Makefile")]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
     )
@@ -81,6 +82,8 @@ def lib():
         L.orc_keccak256.argtypes = [u8p, C.c_size_t, u8p]
         L.orc_keccak256_fixed.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint64, u8p, C.c_int]
         L.orc_keccak256_var.argtypes = [u8p, u64p, C.c_uint64, u8p, C.c_int]
+        L.orc_keccak256_fixed_simd.restype = C.c_int
+        L.orc_keccak256_fixed_simd.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint64, u8p, C.c_int]
         L.orc_hb_new.restype = vp
         L.orc_hb_new.argtypes = [C.c_int]
         L.orc_hb_free.argtypes = [vp]
@@ -134,6 +137,15 @@ def keccak256_fixed(msgs: np.ndarray, msg_len: int | None = None, threads: int =
     out = np.empty((n, 32), np.uint8)
     lib().orc_keccak256_fixed(_p(msgs), msg_len or stride, stride, n, _p(out), threads)
     return out
+
+
+def keccak256_fixed_simd(msgs: np.ndarray, msg_len: int | None = None, threads: int = 1):
+    """8-way AVX-512 multi-buffer variant (best-effort CPU figure); None when the CPU lacks AVX-512F."""
+    msgs = _c(msgs)
+    n, stride = msgs.shape
+    out = np.empty((n, 32), np.uint8)
+    ok = lib().orc_keccak256_fixed_simd(_p(msgs), msg_len or stride, stride, n, _p(out), threads)
+    return out if ok else None
 
 
 def keccak256_var(data: np.ndarray, offsets: np.ndarray, threads: int = 1) -> np.ndarray:

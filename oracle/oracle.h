@@ -40,6 +40,10 @@ void orc_keccak256_fixed(const uint8_t *in, uint32_t msg_len, uint32_t stride, u
                          uint8_t *out32, int threads);
 void orc_keccak256_var(const uint8_t *data, const uint64_t *offsets, uint64_t n, uint8_t *out32,
                        int threads);
+/* Best-effort SIMD figure for the CPU baseline: 8-way AVX-512 multi-buffer Keccak, msg_len <= 135.
+ * Returns 1 if it ran, 0 if the CPU lacks AVX-512F (nothing written). reth itself hashes one key at a time. */
+int orc_keccak256_fixed_simd(const uint8_t *in, uint32_t msg_len, uint32_t stride, uint64_t n, uint8_t *out32,
+                             int threads);
 
 /* ---------------------------------------------------------------- HashBuilder (alloy-trie restatement) */
 typedef struct orc_hb orc_hb;

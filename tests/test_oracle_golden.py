@@ -334,3 +334,16 @@ def test_storage_root_regression_against_second_impl():
     keys = np.frombuffer(b"".join(H(k) for k, _ in st), np.uint8).reshape(-1, 32)
     roots = oracle.storage_roots(keys, u256_be([v for _, v in st]), [0, 4])
     assert roots[0].tobytes() == oracle.trie_root_recursive(keys, [oracle.encode_u256(v) for _, v in st])
+
+
+def test_simd_keccak_matches_scalar():
+    """The 8-way AVX-512 multi-buffer variant used for the best-effort CPU baseline agrees with the scalar oracle."""
+    from tests.util import random_keys
+    if oracle.keccak256_fixed_simd(random_keys(1, 8)) is None:
+        pytest.skip("CPU without AVX-512F")
+    for msg_len, stride in [(32, 32), (20, 20), (20, 32), (1, 4), (135, 136), (64, 80)]:
+        n = 1003
+        msgs = random_keys(msg_len, (n * stride + 31) // 32).reshape(-1)[: n * stride].reshape(n, stride)
+        assert (oracle.keccak256_fixed_simd(msgs, msg_len, threads=3) == oracle.keccak256_fixed(msgs, msg_len)).all()
+    zero_addr = oracle.keccak256_fixed_simd(np.zeros((1, 20), np.uint8))[0].tobytes()
+    assert zero_addr == H("5380c7b7ae81a58eb98d9c78de4a1fd7fd9535fc953ed2be602daaa41767312a")
