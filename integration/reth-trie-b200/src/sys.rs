@@ -1,0 +1,78 @@
+//! Raw bindings of include/b200trie.h (hand-written; `bindgen` over the header gives the same).
+//! UNCOMPILED SKETCH — see Cargo.toml.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_void};
+
+#[repr(C)]
+pub struct b200_ctx {
+    _p: [u8; 0],
+}
+#[repr(C)]
+pub struct b200_trie {
+    _p: [u8; 0],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct b200_account {
+    pub nonce: u64,
+    pub balance_be: [u8; 32],
+    pub code_hash: [u8; 32],
+}
+
+#[repr(C)]
+pub struct b200_updates {
+    pub n_nodes: u64,
+    pub trie_id: *mut u32,
+    pub path_len: *mut u8,
+    pub path_packed: *mut u8,
+    pub state_mask: *mut u16,
+    pub tree_mask: *mut u16,
+    pub hash_mask: *mut u16,
+    pub hash_offset: *mut u64,
+    pub hashes: *mut u8,
+    pub _owner: *mut c_void,
+}
+
+#[repr(C)]
+#[derive(Default, Clone, Copy)]
+pub struct b200_stats {
+    pub leaves_added: u64,
+    pub branches_added: u64,
+    pub extension_nodes: u64,
+    pub hashed_nodes: u64,
+    pub levels: u64,
+    pub device_ms: f64,
+}
+
+pub const B200_OK: i32 = 0;
+pub const B200_ERR_NOT_FOUND: i32 = -8;
+
+#[link(name = "b200trie")]
+unsafe extern "C" {
+    pub fn b200_create(device_ordinal: i32) -> *mut b200_ctx;
+    pub fn b200_create_status() -> i32;
+    pub fn b200_destroy(ctx: *mut b200_ctx);
+    pub fn b200_last_error(ctx: *const b200_ctx) -> *const c_char;
+
+    pub fn b200_keccak256_fixed(ctx: *mut b200_ctx, input: *const u8, msg_len: u32, stride: u32, n: u64, out32: *mut u8) -> i32;
+    pub fn b200_hash_sort_keys(ctx: *mut b200_ctx, input: *const u8, msg_len: u32, stride: u32, n: u64,
+                               out_sorted32: *mut u8, out_perm: *mut u32) -> i32;
+    pub fn b200_hash_sort_storage(ctx: *mut b200_ctx, addresses20: *const u8, n_addr: u32, addr_index: *const u32,
+                                  slots32: *const u8, n: u64, out_sorted64: *mut u8, out_perm: *mut u32) -> i32;
+
+    pub fn b200_storage_roots(ctx: *mut b200_ctx, slot_keys32: *const u8, values32_be: *const u8, seg_offsets: *const u64,
+                              n_accounts: u64, roots32: *mut u8, updates: *mut b200_updates, stats: *mut b200_stats) -> i32;
+    pub fn b200_state_root_full(ctx: *mut b200_ctx, acct_keys32: *const u8, accts: *const b200_account, n_accounts: u64,
+                                slot_keys32: *const u8, values32_be: *const u8, seg_offsets: *const u64, root32: *mut u8,
+                                account_updates: *mut b200_updates, storage_updates: *mut b200_updates,
+                                stats: *mut b200_stats) -> i32;
+    pub fn b200_updates_release(u: *mut b200_updates);
+
+    pub fn b200_trie_create(ctx: *mut b200_ctx, acct_keys32: *const u8, accts: *const b200_account,
+                            storage_roots32: *const u8, n: u64, out: *mut *mut b200_trie, root32: *mut u8) -> i32;
+    pub fn b200_trie_apply(trie: *mut b200_trie, keys32: *const u8, accts: *const b200_account, present: *const u8,
+                           storage_roots32: *const u8, m: u64, root32: *mut u8, out_rebuilt: *mut i32,
+                           updates: *mut b200_updates, stats: *mut b200_stats) -> i32;
+    pub fn b200_trie_destroy(trie: *mut b200_trie);
+}
