@@ -129,6 +129,37 @@ typedef struct {
 } b200_updates;
 B200_API void b200_updates_release(b200_updates *);
 
+/* ------------------------------------------------------------------------------------------------ table rows
+ * Byte-exact rows of reth's trie tables from a b200_updates, in MDBX key order, ready for a cursor append /
+ * upsert loop (write_trie_updates_sorted, crates/storage/provider/src/providers/database/provider.rs:3125-3160;
+ * DatabaseStorageTrieCursor::write_storage_trie_updates_sorted, crates/trie/db/src/trie_cursor.rs:280-312).
+ * Host-only (no device work).  Row r occupies bytes[row_offset[r] .. row_offset[r+1]): the first key_len[r]
+ * bytes are the table key, the rest is the value.
+ *   AccountsTrie (crates/storage/db-api/src/tables/mod.rs:484-487): key = StoredNibbles (LEGACY: one nibble per
+ *     byte, crates/trie/common/src/nibbles.rs:27-66) or PackedStoredNibbles (PACKED: 32 packed bytes + nibble
+ *     count, nibbles.rs:143-213); value = BranchNodeCompact Compact (three big-endian u16 masks, then hashes).
+ *   StoragesTrie (tables/mod.rs:490-494, dup-sorted): key = hashed address = acct_keys32[trie_id]; value =
+ *     StorageTrieEntry = StoredNibblesSubKey (65 B) or PackedStoredNibblesSubKey (33 B) followed by the node
+ *     (crates/trie/common/src/storage.rs:24-44,70-86).
+ * Deleted storage tries (StorageTrieUpdates::deleted) have no rows; the caller clears those duplicates. */
+typedef enum {
+    B200_KEYS_LEGACY = 0, /* StoredNibbles / StoredNibblesSubKey */
+    B200_KEYS_PACKED = 1  /* storage v2: PackedStoredNibbles / PackedStoredNibblesSubKey */
+} b200_key_format;
+
+typedef struct {
+    uint64_t n_rows;
+    uint64_t *row_offset; /* [n_rows+1] into bytes */
+    uint32_t *key_len;    /* [n_rows] */
+    uint8_t *bytes;
+    void *_owner;
+} b200_rows;
+
+B200_API int32_t b200_account_trie_rows(const b200_updates *account_updates, int32_t key_format, b200_rows *out);
+B200_API int32_t b200_storage_trie_rows(const b200_updates *storage_updates, const uint8_t *acct_keys32,
+                                        uint64_t n_accounts, int32_t key_format, b200_rows *out);
+B200_API void b200_rows_release(b200_rows *);
+
 /* TrieStats / TrieRootMetrics (crates/trie/trie/src/stats.rs, metrics.rs:22-40) plus device timing. */
 typedef struct {
     uint64_t leaves_added;

@@ -45,6 +45,17 @@ pub struct b200_stats {
     pub device_ms: f64,
 }
 
+#[repr(C)]
+pub struct b200_rows {
+    pub n_rows: u64,
+    pub row_offset: *mut u64,
+    pub key_len: *mut u32,
+    pub bytes: *mut u8,
+    pub _owner: *mut c_void,
+}
+pub const B200_KEYS_LEGACY: i32 = 0;
+pub const B200_KEYS_PACKED: i32 = 1;
+
 pub const B200_OK: i32 = 0;
 pub const B200_ERR_NOT_FOUND: i32 = -8;
 
@@ -68,6 +79,10 @@ unsafe extern "C" {
                                 account_updates: *mut b200_updates, storage_updates: *mut b200_updates,
                                 stats: *mut b200_stats) -> i32;
     pub fn b200_updates_release(u: *mut b200_updates);
+    pub fn b200_account_trie_rows(account_updates: *const b200_updates, key_format: i32, out: *mut b200_rows) -> i32;
+    pub fn b200_storage_trie_rows(storage_updates: *const b200_updates, acct_keys32: *const u8, n_accounts: u64,
+                                  key_format: i32, out: *mut b200_rows) -> i32;
+    pub fn b200_rows_release(rows: *mut b200_rows);
 
     pub fn b200_trie_create(ctx: *mut b200_ctx, acct_keys32: *const u8, accts: *const b200_account,
                             storage_roots32: *const u8, n: u64, out: *mut *mut b200_trie, root32: *mut u8) -> i32;

@@ -37,6 +37,17 @@ class Updates(C.Structure):
     ]
 
 
+class Rows(C.Structure):
+    """b200_rows (include/b200trie.h): table rows in MDBX key order."""
+    _fields_ = [
+        ("n_rows", C.c_uint64),
+        ("row_offset", C.POINTER(C.c_uint64)),
+        ("key_len", C.POINTER(C.c_uint32)),
+        ("bytes", C.POINTER(C.c_uint8)),
+        ("_owner", C.c_void_p),
+    ]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("leaves_added", C.c_uint64),
@@ -104,6 +115,9 @@ def load():
     sig("b200_sort_keys32_dev", i32, vp, vp, u64, vp, vp)
     sig("b200_hash_sort_storage", i32, vp, vp, u32, vp, vp, u64, vp, vp)
     sig("b200_updates_release", None, PU)
+    sig("b200_account_trie_rows", i32, PU, i32, C.POINTER(Rows))
+    sig("b200_storage_trie_rows", i32, PU, vp, u64, i32, C.POINTER(Rows))
+    sig("b200_rows_release", None, C.POINTER(Rows))
     sig("b200_storage_roots", i32, vp, vp, vp, vp, u64, vp, PU, PS)
     sig("b200_state_root", i32, vp, vp, vp, vp, u64, vp, PU, PS)
     sig("b200_state_root_full", i32, vp, vp, vp, u64, vp, vp, vp, vp, PU, PU, PS)

@@ -229,6 +229,30 @@ class Engine:
             res.append(s.as_dict())
         return res[0] if len(res) == 1 else tuple(res)
 
+    def state_root_full_rows(self, acct_keys, accounts, slot_keys, values, seg_offsets, key_format: int = 0):
+        """state_root_full, with the stored nodes returned as AccountsTrie / StoragesTrie table rows in MDBX key
+        order (reth_b200.tables.TableRows; key_format 0 = legacy nibble keys, 1 = storage-v2 packed keys) — what
+        MerkleStage hands to write_trie_updates_sorted (crates/stages/stages/src/stages/merkle.rs:184-366)."""
+        from . import tables
+        acct_keys = _np(acct_keys).reshape(-1, 32)
+        accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
+        slot_keys = _np(slot_keys).reshape(-1, 32)
+        values = _np(values).reshape(-1, 32)
+        seg_offsets = _np(seg_offsets, np.uint64)
+        if len(seg_offsets) != len(acct_keys) + 1:
+            raise ValueError("seg_offsets must have n_accounts+1 entries")
+        root = np.empty(32, np.uint8)
+        ua, us, s = Updates(), Updates(), Stats()
+        self._check(self.lib.b200_state_root_full(
+            self.ctx, _ptr(acct_keys), _ptr(accounts), len(acct_keys), _ptr(slot_keys), _ptr(values),
+            _ptr(seg_offsets), _ptr(root), C.byref(ua), C.byref(us), C.byref(s)))
+        try:
+            arows, srows = tables.rows_from_updates(ua, us, acct_keys, key_format)
+        finally:
+            self.lib.b200_updates_release(C.byref(ua))
+            self.lib.b200_updates_release(C.byref(us))
+        return root.tobytes(), arows, srows
+
     def subtrie_frontier(self, acct_keys, accounts, slot_keys, values, seg_offsets) -> np.ndarray:
         """This rank's 16-entry frontier as uint8[16, 68] (b200_frontier_entry records)."""
         acct_keys = _np(acct_keys).reshape(-1, 32)

@@ -348,6 +348,87 @@ inline std::pair<Nibbles, BranchNodeCompact> branch_node(const b200_updates &u, 
 }
 }  // namespace detail
 
+// ---------------------------------------------------------------------------------------------- table rows
+/// One row of AccountsTrie / StoragesTrie (crates/storage/db-api/src/tables/mod.rs:484-494,542-572), byte-exact.
+struct TableRow {
+    std::vector<uint8_t> key, value;
+    bool operator==(const TableRow &o) const { return key == o.key && value == o.value; }
+};
+
+namespace detail {
+/// std::map<Nibbles, BranchNodeCompact> (+ trie ids) flattened into a b200_updates view.
+struct FlatUpdates {
+    std::vector<uint32_t> trie_id;
+    std::vector<uint8_t> path_len, path_packed, hashes;
+    std::vector<uint16_t> state, tree, hash;
+    std::vector<uint64_t> hash_offset{0};
+    void push(uint32_t id, const Nibbles &path, const BranchNodeCompact &n) {
+        trie_id.push_back(id);
+        path_len.push_back((uint8_t)path.size());
+        size_t base = path_packed.size();
+        path_packed.resize(base + 32, 0);
+        for (size_t j = 0; j < path.size(); j++) path_packed[base + (j >> 1)] |= (j & 1) ? path[j] : (uint8_t)(path[j] << 4);
+        state.push_back(n.state_mask);
+        tree.push_back(n.tree_mask);
+        hash.push_back(n.hash_mask);
+        for (auto &h : n.hashes) hashes.insert(hashes.end(), h.begin(), h.end());
+        hash_offset.push_back(hash_offset.back() + n.hashes.size());
+    }
+    b200_updates view() {
+        b200_updates u{};
+        u.n_nodes = trie_id.size();
+        u.trie_id = trie_id.data();
+        u.path_len = path_len.data();
+        u.path_packed = path_packed.data();
+        u.state_mask = state.data();
+        u.tree_mask = tree.data();
+        u.hash_mask = hash.data();
+        u.hash_offset = hash_offset.data();
+        u.hashes = hashes.data();
+        return u;
+    }
+};
+inline std::vector<TableRow> take_rows(b200_rows &r) {
+    std::vector<TableRow> out(r.n_rows);
+    for (uint64_t i = 0; i < r.n_rows; i++) {
+        const uint8_t *p = r.bytes + r.row_offset[i], *e = r.bytes + r.row_offset[i + 1];
+        out[i].key.assign(p, p + r.key_len[i]);
+        out[i].value.assign(p + r.key_len[i], e);
+    }
+    b200_rows_release(&r);
+    return out;
+}
+inline void check_rows(int32_t rc, const char *what) {
+    if (rc != B200_OK) throw B200Error(rc, what);
+}
+}  // namespace detail
+
+/// Rows `write_trie_updates_sorted` puts into AccountsTrie (provider.rs:3125-3160), in key order.
+inline std::vector<TableRow> account_trie_rows(const TrieUpdates &u, b200_key_format fmt = B200_KEYS_LEGACY) {
+    detail::FlatUpdates f;
+    for (auto &kv : u.account_nodes) f.push(0, kv.first, kv.second);
+    b200_updates view = f.view();
+    b200_rows rows{};
+    detail::check_rows(b200_account_trie_rows(&view, fmt, &rows), "b200_account_trie_rows");
+    return detail::take_rows(rows);
+}
+/// Rows of StoragesTrie for every storage trie with nodes (trie_cursor.rs:280-312), by hashed address then subkey.
+/// Tries with `is_deleted` carry no rows of their own: the writer clears their duplicates first (`:285-287`).
+inline std::vector<TableRow> storage_trie_rows(const TrieUpdates &u, b200_key_format fmt = B200_KEYS_LEGACY) {
+    detail::FlatUpdates f;
+    std::vector<uint8_t> addrs;
+    uint32_t id = 0;
+    for (auto &kv : u.storage_tries) {
+        addrs.insert(addrs.end(), kv.first.begin(), kv.first.end());
+        for (auto &n : kv.second.storage_nodes) f.push(id, n.first, n.second);
+        id++;
+    }
+    b200_updates view = f.view();
+    b200_rows rows{};
+    detail::check_rows(b200_storage_trie_rows(&view, addrs.data(), id, fmt, &rows), "b200_storage_trie_rows");
+    return detail::take_rows(rows);
+}
+
 /// crates/trie/trie/src/progress.rs:12-21 — a device build never pauses: always Complete.
 struct StateRootProgress {
     B256 root;

@@ -1,0 +1,146 @@
+"""Rows of reth's trie tables from the engine's stored-node records.
+
+`account_trie_rows` / `storage_trie_rows` return `[(key_bytes, value_bytes)]` in MDBX key order, byte for byte what
+`write_trie_updates_sorted` (crates/storage/provider/src/providers/database/provider.rs:3125-3160) puts into
+`AccountsTrie` / `StoragesTrie` (crates/storage/db-api/src/tables/mod.rs:484-494; storage v2 views :542-572).
+The encoding itself is done by the C ABI (b200_account_trie_rows / b200_storage_trie_rows, host-only code in
+csrc/table_rows.cu); this module marshals records into a `b200_updates` and slices the result.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import B200Error, Rows, Updates
+
+KEYS_LEGACY = 0  # StoredNibbles / StoredNibblesSubKey (crates/trie/common/src/nibbles.rs:27-141)
+KEYS_PACKED = 1  # PackedStoredNibbles / PackedStoredNibblesSubKey (nibbles.rs:143-300)
+
+
+def _pack(path: bytes) -> bytes:
+    out = bytearray(32)
+    for i, nib in enumerate(path):
+        out[i >> 1] |= (nib << 4) if not (i & 1) else nib
+    return bytes(out)
+
+
+class _Marshalled:
+    """A b200_updates view over numpy arrays built from records `(trie_id, path_nibbles, state, tree, hash, [hashes])`."""
+
+    def __init__(self, records):
+        n = len(records)
+        self.trie_id = np.array([r[0] for r in records], dtype=np.uint32).reshape(n)
+        self.path_len = np.array([len(r[1]) for r in records], dtype=np.uint8).reshape(n)
+        self.path_packed = np.frombuffer(b"".join(_pack(r[1]) for r in records) or b"\0", dtype=np.uint8).copy()
+        self.state = np.array([r[2] for r in records], dtype=np.uint16).reshape(n)
+        self.tree = np.array([r[3] for r in records], dtype=np.uint16).reshape(n)
+        self.hash = np.array([r[4] for r in records], dtype=np.uint16).reshape(n)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        for i, r in enumerate(records):
+            offs[i + 1] = offs[i] + len(r[5])
+        self.offs = offs
+        self.hashes = np.frombuffer(b"".join(h for r in records for h in r[5]) or b"\0", dtype=np.uint8).copy()
+        u = Updates()
+        u.n_nodes = n
+        cast = lambda a, t: C.cast(a.ctypes.data, C.POINTER(t))
+        u.trie_id, u.path_len, u.path_packed = cast(self.trie_id, C.c_uint32), cast(self.path_len, C.c_uint8), cast(self.path_packed, C.c_uint8)
+        u.state_mask, u.tree_mask, u.hash_mask = cast(self.state, C.c_uint16), cast(self.tree, C.c_uint16), cast(self.hash, C.c_uint16)
+        u.hash_offset, u.hashes = cast(self.offs, C.c_uint64), cast(self.hashes, C.c_uint8)
+        self.struct = u
+
+
+def _slice_rows(rows: Rows, lib) -> list:
+    n = int(rows.n_rows)
+    out = []
+    if n:
+        offs = np.ctypeslib.as_array(rows.row_offset, (n + 1,))
+        kl = np.ctypeslib.as_array(rows.key_len, (n,))
+        blob = np.ctypeslib.as_array(rows.bytes, (int(offs[n]),)).tobytes()
+        for r in range(n):
+            lo, hi, k = int(offs[r]), int(offs[r + 1]), int(kl[r])
+            out.append((blob[lo:lo + k], blob[lo + k:hi]))
+    lib.b200_rows_release(C.byref(rows))
+    return out
+
+
+class TableRows:
+    """Rows straight from the C ABI (no per-row Python objects): numpy views on library-owned memory."""
+
+    def __init__(self, rows: Rows, lib):
+        self._rows, self._lib = rows, lib
+        n = self.n_rows = int(rows.n_rows)
+        self.row_offset = np.ctypeslib.as_array(rows.row_offset, (n + 1,)) if n else np.zeros(1, np.uint64)
+        self.key_len = np.ctypeslib.as_array(rows.key_len, (n,)) if n else np.zeros(0, np.uint32)
+        total = int(self.row_offset[n]) if n else 0
+        self.bytes = np.ctypeslib.as_array(rows.bytes, (total,)) if total else np.zeros(0, np.uint8)
+
+    def to_list(self) -> list:
+        blob = self.bytes.tobytes()
+        out = []
+        for r in range(self.n_rows):
+            lo, hi, k = int(self.row_offset[r]), int(self.row_offset[r + 1]), int(self.key_len[r])
+            out.append((blob[lo:lo + k], blob[lo + k:hi]))
+        return out
+
+    def release(self):
+        if self._rows is not None:
+            self.row_offset = self.key_len = self.bytes = None
+            self._lib.b200_rows_release(C.byref(self._rows))
+            self._rows = None
+
+    def __len__(self):
+        return self.n_rows
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def rows_from_updates(account_updates=None, storage_updates=None, acct_keys=None, key_format: int = KEYS_LEGACY):
+    """Raw path: `b200_updates` structs as the engine filled them (before release) -> (TableRows|None, TableRows|None)."""
+    lib = _lib.load()
+    res = []
+    if account_updates is not None:
+        rows = Rows()
+        rc = lib.b200_account_trie_rows(C.cast(C.byref(account_updates), C.POINTER(Updates)), key_format, C.byref(rows))
+        if rc:
+            raise B200Error(rc, "b200_account_trie_rows")
+        res.append(TableRows(rows, lib))
+    else:
+        res.append(None)
+    if storage_updates is not None:
+        keys = np.ascontiguousarray(acct_keys, dtype=np.uint8).reshape(-1, 32)
+        rows = Rows()
+        rc = lib.b200_storage_trie_rows(C.cast(C.byref(storage_updates), C.POINTER(Updates)), keys.ctypes.data,
+                                        len(keys), key_format, C.byref(rows))
+        if rc:
+            raise B200Error(rc, "b200_storage_trie_rows")
+        res.append(TableRows(rows, lib))
+    else:
+        res.append(None)
+    return tuple(res)
+
+
+def account_trie_rows(records, key_format: int = KEYS_LEGACY) -> list:
+    """records: account-trie `TrieUpdates.account_nodes` as the engine returns them."""
+    lib = _lib.load()
+    m, rows = _Marshalled(records), Rows()
+    rc = lib.b200_account_trie_rows(C.byref(m.struct), key_format, C.byref(rows))
+    if rc:
+        raise B200Error(rc, "b200_account_trie_rows")
+    return _slice_rows(rows, lib)
+
+
+def storage_trie_rows(records, acct_keys, key_format: int = KEYS_LEGACY) -> list:
+    """records: storage-trie nodes with trie_id = account index; acct_keys: the (n,32) hashed addresses."""
+    lib = _lib.load()
+    keys = np.ascontiguousarray(acct_keys, dtype=np.uint8).reshape(-1, 32)
+    m, rows = _Marshalled(records), Rows()
+    rc = lib.b200_storage_trie_rows(C.byref(m.struct), keys.ctypes.data, len(keys), key_format, C.byref(rows))
+    if rc:
+        raise B200Error(rc, "b200_storage_trie_rows")
+    return _slice_rows(rows, lib)

@@ -198,7 +198,56 @@ static void random_state_vs_oracle(const Engine &e) {
     orc_updates_free(&os);
 }
 
+// Table rows — host-only, runs before a device is needed.  Key vectors: crates/trie/common/src/nibbles.rs
+// :321-346 (StoredNibbles [2,4] -> 02 04; subkey = 64 nibble bytes + count), :443-450 (packed 0xAB 0xC0 .. 03).
+static void table_rows_host_only() {
+    TrieUpdates u;
+    BranchNodeCompact n;
+    n.state_mask = 0xf607, n.tree_mask = 0x0005, n.hash_mask = 0x4004;
+    n.hashes = {b256("90d53cd810cc5d4243766cd4451e7b9d14b736a1148b26b3baac7617f617d321"),
+                b256("cc35c964dda53ba6c0b87798073a9628dbc9cd26b5cce88eb69655a9c609caf1")};
+    u.account_nodes[Nibbles{0xA, 0xB, 0xC}] = n;
+    u.account_nodes[Nibbles{2, 4}] = n;
+    auto rows = account_trie_rows(u, B200_KEYS_LEGACY);
+    CHECK(rows.size() == 2);
+    CHECK((rows[0].key == std::vector<uint8_t>{2, 4}));
+    CHECK((rows[1].key == std::vector<uint8_t>{0xA, 0xB, 0xC}));
+    CHECK(rows[0].value.size() == 6 + 64);
+    const uint8_t masks[6] = {0xf6, 0x07, 0x00, 0x05, 0x40, 0x04};
+    CHECK(std::memcmp(rows[0].value.data(), masks, 6) == 0);
+    CHECK(std::memcmp(rows[0].value.data() + 6, n.hashes[0].data(), 32) == 0);
+    CHECK(std::memcmp(rows[0].value.data() + 38, n.hashes[1].data(), 32) == 0);
+    auto packed = account_trie_rows(u, B200_KEYS_PACKED);
+    CHECK(packed.size() == 2 && packed[1].key.size() == 33);
+    CHECK(packed[1].key[0] == 0xAB && packed[1].key[1] == 0xC0 && packed[1].key[2] == 0 && packed[1].key[32] == 3);
+    CHECK(packed[0].key[0] == 0x24 && packed[0].key[32] == 2);
+
+    B256 a1 = b256("1100000000000000000000000000000000000000000000000000000000000000");
+    B256 a0 = b256("0100000000000000000000000000000000000000000000000000000000000000");
+    StorageTrieUpdates s1, s0;
+    s1.storage_nodes[Nibbles{2, 4}] = n;
+    s0.storage_nodes[Nibbles{5}] = n;
+    s0.storage_nodes[Nibbles{5, 0}] = n;
+    u.insert_storage_updates(a1, s1);
+    u.insert_storage_updates(a0, s0);
+    u.insert_storage_updates(b256("2200000000000000000000000000000000000000000000000000000000000000"), StorageTrieUpdates::deleted());
+    auto srows = storage_trie_rows(u, B200_KEYS_LEGACY);
+    CHECK(srows.size() == 3);
+    CHECK(std::memcmp(srows[0].key.data(), a0.data(), 32) == 0 && std::memcmp(srows[2].key.data(), a1.data(), 32) == 0);
+    CHECK(srows[0].value.size() == 65 + 70 && srows[0].value[0] == 5 && srows[0].value[64] == 1);
+    CHECK(srows[1].value[0] == 5 && srows[1].value[1] == 0 && srows[1].value[64] == 2);
+    CHECK(srows[2].value[0] == 2 && srows[2].value[1] == 4 && srows[2].value[2] == 0 && srows[2].value[64] == 2);
+    CHECK(std::memcmp(srows[2].value.data() + 65, masks, 6) == 0);
+    auto sp = storage_trie_rows(u, B200_KEYS_PACKED);
+    CHECK(sp.size() == 3 && sp[2].value.size() == 33 + 70 && sp[2].value[0] == 0x24 && sp[2].value[32] == 2);
+}
+
 int main() {
+    table_rows_host_only();
+    if (failures) {
+        std::printf("host_test: %d FAILURES (host-only part)\n", failures);
+        return 1;
+    }
     try {
         Engine e(0);
         account_and_storage_trie(e);

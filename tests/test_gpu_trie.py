@@ -189,6 +189,24 @@ def test_full_state_random(eng):
     assert su == o_su
 
 
+@pytest.mark.parametrize("packed", [0, 1])
+def test_full_state_table_rows(eng, packed):
+    """the stored nodes of a device build as AccountsTrie / StoragesTrie rows, against rows encoded
+    from the oracle's TrieUpdates by the test-side restatement of the reference codecs."""
+    from tests.test_table_rows import expected_account_rows, expected_storage_rows
+    n = 20_000
+    akeys, accs = synth_accounts(21, n)
+    counts = np.where(np.arange(n) % 4 == 0, 24, 0) + np.where(np.arange(n) % 1999 == 0, 2500, 0)
+    skeys, svals, offs = synth_storage(22, counts, value_mode="mixed")
+    root, arows, srows = eng.state_root_full_rows(akeys, accs, skeys, svals, offs, key_format=packed)
+    o_root, o_au, o_su = oracle.state_root_full(akeys, accs, skeys, svals, offs, want_updates=True, threads=4)
+    assert root == o_root
+    assert arows.to_list() == expected_account_rows(o_au, bool(packed))
+    assert srows.to_list() == expected_storage_rows(o_su, akeys, bool(packed))
+    assert len(arows) > 1000 and len(srows) > 1000
+    arows.release(); srows.release()
+
+
 def test_one_million_leaves(eng):
     """Size-independent check at scale: 1M-account trie root equals the oracle's."""
     keys, accs = synth_accounts(77, 1_000_000)
