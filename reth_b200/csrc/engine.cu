@@ -51,9 +51,9 @@ extern "C" B200_API b200_ctx *b200_create(int32_t device_ordinal) {
     b200_ctx *c = new b200_ctx();
     c->device = device_ordinal;
     auto bail = [&](cudaError_t e) -> b200_ctx * {
-        (void)e;
-        g_create_status = B200_ERR_CUDA;
-        delete c;
+        g_create_status = e == cudaErrorMemoryAllocation ? B200_ERR_OOM : B200_ERR_CUDA;
+        cudaGetLastError();
+        b200_destroy(c);  // releases whatever was created so far
         return nullptr;
     };
     cudaError_t e;
