@@ -281,6 +281,34 @@ B200_API uint64_t b200_trie_device_bytes(const b200_trie *);
 B200_API uint64_t b200_trie_leaves(const b200_trie *);
 B200_API void b200_trie_destroy(b200_trie *);
 
+/* ------------------------------------------------------------------------------------------------ dynamic resident trie
+ * The account trie as an arena of 16-slot branch nodes in HBM that takes a block's upserts AND deletes in place: only
+ * the paths of the changed keys are restructured and re-hashed, whatever the size of the trie.  This is the role of
+ * reth's sparse trie on the live path (ParallelSparseTrie::update_leaf / remove_leaf / root,
+ * crates/trie/sparse/src/parallel.rs) and of TrieWalker + prefix sets on the database path
+ * (crates/trie/trie/src/walker.rs:161-202, crates/trie/common/src/prefix_set.rs).
+ * STATUS: validated bit-exact against the oracle under tools/emu (CPU emulation of these kernels); first B200 run
+ * pending — until then b200_trie_apply (merge + rebuild) is the measured path.
+ *
+ * b200_dtrie_apply: keys32 strictly ascending; present[i] == 0 deletes key i (NULL: all upserts); deleting an absent
+ * key is a no-op.  storage_roots32 may be NULL (new accounts get EMPTY_ROOT_HASH, existing ones keep theirs).
+ * opt_updated = the block's TrieUpdates::account_nodes (re-hashed nodes with tree_mask|hash_mask != 0);
+ * opt_removed = TrieUpdates::removed_nodes as records whose masks are 0 (paths of stored nodes that ceased to exist or to
+ * be stored; updated paths take precedence, crates/trie/common/src/updates.rs:160-167).  Release both with
+ * b200_updates_release. */
+typedef struct b200_dtrie b200_dtrie;
+B200_API int32_t b200_dtrie_create(b200_ctx *, const uint8_t *acct_keys32 /* sorted */, const b200_account *accts,
+                                   const uint8_t *storage_roots32 /* nullable */, uint64_t n, b200_dtrie **out,
+                                   uint8_t root32[32] /* nullable */);
+B200_API int32_t b200_dtrie_apply(b200_dtrie *, const uint8_t *keys32, const b200_account *accts, const uint8_t *present,
+                                  const uint8_t *storage_roots32, uint64_t m, uint8_t root32[32],
+                                  b200_updates *opt_updated, b200_updates *opt_removed, b200_stats *opt_stats);
+B200_API int32_t b200_dtrie_root(b200_dtrie *, uint8_t root32[32]);
+B200_API uint64_t b200_dtrie_leaves(const b200_dtrie *);
+B200_API uint64_t b200_dtrie_nodes(const b200_dtrie *);   /* node slots allocated so far */
+B200_API uint64_t b200_dtrie_device_bytes(const b200_dtrie *);
+B200_API void b200_dtrie_destroy(b200_dtrie *);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,11 +103,10 @@ static int32_t trie_build_owned(b200_trie *t) {
     return B200_OK;
 }
 
-static int32_t trie_create_common(b200_ctx *c, const void *keys, const void *accts, const void *sroots, uint64_t n,
+// caller holds the context lock
+static int32_t trie_create_locked(b200_ctx *c, const void *keys, const void *accts, const void *sroots, uint64_t n,
                                   cudaMemcpyKind kind, b200_trie **out, void *root_out) {
-    if (!c || !out || (n && (!keys || !accts))) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
     *out = nullptr;
-    std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
     b200_trie *t = new b200_trie();
     t->c = c;
@@ -136,6 +135,13 @@ static int32_t trie_create_common(b200_ctx *c, const void *keys, const void *acc
     }
     *out = t;
     return B200_OK;
+}
+
+static int32_t trie_create_common(b200_ctx *c, const void *keys, const void *accts, const void *sroots, uint64_t n,
+                                  cudaMemcpyKind kind, b200_trie **out, void *root_out) {
+    if (!c || !out || (n && (!keys || !accts))) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    std::lock_guard<std::mutex> g(c->mu);
+    return trie_create_locked(c, keys, accts, sroots, n, kind, out, root_out);
 }
 
 extern "C" B200_API int32_t b200_trie_create(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,

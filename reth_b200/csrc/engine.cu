@@ -194,3 +194,4 @@ extern "C" B200_API uint64_t b200_launch_count(const b200_ctx *c) { return c ? c
 #include "eng_roots.inl"
 #include "eng_frontier.inl"
 #include "eng_resident.inl"
+#include "eng_dtrie.inl"

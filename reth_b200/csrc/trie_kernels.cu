@@ -32,5 +32,6 @@ namespace b200 {
 #include "tk_resident.cuh"
 #include "tk_frontier.cuh"
 #include "tk_launchers.cuh"
+#include "tk_dtrie.cuh"
 
 }  // namespace b200

@@ -130,4 +130,69 @@ cudaError_t launch_stored_flags_subset(const ForestDev &f, const uint32_t *ids, 
 cudaError_t launch_pick_subset(const uint32_t *ids, const uint32_t *prefix, const uint32_t *sel_pos, uint32_t n_sel,
                                uint32_t *out_ids, uint32_t *out_prefix, cudaStream_t st);
 
+// ------------------------------------------------------------------------------------------------ dynamic trie (tk_dtrie.cuh)
+constexpr uint32_t DT_NONE = 0xFFFFFFFFu;
+constexpr uint32_t DT_LEAF = 0x80000000u;
+constexpr uint8_t DT_DEAD = 0xFF;  // ndepth / lmeta of a freed slot
+
+enum : int {
+    DG_ROOT = 0,      // child word of the root
+    DG_NLEAVES,       // live leaves
+    DG_LEAF_ALLOC,    // bump pointers
+    DG_NODE_ALLOC,
+    DG_LEAF_FREE,     // free-stack heights
+    DG_NODE_FREE,
+    DG_SEEDS,         // list lengths of the current apply
+    DG_BUILT,
+    DG_REMOVED,
+    DG_LIST_A,
+    DG_LIST_B,
+    DG_NINSERT,
+    DG_FREED_NOW,
+    DG_WORDS = 16
+};
+
+struct DTrieDev {
+    // leaves [lcap]
+    uint8_t *lkey, *lacct, *lsroot, *lref, *lmeta;
+    uint32_t *lparent;
+    uint8_t *lseed;
+    // nodes [ncap]
+    uint32_t *nchild;  // [ncap][16]
+    uint8_t *ndepth;
+    uint32_t *nparent;
+    uint8_t *nref, *nmeta;
+    ushort4 *nmasks;
+    uint8_t *nkey;  // [ncap][32] a key of the subtree: its first ndepth nibbles are the node's path
+    uint32_t *npending;
+    uint8_t *nseed, *ncur, *nnext;
+    // free stacks, lists, globals
+    uint32_t *leaf_free, *node_free;
+    uint32_t *seeds, *built, *removed, *freed_now;
+    uint32_t *g;
+    int *err;
+    unsigned long long *counters;
+    uint32_t lcap, ncap;
+};
+
+enum : uint8_t { DK_NOOP = 0, DK_UPDATE = 1, DK_DELETE = 2, DK_INSERT = 3 };
+
+cudaError_t launch_dt_convert_nodes(const ForestDev &f, uint32_t n_nodes, const uint32_t *node_parent, const DTrieDev &t,
+                                    cudaStream_t st);
+cudaError_t launch_dt_locate(const DTrieDev &t, const uint8_t *keys, const uint8_t *present, uint64_t m, uint8_t *kind,
+                             uint32_t *leaf_of, cudaStream_t st);
+cudaError_t launch_dt_update_detach(const DTrieDev &t, const uint8_t *accts, const uint8_t *sroots, uint64_t m,
+                                    const uint8_t *kind, const uint32_t *leaf_of, uint32_t *touched, cudaStream_t st);
+cudaError_t launch_dt_collapse_round(const DTrieDev &t, const uint32_t *list, const uint32_t *count_p, uint32_t max_count,
+                                     uint8_t *defer, uint32_t *next, uint32_t *next_count, cudaStream_t st);
+cudaError_t launch_dt_insert(const DTrieDev &t, const uint8_t *keys, const uint8_t *accts, const uint8_t *sroots,
+                             const uint32_t *ins_idx, const uint32_t *n_ins_p, uint64_t max_ins, uint64_t *attach,
+                             cudaStream_t st);
+cudaError_t launch_dt_rehash(const DTrieDev &t, uint32_t max_seeds, uint8_t *root_out, cudaStream_t st);
+cudaError_t launch_dt_finish(const DTrieDev &t, uint32_t max_freed, uint8_t *root_out, cudaStream_t st);
+cudaError_t launch_dt_stored_flags(const DTrieDev &t, uint32_t max_built, uint8_t *flags, uint32_t *n_hashes, cudaStream_t st);
+cudaError_t launch_dt_gather_updates(const DTrieDev &t, const uint32_t *stored_ids, uint32_t n_stored,
+                                     const uint32_t *hash_prefix_by_record, const UpdatesDev &out, cudaStream_t st);
+cudaError_t launch_dt_removed_paths(const DTrieDev &t, uint32_t n_removed, uint8_t *path_len, uint8_t *path_packed, cudaStream_t st);
+
 }  // namespace b200

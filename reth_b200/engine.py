@@ -383,3 +383,69 @@ class ResidentTrie:
         if self.handle:
             self.engine.lib.b200_trie_destroy(self.handle)
             self.handle = None
+
+
+class DynamicTrie:
+    """Handle on a b200_dtrie: the account trie as an arena of 16-slot branch nodes in HBM; `apply` takes upserts and
+    deletes in place and re-hashes only the touched paths (reth's sparse-trie role, crates/trie/sparse/src/parallel.rs).
+    Validated under tools/emu; first B200 run pending (see include/b200trie.h)."""
+
+    def __init__(self, engine: Engine, handle, root: bytes):
+        self.engine, self.handle, self._root = engine, handle, root
+
+    @classmethod
+    def create(cls, engine: Engine, acct_keys, accounts, storage_roots32=None) -> "DynamicTrie":
+        acct_keys = _np(acct_keys).reshape(-1, 32)
+        accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
+        sr = None if storage_roots32 is None else _np(storage_roots32).reshape(-1, 32)
+        h = C.c_void_p()
+        root = np.empty(32, np.uint8)
+        engine._check(engine.lib.b200_dtrie_create(engine.ctx, _ptr(acct_keys), _ptr(accounts), _ptr(sr), len(acct_keys),
+                                                   C.byref(h), _ptr(root)))
+        return cls(engine, h, root.tobytes())
+
+    def apply(self, keys, accounts, present=None, storage_roots32=None, want_updates=False, want_stats=False):
+        """keys strictly ascending, present[i] False = delete.  -> root [, updated records, removed paths][, stats]."""
+        keys = _np(keys).reshape(-1, 32)
+        accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
+        pres = None if present is None else _np(np.asarray(present, dtype=np.uint8))
+        sr = None if storage_roots32 is None else _np(storage_roots32).reshape(-1, 32)
+        root = np.empty(32, np.uint8)
+        uu, ur, s = Updates(), Updates(), Stats()
+        self.engine._check(self.engine.lib.b200_dtrie_apply(self.handle, _ptr(keys), _ptr(accounts), _ptr(pres), _ptr(sr),
+                                                            len(keys), _ptr(root),
+                                                            C.byref(uu) if want_updates else None,
+                                                            C.byref(ur) if want_updates else None, C.byref(s)))
+        self._root = root.tobytes()
+        res = [self._root]
+        if want_updates:
+            res.append(updates_to_records(uu, self.engine.lib))
+            res.append([r[1] for r in updates_to_records(ur, self.engine.lib)])
+        if want_stats:
+            res.append(s.as_dict())
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def root(self) -> bytes:
+        out = np.empty(32, np.uint8)
+        self.engine._check(self.engine.lib.b200_dtrie_root(self.handle, _ptr(out)))
+        return out.tobytes()
+
+    def device_bytes(self) -> int:
+        return int(self.engine.lib.b200_dtrie_device_bytes(self.handle))
+
+    def nodes(self) -> int:
+        return int(self.engine.lib.b200_dtrie_nodes(self.handle))
+
+    def __len__(self):
+        return int(self.engine.lib.b200_dtrie_leaves(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.engine.lib.b200_dtrie_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
