@@ -529,6 +529,42 @@ class StateRoot {
     uint64_t threshold_ = 100000;  // DEFAULT_INTERMEDIATE_THRESHOLD, trie.rs:25
 };
 
+/// The account trie resident in HBM as an arena of 16-slot branch nodes (b200_dtrie_*): a block's upserts and deletes
+/// are applied in place and only the touched paths are re-hashed — the part reth's sparse trie plays on the live path
+/// (crates/trie/sparse/src/parallel.rs: update_leaf / remove_leaf / root).  `apply` returns the block's
+/// TrieUpdates{account_nodes, removed_nodes} (crates/trie/common/src/updates.rs:17-26).
+class DynamicTrie {
+  public:
+    DynamicTrie(const Engine &e, const FlatState &f, const std::vector<uint8_t> *storage_roots = nullptr) : e_(e) {
+        e_.check(b200_dtrie_create(e_.raw(), f.acct_keys.data(), f.accts.data(), storage_roots ? storage_roots->data() : nullptr,
+                                   f.n_accounts(), &t_, root_.data()));
+    }
+    DynamicTrie(const DynamicTrie &) = delete;
+    DynamicTrie &operator=(const DynamicTrie &) = delete;
+    ~DynamicTrie() { b200_dtrie_destroy(t_); }
+    const B256 &root() const { return root_; }
+    uint64_t leaves() const { return b200_dtrie_leaves(t_); }
+    /// keys strictly ascending; present[i] == 0 deletes (nullptr: all upserts)
+    std::pair<B256, TrieUpdates> apply(const std::vector<uint8_t> &keys32, const std::vector<b200_account> &accts,
+                                       const std::vector<uint8_t> *present = nullptr,
+                                       const std::vector<uint8_t> *storage_roots = nullptr) {
+        b200_updates up{}, rm{};
+        e_.check(b200_dtrie_apply(t_, keys32.data(), accts.data(), present ? present->data() : nullptr,
+                                  storage_roots ? storage_roots->data() : nullptr, accts.size(), root_.data(), &up, &rm, nullptr));
+        TrieUpdates out;
+        for (uint64_t i = 0; i < up.n_nodes; i++) out.account_nodes.insert(detail::branch_node(up, i));
+        for (uint64_t i = 0; i < rm.n_nodes; i++) out.removed_nodes.insert(detail::branch_node(rm, i).first);
+        b200_updates_release(&up);
+        b200_updates_release(&rm);
+        return {root_, std::move(out)};
+    }
+
+  private:
+    const Engine &e_;
+    b200_dtrie *t_ = nullptr;
+    B256 root_{};
+};
+
 /// ParallelStateRoot::{incremental_root, incremental_root_with_updates} — crates/trie/parallel/src/root.rs:35-77.
 /// The storage-root fan-out and the account fold are the same device launches.
 class ParallelStateRoot : public StateRoot {

@@ -216,15 +216,18 @@ class ResidentStateRoot:
     (`b200_trie_apply`).  Storage roots of the touched accounts are recomputed from their complete post-block storage
     in one `b200_storage_roots` call."""
 
-    def __init__(self, engine: Engine, state: HashedPostStateSorted):
-        from .engine import ACCOUNT_DTYPE, ResidentTrie
+    def __init__(self, engine: Engine, state: HashedPostStateSorted, dynamic: bool = False):
+        """dynamic=True keeps the account trie in a `DynamicTrie` (b200_dtrie_*): new and destroyed accounts are applied in
+        place instead of through merge + rebuild (`commit` then always reports rebuilt=False)."""
+        from .engine import ACCOUNT_DTYPE, DynamicTrie, ResidentTrie
         self.engine = engine
         self.accounts = {k: a for k, a in state.accounts if a is not None}
         self.storages = {k: {s: v for s, v in st.storage_slots if v != 0} for k, st in state.storages.items()
                          if k in self.accounts}
         keys, accts, skeys, svals, offs = state.to_flat()
         sroots = engine.storage_roots(skeys, svals, offs) if len(keys) else np.zeros((0, 32), np.uint8)
-        self.trie = ResidentTrie.create(engine, keys, accts, sroots)
+        self.dynamic = dynamic
+        self.trie = (DynamicTrie if dynamic else ResidentTrie).create(engine, keys, accts, sroots)
         self._dtype = ACCOUNT_DTYPE
 
     def root(self) -> bytes:
@@ -281,6 +284,8 @@ class ResidentStateRoot:
             accts[i]["code_hash"] = np.frombuffer(a.code_hash(), np.uint8)
             sroots[i] = root_of[k]
         try:
+            if self.dynamic:
+                return self.trie.apply(keys, accts, present, sroots), False
             return self.trie.apply(keys, accts, present, sroots)
         except Exception as e:  # noqa: BLE001
             raise StateRootError(str(e)) from e

@@ -198,6 +198,83 @@ static void random_state_vs_oracle(const Engine &e) {
     orc_updates_free(&os);
 }
 
+// DynamicTrie: blocks of inserts / deletes / updates applied in place == oracle root over the merged state, and the
+// node set {previous - removed + updated} == the oracle's stored nodes (the incremental == full criterion of
+// crates/trie/db/tests/trie.rs:680-717).  Opt-in on a GPU until the first validated B200 run (tests/test_gpu_dtrie.py).
+static void dynamic_trie_blocks(const Engine &e) {
+    std::mt19937_64 rng(7);
+    std::map<B256, b200_account> state;
+    auto rand_key = [&] {
+        B256 k;
+        for (auto &b : k) b = (uint8_t)rng();
+        return k;
+    };
+    auto rand_acct = [&] {
+        b200_account a{};
+        a.nonce = rng() & 0xffff;
+        for (int i = 24; i < 32; i++) a.balance_be[i] = (uint8_t)rng();
+        std::memcpy(a.code_hash, KECCAK_EMPTY.data(), 32);
+        return a;
+    };
+    for (int i = 0; i < 1500; i++) state[rand_key()] = rand_acct();
+    auto flat_of = [&](const std::map<B256, b200_account> &st) {
+        FlatState f;
+        for (auto &kv : st) {
+            f.acct_keys.insert(f.acct_keys.end(), kv.first.begin(), kv.first.end());
+            f.accts.push_back(kv.second);
+        }
+        f.seg_offsets.assign(st.size() + 1, 0);
+        return f;
+    };
+    auto oracle_nodes = [&](const std::map<B256, b200_account> &st, B256 &root) {
+        FlatState f = flat_of(st);
+        orc_updates ou{};
+        CHECK(orc_state_root(f.acct_keys.data(), reinterpret_cast<const orc_account *>(f.accts.data()), nullptr, st.size(),
+                             root.data(), &ou) == 0);
+        std::set<std::pair<std::vector<uint8_t>, uint8_t>> paths;
+        for (uint64_t i = 0; i < ou.n_nodes; i++)
+            paths.insert({std::vector<uint8_t>(ou.path_packed + 32 * i, ou.path_packed + 32 * i + 32), ou.path_len[i]});
+        orc_updates_free(&ou);
+        return paths;
+    };
+    B256 oroot;
+    auto db = oracle_nodes(state, oroot);
+    DynamicTrie trie(e, flat_of(state));
+    CHECK(trie.root() == oroot);
+    auto pack = [](const Nibbles &p) {
+        std::vector<uint8_t> out(32, 0);
+        for (size_t j = 0; j < p.size(); j++) out[j >> 1] |= (j & 1) ? p[j] : (uint8_t)(p[j] << 4);
+        return std::make_pair(out, (uint8_t)p.size());
+    };
+    for (int block = 0; block < 6; block++) {
+        std::map<B256, std::pair<uint8_t, b200_account>> dirty;
+        std::vector<B256> existing;
+        for (auto &kv : state) existing.push_back(kv.first);
+        for (int i = 0; i < 120; i++) {
+            int r = (int)(rng() % 3);
+            if (r == 0) dirty[rand_key()] = {1, rand_acct()};
+            else if (r == 1) dirty[existing[rng() % existing.size()]] = {0, b200_account{}};
+            else dirty[existing[rng() % existing.size()]] = {1, rand_acct()};
+        }
+        std::vector<uint8_t> keys, present;
+        std::vector<b200_account> accts;
+        for (auto &kv : dirty) {
+            keys.insert(keys.end(), kv.first.begin(), kv.first.end());
+            present.push_back(kv.second.first);
+            accts.push_back(kv.second.second);
+            if (kv.second.first) state[kv.first] = kv.second.second;
+            else state.erase(kv.first);
+        }
+        auto [root, upd] = trie.apply(keys, accts, &present);
+        auto expect = oracle_nodes(state, oroot);
+        CHECK(root == oroot);
+        CHECK(trie.leaves() == state.size());
+        for (auto &p : upd.removed_nodes) db.erase(pack(p));
+        for (auto &kv : upd.account_nodes) db.insert(pack(kv.first));
+        CHECK(db == expect);
+    }
+}
+
 // Table rows — host-only, runs before a device is needed.  Key vectors: crates/trie/common/src/nibbles.rs
 // :321-346 (StoredNibbles [2,4] -> 02 04; subkey = 64 nibble bytes + count), :443-450 (packed 0xAB 0xC0 .. 03).
 static void table_rows_host_only() {
@@ -255,6 +332,7 @@ int main() {
         extension_node_storage_trie(e);
         prefix_sets_and_destroyed(e);
         random_state_vs_oracle(e);
+        if (std::getenv("B200_EMU") || std::getenv("B200_DTRIE_ON_GPU")) dynamic_trie_blocks(e);
     } catch (const B200Error &err) {
         std::printf("B200Error: %s\n", err.what());
         return err.status == B200_ERR_NO_DEVICE ? 77 : 2;

@@ -22,3 +22,20 @@ def test_cuda_sources_pass_parity_under_cpu_emulation():
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
+
+
+def test_cpp_host_mirror_under_cpu_emulation(tmp_path):
+    """tests/cpp/host_test.cpp (reth's trie tests restated over the C++ host mirror) linked against the emulated build."""
+    emu = os.path.join(ROOT, "tools", "emu")
+    subprocess.run(["make", "-j8", "-C", emu], check=True, capture_output=True)
+    import oracle
+    oracle.build()
+    exe = str(tmp_path / "host_test_emu")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "cpp", "host_test.cpp"), "-o", exe,
+                        os.path.join(emu, "build", "libb200trie_emu.so"), os.path.join(ROOT, "oracle", "liboracle.so"),
+                        "-Wl,-rpath," + os.path.join(emu, "build"), "-Wl,-rpath," + os.path.join(ROOT, "oracle")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=dict(os.environ, B200_EMU="1"))
+    assert r.returncode == 0 and "all checks passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
