@@ -3,7 +3,10 @@
 
 #include <sys/mman.h>
 
+#include <algorithm>
 #include <chrono>
+#include <numeric>
+#include <random>
 #include <mutex>
 #include <vector>
 
@@ -85,6 +88,24 @@ emu_switch:
 
 namespace emu {
 namespace {
+
+// EMU_SCHEDULE=fwd (default) | rev | rand:<seed> — the order in which blocks, warps and lanes get their turns.  Results
+// of a correct kernel do not depend on it; running the tests under several schedules exposes order dependence.
+struct Schedule {
+    int mode;  // 0 forward, 1 reverse, 2 random
+    unsigned seed;
+};
+Schedule schedule() {
+    static const Schedule s = [] {
+        const char *e = getenv("EMU_SCHEDULE");
+        if (!e || !strcmp(e, "fwd")) return Schedule{0, 0};
+        if (!strcmp(e, "rev")) return Schedule{1, 0};
+        if (!strncmp(e, "rand", 4)) return Schedule{2, e[4] == ':' ? (unsigned)strtoul(e + 5, nullptr, 10) : 1u};
+        std::fprintf(stderr, "emu: unknown EMU_SCHEDULE '%s'\n", e);
+        std::abort();
+    }();
+    return s;
+}
 
 void fiber_entry() {
     (*body)();
@@ -173,7 +194,9 @@ uint64_t warp_exchange(uint32_t mask, uint64_t mine, int src_lane, bool *src_val
     unsigned parity = (unsigned)((s.cnt[lane] + 1) & 1);
     s.val[parity][lane] = mine;
     sync_warp(mask);
-    *src_valid = src_lane >= 0 && src_lane < 32 && (mask >> src_lane & 1) && !lane_exited(w, (unsigned)src_lane);
+    // the source took part iff it reached this exchange (it may have run on and exited since: its value stays put)
+    const uint64_t my = s.cnt[lane];
+    *src_valid = src_lane >= 0 && src_lane < 32 && (mask >> src_lane & 1) && s.cnt[src_lane] >= my;
     return *src_valid ? s.val[parity][src_lane] : mine;
 }
 
@@ -183,9 +206,10 @@ uint64_t warp_reduce_or(uint32_t mask, uint64_t mine) {
     unsigned parity = (unsigned)((s.cnt[lane] + 1) & 1);
     s.val[parity][lane] = mine;
     sync_warp(mask);
+    const uint64_t my = s.cnt[lane];
     uint64_t r = 0;
     for (unsigned l = 0; l < 32; l++)
-        if ((mask >> l & 1) && !lane_exited(w, l)) r |= s.val[parity][l];
+        if ((mask >> l & 1) && s.cnt[l] >= my) r |= s.val[parity][l];
     return r;
 }
 
@@ -209,7 +233,23 @@ void run_grid(unsigned grid, unsigned block, const std::function<void()> &thread
     g.gdim = dim3(grid);
     in_kernel = true;
     const unsigned n_warps = (block + 31) / 32;
-    for (unsigned b = 0; b < grid; b++) {
+    const Schedule sched = schedule();
+    std::vector<unsigned> block_order(grid), lane_order(32), warp_order(n_warps);
+    std::iota(block_order.begin(), block_order.end(), 0u);
+    std::iota(lane_order.begin(), lane_order.end(), 0u);
+    std::iota(warp_order.begin(), warp_order.end(), 0u);
+    if (sched.mode == 1) {
+        std::reverse(block_order.begin(), block_order.end());
+        std::reverse(lane_order.begin(), lane_order.end());
+        std::reverse(warp_order.begin(), warp_order.end());
+    } else if (sched.mode == 2) {
+        std::mt19937 rng(sched.seed + (unsigned)stat_launches * 7919u);
+        std::shuffle(block_order.begin(), block_order.end(), rng);
+        std::shuffle(lane_order.begin(), lane_order.end(), rng);
+        std::shuffle(warp_order.begin(), warp_order.end(), rng);
+    }
+    for (unsigned bi = 0; bi < grid; bi++) {
+        const unsigned b = block_order[bi];
         g.bid = uint3{b, 0, 0};
         warps.assign(n_warps, Warp());
         bar_count = 0;
@@ -218,13 +258,16 @@ void run_grid(unsigned grid, unsigned block, const std::function<void()> &thread
         unsigned stalled_rounds = 0;
         while (alive) {
             bool any_progress = false;
-            for (unsigned w = 0; w < n_warps; w++) {
+            for (unsigned wi = 0; wi < n_warps; wi++) {
+                const unsigned w = warp_order[wi];
                 unsigned lo = w * 32, hi = lo + 32 < block ? lo + 32 : block;
                 for (;;) {  // keep a warp going while its lanes still pass sync points or finish
                     uint64_t before = 0, after = 0;
                     bool ran = false;
                     for (unsigned t = lo; t < hi; t++) before += fibers[t].progress;
-                    for (unsigned t = lo; t < hi; t++) {
+                    for (unsigned li = 0; li < 32; li++) {
+                        const unsigned t = lo + lane_order[li];
+                        if (t >= hi) continue;
                         Fiber &f = fibers[t];
                         if (f.done || (f.wait_block && bar_gen == f.wait_gen)) continue;
                         cur = t;
