@@ -300,6 +300,8 @@ typedef struct b200_dtrie b200_dtrie;
 B200_API int32_t b200_dtrie_create(b200_ctx *, const uint8_t *acct_keys32 /* sorted */, const b200_account *accts,
                                    const uint8_t *storage_roots32 /* nullable */, uint64_t n, b200_dtrie **out,
                                    uint8_t root32[32] /* nullable */);
+B200_API int32_t b200_dtrie_create_dev(b200_ctx *, const void *d_acct_keys32, const void *d_accts,
+                                       const void *d_storage_roots32, uint64_t n, b200_dtrie **out, void *d_root32);
 B200_API int32_t b200_dtrie_apply(b200_dtrie *, const uint8_t *keys32, const b200_account *accts, const uint8_t *present,
                                   const uint8_t *storage_roots32, uint64_t m, uint8_t root32[32],
                                   b200_updates *opt_updated, b200_updates *opt_removed, b200_stats *opt_stats);

@@ -140,6 +140,7 @@ def load():
     sig("b200_trie_leaves", u64, vp)
     sig("b200_trie_destroy", None, vp)
     sig("b200_dtrie_create", i32, vp, vp, vp, vp, u64, C.POINTER(vp), vp)
+    sig("b200_dtrie_create_dev", i32, vp, vp, vp, vp, u64, C.POINTER(vp), vp)
     sig("b200_dtrie_apply", i32, vp, vp, vp, vp, vp, u64, vp, PU, PU, PS)
     sig("b200_dtrie_root", i32, vp, vp)
     sig("b200_dtrie_leaves", u64, vp)

@@ -141,14 +141,13 @@ extern "C" B200_API int32_t b200_dtrie_root(b200_dtrie *t, uint8_t root32[32]) {
 }
 
 // Built with the level-synchronous builder (every digest comes from there), then converted: ids carry over.
-extern "C" B200_API int32_t b200_dtrie_create(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
-                                              const uint8_t *storage_roots32, uint64_t n, b200_dtrie **out,
-                                              uint8_t root32[32]) {
+static int32_t dtrie_create_common(b200_ctx *c, const void *acct_keys32, const void *accts, const void *storage_roots32,
+                                   uint64_t n, cudaMemcpyKind kind, b200_dtrie **out, void *root32) {
     if (!c || !out || (n && (!acct_keys32 || !accts))) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
     *out = nullptr;
     std::lock_guard<std::mutex> g(c->mu);
     b200_trie *src = nullptr;
-    TRY(trie_create_locked(c, acct_keys32, accts, storage_roots32, n, cudaMemcpyHostToDevice, &src, nullptr));
+    TRY(trie_create_locked(c, acct_keys32, accts, storage_roots32, n, kind, &src, nullptr));
     cudaStream_t st = c->stream;
     b200_dtrie *t = new b200_dtrie();
     t->c = c;
@@ -179,7 +178,9 @@ extern "C" B200_API int32_t b200_dtrie_create(b200_ctx *c, const uint8_t *acct_k
         CU(launch_dt_convert_nodes(src->f, B, static_cast<const uint32_t *>(src->node_parent.p), d, st));
         c->launches++;
         CU(cudaMemcpyAsync(t->root.p, src->root.p, 32, cudaMemcpyDeviceToDevice, st));
-        if (root32) CU(cudaMemcpyAsync(root32, t->root.p, 32, cudaMemcpyDeviceToHost, st));
+        if (root32)
+            CU(cudaMemcpyAsync(root32, t->root.p, 32,
+                               kind == cudaMemcpyHostToDevice ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
         CU(cudaStreamSynchronize(st));
         return B200_OK;
     };
@@ -191,6 +192,18 @@ extern "C" B200_API int32_t b200_dtrie_create(b200_ctx *c, const uint8_t *acct_k
     }
     *out = t;
     return B200_OK;
+}
+
+extern "C" B200_API int32_t b200_dtrie_create(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
+                                              const uint8_t *storage_roots32, uint64_t n, b200_dtrie **out,
+                                              uint8_t root32[32]) {
+    return dtrie_create_common(c, acct_keys32, accts, storage_roots32, n, cudaMemcpyHostToDevice, out, root32);
+}
+// inputs (and the optional root output) in device memory
+extern "C" B200_API int32_t b200_dtrie_create_dev(b200_ctx *c, const void *d_acct_keys32, const void *d_accts,
+                                                  const void *d_storage_roots32, uint64_t n, b200_dtrie **out,
+                                                  void *d_root32) {
+    return dtrie_create_common(c, d_acct_keys32, d_accts, d_storage_roots32, n, cudaMemcpyDeviceToDevice, out, d_root32);
 }
 
 // host copy of a device record set (same block layout as gather_and_copy)

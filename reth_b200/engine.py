@@ -404,6 +404,14 @@ class DynamicTrie:
                                                    C.byref(h), _ptr(root)))
         return cls(engine, h, root.tobytes())
 
+    @classmethod
+    def create_dev(cls, engine: Engine, t_keys, t_accts, t_sroots, n: int, t_root=None) -> "DynamicTrie":
+        h = C.c_void_p()
+        engine._check(engine.lib.b200_dtrie_create_dev(engine.ctx, t_keys.data_ptr(), t_accts.data_ptr(),
+                                                       t_sroots.data_ptr() if t_sroots is not None else None, n,
+                                                       C.byref(h), t_root.data_ptr() if t_root is not None else None))
+        return cls(engine, h, b"")
+
     def apply(self, keys, accounts, present=None, storage_roots32=None, want_updates=False, want_stats=False):
         """keys strictly ascending, present[i] False = delete.  -> root [, updated records, removed paths][, stats]."""
         keys = _np(keys).reshape(-1, 32)
