@@ -1,5 +1,6 @@
-// eng_dtrie.inl — dynamic resident trie (b200_dtrie_*): the account trie as an arena of 16-slot branch nodes in HBM that
-// takes a block's upserts and deletes in place and re-hashes only the touched paths (device side: tk_dtrie.cuh).
+// eng_dtrie.inl — dynamic resident tries (b200_dtrie_*: the account trie; b200_dstate_*: the account trie plus every
+// storage trie): arenas of 16-slot branch nodes in HBM that take a block's upserts and deletes in place and re-hash only
+// the touched paths (device side: tk_dtrie.cuh).
 // Part of the single translation unit engine.cu (textually included, in this order).
 
 struct IsKind {
@@ -7,209 +8,278 @@ struct IsKind {
     __host__ __device__ bool operator()(uint8_t x) const { return x == k; }
 };
 
-struct b200_dtrie {
+// One arena: the account trie (account = true, a single trie) or the forest of all storage tries (account = false, trie id
+// = id of the owning account leaf in the account arena).
+struct DArena {
     b200_ctx *c = nullptr;
-    bool has_sroots = false;
-    uint64_t bytes = 0;
-    uint32_t lcap = 0, ncap = 0;                         // capacities
+    uint64_t *bytes = nullptr;  // the owner's device-byte counter
+    bool account = true, has_sroots = false, forest = false;
+    uint32_t lcap = 0, ncap = 0, tcap = 0;                   // capacities: leaves, nodes, tries
     uint32_t leaf_alloc = 0, node_alloc = 0, n_leaves = 0;  // device counters as of the last apply
-    DevBuf lkey, lacct, lsroot, lref, lmeta, lparent, lseed;
-    DevBuf nchild, ndepth, nparent, nref, nmeta, nmasks, nkey, npending, nseed, ncur, nnext;
-    DevBuf leaf_free, node_free, g, root;
+    uint8_t *top_out = nullptr;                              // where finished tries put their root hash
+    uint32_t top_stride = 0;
+    DevBuf lkey, lval, lsroot, lref, lmeta, lparent, ltrie, lseed;
+    DevBuf nchild, ndepth, nparent, nref, nmeta, nmasks, nkey, npending, ntrie, nseed, ncur, nnext;
+    DevBuf troot, leaf_free, node_free, g;
     // per-apply scratch
-    DevBuf in_keys, in_accts, in_sroots, in_present, kind, leaf_of, list_a, list_b, ins_idx, attach, seeds, built, removed,
-        freed_now, flags, nh, sel, prefix, pick, out;
+    DevBuf kind, leaf_of, list_a, list_b, ins_idx, attach, seeds, built, removed, freed_now, flags, nh, sel, prefix, pick, out;
+    // outcome of the last apply
+    uint32_t n_built = 0, n_removed = 0;
+    uint32_t val_stride() const { return account ? 72u : 32u; }
 };
 
-static int32_t dt_resize(b200_dtrie *t, DevBuf &b, size_t new_bytes, size_t keep_bytes, bool zero_fill) {
-    b200_ctx *c = t->c;
+static int32_t da_resize(DArena *a, DevBuf &b, size_t new_bytes, size_t keep_bytes, int fill /* -1 none, else byte */) {
+    b200_ctx *c = a->c;
     if (new_bytes <= b.cap) return B200_OK;
     void *p = nullptr;
     size_t want = new_bytes + 256;
     CU(cudaMalloc(&p, want));
-    if (zero_fill) CU(cudaMemsetAsync(p, 0, want, c->stream));
+    if (fill >= 0) CU(cudaMemsetAsync(p, fill, want, c->stream));
     if (b.p && keep_bytes) CU(cudaMemcpyAsync(p, b.p, keep_bytes, cudaMemcpyDeviceToDevice, c->stream));
     if (b.p) {
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaFree(b.p));
-        t->bytes -= b.cap;
+        *a->bytes -= b.cap;
     }
     b.p = p;
     b.cap = want;
-    t->bytes += want;
+    *a->bytes += want;
     return B200_OK;
 }
-static int32_t dt_scratch(b200_dtrie *t, DevBuf &b, size_t bytes) { return dt_resize(t, b, bytes ? bytes : 16, 0, false); }
+static int32_t da_scratch(DArena *a, DevBuf &b, size_t bytes) { return da_resize(a, b, bytes ? bytes : 16, 0, -1); }
 
-// capacity for `leaves` leaf slots and `nodes` node slots, keeping the contents of the slots allocated so far
-static int32_t dt_reserve(b200_dtrie *t, uint64_t leaves, uint64_t nodes) {
-    b200_ctx *c = t->c;
-    if (leaves >= (1ull << 31) || nodes >= (1ull << 31)) return fail(c, B200_ERR_INVALID_ARG, "at most 2^31-1 leaves");
-    if (leaves > t->lcap) {
-        uint64_t cap = std::max<uint64_t>(leaves, (uint64_t)t->lcap + t->lcap / 2) + 1024;
-        size_t used = t->leaf_alloc;
-        TRY(dt_resize(t, t->lkey, cap * 32, used * 32, false));
-        TRY(dt_resize(t, t->lacct, cap * 72, used * 72, false));
-        if (t->has_sroots) TRY(dt_resize(t, t->lsroot, cap * 32, used * 32, false));
-        TRY(dt_resize(t, t->lref, cap * 32, used * 32, false));
-        TRY(dt_resize(t, t->lmeta, cap, used, false));
-        TRY(dt_resize(t, t->lparent, cap * 4, used * 4, false));
-        TRY(dt_resize(t, t->lseed, cap, used, true));
-        TRY(dt_resize(t, t->leaf_free, cap * 4, (size_t)t->lcap * 4, false));
-        t->lcap = (uint32_t)cap;
+// capacity for `leaves` leaf slots, `nodes` node slots and `tries` root words, keeping what is allocated so far
+static int32_t da_reserve(DArena *a, uint64_t leaves, uint64_t nodes, uint64_t tries) {
+    b200_ctx *c = a->c;
+    if (leaves >= (1ull << 31) || nodes >= (1ull << 31)) return fail(c, B200_ERR_INVALID_ARG, "at most 2^31-1 leaves per arena");
+    if (leaves > a->lcap) {
+        uint64_t cap = std::max<uint64_t>(leaves, (uint64_t)a->lcap + a->lcap / 2) + 1024;
+        size_t used = a->leaf_alloc, vs = a->val_stride();
+        TRY(da_resize(a, a->lkey, cap * 32, used * 32, -1));
+        TRY(da_resize(a, a->lval, cap * vs, used * vs, -1));
+        if (a->has_sroots) TRY(da_resize(a, a->lsroot, cap * 32, used * 32, -1));
+        TRY(da_resize(a, a->lref, cap * 32, used * 32, -1));
+        TRY(da_resize(a, a->lmeta, cap, used, -1));
+        TRY(da_resize(a, a->lparent, cap * 4, used * 4, -1));
+        if (a->forest) TRY(da_resize(a, a->ltrie, cap * 4, used * 4, -1));
+        TRY(da_resize(a, a->lseed, cap, used, 0));
+        TRY(da_resize(a, a->leaf_free, cap * 4, (size_t)a->lcap * 4, -1));
+        a->lcap = (uint32_t)cap;
     }
-    if (nodes > t->ncap) {
-        uint64_t cap = std::max<uint64_t>(nodes, (uint64_t)t->ncap + t->ncap / 2) + 1024;
-        size_t used = t->node_alloc;
-        TRY(dt_resize(t, t->nchild, cap * 64, used * 64, false));
-        TRY(dt_resize(t, t->ndepth, cap, used, false));
-        TRY(dt_resize(t, t->nparent, cap * 4, used * 4, false));
-        TRY(dt_resize(t, t->nref, cap * 32, used * 32, false));
-        TRY(dt_resize(t, t->nmeta, cap, used, false));
-        TRY(dt_resize(t, t->nmasks, cap * 8, used * 8, false));
-        TRY(dt_resize(t, t->nkey, cap * 32, used * 32, false));
-        TRY(dt_resize(t, t->npending, cap * 4, used * 4, true));
-        TRY(dt_resize(t, t->nseed, cap, used, true));
-        TRY(dt_resize(t, t->ncur, cap, used, true));
-        TRY(dt_resize(t, t->nnext, cap, used, true));
-        TRY(dt_resize(t, t->node_free, cap * 4, (size_t)t->ncap * 4, false));
-        t->ncap = (uint32_t)cap;
+    if (nodes > a->ncap) {
+        uint64_t cap = std::max<uint64_t>(nodes, (uint64_t)a->ncap + a->ncap / 2) + 1024;
+        size_t used = a->node_alloc;
+        TRY(da_resize(a, a->nchild, cap * 64, used * 64, -1));
+        TRY(da_resize(a, a->ndepth, cap, used, -1));
+        TRY(da_resize(a, a->nparent, cap * 4, used * 4, -1));
+        TRY(da_resize(a, a->nref, cap * 32, used * 32, -1));
+        TRY(da_resize(a, a->nmeta, cap, used, -1));
+        TRY(da_resize(a, a->nmasks, cap * 8, used * 8, -1));
+        TRY(da_resize(a, a->nkey, cap * 32, used * 32, -1));
+        TRY(da_resize(a, a->npending, cap * 4, used * 4, 0));
+        if (a->forest) TRY(da_resize(a, a->ntrie, cap * 4, used * 4, -1));
+        TRY(da_resize(a, a->nseed, cap, used, 0));
+        TRY(da_resize(a, a->ncur, cap, used, 0));
+        TRY(da_resize(a, a->nnext, cap, used, 0));
+        TRY(da_resize(a, a->node_free, cap * 4, (size_t)a->ncap * 4, -1));
+        a->ncap = (uint32_t)cap;
+    }
+    if (tries > a->tcap) {
+        uint64_t cap = std::max<uint64_t>(tries, (uint64_t)a->tcap + a->tcap / 2) + 16;
+        TRY(da_resize(a, a->troot, cap * 4, (size_t)a->tcap * 4, 0xFF));  // new tries are empty (DT_NONE)
+        a->tcap = (uint32_t)cap;
     }
     return B200_OK;
 }
 
-static DTrieDev dt_view(b200_dtrie *t) {
-    b200_ctx *c = t->c;
+static DTrieDev da_view(DArena *a) {
+    b200_ctx *c = a->c;
     DTrieDev d{};
-    d.lkey = static_cast<uint8_t *>(t->lkey.p);
-    d.lacct = static_cast<uint8_t *>(t->lacct.p);
-    d.lsroot = t->has_sroots ? static_cast<uint8_t *>(t->lsroot.p) : nullptr;
-    d.lref = static_cast<uint8_t *>(t->lref.p);
-    d.lmeta = static_cast<uint8_t *>(t->lmeta.p);
-    d.lparent = static_cast<uint32_t *>(t->lparent.p);
-    d.lseed = static_cast<uint8_t *>(t->lseed.p);
-    d.nchild = static_cast<uint32_t *>(t->nchild.p);
-    d.ndepth = static_cast<uint8_t *>(t->ndepth.p);
-    d.nparent = static_cast<uint32_t *>(t->nparent.p);
-    d.nref = static_cast<uint8_t *>(t->nref.p);
-    d.nmeta = static_cast<uint8_t *>(t->nmeta.p);
-    d.nmasks = static_cast<ushort4 *>(t->nmasks.p);
-    d.nkey = static_cast<uint8_t *>(t->nkey.p);
-    d.npending = static_cast<uint32_t *>(t->npending.p);
-    d.nseed = static_cast<uint8_t *>(t->nseed.p);
-    d.ncur = static_cast<uint8_t *>(t->ncur.p);
-    d.nnext = static_cast<uint8_t *>(t->nnext.p);
-    d.leaf_free = static_cast<uint32_t *>(t->leaf_free.p);
-    d.node_free = static_cast<uint32_t *>(t->node_free.p);
-    d.seeds = static_cast<uint32_t *>(t->seeds.p);
-    d.built = static_cast<uint32_t *>(t->built.p);
-    d.removed = static_cast<uint32_t *>(t->removed.p);
-    d.freed_now = static_cast<uint32_t *>(t->freed_now.p);
-    d.g = static_cast<uint32_t *>(t->g.p);
+    d.lkey = static_cast<uint8_t *>(a->lkey.p);
+    d.lval = static_cast<uint8_t *>(a->lval.p);
+    d.lsroot = a->has_sroots ? static_cast<uint8_t *>(a->lsroot.p) : nullptr;
+    d.lref = static_cast<uint8_t *>(a->lref.p);
+    d.lmeta = static_cast<uint8_t *>(a->lmeta.p);
+    d.lparent = static_cast<uint32_t *>(a->lparent.p);
+    d.ltrie = a->forest ? static_cast<uint32_t *>(a->ltrie.p) : nullptr;
+    d.lseed = static_cast<uint8_t *>(a->lseed.p);
+    d.nchild = static_cast<uint32_t *>(a->nchild.p);
+    d.ndepth = static_cast<uint8_t *>(a->ndepth.p);
+    d.nparent = static_cast<uint32_t *>(a->nparent.p);
+    d.nref = static_cast<uint8_t *>(a->nref.p);
+    d.nmeta = static_cast<uint8_t *>(a->nmeta.p);
+    d.nmasks = static_cast<ushort4 *>(a->nmasks.p);
+    d.nkey = static_cast<uint8_t *>(a->nkey.p);
+    d.npending = static_cast<uint32_t *>(a->npending.p);
+    d.ntrie = a->forest ? static_cast<uint32_t *>(a->ntrie.p) : nullptr;
+    d.nseed = static_cast<uint8_t *>(a->nseed.p);
+    d.ncur = static_cast<uint8_t *>(a->ncur.p);
+    d.nnext = static_cast<uint8_t *>(a->nnext.p);
+    d.troot = static_cast<uint32_t *>(a->troot.p);
+    d.top_out = a->top_out;
+    d.top_stride = a->top_stride;
+    d.val_stride = a->val_stride();
+    d.account = a->account ? 1 : 0;
+    d.leaf_free = static_cast<uint32_t *>(a->leaf_free.p);
+    d.node_free = static_cast<uint32_t *>(a->node_free.p);
+    d.seeds = static_cast<uint32_t *>(a->seeds.p);
+    d.built = static_cast<uint32_t *>(a->built.p);
+    d.removed = static_cast<uint32_t *>(a->removed.p);
+    d.freed_now = static_cast<uint32_t *>(a->freed_now.p);
+    d.g = static_cast<uint32_t *>(a->g.p);
     d.err = reinterpret_cast<int *>(small_u32(c) + SM_ERR);
     d.counters = reinterpret_cast<unsigned long long *>(small_u32(c) + SM_COUNTERS);
-    d.lcap = t->lcap;
-    d.ncap = t->ncap;
+    d.lcap = a->lcap;
+    d.ncap = a->ncap;
     return d;
 }
 
-extern "C" B200_API void b200_dtrie_destroy(b200_dtrie *t) {
-    if (!t) return;
-    cudaSetDevice(t->c->device);
-    cudaStreamSynchronize(t->c->stream);
-    DevBuf *bufs[] = {&t->lkey, &t->lacct, &t->lsroot, &t->lref, &t->lmeta, &t->lparent, &t->lseed, &t->nchild, &t->ndepth,
-                      &t->nparent, &t->nref, &t->nmeta, &t->nmasks, &t->nkey, &t->npending, &t->nseed, &t->ncur, &t->nnext,
-                      &t->leaf_free, &t->node_free, &t->g, &t->root, &t->in_keys, &t->in_accts, &t->in_sroots, &t->in_present,
-                      &t->kind, &t->leaf_of, &t->list_a, &t->list_b, &t->ins_idx, &t->attach, &t->seeds, &t->built, &t->removed,
-                      &t->freed_now, &t->flags, &t->nh, &t->sel, &t->prefix, &t->pick, &t->out};
+static void da_free(DArena *a) {
+    DevBuf *bufs[] = {&a->lkey, &a->lval, &a->lsroot, &a->lref, &a->lmeta, &a->lparent, &a->ltrie, &a->lseed, &a->nchild,
+                      &a->ndepth, &a->nparent, &a->nref, &a->nmeta, &a->nmasks, &a->nkey, &a->npending, &a->ntrie, &a->nseed,
+                      &a->ncur, &a->nnext, &a->troot, &a->leaf_free, &a->node_free, &a->g, &a->kind, &a->leaf_of, &a->list_a,
+                      &a->list_b, &a->ins_idx, &a->attach, &a->seeds, &a->built, &a->removed, &a->freed_now, &a->flags, &a->nh,
+                      &a->sel, &a->prefix, &a->pick, &a->out};
     for (DevBuf *b : bufs)
-        if (b->p) cudaFree(b->p);
-    delete t;
-}
-extern "C" B200_API uint64_t b200_dtrie_device_bytes(const b200_dtrie *t) { return t ? t->bytes : 0; }
-extern "C" B200_API uint64_t b200_dtrie_leaves(const b200_dtrie *t) { return t ? t->n_leaves : 0; }
-extern "C" B200_API uint64_t b200_dtrie_nodes(const b200_dtrie *t) { return t ? t->node_alloc : 0; }
-
-extern "C" B200_API int32_t b200_dtrie_root(b200_dtrie *t, uint8_t root32[32]) {
-    if (!t || !root32) return fail(t ? t->c : nullptr, B200_ERR_INVALID_ARG, "bad argument");
-    b200_ctx *c = t->c;
-    std::lock_guard<std::mutex> g(c->mu);
-    CU(cudaSetDevice(c->device));
-    CU(cudaMemcpyAsync(root32, t->root.p, 32, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    return B200_OK;
-}
-
-// Built with the level-synchronous builder (every digest comes from there), then converted: ids carry over.
-static int32_t dtrie_create_common(b200_ctx *c, const void *acct_keys32, const void *accts, const void *storage_roots32,
-                                   uint64_t n, cudaMemcpyKind kind, b200_dtrie **out, void *root32) {
-    if (!c || !out || (n && (!acct_keys32 || !accts))) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
-    *out = nullptr;
-    std::lock_guard<std::mutex> g(c->mu);
-    b200_trie *src = nullptr;
-    TRY(trie_create_locked(c, acct_keys32, accts, storage_roots32, n, kind, &src, nullptr));
-    cudaStream_t st = c->stream;
-    b200_dtrie *t = new b200_dtrie();
-    t->c = c;
-    t->has_sroots = storage_roots32 != nullptr;
-    auto body = [&]() -> int32_t {
-        const uint32_t B = src->B;
-        TRY(dt_reserve(t, n + n / 8 + 16, (uint64_t)B + B / 8 + 16));
-        TRY(dt_resize(t, t->g, DG_WORDS * 4, 0, true));
-        TRY(dt_resize(t, t->root, 64, 0, false));
-        if (n) {
-            CU(cudaMemcpyAsync(t->lkey.p, src->keys.p, n * 32, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(t->lacct.p, src->accts.p, n * 72, cudaMemcpyDeviceToDevice, st));
-            if (t->has_sroots) CU(cudaMemcpyAsync(t->lsroot.p, src->sroots.p, n * 32, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(t->lref.p, src->leaf_ref.p, n * 32, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(t->lmeta.p, src->leaf_meta.p, n, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemcpyAsync(t->lparent.p, src->leaf_parent.p, n * 4, cudaMemcpyDeviceToDevice, st));
+        if (b->p) {
+            cudaFree(b->p);
+            *b = DevBuf{};
         }
-        uint32_t *ps = static_cast<uint32_t *>(c->pinned_small) + 256;  // 64 words of the readback page
-        memset(ps, 0, DG_WORDS * 4);
-        ps[DG_ROOT] = n == 1 ? (0u | DT_LEAF) : DT_NONE;  // n >= 2: the convert kernel writes the root node's id
-        ps[DG_NLEAVES] = (uint32_t)n;
-        ps[DG_LEAF_ALLOC] = (uint32_t)n;
-        ps[DG_NODE_ALLOC] = B;
-        CU(cudaMemcpyAsync(t->g.p, ps, DG_WORDS * 4, cudaMemcpyHostToDevice, st));
-        t->leaf_alloc = t->n_leaves = (uint32_t)n;
-        t->node_alloc = B;
-        DTrieDev d = dt_view(t);
-        CU(launch_dt_convert_nodes(src->f, B, static_cast<const uint32_t *>(src->node_parent.p), d, st));
-        c->launches++;
-        CU(cudaMemcpyAsync(t->root.p, src->root.p, 32, cudaMemcpyDeviceToDevice, st));
-        if (root32)
-            CU(cudaMemcpyAsync(root32, t->root.p, 32,
-                               kind == cudaMemcpyHostToDevice ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
-        CU(cudaStreamSynchronize(st));
-        return B200_OK;
-    };
-    int32_t r = body();
-    b200_trie_destroy(src);
-    if (r != B200_OK) {
-        b200_dtrie_destroy(t);
-        return r;
+}
+
+// Fills the arena from a finished resident build (`src`: the account trie, or a storage forest with its segment table).
+// top_out / top_stride must be set.  Synchronises.
+static int32_t da_from_build(DArena *a, b200_trie *src, uint64_t min_tries) {
+    b200_ctx *c = a->c;
+    cudaStream_t st = c->stream;
+    const uint64_t n = src->n;
+    const uint32_t B = src->B;
+    const uint64_t n_tries = a->forest ? std::max<uint64_t>(src->n_segs, min_tries) : 1;
+    TRY(da_reserve(a, n + n / 8 + 16, (uint64_t)B + B / 8 + 16, n_tries));
+    TRY(da_resize(a, a->g, DG_WORDS * 4, 0, 0));
+    if (n) {
+        CU(cudaMemcpyAsync(a->lkey.p, src->keys.p, n * 32, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(a->lval.p, src->accts.p, n * a->val_stride(), cudaMemcpyDeviceToDevice, st));
+        if (a->has_sroots) CU(cudaMemcpyAsync(a->lsroot.p, src->sroots.p, n * 32, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(a->lref.p, src->leaf_ref.p, n * 32, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(a->lmeta.p, src->leaf_meta.p, n, cudaMemcpyDeviceToDevice, st));
     }
-    *out = t;
+    uint32_t *ps = static_cast<uint32_t *>(c->pinned_small) + 256;  // 64 words of the readback page
+    memset(ps, 0, DG_WORDS * 4);
+    ps[DG_NLEAVES] = (uint32_t)n;
+    ps[DG_LEAF_ALLOC] = (uint32_t)n;
+    ps[DG_NODE_ALLOC] = B;
+    CU(cudaMemcpyAsync(a->g.p, ps, DG_WORDS * 4, cudaMemcpyHostToDevice, st));
+    a->leaf_alloc = a->n_leaves = (uint32_t)n;
+    a->node_alloc = B;
+    const uint32_t *leaf_trie = nullptr;
+    if (a->forest && n) {
+        TRY(da_scratch(a, a->leaf_of, n * 4));
+        CU(launch_dt_leaf_segments(static_cast<const uint64_t *>(src->seg_offsets.p), src->n_segs, n,
+                                   static_cast<uint32_t *>(a->leaf_of.p), st));
+        leaf_trie = static_cast<const uint32_t *>(a->leaf_of.p);
+        c->launches++;
+    }
+    DTrieDev d = da_view(a);
+    CU(launch_dt_convert(src->f, B, static_cast<const uint32_t *>(src->leaf_parent.p),
+                         static_cast<const uint32_t *>(src->node_parent.p), leaf_trie, d, st));
+    c->launches += 2;
+    CU(cudaStreamSynchronize(st));
     return B200_OK;
 }
 
-extern "C" B200_API int32_t b200_dtrie_create(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
-                                              const uint8_t *storage_roots32, uint64_t n, b200_dtrie **out,
-                                              uint8_t root32[32]) {
-    return dtrie_create_common(c, acct_keys32, accts, storage_roots32, n, cudaMemcpyHostToDevice, out, root32);
-}
-// inputs (and the optional root output) in device memory
-extern "C" B200_API int32_t b200_dtrie_create_dev(b200_ctx *c, const void *d_acct_keys32, const void *d_accts,
-                                                  const void *d_storage_roots32, uint64_t n, b200_dtrie **out,
-                                                  void *d_root32) {
-    return dtrie_create_common(c, d_acct_keys32, d_accts, d_storage_roots32, n, cudaMemcpyDeviceToDevice, out, d_root32);
+// ------------------------------------------------------------------------------------------------ one arena, one block
+// Structural part of an apply: classify the m dirty entries, write value updates, detach deleted leaves, collapse, insert.
+// Leaves the seeds in the arena; leaf_of[i] afterwards holds the leaf of every entry that exists (updated, touched or
+// inserted), DT_NONE otherwise.  Every pointer is a device pointer.
+static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const uint8_t *d_keys, const uint8_t *d_vals,
+                              const uint8_t *d_flags, const uint8_t *d_sroots, uint64_t m) {
+    b200_ctx *c = a->c;
+    cudaStream_t st = c->stream;
+    // every insert may take one leaf slot and one node slot from the bump region
+    TRY(da_reserve(a, (uint64_t)a->leaf_alloc + m, (uint64_t)a->node_alloc + m, a->tcap));
+    const uint32_t max_list = (uint32_t)m + 16, max_seeds = (uint32_t)(6 * m + 64);
+    const uint32_t max_built = (uint32_t)(std::min<uint64_t>((uint64_t)max_seeds * 64, (uint64_t)a->node_alloc + m) + 16);
+    TRY(da_scratch(a, a->kind, m));
+    TRY(da_scratch(a, a->leaf_of, m * 4));
+    TRY(da_scratch(a, a->list_a, (size_t)max_list * 4));
+    TRY(da_scratch(a, a->list_b, (size_t)max_list * 4));
+    TRY(da_scratch(a, a->ins_idx, m * 4));
+    TRY(da_scratch(a, a->attach, m * 8));
+    TRY(da_scratch(a, a->seeds, (size_t)max_seeds * 4));
+    TRY(da_scratch(a, a->built, (size_t)max_built * 4));
+    TRY(da_scratch(a, a->removed, ((size_t)max_built + max_list) * 4));
+    TRY(da_scratch(a, a->freed_now, (size_t)max_list * 4));
+    TRY(da_scratch(a, a->flags, max_list));  // per-entry defer flags of a collapse round (re-used for the output flags)
+    DTrieDev d = da_view(a);
+    uint8_t *kind = static_cast<uint8_t *>(a->kind.p);
+    uint32_t *leaf_of = static_cast<uint32_t *>(a->leaf_of.p);
+    CU(cudaMemsetAsync(d.g + DG_SEEDS, 0, (DG_WORDS - DG_SEEDS) * 4, st));  // the per-apply list lengths
+    // ---- locate, value updates, detach deleted leaves
+    CU(launch_dt_locate(d, d_trie_of_key, d_keys, d_vals, d_flags, m, kind, leaf_of, st));
+    uint32_t *list_cur = static_cast<uint32_t *>(a->list_a.p), *list_next = static_cast<uint32_t *>(a->list_b.p);
+    uint32_t *cnt_cur = d.g + DG_LIST_A, *cnt_next = d.g + DG_LIST_B;
+    CU(launch_dt_update_detach(d, d_vals, d_sroots, m, kind, leaf_of, list_cur, st));
+    c->launches += 2;
+    // ---- collapse rounds until no node is left that lost children
+    uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
+    for (int round = 0;; round++) {
+        CU(cudaMemcpyAsync(ps + 200, cnt_cur, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ps + 201, small_u32(c) + SM_ERR, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (ps[201] != B200_DEVERR_NONE) return map_dev_error(c, (int)ps[201]);
+        if (ps[200] == 0) break;
+        if (round > 200) return fail(c, B200_ERR_CUDA, "collapse rounds do not converge");
+        CU(cudaMemsetAsync(cnt_next, 0, 4, st));
+        CU(launch_dt_collapse_round(d, list_cur, cnt_cur, ps[200], static_cast<uint8_t *>(a->flags.p), list_next, cnt_next, st));
+        c->launches += 4;
+        std::swap(list_cur, list_next);
+        std::swap(cnt_cur, cnt_next);
+    }
+    // ---- inserts: the dense list of insert entries, their attach points, one thread per run
+    uint32_t *ins_idx = static_cast<uint32_t *>(a->ins_idx.p);
+    thrust::counting_iterator<uint32_t> counting(0);
+    auto is_insert = thrust::make_transform_iterator(kind, IsKind{DK_INSERT});
+    size_t t_sel = 0;
+    CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, is_insert, ins_idx, d.g + DG_NINSERT, (int64_t)m, st));
+    ENSURE(cub_temp, t_sel);
+    CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, is_insert, ins_idx, d.g + DG_NINSERT, (int64_t)m, st));
+    CU(launch_dt_insert(d, d_trie_of_key, d_keys, d_vals, d_sroots, ins_idx, d.g + DG_NINSERT, m,
+                        static_cast<uint64_t *>(a->attach.p), leaf_of, st));
+    c->launches += 3;
+    return B200_OK;
 }
 
-// host copy of a device record set (same block layout as gather_and_copy)
-static int32_t dt_collect_updates(b200_dtrie *t, const DTrieDev &d, uint32_t n_built, b200_updates *u) {
-    b200_ctx *c = t->c;
+// re-hash of the seeded paths, recycling of the freed nodes (asynchronous)
+static int32_t da_rehash(DArena *a, uint64_t m) {
+    b200_ctx *c = a->c;
+    DTrieDev d = da_view(a);
+    CU(launch_dt_rehash(d, (uint32_t)(6 * m + 64), c->stream));
+    CU(launch_dt_finish(d, (uint32_t)m + 16, c->stream));
+    c->launches += 5;
+    return B200_OK;
+}
+
+// device counters -> host mirror (after a synchronisation point that covers the copy)
+static int32_t da_pull_counters(DArena *a, uint32_t *pinned64) {
+    b200_ctx *c = a->c;
+    CU(cudaMemcpyAsync(pinned64, a->g.p, DG_WORDS * 4, cudaMemcpyDeviceToHost, c->stream));
+    return B200_OK;
+}
+static void da_take_counters(DArena *a, const uint32_t *pinned64) {
+    a->n_leaves = pinned64[DG_NLEAVES];
+    a->leaf_alloc = pinned64[DG_LEAF_ALLOC];
+    a->node_alloc = pinned64[DG_NODE_ALLOC];
+    a->n_built = pinned64[DG_BUILT];
+    a->n_removed = pinned64[DG_REMOVED];
+}
+
+// host copy of the re-hashed stored nodes (same block layout as gather_and_copy)
+static int32_t da_collect_updates(DArena *a, b200_updates *u) {
+    b200_ctx *c = a->c;
     cudaStream_t st = c->stream;
+    const uint32_t n_built = a->n_built;
+    DTrieDev d = da_view(a);
     memset(u, 0, sizeof *u);
     UpdatesOwner *owner = new UpdatesOwner();
     u->_owner = owner;
@@ -217,15 +287,15 @@ static int32_t dt_collect_updates(b200_dtrie *t, const DTrieDev &d, uint32_t n_b
     uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
     const uint32_t *pick_ids = nullptr, *pick_prefix = nullptr;
     if (n_built) {
-        TRY(dt_scratch(t, t->flags, n_built));
-        TRY(dt_scratch(t, t->nh, (size_t)n_built * 4));
-        TRY(dt_scratch(t, t->sel, (size_t)n_built * 4));
-        TRY(dt_scratch(t, t->prefix, ((size_t)n_built + 1) * 4));
-        TRY(dt_scratch(t, t->pick, (size_t)n_built * 8));
-        uint8_t *flags = static_cast<uint8_t *>(t->flags.p);
-        uint32_t *nh = static_cast<uint32_t *>(t->nh.p), *sel = static_cast<uint32_t *>(t->sel.p);
-        uint32_t *prefix = static_cast<uint32_t *>(t->prefix.p);
-        uint32_t *ids = static_cast<uint32_t *>(t->pick.p), *pref = ids + n_built;
+        TRY(da_scratch(a, a->flags, n_built));
+        TRY(da_scratch(a, a->nh, (size_t)n_built * 4));
+        TRY(da_scratch(a, a->sel, (size_t)n_built * 4));
+        TRY(da_scratch(a, a->prefix, ((size_t)n_built + 1) * 4));
+        TRY(da_scratch(a, a->pick, (size_t)n_built * 8));
+        uint8_t *flags = static_cast<uint8_t *>(a->flags.p);
+        uint32_t *nh = static_cast<uint32_t *>(a->nh.p), *sel = static_cast<uint32_t *>(a->sel.p);
+        uint32_t *prefix = static_cast<uint32_t *>(a->prefix.p);
+        uint32_t *ids = static_cast<uint32_t *>(a->pick.p), *pref = ids + n_built;
         uint32_t *n_stored_p = small_u32(c) + SM_NSTORED;
         CU(launch_dt_stored_flags(d, n_built, flags, nh, st));
         size_t t_sel = 0, t_scan = 0;
@@ -269,8 +339,8 @@ static int32_t dt_collect_updates(b200_dtrie *t, const DTrieDev &d, uint32_t n_b
     u->hashes = h + o_hash;
     u->hash_offset = reinterpret_cast<uint64_t *>(h + o_ho64);
     if (n_stored) {
-        TRY(dt_scratch(t, t->out, dev_total));
-        uint8_t *dv = static_cast<uint8_t *>(t->out.p);
+        TRY(da_scratch(a, a->out, dev_total));
+        uint8_t *dv = static_cast<uint8_t *>(a->out.p);
         UpdatesDev ud;
         ud.trie_id = reinterpret_cast<uint32_t *>(dv + o_tid);
         ud.path_len = dv + o_plen;
@@ -291,27 +361,27 @@ static int32_t dt_collect_updates(b200_dtrie *t, const DTrieDev &d, uint32_t n_b
     return B200_OK;
 }
 
-// removed_nodes as records without masks or hashes; paths that are also in `updated` are dropped (updated nodes take
-// precedence over removed ones, crates/trie/common/src/updates.rs:160-167)
-static int32_t dt_collect_removed(b200_dtrie *t, const DTrieDev &d, uint32_t n_removed, const b200_updates *updated,
-                                  b200_updates *u) {
-    b200_ctx *c = t->c;
+// removed_nodes as records without masks or hashes; paths that are also in `updated` (same trie) are dropped: updated
+// nodes take precedence over removed ones (crates/trie/common/src/updates.rs:160-167)
+static int32_t da_collect_removed(DArena *a, const b200_updates *updated, b200_updates *u) {
+    b200_ctx *c = a->c;
     cudaStream_t st = c->stream;
+    DTrieDev d = da_view(a);
     memset(u, 0, sizeof *u);
     UpdatesOwner *owner = new UpdatesOwner();
     u->_owner = owner;
-    size_t n = n_removed;
+    const size_t n = a->n_removed;
     size_t o_len = 0, o_path = align_up(n, 16), o_tid = align_up(o_path + n * 32, 16), o_masks = align_up(o_tid + n * 4, 16),
            o_ho = align_up(o_masks + n * 2, 16), total = o_ho + (n + 1) * 8;
     CU(cudaMallocHost(&owner->host, total));
     uint8_t *h = static_cast<uint8_t *>(owner->host);
     memset(h, 0, total);
     if (n) {
-        TRY(dt_scratch(t, t->out, o_tid));
-        uint8_t *dv = static_cast<uint8_t *>(t->out.p);
-        CU(launch_dt_removed_paths(d, n_removed, dv + o_len, dv + o_path, st));
+        TRY(da_scratch(a, a->out, o_masks));
+        uint8_t *dv = static_cast<uint8_t *>(a->out.p);
+        CU(launch_dt_removed_paths(d, (uint32_t)n, dv + o_len, dv + o_path, reinterpret_cast<uint32_t *>(dv + o_tid), st));
         c->launches++;
-        CU(cudaMemcpyAsync(h, dv, o_tid, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h, dv, o_masks, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     u->path_len = h + o_len;
@@ -320,25 +390,126 @@ static int32_t dt_collect_removed(b200_dtrie *t, const DTrieDev &d, uint32_t n_r
     u->state_mask = u->tree_mask = u->hash_mask = reinterpret_cast<uint16_t *>(h + o_masks);  // all zero
     u->hash_offset = reinterpret_cast<uint64_t *>(h + o_ho);                                     // all zero
     u->hashes = h;
-    // updated nodes take precedence; a path can be recorded once only, but sort + unique keeps this independent of that
-    auto key_of = [](const uint8_t *packed, uint8_t len) { return std::string(reinterpret_cast<const char *>(packed), 32) + (char)len; };
+    auto key_of = [](uint32_t trie, const uint8_t *packed, uint8_t len) {
+        std::string k(reinterpret_cast<const char *>(&trie), 4);
+        k.append(reinterpret_cast<const char *>(packed), 32);
+        k.push_back((char)len);
+        return k;
+    };
     std::vector<std::string> upd, rem;
     if (updated)
-        for (uint64_t i = 0; i < updated->n_nodes; i++) upd.push_back(key_of(updated->path_packed + 32 * i, updated->path_len[i]));
+        for (uint64_t i = 0; i < updated->n_nodes; i++)
+            upd.push_back(key_of(updated->trie_id[i], updated->path_packed + 32 * i, updated->path_len[i]));
     std::sort(upd.begin(), upd.end());
     for (size_t i = 0; i < n; i++) {
-        std::string k = key_of(u->path_packed + 32 * i, u->path_len[i]);
+        std::string k = key_of(u->trie_id[i], u->path_packed + 32 * i, u->path_len[i]);
         if (!std::binary_search(upd.begin(), upd.end(), k)) rem.push_back(std::move(k));
     }
     std::sort(rem.begin(), rem.end());
     rem.erase(std::unique(rem.begin(), rem.end()), rem.end());
     size_t w = 0;
     for (const std::string &k : rem) {
-        memcpy(u->path_packed + 32 * w, k.data(), 32);
-        u->path_len[w] = (uint8_t)k[32];
+        memcpy(&u->trie_id[w], k.data(), 4);
+        memcpy(u->path_packed + 32 * w, k.data() + 4, 32);
+        u->path_len[w] = (uint8_t)k[36];
         w++;
     }
     u->n_nodes = w;
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ b200_dtrie: accounts only
+struct b200_dtrie {
+    b200_ctx *c = nullptr;
+    uint64_t bytes = 0;
+    DArena a;
+    DevBuf root, in_keys, in_accts, in_sroots, in_present;
+};
+
+static void dbuf_free(DevBuf &b) {
+    if (b.p) cudaFree(b.p);
+    b = DevBuf{};
+}
+
+extern "C" B200_API void b200_dtrie_destroy(b200_dtrie *t) {
+    if (!t) return;
+    cudaSetDevice(t->c->device);
+    cudaStreamSynchronize(t->c->stream);
+    da_free(&t->a);
+    dbuf_free(t->root);
+    dbuf_free(t->in_keys);
+    dbuf_free(t->in_accts);
+    dbuf_free(t->in_sroots);
+    dbuf_free(t->in_present);
+    delete t;
+}
+extern "C" B200_API uint64_t b200_dtrie_device_bytes(const b200_dtrie *t) { return t ? t->bytes : 0; }
+extern "C" B200_API uint64_t b200_dtrie_leaves(const b200_dtrie *t) { return t ? t->a.n_leaves : 0; }
+extern "C" B200_API uint64_t b200_dtrie_nodes(const b200_dtrie *t) { return t ? t->a.node_alloc : 0; }
+
+extern "C" B200_API int32_t b200_dtrie_root(b200_dtrie *t, uint8_t root32[32]) {
+    if (!t || !root32) return fail(t ? t->c : nullptr, B200_ERR_INVALID_ARG, "bad argument");
+    b200_ctx *c = t->c;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(root32, t->root.p, 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B200_OK;
+}
+
+// Built with the level-synchronous builder (every digest comes from there), then converted: ids carry over.
+static int32_t dtrie_create_common(b200_ctx *c, const void *acct_keys32, const void *accts, const void *storage_roots32,
+                                   uint64_t n, cudaMemcpyKind kind, b200_dtrie **out, void *root32) {
+    if (!c || !out || (n && (!acct_keys32 || !accts))) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(c->mu);
+    b200_trie *src = nullptr;
+    TRY(trie_create_locked(c, acct_keys32, accts, storage_roots32, n, kind, &src, nullptr));
+    cudaStream_t st = c->stream;
+    b200_dtrie *t = new b200_dtrie();
+    t->c = c;
+    t->a.c = c;
+    t->a.bytes = &t->bytes;
+    t->a.account = true;
+    t->a.has_sroots = storage_roots32 != nullptr;
+    auto body = [&]() -> int32_t {
+        TRY(da_resize(&t->a, t->root, 64, 0, -1));
+        t->a.top_out = static_cast<uint8_t *>(t->root.p);
+        t->a.top_stride = 0;
+        TRY(da_from_build(&t->a, src, 1));
+        CU(cudaMemcpyAsync(t->root.p, src->root.p, 32, cudaMemcpyDeviceToDevice, st));
+        if (root32)
+            CU(cudaMemcpyAsync(root32, t->root.p, 32,
+                               kind == cudaMemcpyHostToDevice ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        return B200_OK;
+    };
+    int32_t r = body();
+    b200_trie_destroy(src);
+    if (r != B200_OK) {
+        b200_dtrie_destroy(t);
+        return r;
+    }
+    *out = t;
+    return B200_OK;
+}
+
+extern "C" B200_API int32_t b200_dtrie_create(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
+                                              const uint8_t *storage_roots32, uint64_t n, b200_dtrie **out,
+                                              uint8_t root32[32]) {
+    return dtrie_create_common(c, acct_keys32, accts, storage_roots32, n, cudaMemcpyHostToDevice, out, root32);
+}
+// inputs (and the optional root output) in device memory
+extern "C" B200_API int32_t b200_dtrie_create_dev(b200_ctx *c, const void *d_acct_keys32, const void *d_accts,
+                                                  const void *d_storage_roots32, uint64_t n, b200_dtrie **out,
+                                                  void *d_root32) {
+    return dtrie_create_common(c, d_acct_keys32, d_accts, d_storage_roots32, n, cudaMemcpyDeviceToDevice, out, d_root32);
+}
+
+static int32_t h2d_into(DArena *a, DevBuf &b, const void *src, size_t bytes) {
+    b200_ctx *c = a->c;
+    TRY(da_scratch(a, b, bytes));
+    if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
     return B200_OK;
 }
 
@@ -357,113 +528,39 @@ extern "C" B200_API int32_t b200_dtrie_apply(b200_dtrie *t, const uint8_t *keys3
     std::lock_guard<std::mutex> lock(c->mu);
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
-    if (storage_roots32 && !t->has_sroots) return fail(c, B200_ERR_INVALID_ARG, "trie was created without storage roots");
+    DArena *a = &t->a;
+    if (storage_roots32 && !a->has_sroots) return fail(c, B200_ERR_INVALID_ARG, "trie was created without storage roots");
     TRY(reset_build_state(c));
-    uint32_t n_built = 0, n_removed = 0;
+    a->n_built = a->n_removed = 0;
     if (m) {
-        // every insert may take one leaf slot and one node slot from the bump region
-        TRY(dt_reserve(t, (uint64_t)t->leaf_alloc + m, (uint64_t)t->node_alloc + m));
-        const uint32_t max_list = (uint32_t)m + 16, max_seeds = (uint32_t)(6 * m + 64);
-        const uint64_t max_built64 = std::min<uint64_t>((uint64_t)max_seeds * 64, (uint64_t)t->node_alloc + m) + 16;
-        const uint32_t max_built = (uint32_t)max_built64;
-        TRY(dt_scratch(t, t->in_keys, m * 32));
-        TRY(dt_scratch(t, t->in_accts, m * 72));
-        TRY(dt_scratch(t, t->kind, m));
-        TRY(dt_scratch(t, t->leaf_of, m * 4));
-        TRY(dt_scratch(t, t->list_a, (size_t)max_list * 4));
-        TRY(dt_scratch(t, t->list_b, (size_t)max_list * 4));
-        TRY(dt_scratch(t, t->ins_idx, m * 4));
-        TRY(dt_scratch(t, t->attach, m * 8));
-        TRY(dt_scratch(t, t->seeds, (size_t)max_seeds * 4));
-        TRY(dt_scratch(t, t->built, (size_t)max_built * 4));
-        TRY(dt_scratch(t, t->removed, ((size_t)max_built + max_list) * 4));
-        TRY(dt_scratch(t, t->freed_now, (size_t)max_list * 4));
-        TRY(dt_scratch(t, t->flags, max_list));  // per-entry defer flags of a collapse round (re-used for the output flags)
-        CU(cudaMemcpyAsync(t->in_keys.p, keys32, m * 32, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(t->in_accts.p, accts, m * 72, cudaMemcpyHostToDevice, st));
-        const uint8_t *d_present = nullptr, *d_sroots = nullptr;
-        if (present) {
-            TRY(dt_scratch(t, t->in_present, m));
-            CU(cudaMemcpyAsync(t->in_present.p, present, m, cudaMemcpyHostToDevice, st));
-            d_present = static_cast<const uint8_t *>(t->in_present.p);
-        }
-        if (storage_roots32) {
-            TRY(dt_scratch(t, t->in_sroots, m * 32));
-            CU(cudaMemcpyAsync(t->in_sroots.p, storage_roots32, m * 32, cudaMemcpyHostToDevice, st));
-            d_sroots = static_cast<const uint8_t *>(t->in_sroots.p);
-        }
-        DTrieDev d = dt_view(t);
-        const uint8_t *d_keys = static_cast<const uint8_t *>(t->in_keys.p), *d_accts = static_cast<const uint8_t *>(t->in_accts.p);
-        uint8_t *kind = static_cast<uint8_t *>(t->kind.p);
-        uint32_t *leaf_of = static_cast<uint32_t *>(t->leaf_of.p);
-        CU(cudaMemsetAsync(d.g + DG_SEEDS, 0, (DG_WORDS - DG_SEEDS) * 4, st));  // the per-apply list lengths
-        // ---- locate, value updates, detach deleted leaves
-        CU(launch_dt_locate(d, d_keys, d_present, m, kind, leaf_of, st));
-        uint32_t *list_cur = static_cast<uint32_t *>(t->list_a.p), *list_next = static_cast<uint32_t *>(t->list_b.p);
-        uint32_t *cnt_cur = d.g + DG_LIST_A, *cnt_next = d.g + DG_LIST_B;
-        CU(launch_dt_update_detach(d, d_accts, d_sroots, m, kind, leaf_of, list_cur, st));
-        c->launches += 2;
-        // ---- collapse rounds until no node is left that lost children
-        uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
-        for (int round = 0;; round++) {
-            CU(cudaMemcpyAsync(ps + 200, cnt_cur, 4, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(ps + 201, small_u32(c) + SM_ERR, 4, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            if (ps[201] != B200_DEVERR_NONE) return map_dev_error(c, (int)ps[201]);
-            if (ps[200] == 0) break;
-            if (round > 200) return fail(c, B200_ERR_CUDA, "collapse rounds do not converge");
-            CU(cudaMemsetAsync(cnt_next, 0, 4, st));
-            CU(launch_dt_collapse_round(d, list_cur, cnt_cur, ps[200], static_cast<uint8_t *>(t->flags.p), list_next, cnt_next, st));
-            c->launches += 4;
-            std::swap(list_cur, list_next);
-            std::swap(cnt_cur, cnt_next);
-        }
-        // ---- inserts: the dense list of insert keys, their attach points, one thread per run
-        {
-            uint32_t *ins_idx = static_cast<uint32_t *>(t->ins_idx.p);
-            thrust::counting_iterator<uint32_t> counting(0);
-            auto is_insert = thrust::make_transform_iterator(kind, IsKind{DK_INSERT});
-            size_t t_sel = 0;
-            CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, is_insert, ins_idx, d.g + DG_NINSERT, (int64_t)m, st));
-            ENSURE(cub_temp, t_sel);
-            CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, is_insert, ins_idx, d.g + DG_NINSERT, (int64_t)m, st));
-            CU(launch_dt_insert(d, d_keys, d_accts, d_sroots, ins_idx, d.g + DG_NINSERT, m, static_cast<uint64_t *>(t->attach.p), st));
-            c->launches += 3;
-        }
-        // ---- re-hash the dirty paths
-        CU(launch_dt_rehash(d, max_seeds, static_cast<uint8_t *>(t->root.p), st));
-        CU(launch_dt_finish(d, max_list, static_cast<uint8_t *>(t->root.p), st));
-        c->launches += 5;
+        TRY(h2d_into(a, t->in_keys, keys32, m * 32));
+        TRY(h2d_into(a, t->in_accts, accts, m * 72));
+        if (present) TRY(h2d_into(a, t->in_present, present, m));
+        if (storage_roots32) TRY(h2d_into(a, t->in_sroots, storage_roots32, m * 32));
+        TRY(da_restructure(a, nullptr, static_cast<const uint8_t *>(t->in_keys.p), static_cast<const uint8_t *>(t->in_accts.p),
+                           present ? static_cast<const uint8_t *>(t->in_present.p) : nullptr,
+                           storage_roots32 ? static_cast<const uint8_t *>(t->in_sroots.p) : nullptr, m));
+        TRY(da_rehash(a, m));
         c->stats.leaves_added += m;
-        TRY(finish_build_state(c));
-        // ---- counters back to the host
-        CU(cudaMemcpyAsync(ps + 256, d.g, DG_WORDS * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(root32, t->root.p, 32, cudaMemcpyDeviceToHost, st));
-        TRY(sync_and_status(c));
-        t->n_leaves = ps[256 + DG_NLEAVES];
-        t->leaf_alloc = ps[256 + DG_LEAF_ALLOC];
-        t->node_alloc = ps[256 + DG_NODE_ALLOC];
-        n_built = ps[256 + DG_BUILT];
-        n_removed = ps[256 + DG_REMOVED];
-        c->stats.branches_added = n_built;
-        if (opt_updated || opt_removed) {
-            b200_updates tmp{};
-            b200_updates *upd = opt_updated ? opt_updated : &tmp;
-            int32_t r = dt_collect_updates(t, d, n_built, upd);
-            if (r == B200_OK && opt_removed) r = dt_collect_removed(t, d, n_removed, upd, opt_removed);
-            if (!opt_updated) b200_updates_release(&tmp);
-            if (r != B200_OK) {
-                if (opt_updated) b200_updates_release(opt_updated);
-                if (opt_removed) b200_updates_release(opt_removed);
-                return r;
-            }
+    }
+    TRY(finish_build_state(c));
+    uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
+    if (m) TRY(da_pull_counters(a, ps + 256));
+    CU(cudaMemcpyAsync(root32, t->root.p, 32, cudaMemcpyDeviceToHost, st));
+    TRY(sync_and_status(c));
+    if (m) da_take_counters(a, ps + 256);
+    c->stats.branches_added = a->n_built;
+    if (opt_updated || opt_removed) {
+        b200_updates tmp{};
+        b200_updates *upd = opt_updated ? opt_updated : &tmp;
+        int32_t r = da_collect_updates(a, upd);
+        if (r == B200_OK && opt_removed) r = da_collect_removed(a, upd, opt_removed);
+        if (!opt_updated) b200_updates_release(&tmp);
+        if (r != B200_OK) {
+            if (opt_updated) b200_updates_release(opt_updated);
+            if (opt_removed) b200_updates_release(opt_removed);
+            return r;
         }
-    } else {
-        TRY(finish_build_state(c));
-        CU(cudaMemcpyAsync(root32, t->root.p, 32, cudaMemcpyDeviceToHost, st));
-        TRY(sync_and_status(c));
-        if (opt_updated) TRY(dt_collect_updates(t, dt_view(t), 0, opt_updated));
-        if (opt_removed) TRY(dt_collect_removed(t, dt_view(t), 0, opt_updated, opt_removed));
     }
     if (opt_stats) *opt_stats = c->stats;
     return B200_OK;

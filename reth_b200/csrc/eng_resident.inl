@@ -14,6 +14,11 @@ struct b200_trie {
     uint32_t B = 0;
     ForestDev f{};
     bool has_sroots = false;
+    // a storage FOREST instead of the account trie (used to seed the dynamic state, eng_dtrie.inl): `accts` then holds
+    // the 32-byte slot values, seg_offsets the n_segs+1 segment bounds, seg_roots receives the n_segs storage roots
+    bool forest = false;
+    uint64_t n_segs = 0;
+    DevBuf seg_offsets, seg_roots;
     uint64_t bytes = 0;
     uint32_t level_count[64] = {};
     DevBuf keys, accts, sroots, Lp, nibs, leaf_ref, leaf_meta, S, E, gap_sorted, node_start, node_ref, node_meta, node_l,
@@ -50,7 +55,8 @@ extern "C" B200_API void b200_trie_destroy(b200_trie *t) {
     DevBuf *bufs[] = {&t->keys, &t->accts, &t->sroots, &t->Lp, &t->nibs, &t->leaf_ref, &t->leaf_meta, &t->S, &t->E,
                       &t->gap_sorted, &t->node_start, &t->node_ref, &t->node_meta, &t->node_l, &t->node_r, &t->node_masks,
                       &t->leaf_parent, &t->node_parent, &t->dirty, &t->dirty_ids, &t->dirty_key, &t->dirty_key2,
-                      &t->dirty_order, &t->idx, &t->in_keys, &t->in_accts, &t->in_sroots, &t->root};
+                      &t->dirty_order, &t->idx, &t->in_keys, &t->in_accts, &t->in_sroots, &t->root, &t->seg_offsets,
+                      &t->seg_roots};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     delete t;
@@ -64,9 +70,16 @@ static int32_t trie_build_owned(b200_trie *t) {
     TRY(reset_build_state(c));
     Built b;
     TRY(trie_alloc(t, t->root, 64));
-    TRY(account_root_on_device(c, static_cast<const uint8_t *>(t->keys.p), static_cast<const uint8_t *>(t->accts.p),
-                               t->has_sroots ? static_cast<const uint8_t *>(t->sroots.p) : nullptr, t->n,
-                               static_cast<uint8_t *>(t->root.p), true, b));
+    if (t->forest) {
+        TRY(trie_alloc(t, t->seg_roots, (t->n_segs ? t->n_segs : 1) * 32));
+        TRY(storage_roots_on_device(c, static_cast<const uint8_t *>(t->keys.p), static_cast<const uint8_t *>(t->accts.p),
+                                    static_cast<const uint64_t *>(t->seg_offsets.p), t->n_segs, t->n,
+                                    static_cast<uint8_t *>(t->seg_roots.p), true, b));
+    } else {
+        TRY(account_root_on_device(c, static_cast<const uint8_t *>(t->keys.p), static_cast<const uint8_t *>(t->accts.p),
+                                   t->has_sroots ? static_cast<const uint8_t *>(t->sroots.p) : nullptr, t->n,
+                                   static_cast<uint8_t *>(t->root.p), true, b));
+    }
     TRY(finish_build_state(c));
     TRY(sync_and_status(c));
     t->f = b.f;

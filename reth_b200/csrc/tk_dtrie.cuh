@@ -50,9 +50,28 @@ static __device__ __forceinline__ void dt_copy72(uint8_t *dst, const uint8_t *sr
     for (int w = 0; w < 9; w++) d[w] = s[w];
 }
 
-static __device__ __forceinline__ void dt_set_child(const DTrieDev &t, uint32_t parent, uint32_t slot, uint32_t word) {
-    if (parent == DT_NONE) t.g[DG_ROOT] = word;
-    else t.nchild[16 * (uint64_t)parent + slot] = word;
+static __device__ __forceinline__ uint32_t dt_trie_of(const DTrieDev &t, uint32_t word) {
+    if (!t.ltrie) return 0;
+    return (word & DT_LEAF) ? t.ltrie[word & ~DT_LEAF] : t.ntrie[word];
+}
+static __device__ __forceinline__ void dt_put_empty_root(uint8_t *dst) {  // EMPTY_ROOT_HASH
+    uint32_t *w = reinterpret_cast<uint32_t *>(dst);
+    w[0] = 0x171fe856u; w[1] = 0xa655cc1bu; w[2] = 0xe64583ffu; w[3] = 0x6ef8c092u;
+    w[4] = 0x1be0485bu; w[5] = 0xc0ad6c99u; w[6] = 0xb52f6201u; w[7] = 0x21b463e3u;
+}
+// parent == NONE addresses the root word of `trie`; a trie that becomes empty gets EMPTY_ROOT_HASH as its root right
+// away (no wavefront will visit it)
+static __device__ __forceinline__ void dt_set_child(const DTrieDev &t, uint32_t trie, uint32_t parent, uint32_t slot, uint32_t word) {
+    if (parent == DT_NONE) {
+        t.troot[trie] = word;
+        if (word == DT_NONE) dt_put_empty_root(t.top_out + (uint64_t)t.top_stride * trie);
+    } else {
+        t.nchild[16 * (uint64_t)parent + slot] = word;
+    }
+}
+static __device__ __forceinline__ void dt_copy_val(const DTrieDev &t, uint32_t x, const uint8_t *src) {
+    if (t.account) dt_copy72(t.lval + 72 * (uint64_t)x, src);
+    else dt_copy32(t.lval + 32 * (uint64_t)x, src);
 }
 static __device__ __forceinline__ void dt_set_parent(const DTrieDev &t, uint32_t word, uint32_t parent) {
     if (word & DT_LEAF) t.lparent[word & ~DT_LEAF] = parent;
@@ -82,8 +101,10 @@ static __device__ __forceinline__ uint32_t dt_alloc_leaf(const DTrieDev &t) {
     t.lseed[id] = 0;
     return id;
 }
-static __device__ __forceinline__ uint32_t dt_alloc_node(const DTrieDev &t, uint32_t depth, const uint8_t *key, uint32_t parent) {
+static __device__ __forceinline__ uint32_t dt_alloc_node(const DTrieDev &t, uint32_t trie, uint32_t depth, const uint8_t *key,
+                                                        uint32_t parent) {
     uint32_t v = dt_pop(&t.g[DG_NODE_FREE], t.node_free, &t.g[DG_NODE_ALLOC]);
+    if (t.ntrie) t.ntrie[v] = trie;
     uint4 none = make_uint4(DT_NONE, DT_NONE, DT_NONE, DT_NONE);
     uint4 *ch = reinterpret_cast<uint4 *>(t.nchild + 16 * (uint64_t)v);
     ch[0] = none; ch[1] = none; ch[2] = none; ch[3] = none;
@@ -115,7 +136,8 @@ __global__ void dt_recycle_kernel(DTrieDev t) {  // end of an apply: this apply'
     if (i >= t.g[DG_FREED_NOW]) return;
     t.node_free[t.g[DG_NODE_FREE] + i] = t.freed_now[i];
 }
-__global__ void dt_removed_paths_kernel(DTrieDev t, uint32_t n_removed, uint8_t *__restrict__ path_len, uint8_t *__restrict__ path_packed) {
+__global__ void dt_removed_paths_kernel(DTrieDev t, uint32_t n_removed, uint8_t *__restrict__ path_len, uint8_t *__restrict__ path_packed,
+                                        uint32_t *__restrict__ trie_id) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_removed) return;
     uint32_t v = t.removed[i];
@@ -124,12 +146,14 @@ __global__ void dt_removed_paths_kernel(DTrieDev t, uint32_t n_removed, uint8_t 
     uint8_t *pp = path_packed + 32 * (uint64_t)i;
     for (uint32_t b = 0; b < 32; b++) pp[b] = (uint8_t)(2 * b + 1 < d ? key[b] : (2 * b < d ? (key[b] & 0xF0) : 0));
     path_len[i] = (uint8_t)d;
+    trie_id[i] = t.ntrie ? t.ntrie[v] : 0;
 }
 
 // ------------------------------------------------------------------------------------------------ create
 // Conversion of a finished level-synchronous build (ForestDev, one trie) into the arena: node ids and leaf ids carry
 // over unchanged.
-__global__ void dt_convert_nodes_kernel(ForestDev f, uint32_t n_nodes, const uint32_t *__restrict__ node_parent, DTrieDev t) {
+__global__ void dt_convert_nodes_kernel(ForestDev f, uint32_t n_nodes, const uint32_t *__restrict__ node_parent,
+                                        const uint32_t *__restrict__ leaf_trie, DTrieDev t) {
     uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes) return;
     uint32_t j0 = f.node_start[v], k = f.node_start[v + 1] - j0;
@@ -150,7 +174,31 @@ __global__ void dt_convert_nodes_kernel(ForestDev f, uint32_t n_nodes, const uin
     t.nseed[v] = 0;
     t.ncur[v] = 0;
     t.nnext[v] = 0;
-    if (node_parent[v] == DT_NONE) t.g[DG_ROOT] = v;
+    uint32_t trie = leaf_trie ? leaf_trie[f.node_l[v]] : 0;
+    if (t.ntrie) t.ntrie[v] = trie;
+    if (node_parent[v] == DT_NONE) t.troot[trie] = v;
+}
+// single-leaf tries: the root word is the leaf itself (leaf_parent == NONE)
+__global__ void dt_convert_leaves_kernel(uint64_t n, const uint32_t *__restrict__ leaf_parent, const uint32_t *__restrict__ leaf_trie,
+                                         DTrieDev t) {
+    uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    uint32_t trie = leaf_trie ? leaf_trie[x] : 0;
+    if (t.ltrie) t.ltrie[x] = trie;
+    t.lparent[x] = leaf_parent[x];
+    if (leaf_parent[x] == DT_NONE) t.troot[trie] = (uint32_t)x | DT_LEAF;
+}
+// leaf_trie[x] = segment (trie) of leaf x of a forest build
+__global__ void dt_leaf_segments_kernel(const uint64_t *__restrict__ seg_offsets, uint64_t n_segs, uint64_t n, uint32_t *__restrict__ leaf_trie) {
+    uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    uint64_t lo = 0, hi = n_segs;  // last segment with offset <= x
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (seg_offsets[mid] <= x) lo = mid;
+        else hi = mid;
+    }
+    leaf_trie[x] = (uint32_t)lo;
 }
 
 // ------------------------------------------------------------------------------------------------ locate
@@ -159,12 +207,12 @@ struct DtLoc {
     uint32_t parent, slot, child;  // attach point and what hangs there now
     bool found;                    // child is the leaf holding exactly this key
 };
-static __device__ __forceinline__ DtLoc dt_descend(const DTrieDev &t, const uint8_t *key) {
+static __device__ __forceinline__ DtLoc dt_descend(const DTrieDev &t, uint32_t trie, const uint8_t *key) {
     DtLoc r;
     r.parent = DT_NONE;
     r.slot = 0;
     r.found = false;
-    uint32_t cur = t.g[DG_ROOT];
+    uint32_t cur = t.troot[trie];
     uint32_t matched = 0;  // nibbles known to agree with everything below `cur`
     for (;;) {
         r.child = cur;
@@ -182,23 +230,43 @@ static __device__ __forceinline__ DtLoc dt_descend(const DTrieDev &t, const uint
     }
 }
 
-__global__ void dt_locate_kernel(DTrieDev t, const uint8_t *__restrict__ keys, const uint8_t *__restrict__ present, uint64_t m,
+// flags[i] (accounts): bit 0 = present (0 deletes), bit 1 = touch only (the leaf's data is unchanged but it must be
+// re-hashed: its storage root changes); nullptr = all present.  Storage slots: a zero value deletes.
+// trie_of_key (forest arenas): the trie each key belongs to, DT_NONE = skip the entry.
+__global__ void dt_locate_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_key, const uint8_t *__restrict__ keys,
+                                 const uint8_t *__restrict__ vals, const uint8_t *__restrict__ flags, uint64_t m,
                                  uint8_t *__restrict__ kind, uint32_t *__restrict__ leaf_of) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    if (i) {  // strictly ascending: the insert runs rely on it
+    const uint32_t trie = trie_of_key ? trie_of_key[i] : 0;
+    if (trie == DT_NONE) {
+        kind[i] = DK_NOOP;
+        leaf_of[i] = DT_NONE;
+        return;
+    }
+    if (i && (!trie_of_key || trie_of_key[i - 1] == trie)) {  // strictly ascending inside a trie: the insert runs rely on it
         const uint8_t *a = keys + 32 * (i - 1), *b = keys + 32 * i;
         uint32_t l = dt_lcp(a, b, 0, 64);
         if (l == 64 || dt_nib(a, l) > dt_nib(b, l)) atomicExch(t.err, B200_DEVERR_UNSORTED);
     }
-    DtLoc loc = dt_descend(t, keys + 32 * i);
-    bool want = present == nullptr || present[i] != 0;
-    kind[i] = loc.found ? (want ? DK_UPDATE : DK_DELETE) : (want ? DK_INSERT : DK_NOOP);
+    DtLoc loc = dt_descend(t, trie, keys + 32 * i);
+    bool want, touch = false;
+    if (t.account) {
+        want = flags == nullptr || (flags[i] & 1);
+        touch = flags != nullptr && (flags[i] & 2);
+    } else {
+        const uint64_t *v = reinterpret_cast<const uint64_t *>(vals + 32 * i);
+        want = (v[0] | v[1] | v[2] | v[3]) != 0;
+    }
+    uint8_t k;
+    if (touch) k = (want && loc.found) ? DK_TOUCH : DK_NOOP;
+    else k = loc.found ? (want ? DK_UPDATE : DK_DELETE) : (want ? DK_INSERT : DK_NOOP);
+    kind[i] = k;
     leaf_of[i] = loc.found ? (loc.child & ~DT_LEAF) : DT_NONE;
 }
 
 // value changes of existing leaves; deleted leaves leave their parent's slot
-__global__ void dt_update_detach_kernel(DTrieDev t, const uint8_t *__restrict__ accts, const uint8_t *__restrict__ sroots,
+__global__ void dt_update_detach_kernel(DTrieDev t, const uint8_t *__restrict__ vals, const uint8_t *__restrict__ sroots,
                                         uint64_t m, const uint8_t *__restrict__ kind, const uint32_t *__restrict__ leaf_of,
                                         uint32_t *__restrict__ touched) {
     if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
@@ -206,13 +274,15 @@ __global__ void dt_update_detach_kernel(DTrieDev t, const uint8_t *__restrict__ 
     if (i >= m) return;
     uint32_t x = leaf_of[i];
     if (kind[i] == DK_UPDATE) {
-        dt_copy72(t.lacct + 72 * (uint64_t)x, accts + 72 * i);
+        dt_copy_val(t, x, vals + (uint64_t)t.val_stride * i);
         if (sroots && t.lsroot) dt_copy32(t.lsroot + 32 * (uint64_t)x, sroots + 32 * i);
+        dt_seed(t, x | DT_LEAF);
+    } else if (kind[i] == DK_TOUCH) {
         dt_seed(t, x | DT_LEAF);
     } else if (kind[i] == DK_DELETE) {
         uint32_t p = t.lparent[x];
         if (p == DT_NONE) {
-            t.g[DG_ROOT] = DT_NONE;
+            dt_set_child(t, dt_trie_of(t, x | DT_LEAF), DT_NONE, 0, DT_NONE);
         } else {
             t.nchild[16 * (uint64_t)p + dt_nib(t.lkey + 32 * (uint64_t)x, t.ndepth[p])] = DT_NONE;
             if (!dt_test_and_set(t.nnext, p)) touched[atomicAdd(&t.g[DG_LIST_A], 1u)] = p;
@@ -279,49 +349,51 @@ __global__ void dt_collapse_round_kernel(DTrieDev t, const uint32_t *__restrict_
         return;
     }
     uint32_t slot = gp == DT_NONE ? 0 : dt_nib(t.nkey + 32 * (uint64_t)v, t.ndepth[gp]);
+    const uint32_t trie = dt_trie_of(t, v);
     if (cnt == 1) {  // path compression: the only child takes this node's place
-        dt_set_child(t, gp, slot, only);
+        dt_set_child(t, trie, gp, slot, only);
         dt_set_parent(t, only, gp);
         dt_seed(t, only);  // its parent depth changed: the leaf path / extension above it is different now
     } else {
-        dt_set_child(t, gp, slot, DT_NONE);
+        dt_set_child(t, trie, gp, slot, DT_NONE);
         if (gp != DT_NONE) push_next(gp);
     }
     dt_free_node(t, v);
 }
 
 // ------------------------------------------------------------------------------------------------ insert
-// attach[i] = (parent << 4 | slot) of insert key i in the structure left by the deletes; keys with equal attach words
-// are consecutive (they share the prefix that leads to that slot).
-__global__ void dt_insert_locate_kernel(DTrieDev t, const uint8_t *__restrict__ keys, const uint32_t *__restrict__ ins_idx,
-                                        const uint32_t *__restrict__ n_ins_p, uint64_t *__restrict__ attach) {
+// attach[j] identifies where insert key j hangs in the structure left by the deletes: (parent << 4 | slot), or, at a
+// trie's root word, (1 << 63 | trie).  Keys with equal attach words are consecutive (same trie, same leading prefix).
+__global__ void dt_insert_locate_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_key, const uint8_t *__restrict__ keys,
+                                        const uint32_t *__restrict__ ins_idx, const uint32_t *__restrict__ n_ins_p,
+                                        uint64_t *__restrict__ attach) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= *n_ins_p) return;
-    DtLoc loc = dt_descend(t, keys + 32 * (uint64_t)ins_idx[j]);
-    attach[j] = ((uint64_t)loc.parent << 4) | loc.slot;
+    const uint32_t i = ins_idx[j];
+    const uint32_t trie = trie_of_key ? trie_of_key[i] : 0;
+    DtLoc loc = dt_descend(t, trie, keys + 32 * (uint64_t)i);
+    attach[j] = loc.parent == DT_NONE ? ((1ull << 63) | trie) : (((uint64_t)loc.parent << 4) | loc.slot);
 }
 
-static __device__ __forceinline__ void dt_insert_one(const DTrieDev &t, const uint8_t *key, const uint8_t *acct, const uint8_t *sroot,
-                                                     uint32_t parent, uint32_t slot) {
+// returns the id of the new leaf
+static __device__ __forceinline__ uint32_t dt_insert_one(const DTrieDev &t, uint32_t trie, const uint8_t *key, const uint8_t *val,
+                                                         const uint8_t *sroot, uint32_t parent, uint32_t slot) {
     uint32_t matched = parent == DT_NONE ? 0 : (uint32_t)t.ndepth[parent] + 1;
-    uint32_t cur = parent == DT_NONE ? t.g[DG_ROOT] : t.nchild[16 * (uint64_t)parent + slot];
+    uint32_t cur = parent == DT_NONE ? t.troot[trie] : t.nchild[16 * (uint64_t)parent + slot];
     // the new leaf
     uint32_t x = dt_alloc_leaf(t);
     dt_copy32(t.lkey + 32 * (uint64_t)x, key);
-    dt_copy72(t.lacct + 72 * (uint64_t)x, acct);
+    dt_copy_val(t, x, val);
+    if (t.ltrie) t.ltrie[x] = trie;
     if (t.lsroot) {
         if (sroot) dt_copy32(t.lsroot + 32 * (uint64_t)x, sroot);
-        else {  // EMPTY_ROOT_HASH
-            uint32_t *w = reinterpret_cast<uint32_t *>(t.lsroot + 32 * (uint64_t)x);
-            w[0] = 0x171fe856u; w[1] = 0xa655cc1bu; w[2] = 0xe64583ffu; w[3] = 0x6ef8c092u;
-            w[4] = 0x1be0485bu; w[5] = 0xc0ad6c99u; w[6] = 0xb52f6201u; w[7] = 0x21b463e3u;
-        }
+        else dt_put_empty_root(t.lsroot + 32 * (uint64_t)x);
     }
     t.lmeta[x] = 0;
     atomicAdd(&t.g[DG_NLEAVES], 1u);
     for (;;) {
         if (cur == DT_NONE) {
-            dt_set_child(t, parent, slot, x | DT_LEAF);
+            dt_set_child(t, trie, parent, slot, x | DT_LEAF);
             t.lparent[x] = parent;
             break;
         }
@@ -329,12 +401,12 @@ static __device__ __forceinline__ void dt_insert_one(const DTrieDev &t, const ui
         uint32_t limit = (cur & DT_LEAF) ? 64u : (uint32_t)t.ndepth[cur];
         uint32_t l = dt_lcp(key, other, matched, limit);
         if (l < limit) {  // diverges above `cur`: a new branch at depth l holds both
-            uint32_t b = dt_alloc_node(t, l, key, parent);
+            uint32_t b = dt_alloc_node(t, trie, l, key, parent);
             t.nchild[16 * (uint64_t)b + dt_nib(key, l)] = x | DT_LEAF;
             t.nchild[16 * (uint64_t)b + dt_nib(other, l)] = cur;
             t.lparent[x] = b;
             dt_set_parent(t, cur, b);
-            dt_set_child(t, parent, slot, b);
+            dt_set_child(t, trie, parent, slot, b);
             dt_seed(t, b);
             dt_seed(t, cur);  // parent depth changed
             break;
@@ -346,21 +418,26 @@ static __device__ __forceinline__ void dt_insert_one(const DTrieDev &t, const ui
         cur = t.nchild[16 * (uint64_t)cur + slot];
     }
     dt_seed(t, x | DT_LEAF);
+    return x;
 }
 
-__global__ void dt_insert_runs_kernel(DTrieDev t, const uint8_t *__restrict__ keys, const uint8_t *__restrict__ accts,
-                                      const uint8_t *__restrict__ sroots, const uint32_t *__restrict__ ins_idx,
-                                      const uint32_t *__restrict__ n_ins_p, const uint64_t *__restrict__ attach) {
+__global__ void dt_insert_runs_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_key, const uint8_t *__restrict__ keys,
+                                      const uint8_t *__restrict__ vals, const uint8_t *__restrict__ sroots,
+                                      const uint32_t *__restrict__ ins_idx, const uint32_t *__restrict__ n_ins_p,
+                                      const uint64_t *__restrict__ attach, uint32_t *__restrict__ leaf_of) {
     if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
     const uint32_t n_ins = *n_ins_p;
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_ins) return;
     uint64_t a = attach[j];
     if (j && attach[j - 1] == a) return;  // not the head of its run
-    uint32_t parent = (uint32_t)(a >> 4), slot = (uint32_t)(a & 15);
+    const bool at_root = (a >> 63) != 0;
+    uint32_t parent = at_root ? DT_NONE : (uint32_t)(a >> 4), slot = at_root ? 0u : (uint32_t)(a & 15);
     for (uint32_t q = j; q < n_ins && attach[q] == a; q++) {
         uint64_t i = ins_idx[q];
-        dt_insert_one(t, keys + 32 * i, accts + 72 * i, sroots ? sroots + 32 * i : nullptr, parent, slot);
+        uint32_t trie = trie_of_key ? trie_of_key[i] : 0;
+        leaf_of[i] = dt_insert_one(t, trie, keys + 32 * i, vals + (uint64_t)t.val_stride * i, sroots ? sroots + 32 * i : nullptr,
+                                   parent, slot);
     }
 }
 
@@ -532,8 +609,7 @@ __device__ __forceinline__ void dt_warp_build_node(const DTrieDev &t, uint32_t v
 // One warp per seed: re-hash the item if nothing below it is dirty, then climb; the last dirty child to arrive at a
 // node re-hashes it.  The warp that runs out of parents holds the new root reference.
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) dt_wavefront_kernel(DTrieDev t, const uint32_t *__restrict__ count_p,
-                                                                 uint8_t *__restrict__ root_out) {
+__global__ void __launch_bounds__(WARPS * 32) dt_wavefront_kernel(DTrieDev t, const uint32_t *__restrict__ count_p) {
     __shared__ __align__(16) uint8_t sbuf[WARPS][WARP_BUF];
     if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -559,24 +635,38 @@ __global__ void __launch_bounds__(WARPS * 32) dt_wavefront_kernel(DTrieDev t, co
                 uint32_t k[8];
                 load32_nc(t.lkey + 32 * (uint64_t)x, k);
                 LinBuf lb{buf, 0};
-                len = encode_leaf<LinBuf, true>(lb, k, pd, t.lacct + 72 * (uint64_t)x,
-                                                t.lsroot ? t.lsroot + 32 * (uint64_t)x : nullptr, t.err);
-                buf[len] |= 0x01;
-                buf[(len / 136 + 1) * 136 - 1] |= 0x80;
+                if (t.account)
+                    len = encode_leaf<LinBuf, true>(lb, k, pd, t.lval + 72 * (uint64_t)x,
+                                                    t.lsroot ? t.lsroot + 32 * (uint64_t)x : nullptr, t.err);
+                else
+                    len = encode_leaf<LinBuf, false>(lb, k, pd, t.lval + 32 * (uint64_t)x, nullptr, t.err);
             }
             len = __shfl_sync(0xffffffffu, len, 0);
-            __syncwarp();
-            uint64_t a = kw.hash(buf, len / 136 + 1, lane);  // account leaves are >= 70 bytes: always hashed
+            uint32_t lmeta;
+            if (len >= 32 || pd < 0) {  // account leaves are >= 70 bytes; a short storage leaf is hashed only as a whole trie
+                if (lane == 0) {
+                    buf[len] |= 0x01;
+                    buf[(len / 136 + 1) * 136 - 1] |= 0x80;
+                }
+                __syncwarp();
+                uint64_t a = kw.hash(buf, len / 136 + 1, lane);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                uint64_t w = shfl64(a, q);
-                out[2 * q] = (uint32_t)w;
-                out[2 * q + 1] = (uint32_t)(w >> 32);
+                for (int q = 0; q < 4; q++) {
+                    uint64_t w = shfl64(a, q);
+                    out[2 * q] = (uint32_t)w;
+                    out[2 * q + 1] = (uint32_t)(w >> 32);
+                }
+                hashed += lane == 0;
+                lmeta = 0;
+            } else {
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 8; q++) out[q] = bufw[q];
+                lmeta = len;
             }
-            hashed += lane == 0;
             if (lane == 0) {
                 store32(t.lref + 32 * (uint64_t)x, out);
-                t.lmeta[x] = 0;
+                t.lmeta[x] = (uint8_t)lmeta;
             }
             __syncwarp();
         } else {
@@ -599,7 +689,7 @@ __global__ void __launch_bounds__(WARPS * 32) dt_wavefront_kernel(DTrieDev t, co
             dt_warp_build_node(t, p, buf, kw, lane, hashed, exts, out);
             p = t.nparent[p];
         }
-        if (top && lane == 0) store32(root_out, out);
+        if (top && lane == 0) store32(t.top_out + (uint64_t)t.top_stride * dt_trie_of(t, s), out);  // the trie's new root
     }
     if (lane == 0) {
         if (hashed) atomicAdd(&t.counters[CNT_HASHED], (unsigned long long)hashed);
@@ -625,7 +715,7 @@ __global__ void dt_gather_updates_kernel(DTrieDev t, const uint32_t *__restrict_
     uint32_t v = stored_ids[i];
     ushort4 m = t.nmasks[v];
     uint32_t d = m.w;
-    out.trie_id[i] = 0;
+    out.trie_id[i] = t.ntrie ? t.ntrie[v] : 0;
     out.path_len[i] = (uint8_t)d;
     const uint8_t *key = t.nkey + 32 * (uint64_t)v;
     uint8_t *pp = out.path_packed + 32 * (uint64_t)i;
@@ -644,14 +734,20 @@ __global__ void dt_gather_updates_kernel(DTrieDev t, const uint32_t *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-cudaError_t launch_dt_convert_nodes(const ForestDev &f, uint32_t n_nodes, const uint32_t *node_parent, const DTrieDev &t,
-                                    cudaStream_t st) {
-    if (n_nodes) dt_convert_nodes_kernel<<<blocks_for(n_nodes, 128), 128, 0, st>>>(f, n_nodes, node_parent, t);
+// leaf_trie: trie (segment) of every leaf of a forest build, nullptr for a single trie
+cudaError_t launch_dt_convert(const ForestDev &f, uint32_t n_nodes, const uint32_t *leaf_parent, const uint32_t *node_parent,
+                              const uint32_t *leaf_trie, const DTrieDev &t, cudaStream_t st) {
+    if (f.n) dt_convert_leaves_kernel<<<blocks_for(f.n, 256), 256, 0, st>>>(f.n, leaf_parent, leaf_trie, t);
+    if (n_nodes) dt_convert_nodes_kernel<<<blocks_for(n_nodes, 128), 128, 0, st>>>(f, n_nodes, node_parent, leaf_trie, t);
     return cudaGetLastError();
 }
-cudaError_t launch_dt_locate(const DTrieDev &t, const uint8_t *keys, const uint8_t *present, uint64_t m, uint8_t *kind,
-                             uint32_t *leaf_of, cudaStream_t st) {
-    dt_locate_kernel<<<blocks_for(m, 128), 128, 0, st>>>(t, keys, present, m, kind, leaf_of);
+cudaError_t launch_dt_leaf_segments(const uint64_t *seg_offsets, uint64_t n_segs, uint64_t n, uint32_t *leaf_trie, cudaStream_t st) {
+    if (n) dt_leaf_segments_kernel<<<blocks_for(n, 256), 256, 0, st>>>(seg_offsets, n_segs, n, leaf_trie);
+    return cudaGetLastError();
+}
+cudaError_t launch_dt_locate(const DTrieDev &t, const uint32_t *trie_of_key, const uint8_t *keys, const uint8_t *vals,
+                             const uint8_t *flags, uint64_t m, uint8_t *kind, uint32_t *leaf_of, cudaStream_t st) {
+    dt_locate_kernel<<<blocks_for(m, 128), 128, 0, st>>>(t, trie_of_key, keys, vals, flags, m, kind, leaf_of);
     return cudaGetLastError();
 }
 cudaError_t launch_dt_update_detach(const DTrieDev &t, const uint8_t *accts, const uint8_t *sroots, uint64_t m,
@@ -669,37 +765,32 @@ cudaError_t launch_dt_collapse_round(const DTrieDev &t, const uint32_t *list, co
     dt_round_end_kernel<<<blocks, 128, 0, st>>>(t, list, count_p);
     return cudaGetLastError();
 }
-cudaError_t launch_dt_insert(const DTrieDev &t, const uint8_t *keys, const uint8_t *accts, const uint8_t *sroots,
-                             const uint32_t *ins_idx, const uint32_t *n_ins_p, uint64_t max_ins, uint64_t *attach,
-                             cudaStream_t st) {
+cudaError_t launch_dt_insert(const DTrieDev &t, const uint32_t *trie_of_key, const uint8_t *keys, const uint8_t *vals,
+                             const uint8_t *sroots, const uint32_t *ins_idx, const uint32_t *n_ins_p, uint64_t max_ins,
+                             uint64_t *attach, uint32_t *leaf_of, cudaStream_t st) {
     unsigned blocks = blocks_for(max_ins, 128);
-    dt_insert_locate_kernel<<<blocks, 128, 0, st>>>(t, keys, ins_idx, n_ins_p, attach);
-    dt_insert_runs_kernel<<<blocks, 128, 0, st>>>(t, keys, accts, sroots, ins_idx, n_ins_p, attach);
+    dt_insert_locate_kernel<<<blocks, 128, 0, st>>>(t, trie_of_key, keys, ins_idx, n_ins_p, attach);
+    dt_insert_runs_kernel<<<blocks, 128, 0, st>>>(t, trie_of_key, keys, vals, sroots, ins_idx, n_ins_p, attach, leaf_of);
     return cudaGetLastError();
 }
 // mark -> starts -> wavefront -> finish (empty-trie root, recycling of this apply's freed nodes)
-__global__ void dt_finish_kernel(DTrieDev t, uint8_t *__restrict__ root_out) {
-    if (t.g[DG_ROOT] == DT_NONE) {  // EMPTY_ROOT_HASH
-        uint32_t *w = reinterpret_cast<uint32_t *>(root_out);
-        w[0] = 0x171fe856u; w[1] = 0xa655cc1bu; w[2] = 0xe64583ffu; w[3] = 0x6ef8c092u;
-        w[4] = 0x1be0485bu; w[5] = 0xc0ad6c99u; w[6] = 0xb52f6201u; w[7] = 0x21b463e3u;
-    }
+__global__ void dt_finish_kernel(DTrieDev t) {
     t.g[DG_NODE_FREE] += t.g[DG_FREED_NOW];
     t.g[DG_FREED_NOW] = 0;
 }
-cudaError_t launch_dt_rehash(const DTrieDev &t, uint32_t max_seeds, uint8_t *root_out, cudaStream_t st) {
+cudaError_t launch_dt_rehash(const DTrieDev &t, uint32_t max_seeds, cudaStream_t st) {
     constexpr int WARPS = 4;
     const uint32_t *count_p = t.g + DG_SEEDS;
     unsigned blocks = blocks_for(max_seeds, 128);
     dt_mark_kernel<<<blocks, 128, 0, st>>>(t, count_p);
     dt_starts_kernel<<<blocks, 128, 0, st>>>(t, count_p);
     unsigned wblocks = blocks_for(max_seeds, WARPS), cap = (unsigned)sms() * 16;
-    dt_wavefront_kernel<WARPS><<<wblocks < cap ? wblocks : cap, WARPS * 32, 0, st>>>(t, count_p, root_out);
+    dt_wavefront_kernel<WARPS><<<wblocks < cap ? wblocks : cap, WARPS * 32, 0, st>>>(t, count_p);
     return cudaGetLastError();
 }
-cudaError_t launch_dt_finish(const DTrieDev &t, uint32_t max_freed, uint8_t *root_out, cudaStream_t st) {
+cudaError_t launch_dt_finish(const DTrieDev &t, uint32_t max_freed, cudaStream_t st) {
     if (max_freed) dt_recycle_kernel<<<blocks_for(max_freed, 128), 128, 0, st>>>(t);
-    dt_finish_kernel<<<1, 1, 0, st>>>(t, root_out);
+    dt_finish_kernel<<<1, 1, 0, st>>>(t);
     return cudaGetLastError();
 }
 cudaError_t launch_dt_stored_flags(const DTrieDev &t, uint32_t max_built, uint8_t *flags, uint32_t *n_hashes, cudaStream_t st) {
@@ -711,7 +802,8 @@ cudaError_t launch_dt_gather_updates(const DTrieDev &t, const uint32_t *stored_i
     if (n_stored) dt_gather_updates_kernel<<<blocks_for(n_stored, 128), 128, 0, st>>>(t, stored_ids, n_stored, hash_prefix_by_record, out);
     return cudaGetLastError();
 }
-cudaError_t launch_dt_removed_paths(const DTrieDev &t, uint32_t n_removed, uint8_t *path_len, uint8_t *path_packed, cudaStream_t st) {
-    if (n_removed) dt_removed_paths_kernel<<<blocks_for(n_removed, 128), 128, 0, st>>>(t, n_removed, path_len, path_packed);
+cudaError_t launch_dt_removed_paths(const DTrieDev &t, uint32_t n_removed, uint8_t *path_len, uint8_t *path_packed,
+                                    uint32_t *trie_id, cudaStream_t st) {
+    if (n_removed) dt_removed_paths_kernel<<<blocks_for(n_removed, 128), 128, 0, st>>>(t, n_removed, path_len, path_packed, trie_id);
     return cudaGetLastError();
 }

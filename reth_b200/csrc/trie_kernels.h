@@ -136,7 +136,7 @@ constexpr uint32_t DT_LEAF = 0x80000000u;
 constexpr uint8_t DT_DEAD = 0xFF;  // ndepth / lmeta of a freed slot
 
 enum : int {
-    DG_ROOT = 0,      // child word of the root
+    DG_UNUSED0 = 0,
     DG_NLEAVES,       // live leaves
     DG_LEAF_ALLOC,    // bump pointers
     DG_NODE_ALLOC,
@@ -154,8 +154,8 @@ enum : int {
 
 struct DTrieDev {
     // leaves [lcap]
-    uint8_t *lkey, *lacct, *lsroot, *lref, *lmeta;
-    uint32_t *lparent;
+    uint8_t *lkey, *lval, *lsroot, *lref, *lmeta;  // lval: 72-byte account or 32-byte slot value; lsroot: accounts only
+    uint32_t *lparent, *ltrie;                     // ltrie / ntrie: owning trie (nullptr = a single trie, id 0)
     uint8_t *lseed;
     // nodes [ncap]
     uint32_t *nchild;  // [ncap][16]
@@ -164,8 +164,14 @@ struct DTrieDev {
     uint8_t *nref, *nmeta;
     ushort4 *nmasks;
     uint8_t *nkey;  // [ncap][32] a key of the subtree: its first ndepth nibbles are the node's path
-    uint32_t *npending;
+    uint32_t *npending, *ntrie;
     uint8_t *nseed, *ncur, *nnext;
+    // tries
+    uint32_t *troot;     // [n_tries] child word of every trie's root
+    uint8_t *top_out;    // the warp that finishes trie r stores its new root hash at top_out + top_stride * r
+    uint32_t top_stride;
+    uint32_t val_stride;  // 72 | 32
+    int account;          // leaf encoding: rlp(TrieAccount) | rlp(U256)
     // free stacks, lists, globals
     uint32_t *leaf_free, *node_free;
     uint32_t *seeds, *built, *removed, *freed_now;
@@ -175,24 +181,26 @@ struct DTrieDev {
     uint32_t lcap, ncap;
 };
 
-enum : uint8_t { DK_NOOP = 0, DK_UPDATE = 1, DK_DELETE = 2, DK_INSERT = 3 };
+enum : uint8_t { DK_NOOP = 0, DK_UPDATE = 1, DK_DELETE = 2, DK_INSERT = 3, DK_TOUCH = 4 };
 
-cudaError_t launch_dt_convert_nodes(const ForestDev &f, uint32_t n_nodes, const uint32_t *node_parent, const DTrieDev &t,
-                                    cudaStream_t st);
-cudaError_t launch_dt_locate(const DTrieDev &t, const uint8_t *keys, const uint8_t *present, uint64_t m, uint8_t *kind,
-                             uint32_t *leaf_of, cudaStream_t st);
+cudaError_t launch_dt_convert(const ForestDev &f, uint32_t n_nodes, const uint32_t *leaf_parent, const uint32_t *node_parent,
+                              const uint32_t *leaf_trie, const DTrieDev &t, cudaStream_t st);
+cudaError_t launch_dt_leaf_segments(const uint64_t *seg_offsets, uint64_t n_segs, uint64_t n, uint32_t *leaf_trie, cudaStream_t st);
+cudaError_t launch_dt_locate(const DTrieDev &t, const uint32_t *trie_of_key, const uint8_t *keys, const uint8_t *vals,
+                             const uint8_t *flags, uint64_t m, uint8_t *kind, uint32_t *leaf_of, cudaStream_t st);
 cudaError_t launch_dt_update_detach(const DTrieDev &t, const uint8_t *accts, const uint8_t *sroots, uint64_t m,
                                     const uint8_t *kind, const uint32_t *leaf_of, uint32_t *touched, cudaStream_t st);
 cudaError_t launch_dt_collapse_round(const DTrieDev &t, const uint32_t *list, const uint32_t *count_p, uint32_t max_count,
                                      uint8_t *defer, uint32_t *next, uint32_t *next_count, cudaStream_t st);
-cudaError_t launch_dt_insert(const DTrieDev &t, const uint8_t *keys, const uint8_t *accts, const uint8_t *sroots,
-                             const uint32_t *ins_idx, const uint32_t *n_ins_p, uint64_t max_ins, uint64_t *attach,
-                             cudaStream_t st);
-cudaError_t launch_dt_rehash(const DTrieDev &t, uint32_t max_seeds, uint8_t *root_out, cudaStream_t st);
-cudaError_t launch_dt_finish(const DTrieDev &t, uint32_t max_freed, uint8_t *root_out, cudaStream_t st);
+cudaError_t launch_dt_insert(const DTrieDev &t, const uint32_t *trie_of_key, const uint8_t *keys, const uint8_t *vals,
+                             const uint8_t *sroots, const uint32_t *ins_idx, const uint32_t *n_ins_p, uint64_t max_ins,
+                             uint64_t *attach, uint32_t *leaf_of, cudaStream_t st);
+cudaError_t launch_dt_rehash(const DTrieDev &t, uint32_t max_seeds, cudaStream_t st);
+cudaError_t launch_dt_finish(const DTrieDev &t, uint32_t max_freed, cudaStream_t st);
 cudaError_t launch_dt_stored_flags(const DTrieDev &t, uint32_t max_built, uint8_t *flags, uint32_t *n_hashes, cudaStream_t st);
 cudaError_t launch_dt_gather_updates(const DTrieDev &t, const uint32_t *stored_ids, uint32_t n_stored,
                                      const uint32_t *hash_prefix_by_record, const UpdatesDev &out, cudaStream_t st);
-cudaError_t launch_dt_removed_paths(const DTrieDev &t, uint32_t n_removed, uint8_t *path_len, uint8_t *path_packed, cudaStream_t st);
+cudaError_t launch_dt_removed_paths(const DTrieDev &t, uint32_t n_removed, uint8_t *path_len, uint8_t *path_packed,
+                                    uint32_t *trie_id, cudaStream_t st);
 
 }  // namespace b200
