@@ -311,6 +311,39 @@ B200_API uint64_t b200_dtrie_nodes(const b200_dtrie *);   /* node slots allocate
 B200_API uint64_t b200_dtrie_device_bytes(const b200_dtrie *);
 B200_API void b200_dtrie_destroy(b200_dtrie *);
 
+/* ------------------------------------------------------------------------------------------------ dynamic resident state
+ * b200_dtrie plus every storage trie: the whole hashed state (HashedAccounts + HashedStorages) lives in HBM as two arenas
+ * and a block's HashedPostStateSorted (crates/trie/common/src/hashed_state.rs:519-524,710-715) is applied in place —
+ * account upserts / destructions, per-account slot upserts / deletions (zero value) / wipes.  Storage roots flow into the
+ * account leaves on the device; only the touched paths of the touched tries are re-hashed.  This is the complete role
+ * of reth's SparseStateTrie on the live path (crates/trie/sparse/src/state.rs) and of StateRoot::overlay_root_with_updates
+ * (crates/trie/db/src/state.rs:184-230).  STATUS as b200_dtrie: emulation-validated, first B200 run pending.
+ *
+ * create: like b200_state_root_full (segment a = storage of account a).
+ * apply:  m account entries, keys strictly ascending; acct_flags[i]: bit 0 = exists after the block (0 = destroyed: its
+ *         storage trie is released), bit 1 = account data unchanged (accts[i] ignored; its leaf is re-hashed because its
+ *         storage root changes), bit 2 = storage wiped before this block's slots apply (HashedStorage::wiped); NULL =
+ *         all plain upserts.  Slots of entry i: seg_offsets[i] .. seg_offsets[i+1], keys ascending, zero value deletes.
+ *         Every account whose storage changes needs an entry.  Entries for absent accounts with bit 0 clear / bit 1 set
+ *         are ignored together with their slots.
+ * outputs (all optional): account TrieUpdates as in b200_dtrie_apply; storage records with trie_id = account entry
+ *         index; opt_storage_deleted[i] = 1 when entry i's storage trie was released (StorageTrieUpdates::is_deleted). */
+typedef struct b200_dstate b200_dstate;
+B200_API int32_t b200_dstate_create(b200_ctx *, const uint8_t *acct_keys32, const b200_account *accts, uint64_t n_accounts,
+                                    const uint8_t *slot_keys32, const uint8_t *values32_be, const uint64_t *seg_offsets,
+                                    b200_dstate **out, uint8_t root32[32] /* nullable */);
+B200_API int32_t b200_dstate_apply(b200_dstate *, const uint8_t *acct_keys32, const b200_account *accts,
+                                   const uint8_t *acct_flags, uint64_t m, const uint8_t *slot_keys32,
+                                   const uint8_t *values32_be, const uint64_t *seg_offsets, uint8_t root32[32],
+                                   b200_updates *opt_acct_updated, b200_updates *opt_acct_removed,
+                                   b200_updates *opt_storage_updated, b200_updates *opt_storage_removed,
+                                   uint8_t *opt_storage_deleted, b200_stats *opt_stats);
+B200_API int32_t b200_dstate_root(b200_dstate *, uint8_t root32[32]);
+B200_API uint64_t b200_dstate_accounts(const b200_dstate *);
+B200_API uint64_t b200_dstate_slots(const b200_dstate *);
+B200_API uint64_t b200_dstate_device_bytes(const b200_dstate *);
+B200_API void b200_dstate_destroy(b200_dstate *);
+
 #ifdef __cplusplus
 }
 #endif

@@ -150,6 +150,35 @@ static int32_t trie_create_locked(b200_ctx *c, const void *keys, const void *acc
     return B200_OK;
 }
 
+// A storage forest kept resident the same way (seed of the dynamic state): slot keys / values / segment table on the host
+// or the device (`kind`), roots of all segments in (*out)->seg_roots.  Caller holds the context lock.
+static int32_t forest_create_locked(b200_ctx *c, const void *slot_keys, const void *values, const void *seg_offsets,
+                                    uint64_t n_segs, uint64_t n_slots, cudaMemcpyKind kind, b200_trie **out) {
+    *out = nullptr;
+    CU(cudaSetDevice(c->device));
+    b200_trie *t = new b200_trie();
+    t->c = c;
+    t->n = n_slots;
+    t->forest = true;
+    t->n_segs = n_segs;
+    int32_t r = B200_OK;
+    auto put = [&](DevBuf &b, const void *src, size_t bytes) -> int32_t {
+        TRY(trie_alloc(t, b, bytes ? bytes : 16));
+        if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, kind, c->stream));
+        return B200_OK;
+    };
+    r = put(t->keys, slot_keys, n_slots * 32);
+    if (r == B200_OK) r = put(t->accts, values, n_slots * 32);
+    if (r == B200_OK) r = put(t->seg_offsets, seg_offsets, (n_segs + 1) * 8);
+    if (r == B200_OK) r = trie_build_owned(t);
+    if (r != B200_OK) {
+        b200_trie_destroy(t);
+        return r;
+    }
+    *out = t;
+    return B200_OK;
+}
+
 static int32_t trie_create_common(b200_ctx *c, const void *keys, const void *accts, const void *sroots, uint64_t n,
                                   cudaMemcpyKind kind, b200_trie **out, void *root_out) {
     if (!c || !out || (n && (!keys || !accts))) return fail(c, B200_ERR_INVALID_ARG, "bad argument");

@@ -733,6 +733,68 @@ __global__ void dt_gather_updates_kernel(DTrieDev t, const uint32_t *__restrict_
         }
 }
 
+// ------------------------------------------------------------------------------------------------ dynamic state glue
+// Which storage tries a block wipes: the tries of destroyed accounts and of accounts flagged "storage wiped"
+// (HashedStorage::wiped, crates/trie/common/src/hashed_state.rs:423-428).  Trie id = id of the account's leaf.
+__global__ void dt_wipe_list_kernel(const uint8_t *__restrict__ kind, const uint8_t *__restrict__ flags,
+                                    const uint32_t *__restrict__ leaf_of, uint64_t m, uint32_t *__restrict__ tries,
+                                    uint32_t *__restrict__ count) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint8_t k = kind[i];
+    bool wiped = flags != nullptr && (flags[i] & 4);
+    if (k == DK_DELETE || (wiped && (k == DK_UPDATE || k == DK_TOUCH))) tries[atomicAdd(count, 1u)] = leaf_of[i];
+}
+static __device__ __forceinline__ void dt_wipe_leaf(const DTrieDev &t, uint32_t x) {
+    t.lmeta[x] = DT_DEAD;
+    t.lseed[x] = 0;
+    t.leaf_free[atomicAdd(&t.g[DG_LEAF_FREE], 1u)] = x;
+    atomicSub(&t.g[DG_NLEAVES], 1u);
+}
+// breadth-first release of whole tries: no removed-node records (reth reports a wiped storage trie as is_deleted)
+__global__ void dt_wipe_begin_kernel(DTrieDev t, const uint32_t *__restrict__ tries, const uint32_t *__restrict__ count_p,
+                                     uint32_t *__restrict__ next, uint32_t *next_count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count_p) return;
+    uint32_t r = tries[i], w = t.troot[r];
+    if (w == DT_NONE) return;
+    dt_set_child(t, r, DT_NONE, 0, DT_NONE);
+    if (w & DT_LEAF) dt_wipe_leaf(t, w & ~DT_LEAF);
+    else next[atomicAdd(next_count, 1u)] = w;
+}
+__global__ void dt_wipe_round_kernel(DTrieDev t, const uint32_t *__restrict__ list, const uint32_t *__restrict__ count_p,
+                                     uint32_t *__restrict__ next, uint32_t *next_count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count_p) return;
+    uint32_t v = list[i];
+    const uint32_t *ch = t.nchild + 16 * (uint64_t)v;
+    for (int s = 0; s < 16; s++) {
+        uint32_t w = ch[s];
+        if (w == DT_NONE) continue;
+        if (w & DT_LEAF) dt_wipe_leaf(t, w & ~DT_LEAF);
+        else next[atomicAdd(next_count, 1u)] = w;
+    }
+    t.ndepth[v] = DT_DEAD;
+    t.nmeta[v] = 0;
+    t.npending[v] = 0;
+    t.node_free[atomicAdd(&t.g[DG_NODE_FREE], 1u)] = v;
+}
+// trie_of_key[j] for storage entry j of account entry i (seg_offsets[i] <= j < seg_offsets[i+1]): the account's leaf if
+// the account exists after the block, DT_NONE (entry ignored) otherwise
+__global__ void dt_expand_tries_kernel(const uint64_t *__restrict__ seg_offsets, uint64_t m, const uint8_t *__restrict__ kind,
+                                       const uint32_t *__restrict__ leaf_of, uint64_t n_entries, uint32_t *__restrict__ trie_of_key) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_entries) return;
+    uint64_t lo = 0, hi = m;  // last account with offset <= j
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (seg_offsets[mid] <= j) lo = mid;
+        else hi = mid;
+    }
+    uint8_t k = kind[lo];
+    trie_of_key[j] = (k == DK_UPDATE || k == DK_TOUCH || k == DK_INSERT) ? leaf_of[lo] : DT_NONE;
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 // leaf_trie: trie (segment) of every leaf of a forest build, nullptr for a single trie
 cudaError_t launch_dt_convert(const ForestDev &f, uint32_t n_nodes, const uint32_t *leaf_parent, const uint32_t *node_parent,
@@ -805,5 +867,25 @@ cudaError_t launch_dt_gather_updates(const DTrieDev &t, const uint32_t *stored_i
 cudaError_t launch_dt_removed_paths(const DTrieDev &t, uint32_t n_removed, uint8_t *path_len, uint8_t *path_packed,
                                     uint32_t *trie_id, cudaStream_t st) {
     if (n_removed) dt_removed_paths_kernel<<<blocks_for(n_removed, 128), 128, 0, st>>>(t, n_removed, path_len, path_packed, trie_id);
+    return cudaGetLastError();
+}
+cudaError_t launch_dt_wipe_list(const uint8_t *kind, const uint8_t *flags, const uint32_t *leaf_of, uint64_t m, uint32_t *tries,
+                                uint32_t *count, cudaStream_t st) {
+    if (m) dt_wipe_list_kernel<<<blocks_for(m, 256), 256, 0, st>>>(kind, flags, leaf_of, m, tries, count);
+    return cudaGetLastError();
+}
+cudaError_t launch_dt_wipe_begin(const DTrieDev &t, const uint32_t *tries, const uint32_t *count_p, uint32_t max_count,
+                                 uint32_t *next, uint32_t *next_count, cudaStream_t st) {
+    if (max_count) dt_wipe_begin_kernel<<<blocks_for(max_count, 128), 128, 0, st>>>(t, tries, count_p, next, next_count);
+    return cudaGetLastError();
+}
+cudaError_t launch_dt_wipe_round(const DTrieDev &t, const uint32_t *list, const uint32_t *count_p, uint32_t max_count,
+                                 uint32_t *next, uint32_t *next_count, cudaStream_t st) {
+    if (max_count) dt_wipe_round_kernel<<<blocks_for(max_count, 128), 128, 0, st>>>(t, list, count_p, next, next_count);
+    return cudaGetLastError();
+}
+cudaError_t launch_dt_expand_tries(const uint64_t *seg_offsets, uint64_t m, const uint8_t *kind, const uint32_t *leaf_of,
+                                   uint64_t n_entries, uint32_t *trie_of_key, cudaStream_t st) {
+    if (n_entries) dt_expand_tries_kernel<<<blocks_for(n_entries, 256), 256, 0, st>>>(seg_offsets, m, kind, leaf_of, n_entries, trie_of_key);
     return cudaGetLastError();
 }

@@ -457,3 +457,79 @@ class DynamicTrie:
             self.close()
         except Exception:
             pass
+
+
+class DynamicState:
+    """Handle on a b200_dstate: accounts AND all storage tries resident; `apply` commits one block's hashed post state in
+    place (see include/b200trie.h).  Emulation-validated; first B200 run pending."""
+    EXISTS, UNCHANGED, WIPED = 1, 2, 4
+
+    def __init__(self, engine: Engine, handle, root: bytes):
+        self.engine, self.handle, self._root = engine, handle, root
+
+    @classmethod
+    def create(cls, engine: Engine, acct_keys, accounts, slot_keys, values, seg_offsets) -> "DynamicState":
+        acct_keys = _np(acct_keys).reshape(-1, 32)
+        accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
+        slot_keys = _np(slot_keys).reshape(-1, 32)
+        values = _np(values).reshape(-1, 32)
+        seg_offsets = _np(seg_offsets, np.uint64)
+        if len(seg_offsets) != len(acct_keys) + 1:
+            raise ValueError("seg_offsets must have n_accounts+1 entries")
+        h = C.c_void_p()
+        root = np.empty(32, np.uint8)
+        engine._check(engine.lib.b200_dstate_create(engine.ctx, _ptr(acct_keys), _ptr(accounts), len(acct_keys),
+                                                    _ptr(slot_keys), _ptr(values), _ptr(seg_offsets), C.byref(h), _ptr(root)))
+        return cls(engine, h, root.tobytes())
+
+    def apply(self, acct_keys, accounts, flags, slot_keys, values, seg_offsets, want_updates=False):
+        """-> root, or (root, acct_updated, acct_removed_paths, storage_updated, storage_removed [(entry, path)],
+        storage_deleted flags) with want_updates."""
+        acct_keys = _np(acct_keys).reshape(-1, 32)
+        m = len(acct_keys)
+        accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
+        fl = None if flags is None else _np(np.asarray(flags, dtype=np.uint8))
+        slot_keys = _np(slot_keys).reshape(-1, 32)
+        values = _np(values).reshape(-1, 32)
+        seg_offsets = _np(seg_offsets, np.uint64)
+        if len(seg_offsets) != m + 1:
+            raise ValueError("seg_offsets must have m+1 entries")
+        root = np.empty(32, np.uint8)
+        au, ar, su, sr, s = Updates(), Updates(), Updates(), Updates(), Stats()
+        deleted = np.zeros(max(m, 1), np.uint8)
+        w = want_updates
+        self.engine._check(self.engine.lib.b200_dstate_apply(
+            self.handle, _ptr(acct_keys), _ptr(accounts), _ptr(fl), m, _ptr(slot_keys), _ptr(values), _ptr(seg_offsets),
+            _ptr(root), C.byref(au) if w else None, C.byref(ar) if w else None, C.byref(su) if w else None,
+            C.byref(sr) if w else None, _ptr(deleted) if w else None, C.byref(s)))
+        self._root = root.tobytes()
+        if not w:
+            return self._root
+        lib = self.engine.lib
+        return (self._root, updates_to_records(au, lib), [r[1] for r in updates_to_records(ar, lib)],
+                updates_to_records(su, lib), [(r[0], r[1]) for r in updates_to_records(sr, lib)], deleted[:m].copy())
+
+    def root(self) -> bytes:
+        out = np.empty(32, np.uint8)
+        self.engine._check(self.engine.lib.b200_dstate_root(self.handle, _ptr(out)))
+        return out.tobytes()
+
+    def accounts(self) -> int:
+        return int(self.engine.lib.b200_dstate_accounts(self.handle))
+
+    def slots(self) -> int:
+        return int(self.engine.lib.b200_dstate_slots(self.handle))
+
+    def device_bytes(self) -> int:
+        return int(self.engine.lib.b200_dstate_device_bytes(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.engine.lib.b200_dstate_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,216 @@
+"""Dynamic resident state (b200_dstate_*): accounts and every storage trie resident; blocks of account
+upserts / destructions and slot upserts / deletions / wipes applied in place.  After every block the root equals the
+oracle's from-scratch StateRoot over the merged state, and the account / storage TrieUpdates applied to a model of
+AccountsTrie / StoragesTrie reproduce the oracle's full node sets (reth's incremental == full criterion,
+crates/trie/db/tests/trie.rs:680-717, crates/trie/parallel/src/root.rs:287-400).
+
+Gate: emulation-validated only so far (`pytest -m gpu --emu`); opt-in on a GPU with B200_DTRIE_ON_GPU=1."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = [
+    pytest.mark.gpu,
+    pytest.mark.skipif(not (os.environ.get("B200_EMU") or os.environ.get("B200_DTRIE_ON_GPU")),
+                       reason="dynamic state: validated under tools/emu only; set B200_DTRIE_ON_GPU=1 to run on a GPU"),
+]
+
+EXISTS, UNCHANGED, WIPED = 1, 2, 4
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from reth_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def acct(nonce, balance=0):
+    a = np.zeros((), oracle.ACCOUNT_DTYPE)
+    a["nonce"] = nonce
+    a["balance"] = np.frombuffer(int(balance).to_bytes(32, "big"), np.uint8)
+    a["code_hash"] = np.frombuffer(oracle.KECCAK_EMPTY, np.uint8)
+    return a
+
+
+def flatten(state):
+    """state: {addr: (account, {slot: int})} -> flat sorted arrays"""
+    ks = sorted(state)
+    n = len(ks)
+    keys = np.frombuffer(b"".join(ks), np.uint8).reshape(n, 32) if n else np.zeros((0, 32), np.uint8)
+    accs = np.zeros(n, oracle.ACCOUNT_DTYPE)
+    sk, sv, offs = [], [], [0]
+    for i, k in enumerate(ks):
+        accs[i] = state[k][0]
+        for s in sorted(state[k][1]):
+            sk.append(s)
+            sv.append(int(state[k][1][s]).to_bytes(32, "big"))
+        offs.append(len(sk))
+    skeys = np.frombuffer(b"".join(sk), np.uint8).reshape(-1, 32) if sk else np.zeros((0, 32), np.uint8)
+    svals = np.frombuffer(b"".join(sv), np.uint8).reshape(-1, 32) if sv else np.zeros((0, 32), np.uint8)
+    return ks, keys, accs, skeys, svals, np.array(offs, np.uint64)
+
+
+def model(state):
+    ks, keys, accs, skeys, svals, offs = flatten(state)
+    root, au, su = oracle.state_root_full(keys, accs, skeys, svals, offs, want_updates=True)
+    acct_nodes = {r[1]: r[2:] for r in au}
+    storage_nodes = {}
+    for r in su:
+        storage_nodes.setdefault(ks[r[0]], {})[r[1]] = r[2:]
+    return root, acct_nodes, storage_nodes
+
+
+class Harness:
+    def __init__(self, eng, state):
+        from reth_b200 import DynamicState
+        self.state = {k: (a.copy(), dict(s)) for k, (a, s) in state.items()}
+        _, keys, accs, skeys, svals, offs = flatten(self.state)
+        self.ds = DynamicState.create(eng, keys, accs, skeys, svals, offs)
+        root, self.adb, self.sdb = model(self.state)
+        assert self.ds._root == root
+
+    def commit(self, block):
+        """block: {addr: (flags, account, {slot: value})}"""
+        ks = sorted(block)
+        m = len(ks)
+        keys = np.frombuffer(b"".join(ks), np.uint8).reshape(m, 32) if m else np.zeros((0, 32), np.uint8)
+        accs = np.zeros(m, oracle.ACCOUNT_DTYPE)
+        flags = np.zeros(m, np.uint8)
+        sk, sv, offs = [], [], [0]
+        for i, k in enumerate(ks):
+            fl, a, slots = block[k]
+            flags[i], accs[i] = fl, a
+            for s in sorted(slots):
+                sk.append(s)
+                sv.append(int(slots[s]).to_bytes(32, "big"))
+            offs.append(len(sk))
+            # the model: HashedPostState overlay rules (hashed_cursor/post_state.rs:185-195,260-297)
+            if not (fl & EXISTS):
+                self.state.pop(k, None)
+                continue
+            if fl & UNCHANGED:
+                if k not in self.state:
+                    continue
+                cur_a, cur_s = self.state[k]
+            else:
+                cur_a, cur_s = a.copy(), (self.state[k][1] if k in self.state else {})
+            cur_s = {} if (fl & WIPED) else dict(cur_s)
+            for s, v in slots.items():
+                if v == 0:
+                    cur_s.pop(s, None)
+                else:
+                    cur_s[s] = v
+            self.state[k] = (cur_a, cur_s)
+        skeys = np.frombuffer(b"".join(sk), np.uint8).reshape(-1, 32) if sk else np.zeros((0, 32), np.uint8)
+        svals = np.frombuffer(b"".join(sv), np.uint8).reshape(-1, 32) if sv else np.zeros((0, 32), np.uint8)
+        root, au, ar, su, sr, deleted = self.ds.apply(keys, accs, flags, skeys, svals, np.array(offs, np.uint64),
+                                                      want_updates=True)
+        o_root, o_adb, o_sdb = model(self.state)
+        assert root == o_root == self.ds.root()
+        assert self.ds.accounts() == len(self.state)
+        assert self.ds.slots() == sum(len(s) for _, s in self.state.values())
+        for p in ar:
+            self.adb.pop(p, None)
+        for r in au:
+            self.adb[r[1]] = r[2:]
+        assert self.adb == o_adb
+        for i, k in enumerate(ks):
+            if deleted[i]:
+                self.sdb.pop(k, None)          # StorageTrieUpdates::is_deleted: clear the account's duplicates
+        for entry, p in sr:
+            self.sdb.get(ks[entry], {}).pop(p, None)
+        for r in su:
+            self.sdb.setdefault(ks[r[0]], {})[r[1]] = r[2:]
+        assert {k: v for k, v in self.sdb.items() if v} == o_sdb
+        return root
+
+
+def rkey(rng):
+    return rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+
+
+def random_state(rng, n, with_storage=0.4, max_slots=40):
+    st = {}
+    for _ in range(n):
+        slots = {}
+        if rng.random() < with_storage:
+            slots = {rkey(rng): int(rng.integers(1, 2**62)) for _ in range(int(rng.integers(1, max_slots)))}
+        st[rkey(rng)] = (acct(int(rng.integers(0, 50)), int(rng.integers(1, 2**60))), slots)
+    return st
+
+
+def random_block(rng, state, n_touch, step):
+    block = {}
+    live = sorted(state)
+    for _ in range(n_touch):
+        r = rng.integers(0, 7)
+        if r == 0 or not live:                                   # new account, maybe with storage
+            slots = {rkey(rng): int(rng.integers(1, 2**60)) for _ in range(int(rng.integers(0, 12)))}
+            block[rkey(rng)] = (EXISTS, acct(step, 5), slots)
+        elif r == 1:                                             # destroyed
+            block[live[rng.integers(0, len(live))]] = (0, acct(0), {})
+        elif r == 2:                                             # balance change only
+            k = live[rng.integers(0, len(live))]
+            a = state[k][0].copy()
+            a["nonce"] += 1
+            block[k] = (EXISTS, a, {})
+        elif r in (3, 4):                                        # storage-only change: new slots, changed slots, zeroed slots
+            k = live[rng.integers(0, len(live))]
+            cur = sorted(state[k][1])
+            slots = {rkey(rng): int(rng.integers(1, 2**60)) for _ in range(int(rng.integers(1, 6)))}
+            for s in cur[:int(rng.integers(0, 4))]:
+                slots[s] = 0 if rng.random() < 0.5 else int(rng.integers(1, 2**50))
+            block[k] = (EXISTS | UNCHANGED, acct(0), slots)
+        elif r == 5:                                             # wipe + refill (selfdestruct & recreate)
+            k = live[rng.integers(0, len(live))]
+            slots = {rkey(rng): int(rng.integers(1, 2**60)) for _ in range(int(rng.integers(0, 5)))}
+            block[k] = (EXISTS | WIPED, state[k][0].copy(), slots)
+        else:                                                    # storage for an account that does not exist: ignored
+            block[rkey(rng)] = (EXISTS | UNCHANGED, acct(0), {rkey(rng): 7})
+    return block
+
+
+@pytest.mark.parametrize("n0,blocks,touch", [(0, 5, 6), (3, 6, 5), (200, 8, 40), (1500, 5, 150)])
+def test_random_blocks_match_full_state_root(eng, n0, blocks, touch):
+    rng = np.random.default_rng(400 + n0)
+    h = Harness(eng, random_state(rng, n0))
+    for step in range(blocks):
+        h.commit(random_block(rng, h.state, touch, step + 1))
+    h.ds.close()
+
+
+def test_storage_lifecycle_of_one_account(eng):
+    rng = np.random.default_rng(9)
+    st = random_state(rng, 50, with_storage=0.0)
+    h = Harness(eng, st)
+    k = sorted(h.state)[7]
+    slots = [rkey(rng) for _ in range(300)]
+    h.commit({k: (EXISTS | UNCHANGED, acct(0), {s: i + 1 for i, s in enumerate(slots[:1])})})      # first slot: root = leaf
+    h.commit({k: (EXISTS | UNCHANGED, acct(0), {s: i + 1 for i, s in enumerate(slots)})})          # grows
+    h.commit({k: (EXISTS | UNCHANGED, acct(0), {s: 0 for s in slots[::2]})})                        # half deleted
+    h.commit({k: (EXISTS | UNCHANGED, acct(0), {s: 0 for s in slots[1::2]})})                       # empty again
+    assert h.ds.slots() == 0
+    h.commit({k: (EXISTS | UNCHANGED, acct(0), {s: 9 for s in slots[:40]})})
+    h.commit({k: (EXISTS | WIPED, h.state[k][0].copy(), {slots[0]: 1})})                            # wiped, one slot back
+    h.commit({k: (0, acct(0), {})})                                                                 # destroyed
+    assert h.ds.slots() == 0
+    h.commit({k: (EXISTS, acct(1, 1), {slots[5]: 5})})                                              # re-created
+    h.ds.close()
+
+
+def test_destroyed_and_recreated_in_neighbouring_blocks_reuses_slots(eng):
+    rng = np.random.default_rng(10)
+    h = Harness(eng, random_state(rng, 120, with_storage=0.8, max_slots=25))
+    for step in range(4):
+        live = sorted(h.state)
+        kill = {live[i]: (0, acct(0), {}) for i in rng.choice(len(live), 30, replace=False)}
+        h.commit(kill)
+        born = {rkey(rng): (EXISTS, acct(step), {rkey(rng): int(rng.integers(1, 2**40)) for _ in range(int(rng.integers(0, 20)))})
+                for _ in range(30)}
+        h.commit(born)
+    h.ds.close()
