@@ -9,5 +9,5 @@ from .hashed_state import (Account, HashedPostState, HashedPostStateSorted, Hash
                            HashedStorageSorted, KeccakKeyHasher, PrefixSet, PrefixSetMut, TriePrefixSets,
                            TriePrefixSetsMut, unpack_nibbles)
 from .stages import AccountHashingStage, MerkleStage, StageError, StorageHashingStage, Tables  # noqa: F401,E402
-from .trie import (BranchNodeCompact, ParallelStateRoot, ResidentStateRoot, StateRoot, StateRootError, StateRootProgress,  # noqa: F401,E402
+from .trie import (BranchNodeCompact, DynamicStateRoot, ParallelStateRoot, ResidentStateRoot, StateRoot, StateRootError, StateRootProgress,  # noqa: F401,E402
                    StorageRoot, StorageTrieUpdates, TrieUpdates)

@@ -292,3 +292,74 @@ class ResidentStateRoot:
 
     def close(self):
         self.trie.close()
+
+
+class DynamicStateRoot:
+    """Live-path commitment with the WHOLE hashed state resident in HBM (b200_dstate_*): accounts and every storage trie.
+
+    The role of reth's `SparseStateTrie` fed by the state-root task (crates/trie/sparse/src/state.rs,
+    crates/engine/tree/src/tree/payload_processor/sparse_trie.rs) and of `StateRoot::overlay_root_with_updates`
+    (crates/trie/db/src/state.rs:184-230): `commit(HashedPostState)` applies one block in place — new / changed /
+    destroyed accounts, slot writes, zeroed slots, wiped storages — and returns the new root with the block's
+    `TrieUpdates` (account_nodes, removed_nodes, storage_tries with is_deleted).  Nothing of the state is kept on the host.
+    Emulation-validated; first B200 run pending (include/b200trie.h)."""
+
+    def __init__(self, engine: Engine, state: HashedPostStateSorted):
+        from .engine import ACCOUNT_DTYPE, DynamicState
+        keys, accts, skeys, svals, offs = state.to_flat()
+        self.ds = DynamicState.create(engine, keys, accts, skeys, svals, offs)
+        self._dtype = ACCOUNT_DTYPE
+
+    def root(self) -> bytes:
+        return self.ds.root()
+
+    def commit(self, post) -> Tuple[bytes, TrieUpdates]:
+        """post: HashedPostState -> (root, TrieUpdates of the block)."""
+        from .engine import DynamicState as DS
+        touched = sorted(set(post.accounts) | set(post.storages))
+        m = len(touched)
+        keys = np.frombuffer(b"".join(touched), np.uint8).reshape(m, 32) if m else np.zeros((0, 32), np.uint8)
+        accts = np.zeros(m, self._dtype)
+        flags = np.zeros(m, np.uint8)
+        sk, sv, offs = [], [], [0]
+        for i, k in enumerate(touched):
+            hs = post.storages.get(k)
+            if k in post.accounts:
+                a = post.accounts[k]
+                if a is None:
+                    offs.append(len(sk))  # destroyed: flags 0, its slots (if any) are irrelevant
+                    continue
+                flags[i] = DS.EXISTS
+                accts[i]["nonce"] = a.nonce
+                accts[i]["balance"] = np.frombuffer(int(a.balance).to_bytes(32, "big"), np.uint8)
+                accts[i]["code_hash"] = np.frombuffer(a.code_hash(), np.uint8)
+            else:
+                flags[i] = DS.EXISTS | DS.UNCHANGED  # storage-only change
+            if hs is not None:
+                if hs.wiped:
+                    flags[i] |= DS.WIPED
+                for s, v in sorted(hs.storage.items()):
+                    sk.append(s)
+                    sv.append(int(v).to_bytes(32, "big"))
+            offs.append(len(sk))
+        skeys = np.frombuffer(b"".join(sk), np.uint8).reshape(-1, 32) if sk else np.zeros((0, 32), np.uint8)
+        svals = np.frombuffer(b"".join(sv), np.uint8).reshape(-1, 32) if sv else np.zeros((0, 32), np.uint8)
+        try:
+            root, au, ar, su, sr, deleted = self.ds.apply(keys, accts, flags, skeys, svals, np.array(offs, np.uint64),
+                                                          want_updates=True)
+        except Exception as e:  # noqa: BLE001
+            raise StateRootError(str(e)) from e
+        upd = TrieUpdates()
+        upd.account_nodes = _records_to_nodes(au).get(0, {})
+        upd.removed_nodes = {bytes(p) for p in ar}
+        per_entry = _records_to_nodes(su)
+        removed_per_entry: Dict[int, set] = {}
+        for entry, p in sr:
+            removed_per_entry.setdefault(entry, set()).add(bytes(p))
+        for i, k in enumerate(touched):
+            st = StorageTrieUpdates(bool(deleted[i]), per_entry.get(i, {}), removed_per_entry.get(i, set()))
+            upd.insert_storage_updates(k, st)
+        return root, upd
+
+    def close(self):
+        self.ds.close()

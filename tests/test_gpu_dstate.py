@@ -214,3 +214,74 @@ def test_destroyed_and_recreated_in_neighbouring_blocks_reuses_slots(eng):
                 for _ in range(30)}
         h.commit(born)
     h.ds.close()
+
+
+def test_dynamic_state_root_commits_hashed_post_states(eng):
+    """The host mirror: blocks arrive as reth's HashedPostState (accounts: Some / None = destroyed; storages with wiped
+    flag and zero = delete); after every block root and TrieUpdates agree with a from-scratch StateRoot over the merged
+    state (crates/trie/db/tests/trie.rs:680-717)."""
+    from reth_b200 import Account, DynamicStateRoot, HashedPostState, HashedStorage, StateRoot
+    rng = np.random.default_rng(78)
+    rk = lambda: bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+    base = HashedPostState()
+    for _ in range(500):
+        k = rk()
+        base.accounts[k] = Account(int(rng.integers(0, 50)), int(rng.integers(1, 2**62)))
+        if rng.random() < 0.3:
+            base.storages[k] = HashedStorage(False, {rk(): int(rng.integers(1, 2**62)) for _ in range(int(rng.integers(1, 30)))})
+    merged = HashedPostState(dict(base.accounts), {k: HashedStorage(False, dict(v.storage)) for k, v in base.storages.items()})
+    ds = DynamicStateRoot(eng, base.into_sorted())
+    root0, full0 = StateRoot(eng, base.into_sorted()).root_with_updates()
+    assert ds.root() == root0
+    acct_db = dict(full0.account_nodes)
+    stor_db = {k: dict(v.storage_nodes) for k, v in full0.storage_tries.items() if v.storage_nodes}
+    for block in range(5):
+        post = HashedPostState()
+        live = [k for k, a in merged.accounts.items() if a is not None]
+        for i in rng.choice(len(live), 30, replace=False):
+            a = merged.accounts[live[i]]
+            post.accounts[live[i]] = Account(a.nonce + 1, a.balance + 7, a.bytecode_hash)
+        for _ in range(8):
+            k = rk()
+            post.accounts[k] = Account(0, int(rng.integers(1, 10**18)))
+            if rng.random() < 0.5:
+                post.storages[k] = HashedStorage(False, {rk(): int(rng.integers(1, 2**60)) for _ in range(5)})
+        for i in rng.choice(len(live), 4, replace=False):
+            post.accounts[live[i]] = None
+            post.storages[live[i]] = HashedStorage(True, {})
+        with_storage = [k for k in merged.storages if merged.accounts.get(k) is not None and k not in post.accounts]
+        for k in with_storage[:6]:
+            slots = list(merged.storages[k].storage)
+            changes = {slots[0]: 0} if slots else {}
+            changes[rk()] = int(rng.integers(1, 2**60))
+            post.storages[k] = HashedStorage(block == 3, changes)
+        root, upd = ds.commit(post)
+        for k, hs in post.storages.items():
+            cur = {} if hs.wiped else dict(merged.storages.get(k, HashedStorage()).storage)
+            for s, v in hs.storage.items():
+                if v == 0:
+                    cur.pop(s, None)
+                else:
+                    cur[s] = v
+            merged.storages[k] = HashedStorage(False, cur)
+        for k, a in post.accounts.items():
+            if a is None:
+                merged.accounts.pop(k, None)
+                merged.storages.pop(k, None)
+            else:
+                merged.accounts[k] = a
+        o_root, o_full = StateRoot(eng, merged.into_sorted()).root_with_updates()
+        assert root == o_root, block
+        for p in upd.removed_nodes:
+            acct_db.pop(p, None)
+        acct_db.update(upd.account_nodes)
+        assert acct_db == o_full.account_nodes
+        for k, st in upd.storage_tries.items():
+            if st.is_deleted:
+                stor_db.pop(k, None)
+            cur = stor_db.setdefault(k, {})
+            for p in st.removed_nodes:
+                cur.pop(p, None)
+            cur.update(st.storage_nodes)
+        assert {k: v for k, v in stor_db.items() if v} == {k: v.storage_nodes for k, v in o_full.storage_tries.items() if v.storage_nodes}
+    ds.close()
