@@ -132,6 +132,7 @@ static int32_t map_dev_error(b200_ctx *c, int code) {
             return fail(c, B200_ERR_INLINE_HASH_CHILD, "inline (<32 byte) branch child under a hash_mask bit");
         case B200_DEVERR_BAD_OFFSETS: return fail(c, B200_ERR_INVALID_ARG, "seg_offsets must start at 0, end at n and be monotone");
         case B200_DEVERR_NOT_FOUND: return fail(c, B200_ERR_NOT_FOUND, "key not found in the resident trie");
+        case B200_DEVERR_CORRUPT: return fail(c, B200_ERR_CUDA, "dynamic trie: a walk exceeded 64 hops (damaged structure)");
         default: return fail(c, B200_ERR_CUDA, "unknown device error %d", code);
     }
 }

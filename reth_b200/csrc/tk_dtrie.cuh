@@ -90,11 +90,12 @@ static __device__ __forceinline__ void dt_seed(const DTrieDev &t, uint32_t word)
 }
 
 static __device__ __forceinline__ uint32_t dt_pop(uint32_t *count, const uint32_t *stack, uint32_t *bump) {
-    for (;;) {
+    for (int tries = 0; tries < 64; tries++) {  // under heavy contention give up on recycling and take a fresh slot
         uint32_t c = *(volatile uint32_t *)count;
-        if (c == 0) return atomicAdd(bump, 1u);
+        if (c == 0) break;
         if (atomicCAS(count, c, c - 1) == c) return stack[c - 1];
     }
+    return atomicAdd(bump, 1u);
 }
 static __device__ __forceinline__ uint32_t dt_alloc_leaf(const DTrieDev &t) {
     uint32_t id = dt_pop(&t.g[DG_LEAF_FREE], t.leaf_free, &t.g[DG_LEAF_ALLOC]);
@@ -214,7 +215,12 @@ static __device__ __forceinline__ DtLoc dt_descend(const DTrieDev &t, uint32_t t
     r.found = false;
     uint32_t cur = t.troot[trie];
     uint32_t matched = 0;  // nibbles known to agree with everything below `cur`
-    for (;;) {
+    for (int hops = 0;; hops++) {
+        if (hops > DT_MAX_HOPS) {  // depth grows with every hop: more than 64 means a damaged structure, never a long path
+            atomicExch(t.err, B200_DEVERR_CORRUPT);
+            r.child = DT_NONE;
+            return r;
+        }
         r.child = cur;
         if (cur == DT_NONE) return r;
         if (cur & DT_LEAF) {
@@ -391,7 +397,11 @@ static __device__ __forceinline__ uint32_t dt_insert_one(const DTrieDev &t, uint
     }
     t.lmeta[x] = 0;
     atomicAdd(&t.g[DG_NLEAVES], 1u);
-    for (;;) {
+    for (int hops = 0;; hops++) {
+        if (hops > DT_MAX_HOPS) {
+            atomicExch(t.err, B200_DEVERR_CORRUPT);
+            break;
+        }
         if (cur == DT_NONE) {
             dt_set_child(t, trie, parent, slot, x | DT_LEAF);
             t.lparent[x] = parent;
@@ -458,7 +468,11 @@ __global__ void dt_mark_kernel(DTrieDev t, const uint32_t *__restrict__ count_p)
     uint32_t s = t.seeds[i];
     if (!dt_alive(t, s)) return;
     uint32_t p = dt_parent_of(t, s);
-    while (p != DT_NONE) {
+    for (int hops = 0; p != DT_NONE; hops++) {
+        if (hops > DT_MAX_HOPS) {
+            atomicExch(t.err, B200_DEVERR_CORRUPT);
+            break;
+        }
         if (atomicAdd(&t.npending[p], 1u) != 0u) break;
         if (t.nseed[p]) break;
         p = t.nparent[p];
@@ -674,7 +688,12 @@ __global__ void __launch_bounds__(WARPS * 32) dt_wavefront_kernel(DTrieDev t, co
             p = t.nparent[s];
         }
         bool top = true;
-        while (p != DT_NONE) {
+        for (int hops = 0; p != DT_NONE; hops++) {
+            if (hops > DT_MAX_HOPS) {  // uniform across the warp
+                if (lane == 0) atomicExch(t.err, B200_DEVERR_CORRUPT);
+                top = false;
+                break;
+            }
             uint32_t last = 0;
             if (lane == 0) {
                 __threadfence();

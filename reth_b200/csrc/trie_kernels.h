@@ -14,6 +14,7 @@ enum : int {
     B200_DEVERR_INLINE_HASH_CHILD = 3,
     B200_DEVERR_BAD_OFFSETS = 4,
     B200_DEVERR_NOT_FOUND = 5,
+    B200_DEVERR_CORRUPT = 6,  // dynamic trie: a walk did not terminate within 64 hops
 };
 
 // node / leaf meta byte
@@ -134,6 +135,7 @@ cudaError_t launch_pick_subset(const uint32_t *ids, const uint32_t *prefix, cons
 constexpr uint32_t DT_NONE = 0xFFFFFFFFu;
 constexpr uint32_t DT_LEAF = 0x80000000u;
 constexpr uint8_t DT_DEAD = 0xFF;  // ndepth / lmeta of a freed slot
+constexpr int DT_MAX_HOPS = 66;
 
 enum : int {
     DG_UNUSED0 = 0,
