@@ -338,6 +338,15 @@ B200_API int32_t b200_dstate_apply(b200_dstate *, const uint8_t *acct_keys32, co
                                    b200_updates *opt_acct_updated, b200_updates *opt_acct_removed,
                                    b200_updates *opt_storage_updated, b200_updates *opt_storage_removed,
                                    uint8_t *opt_storage_deleted, b200_stats *opt_stats);
+/* Multi-GPU: one rank's shard of a state split by top key nibble (the layout of b200_subtrie_frontier).
+ * The shard keeps its accounts as 16 bucket tries; after every apply b200_dstate_frontier returns its 16 entries (empty
+ * for buckets it does not hold), the ranks all-gather them (NCCL, 16 x 68 bytes) and b200_root_from_frontier gives the
+ * state root.  root32 of create / apply is the root of the shard on its own (equal to the state root when one rank
+ * holds every bucket).  TrieUpdates are unaffected by the sharding (the depth-0 root branch is never stored). */
+B200_API int32_t b200_dstate_create_sharded(b200_ctx *, const uint8_t *acct_keys32, const b200_account *accts,
+                                            uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
+                                            const uint64_t *seg_offsets, b200_dstate **out, uint8_t root32[32]);
+B200_API int32_t b200_dstate_frontier(b200_dstate *, b200_frontier_entry out16[16]);
 B200_API int32_t b200_dstate_root(b200_dstate *, uint8_t root32[32]);
 B200_API uint64_t b200_dstate_accounts(const b200_dstate *);
 B200_API uint64_t b200_dstate_slots(const b200_dstate *);

@@ -574,6 +574,8 @@ struct b200_dstate {
     b200_ctx *c = nullptr;
     uint64_t bytes = 0;
     DArena acc, sto;
+    bool sharded = false;  // accounts as 16 top-nibble bucket tries: this state is one rank's shard
+    DevBuf bucket_roots, frontier, acct_tries;
     DevBuf root, in_akeys, in_accts, in_aflags, in_skeys, in_svals, in_offs, trie_of_key, wipe_a, wipe_b, wipe_cnt;
 };
 
@@ -584,7 +586,7 @@ extern "C" B200_API void b200_dstate_destroy(b200_dstate *t) {
     da_free(&t->acc);
     da_free(&t->sto);
     DevBuf *bufs[] = {&t->root, &t->in_akeys, &t->in_accts, &t->in_aflags, &t->in_skeys, &t->in_svals, &t->in_offs,
-                      &t->trie_of_key, &t->wipe_a, &t->wipe_b, &t->wipe_cnt};
+                      &t->trie_of_key, &t->wipe_a, &t->wipe_b, &t->wipe_cnt, &t->bucket_roots, &t->frontier, &t->acct_tries};
     for (DevBuf *b : bufs) dbuf_free(*b);
     delete t;
 }
@@ -602,9 +604,21 @@ extern "C" B200_API int32_t b200_dstate_root(b200_dstate *t, uint8_t root32[32])
     return B200_OK;
 }
 
-extern "C" B200_API int32_t b200_dstate_create(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
-                                               uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
-                                               const uint64_t *seg_offsets, b200_dstate **out, uint8_t root32[32]) {
+// this shard's 16 frontier entries and the root they give on their own (enqueued; t->frontier / t->root)
+static int32_t dstate_frontier_on_device(b200_dstate *t) {
+    b200_ctx *c = t->c;
+    DTrieDev d = da_view(&t->acc);
+    CU(launch_dt_frontier(d, static_cast<const uint8_t *>(t->bucket_roots.p), static_cast<FrontierEntryDev *>(t->frontier.p),
+                          c->stream));
+    CU(launch_root_from_frontier(static_cast<const FrontierEntryDev *>(t->frontier.p), static_cast<uint8_t *>(t->root.p),
+                                 c->stream));
+    c->launches += 2;
+    return B200_OK;
+}
+
+static int32_t dstate_create_impl(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts, uint64_t n_accounts,
+                                  const uint8_t *slot_keys32, const uint8_t *values32_be, const uint64_t *seg_offsets,
+                                  bool sharded, b200_dstate **out, uint8_t root32[32]) {
     if (!c || !out || !seg_offsets || (n_accounts && (!acct_keys32 || !accts))) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
     *out = nullptr;
     TRY(check_offsets_host(c, seg_offsets, n_accounts));
@@ -615,7 +629,22 @@ extern "C" B200_API int32_t b200_dstate_create(b200_ctx *c, const uint8_t *acct_
     b200_trie *src_s = nullptr, *src_a = nullptr;
     TRY(forest_create_locked(c, slot_keys32, values32_be, seg_offsets, n_accounts, n_slots, cudaMemcpyHostToDevice, &src_s));
     // the account trie takes its storage roots straight from the forest build (device memory: cudaMemcpyDefault)
-    int32_t r = trie_create_locked(c, acct_keys32, accts, src_s->seg_roots.p, n_accounts, cudaMemcpyDefault, &src_a, nullptr);
+    int32_t r;
+    if (sharded) {
+        uint64_t bucket_offsets[17];
+        for (uint32_t b = 0; b <= 16; b++) {  // first account whose top nibble >= b
+            uint64_t lo = 0, hi = n_accounts;
+            while (lo < hi) {
+                uint64_t mid = (lo + hi) >> 1;
+                if ((uint32_t)(acct_keys32[32 * mid] >> 4) < b) lo = mid + 1;
+                else hi = mid;
+            }
+            bucket_offsets[b] = lo;
+        }
+        r = bucket_forest_create_locked(c, acct_keys32, accts, src_s->seg_roots.p, n_accounts, bucket_offsets, cudaMemcpyDefault, &src_a);
+    } else {
+        r = trie_create_locked(c, acct_keys32, accts, src_s->seg_roots.p, n_accounts, cudaMemcpyDefault, &src_a, nullptr);
+    }
     if (r != B200_OK) {
         b200_trie_destroy(src_s);
         return r;
@@ -626,17 +655,28 @@ extern "C" B200_API int32_t b200_dstate_create(b200_ctx *c, const uint8_t *acct_
     t->acc.bytes = t->sto.bytes = &t->bytes;
     t->acc.account = true;
     t->acc.has_sroots = true;
+    t->acc.forest = sharded;
+    t->sharded = sharded;
     t->sto.account = false;
     t->sto.forest = true;
     auto body = [&]() -> int32_t {
         TRY(da_resize(&t->acc, t->root, 64, 0, -1));
-        t->acc.top_out = static_cast<uint8_t *>(t->root.p);
-        t->acc.top_stride = 0;
-        TRY(da_from_build(&t->acc, src_a, 1));
+        if (sharded) {
+            TRY(da_resize(&t->acc, t->bucket_roots, 16 * 32, 0, 0));
+            TRY(da_resize(&t->acc, t->frontier, 16 * sizeof(FrontierEntryDev), 0, 0));
+            CU(cudaMemcpyAsync(t->bucket_roots.p, src_a->seg_roots.p, 16 * 32, cudaMemcpyDeviceToDevice, st));
+            t->acc.top_out = static_cast<uint8_t *>(t->bucket_roots.p);
+            t->acc.top_stride = 32;
+        } else {
+            t->acc.top_out = static_cast<uint8_t *>(t->root.p);
+            t->acc.top_stride = 0;
+        }
+        TRY(da_from_build(&t->acc, src_a, sharded ? 16 : 1));
         t->sto.top_out = static_cast<uint8_t *>(t->acc.lsroot.p);
         t->sto.top_stride = 32;
         TRY(da_from_build(&t->sto, src_s, t->acc.lcap));
-        CU(cudaMemcpyAsync(t->root.p, src_a->root.p, 32, cudaMemcpyDeviceToDevice, st));
+        if (sharded) TRY(dstate_frontier_on_device(t));
+        else CU(cudaMemcpyAsync(t->root.p, src_a->root.p, 32, cudaMemcpyDeviceToDevice, st));
         if (root32) CU(cudaMemcpyAsync(root32, t->root.p, 32, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         return B200_OK;
@@ -649,6 +689,32 @@ extern "C" B200_API int32_t b200_dstate_create(b200_ctx *c, const uint8_t *acct_
         return r;
     }
     *out = t;
+    return B200_OK;
+}
+
+extern "C" B200_API int32_t b200_dstate_create(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
+                                               uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
+                                               const uint64_t *seg_offsets, b200_dstate **out, uint8_t root32[32]) {
+    return dstate_create_impl(c, acct_keys32, accts, n_accounts, slot_keys32, values32_be, seg_offsets, false, out, root32);
+}
+// One rank's shard of a state that is split by top key nibble (any subset of the 16 buckets).  root32 (nullable) receives
+// the root this shard has on its own; the global root is b200_root_from_frontier over the gathered b200_dstate_frontier
+// entries of all ranks.
+extern "C" B200_API int32_t b200_dstate_create_sharded(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
+                                                       uint64_t n_accounts, const uint8_t *slot_keys32,
+                                                       const uint8_t *values32_be, const uint64_t *seg_offsets,
+                                                       b200_dstate **out, uint8_t root32[32]) {
+    return dstate_create_impl(c, acct_keys32, accts, n_accounts, slot_keys32, values32_be, seg_offsets, true, out, root32);
+}
+// The 16 top-nibble frontier entries of a sharded state as of its last apply (empty entries for buckets it does not hold).
+extern "C" B200_API int32_t b200_dstate_frontier(b200_dstate *t, b200_frontier_entry out16[16]) {
+    if (!t || !out16) return fail(t ? t->c : nullptr, B200_ERR_INVALID_ARG, "bad argument");
+    b200_ctx *c = t->c;
+    if (!t->sharded) return fail(c, B200_ERR_INVALID_ARG, "not a sharded state (b200_dstate_create_sharded)");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(out16, t->frontier.p, 16 * sizeof(FrontierEntryDev), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return B200_OK;
 }
 
@@ -690,7 +756,14 @@ extern "C" B200_API int32_t b200_dstate_apply(b200_dstate *t, const uint8_t *acc
         TRY(h2d_into(A, t->in_offs, seg_offsets, (m + 1) * 8));
         const uint8_t *d_flags = acct_flags ? static_cast<const uint8_t *>(t->in_aflags.p) : nullptr;
         // ---- accounts: structure only (their leaves are re-hashed after the storage roots are known)
-        TRY(da_restructure(A, nullptr, static_cast<const uint8_t *>(t->in_akeys.p), static_cast<const uint8_t *>(t->in_accts.p),
+        const uint32_t *d_acct_tries = nullptr;
+        if (t->sharded) {  // bucket trie of every account entry = its top key nibble
+            TRY(da_scratch(A, t->acct_tries, m * 4));
+            CU(launch_dt_nibble_tries(static_cast<const uint8_t *>(t->in_akeys.p), m, static_cast<uint32_t *>(t->acct_tries.p), st));
+            c->launches++;
+            d_acct_tries = static_cast<const uint32_t *>(t->acct_tries.p);
+        }
+        TRY(da_restructure(A, d_acct_tries, static_cast<const uint8_t *>(t->in_akeys.p), static_cast<const uint8_t *>(t->in_accts.p),
                            d_flags, nullptr, m));
         const uint8_t *a_kind = static_cast<const uint8_t *>(A->kind.p);
         const uint32_t *a_leaf = static_cast<const uint32_t *>(A->leaf_of.p);
@@ -739,6 +812,7 @@ extern "C" B200_API int32_t b200_dstate_apply(b200_dstate *t, const uint8_t *acc
         }
         // ---- accounts: re-hash
         TRY(da_rehash(A, m));
+        if (t->sharded) TRY(dstate_frontier_on_device(t));
         c->stats.leaves_added += m;
         // what the host needs to label the storage records
         h_kind.resize(m);

@@ -17,6 +17,7 @@ struct b200_trie {
     // a storage FOREST instead of the account trie (used to seed the dynamic state, eng_dtrie.inl): `accts` then holds
     // the 32-byte slot values, seg_offsets the n_segs+1 segment bounds, seg_roots receives the n_segs storage roots
     bool forest = false;
+    bool forest_account = false;  // forest of ACCOUNT tries (top-nibble buckets of a sharded state): accts / sroots as usual
     uint64_t n_segs = 0;
     DevBuf seg_offsets, seg_roots;
     uint64_t bytes = 0;
@@ -72,9 +73,18 @@ static int32_t trie_build_owned(b200_trie *t) {
     TRY(trie_alloc(t, t->root, 64));
     if (t->forest) {
         TRY(trie_alloc(t, t->seg_roots, (t->n_segs ? t->n_segs : 1) * 32));
-        TRY(storage_roots_on_device(c, static_cast<const uint8_t *>(t->keys.p), static_cast<const uint8_t *>(t->accts.p),
-                                    static_cast<const uint64_t *>(t->seg_offsets.p), t->n_segs, t->n,
-                                    static_cast<uint8_t *>(t->seg_roots.p), true, b));
+        if (t->forest_account) {
+            TRY(build_forest(c, static_cast<const uint8_t *>(t->keys.p), t->n, static_cast<const uint64_t *>(t->seg_offsets.p),
+                             t->n_segs, true, static_cast<const uint8_t *>(t->accts.p),
+                             t->has_sroots ? static_cast<const uint8_t *>(t->sroots.p) : nullptr, true, b));
+            CU(launch_segment_roots(b.f, static_cast<const uint64_t *>(t->seg_offsets.p), t->n_segs,
+                                    static_cast<uint8_t *>(t->seg_roots.p), c->stream));
+            c->launches++;
+        } else {
+            TRY(storage_roots_on_device(c, static_cast<const uint8_t *>(t->keys.p), static_cast<const uint8_t *>(t->accts.p),
+                                        static_cast<const uint64_t *>(t->seg_offsets.p), t->n_segs, t->n,
+                                        static_cast<uint8_t *>(t->seg_roots.p), true, b));
+        }
     } else {
         TRY(account_root_on_device(c, static_cast<const uint8_t *>(t->keys.p), static_cast<const uint8_t *>(t->accts.p),
                                    t->has_sroots ? static_cast<const uint8_t *>(t->sroots.p) : nullptr, t->n,
@@ -170,6 +180,36 @@ static int32_t forest_create_locked(b200_ctx *c, const void *slot_keys, const vo
     r = put(t->keys, slot_keys, n_slots * 32);
     if (r == B200_OK) r = put(t->accts, values, n_slots * 32);
     if (r == B200_OK) r = put(t->seg_offsets, seg_offsets, (n_segs + 1) * 8);
+    if (r == B200_OK) r = trie_build_owned(t);
+    if (r != B200_OK) {
+        b200_trie_destroy(t);
+        return r;
+    }
+    *out = t;
+    return B200_OK;
+}
+
+// The accounts of one shard as a forest of 16 top-nibble bucket tries (seg_offsets: 17 bucket bounds on the host).
+static int32_t bucket_forest_create_locked(b200_ctx *c, const void *keys, const void *accts, const void *sroots, uint64_t n,
+                                           const uint64_t *bucket_offsets17, cudaMemcpyKind kind, b200_trie **out) {
+    *out = nullptr;
+    CU(cudaSetDevice(c->device));
+    b200_trie *t = new b200_trie();
+    t->c = c;
+    t->n = n;
+    t->forest = t->forest_account = true;
+    t->n_segs = 16;
+    t->has_sroots = sroots != nullptr;
+    int32_t r = B200_OK;
+    auto put = [&](DevBuf &b, const void *src, size_t bytes, cudaMemcpyKind k) -> int32_t {
+        TRY(trie_alloc(t, b, bytes ? bytes : 16));
+        if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, k, c->stream));
+        return B200_OK;
+    };
+    r = put(t->keys, keys, n * 32, kind);
+    if (r == B200_OK) r = put(t->accts, accts, n * 72, kind);
+    if (r == B200_OK && sroots) r = put(t->sroots, sroots, n * 32, kind);
+    if (r == B200_OK) r = put(t->seg_offsets, bucket_offsets17, 17 * 8, cudaMemcpyHostToDevice);
     if (r == B200_OK) r = trie_build_owned(t);
     if (r != B200_OK) {
         b200_trie_destroy(t);

@@ -495,8 +495,11 @@ __global__ void dt_starts_kernel(DTrieDev t, const uint32_t *__restrict__ count_
 }
 
 // One warp builds node v from its 16 child slots (lane = nibble).  All 32 lanes must call.
-__device__ __forceinline__ void dt_warp_build_node(const DTrieDev &t, uint32_t v, uint8_t *buf, const WarpKeccak &kw, int lane,
-                                                   uint32_t &hashed, uint32_t &exts, uint32_t (&out)[8]) {
+// PD_OVERRIDE >= -1: encode as if the parent were at that depth and leave the arena untouched (multi-GPU frontier:
+// a bucket's top node as child of the depth-0 root branch); returns the RlpNode meta (inline length | META_EXT ...).
+template <int PD_OVERRIDE = -2>
+__device__ __forceinline__ uint32_t dt_warp_build_node(const DTrieDev &t, uint32_t v, uint8_t *buf, const WarpKeccak &kw, int lane,
+                                                       uint32_t &hashed, uint32_t &exts, uint32_t (&out)[8]) {
     uint32_t *bufw = reinterpret_cast<uint32_t *>(buf);
     const int d = t.ndepth[v];
     const uint32_t cw = lane < 16 ? t.nchild[16 * (uint64_t)v + lane] : DT_NONE;
@@ -560,7 +563,7 @@ __device__ __forceinline__ void dt_warp_build_node(const DTrieDev &t, uint32_t v
     }
     __syncwarp();
     const uint32_t par = t.nparent[v];
-    const int pd = par == DT_NONE ? -1 : (int)t.ndepth[par];
+    const int pd = PD_OVERRIDE >= -1 ? PD_OVERRIDE : (par == DT_NONE ? -1 : (int)t.ndepth[par]);
     const bool is_root = pd < 0, need_ext = pd + 1 < d;
     uint32_t meta;
     if (total >= 32 || (is_root && !need_ext)) {
@@ -608,6 +611,10 @@ __device__ __forceinline__ void dt_warp_build_node(const DTrieDev &t, uint32_t v
         }
         exts += lane == 0;
     }
+    if (PD_OVERRIDE >= -1) {
+        __syncwarp();
+        return meta;
+    }
     if (lane == 0) {
         if ((tree_mask | hash_mask) != 0) meta |= META_STORED;
         if ((t.nmeta[v] & META_STORED) && !(meta & META_STORED)) dt_record_removed(t, v);
@@ -618,6 +625,7 @@ __device__ __forceinline__ void dt_warp_build_node(const DTrieDev &t, uint32_t v
         t.built[atomicAdd(&t.g[DG_BUILT], 1u)] = v;
     }
     __syncwarp();
+    return meta;
 }
 
 // One warp per seed: re-hash the item if nothing below it is dirty, then climb; the last dirty child to arrive at a
@@ -750,6 +758,69 @@ __global__ void dt_gather_updates_kernel(DTrieDev t, const uint32_t *__restrict_
             dt_copy32(out.hashes + 32 * (uint64_t)h, t.nref + 32 * (uint64_t)ch[s]);
             h++;
         }
+}
+
+// ------------------------------------------------------------------------------------------------ sharded accounts
+// Multi-GPU layout of §6 for the dynamic state: the account arena holds one trie per top-nibble bucket (trie id = nibble,
+// every bucket a trie of its own, so its root hash is the frontier's as_root); as_child re-encodes the bucket's top item
+// as a child of the depth-0 root branch.  One warp per bucket.
+__global__ void dt_nibble_tries_kernel(const uint8_t *__restrict__ keys, uint64_t m, uint32_t *__restrict__ trie_of_key) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) trie_of_key[i] = keys[32 * i] >> 4;
+}
+__global__ void __launch_bounds__(512) dt_frontier_kernel(DTrieDev t, const uint8_t *__restrict__ bucket_roots,
+                                                          FrontierEntryDev *__restrict__ out) {
+    __shared__ __align__(16) uint8_t sbuf[16][WARP_BUF];
+    const int lane = threadIdx.x & 31, b = threadIdx.x >> 5;
+    uint8_t *buf = sbuf[b];
+    uint32_t *bufw = reinterpret_cast<uint32_t *>(buf);
+    WarpKeccak kw;
+    kw.init(lane);
+    FrontierEntryDev &e = out[b];
+    for (int i = lane; i < (int)sizeof(FrontierEntryDev); i += 32) reinterpret_cast<uint8_t *>(&e)[i] = 0;
+    __syncwarp();
+    const uint32_t w = t.troot[b];
+    if (w == DT_NONE || *(volatile int *)t.err != B200_DEVERR_NONE) return;
+    uint32_t out8[8], hashed = 0, exts = 0, meta;
+    if (w & DT_LEAF) {
+        const uint32_t x = w & ~DT_LEAF;
+        for (uint32_t q = lane; q < 68; q += 32) bufw[q] = 0;
+        __syncwarp();
+        uint32_t len = 0;
+        if (lane == 0) {
+            uint32_t k[8];
+            load32_nc(t.lkey + 32 * (uint64_t)x, k);
+            LinBuf lb{buf, 0};
+            len = encode_leaf<LinBuf, true>(lb, k, 0, t.lval + 72 * (uint64_t)x, t.lsroot ? t.lsroot + 32 * (uint64_t)x : nullptr, t.err);
+            buf[len] |= 0x01;
+            buf[(len / 136 + 1) * 136 - 1] |= 0x80;
+        }
+        len = __shfl_sync(0xffffffffu, len, 0);
+        __syncwarp();
+        uint64_t a = kw.hash(buf, len / 136 + 1, lane);  // account leaves are >= 70 bytes: always a hash reference
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint64_t v = shfl64(a, q);
+            out8[2 * q] = (uint32_t)v;
+            out8[2 * q + 1] = (uint32_t)(v >> 32);
+        }
+        meta = 0;
+    } else {
+        meta = dt_warp_build_node<0>(t, w, buf, kw, lane, hashed, exts, out8);
+    }
+    if (lane == 0) {
+        e.as_root_len = 32;
+        for (int i = 0; i < 32; i++) e.as_root[i] = bucket_roots[32 * b + i];
+        uint32_t il = meta & META_LEN;
+        if (il == 0) {
+            e.as_child_len = 33;
+            e.as_child[0] = 0xa0;
+            for (int i = 0; i < 32; i++) e.as_child[1 + i] = (uint8_t)(out8[i >> 2] >> (8 * (i & 3)));
+        } else {
+            e.as_child_len = (uint8_t)il;
+            for (uint32_t i = 0; i < il; i++) e.as_child[i] = (uint8_t)(out8[i >> 2] >> (8 * (i & 3)));
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ dynamic state glue
@@ -906,5 +977,13 @@ cudaError_t launch_dt_wipe_round(const DTrieDev &t, const uint32_t *list, const 
 cudaError_t launch_dt_expand_tries(const uint64_t *seg_offsets, uint64_t m, const uint8_t *kind, const uint32_t *leaf_of,
                                    uint64_t n_entries, uint32_t *trie_of_key, cudaStream_t st) {
     if (n_entries) dt_expand_tries_kernel<<<blocks_for(n_entries, 256), 256, 0, st>>>(seg_offsets, m, kind, leaf_of, n_entries, trie_of_key);
+    return cudaGetLastError();
+}
+cudaError_t launch_dt_nibble_tries(const uint8_t *keys, uint64_t m, uint32_t *trie_of_key, cudaStream_t st) {
+    if (m) dt_nibble_tries_kernel<<<blocks_for(m, 256), 256, 0, st>>>(keys, m, trie_of_key);
+    return cudaGetLastError();
+}
+cudaError_t launch_dt_frontier(const DTrieDev &t, const uint8_t *bucket_roots, FrontierEntryDev *out, cudaStream_t st) {
+    dt_frontier_kernel<<<1, 512, 0, st>>>(t, bucket_roots, out);
     return cudaGetLastError();
 }

@@ -214,4 +214,7 @@ cudaError_t launch_dt_wipe_round(const DTrieDev &t, const uint32_t *list, const 
 cudaError_t launch_dt_expand_tries(const uint64_t *seg_offsets, uint64_t m, const uint8_t *kind, const uint32_t *leaf_of,
                                    uint64_t n_entries, uint32_t *trie_of_key, cudaStream_t st);
 
+cudaError_t launch_dt_nibble_tries(const uint8_t *keys, uint64_t m, uint32_t *trie_of_key, cudaStream_t st);
+cudaError_t launch_dt_frontier(const DTrieDev &t, const uint8_t *bucket_roots, FrontierEntryDev *out, cudaStream_t st);
+
 }  // namespace b200

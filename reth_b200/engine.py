@@ -468,7 +468,9 @@ class DynamicState:
         self.engine, self.handle, self._root = engine, handle, root
 
     @classmethod
-    def create(cls, engine: Engine, acct_keys, accounts, slot_keys, values, seg_offsets) -> "DynamicState":
+    def create(cls, engine: Engine, acct_keys, accounts, slot_keys, values, seg_offsets, sharded: bool = False) -> "DynamicState":
+        """sharded=True: one rank's shard of a state split by top key nibble (b200_dstate_create_sharded): use `frontier()`
+        after every apply, gather the entries of all ranks and finish with Engine.root_from_frontier."""
         acct_keys = _np(acct_keys).reshape(-1, 32)
         accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
         slot_keys = _np(slot_keys).reshape(-1, 32)
@@ -478,9 +480,16 @@ class DynamicState:
             raise ValueError("seg_offsets must have n_accounts+1 entries")
         h = C.c_void_p()
         root = np.empty(32, np.uint8)
-        engine._check(engine.lib.b200_dstate_create(engine.ctx, _ptr(acct_keys), _ptr(accounts), len(acct_keys),
-                                                    _ptr(slot_keys), _ptr(values), _ptr(seg_offsets), C.byref(h), _ptr(root)))
+        fn = engine.lib.b200_dstate_create_sharded if sharded else engine.lib.b200_dstate_create
+        engine._check(fn(engine.ctx, _ptr(acct_keys), _ptr(accounts), len(acct_keys), _ptr(slot_keys), _ptr(values),
+                         _ptr(seg_offsets), C.byref(h), _ptr(root)))
         return cls(engine, h, root.tobytes())
+
+    def frontier(self) -> np.ndarray:
+        """(16, 68) uint8: this shard's b200_frontier_entry array as of the last apply."""
+        out = (FrontierEntry * 16)()
+        self.engine._check(self.engine.lib.b200_dstate_frontier(self.handle, out))
+        return np.frombuffer(bytes(out), np.uint8).reshape(16, 68).copy()
 
     def apply(self, acct_keys, accounts, flags, slot_keys, values, seg_offsets, want_updates=False):
         """-> root, or (root, acct_updated, acct_removed_paths, storage_updated, storage_removed [(entry, path)],

@@ -285,3 +285,113 @@ def test_dynamic_state_root_commits_hashed_post_states(eng):
             cur.update(st.storage_nodes)
         assert {k: v for k, v in stor_db.items() if v} == {k: v.storage_nodes for k, v in o_full.storage_tries.items() if v.storage_nodes}
     ds.close()
+
+
+class ShardedHarness:
+    """`world` shards of one state (rank r owns top nibbles [16r/world, 16(r+1)/world)), as separate b200_dstate objects in
+    one process; a block is routed by top nibble, the frontiers are merged the way the NCCL all-gather would."""
+
+    def __init__(self, eng, state, world):
+        from reth_b200 import DynamicState
+        self.eng, self.world = eng, world
+        self.state = {k: (a.copy(), dict(s)) for k, (a, s) in state.items()}
+        self.shards = []
+        for r in range(world):
+            part = {k: v for k, v in self.state.items() if self.rank_of(k) == r}
+            _, keys, accs, skeys, svals, offs = flatten(part)
+            self.shards.append(DynamicState.create(eng, keys, accs, skeys, svals, offs, sharded=True))
+        root, self.adb, self.sdb = model(self.state)
+        assert self.global_root() == root
+
+    def rank_of(self, k):
+        return (k[0] >> 4) * self.world // 16
+
+    def global_root(self):
+        merged = np.zeros((16, 68), np.uint8)
+        for r, ds in enumerate(self.shards):
+            fr = ds.frontier()
+            lo, hi = -(-16 * r // self.world), -(-16 * (r + 1) // self.world)
+            mine = [b for b in range(16) if b * self.world // 16 == r]
+            assert not fr[[b for b in range(16) if b not in mine]].any()
+            merged[mine] = fr[mine]
+        return self.eng.root_from_frontier(merged)
+
+    def commit(self, block):
+        for k, (fl, a, slots) in block.items():           # the model (same overlay rules as Harness.commit)
+            if not (fl & EXISTS):
+                self.state.pop(k, None)
+                continue
+            if fl & UNCHANGED:
+                if k not in self.state:
+                    continue
+                cur_a, cur_s = self.state[k]
+            else:
+                cur_a, cur_s = a.copy(), (self.state[k][1] if k in self.state else {})
+            cur_s = {} if (fl & WIPED) else dict(cur_s)
+            for s, v in slots.items():
+                if v == 0:
+                    cur_s.pop(s, None)
+                else:
+                    cur_s[s] = v
+            self.state[k] = (cur_a, cur_s)
+        for r, ds in enumerate(self.shards):
+            ks = sorted(k for k in block if self.rank_of(k) == r)
+            m = len(ks)
+            keys = np.frombuffer(b"".join(ks), np.uint8).reshape(m, 32) if m else np.zeros((0, 32), np.uint8)
+            accs = np.zeros(m, oracle.ACCOUNT_DTYPE)
+            flags = np.zeros(m, np.uint8)
+            sk, sv, offs = [], [], [0]
+            for i, k in enumerate(ks):
+                flags[i], accs[i] = block[k][0], block[k][1]
+                for s in sorted(block[k][2]):
+                    sk.append(s)
+                    sv.append(int(block[k][2][s]).to_bytes(32, "big"))
+                offs.append(len(sk))
+            skeys = np.frombuffer(b"".join(sk), np.uint8).reshape(-1, 32) if sk else np.zeros((0, 32), np.uint8)
+            svals = np.frombuffer(b"".join(sv), np.uint8).reshape(-1, 32) if sv else np.zeros((0, 32), np.uint8)
+            _, au, ar, su, sr, deleted = ds.apply(keys, accs, flags, skeys, svals, np.array(offs, np.uint64), want_updates=True)
+            for p in ar:
+                self.adb.pop(p, None)
+            for rec in au:
+                self.adb[rec[1]] = rec[2:]
+            for i, k in enumerate(ks):
+                if deleted[i]:
+                    self.sdb.pop(k, None)
+            for entry, p in sr:
+                self.sdb.get(ks[entry], {}).pop(p, None)
+            for rec in su:
+                self.sdb.setdefault(ks[rec[0]], {})[rec[1]] = rec[2:]
+        o_root, o_adb, o_sdb = model(self.state)
+        assert self.global_root() == o_root
+        assert self.adb == o_adb                      # the union of the shards' TrieUpdates == the unsharded node set
+        assert {k: v for k, v in self.sdb.items() if v} == o_sdb
+        assert sum(ds.accounts() for ds in self.shards) == len(self.state)
+
+
+@pytest.mark.parametrize("world", [1, 2, 8, 16])
+def test_sharded_state_matches_full_root(eng, world):
+    rng = np.random.default_rng(900 + world)
+    h = ShardedHarness(eng, random_state(rng, 400), world)
+    for step in range(4):
+        h.commit(random_block(rng, h.state, 60, step + 1))
+    for ds in h.shards:
+        ds.close()
+
+
+def test_sharded_state_degenerate_buckets(eng):
+    """All accounts in one bucket (the global root is not a depth-0 branch), then a second bucket appears and vanishes."""
+    rng = np.random.default_rng(31)
+    st = {}
+    for _ in range(40):
+        k = bytearray(rkey(rng))
+        k[0] = 0x30 | (k[0] & 15)
+        st[bytes(k)] = (acct(1, 5), {})
+    h = ShardedHarness(eng, st, 4)
+    other = bytearray(rkey(rng))
+    other[0] = 0xC1
+    h.commit({bytes(other): (EXISTS, acct(2, 2), {rkey(rng): 9})})
+    h.commit({bytes(other): (0, acct(0), {})})
+    h.commit({k: (0, acct(0), {}) for k in sorted(h.state)[1:]})      # a single account left
+    h.commit({k: (0, acct(0), {}) for k in sorted(h.state)})           # empty state
+    for ds in h.shards:
+        ds.close()
