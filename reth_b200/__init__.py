@@ -11,3 +11,4 @@ from .hashed_state import (Account, HashedPostState, HashedPostStateSorted, Hash
 from .stages import AccountHashingStage, MerkleStage, StageError, StorageHashingStage, Tables  # noqa: F401,E402
 from .trie import (BranchNodeCompact, DynamicStateRoot, ParallelStateRoot, ResidentStateRoot, StateRoot, StateRootError, StateRootProgress,  # noqa: F401,E402
                    StorageRoot, StorageTrieUpdates, TrieUpdates)
+from .sharded import ShardedDynamicStateRoot  # noqa: F401,E402

@@ -304,10 +304,12 @@ class DynamicStateRoot:
     `TrieUpdates` (account_nodes, removed_nodes, storage_tries with is_deleted).  Nothing of the state is kept on the host.
     Emulation-validated; first B200 run pending (include/b200trie.h)."""
 
-    def __init__(self, engine: Engine, state: HashedPostStateSorted):
+    def __init__(self, engine: Engine, state: HashedPostStateSorted, sharded: bool = False):
+        """sharded=True: this object is one rank's shard (see reth_b200.sharded.ShardedDynamicStateRoot); `commit`'s root is
+        then the shard's own root and the state root comes from the gathered frontiers."""
         from .engine import ACCOUNT_DTYPE, DynamicState
         keys, accts, skeys, svals, offs = state.to_flat()
-        self.ds = DynamicState.create(engine, keys, accts, skeys, svals, offs)
+        self.ds = DynamicState.create(engine, keys, accts, skeys, svals, offs, sharded=sharded)
         self._dtype = ACCOUNT_DTYPE
 
     def root(self) -> bytes:
