@@ -11,6 +11,22 @@ pub struct b200_ctx {
 pub struct b200_trie {
     _p: [u8; 0],
 }
+#[repr(C)]
+pub struct b200_dtrie {
+    _p: [u8; 0],
+}
+#[repr(C)]
+pub struct b200_dstate {
+    _p: [u8; 0],
+}
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct b200_frontier_entry {
+    pub as_child_len: u8,
+    pub as_child: [u8; 33],
+    pub as_root_len: u8,
+    pub as_root: [u8; 33],
+}
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -90,4 +106,26 @@ unsafe extern "C" {
                            storage_roots32: *const u8, m: u64, root32: *mut u8, out_rebuilt: *mut i32,
                            updates: *mut b200_updates, stats: *mut b200_stats) -> i32;
     pub fn b200_trie_destroy(trie: *mut b200_trie);
+
+    // dynamic resident trie / state (emulation-validated; include/b200trie.h)
+    pub fn b200_dtrie_create(ctx: *mut b200_ctx, acct_keys32: *const u8, accts: *const b200_account, storage_roots32: *const u8,
+                             n: u64, out: *mut *mut b200_dtrie, root32: *mut u8) -> i32;
+    pub fn b200_dtrie_apply(trie: *mut b200_dtrie, keys32: *const u8, accts: *const b200_account, present: *const u8,
+                            storage_roots32: *const u8, m: u64, root32: *mut u8, updated: *mut b200_updates,
+                            removed: *mut b200_updates, stats: *mut b200_stats) -> i32;
+    pub fn b200_dtrie_destroy(trie: *mut b200_dtrie);
+    pub fn b200_dstate_create(ctx: *mut b200_ctx, acct_keys32: *const u8, accts: *const b200_account, n_accounts: u64,
+                              slot_keys32: *const u8, values32_be: *const u8, seg_offsets: *const u64,
+                              out: *mut *mut b200_dstate, root32: *mut u8) -> i32;
+    pub fn b200_dstate_create_sharded(ctx: *mut b200_ctx, acct_keys32: *const u8, accts: *const b200_account, n_accounts: u64,
+                                      slot_keys32: *const u8, values32_be: *const u8, seg_offsets: *const u64,
+                                      out: *mut *mut b200_dstate, root32: *mut u8) -> i32;
+    pub fn b200_dstate_apply(state: *mut b200_dstate, acct_keys32: *const u8, accts: *const b200_account, acct_flags: *const u8,
+                             m: u64, slot_keys32: *const u8, values32_be: *const u8, seg_offsets: *const u64, root32: *mut u8,
+                             acct_updated: *mut b200_updates, acct_removed: *mut b200_updates,
+                             storage_updated: *mut b200_updates, storage_removed: *mut b200_updates,
+                             storage_deleted: *mut u8, stats: *mut b200_stats) -> i32;
+    pub fn b200_dstate_frontier(state: *mut b200_dstate, out16: *mut b200_frontier_entry) -> i32;
+    pub fn b200_root_from_frontier(ctx: *mut b200_ctx, frontier16: *const b200_frontier_entry, root32: *mut u8) -> i32;
+    pub fn b200_dstate_destroy(state: *mut b200_dstate);
 }
