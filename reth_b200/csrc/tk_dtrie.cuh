@@ -564,53 +564,7 @@ __device__ __forceinline__ uint32_t dt_warp_build_node(const DTrieDev &t, uint32
     __syncwarp();
     const uint32_t par = t.nparent[v];
     const int pd = PD_OVERRIDE >= -1 ? PD_OVERRIDE : (par == DT_NONE ? -1 : (int)t.ndepth[par]);
-    const bool is_root = pd < 0, need_ext = pd + 1 < d;
-    uint32_t meta;
-    if (total >= 32 || (is_root && !need_ext)) {
-        uint64_t a = kw.hash(buf, blocks, lane);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            uint64_t w = shfl64(a, i);
-            out[2 * i] = (uint32_t)w;
-            out[2 * i + 1] = (uint32_t)(w >> 32);
-        }
-        meta = 0;
-        hashed += lane == 0;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) out[i] = bufw[i];
-        meta = total;
-    }
-    if (need_ext) {
-        __syncwarp();
-        for (uint32_t w = lane; w < 34; w += 32) bufw[w] = 0;
-        __syncwarp();
-        uint32_t elen = 0;
-        if (lane == 0) {
-            LinBuf lb{buf, 0};
-            elen = encode_extension(lb, t.nkey + 32 * (uint64_t)v, (uint32_t)(pd + 1), (uint32_t)d, out, meta);
-            buf[elen] |= 0x01;
-            buf[135] |= 0x80;
-        }
-        elen = __shfl_sync(0xffffffffu, elen, 0);
-        __syncwarp();
-        if (elen >= 32 || is_root) {
-            uint64_t a = kw.hash(buf, 1, lane);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                uint64_t w = shfl64(a, i);
-                out[2 * i] = (uint32_t)w;
-                out[2 * i + 1] = (uint32_t)(w >> 32);
-            }
-            meta = META_EXT;
-            hashed += lane == 0;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; i++) out[i] = bufw[i];
-            meta = elen | META_EXT;
-        }
-        exts += lane == 0;
-    }
+    uint32_t meta = warp_finish_node(buf, total, blocks, d, pd, t.nkey + 32 * (uint64_t)v, kw, lane, hashed, exts, out);
     if (PD_OVERRIDE >= -1) {
         __syncwarp();
         return meta;

@@ -101,6 +101,64 @@ __device__ __forceinline__ ChildInfo fetch_child_c(const ForestDev &f, uint32_t 
     return ci;
 }
 
+// (Same steps as the tail of warp_build_node below, which keeps its own copy: its SASS is the one measured on the B200.)
+// The assembled branch RLP (`total` bytes, padded into `blocks` rate blocks of `buf`) -> RlpNode of the node as seen from a
+// parent at depth pd: hashed if >= 32 bytes (or a trie root), wrapped in an extension node when more than one nibble
+// separates it from the parent.  Uniform control flow: all 32 lanes call.  Returns the meta byte (inline length | META_EXT).
+__device__ __forceinline__ uint32_t warp_finish_node(uint8_t *buf, uint32_t total, uint32_t blocks, int d, int pd,
+                                                     const uint8_t *key, const WarpKeccak &kw, int lane, uint32_t &hashed,
+                                                     uint32_t &exts, uint32_t (&out)[8]) {
+    uint32_t *bufw = reinterpret_cast<uint32_t *>(buf);
+    bool is_root = pd < 0, need_ext = pd + 1 < d;
+    uint32_t meta;
+    if (total >= 32 || (is_root && !need_ext)) {
+        uint64_t a = kw.hash(buf, blocks, lane);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint64_t w = shfl64(a, i);
+            out[2 * i] = (uint32_t)w;
+            out[2 * i + 1] = (uint32_t)(w >> 32);
+        }
+        meta = 0;
+        hashed += lane == 0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) out[i] = bufw[i];
+        meta = total;
+    }
+    if (need_ext) {
+        __syncwarp();
+        for (uint32_t w = lane; w < 34; w += 32) bufw[w] = 0;
+        __syncwarp();
+        uint32_t elen = 0;
+        if (lane == 0) {
+            LinBuf lb{buf, 0};
+            elen = encode_extension(lb, key, (uint32_t)(pd + 1), (uint32_t)d, out, meta);
+            buf[elen] |= 0x01;
+            buf[135] |= 0x80;
+        }
+        elen = __shfl_sync(0xffffffffu, elen, 0);
+        __syncwarp();
+        if (elen >= 32 || is_root) {
+            uint64_t a = kw.hash(buf, 1, lane);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint64_t w = shfl64(a, i);
+                out[2 * i] = (uint32_t)w;
+                out[2 * i + 1] = (uint32_t)(w >> 32);
+            }
+            meta = META_EXT;
+            hashed += lane == 0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) out[i] = bufw[i];
+            meta = elen | META_EXT;
+        }
+        exts += lane == 0;
+    }
+    return meta;
+}
+
 // One warp builds branch node v of depth d (all 32 lanes must call).  Returns through lane 0's stores.
 template <bool COHERENT>
 __device__ __forceinline__ void warp_build_node(const ForestDev &f, uint32_t v, int d, uint8_t *buf, const WarpKeccak &kw,
