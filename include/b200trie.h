@@ -347,6 +347,24 @@ B200_API int32_t b200_dstate_create_sharded(b200_ctx *, const uint8_t *acct_keys
                                             uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
                                             const uint64_t *seg_offsets, b200_dstate **out, uint8_t root32[32]);
 B200_API int32_t b200_dstate_frontier(b200_dstate *, b200_frontier_entry out16[16]);
+/* Merkle proofs from the resident state (eth_getProof / reth's Proof::account_proof and storage_proof,
+ * crates/trie/trie/src/proof/mod.rs): target t's proof is nodes node_offset[t] .. node_offset[t+1], node k's RLP is
+ * rlp[rlp_offset[k] .. rlp_offset[k+1]), root first — every node whose position is a prefix of the target key (what
+ * alloy-trie's ProofRetainer keeps): extension and branch are separate nodes, the walk ends at a leaf (inclusion, or
+ * exclusion by another key), at an empty branch slot or inside a diverging extension.  An empty trie gives the single
+ * node 0x80.  Pinned by reth's own vectors (crates/trie/db/tests/proof.rs:44-165).  Not for sharded states. */
+typedef struct {
+    uint64_t n_targets;
+    uint64_t *node_offset; /* [n_targets+1] */
+    uint64_t n_nodes;
+    uint64_t *rlp_offset;  /* [n_nodes+1] */
+    uint8_t *rlp;
+    void *_owner;
+} b200_proofs;
+B200_API int32_t b200_dstate_account_proofs(b200_dstate *, const uint8_t *acct_keys32, uint64_t n, b200_proofs *out);
+B200_API int32_t b200_dstate_storage_proofs(b200_dstate *, const uint8_t *acct_key32, const uint8_t *slot_keys32, uint64_t n,
+                                            uint8_t storage_root32[32] /* nullable */, b200_proofs *out);
+B200_API void b200_proofs_release(b200_proofs *);
 B200_API int32_t b200_dstate_root(b200_dstate *, uint8_t root32[32]);
 B200_API uint64_t b200_dstate_accounts(const b200_dstate *);
 B200_API uint64_t b200_dstate_slots(const b200_dstate *);

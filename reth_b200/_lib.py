@@ -48,6 +48,18 @@ class Rows(C.Structure):
     ]
 
 
+class Proofs(C.Structure):
+    """b200_proofs (include/b200trie.h)."""
+    _fields_ = [
+        ("n_targets", C.c_uint64),
+        ("node_offset", C.POINTER(C.c_uint64)),
+        ("n_nodes", C.c_uint64),
+        ("rlp_offset", C.POINTER(C.c_uint64)),
+        ("rlp", C.POINTER(C.c_uint8)),
+        ("_owner", C.c_void_p),
+    ]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("leaves_added", C.c_uint64),
@@ -151,6 +163,9 @@ def load():
     sig("b200_dstate_create_sharded", i32, vp, vp, vp, u64, vp, vp, vp, C.POINTER(vp), vp)
     sig("b200_dstate_frontier", i32, vp, C.POINTER(FrontierEntry))
     sig("b200_dstate_apply", i32, vp, vp, vp, vp, u64, vp, vp, vp, vp, PU, PU, PU, PU, vp, PS)
+    sig("b200_dstate_account_proofs", i32, vp, vp, u64, C.POINTER(Proofs))
+    sig("b200_dstate_storage_proofs", i32, vp, vp, vp, u64, vp, C.POINTER(Proofs))
+    sig("b200_proofs_release", None, C.POINTER(Proofs))
     sig("b200_dstate_root", i32, vp, vp)
     sig("b200_dstate_accounts", u64, vp)
     sig("b200_dstate_slots", u64, vp)

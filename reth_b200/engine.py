@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import B200Error, FrontierEntry, Stats, Updates
+from ._lib import B200Error, FrontierEntry, Proofs, Stats, Updates
 
 ACCOUNT_DTYPE = np.dtype([("nonce", "<u8"), ("balance", "u1", (32,)), ("code_hash", "u1", (32,))])
 KECCAK_EMPTY = bytes.fromhex("c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470")
@@ -517,6 +517,35 @@ class DynamicState:
         lib = self.engine.lib
         return (self._root, updates_to_records(au, lib), [r[1] for r in updates_to_records(ar, lib)],
                 updates_to_records(su, lib), [(r[0], r[1]) for r in updates_to_records(sr, lib)], deleted[:m].copy())
+
+    def _take_proofs(self, p: Proofs) -> list:
+        n, nn = int(p.n_targets), int(p.n_nodes)
+        res = []
+        if n:
+            no = np.ctypeslib.as_array(p.node_offset, (n + 1,))
+            ro = np.ctypeslib.as_array(p.rlp_offset, (nn + 1,))
+            blob = np.ctypeslib.as_array(p.rlp, (max(int(ro[nn]), 1),)).tobytes()
+            for t in range(n):
+                res.append([blob[int(ro[k]):int(ro[k + 1])] for k in range(int(no[t]), int(no[t + 1]))])
+        self.engine.lib.b200_proofs_release(C.byref(p))
+        return res
+
+    def account_proofs(self, acct_keys) -> list:
+        """-> for every target hashed address the list of node RLPs from the root down (Proof::account_proof)."""
+        acct_keys = _np(acct_keys).reshape(-1, 32)
+        p = Proofs()
+        self.engine._check(self.engine.lib.b200_dstate_account_proofs(self.handle, _ptr(acct_keys), len(acct_keys), C.byref(p)))
+        return self._take_proofs(p)
+
+    def storage_proofs(self, acct_key: bytes, slot_keys):
+        """-> (storage root, [proof of every hashed slot key]) of one account (Proof::storage_proof)."""
+        ak = np.frombuffer(bytes(acct_key), np.uint8).copy()
+        slot_keys = _np(slot_keys).reshape(-1, 32)
+        sroot = np.empty(32, np.uint8)
+        p = Proofs()
+        self.engine._check(self.engine.lib.b200_dstate_storage_proofs(self.handle, _ptr(ak), _ptr(slot_keys), len(slot_keys),
+                                                                      _ptr(sroot), C.byref(p)))
+        return sroot.tobytes(), self._take_proofs(p)
 
     def root(self) -> bytes:
         out = np.empty(32, np.uint8)
