@@ -714,443 +714,3 @@ __global__ void dt_gather_updates_kernel(DTrieDev t, const uint32_t *__restrict_
         }
 }
 
-// ------------------------------------------------------------------------------------------------ sharded accounts
-// Multi-GPU layout of §6 for the dynamic state: the account arena holds one trie per top-nibble bucket (trie id = nibble,
-// every bucket a trie of its own, so its root hash is the frontier's as_root); as_child re-encodes the bucket's top item
-// as a child of the depth-0 root branch.  One warp per bucket.
-__global__ void dt_nibble_tries_kernel(const uint8_t *__restrict__ keys, uint64_t m, uint32_t *__restrict__ trie_of_key) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m) trie_of_key[i] = keys[32 * i] >> 4;
-}
-__global__ void __launch_bounds__(512) dt_frontier_kernel(DTrieDev t, const uint8_t *__restrict__ bucket_roots,
-                                                          FrontierEntryDev *__restrict__ out) {
-    __shared__ __align__(16) uint8_t sbuf[16][WARP_BUF];
-    const int lane = threadIdx.x & 31, b = threadIdx.x >> 5;
-    uint8_t *buf = sbuf[b];
-    uint32_t *bufw = reinterpret_cast<uint32_t *>(buf);
-    WarpKeccak kw;
-    kw.init(lane);
-    FrontierEntryDev &e = out[b];
-    for (int i = lane; i < (int)sizeof(FrontierEntryDev); i += 32) reinterpret_cast<uint8_t *>(&e)[i] = 0;
-    __syncwarp();
-    const uint32_t w = t.troot[b];
-    if (w == DT_NONE || *(volatile int *)t.err != B200_DEVERR_NONE) return;
-    uint32_t out8[8], hashed = 0, exts = 0, meta;
-    if (w & DT_LEAF) {
-        const uint32_t x = w & ~DT_LEAF;
-        for (uint32_t q = lane; q < 68; q += 32) bufw[q] = 0;
-        __syncwarp();
-        uint32_t len = 0;
-        if (lane == 0) {
-            uint32_t k[8];
-            load32_nc(t.lkey + 32 * (uint64_t)x, k);
-            LinBuf lb{buf, 0};
-            len = encode_leaf<LinBuf, true>(lb, k, 0, t.lval + 72 * (uint64_t)x, t.lsroot ? t.lsroot + 32 * (uint64_t)x : nullptr, t.err);
-            buf[len] |= 0x01;
-            buf[(len / 136 + 1) * 136 - 1] |= 0x80;
-        }
-        len = __shfl_sync(0xffffffffu, len, 0);
-        __syncwarp();
-        uint64_t a = kw.hash(buf, len / 136 + 1, lane);  // account leaves are >= 70 bytes: always a hash reference
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            uint64_t v = shfl64(a, q);
-            out8[2 * q] = (uint32_t)v;
-            out8[2 * q + 1] = (uint32_t)(v >> 32);
-        }
-        meta = 0;
-    } else {
-        meta = dt_warp_build_node<0>(t, w, buf, kw, lane, hashed, exts, out8);
-    }
-    if (lane == 0) {
-        e.as_root_len = 32;
-        for (int i = 0; i < 32; i++) e.as_root[i] = bucket_roots[32 * b + i];
-        uint32_t il = meta & META_LEN;
-        if (il == 0) {
-            e.as_child_len = 33;
-            e.as_child[0] = 0xa0;
-            for (int i = 0; i < 32; i++) e.as_child[1 + i] = (uint8_t)(out8[i >> 2] >> (8 * (i & 3)));
-        } else {
-            e.as_child_len = (uint8_t)il;
-            for (uint32_t i = 0; i < il; i++) e.as_child[i] = (uint8_t)(out8[i >> 2] >> (8 * (i & 3)));
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ dynamic state glue
-// Which storage tries a block wipes: the tries of destroyed accounts and of accounts flagged "storage wiped"
-// (HashedStorage::wiped, crates/trie/common/src/hashed_state.rs:423-428).  Trie id = id of the account's leaf.
-__global__ void dt_wipe_list_kernel(const uint8_t *__restrict__ kind, const uint8_t *__restrict__ flags,
-                                    const uint32_t *__restrict__ leaf_of, uint64_t m, uint32_t *__restrict__ tries,
-                                    uint32_t *__restrict__ count) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    uint8_t k = kind[i];
-    bool wiped = flags != nullptr && (flags[i] & 4);
-    if (k == DK_DELETE || (wiped && (k == DK_UPDATE || k == DK_TOUCH))) tries[atomicAdd(count, 1u)] = leaf_of[i];
-}
-static __device__ __forceinline__ void dt_wipe_leaf(const DTrieDev &t, uint32_t x) {
-    t.lmeta[x] = DT_DEAD;
-    t.lseed[x] = 0;
-    t.leaf_free[atomicAdd(&t.g[DG_LEAF_FREE], 1u)] = x;
-    atomicSub(&t.g[DG_NLEAVES], 1u);
-}
-// breadth-first release of whole tries: no removed-node records (reth reports a wiped storage trie as is_deleted)
-__global__ void dt_wipe_begin_kernel(DTrieDev t, const uint32_t *__restrict__ tries, const uint32_t *__restrict__ count_p,
-                                     uint32_t *__restrict__ next, uint32_t *next_count) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *count_p) return;
-    uint32_t r = tries[i], w = t.troot[r];
-    if (w == DT_NONE) return;
-    dt_set_child(t, r, DT_NONE, 0, DT_NONE);
-    if (w & DT_LEAF) dt_wipe_leaf(t, w & ~DT_LEAF);
-    else next[atomicAdd(next_count, 1u)] = w;
-}
-__global__ void dt_wipe_round_kernel(DTrieDev t, const uint32_t *__restrict__ list, const uint32_t *__restrict__ count_p,
-                                     uint32_t *__restrict__ next, uint32_t *next_count) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *count_p) return;
-    uint32_t v = list[i];
-    const uint32_t *ch = t.nchild + 16 * (uint64_t)v;
-    for (int s = 0; s < 16; s++) {
-        uint32_t w = ch[s];
-        if (w == DT_NONE) continue;
-        if (w & DT_LEAF) dt_wipe_leaf(t, w & ~DT_LEAF);
-        else next[atomicAdd(next_count, 1u)] = w;
-    }
-    t.ndepth[v] = DT_DEAD;
-    t.nmeta[v] = 0;
-    t.npending[v] = 0;
-    t.node_free[atomicAdd(&t.g[DG_NODE_FREE], 1u)] = v;
-}
-// trie_of_key[j] for storage entry j of account entry i (seg_offsets[i] <= j < seg_offsets[i+1]): the account's leaf if
-// the account exists after the block, DT_NONE (entry ignored) otherwise
-__global__ void dt_expand_tries_kernel(const uint64_t *__restrict__ seg_offsets, uint64_t m, const uint8_t *__restrict__ kind,
-                                       const uint32_t *__restrict__ leaf_of, uint64_t n_entries, uint32_t *__restrict__ trie_of_key) {
-    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_entries) return;
-    uint64_t lo = 0, hi = m;  // last account with offset <= j
-    while (hi - lo > 1) {
-        uint64_t mid = (lo + hi) >> 1;
-        if (seg_offsets[mid] <= j) lo = mid;
-        else hi = mid;
-    }
-    uint8_t k = kind[lo];
-    trie_of_key[j] = (k == DK_UPDATE || k == DK_TOUCH || k == DK_INSERT) ? leaf_of[lo] : DT_NONE;
-}
-
-// ------------------------------------------------------------------------------------------------ proofs
-// Merkle proofs from the resident arenas: for a target key, the RLP of every node whose position is a prefix
-// of the key, root first — what alloy-trie's ProofRetainer keeps while reth's Proof::account_proof / storage_proof walk
-// the trie (crates/trie/trie/src/proof/mod.rs).  An extension node and the branch below it are two proof nodes; the walk
-// stops at a leaf (inclusion, or exclusion by a different key), at an empty slot, or inside an extension whose nibbles
-// differ from the key.  One thread per target; two passes (sizes, then bytes) around an exclusive scan.
-struct CountBuf {  // sizing pass: same interface as LinBuf, nothing is written
-    uint32_t n;
-    __device__ __forceinline__ void byte(uint32_t) { n++; }
-    __device__ __forceinline__ void tail32(const uint32_t (&)[8], uint32_t b0) { n += 32 - b0; }
-    __device__ __forceinline__ void words8(const uint32_t (&)[8]) { n += 32; }
-};
-
-// keccak256 of `len` bytes at an arbitrarily aligned global address (thread-serial; proofs are not a throughput path)
-static __device__ void dt_keccak_global(const uint8_t *p, uint32_t len, uint32_t (&dig)[8]) {
-    uint64_t a[25];
-#pragma unroll
-    for (int i = 0; i < 25; i++) a[i] = 0;
-    uint32_t off = 0;
-    for (;;) {
-        uint32_t take = len - off < 136 ? len - off : 136;
-        for (uint32_t lane = 0; lane < 17; lane++) {
-            uint64_t w = 0;
-            for (uint32_t b = 0; b < 8; b++) {
-                uint32_t i = 8 * lane + b;
-                uint32_t x = i < take ? p[off + i] : 0;
-                if (take < 136 && i == take) x ^= 0x01;
-                if (take < 136 && i == 135) x ^= 0x80;
-                w |= (uint64_t)x << (8 * b);
-            }
-#pragma unroll
-            for (int q = 0; q < 17; q++)
-                if ((uint32_t)q == lane) a[q] ^= w;
-        }
-        keccak_f1600(a);
-        off += take;
-        if (take < 136) break;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        dig[2 * i] = (uint32_t)a[i];
-        dig[2 * i + 1] = (uint32_t)(a[i] >> 32);
-    }
-}
-
-static __device__ __forceinline__ uint32_t dt_branch_rlp_len(const DTrieDev &t, uint32_t v, uint32_t &payload) {
-    payload = 1;
-    for (int s = 0; s < 16; s++) {
-        uint32_t cw = t.nchild[16 * (uint64_t)v + s];
-        if (cw == DT_NONE) {
-            payload += 1;
-        } else {
-            uint32_t m = (cw & DT_LEAF) ? t.lmeta[cw & ~DT_LEAF] : t.nmeta[cw];
-            payload += (m & META_LEN) ? (m & META_LEN) : 33u;
-        }
-    }
-    return list_header_len(payload) + payload;
-}
-static __device__ void dt_write_branch_rlp(const DTrieDev &t, uint32_t v, uint32_t payload, uint8_t *dst) {
-    LinBuf lb{dst, 0};
-    put_list_header(lb, payload);
-    for (int s = 0; s < 16; s++) {
-        uint32_t cw = t.nchild[16 * (uint64_t)v + s];
-        if (cw == DT_NONE) {
-            lb.byte(0x80);
-            continue;
-        }
-        bool leaf = (cw & DT_LEAF) != 0;
-        uint32_t id = cw & ~DT_LEAF, m = leaf ? t.lmeta[id] : t.nmeta[id];
-        uint32_t ref[8];
-        load32_nc((leaf ? t.lref : t.nref) + 32 * (uint64_t)id, ref);
-        uint32_t il = m & META_LEN;
-        if (il == 0) {
-            lb.byte(0xa0);
-            lb.words8(ref);
-        } else {
-            for (uint32_t b = 0; b < il; b++) lb.byte(byte_at(ref, b));
-        }
-    }
-    lb.byte(0x80);
-}
-
-// Walks target `key` in trie `trie`.  WRITE = false: returns node / byte counts.  WRITE = true: writes the nodes at
-// rlp + byte_base and their start offsets at rlp_offset[node_base ..].
-template <bool WRITE>
-static __device__ void dt_proof_walk(const DTrieDev &t, uint32_t trie, const uint8_t *key, uint32_t &n_nodes, uint64_t &n_bytes,
-                                     uint8_t *rlp, uint64_t byte_base, uint64_t *rlp_offset, uint64_t node_base) {
-    n_nodes = 0;
-    n_bytes = 0;
-    uint32_t cur = t.troot[trie];
-    int pd = -1;
-    auto begin_node = [&](uint32_t len) {
-        if (WRITE) rlp_offset[node_base + n_nodes] = byte_base + n_bytes;
-        n_nodes++;
-        n_bytes += len;
-    };
-    if (cur == DT_NONE) {  // empty trie: the proof is the empty string (EMPTY_STRING_CODE), proof.rs:121-126
-        if (WRITE) rlp[byte_base] = 0x80;
-        begin_node(1);
-        return;
-    }
-    for (int hops = 0; hops <= DT_MAX_HOPS; hops++) {
-        if (cur & DT_LEAF) {
-            const uint32_t x = cur & ~DT_LEAF;
-            uint32_t k[8];
-            load32_nc(t.lkey + 32 * (uint64_t)x, k);
-            const uint8_t *val = t.lval + (uint64_t)t.val_stride * x;
-            const uint8_t *sr = t.lsroot ? t.lsroot + 32 * (uint64_t)x : nullptr;
-            CountBuf cb{0};
-            uint32_t len = t.account ? encode_leaf<CountBuf, true>(cb, k, pd, val, sr, t.err) : encode_leaf<CountBuf, false>(cb, k, pd, val, nullptr, t.err);
-            if (WRITE) {
-                LinBuf lb{rlp + byte_base + n_bytes, 0};
-                if (t.account) encode_leaf<LinBuf, true>(lb, k, pd, val, sr, t.err);
-                else encode_leaf<LinBuf, false>(lb, k, pd, val, nullptr, t.err);
-            }
-            begin_node(len);
-            return;
-        }
-        const uint32_t v = cur;
-        const int d = t.ndepth[v];
-        const uint8_t *nk = t.nkey + 32 * (uint64_t)v;
-        uint32_t payload;
-        const uint32_t blen = dt_branch_rlp_len(t, v, payload);
-        const bool ext = pd + 1 < d;
-        const bool matches = dt_lcp(key, nk, (uint32_t)(pd + 1), (uint32_t)d) == (uint32_t)d;
-        if (ext) {  // the extension node sits at a prefix of the key (we got here); the branch only if its nibbles match
-            uint32_t m = (uint32_t)(d - (pd + 1)), hp_len = 1 + (m >> 1), path_str = hp_len == 1 ? 1 : 1 + hp_len;
-            uint32_t clen = blen >= 32 ? 33 : blen;
-            uint32_t epayload = path_str + clen, elen = list_header_len(epayload) + epayload;
-            if (WRITE) {
-                // the branch's RLP is needed first (its hash, or itself when shorter than 32 bytes, is the extension's
-                // child): written to its final place right after the extension when it belongs to the proof, to a
-                // thread-local buffer otherwise
-                uint8_t *ext_at = rlp + byte_base + n_bytes;
-                uint8_t tmp[544];
-                uint8_t *br_at = matches ? ext_at + elen : tmp;
-                dt_write_branch_rlp(t, v, payload, br_at);
-                uint32_t child[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (blen >= 32) dt_keccak_global(br_at, blen, child);
-                else
-                    for (uint32_t b = 0; b < blen; b++) child[b >> 2] |= (uint32_t)br_at[b] << (8 * (b & 3));
-                LinBuf lb{ext_at, 0};
-                encode_extension(lb, nk, (uint32_t)(pd + 1), (uint32_t)d, child, blen >= 32 ? 0u : blen);
-            }
-            begin_node(elen);
-            if (!matches) return;
-            begin_node(blen);
-        } else {
-            if (WRITE) dt_write_branch_rlp(t, v, payload, rlp + byte_base + n_bytes);
-            begin_node(blen);
-        }
-        pd = d;
-        cur = t.nchild[16 * (uint64_t)v + dt_nib(key, (uint32_t)d)];
-        if (cur == DT_NONE) return;  // exclusion: the branch has no child for the key's next nibble
-    }
-    atomicExch(t.err, B200_DEVERR_CORRUPT);
-}
-
-// trie_of_target: nullptr = trie 0; DT_NONE entries (storage of an absent account) prove against the empty trie
-__global__ void dt_proof_size_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_target, const uint8_t *__restrict__ keys,
-                                     uint64_t n, uint32_t *__restrict__ node_count, uint64_t *__restrict__ byte_count) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t trie = trie_of_target ? trie_of_target[i] : 0;
-    uint32_t nn;
-    uint64_t nb;
-    if (trie == DT_NONE) {
-        nn = 1;
-        nb = 1;
-    } else {
-        dt_proof_walk<false>(t, trie, keys + 32 * i, nn, nb, nullptr, 0, nullptr, 0);
-    }
-    node_count[i] = nn;
-    byte_count[i] = nb;
-}
-__global__ void dt_proof_write_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_target, const uint8_t *__restrict__ keys,
-                                      uint64_t n, const uint64_t *__restrict__ node_base, const uint64_t *__restrict__ byte_base,
-                                      uint8_t *__restrict__ rlp, uint64_t *__restrict__ rlp_offset) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t trie = trie_of_target ? trie_of_target[i] : 0;
-    uint32_t nn;
-    uint64_t nb;
-    if (trie == DT_NONE) {
-        rlp[byte_base[i]] = 0x80;
-        rlp_offset[node_base[i]] = byte_base[i];
-    } else {
-        dt_proof_walk<true>(t, trie, keys + 32 * i, nn, nb, rlp, byte_base[i], rlp_offset, node_base[i]);
-    }
-}
-// the account leaf (= storage trie id) of one account key, DT_NONE when the account does not exist
-__global__ void dt_find_leaf_kernel(DTrieDev t, const uint8_t *__restrict__ key, uint32_t *__restrict__ out, uint64_t n_copies) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_copies) return;
-    DtLoc loc = dt_descend(t, t.ltrie ? (uint32_t)(key[0] >> 4) : 0u, key);
-    out[i] = loc.found ? (loc.child & ~DT_LEAF) : DT_NONE;
-}
-
-// ------------------------------------------------------------------------------------------------ launchers
-// leaf_trie: trie (segment) of every leaf of a forest build, nullptr for a single trie
-cudaError_t launch_dt_convert(const ForestDev &f, uint32_t n_nodes, const uint32_t *leaf_parent, const uint32_t *node_parent,
-                              const uint32_t *leaf_trie, const DTrieDev &t, cudaStream_t st) {
-    if (f.n) dt_convert_leaves_kernel<<<blocks_for(f.n, 256), 256, 0, st>>>(f.n, leaf_parent, leaf_trie, t);
-    if (n_nodes) dt_convert_nodes_kernel<<<blocks_for(n_nodes, 128), 128, 0, st>>>(f, n_nodes, node_parent, leaf_trie, t);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_leaf_segments(const uint64_t *seg_offsets, uint64_t n_segs, uint64_t n, uint32_t *leaf_trie, cudaStream_t st) {
-    if (n) dt_leaf_segments_kernel<<<blocks_for(n, 256), 256, 0, st>>>(seg_offsets, n_segs, n, leaf_trie);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_locate(const DTrieDev &t, const uint32_t *trie_of_key, const uint8_t *keys, const uint8_t *vals,
-                             const uint8_t *flags, uint64_t m, uint8_t *kind, uint32_t *leaf_of, cudaStream_t st) {
-    dt_locate_kernel<<<blocks_for(m, 128), 128, 0, st>>>(t, trie_of_key, keys, vals, flags, m, kind, leaf_of);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_update_detach(const DTrieDev &t, const uint8_t *accts, const uint8_t *sroots, uint64_t m,
-                                    const uint8_t *kind, const uint32_t *leaf_of, uint32_t *touched, cudaStream_t st) {
-    dt_update_detach_kernel<<<blocks_for(m, 128), 128, 0, st>>>(t, accts, sroots, m, kind, leaf_of, touched);
-    return cudaGetLastError();
-}
-// one collapse round over `list` (count on the device, at most max_count): begin / act / end
-cudaError_t launch_dt_collapse_round(const DTrieDev &t, const uint32_t *list, const uint32_t *count_p, uint32_t max_count,
-                                     uint8_t *defer, uint32_t *next, uint32_t *next_count, cudaStream_t st) {
-    unsigned blocks = blocks_for(max_count, 128);
-    dt_round_begin_kernel<<<blocks, 128, 0, st>>>(t, list, count_p);
-    dt_round_defer_kernel<<<blocks, 128, 0, st>>>(t, list, count_p, defer);
-    dt_collapse_round_kernel<<<blocks, 128, 0, st>>>(t, list, count_p, defer, next, next_count);
-    dt_round_end_kernel<<<blocks, 128, 0, st>>>(t, list, count_p);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_insert(const DTrieDev &t, const uint32_t *trie_of_key, const uint8_t *keys, const uint8_t *vals,
-                             const uint8_t *sroots, const uint32_t *ins_idx, const uint32_t *n_ins_p, uint64_t max_ins,
-                             uint64_t *attach, uint32_t *leaf_of, cudaStream_t st) {
-    unsigned blocks = blocks_for(max_ins, 128);
-    dt_insert_locate_kernel<<<blocks, 128, 0, st>>>(t, trie_of_key, keys, ins_idx, n_ins_p, attach);
-    dt_insert_runs_kernel<<<blocks, 128, 0, st>>>(t, trie_of_key, keys, vals, sroots, ins_idx, n_ins_p, attach, leaf_of);
-    return cudaGetLastError();
-}
-// mark -> starts -> wavefront -> finish (empty-trie root, recycling of this apply's freed nodes)
-__global__ void dt_finish_kernel(DTrieDev t) {
-    t.g[DG_NODE_FREE] += t.g[DG_FREED_NOW];
-    t.g[DG_FREED_NOW] = 0;
-}
-cudaError_t launch_dt_rehash(const DTrieDev &t, uint32_t max_seeds, cudaStream_t st) {
-    constexpr int WARPS = 4;
-    const uint32_t *count_p = t.g + DG_SEEDS;
-    unsigned blocks = blocks_for(max_seeds, 128);
-    dt_mark_kernel<<<blocks, 128, 0, st>>>(t, count_p);
-    dt_starts_kernel<<<blocks, 128, 0, st>>>(t, count_p);
-    unsigned wblocks = blocks_for(max_seeds, WARPS), cap = (unsigned)sms() * 16;
-    dt_wavefront_kernel<WARPS><<<wblocks < cap ? wblocks : cap, WARPS * 32, 0, st>>>(t, count_p);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_finish(const DTrieDev &t, uint32_t max_freed, cudaStream_t st) {
-    if (max_freed) dt_recycle_kernel<<<blocks_for(max_freed, 128), 128, 0, st>>>(t);
-    dt_finish_kernel<<<1, 1, 0, st>>>(t);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_stored_flags(const DTrieDev &t, uint32_t max_built, uint8_t *flags, uint32_t *n_hashes, cudaStream_t st) {
-    if (max_built) dt_stored_flags_kernel<<<blocks_for(max_built, 256), 256, 0, st>>>(t, t.g + DG_BUILT, flags, n_hashes);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_gather_updates(const DTrieDev &t, const uint32_t *stored_ids, uint32_t n_stored,
-                                     const uint32_t *hash_prefix_by_record, const UpdatesDev &out, cudaStream_t st) {
-    if (n_stored) dt_gather_updates_kernel<<<blocks_for(n_stored, 128), 128, 0, st>>>(t, stored_ids, n_stored, hash_prefix_by_record, out);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_removed_paths(const DTrieDev &t, uint32_t n_removed, uint8_t *path_len, uint8_t *path_packed,
-                                    uint32_t *trie_id, cudaStream_t st) {
-    if (n_removed) dt_removed_paths_kernel<<<blocks_for(n_removed, 128), 128, 0, st>>>(t, n_removed, path_len, path_packed, trie_id);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_wipe_list(const uint8_t *kind, const uint8_t *flags, const uint32_t *leaf_of, uint64_t m, uint32_t *tries,
-                                uint32_t *count, cudaStream_t st) {
-    if (m) dt_wipe_list_kernel<<<blocks_for(m, 256), 256, 0, st>>>(kind, flags, leaf_of, m, tries, count);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_wipe_begin(const DTrieDev &t, const uint32_t *tries, const uint32_t *count_p, uint32_t max_count,
-                                 uint32_t *next, uint32_t *next_count, cudaStream_t st) {
-    if (max_count) dt_wipe_begin_kernel<<<blocks_for(max_count, 128), 128, 0, st>>>(t, tries, count_p, next, next_count);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_wipe_round(const DTrieDev &t, const uint32_t *list, const uint32_t *count_p, uint32_t max_count,
-                                 uint32_t *next, uint32_t *next_count, cudaStream_t st) {
-    if (max_count) dt_wipe_round_kernel<<<blocks_for(max_count, 128), 128, 0, st>>>(t, list, count_p, next, next_count);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_expand_tries(const uint64_t *seg_offsets, uint64_t m, const uint8_t *kind, const uint32_t *leaf_of,
-                                   uint64_t n_entries, uint32_t *trie_of_key, cudaStream_t st) {
-    if (n_entries) dt_expand_tries_kernel<<<blocks_for(n_entries, 256), 256, 0, st>>>(seg_offsets, m, kind, leaf_of, n_entries, trie_of_key);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_nibble_tries(const uint8_t *keys, uint64_t m, uint32_t *trie_of_key, cudaStream_t st) {
-    if (m) dt_nibble_tries_kernel<<<blocks_for(m, 256), 256, 0, st>>>(keys, m, trie_of_key);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_frontier(const DTrieDev &t, const uint8_t *bucket_roots, FrontierEntryDev *out, cudaStream_t st) {
-    dt_frontier_kernel<<<1, 512, 0, st>>>(t, bucket_roots, out);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_proof_sizes(const DTrieDev &t, const uint32_t *trie_of_target, const uint8_t *keys, uint64_t n,
-                                  uint32_t *node_count, uint64_t *byte_count, cudaStream_t st) {
-    if (n) dt_proof_size_kernel<<<blocks_for(n, 64), 64, 0, st>>>(t, trie_of_target, keys, n, node_count, byte_count);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_proof_write(const DTrieDev &t, const uint32_t *trie_of_target, const uint8_t *keys, uint64_t n,
-                                  const uint64_t *node_base, const uint64_t *byte_base, uint8_t *rlp, uint64_t *rlp_offset,
-                                  cudaStream_t st) {
-    if (n) dt_proof_write_kernel<<<blocks_for(n, 64), 64, 0, st>>>(t, trie_of_target, keys, n, node_base, byte_base, rlp, rlp_offset);
-    return cudaGetLastError();
-}
-cudaError_t launch_dt_find_leaf(const DTrieDev &t, const uint8_t *key, uint32_t *out, uint64_t n_copies, cudaStream_t st) {
-    if (n_copies) dt_find_leaf_kernel<<<blocks_for(n_copies, 128), 128, 0, st>>>(t, key, out, n_copies);
-    return cudaGetLastError();
-}

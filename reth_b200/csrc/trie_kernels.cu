@@ -33,5 +33,8 @@ namespace b200 {
 #include "tk_frontier.cuh"
 #include "tk_launchers.cuh"
 #include "tk_dtrie.cuh"
+#include "tk_dstate.cuh"
+#include "tk_proofs.cuh"
+#include "tk_dtrie_launchers.cuh"
 
 }  // namespace b200
