@@ -1,0 +1,24 @@
+#!/usr/bin/env bash
+# Round-2 opener: first B200 run of everything that was validated under tools/emu only (dynamic trie / state / proofs),
+# then their latency, all under timeouts so that a misbehaving kernel costs minutes, not the budget.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/first_gpu_call.sh'
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+export B200_DTRIE_ON_GPU=1
+{
+  echo "== gated GPU tests"
+  timeout 600 python -m pytest tests/test_gpu_dtrie.py tests/test_gpu_dstate.py tests/test_gpu_proofs.py -m gpu -q -x 2>&1 | tail -15
+  echo "== C++ host mirror incl. DynamicTrie"
+  timeout 300 python -m pytest tests/test_cpp_host.py -m gpu -q 2>&1 | tail -3
+  echo "== compute-sanitizer on the smallest dynamic test (racecheck is the point: emulation cannot see races)"
+  timeout 600 compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_dtrie.py -m gpu -q -x -k "n0-50 or 50-10-20" 2>&1 | tail -15
+  timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_dstate.py -m gpu -q -x -k "3-6-5" 2>&1 | tail -15
+  echo "== dynamic trie latency vs merge+rebuild (C5 shape)"
+  timeout 600 python tools/dtrie_bench.py --base 100000000 --dirty 10000 --mix 100,0,0 2>&1 | tail -2
+  timeout 600 python tools/dtrie_bench.py --base 100000000 --dirty 10000 --mix 80,10,10 2>&1 | tail -2
+  timeout 600 python tools/dtrie_bench.py --base 10000000 --dirty 10000 --mix 80,10,10 --compare 2>&1 | tail -2
+  echo "== dynamic state (C3 shape, 2000 touched accounts per block)"
+  timeout 900 python tools/dstate_bench.py --accounts 1000000 --slots 16 --touch 2000 --slot-writes 10 2>&1 | tail -2
+} > gpurun_out/first_gpu_call.log 2>&1
+tail -60 gpurun_out/first_gpu_call.log
