@@ -565,6 +565,116 @@ class DynamicTrie {
     B256 root_{};
 };
 
+/// The whole hashed state resident in HBM (b200_dstate_*): accounts and every storage trie.  `commit` applies one block's
+/// HashedPostState in place and returns the new state root with the block's TrieUpdates — the role of reth's
+/// SparseStateTrie on the live path (crates/trie/sparse/src/state.rs) and of StateRoot::overlay_root_with_updates
+/// (crates/trie/db/src/state.rs:184-230); `account_proof` / `storage_proof` serve Proof::account_proof
+/// (crates/trie/trie/src/proof/mod.rs) from the same state.
+class DynamicStateRoot {
+  public:
+    DynamicStateRoot(const Engine &e, const HashedPostStateSorted &state) : e_(e) {
+        FlatState f = state.to_flat();
+        e_.check(b200_dstate_create(e_.raw(), f.acct_keys.data(), f.accts.data(), f.n_accounts(), f.slot_keys.data(),
+                                    f.slot_values.data(), f.seg_offsets.data(), &s_, root_.data()));
+    }
+    DynamicStateRoot(const DynamicStateRoot &) = delete;
+    DynamicStateRoot &operator=(const DynamicStateRoot &) = delete;
+    ~DynamicStateRoot() { b200_dstate_destroy(s_); }
+    const B256 &root() const { return root_; }
+    uint64_t accounts() const { return b200_dstate_accounts(s_); }
+    uint64_t slots() const { return b200_dstate_slots(s_); }
+
+    std::pair<B256, TrieUpdates> commit(const HashedPostState &post) {
+        std::set<B256> touched;
+        for (auto &ka : post.accounts) touched.insert(ka.first);
+        for (auto &ks : post.storages) touched.insert(ks.first);
+        std::vector<B256> order(touched.begin(), touched.end());
+        std::vector<uint8_t> keys, flags, slot_keys, slot_vals;
+        std::vector<b200_account> accts(order.size());
+        std::vector<uint64_t> offs{0};
+        for (size_t i = 0; i < order.size(); i++) {
+            const B256 &k = order[i];
+            keys.insert(keys.end(), k.begin(), k.end());
+            auto ia = post.accounts.find(k);
+            auto is = post.storages.find(k);
+            uint8_t fl = 0;
+            if (ia != post.accounts.end()) {
+                if (ia->second) {
+                    fl = 1;  // exists
+                    accts[i].nonce = ia->second->nonce;
+                    std::memcpy(accts[i].balance_be, ia->second->balance.data(), 32);
+                    const B256 &ch = ia->second->bytecode_hash ? *ia->second->bytecode_hash : KECCAK_EMPTY;
+                    std::memcpy(accts[i].code_hash, ch.data(), 32);
+                }  // else destroyed: flags 0
+            } else {
+                fl = 1 | 2;  // storage-only entry: account data unchanged
+            }
+            if (fl && is != post.storages.end()) {
+                if (is->second.wiped) fl |= 4;
+                for (auto &sv : is->second.storage) {
+                    slot_keys.insert(slot_keys.end(), sv.first.begin(), sv.first.end());
+                    slot_vals.insert(slot_vals.end(), sv.second.begin(), sv.second.end());
+                }
+            }
+            flags.push_back(fl);
+            offs.push_back(slot_keys.size() / 32);
+        }
+        b200_updates au{}, ar{}, su{}, sr{};
+        std::vector<uint8_t> deleted(order.size() + 1, 0);
+        e_.check(b200_dstate_apply(s_, keys.data(), accts.data(), flags.data(), order.size(), slot_keys.data(), slot_vals.data(),
+                                   offs.data(), root_.data(), &au, &ar, &su, &sr, deleted.data(), nullptr));
+        TrieUpdates out;
+        for (uint64_t i = 0; i < au.n_nodes; i++) out.account_nodes.insert(detail::branch_node(au, i));
+        for (uint64_t i = 0; i < ar.n_nodes; i++) out.removed_nodes.insert(detail::branch_node(ar, i).first);
+        std::map<uint32_t, StorageTrieUpdates> per_entry;
+        for (uint64_t i = 0; i < su.n_nodes; i++) per_entry[su.trie_id[i]].storage_nodes.insert(detail::branch_node(su, i));
+        for (uint64_t i = 0; i < sr.n_nodes; i++) per_entry[sr.trie_id[i]].removed_nodes.insert(detail::branch_node(sr, i).first);
+        for (size_t i = 0; i < order.size(); i++) {
+            StorageTrieUpdates st = per_entry.count((uint32_t)i) ? per_entry[(uint32_t)i] : StorageTrieUpdates{};
+            st.is_deleted = deleted[i] != 0;
+            out.insert_storage_updates(order[i], std::move(st));
+        }
+        for (b200_updates *u : {&au, &ar, &su, &sr}) b200_updates_release(u);
+        return {root_, std::move(out)};
+    }
+
+    /// node RLPs from the state root down to the account (or to where the trie shows it does not exist)
+    std::vector<std::vector<uint8_t>> account_proof(const B256 &hashed_address) const {
+        b200_proofs p{};
+        e_.check(b200_dstate_account_proofs(s_, hashed_address.data(), 1, &p));
+        return take(p, 0);
+    }
+    /// (storage root, one proof per hashed slot)
+    std::pair<B256, std::vector<std::vector<std::vector<uint8_t>>>> storage_proofs(const B256 &hashed_address,
+                                                                                   const std::vector<B256> &hashed_slots) const {
+        std::vector<uint8_t> sk;
+        for (auto &s : hashed_slots) sk.insert(sk.end(), s.begin(), s.end());
+        b200_proofs p{};
+        B256 sroot{};
+        e_.check(b200_dstate_storage_proofs(s_, hashed_address.data(), sk.data(), hashed_slots.size(), sroot.data(), &p));
+        std::vector<std::vector<std::vector<uint8_t>>> out;
+        for (uint64_t t = 0; t < hashed_slots.size(); t++) out.push_back(nodes_of(p, t));
+        b200_proofs_release(&p);
+        return {sroot, std::move(out)};
+    }
+
+  private:
+    static std::vector<std::vector<uint8_t>> nodes_of(const b200_proofs &p, uint64_t t) {
+        std::vector<std::vector<uint8_t>> out;
+        for (uint64_t k = p.node_offset[t]; k < p.node_offset[t + 1]; k++)
+            out.emplace_back(p.rlp + p.rlp_offset[k], p.rlp + p.rlp_offset[k + 1]);
+        return out;
+    }
+    static std::vector<std::vector<uint8_t>> take(b200_proofs &p, uint64_t t) {
+        auto out = nodes_of(p, t);
+        b200_proofs_release(&p);
+        return out;
+    }
+    const Engine &e_;
+    b200_dstate *s_ = nullptr;
+    B256 root_{};
+};
+
 /// ParallelStateRoot::{incremental_root, incremental_root_with_updates} — crates/trie/parallel/src/root.rs:35-77.
 /// The storage-root fan-out and the account fold are the same device launches.
 class ParallelStateRoot : public StateRoot {

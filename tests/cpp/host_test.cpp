@@ -275,6 +275,87 @@ static void dynamic_trie_blocks(const Engine &e) {
     }
 }
 
+// DynamicStateRoot: blocks with new / changed / destroyed accounts and slot writes / zeroing / wipes; root == oracle over
+// the merged state after every block, and an account proof hashes up to that root.  Opt-in on a GPU like dynamic_trie_blocks.
+static void dynamic_state_blocks(const Engine &e) {
+    std::mt19937_64 rng(11);
+    auto rand_key = [&] {
+        B256 k;
+        for (auto &b : k) b = (uint8_t)rng();
+        return k;
+    };
+    HashedPostState merged;
+    for (int i = 0; i < 400; i++) {
+        B256 k = rand_key();
+        merged.accounts[k] = Account{rng() & 0xff, u256_from_u64(rng()), std::nullopt};
+        if (i % 3 == 0)
+            for (int s = 0; s < 1 + (int)(rng() % 20); s++) merged.storages[k].storage[rand_key()] = u256_from_u64(rng() | 1);
+    }
+    auto oracle_root = [&](const HashedPostState &st) {
+        FlatState f = st.into_sorted().to_flat();
+        B256 r;
+        CHECK(orc_state_root_full(f.acct_keys.data(), reinterpret_cast<const orc_account *>(f.accts.data()), f.n_accounts(),
+                                  f.slot_keys.data(), f.slot_values.data(), f.seg_offsets.data(), r.data(), nullptr, nullptr, 2) == 0);
+        return r;
+    };
+    DynamicStateRoot ds(e, merged.into_sorted());
+    CHECK(ds.root() == oracle_root(merged));
+    for (int block = 0; block < 4; block++) {
+        HashedPostState post;
+        std::vector<B256> live;
+        for (auto &ka : merged.accounts) live.push_back(ka.first);
+        for (int i = 0; i < 20; i++) {  // balance changes
+            const B256 &k = live[rng() % live.size()];
+            Account a = *merged.accounts[k];
+            a.nonce++;
+            post.accounts[k] = a;
+        }
+        for (int i = 0; i < 5; i++) {  // new accounts with storage
+            B256 k = rand_key();
+            post.accounts[k] = Account{0, u256_from_u64(7), std::nullopt};
+            post.storages[k].storage[rand_key()] = u256_from_u64(9);
+        }
+        for (int i = 0; i < 3; i++) {  // destroyed
+            const B256 &k = live[rng() % live.size()];
+            post.accounts[k] = std::nullopt;
+            post.storages[k].wiped = true;
+            post.storages[k].storage.clear();
+        }
+        int touched = 0;
+        for (auto &ks : merged.storages) {  // storage-only writes, one zeroed slot each
+            if (post.accounts.count(ks.first) || ks.second.storage.empty() || ++touched > 6) continue;
+            post.storages[ks.first].storage[ks.second.storage.begin()->first] = U256{};
+            post.storages[ks.first].storage[rand_key()] = u256_from_u64(rng() | 1);
+        }
+        auto [root, upd] = ds.commit(post);
+        for (auto &ks : post.storages) {  // the model: HashedPostState::extend + deletion rules
+            HashedStorage &cur = merged.storages[ks.first];
+            if (ks.second.wiped) cur.storage.clear();
+            for (auto &sv : ks.second.storage) {
+                if (is_zero(sv.second)) cur.storage.erase(sv.first);
+                else cur.storage[sv.first] = sv.second;
+            }
+        }
+        for (auto &ka : post.accounts) {
+            if (!ka.second) {
+                merged.accounts.erase(ka.first);
+                merged.storages.erase(ka.first);
+            } else {
+                merged.accounts[ka.first] = ka.second;
+            }
+        }
+        CHECK(root == oracle_root(merged));
+        CHECK(ds.accounts() == merged.accounts.size());
+        CHECK(!upd.account_nodes.empty());
+        // an inclusion proof: its first node hashes to the root
+        auto proof = ds.account_proof(merged.accounts.begin()->first);
+        CHECK(!proof.empty());
+        B256 h;
+        orc_keccak256(proof[0].data(), proof[0].size(), h.data());
+        CHECK(h == root);
+    }
+}
+
 // Table rows — host-only, runs before a device is needed.  Key vectors: crates/trie/common/src/nibbles.rs
 // :321-346 (StoredNibbles [2,4] -> 02 04; subkey = 64 nibble bytes + count), :443-450 (packed 0xAB 0xC0 .. 03).
 static void table_rows_host_only() {
@@ -332,7 +413,10 @@ int main() {
         extension_node_storage_trie(e);
         prefix_sets_and_destroyed(e);
         random_state_vs_oracle(e);
-        if (std::getenv("B200_EMU") || std::getenv("B200_DTRIE_ON_GPU")) dynamic_trie_blocks(e);
+        if (std::getenv("B200_EMU") || std::getenv("B200_DTRIE_ON_GPU")) {
+            dynamic_trie_blocks(e);
+            dynamic_state_blocks(e);
+        }
     } catch (const B200Error &err) {
         std::printf("B200Error: %s\n", err.what());
         return err.status == B200_ERR_NO_DEVICE ? 77 : 2;
