@@ -223,3 +223,35 @@ def test_rejects_unsorted_or_duplicate_keys_and_stays_consistent(eng):
     assert h.trie.root() == before
     h.commit({ks[0]: (0, acct(0))})      # still usable
     h.trie.close()
+
+
+def test_clustered_keys_long_extensions(eng):
+    """Keys drawn from a few long shared prefixes: deep branches under long extension nodes, so inserts split extensions at
+    every depth and deletes merge them back (the shapes uniform keccak keys almost never produce)."""
+    rng = np.random.default_rng(21)
+    prefixes = [rng.integers(0, 256, int(rng.integers(3, 31)), dtype=np.uint8).tobytes() for _ in range(6)]
+    prefixes += [prefixes[0][:5] + bytes([prefixes[0][5] ^ 0x01]) + prefixes[0][6:], prefixes[1][:9]]
+
+    def clustered():
+        p = prefixes[int(rng.integers(0, len(prefixes)))]
+        cut = int(rng.integers(1, len(p) + 1))
+        return p[:cut] + rng.integers(0, 256, 32 - cut, dtype=np.uint8).tobytes()
+
+    h = Harness(eng, 0, seed=30)
+    h.commit({clustered(): (1, acct(1)) for _ in range(400)})
+    for step in range(6):
+        existing = sorted(h.state)
+        dirty = {}
+        for _ in range(120):
+            r = rng.integers(0, 3)
+            if r == 0:
+                dirty[clustered()] = (1, acct(step + 2))
+            elif r == 1:
+                dirty[existing[int(rng.integers(0, len(existing)))]] = (0, acct(0))
+            else:
+                k = bytearray(existing[int(rng.integers(0, len(existing)))])
+                k[int(rng.integers(0, 32))] ^= 1 << int(rng.integers(0, 8))     # one bit away: splits deep inside an edge
+                dirty[bytes(k)] = (1, acct(7))
+        h.commit(dirty)
+    h.commit({k: (0, acct(0)) for k in sorted(h.state)[3:]})                    # collapse almost everything
+    h.trie.close()
