@@ -252,10 +252,28 @@ static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const ui
 }
 
 // re-hash of the seeded paths, recycling of the freed nodes (asynchronous)
+// Small dirty sets: one warp per seed (latency).  Large ones: one thread per seed through the populous levels, warps for
+// the sparse top of the single account trie (split depth 3: <= 4096 nodes per level above it); a storage forest has no
+// common sparse top, its threads climb all the way.  B200_DT_TWO_STAGE_MIN overrides the switch-over (tuning / tests).
+static uint64_t dt_two_stage_min() {
+    static const uint64_t v = [] {
+        const char *e = getenv("B200_DT_TWO_STAGE_MIN");
+        return e ? strtoull(e, nullptr, 10) : (uint64_t)WARP_LEVEL_MAX;
+    }();
+    return v;
+}
 static int32_t da_rehash(DArena *a, uint64_t m) {
     b200_ctx *c = a->c;
+    const uint32_t max_seeds = (uint32_t)(6 * m + 64);
+    uint32_t *handoff = nullptr, *handoff_count = nullptr;
+    if (m > dt_two_stage_min()) {  // every seed hands over at most once
+        TRY(da_scratch(a, a->sel, ((size_t)max_seeds + 1) * 4));
+        handoff = static_cast<uint32_t *>(a->sel.p) + 1;
+        handoff_count = static_cast<uint32_t *>(a->sel.p);
+        CU(cudaMemsetAsync(handoff_count, 0, 4, c->stream));
+    }
     DTrieDev d = da_view(a);
-    CU(launch_dt_rehash(d, (uint32_t)(6 * m + 64), c->stream));
+    CU(launch_dt_rehash(d, max_seeds, handoff, handoff_count, (a->forest && !a->account) ? 0 : 3, c->stream));
     CU(launch_dt_finish(d, (uint32_t)m + 16, c->stream));
     c->launches += 5;
     return B200_OK;

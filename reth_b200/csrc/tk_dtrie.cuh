@@ -678,6 +678,189 @@ __global__ void __launch_bounds__(WARPS * 32) dt_wavefront_kernel(DTrieDev t, co
     }
 }
 
+// ------------------------------------------------------------------------------------------------ two-stage re-hash
+// Large dirty sets (sync catch-up, thousands of blocks per commit): the warp-per-seed wavefront spends ~14x the
+// instructions of the register-resident sponge.  Stage A: one THREAD per seed hashes its item and climbs while the
+// ancestors are deep (depth >= split_depth: the populous levels); where the trie thins out it hands the arrival over.
+// Stage B (dt_climb_kernel): one WARP per hand-over finishes the sparse top with the latency-optimised builder.
+// Same last-arriver protocol as dt_wavefront_kernel; the two stages are separate launches.
+template <int BLOCK>
+__device__ __forceinline__ void dt_thread_build_node(Strip<BLOCK> &s, uint32_t *smem, const DTrieDev &t, uint32_t v,
+                                                     uint32_t &hashed, uint32_t &exts, uint32_t (&ref)[8]) {
+    s.init(smem);
+    const uint32_t *ch = t.nchild + 16 * (uint64_t)v;
+    const int d = t.ndepth[v];
+    uint32_t payload = 1, state_mask = 0, tree_mask = 0, hash_mask = 0;
+    for (int k = 0; k < 16; k++) {
+        uint32_t cw = ch[k];
+        if (cw == DT_NONE) {
+            payload += 1;
+            continue;
+        }
+        bool leaf = (cw & DT_LEAF) != 0;
+        uint32_t id = cw & ~DT_LEAF;
+        uint32_t m = __ldcg(leaf ? t.lmeta + id : t.nmeta + id);
+        payload += (m & META_LEN) ? (m & META_LEN) : 33u;
+        state_mask |= 1u << k;
+        if (!leaf) {
+            if (!(m & META_EXT)) {
+                hash_mask |= 1u << k;
+                if (m & META_LEN) atomicExch(t.err, B200_DEVERR_INLINE_HASH_CHILD);
+            }
+            if (m & META_STORED) tree_mask |= 1u << k;
+        }
+    }
+    put_list_header(s, payload);
+    for (int k = 0; k < 16; k++) {
+        uint32_t cw = ch[k];
+        if (cw == DT_NONE) {
+            s.byte(0x80);
+            continue;
+        }
+        bool leaf = (cw & DT_LEAF) != 0;
+        uint32_t id = cw & ~DT_LEAF;
+        uint32_t m = __ldcg(leaf ? t.lmeta + id : t.nmeta + id);
+        const uint4 *q = reinterpret_cast<const uint4 *>((leaf ? t.lref : t.nref) + 32 * (uint64_t)id);
+        uint4 x = __ldcg(q), y = __ldcg(q + 1);
+        uint32_t cr[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+        uint32_t il = m & META_LEN;
+        if (il == 0) {
+            s.byte(0xa0);
+            s.words8(cr);
+        } else {
+            for (uint32_t b = 0; b < il; b++) s.byte(byte_at(cr, b));
+        }
+    }
+    s.byte(0x80);
+    const uint32_t len = list_header_len(payload) + payload;
+    const uint32_t par = t.nparent[v];
+    const int pd = par == DT_NONE ? -1 : (int)t.ndepth[par];
+    const bool is_root = pd < 0, need_ext = pd + 1 < d;
+    uint32_t meta = strip_to_ref(s, len, is_root && !need_ext, ref, hashed);
+    if (need_ext) {
+        s.reset();
+        uint32_t elen = encode_extension(s, t.nkey + 32 * (uint64_t)v, (uint32_t)(pd + 1), (uint32_t)d, ref, meta);
+        meta = strip_to_ref(s, elen, is_root, ref, hashed) | META_EXT;
+        exts++;
+    }
+    if ((tree_mask | hash_mask) != 0) meta |= META_STORED;
+    if ((t.nmeta[v] & META_STORED) && !(meta & META_STORED)) dt_record_removed(t, v);
+    store32(t.nref + 32 * (uint64_t)v, ref);
+    t.nmeta[v] = (uint8_t)meta;
+    t.nmasks[v] = make_ushort4((unsigned short)state_mask, (unsigned short)tree_mask, (unsigned short)hash_mask, (unsigned short)d);
+    t.built[atomicAdd(&t.g[DG_BUILT], 1u)] = v;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) dt_wavefront_thread_kernel(DTrieDev t, const uint32_t *__restrict__ count_p,
+                                                                   uint32_t *__restrict__ handoff_list,
+                                                                   uint32_t *__restrict__ handoff_count, int split_depth) {
+    extern __shared__ uint32_t smem[];
+    if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
+    Strip<BLOCK> s;
+    uint32_t hashed = 0, exts = 0;
+    const uint32_t e = blockIdx.x * BLOCK + threadIdx.x;
+    const uint32_t sd = e < *count_p ? t.seeds[e] : DT_NONE;
+    if (sd != DT_NONE) {
+        uint32_t ref[8];
+        uint32_t p;
+        if (sd & DT_LEAF) {
+            const uint32_t x = sd & ~DT_LEAF;
+            s.init(smem);
+            p = t.lparent[x];
+            const int pd = p == DT_NONE ? -1 : (int)t.ndepth[p];
+            uint32_t k[8];
+            load32_nc(t.lkey + 32 * (uint64_t)x, k);
+            uint32_t len = t.account ? encode_leaf<Strip<BLOCK>, true>(s, k, pd, t.lval + 72 * (uint64_t)x,
+                                                                        t.lsroot ? t.lsroot + 32 * (uint64_t)x : nullptr, t.err)
+                                     : encode_leaf<Strip<BLOCK>, false>(s, k, pd, t.lval + 32 * (uint64_t)x, nullptr, t.err);
+            uint32_t meta = strip_to_ref(s, len, pd < 0, ref, hashed);
+            store32(t.lref + 32 * (uint64_t)x, ref);
+            t.lmeta[x] = (uint8_t)meta;
+        } else {
+            dt_thread_build_node<BLOCK>(s, smem, t, sd, hashed, exts, ref);
+            p = t.nparent[sd];
+        }
+        bool top = true;
+        for (int hops = 0; p != DT_NONE; hops++) {
+            if (hops > DT_MAX_HOPS) {
+                atomicExch(t.err, B200_DEVERR_CORRUPT);
+                top = false;
+                break;
+            }
+            if ((int)t.ndepth[p] < split_depth) {  // the sparse top belongs to the warps: hand the arrival over
+                __threadfence();
+                handoff_list[atomicAdd(handoff_count, 1u)] = p;
+                top = false;
+                break;
+            }
+            __threadfence();
+            bool last = atomicSub(&t.npending[p], 1u) == 1u;
+            __threadfence();
+            if (!last) {
+                top = false;
+                break;
+            }
+            dt_thread_build_node<BLOCK>(s, smem, t, p, hashed, exts, ref);
+            p = t.nparent[p];
+        }
+        if (top) store32(t.top_out + (uint64_t)t.top_stride * dt_trie_of(t, sd), ref);
+    }
+    for (int o = 16; o; o >>= 1) {
+        hashed += __shfl_xor_sync(0xffffffffu, hashed, o);
+        exts += __shfl_xor_sync(0xffffffffu, exts, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (hashed) atomicAdd(&t.counters[CNT_HASHED], (unsigned long long)hashed);
+        if (exts) atomicAdd(&t.counters[CNT_EXT], (unsigned long long)exts);
+    }
+}
+
+// Stage B: every list entry is one arrival at node p (a dirty child that stage A finished).
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) dt_climb_kernel(DTrieDev t, const uint32_t *__restrict__ arrivals,
+                                                             const uint32_t *__restrict__ count_p) {
+    __shared__ __align__(16) uint8_t sbuf[WARPS][WARP_BUF];
+    if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *buf = sbuf[warp];
+    WarpKeccak kw;
+    kw.init(lane);
+    uint32_t hashed = 0, exts = 0;
+    const uint32_t count = *count_p;
+    for (uint32_t e = blockIdx.x * WARPS + warp; e < count; e += gridDim.x * WARPS) {
+        uint32_t p = arrivals[e];
+        const uint32_t first = p;
+        uint32_t out[8];
+        bool top = true;
+        for (int hops = 0; p != DT_NONE; hops++) {
+            if (hops > DT_MAX_HOPS) {
+                if (lane == 0) atomicExch(t.err, B200_DEVERR_CORRUPT);
+                top = false;
+                break;
+            }
+            uint32_t last = 0;
+            if (lane == 0) {
+                __threadfence();
+                last = atomicSub(&t.npending[p], 1u) == 1u;
+                __threadfence();
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (!last) {
+                top = false;
+                break;
+            }
+            dt_warp_build_node(t, p, buf, kw, lane, hashed, exts, out);
+            p = t.nparent[p];
+        }
+        if (top && lane == 0) store32(t.top_out + (uint64_t)t.top_stride * dt_trie_of(t, first), out);
+    }
+    if (lane == 0) {
+        if (hashed) atomicAdd(&t.counters[CNT_HASHED], (unsigned long long)hashed);
+        if (exts) atomicAdd(&t.counters[CNT_EXT], (unsigned long long)exts);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ TrieUpdates
 // flags[i] = 1 iff re-hashed node built[i] is stored (tree|hash mask != 0, path not empty); n_hashes[i] its hash count
 __global__ void dt_stored_flags_kernel(DTrieDev t, const uint32_t *__restrict__ count_p, uint8_t *__restrict__ flags,

@@ -47,14 +47,33 @@ __global__ void dt_finish_kernel(DTrieDev t) {
     t.g[DG_NODE_FREE] += t.g[DG_FREED_NOW];
     t.g[DG_FREED_NOW] = 0;
 }
-cudaError_t launch_dt_rehash(const DTrieDev &t, uint32_t max_seeds, cudaStream_t st) {
+// handoff != nullptr selects the two-stage form (thread per seed below split_depth's levels, warps above)
+cudaError_t launch_dt_rehash(const DTrieDev &t, uint32_t max_seeds, uint32_t *handoff, uint32_t *handoff_count, int split_depth,
+                             cudaStream_t st) {
     constexpr int WARPS = 4;
     const uint32_t *count_p = t.g + DG_SEEDS;
     unsigned blocks = blocks_for(max_seeds, 128);
     dt_mark_kernel<<<blocks, 128, 0, st>>>(t, count_p);
     dt_starts_kernel<<<blocks, 128, 0, st>>>(t, count_p);
-    unsigned wblocks = blocks_for(max_seeds, WARPS), cap = (unsigned)sms() * 16;
-    dt_wavefront_kernel<WARPS><<<wblocks < cap ? wblocks : cap, WARPS * 32, 0, st>>>(t, count_p);
+    unsigned cap = (unsigned)sms() * 16;
+    if (handoff == nullptr) {
+        unsigned wblocks = blocks_for(max_seeds, WARPS);
+        dt_wavefront_kernel<WARPS><<<wblocks < cap ? wblocks : cap, WARPS * 32, 0, st>>>(t, count_p);
+        return cudaGetLastError();
+    }
+    constexpr int TB = 64;
+    auto ka = dt_wavefront_thread_kernel<TB>;
+    size_t smem = (size_t)BRANCH_WORDS * TB * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    ka<<<blocks_for(max_seeds, TB), TB, smem, st>>>(t, count_p, handoff, handoff_count, split_depth);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    unsigned wblocks = blocks_for(max_seeds, WARPS);
+    dt_climb_kernel<WARPS><<<wblocks < cap ? wblocks : cap, WARPS * 32, 0, st>>>(t, handoff, handoff_count);
     return cudaGetLastError();
 }
 cudaError_t launch_dt_finish(const DTrieDev &t, uint32_t max_freed, cudaStream_t st) {

@@ -197,7 +197,8 @@ cudaError_t launch_dt_collapse_round(const DTrieDev &t, const uint32_t *list, co
 cudaError_t launch_dt_insert(const DTrieDev &t, const uint32_t *trie_of_key, const uint8_t *keys, const uint8_t *vals,
                              const uint8_t *sroots, const uint32_t *ins_idx, const uint32_t *n_ins_p, uint64_t max_ins,
                              uint64_t *attach, uint32_t *leaf_of, cudaStream_t st);
-cudaError_t launch_dt_rehash(const DTrieDev &t, uint32_t max_seeds, cudaStream_t st);
+cudaError_t launch_dt_rehash(const DTrieDev &t, uint32_t max_seeds, uint32_t *handoff, uint32_t *handoff_count, int split_depth,
+                             cudaStream_t st);
 cudaError_t launch_dt_finish(const DTrieDev &t, uint32_t max_freed, cudaStream_t st);
 cudaError_t launch_dt_stored_flags(const DTrieDev &t, uint32_t max_built, uint8_t *flags, uint32_t *n_hashes, cudaStream_t st);
 cudaError_t launch_dt_gather_updates(const DTrieDev &t, const uint32_t *stored_ids, uint32_t n_stored,

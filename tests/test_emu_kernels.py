@@ -24,6 +24,17 @@ def test_cuda_sources_pass_parity_under_cpu_emulation():
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
 
 
+def test_dynamic_tries_two_stage_rehash_under_cpu_emulation():
+    """The dynamic tries again with the thread-per-seed + warp-climb re-hash forced for every block size
+    (B200_DT_TWO_STAGE_MIN=0; by default only dirty sets above 4096 entries take it)."""
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_dtrie.py", "tests/test_gpu_dstate.py", "-m", "gpu",
+                        "--emu", "-q", "-x", "-p", "no:cacheprovider"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=1500, env=dict(os.environ, B200_DT_TWO_STAGE_MIN="0"))
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout, tail
+
+
 def test_cpp_host_mirror_under_cpu_emulation(tmp_path):
     """tests/cpp/host_test.cpp (reth's trie tests restated over the C++ host mirror) linked against the emulated build."""
     emu = os.path.join(ROOT, "tools", "emu")
