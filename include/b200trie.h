@@ -346,6 +346,11 @@ B200_API int32_t b200_dstate_apply(b200_dstate *, const uint8_t *acct_keys32, co
 B200_API int32_t b200_dstate_create_sharded(b200_ctx *, const uint8_t *acct_keys32, const b200_account *accts,
                                             uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
                                             const uint64_t *seg_offsets, b200_dstate **out, uint8_t root32[32]);
+/* Device-resident seed: every pointer is a device pointer (a state too large to stage through one host call is uploaded
+ * in pieces by the caller); n_slots = d_seg_offsets[n_accounts]; sharded != 0 selects the sharded layout. */
+B200_API int32_t b200_dstate_create_dev(b200_ctx *, const void *d_acct_keys32, const void *d_accts, uint64_t n_accounts,
+                                        const void *d_slot_keys32, const void *d_values32_be, const void *d_seg_offsets,
+                                        uint64_t n_slots, int32_t sharded, b200_dstate **out, void *d_root32 /* nullable */);
 B200_API int32_t b200_dstate_frontier(b200_dstate *, b200_frontier_entry out16[16]);
 /* Merkle proofs from the resident state (eth_getProof / reth's Proof::account_proof and storage_proof,
  * crates/trie/trie/src/proof/mod.rs): target t's proof is nodes node_offset[t] .. node_offset[t+1], node k's RLP is

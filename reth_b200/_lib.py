@@ -161,6 +161,7 @@ def load():
     sig("b200_dtrie_destroy", None, vp)
     sig("b200_dstate_create", i32, vp, vp, vp, u64, vp, vp, vp, C.POINTER(vp), vp)
     sig("b200_dstate_create_sharded", i32, vp, vp, vp, u64, vp, vp, vp, C.POINTER(vp), vp)
+    sig("b200_dstate_create_dev", i32, vp, vp, vp, u64, vp, vp, vp, u64, i32, C.POINTER(vp), vp)
     sig("b200_dstate_frontier", i32, vp, C.POINTER(FrontierEntry))
     sig("b200_dstate_apply", i32, vp, vp, vp, vp, u64, vp, vp, vp, vp, PU, PU, PU, PU, vp, PS)
     sig("b200_dstate_account_proofs", i32, vp, vp, u64, C.POINTER(Proofs))

@@ -51,30 +51,46 @@ static int32_t dstate_frontier_on_device(b200_dstate *t) {
     return B200_OK;
 }
 
+// on_device: every input pointer is a device pointer and n_slots_dev gives the slot count (the segment table is then
+// validated by the build itself: B200_ERR_INVALID_ARG through the sticky status)
 static int32_t dstate_create_impl(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts, uint64_t n_accounts,
                                   const uint8_t *slot_keys32, const uint8_t *values32_be, const uint64_t *seg_offsets,
-                                  bool sharded, b200_dstate **out, uint8_t root32[32]) {
+                                  bool sharded, bool on_device, uint64_t n_slots_dev, b200_dstate **out, uint8_t root32[32]) {
     if (!c || !out || !seg_offsets || (n_accounts && (!acct_keys32 || !accts))) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
     *out = nullptr;
-    TRY(check_offsets_host(c, seg_offsets, n_accounts));
-    const uint64_t n_slots = seg_offsets[n_accounts];
+    if (!on_device) TRY(check_offsets_host(c, seg_offsets, n_accounts));
+    const uint64_t n_slots = on_device ? n_slots_dev : seg_offsets[n_accounts];
     if (n_slots && (!slot_keys32 || !values32_be)) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
     std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
+    const cudaMemcpyKind in_kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     b200_trie *src_s = nullptr, *src_a = nullptr;
-    TRY(forest_create_locked(c, slot_keys32, values32_be, seg_offsets, n_accounts, n_slots, cudaMemcpyHostToDevice, &src_s));
+    TRY(forest_create_locked(c, slot_keys32, values32_be, seg_offsets, n_accounts, n_slots, in_kind, &src_s));
     // the account trie takes its storage roots straight from the forest build (device memory: cudaMemcpyDefault)
     int32_t r;
     if (sharded) {
         uint64_t bucket_offsets[17];
-        for (uint32_t b = 0; b <= 16; b++) {  // first account whose top nibble >= b
-            uint64_t lo = 0, hi = n_accounts;
-            while (lo < hi) {
-                uint64_t mid = (lo + hi) >> 1;
-                if ((uint32_t)(acct_keys32[32 * mid] >> 4) < b) lo = mid + 1;
-                else hi = mid;
+        if (on_device) {  // nibble_buckets_kernel: 17 binary searches on the device
+            uint64_t *d_offs = reinterpret_cast<uint64_t *>(small_u32(c) + SM_HIST);
+            cudaError_t e = launch_nibble_buckets(acct_keys32, n_accounts, d_offs, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(bucket_offsets, d_offs, sizeof bucket_offsets, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) {
+                b200_trie_destroy(src_s);
+                return fail(c, B200_ERR_CUDA, "bucket offsets: %s", cudaGetErrorString(e));
             }
-            bucket_offsets[b] = lo;
+            c->launches++;
+        } else {
+            for (uint32_t b = 0; b <= 16; b++) {  // first account whose top nibble >= b
+                uint64_t lo = 0, hi = n_accounts;
+                while (lo < hi) {
+                    uint64_t mid = (lo + hi) >> 1;
+                    if ((uint32_t)(acct_keys32[32 * mid] >> 4) < b) lo = mid + 1;
+                    else hi = mid;
+                }
+                bucket_offsets[b] = lo;
+            }
         }
         r = bucket_forest_create_locked(c, acct_keys32, accts, src_s->seg_roots.p, n_accounts, bucket_offsets, cudaMemcpyDefault, &src_a);
     } else {
@@ -112,7 +128,7 @@ static int32_t dstate_create_impl(b200_ctx *c, const uint8_t *acct_keys32, const
         TRY(da_from_build(&t->sto, src_s, t->acc.lcap));
         if (sharded) TRY(dstate_frontier_on_device(t));
         else CU(cudaMemcpyAsync(t->root.p, src_a->root.p, 32, cudaMemcpyDeviceToDevice, st));
-        if (root32) CU(cudaMemcpyAsync(root32, t->root.p, 32, cudaMemcpyDeviceToHost, st));
+        if (root32) CU(cudaMemcpyAsync(root32, t->root.p, 32, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         return B200_OK;
     };
@@ -130,7 +146,18 @@ static int32_t dstate_create_impl(b200_ctx *c, const uint8_t *acct_keys32, const
 extern "C" B200_API int32_t b200_dstate_create(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
                                                uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
                                                const uint64_t *seg_offsets, b200_dstate **out, uint8_t root32[32]) {
-    return dstate_create_impl(c, acct_keys32, accts, n_accounts, slot_keys32, values32_be, seg_offsets, false, out, root32);
+    return dstate_create_impl(c, acct_keys32, accts, n_accounts, slot_keys32, values32_be, seg_offsets, false, false, 0, out, root32);
+}
+// Device-resident seed (a state too large to stage through one host call is uploaded in pieces by the caller): every
+// pointer is a device pointer, d_seg_offsets has n_accounts+1 entries, n_slots = d_seg_offsets[n_accounts]; `sharded`
+// selects b200_dstate_create_sharded's layout.  d_root32 (nullable) is a device buffer.
+extern "C" B200_API int32_t b200_dstate_create_dev(b200_ctx *c, const void *d_acct_keys32, const void *d_accts, uint64_t n_accounts,
+                                                   const void *d_slot_keys32, const void *d_values32_be, const void *d_seg_offsets,
+                                                   uint64_t n_slots, int32_t sharded, b200_dstate **out, void *d_root32) {
+    return dstate_create_impl(c, static_cast<const uint8_t *>(d_acct_keys32), static_cast<const b200_account *>(d_accts), n_accounts,
+                              static_cast<const uint8_t *>(d_slot_keys32), static_cast<const uint8_t *>(d_values32_be),
+                              static_cast<const uint64_t *>(d_seg_offsets), sharded != 0, true, n_slots, out,
+                              static_cast<uint8_t *>(d_root32));
 }
 // One rank's shard of a state that is split by top key nibble (any subset of the 16 buckets).  root32 (nullable) receives
 // the root this shard has on its own; the global root is b200_root_from_frontier over the gathered b200_dstate_frontier
@@ -139,7 +166,7 @@ extern "C" B200_API int32_t b200_dstate_create_sharded(b200_ctx *c, const uint8_
                                                        uint64_t n_accounts, const uint8_t *slot_keys32,
                                                        const uint8_t *values32_be, const uint64_t *seg_offsets,
                                                        b200_dstate **out, uint8_t root32[32]) {
-    return dstate_create_impl(c, acct_keys32, accts, n_accounts, slot_keys32, values32_be, seg_offsets, true, out, root32);
+    return dstate_create_impl(c, acct_keys32, accts, n_accounts, slot_keys32, values32_be, seg_offsets, true, false, 0, out, root32);
 }
 // The 16 top-nibble frontier entries of a sharded state as of its last apply (empty entries for buckets it does not hold).
 extern "C" B200_API int32_t b200_dstate_frontier(b200_dstate *t, b200_frontier_entry out16[16]) {

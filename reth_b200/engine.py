@@ -485,6 +485,17 @@ class DynamicState:
                          _ptr(seg_offsets), C.byref(h), _ptr(root)))
         return cls(engine, h, root.tobytes())
 
+    @classmethod
+    def create_dev(cls, engine: Engine, p_acct_keys: int, p_accts: int, n_accounts: int, p_slot_keys: int, p_values: int,
+                   p_seg_offsets: int, n_slots: int, sharded: bool = False) -> "DynamicState":
+        """Seed from device-resident arrays given as raw device addresses (torch tensors: `.data_ptr()`)."""
+        h = C.c_void_p()
+        engine._check(engine.lib.b200_dstate_create_dev(engine.ctx, p_acct_keys, p_accts, n_accounts, p_slot_keys, p_values,
+                                                        p_seg_offsets, n_slots, 1 if sharded else 0, C.byref(h), None))
+        ds = cls(engine, h, b"")
+        ds._root = ds.root()
+        return ds
+
     def frontier(self) -> np.ndarray:
         """(16, 68) uint8: this shard's b200_frontier_entry array as of the last apply."""
         out = (FrontierEntry * 16)()

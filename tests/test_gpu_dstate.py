@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 import oracle
+from tests.util import to_device_ptrs
 
 pytestmark = [
     pytest.mark.gpu,
@@ -395,3 +396,19 @@ def test_sharded_state_degenerate_buckets(eng):
     h.commit({k: (0, acct(0), {}) for k in sorted(h.state)})           # empty state
     for ds in h.shards:
         ds.close()
+
+
+@pytest.mark.parametrize("sharded", [False, True])
+def test_device_resident_seed(eng, sharded):
+    """b200_dstate_create_dev: the seed arrays already live in device memory (tests/util.py:to_device_ptrs)."""
+    from reth_b200 import DynamicState
+    rng = np.random.default_rng(55)
+    state = random_state(rng, 600)
+    _, keys, accs, skeys, svals, offs = flatten(state)
+    ptrs, hold = to_device_ptrs((keys, accs, skeys, svals, offs))
+    ds = DynamicState.create_dev(eng, ptrs[0], ptrs[1], len(keys), ptrs[2], ptrs[3], ptrs[4], len(skeys), sharded=sharded)
+    root, _, _ = model(state)
+    if sharded:
+        assert eng.root_from_frontier(ds.frontier()) == root
+    assert ds.root() == root and ds.accounts() == len(state)
+    ds.close()

@@ -121,3 +121,16 @@ def synth_storage(seed: int, counts, value_mode="u64"):
         vals[addr, 12] |= 1
         vals[sel == 3, 0] |= 1
     return keys, vals, offs
+
+
+def to_device_ptrs(arrays):
+    """Raw device addresses of copies of `arrays` (+ the objects that keep them alive): CUDA tensors on a GPU; under
+    tools/emu device memory is host memory, so the numpy arrays themselves."""
+    import os
+    arrays = [np.ascontiguousarray(a) for a in arrays]
+    if not os.environ.get("B200_EMU"):
+        import torch
+        if torch.cuda.is_available():
+            hold = [torch.from_numpy(a.view(np.uint8).reshape(-1)).cuda() for a in arrays]
+            return [t.data_ptr() for t in hold], hold
+    return [a.ctypes.data for a in arrays], arrays
