@@ -237,17 +237,47 @@ static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const ui
         std::swap(list_cur, list_next);
         std::swap(cnt_cur, cnt_next);
     }
-    // ---- inserts: the dense list of insert entries, their attach points, one thread per run
-    uint32_t *ins_idx = static_cast<uint32_t *>(a->ins_idx.p);
+    // ---- inserts, in rounds: the dense list of insert entries; per round their attach points, then one thread per run
+    // inserts up to DT_KEYS_PER_RUN of its keys; what is left is compacted (order kept) and goes round again
+    constexpr uint32_t DT_KEYS_PER_RUN = 8;
+    uint32_t *idx_cur = static_cast<uint32_t *>(a->ins_idx.p);
     thrust::counting_iterator<uint32_t> counting(0);
     auto is_insert = thrust::make_transform_iterator(kind, IsKind{DK_INSERT});
     size_t t_sel = 0;
-    CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, is_insert, ins_idx, d.g + DG_NINSERT, (int64_t)m, st));
+    CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, is_insert, idx_cur, d.g + DG_NINSERT, (int64_t)m, st));
     ENSURE(cub_temp, t_sel);
-    CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, is_insert, ins_idx, d.g + DG_NINSERT, (int64_t)m, st));
-    CU(launch_dt_insert(d, d_trie_of_key, d_keys, d_vals, d_sroots, ins_idx, d.g + DG_NINSERT, m,
-                        static_cast<uint64_t *>(a->attach.p), leaf_of, st));
-    c->launches += 3;
+    CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, is_insert, idx_cur, d.g + DG_NINSERT, (int64_t)m, st));
+    c->launches++;
+    TRY(da_scratch(a, a->nh, m + 16));  // per-entry "still to insert" flags of a round
+    uint8_t *pending = static_cast<uint8_t *>(a->nh.p);
+    uint32_t *leftover = d.g + DG_LIST_A;  // free again: the collapse rounds are over
+    uint32_t *idx_next = nullptr;
+    uint64_t bound = m;  // upper bound of the entries still to insert
+    for (int round = 0;; round++) {
+        CU(cudaMemsetAsync(leftover, 0, 4, st));
+        CU(launch_dt_insert(d, d_trie_of_key, d_keys, d_vals, d_sroots, idx_cur, d.g + DG_NINSERT, bound,
+                            static_cast<uint64_t *>(a->attach.p), leaf_of, DT_KEYS_PER_RUN, pending, leftover, st));
+        c->launches += 2;
+        CU(cudaMemcpyAsync(ps + 200, leftover, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ps + 201, small_u32(c) + SM_ERR, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ps + 202, d.g + DG_NINSERT, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (ps[201] != B200_DEVERR_NONE) return map_dev_error(c, (int)ps[201]);
+        if (ps[200] == 0) break;
+        if (round > 80) return fail(c, B200_ERR_CUDA, "insert rounds do not converge");
+        if (!idx_next) {
+            TRY(da_scratch(a, a->sel, m * 4));
+            idx_next = static_cast<uint32_t *>(a->sel.p);
+        }
+        const int64_t live = ps[202];  // entries of this round: exactly those whose `pending` flag was just written
+        size_t t2 = 0;
+        CU(cub::DeviceSelect::Flagged(nullptr, t2, idx_cur, pending, idx_next, d.g + DG_NINSERT, live, st));
+        ENSURE(cub_temp, t2);
+        CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t2, idx_cur, pending, idx_next, d.g + DG_NINSERT, live, st));
+        c->launches++;
+        std::swap(idx_cur, idx_next);
+        bound = ps[200];
+    }
     return B200_OK;
 }
 

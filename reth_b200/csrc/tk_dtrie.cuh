@@ -431,10 +431,15 @@ static __device__ __forceinline__ uint32_t dt_insert_one(const DTrieDev &t, uint
     return x;
 }
 
+// One thread per run inserts its first `max_per_run` keys; the rest of a long run is left for the next round, by which
+// time the keys just inserted have fanned the attach point out into up to 16 deeper ones per level — a run of r keys
+// needs ~log(r) rounds instead of r serial inserts (a new contract with 100k slots, a bulk load into an empty trie).
+// pending[j] = 1 for every entry that is still to be inserted; *leftover counts them.
 __global__ void dt_insert_runs_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_key, const uint8_t *__restrict__ keys,
                                       const uint8_t *__restrict__ vals, const uint8_t *__restrict__ sroots,
                                       const uint32_t *__restrict__ ins_idx, const uint32_t *__restrict__ n_ins_p,
-                                      const uint64_t *__restrict__ attach, uint32_t *__restrict__ leaf_of) {
+                                      const uint64_t *__restrict__ attach, uint32_t *__restrict__ leaf_of, uint32_t max_per_run,
+                                      uint8_t *__restrict__ pending, uint32_t *__restrict__ leftover) {
     if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
     const uint32_t n_ins = *n_ins_p;
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -443,12 +448,21 @@ __global__ void dt_insert_runs_kernel(DTrieDev t, const uint32_t *__restrict__ t
     if (j && attach[j - 1] == a) return;  // not the head of its run
     const bool at_root = (a >> 63) != 0;
     uint32_t parent = at_root ? DT_NONE : (uint32_t)(a >> 4), slot = at_root ? 0u : (uint32_t)(a & 15);
+    uint32_t done = 0, left = 0;
     for (uint32_t q = j; q < n_ins && attach[q] == a; q++) {
+        if (done == max_per_run) {
+            pending[q] = 1;
+            left++;
+            continue;
+        }
         uint64_t i = ins_idx[q];
         uint32_t trie = trie_of_key ? trie_of_key[i] : 0;
         leaf_of[i] = dt_insert_one(t, trie, keys + 32 * i, vals + (uint64_t)t.val_stride * i, sroots ? sroots + 32 * i : nullptr,
                                    parent, slot);
+        pending[q] = 0;
+        done++;
     }
+    if (left) atomicAdd(leftover, left);
 }
 
 // ------------------------------------------------------------------------------------------------ mark + wavefront

@@ -34,12 +34,15 @@ cudaError_t launch_dt_collapse_round(const DTrieDev &t, const uint32_t *list, co
     dt_round_end_kernel<<<blocks, 128, 0, st>>>(t, list, count_p);
     return cudaGetLastError();
 }
+// one insertion round: attach points of the (remaining) insert entries, then at most max_per_run keys per run
 cudaError_t launch_dt_insert(const DTrieDev &t, const uint32_t *trie_of_key, const uint8_t *keys, const uint8_t *vals,
                              const uint8_t *sroots, const uint32_t *ins_idx, const uint32_t *n_ins_p, uint64_t max_ins,
-                             uint64_t *attach, uint32_t *leaf_of, cudaStream_t st) {
+                             uint64_t *attach, uint32_t *leaf_of, uint32_t max_per_run, uint8_t *pending, uint32_t *leftover,
+                             cudaStream_t st) {
     unsigned blocks = blocks_for(max_ins, 128);
     dt_insert_locate_kernel<<<blocks, 128, 0, st>>>(t, trie_of_key, keys, ins_idx, n_ins_p, attach);
-    dt_insert_runs_kernel<<<blocks, 128, 0, st>>>(t, trie_of_key, keys, vals, sroots, ins_idx, n_ins_p, attach, leaf_of);
+    dt_insert_runs_kernel<<<blocks, 128, 0, st>>>(t, trie_of_key, keys, vals, sroots, ins_idx, n_ins_p, attach, leaf_of, max_per_run,
+                                                  pending, leftover);
     return cudaGetLastError();
 }
 // mark -> starts -> wavefront -> finish (empty-trie root, recycling of this apply's freed nodes)

@@ -196,7 +196,8 @@ cudaError_t launch_dt_collapse_round(const DTrieDev &t, const uint32_t *list, co
                                      uint8_t *defer, uint32_t *next, uint32_t *next_count, cudaStream_t st);
 cudaError_t launch_dt_insert(const DTrieDev &t, const uint32_t *trie_of_key, const uint8_t *keys, const uint8_t *vals,
                              const uint8_t *sroots, const uint32_t *ins_idx, const uint32_t *n_ins_p, uint64_t max_ins,
-                             uint64_t *attach, uint32_t *leaf_of, cudaStream_t st);
+                             uint64_t *attach, uint32_t *leaf_of, uint32_t max_per_run, uint8_t *pending, uint32_t *leftover,
+                             cudaStream_t st);
 cudaError_t launch_dt_rehash(const DTrieDev &t, uint32_t max_seeds, uint32_t *handoff, uint32_t *handoff_count, int split_depth,
                              cudaStream_t st);
 cudaError_t launch_dt_finish(const DTrieDev &t, uint32_t max_freed, cudaStream_t st);

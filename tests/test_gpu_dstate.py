@@ -412,3 +412,16 @@ def test_device_resident_seed(eng, sharded):
         assert eng.root_from_frontier(ds.frontier()) == root
     assert ds.root() == root and ds.accounts() == len(state)
     ds.close()
+
+
+def test_new_contract_with_many_slots_in_one_block(eng):
+    """A whole storage trie appears in one block: every slot attaches at the new trie's root word, i.e. one long insert
+    run — handled in rounds (8 keys per run and round), not serially."""
+    rng = np.random.default_rng(77)
+    h = Harness(eng, random_state(rng, 100, with_storage=0.2))
+    big = {rkey(rng): int(rng.integers(1, 2**60)) for _ in range(5000)}
+    h.commit({rkey(rng): (EXISTS, acct(1, 1), big)})
+    k = next(a for a, (_, s) in h.state.items() if len(s) == 5000)
+    h.commit({k: (EXISTS | UNCHANGED, acct(0), {s: 0 for s in sorted(big)[::2]})})          # half of it deleted again
+    h.commit({k: (EXISTS | UNCHANGED, acct(0), {rkey(rng): 5 for _ in range(2000)})})       # and 2000 more
+    h.ds.close()
