@@ -6,6 +6,11 @@ out of scope; what is mirrored is each stage's full-pass data tr
   StorageHashingStage : PlainStorageState[address][slot]     -> HashedStorages[keccak(addr)][keccak(slot)] (sorted)
   MerkleStage         : HashedAccounts + HashedStorages      -> state root (+ AccountsTrie/StoragesTrie updates),
                         validated against the header's state root (merkle.rs:437-453)
+
+and the incremental leg the pipeline takes for short block ranges (merkle.rs:255-300 with the incremental hashing of
+crates/storage/provider/src/providers/database/provider.rs:3206-3221,3266-3280): the changed plain accounts / slots of the
+range are hashed in one device batch, folded into the hashed tables and committed to a state kept resident on the device
+(`DynamicStateRoot`); the returned TrieUpdates are applied to the trie tables the way write_trie_updates does.
 """
 from __future__ import annotations
 
@@ -15,8 +20,8 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from .engine import Engine
-from .hashed_state import Account, HashedPostStateSorted, HashedStorageSorted
-from .trie import StateRoot, TrieUpdates
+from .hashed_state import Account, HashedPostState, HashedPostStateSorted, HashedStorage, HashedStorageSorted, KeccakKeyHasher
+from .trie import DynamicStateRoot, StateRoot, StorageTrieUpdates, TrieUpdates
 
 
 class StageError(RuntimeError):
@@ -88,8 +93,10 @@ class MerkleStage:
 
     def __init__(self, engine: Engine):
         self.engine = engine
+        self.resident: Optional[DynamicStateRoot] = None   # seeded by the first incremental execution
 
     def execute(self, t: Tables, expected_state_root: Optional[bytes] = None) -> bytes:
+        self.close()  # a rebuild invalidates the resident state
         state = HashedPostStateSorted(list(t.hashed_accounts),
                                       {k: HashedStorageSorted(list(v)) for k, v in t.hashed_storages.items()})
         root, updates = StateRoot(self.engine, state).root_with_updates()
@@ -98,3 +105,89 @@ class MerkleStage:
             raise StageError(f"state root mismatch: got {root.hex()}, expected {expected_state_root.hex()}")
         t.trie_updates = updates
         return root
+
+    # ------------------------------------------------------------------ incremental leg
+    def execute_incremental(self, t: Tables, changed_accounts: Dict[bytes, Optional[Account]],
+                            changed_storage: Dict[bytes, Dict[int, int]], wiped: Optional[set] = None,
+                            expected_state_root: Optional[bytes] = None) -> bytes:
+        """changed_accounts: plain address -> new Account (None = destroyed); changed_storage: plain address -> {slot:
+        new value (0 = cleared)}; wiped: addresses whose storage is wiped before the changes apply.  Updates the plain and
+        hashed tables, commits to the resident state and applies the TrieUpdates to `t.trie_updates`."""
+        wiped = wiped or set()
+        if t.trie_updates is None:
+            raise StageError("no trie tables: run the rebuild (execute) once before incremental executions")
+        if self.resident is None:  # seed the device state from the hashed tables as they stand BEFORE this range
+            seed = HashedPostStateSorted(list(t.hashed_accounts),
+                                         {k: HashedStorageSorted(list(v)) for k, v in t.hashed_storages.items()})
+            self.resident = DynamicStateRoot(self.engine, seed)
+        # 1. incremental hashing: every changed address and slot in one device batch each
+        hasher = KeccakKeyHasher(self.engine)
+        addrs = sorted(set(changed_accounts) | set(changed_storage) | set(wiped))
+        ha = dict(zip(addrs, hasher.hash_keys(addrs)))
+        slot_list = sorted({int(s) for st in changed_storage.values() for s in st})
+        hs = dict(zip(slot_list, hasher.hash_keys([s.to_bytes(32, "big") for s in slot_list])))
+        post = HashedPostState()
+        for a, acc in changed_accounts.items():
+            post.accounts[ha[a]] = acc
+        for a in set(changed_storage) | set(wiped):
+            post.storages[ha[a]] = HashedStorage(a in wiped, {hs[int(s)]: int(v) for s, v in changed_storage.get(a, {}).items()})
+        # 2. plain + hashed tables
+        hashed_accounts = dict(t.hashed_accounts)
+        for a, acc in changed_accounts.items():
+            if acc is None:
+                t.plain_accounts.pop(a, None)
+                t.plain_storage.pop(a, None)
+                hashed_accounts.pop(ha[a], None)
+                t.hashed_storages.pop(ha[a], None)
+            else:
+                t.plain_accounts[a] = acc
+                hashed_accounts[ha[a]] = acc
+        for a in set(changed_storage) | set(wiped):
+            if changed_accounts.get(a, 0) is None:
+                continue
+            plain = {} if a in wiped else dict(t.plain_storage.get(a, {}))
+            hashed = {} if a in wiped else dict(t.hashed_storages.get(ha[a], []))
+            for s, v in changed_storage.get(a, {}).items():
+                if v == 0:
+                    plain.pop(int(s), None)
+                    hashed.pop(hs[int(s)], None)
+                else:
+                    plain[int(s)] = int(v)
+                    hashed[hs[int(s)]] = int(v)
+            t.plain_storage[a] = plain
+            if hashed:
+                t.hashed_storages[ha[a]] = sorted(hashed.items())
+            else:
+                t.hashed_storages.pop(ha[a], None)
+        t.hashed_accounts = sorted(hashed_accounts.items())
+        # 3. commit on the device, validate, write the trie tables
+        root, upd = self.resident.commit(post)
+        if expected_state_root is not None and root != expected_state_root:
+            raise StageError(f"state root mismatch: got {root.hex()}, expected {expected_state_root.hex()}")
+        self.write_trie_updates(t.trie_updates, upd)
+        return root
+
+    @staticmethod
+    def write_trie_updates(tables: TrieUpdates, upd: TrieUpdates):
+        """write_trie_updates_sorted (crates/storage/provider/src/providers/database/provider.rs:3125-3160,
+        crates/trie/db/src/trie_cursor.rs:280-312): removed paths deleted, updated nodes upserted; a deleted storage trie
+        loses all its rows first."""
+        for p in upd.removed_nodes:
+            tables.account_nodes.pop(p, None)
+        tables.account_nodes.update(upd.account_nodes)
+        for addr, st in upd.storage_tries.items():
+            cur = tables.storage_tries.get(addr)
+            if st.is_deleted or cur is None:
+                cur = StorageTrieUpdates()
+            for p in st.removed_nodes:
+                cur.storage_nodes.pop(p, None)
+            cur.storage_nodes.update(st.storage_nodes)
+            if cur.storage_nodes:
+                tables.storage_tries[addr] = cur
+            else:
+                tables.storage_tries.pop(addr, None)
+
+    def close(self):
+        if self.resident is not None:
+            self.resident.close()
+            self.resident = None

@@ -425,3 +425,63 @@ def test_new_contract_with_many_slots_in_one_block(eng):
     h.commit({k: (EXISTS | UNCHANGED, acct(0), {s: 0 for s in sorted(big)[::2]})})          # half of it deleted again
     h.commit({k: (EXISTS | UNCHANGED, acct(0), {rkey(rng): 5 for _ in range(2000)})})       # and 2000 more
     h.ds.close()
+
+
+def test_merkle_stage_incremental_equals_rebuild(eng):
+    """The three stages end to end: a full pass (AccountHashing, StorageHashing, MerkleStage rebuild), then ranges of
+    changes through MerkleStage.execute_incremental (incremental hashing + the resident state).  After every range the
+    root and the trie tables equal what a rebuild over the updated plain state produces
+    (crates/stages/stages/src/stages/merkle.rs:520-618 execute_small_merkle / execute_chunked_merkle)."""
+    from reth_b200 import Account, AccountHashingStage, MerkleStage, StorageHashingStage
+    from reth_b200.stages import Tables
+    rng = np.random.default_rng(88)
+    ra = lambda: bytes(rng.integers(0, 256, 20, dtype=np.uint8))
+    t = Tables()
+    for _ in range(400):
+        a = ra()
+        t.plain_accounts[a] = Account(int(rng.integers(0, 9)), int(rng.integers(1, 2**60)))
+        if rng.random() < 0.3:
+            t.plain_storage[a] = {int(rng.integers(0, 2**63)): int(rng.integers(1, 2**60)) for _ in range(int(rng.integers(1, 25)))}
+    AccountHashingStage(eng).execute(t)
+    StorageHashingStage(eng).execute(t)
+    stage = MerkleStage(eng)
+    stage.execute(t)
+
+    def rebuild(plain_accounts, plain_storage):
+        r = Tables(plain_accounts=dict(plain_accounts), plain_storage={a: dict(s) for a, s in plain_storage.items()})
+        AccountHashingStage(eng).execute(r)
+        StorageHashingStage(eng).execute(r)
+        root = MerkleStage(eng).execute(r)
+        return root, r
+
+    for rng_no in range(4):
+        live = sorted(t.plain_accounts)
+        changed_accounts, changed_storage, wiped = {}, {}, set()
+        for i in rng.choice(len(live), 25, replace=False):
+            acc = t.plain_accounts[live[i]]
+            changed_accounts[live[i]] = Account(acc.nonce + 1, acc.balance + 3, acc.bytecode_hash)
+        for _ in range(6):
+            a = ra()
+            changed_accounts[a] = Account(0, 5)
+            changed_storage[a] = {int(rng.integers(0, 2**63)): 9 for _ in range(4)}
+        for i in rng.choice(len(live), 3, replace=False):
+            changed_accounts[live[i]] = None
+            changed_storage.pop(live[i], None)
+        with_storage = [a for a in t.plain_storage if t.plain_storage[a] and changed_accounts.get(a, 0) is not None]
+        for a in with_storage[:5]:
+            slots = sorted(t.plain_storage[a])
+            changed_storage[a] = {slots[0]: 0, int(rng.integers(0, 2**63)): int(rng.integers(1, 2**40))}
+        if rng_no == 2 and with_storage:
+            wiped.add(with_storage[-1])
+            changed_storage[with_storage[-1]] = {7: 7}
+        root = stage.execute_incremental(t, changed_accounts, changed_storage, wiped)
+        o_root, r = rebuild(t.plain_accounts, t.plain_storage)
+        assert root == o_root
+        assert t.hashed_accounts == r.hashed_accounts and t.hashed_storages == r.hashed_storages
+        assert t.trie_updates.account_nodes == r.trie_updates.account_nodes
+        mine = {k: v.storage_nodes for k, v in t.trie_updates.storage_tries.items() if v.storage_nodes}
+        theirs = {k: v.storage_nodes for k, v in r.trie_updates.storage_tries.items() if v.storage_nodes}
+        assert mine == theirs
+    with pytest.raises(Exception):
+        stage.execute_incremental(t, {ra(): Account(1, 1)}, {}, expected_state_root=b"\\x00" * 32)
+    stage.close()
