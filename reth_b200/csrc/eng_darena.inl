@@ -193,12 +193,11 @@ static int32_t da_from_build(DArena *a, b200_trie *src, uint64_t min_tries) {
 // Structural part of an apply: classify the m dirty entries, write value updates, detach deleted leaves, collapse, insert.
 // Leaves the seeds in the arena; leaf_of[i] afterwards holds the leaf of every entry that exists (updated, touched or
 // inserted), DT_NONE otherwise.  Every pointer is a device pointer.
-static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const uint8_t *d_keys, const uint8_t *d_vals,
-                              const uint8_t *d_flags, const uint8_t *d_sroots, uint64_t m) {
-    b200_ctx *c = a->c;
-    cudaStream_t st = c->stream;
+// Every allocation one block of m entries can need (capacity for m inserts, all scratch): called for ALL arenas of a
+// block before the first kernel mutates anything, so that running out of memory cannot leave a state half-applied.
+static int32_t da_prepare(DArena *a, uint64_t m, uint64_t tries) {
     // every insert may take one leaf slot and one node slot from the bump region
-    TRY(da_reserve(a, (uint64_t)a->leaf_alloc + m, (uint64_t)a->node_alloc + m, a->tcap));
+    TRY(da_reserve(a, (uint64_t)a->leaf_alloc + m, (uint64_t)a->node_alloc + m, std::max<uint64_t>(tries, a->tcap)));
     const uint32_t max_list = (uint32_t)m + 16, max_seeds = (uint32_t)(6 * m + 64);
     const uint32_t max_built = (uint32_t)(std::min<uint64_t>((uint64_t)max_seeds * 64, (uint64_t)a->node_alloc + m) + 16);
     TRY(da_scratch(a, a->kind, m));
@@ -212,6 +211,16 @@ static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const ui
     TRY(da_scratch(a, a->removed, ((size_t)max_built + max_list) * 4));
     TRY(da_scratch(a, a->freed_now, (size_t)max_list * 4));
     TRY(da_scratch(a, a->flags, max_list));  // per-entry defer flags of a collapse round (re-used for the output flags)
+    TRY(da_scratch(a, a->nh, m + 16));       // per-entry "still to insert" flags of an insert round
+    TRY(da_scratch(a, a->sel, ((size_t)max_seeds + 1) * 4));  // second insert list / hand-over list of the two-stage re-hash
+    return B200_OK;
+}
+
+static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const uint8_t *d_keys, const uint8_t *d_vals,
+                              const uint8_t *d_flags, const uint8_t *d_sroots, uint64_t m) {
+    b200_ctx *c = a->c;
+    cudaStream_t st = c->stream;
+    const uint32_t max_list = (uint32_t)m + 16;
     DTrieDev d = da_view(a);
     uint8_t *kind = static_cast<uint8_t *>(a->kind.p);
     uint32_t *leaf_of = static_cast<uint32_t *>(a->leaf_of.p);

@@ -212,15 +212,26 @@ extern "C" B200_API int32_t b200_dstate_apply(b200_dstate *t, const uint8_t *acc
     std::vector<uint8_t> h_kind;
     std::vector<uint32_t> h_leaf;
     if (m) {
+        // all memory first: nothing below may fail for lack of it once the first arena has been touched
+        TRY(da_prepare(A, m, 1));
+        TRY(da_prepare(S, n_entries, A->lcap));
+        TRY(da_resize(A, t->wipe_cnt, 16, 0, 0));
+        TRY(da_scratch(A, t->wipe_a, std::max<size_t>((size_t)m, (size_t)S->node_alloc) * 4 + 16));
+        TRY(da_scratch(A, t->wipe_b, std::max<size_t>((size_t)m, (size_t)S->node_alloc) * 4 + 16));
+        TRY(da_scratch(A, t->trie_of_key, std::max<size_t>((size_t)m, (size_t)n_entries) * 4 + 16));
+        if (t->sharded) TRY(da_scratch(A, t->acct_tries, m * 4));
         TRY(h2d_into(A, t->in_akeys, acct_keys32, m * 32));
         TRY(h2d_into(A, t->in_accts, accts, m * 72));
         if (acct_flags) TRY(h2d_into(A, t->in_aflags, acct_flags, m));
         TRY(h2d_into(A, t->in_offs, seg_offsets, (m + 1) * 8));
+        if (n_entries) {
+            TRY(h2d_into(S, t->in_skeys, slot_keys32, n_entries * 32));
+            TRY(h2d_into(S, t->in_svals, values32_be, n_entries * 32));
+        }
         const uint8_t *d_flags = acct_flags ? static_cast<const uint8_t *>(t->in_aflags.p) : nullptr;
         // ---- accounts: structure only (their leaves are re-hashed after the storage roots are known)
         const uint32_t *d_acct_tries = nullptr;
         if (t->sharded) {  // bucket trie of every account entry = its top key nibble
-            TRY(da_scratch(A, t->acct_tries, m * 4));
             CU(launch_dt_nibble_tries(static_cast<const uint8_t *>(t->in_akeys.p), m, static_cast<uint32_t *>(t->acct_tries.p), st));
             c->launches++;
             d_acct_tries = static_cast<const uint32_t *>(t->acct_tries.p);
@@ -230,15 +241,10 @@ extern "C" B200_API int32_t b200_dstate_apply(b200_dstate *t, const uint8_t *acc
         const uint8_t *a_kind = static_cast<const uint8_t *>(A->kind.p);
         const uint32_t *a_leaf = static_cast<const uint32_t *>(A->leaf_of.p);
         // ---- storage tries of destroyed / wiped accounts
-        TRY(da_reserve(S, S->leaf_alloc, S->node_alloc, A->lcap));
         S->top_out = static_cast<uint8_t *>(A->lsroot.p);  // the account arena may have been re-allocated
         S->top_stride = 32;
-        TRY(da_resize(A, t->wipe_cnt, 16, 0, 0));
         uint32_t *wc = static_cast<uint32_t *>(t->wipe_cnt.p);  // [0] tries to wipe, [1] / [2] BFS list lengths
         CU(cudaMemsetAsync(wc, 0, 16, st));
-        TRY(da_scratch(A, t->wipe_a, std::max<size_t>((size_t)m, (size_t)S->node_alloc) * 4 + 16));
-        TRY(da_scratch(A, t->wipe_b, std::max<size_t>((size_t)m, (size_t)S->node_alloc) * 4 + 16));
-        TRY(da_scratch(A, t->trie_of_key, std::max<size_t>((size_t)m, (size_t)n_entries) * 4 + 16));
         uint32_t *wipe_tries = static_cast<uint32_t *>(t->trie_of_key.p);  // borrowed until the storage entries are expanded
         CU(launch_dt_wipe_list(a_kind, d_flags, a_leaf, m, wipe_tries, wc, st));
         c->launches++;
@@ -262,8 +268,6 @@ extern "C" B200_API int32_t b200_dstate_apply(b200_dstate *t, const uint8_t *acc
         }
         // ---- storage slots of the surviving accounts
         if (n_entries) {
-            TRY(h2d_into(S, t->in_skeys, slot_keys32, n_entries * 32));
-            TRY(h2d_into(S, t->in_svals, values32_be, n_entries * 32));
             uint32_t *trie_of_key = static_cast<uint32_t *>(t->trie_of_key.p);
             CU(launch_dt_expand_tries(static_cast<const uint64_t *>(t->in_offs.p), m, a_kind, a_leaf, n_entries, trie_of_key, st));
             c->launches++;

@@ -116,6 +116,7 @@ extern "C" B200_API int32_t b200_dtrie_apply(b200_dtrie *t, const uint8_t *keys3
     TRY(reset_build_state(c));
     a->n_built = a->n_removed = 0;
     if (m) {
+        TRY(da_prepare(a, m, 1));
         TRY(h2d_into(a, t->in_keys, keys32, m * 32));
         TRY(h2d_into(a, t->in_accts, accts, m * 72));
         if (present) TRY(h2d_into(a, t->in_present, present, m));
