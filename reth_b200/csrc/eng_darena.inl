@@ -220,7 +220,7 @@ static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const ui
                               const uint8_t *d_flags, const uint8_t *d_sroots, uint64_t m) {
     b200_ctx *c = a->c;
     cudaStream_t st = c->stream;
-    const uint32_t max_list = (uint32_t)m + 16;
+    TRY(da_prepare(a, m, a->tcap));  // no-op when the caller prepared already
     DTrieDev d = da_view(a);
     uint8_t *kind = static_cast<uint8_t *>(a->kind.p);
     uint32_t *leaf_of = static_cast<uint32_t *>(a->leaf_of.p);
