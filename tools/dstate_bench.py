@@ -18,7 +18,6 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 
 
 def main():
@@ -30,12 +29,28 @@ def main():
     ap.add_argument("--blocks", type=int, default=12)
     ap.add_argument("--check", action="store_true")
     args = ap.parse_args()
-    from reth_b200 import ACCOUNT_DTYPE, DynamicState, Engine
-    from tests.util import synth_accounts, synth_storage
+    from reth_b200 import ACCOUNT_DTYPE, KECCAK_EMPTY, DynamicState, Engine
     eng = Engine(0)
     n = args.accounts
-    keys, accs = synth_accounts(3, n)
-    skeys, svals, offs = synth_storage(3, np.full(n, args.slots), "u64")
+    g = np.random.default_rng(3)
+
+    def sorted_keys(count, groups=None):
+        k = g.integers(0, 256, (count, 32), dtype=np.uint8)
+        cols = tuple(k[:, i] for i in range(31, -1, -1))
+        order = np.lexsort(cols if groups is None else cols + (groups,))
+        return k[order]
+
+    keys = sorted_keys(n)
+    accs = np.zeros(n, ACCOUNT_DTYPE)
+    accs["nonce"] = g.integers(0, 1 << 16, n)
+    accs["balance"][:, 24:] = g.integers(0, 256, (n, 8), dtype=np.uint8)
+    accs["code_hash"] = np.frombuffer(KECCAK_EMPTY, np.uint8)
+    total = n * args.slots
+    skeys = sorted_keys(total, np.repeat(np.arange(n), args.slots))
+    svals = np.zeros((total, 32), np.uint8)
+    svals[:, 24:] = g.integers(0, 256, (total, 8), dtype=np.uint8)
+    svals[:, 31] |= 1
+    offs = (np.arange(n + 1, dtype=np.uint64) * np.uint64(args.slots))
     t0 = time.perf_counter()
     ds = DynamicState.create(eng, keys, accs, skeys, svals, offs)
     build_s = time.perf_counter() - t0
