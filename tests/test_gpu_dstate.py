@@ -485,3 +485,34 @@ def test_merkle_stage_incremental_equals_rebuild(eng):
     with pytest.raises(Exception):
         stage.execute_incremental(t, {ra(): Account(1, 1)}, {}, expected_state_root=b"\\x00" * 32)
     stage.close()
+
+
+def test_block_updates_as_table_rows(eng):
+    """The block's storage records (trie_id = account entry index) feed b200_storage_trie_rows with the block's own account
+    keys: rows come out in StoragesTrie key order (address, then sub-key), ready for the cursor upsert loop."""
+    from reth_b200 import tables
+    rng = np.random.default_rng(91)
+    h = Harness(eng, random_state(rng, 300, with_storage=0.6, max_slots=80))
+    block = random_block(rng, h.state, 80, 1)
+    ks = sorted(block)
+    keys = np.frombuffer(b"".join(ks), np.uint8).reshape(-1, 32)
+    accs = np.zeros(len(ks), oracle.ACCOUNT_DTYPE)
+    flags = np.zeros(len(ks), np.uint8)
+    sk, sv, offs = [], [], [0]
+    for i, k in enumerate(ks):
+        flags[i], accs[i] = block[k][0], block[k][1]
+        for s in sorted(block[k][2]):
+            sk.append(s)
+            sv.append(int(block[k][2][s]).to_bytes(32, "big"))
+        offs.append(len(sk))
+    skeys = np.frombuffer(b"".join(sk), np.uint8).reshape(-1, 32) if sk else np.zeros((0, 32), np.uint8)
+    svals = np.frombuffer(b"".join(sv), np.uint8).reshape(-1, 32) if sv else np.zeros((0, 32), np.uint8)
+    _, au, _, su, _, _ = h.ds.apply(keys, accs, flags, skeys, svals, np.array(offs, np.uint64), want_updates=True)
+    arows = tables.account_trie_rows(au, tables.KEYS_PACKED)
+    assert [k for k, _ in arows] == sorted(k for k, _ in arows) and len(arows) == len(au)
+    srows = tables.storage_trie_rows(su, keys, tables.KEYS_PACKED)
+    assert len(srows) == len(su)
+    order = [(k, v[:33]) for k, v in srows]
+    assert order == sorted(order)
+    assert {k for k, _ in srows} <= set(ks)
+    h.ds.close()
