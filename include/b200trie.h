@@ -364,6 +364,8 @@ typedef struct {
     uint64_t n_nodes;
     uint64_t *rlp_offset;  /* [n_nodes+1] */
     uint8_t *rlp;
+    uint8_t *node_depth;   /* [n_nodes] nibbles of the target key that lead to the node: its path in a ProofNodes /
+                              MultiProof map (crates/trie/common/src/proofs.rs) is target[..node_depth] */
     void *_owner;
 } b200_proofs;
 B200_API int32_t b200_dstate_account_proofs(b200_dstate *, const uint8_t *acct_keys32, uint64_t n, b200_proofs *out);

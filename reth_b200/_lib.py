@@ -56,6 +56,7 @@ class Proofs(C.Structure):
         ("n_nodes", C.c_uint64),
         ("rlp_offset", C.POINTER(C.c_uint64)),
         ("rlp", C.POINTER(C.c_uint8)),
+        ("node_depth", C.POINTER(C.c_uint8)),
         ("_owner", C.c_void_p),
     ]
 

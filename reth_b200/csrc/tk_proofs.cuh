@@ -88,19 +88,23 @@ static __device__ void dt_write_branch_rlp(const DTrieDev &t, uint32_t v, uint32
 // rlp + byte_base and their start offsets at rlp_offset[node_base ..].
 template <bool WRITE>
 static __device__ void dt_proof_walk(const DTrieDev &t, uint32_t trie, const uint8_t *key, uint32_t &n_nodes, uint64_t &n_bytes,
-                                     uint8_t *rlp, uint64_t byte_base, uint64_t *rlp_offset, uint64_t node_base) {
+                                     uint8_t *rlp, uint64_t byte_base, uint64_t *rlp_offset, uint8_t *node_depth, uint64_t node_base) {
     n_nodes = 0;
     n_bytes = 0;
     uint32_t cur = t.troot[trie];
     int pd = -1;
-    auto begin_node = [&](uint32_t len) {
-        if (WRITE) rlp_offset[node_base + n_nodes] = byte_base + n_bytes;
+    // depth = number of key nibbles that lead to the node: its path in a ProofNodes / MultiProof map is key[..depth]
+    auto begin_node = [&](uint32_t len, int depth) {
+        if (WRITE) {
+            rlp_offset[node_base + n_nodes] = byte_base + n_bytes;
+            node_depth[node_base + n_nodes] = (uint8_t)depth;
+        }
         n_nodes++;
         n_bytes += len;
     };
     if (cur == DT_NONE) {  // empty trie: the proof is the empty string (EMPTY_STRING_CODE), proof.rs:121-126
         if (WRITE) rlp[byte_base] = 0x80;
-        begin_node(1);
+        begin_node(1, 0);
         return;
     }
     for (int hops = 0; hops <= DT_MAX_HOPS; hops++) {
@@ -117,7 +121,7 @@ static __device__ void dt_proof_walk(const DTrieDev &t, uint32_t trie, const uin
                 if (t.account) encode_leaf<LinBuf, true>(lb, k, pd, val, sr, t.err);
                 else encode_leaf<LinBuf, false>(lb, k, pd, val, nullptr, t.err);
             }
-            begin_node(len);
+            begin_node(len, pd + 1);
             return;
         }
         const uint32_t v = cur;
@@ -146,12 +150,12 @@ static __device__ void dt_proof_walk(const DTrieDev &t, uint32_t trie, const uin
                 LinBuf lb{ext_at, 0};
                 encode_extension(lb, nk, (uint32_t)(pd + 1), (uint32_t)d, child, blen >= 32 ? 0u : blen);
             }
-            begin_node(elen);
+            begin_node(elen, pd + 1);
             if (!matches) return;
-            begin_node(blen);
+            begin_node(blen, d);
         } else {
             if (WRITE) dt_write_branch_rlp(t, v, payload, rlp + byte_base + n_bytes);
-            begin_node(blen);
+            begin_node(blen, d);
         }
         pd = d;
         cur = t.nchild[16 * (uint64_t)v + dt_nib(key, (uint32_t)d)];
@@ -172,14 +176,14 @@ __global__ void dt_proof_size_kernel(DTrieDev t, const uint32_t *__restrict__ tr
         nn = 1;
         nb = 1;
     } else {
-        dt_proof_walk<false>(t, trie, keys + 32 * i, nn, nb, nullptr, 0, nullptr, 0);
+        dt_proof_walk<false>(t, trie, keys + 32 * i, nn, nb, nullptr, 0, nullptr, nullptr, 0);
     }
     node_count[i] = nn;
     byte_count[i] = nb;
 }
 __global__ void dt_proof_write_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_target, const uint8_t *__restrict__ keys,
                                       uint64_t n, const uint64_t *__restrict__ node_base, const uint64_t *__restrict__ byte_base,
-                                      uint8_t *__restrict__ rlp, uint64_t *__restrict__ rlp_offset) {
+                                      uint8_t *__restrict__ rlp, uint64_t *__restrict__ rlp_offset, uint8_t *__restrict__ node_depth) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t trie = trie_of_target ? trie_of_target[i] : 0;
@@ -188,8 +192,9 @@ __global__ void dt_proof_write_kernel(DTrieDev t, const uint32_t *__restrict__ t
     if (trie == DT_NONE) {
         rlp[byte_base[i]] = 0x80;
         rlp_offset[node_base[i]] = byte_base[i];
+        node_depth[node_base[i]] = 0;
     } else {
-        dt_proof_walk<true>(t, trie, keys + 32 * i, nn, nb, rlp, byte_base[i], rlp_offset, node_base[i]);
+        dt_proof_walk<true>(t, trie, keys + 32 * i, nn, nb, rlp, byte_base[i], rlp_offset, node_depth, node_base[i]);
     }
 }
 // the account leaf (= storage trie id) of one account key, DT_NONE when the account does not exist

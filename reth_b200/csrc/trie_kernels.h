@@ -223,7 +223,7 @@ cudaError_t launch_dt_proof_sizes(const DTrieDev &t, const uint32_t *trie_of_tar
                                   uint32_t *node_count, uint64_t *byte_count, cudaStream_t st);
 cudaError_t launch_dt_proof_write(const DTrieDev &t, const uint32_t *trie_of_target, const uint8_t *keys, uint64_t n,
                                   const uint64_t *node_base, const uint64_t *byte_base, uint8_t *rlp, uint64_t *rlp_offset,
-                                  cudaStream_t st);
+                                  uint8_t *node_depth, cudaStream_t st);
 cudaError_t launch_dt_find_leaf(const DTrieDev &t, const uint8_t *key, uint32_t *out, uint64_t n_copies, cudaStream_t st);
 
 }  // namespace b200

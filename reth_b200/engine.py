@@ -529,17 +529,35 @@ class DynamicState:
         return (self._root, updates_to_records(au, lib), [r[1] for r in updates_to_records(ar, lib)],
                 updates_to_records(su, lib), [(r[0], r[1]) for r in updates_to_records(sr, lib)], deleted[:m].copy())
 
-    def _take_proofs(self, p: Proofs) -> list:
+    def _take_proofs(self, p: Proofs, with_depths: bool = False) -> list:
         n, nn = int(p.n_targets), int(p.n_nodes)
         res = []
         if n:
             no = np.ctypeslib.as_array(p.node_offset, (n + 1,))
             ro = np.ctypeslib.as_array(p.rlp_offset, (nn + 1,))
+            nd = np.ctypeslib.as_array(p.node_depth, (max(nn, 1),))
             blob = np.ctypeslib.as_array(p.rlp, (max(int(ro[nn]), 1),)).tobytes()
             for t in range(n):
-                res.append([blob[int(ro[k]):int(ro[k + 1])] for k in range(int(no[t]), int(no[t + 1]))])
+                rng_ = range(int(no[t]), int(no[t + 1]))
+                if with_depths:
+                    res.append([(int(nd[k]), blob[int(ro[k]):int(ro[k + 1])]) for k in rng_])
+                else:
+                    res.append([blob[int(ro[k]):int(ro[k + 1])] for k in rng_])
         self.engine.lib.b200_proofs_release(C.byref(p))
         return res
+
+    def account_multiproof(self, acct_keys) -> dict:
+        """MultiProof::account_subtree (crates/trie/common/src/proofs.rs): {node path (nibbles) -> RLP} over all targets,
+        every node once."""
+        acct_keys = _np(acct_keys).reshape(-1, 32)
+        p = Proofs()
+        self.engine._check(self.engine.lib.b200_dstate_account_proofs(self.handle, _ptr(acct_keys), len(acct_keys), C.byref(p)))
+        out = {}
+        for key, nodes in zip(acct_keys, self._take_proofs(p, with_depths=True)):
+            nib = bytes(x for b in key.tobytes() for x in (b >> 4, b & 15))
+            for depth, rlp in nodes:
+                out[nib[:depth]] = rlp
+        return out
 
     def account_proofs(self, acct_keys) -> list:
         """-> for every target hashed address the list of node RLPs from the root down (Proof::account_proof)."""

@@ -233,3 +233,19 @@ def test_proofs_follow_the_state_through_blocks(eng):
             else:
                 verify(root, k, proof, None)
     h.ds.close()
+
+
+def test_account_multiproof_is_the_union_of_the_proofs(eng, golden_allocs):
+    """MultiProof::account_subtree: path -> node over all targets.  On the testspec state the four targets of proof.rs give
+    exactly the eight distinct nodes of the trie, keyed by their positions (root extension at the empty path, ...)."""
+    ds, keys = state_from_alloc(eng, golden_allocs["testspec"]["alloc"])
+    hashed = np.frombuffer(b"".join(oracle.keccak256(H(a)) for a in TESTSPEC), np.uint8).reshape(-1, 32)
+    mp = ds.account_multiproof(hashed)
+    all_nodes = {n for proof in TESTSPEC.values() for n in proof}
+    assert {v.hex() for v in mp.values()} == all_nodes and len(mp) == len(all_nodes) == 8
+    assert mp[b""].hex() == TESTSPEC["2031f89b3ea8014eb51a78c316e42af3e0d7695f"][0]          # the root extension node
+    for path, rlp in mp.items():                                                               # every path is a prefix of a target
+        assert any(bytes(nibbles(k.tobytes()))[:len(path)] == path for k in hashed)
+    # the extension 'a7' (2 nibbles) puts the first branch at path [a, 7]
+    assert bytes([0xa, 0x7]) in mp and len(rlp_items(mp[bytes([0xa, 0x7])])) == 17
+    ds.close()
