@@ -80,7 +80,6 @@ __global__ void dt_wipe_list_kernel(const uint8_t *__restrict__ kind, const uint
 }
 static __device__ __forceinline__ void dt_wipe_leaf(const DTrieDev &t, uint32_t x) {
     t.lmeta[x] = DT_DEAD;
-    t.lseed[x] = 0;
     t.leaf_free[atomicAdd(&t.g[DG_LEAF_FREE], 1u)] = x;
     atomicSub(&t.g[DG_NLEAVES], 1u);
 }

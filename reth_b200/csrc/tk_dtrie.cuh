@@ -98,9 +98,9 @@ static __device__ __forceinline__ uint32_t dt_pop(uint32_t *count, const uint32_
     return atomicAdd(bump, 1u);
 }
 static __device__ __forceinline__ uint32_t dt_alloc_leaf(const DTrieDev &t) {
-    uint32_t id = dt_pop(&t.g[DG_LEAF_FREE], t.leaf_free, &t.g[DG_LEAF_ALLOC]);
-    t.lseed[id] = 0;
-    return id;
+    // (the seed flag of a free slot is already clear: dt_starts_kernel clears every flag it listed, fresh capacity is
+    // zero-filled; no plain store here, other threads of this kernel update neighbouring flags with atomics)
+    return dt_pop(&t.g[DG_LEAF_FREE], t.leaf_free, &t.g[DG_LEAF_ALLOC]);
 }
 static __device__ __forceinline__ uint32_t dt_alloc_node(const DTrieDev &t, uint32_t trie, uint32_t depth, const uint8_t *key,
                                                         uint32_t parent) {
@@ -114,10 +114,7 @@ static __device__ __forceinline__ uint32_t dt_alloc_node(const DTrieDev &t, uint
     t.nmeta[v] = 0;
     t.nmasks[v] = make_ushort4(0, 0, 0, (unsigned short)depth);
     dt_copy32(t.nkey + 32 * (uint64_t)v, key);
-    t.npending[v] = 0;
-    t.nseed[v] = 0;
-    t.ncur[v] = 0;
-    t.nnext[v] = 0;
+    t.npending[v] = 0;  // (nseed / ncur / nnext of a free slot are clear already, see dt_alloc_leaf)
     return v;
 }
 // A stored node that ceases to exist (or to be stored) is one of reth's removed_nodes; its path is read from nkey /
@@ -294,7 +291,6 @@ __global__ void dt_update_detach_kernel(DTrieDev t, const uint8_t *__restrict__ 
             if (!dt_test_and_set(t.nnext, p)) touched[atomicAdd(&t.g[DG_LIST_A], 1u)] = p;
         }
         t.lmeta[x] = DT_DEAD;
-        t.lseed[x] = 0;
         t.leaf_free[atomicAdd(&t.g[DG_LEAF_FREE], 1u)] = x;
         atomicSub(&t.g[DG_NLEAVES], 1u);
     }
