@@ -294,6 +294,9 @@ def main():
                     "--c4-leaves leaves, 80%% EOAs, Zipf(1.2) storage sizes")
     ap.add_argument("--c4-leaves", type=int, default=31_250_000, help="leaves per GPU (250M over 8 GPUs)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--dynamic", action="store_true", help="also time the dynamic resident trie / state (tools/dtrie_bench.py, "
+                    "tools/dstate_bench.py) in subprocesses and attach their JSON under \"dynamic\" (off by default: those "
+                    "paths are emulation-validated only until their first B200 run)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -430,6 +433,10 @@ def main():
         if state_root is not None:
             state_root["cpu_baseline"] = cpu_state_root_baseline()
 
+    dynamic = None
+    if args.dynamic and rank == 0 and world == 1:
+        dynamic = bench_dynamic(args)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -442,6 +449,8 @@ def main():
             "cpu_baseline": cpu, "state_root": state_root, "mainnet_shape": c4, "incremental": incremental,
             "parity_spot_check": parity_ok,
         }
+        if dynamic is not None:
+            line["dynamic"] = dynamic
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -693,6 +702,27 @@ def bench_incremental(args, eng, dev):
     del keys, accts
     torch.cuda.empty_cache()
     return res
+
+
+def bench_dynamic(args):
+    """--dynamic: the emulation-validated dynamic trie / state, each in its own process (its own CUDA context and a
+    timeout), so that whatever happens there cannot touch the numbers above."""
+    import subprocess
+    root = os.path.dirname(os.path.abspath(__file__))
+    out = {}
+    runs = {
+        "dtrie_value_updates": ["tools/dtrie_bench.py", "--base", str(args.base_accounts), "--dirty", str(args.dirty), "--mix", "100,0,0"],
+        "dtrie_mixed_block": ["tools/dtrie_bench.py", "--base", str(args.base_accounts), "--dirty", str(args.dirty), "--mix", "80,10,10"],
+        "dstate_c3_shape": ["tools/dstate_bench.py", "--accounts", "1000000", "--slots", "16", "--touch", "2000", "--slot-writes", "10"],
+    }
+    for name, cmd in runs.items():
+        try:
+            r = subprocess.run([sys.executable] + cmd, cwd=root, capture_output=True, text=True, timeout=900)
+            last = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            out[name] = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return out
 
 
 def eng_account_dtype():

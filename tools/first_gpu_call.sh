@@ -16,6 +16,7 @@ export B200_DTRIE_ON_GPU=1
   echo "== compute-sanitizer on the smallest dynamic test (racecheck is the point: emulation cannot see races)"
   timeout 600 compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_dtrie.py -m gpu -q -x -k "n0-50 or 50-10-20" 2>&1 | tail -15
   timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_dstate.py -m gpu -q -x -k "3-6-5" 2>&1 | tail -15
+  echo "== (afterwards: python bench.py --dynamic adds these legs to the official JSON line)"
   echo "== dynamic trie latency vs merge+rebuild (C5 shape)"
   timeout 600 python tools/dtrie_bench.py --base 100000000 --dirty 10000 --mix 100,0,0 2>&1 | tail -2
   timeout 600 python tools/dtrie_bench.py --base 100000000 --dirty 10000 --mix 80,10,10 2>&1 | tail -2
