@@ -11,7 +11,7 @@ struct b200_dstate {
     DArena acc, sto;
     bool sharded = false;  // accounts as 16 top-nibble bucket tries: this state is one rank's shard
     DevBuf bucket_roots, frontier, acct_tries;
-    DevBuf root, in_akeys, in_accts, in_aflags, in_skeys, in_svals, in_offs, trie_of_key, wipe_a, wipe_b, wipe_cnt;
+    DevBuf root, in_akeys, in_accts, in_aflags, in_skeys, in_svals, in_offs, trie_of_key, wipe_cnt;
 };
 
 extern "C" B200_API void b200_dstate_destroy(b200_dstate *t) {
@@ -21,7 +21,7 @@ extern "C" B200_API void b200_dstate_destroy(b200_dstate *t) {
     da_free(&t->acc);
     da_free(&t->sto);
     DevBuf *bufs[] = {&t->root, &t->in_akeys, &t->in_accts, &t->in_aflags, &t->in_skeys, &t->in_svals, &t->in_offs,
-                      &t->trie_of_key, &t->wipe_a, &t->wipe_b, &t->wipe_cnt, &t->bucket_roots, &t->frontier, &t->acct_tries};
+                      &t->trie_of_key, &t->wipe_cnt, &t->bucket_roots, &t->frontier, &t->acct_tries};
     for (DevBuf *b : bufs) dbuf_free(*b);
     delete t;
 }
@@ -216,8 +216,6 @@ extern "C" B200_API int32_t b200_dstate_apply(b200_dstate *t, const uint8_t *acc
         TRY(da_prepare(A, m, 1));
         TRY(da_prepare(S, n_entries, A->lcap));
         TRY(da_resize(A, t->wipe_cnt, 16, 0, 0));
-        TRY(da_scratch(A, t->wipe_a, std::max<size_t>((size_t)m, (size_t)S->node_alloc) * 4 + 16));
-        TRY(da_scratch(A, t->wipe_b, std::max<size_t>((size_t)m, (size_t)S->node_alloc) * 4 + 16));
         TRY(da_scratch(A, t->trie_of_key, std::max<size_t>((size_t)m, (size_t)n_entries) * 4 + 16));
         if (t->sharded) TRY(da_scratch(A, t->acct_tries, m * 4));
         TRY(h2d_into(A, t->in_akeys, acct_keys32, m * 32));
@@ -243,27 +241,28 @@ extern "C" B200_API int32_t b200_dstate_apply(b200_dstate *t, const uint8_t *acc
         // ---- storage tries of destroyed / wiped accounts
         S->top_out = static_cast<uint8_t *>(A->lsroot.p);  // the account arena may have been re-allocated
         S->top_stride = 32;
-        uint32_t *wc = static_cast<uint32_t *>(t->wipe_cnt.p);  // [0] tries to wipe, [1] / [2] BFS list lengths
+        uint32_t *wc = static_cast<uint32_t *>(t->wipe_cnt.p);  // [0] tries to wipe
         CU(cudaMemsetAsync(wc, 0, 16, st));
         uint32_t *wipe_tries = static_cast<uint32_t *>(t->trie_of_key.p);  // borrowed until the storage entries are expanded
         CU(launch_dt_wipe_list(a_kind, d_flags, a_leaf, m, wipe_tries, wc, st));
         c->launches++;
         {
             DTrieDev ds = da_view(S);
-            uint32_t *cur = static_cast<uint32_t *>(t->wipe_a.p), *next = static_cast<uint32_t *>(t->wipe_b.p);
-            uint32_t *cnt_cur = wc + 1, *cnt_next = wc + 2;
-            CU(launch_dt_wipe_begin(ds, wipe_tries, wc, (uint32_t)m, cur, cnt_cur, st));
+            // the free stack is the BFS queue: every round visits what the round before pushed
+            CU(cudaMemcpyAsync(ps + 200, ds.g + DG_NODE_FREE, 4, cudaMemcpyDeviceToHost, st));
+            CU(launch_dt_wipe_begin(ds, wipe_tries, wc, (uint32_t)m, st));
             c->launches++;
-            for (int round = 0;; round++) {
-                CU(cudaMemcpyAsync(ps + 200, cnt_cur, 4, cudaMemcpyDeviceToHost, st));
-                CU(cudaStreamSynchronize(st));
-                if (ps[200] == 0) break;
+            CU(cudaMemcpyAsync(ps + 201, ds.g + DG_NODE_FREE, 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            uint32_t lo = ps[200], hi = ps[201];
+            for (int round = 0; hi > lo; round++) {
                 if (round > 70) return fail(c, B200_ERR_CUDA, "storage wipe does not terminate");
-                CU(cudaMemsetAsync(cnt_next, 0, 4, st));
-                CU(launch_dt_wipe_round(ds, cur, cnt_cur, ps[200], next, cnt_next, st));
+                CU(launch_dt_wipe_round(ds, lo, hi, st));
                 c->launches++;
-                std::swap(cur, next);
-                std::swap(cnt_cur, cnt_next);
+                CU(cudaMemcpyAsync(ps + 201, ds.g + DG_NODE_FREE, 4, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                lo = hi;
+                hi = ps[201];
             }
         }
         // ---- storage slots of the surviving accounts

@@ -83,33 +83,32 @@ static __device__ __forceinline__ void dt_wipe_leaf(const DTrieDev &t, uint32_t 
     t.leaf_free[atomicAdd(&t.g[DG_LEAF_FREE], 1u)] = x;
     atomicSub(&t.g[DG_NLEAVES], 1u);
 }
-// breadth-first release of whole tries: no removed-node records (reth reports a wiped storage trie as is_deleted)
-__global__ void dt_wipe_begin_kernel(DTrieDev t, const uint32_t *__restrict__ tries, const uint32_t *__restrict__ count_p,
-                                     uint32_t *__restrict__ next, uint32_t *next_count) {
+// Breadth-first release of whole tries; no removed-node records (reth reports a wiped storage trie as is_deleted).  The
+// free stack doubles as the BFS queue: a released node is pushed onto node_free at once (nothing pops during a wipe), and
+// the next round visits exactly the stack region the previous round pushed — its child words are still intact.
+__global__ void dt_wipe_begin_kernel(DTrieDev t, const uint32_t *__restrict__ tries, const uint32_t *__restrict__ count_p) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *count_p) return;
     uint32_t r = tries[i], w = t.troot[r];
     if (w == DT_NONE) return;
     dt_set_child(t, r, DT_NONE, 0, DT_NONE);
     if (w & DT_LEAF) dt_wipe_leaf(t, w & ~DT_LEAF);
-    else next[atomicAdd(next_count, 1u)] = w;
+    else t.node_free[atomicAdd(&t.g[DG_NODE_FREE], 1u)] = w;
 }
-__global__ void dt_wipe_round_kernel(DTrieDev t, const uint32_t *__restrict__ list, const uint32_t *__restrict__ count_p,
-                                     uint32_t *__restrict__ next, uint32_t *next_count) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *count_p) return;
-    uint32_t v = list[i];
+__global__ void dt_wipe_round_kernel(DTrieDev t, uint32_t lo, uint32_t hi) {  // node_free[lo, hi): pushed by the round before
+    uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    uint32_t v = t.node_free[i];
     const uint32_t *ch = t.nchild + 16 * (uint64_t)v;
     for (int s = 0; s < 16; s++) {
         uint32_t w = ch[s];
         if (w == DT_NONE) continue;
         if (w & DT_LEAF) dt_wipe_leaf(t, w & ~DT_LEAF);
-        else next[atomicAdd(next_count, 1u)] = w;
+        else t.node_free[atomicAdd(&t.g[DG_NODE_FREE], 1u)] = w;
     }
     t.ndepth[v] = DT_DEAD;
     t.nmeta[v] = 0;
     t.npending[v] = 0;
-    t.node_free[atomicAdd(&t.g[DG_NODE_FREE], 1u)] = v;
 }
 // trie_of_key[j] for storage entry j of account entry i (seg_offsets[i] <= j < seg_offsets[i+1]): the account's leaf if
 // the account exists after the block, DT_NONE (entry ignored) otherwise

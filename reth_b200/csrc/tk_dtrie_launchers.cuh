@@ -104,13 +104,12 @@ cudaError_t launch_dt_wipe_list(const uint8_t *kind, const uint8_t *flags, const
     return cudaGetLastError();
 }
 cudaError_t launch_dt_wipe_begin(const DTrieDev &t, const uint32_t *tries, const uint32_t *count_p, uint32_t max_count,
-                                 uint32_t *next, uint32_t *next_count, cudaStream_t st) {
-    if (max_count) dt_wipe_begin_kernel<<<blocks_for(max_count, 128), 128, 0, st>>>(t, tries, count_p, next, next_count);
+                                 cudaStream_t st) {
+    if (max_count) dt_wipe_begin_kernel<<<blocks_for(max_count, 128), 128, 0, st>>>(t, tries, count_p);
     return cudaGetLastError();
 }
-cudaError_t launch_dt_wipe_round(const DTrieDev &t, const uint32_t *list, const uint32_t *count_p, uint32_t max_count,
-                                 uint32_t *next, uint32_t *next_count, cudaStream_t st) {
-    if (max_count) dt_wipe_round_kernel<<<blocks_for(max_count, 128), 128, 0, st>>>(t, list, count_p, next, next_count);
+cudaError_t launch_dt_wipe_round(const DTrieDev &t, uint32_t lo, uint32_t hi, cudaStream_t st) {
+    if (hi > lo) dt_wipe_round_kernel<<<blocks_for(hi - lo, 128), 128, 0, st>>>(t, lo, hi);
     return cudaGetLastError();
 }
 cudaError_t launch_dt_expand_tries(const uint64_t *seg_offsets, uint64_t m, const uint8_t *kind, const uint32_t *leaf_of,

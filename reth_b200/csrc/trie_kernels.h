@@ -210,9 +210,8 @@ cudaError_t launch_dt_removed_paths(const DTrieDev &t, uint32_t n_removed, uint8
 cudaError_t launch_dt_wipe_list(const uint8_t *kind, const uint8_t *flags, const uint32_t *leaf_of, uint64_t m, uint32_t *tries,
                                 uint32_t *count, cudaStream_t st);
 cudaError_t launch_dt_wipe_begin(const DTrieDev &t, const uint32_t *tries, const uint32_t *count_p, uint32_t max_count,
-                                 uint32_t *next, uint32_t *next_count, cudaStream_t st);
-cudaError_t launch_dt_wipe_round(const DTrieDev &t, const uint32_t *list, const uint32_t *count_p, uint32_t max_count,
-                                 uint32_t *next, uint32_t *next_count, cudaStream_t st);
+                                 cudaStream_t st);
+cudaError_t launch_dt_wipe_round(const DTrieDev &t, uint32_t lo, uint32_t hi, cudaStream_t st);
 cudaError_t launch_dt_expand_tries(const uint64_t *seg_offsets, uint64_t m, const uint8_t *kind, const uint32_t *leaf_of,
                                    uint64_t n_entries, uint32_t *trie_of_key, cudaStream_t st);
 
