@@ -12,3 +12,4 @@ from .stages import AccountHashingStage, MerkleStage, StageError, StorageHashing
 from .trie import (BranchNodeCompact, DynamicStateRoot, ParallelStateRoot, ResidentStateRoot, StateRoot, StateRootError, StateRootProgress,  # noqa: F401,E402
                    StorageRoot, StorageTrieUpdates, TrieUpdates)
 from .sharded import ShardedDynamicStateRoot  # noqa: F401,E402
+from .verify import Verifier  # noqa: F401,E402

@@ -177,3 +177,39 @@ def test_resident_state_root_commits_blocks(eng, dynamic):
         assert root == StateRoot(eng, merged.into_sorted()).root(), block
         assert rebuilt == (block % 2 == 0 and not dynamic)
     rs.close()
+
+
+def test_verifier_reports_extra_wrong_and_missing_nodes(eng):
+    """reth's Verifier (crates/trie/trie/src/verify.rs, tests :540-760): consistent tables give no output; a dropped node is
+    Missing, a planted one Extra, a node with a flipped mask Wrong — for the accounts trie and for a storage trie."""
+    from dataclasses import replace
+    from reth_b200 import Verifier
+    from reth_b200.verify import Extra, Missing, Wrong
+    rng = np.random.default_rng(4)
+    rk = lambda: bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+    st = HashedPostState()
+    for i in range(600):
+        k = rk()
+        st.accounts[k] = Account(i % 5, 10 + i)
+        if i % 50 == 0:
+            st.storages[k] = HashedStorage(False, {rk(): int(rng.integers(1, 2**60)) for _ in range(400)})
+    sorted_state = st.into_sorted()
+    _, tables = StateRoot(eng, sorted_state).root_with_updates()
+    v = Verifier(eng, sorted_state)
+    assert v.verify(tables) == []
+    apaths = sorted(tables.account_nodes)
+    dropped = tables.account_nodes.pop(apaths[3])
+    flipped_path = apaths[7]
+    good = tables.account_nodes[flipped_path]
+    tables.account_nodes[flipped_path] = replace(good, tree_mask=good.tree_mask ^ 1)
+    planted_path = bytes([0xF, 0xF, 0xF, 0xF, 0xF])
+    tables.account_nodes[planted_path] = good
+    addr = next(a for a, s in tables.storage_tries.items() if len(s.storage_nodes) > 3)
+    spaths = sorted(tables.storage_tries[addr].storage_nodes)
+    sdropped = tables.storage_tries[addr].storage_nodes.pop(spaths[1])
+    out = v.verify(tables)
+    assert Missing(None, apaths[3], dropped) in out
+    assert Wrong(None, flipped_path, good, tables.account_nodes[flipped_path]) in out
+    assert Extra(None, planted_path, good) in out
+    assert Missing(addr, spaths[1], sdropped) in out
+    assert len(out) == 4
