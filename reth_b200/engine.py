@@ -478,6 +478,8 @@ class DynamicState:
         seg_offsets = _np(seg_offsets, np.uint64)
         if len(seg_offsets) != len(acct_keys) + 1:
             raise ValueError("seg_offsets must have n_accounts+1 entries")
+        if int(seg_offsets[-1]) != len(slot_keys) or len(values) != len(slot_keys):
+            raise ValueError("seg_offsets[-1] must equal the number of slot rows (keys and values)")
         h = C.c_void_p()
         root = np.empty(32, np.uint8)
         fn = engine.lib.b200_dstate_create_sharded if sharded else engine.lib.b200_dstate_create
@@ -514,6 +516,8 @@ class DynamicState:
         seg_offsets = _np(seg_offsets, np.uint64)
         if len(seg_offsets) != m + 1:
             raise ValueError("seg_offsets must have m+1 entries")
+        if (m and int(seg_offsets[m]) != len(slot_keys)) or len(values) != len(slot_keys):
+            raise ValueError("seg_offsets[m] must equal the number of slot rows (keys and values)")
         root = np.empty(32, np.uint8)
         au, ar, su, sr, s = Updates(), Updates(), Updates(), Updates(), Stats()
         deleted = np.zeros(max(m, 1), np.uint8)

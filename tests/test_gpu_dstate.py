@@ -516,3 +516,40 @@ def test_block_updates_as_table_rows(eng):
     assert order == sorted(order)
     assert {k for k, _ in srows} <= set(ks)
     h.ds.close()
+
+
+def test_bad_arguments_are_rejected_not_crashed(eng):
+    """The C ABI never aborts: null pointers, malformed segment tables, unsorted keys and misuse of a plain state as a
+    sharded one come back as error codes, and the state stays usable."""
+    import ctypes as C
+    from reth_b200 import DynamicState
+    from reth_b200._lib import B200Error
+    lib, ctx = eng.lib, eng.ctx
+    h = C.c_void_p()
+    assert lib.b200_dstate_create(ctx, None, None, 5, None, None, None, C.byref(h), None) < 0          # null inputs, n > 0
+    assert lib.b200_dstate_create(None, None, None, 0, None, None, None, C.byref(h), None) < 0         # null context
+    rng = np.random.default_rng(1)
+    state = random_state(rng, 50)
+    _, keys, accs, skeys, svals, offs = flatten(state)
+    bad_offs = offs.copy()
+    bad_offs[3] = bad_offs[-1] + 5                                                                      # not monotone
+    assert lib.b200_dstate_create(ctx, keys.ctypes.data, accs.ctypes.data, len(keys), skeys.ctypes.data, svals.ctypes.data,
+                                  bad_offs.ctypes.data, C.byref(h), None) < 0
+    ds = DynamicState.create(eng, keys, accs, skeys, svals, offs)
+    root = ds.root()
+    with pytest.raises(B200Error):                                                                      # unsorted account keys
+        ds.apply(keys[[5, 2]], accs[[5, 2]], None, np.zeros((0, 32), np.uint8), np.zeros((0, 32), np.uint8), np.zeros(3, np.uint64))
+    with pytest.raises(ValueError):                                                                     # segment table vs slot rows
+        ds.apply(keys[:2], accs[:2], None, np.zeros((0, 32), np.uint8), np.zeros((0, 32), np.uint8), np.array([0, 0, 9], np.uint64))
+    with pytest.raises(B200Error):                                                                      # segment table not monotone
+        ds.apply(keys[:2], accs[:2], None, skeys[:4], svals[:4], np.array([0, 5, 4], np.uint64))
+    with pytest.raises(B200Error):                                                                      # not a sharded state
+        ds.frontier()
+    assert lib.b200_dstate_apply(ds.handle, None, None, None, 3, None, None, None, None, None, None, None, None, None, None) < 0
+    assert lib.b200_dstate_account_proofs(ds.handle, None, 4, None) < 0
+    assert lib.b200_dstate_root(None, None) < 0
+    lib.b200_dstate_destroy(None)                                                                       # no-op
+    lib.b200_proofs_release(None)
+    assert ds.root() == root                                                                            # untouched by all of the above
+    assert ds.apply(keys[:1], accs[:1], None, np.zeros((0, 32), np.uint8), np.zeros((0, 32), np.uint8), np.zeros(2, np.uint64)) == root
+    ds.close()
