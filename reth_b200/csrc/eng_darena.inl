@@ -375,47 +375,19 @@ static int32_t da_collect_updates(DArena *a, b200_updates *u) {
         pick_ids = ids;
         pick_prefix = pref;
     }
-    size_t o_tid = 0;
-    size_t o_plen = align_up(o_tid + (size_t)n_stored * 4, 16);
-    size_t o_path = align_up(o_plen + n_stored, 16);
-    size_t o_sm = align_up(o_path + (size_t)n_stored * 32, 16);
-    size_t o_tm = align_up(o_sm + (size_t)n_stored * 2, 16);
-    size_t o_hm = align_up(o_tm + (size_t)n_stored * 2, 16);
-    size_t o_ho32 = align_up(o_hm + (size_t)n_stored * 2, 16);
-    size_t o_hash = align_up(o_ho32 + (size_t)n_stored * 4, 16);
-    size_t o_ho64 = align_up(o_hash + (size_t)n_hashes * 32, 16);
-    size_t dev_total = o_ho64, host_total = o_ho64 + ((size_t)n_stored + 1) * 8;
-    CU(cudaMallocHost(&owner->host, host_total ? host_total : 16));
+    const UpdatesLayout lay(n_stored, n_hashes);
+    CU(cudaMallocHost(&owner->host, lay.host_total ? lay.host_total : 16));
     uint8_t *h = static_cast<uint8_t *>(owner->host);
-    u->n_nodes = n_stored;
-    u->trie_id = reinterpret_cast<uint32_t *>(h + o_tid);
-    u->path_len = h + o_plen;
-    u->path_packed = h + o_path;
-    u->state_mask = reinterpret_cast<uint16_t *>(h + o_sm);
-    u->tree_mask = reinterpret_cast<uint16_t *>(h + o_tm);
-    u->hash_mask = reinterpret_cast<uint16_t *>(h + o_hm);
-    u->hashes = h + o_hash;
-    u->hash_offset = reinterpret_cast<uint64_t *>(h + o_ho64);
+    lay.bind_host(u, h, n_stored);
     if (n_stored) {
-        TRY(da_scratch(a, a->out, dev_total));
+        TRY(da_scratch(a, a->out, lay.dev_total));
         uint8_t *dv = static_cast<uint8_t *>(a->out.p);
-        UpdatesDev ud;
-        ud.trie_id = reinterpret_cast<uint32_t *>(dv + o_tid);
-        ud.path_len = dv + o_plen;
-        ud.path_packed = dv + o_path;
-        ud.state_mask = reinterpret_cast<uint16_t *>(dv + o_sm);
-        ud.tree_mask = reinterpret_cast<uint16_t *>(dv + o_tm);
-        ud.hash_mask = reinterpret_cast<uint16_t *>(dv + o_hm);
-        ud.hash_offset = reinterpret_cast<uint32_t *>(dv + o_ho32);
-        ud.hashes = dv + o_hash;
-        CU(launch_dt_gather_updates(d, pick_ids, n_stored, pick_prefix, ud, st));
+        CU(launch_dt_gather_updates(d, pick_ids, n_stored, pick_prefix, lay.bind_dev(dv), st));
         c->launches++;
-        CU(cudaMemcpyAsync(h, dv, dev_total, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h, dv, lay.dev_total, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        const uint32_t *ho32 = reinterpret_cast<const uint32_t *>(h + o_ho32);
-        for (uint32_t i = 0; i < n_stored; i++) u->hash_offset[i] = ho32[i];
     }
-    u->hash_offset[n_stored] = n_hashes;
+    lay.finish_host(u, h, n_stored, n_hashes);
     return B200_OK;
 }
 

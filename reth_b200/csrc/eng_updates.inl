@@ -18,37 +18,35 @@ extern "C" B200_API void b200_updates_release(b200_updates *u) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Gathers the records of `n_stored` stored nodes (ids on the device) into `u` (host, page-locked).
-static int32_t gather_and_copy(b200_ctx *c, const ForestDev &f, const uint32_t *d_stored_ids, uint32_t n_stored,
-                               uint32_t n_hashes, const uint32_t *d_prefix_by_node, const uint32_t *d_prefix_by_record,
-                               const uint64_t *d_seg_offsets, uint64_t n_segs, b200_updates *u, UpdatesOwner *owner) {
-    cudaStream_t st = c->stream;
-    // one device block + one pinned host block, same layout
-    size_t o_tid = 0;
-    size_t o_plen = align_up(o_tid + (size_t)n_stored * 4, 16);
-    size_t o_path = align_up(o_plen + n_stored, 16);
-    size_t o_sm = align_up(o_path + (size_t)n_stored * 32, 16);
-    size_t o_tm = align_up(o_sm + (size_t)n_stored * 2, 16);
-    size_t o_hm = align_up(o_tm + (size_t)n_stored * 2, 16);
-    size_t o_ho32 = align_up(o_hm + (size_t)n_stored * 2, 16);
-    size_t o_hash = align_up(o_ho32 + (size_t)n_stored * 4, 16);
-    size_t o_ho64 = align_up(o_hash + (size_t)n_hashes * 32, 16);
-    size_t dev_total = o_ho64;
-    size_t host_total = o_ho64 + ((size_t)n_stored + 1) * 8;
-    CU(cudaMallocHost(&owner->host, host_total ? host_total : 16));
-    uint8_t *h = static_cast<uint8_t *>(owner->host);
-    u->n_nodes = n_stored;
-    u->trie_id = reinterpret_cast<uint32_t *>(h + o_tid);
-    u->path_len = h + o_plen;
-    u->path_packed = h + o_path;
-    u->state_mask = reinterpret_cast<uint16_t *>(h + o_sm);
-    u->tree_mask = reinterpret_cast<uint16_t *>(h + o_tm);
-    u->hash_mask = reinterpret_cast<uint16_t *>(h + o_hm);
-    u->hashes = h + o_hash;
-    u->hash_offset = reinterpret_cast<uint64_t *>(h + o_ho64);
-    if (n_stored) {
-        ENSURE(out_a, dev_total);
-        uint8_t *d = static_cast<uint8_t *>(c->out_a.p);
+// One block holding every array of a b200_updates; the same layout on the device (gather target) and in page-locked host
+// memory (what the caller receives), so a single copy brings the records over.
+struct UpdatesLayout {
+    size_t o_tid, o_plen, o_path, o_sm, o_tm, o_hm, o_ho32, o_hash, o_ho64, dev_total, host_total;
+    UpdatesLayout(uint32_t n_stored, uint32_t n_hashes) {
+        o_tid = 0;
+        o_plen = align_up(o_tid + (size_t)n_stored * 4, 16);
+        o_path = align_up(o_plen + n_stored, 16);
+        o_sm = align_up(o_path + (size_t)n_stored * 32, 16);
+        o_tm = align_up(o_sm + (size_t)n_stored * 2, 16);
+        o_hm = align_up(o_tm + (size_t)n_stored * 2, 16);
+        o_ho32 = align_up(o_hm + (size_t)n_stored * 2, 16);
+        o_hash = align_up(o_ho32 + (size_t)n_stored * 4, 16);
+        o_ho64 = align_up(o_hash + (size_t)n_hashes * 32, 16);
+        dev_total = o_ho64;
+        host_total = o_ho64 + ((size_t)n_stored + 1) * 8;
+    }
+    void bind_host(b200_updates *u, uint8_t *h, uint32_t n_stored) const {
+        u->n_nodes = n_stored;
+        u->trie_id = reinterpret_cast<uint32_t *>(h + o_tid);
+        u->path_len = h + o_plen;
+        u->path_packed = h + o_path;
+        u->state_mask = reinterpret_cast<uint16_t *>(h + o_sm);
+        u->tree_mask = reinterpret_cast<uint16_t *>(h + o_tm);
+        u->hash_mask = reinterpret_cast<uint16_t *>(h + o_hm);
+        u->hashes = h + o_hash;
+        u->hash_offset = reinterpret_cast<uint64_t *>(h + o_ho64);
+    }
+    UpdatesDev bind_dev(uint8_t *d) const {
         UpdatesDev ud;
         ud.trie_id = reinterpret_cast<uint32_t *>(d + o_tid);
         ud.path_len = d + o_plen;
@@ -58,15 +56,35 @@ static int32_t gather_and_copy(b200_ctx *c, const ForestDev &f, const uint32_t *
         ud.hash_mask = reinterpret_cast<uint16_t *>(d + o_hm);
         ud.hash_offset = reinterpret_cast<uint32_t *>(d + o_ho32);
         ud.hashes = d + o_hash;
-        CU(launch_gather_updates(f, d_stored_ids, n_stored, d_prefix_by_node, d_prefix_by_record, d_seg_offsets, n_segs,
-                                 ud, st));
-        c->launches++;
-        CU(cudaMemcpyAsync(h, d, dev_total, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        return ud;
+    }
+    // after the device block has been copied to h: widen the 32-bit hash offsets and append the total
+    void finish_host(b200_updates *u, const uint8_t *h, uint32_t n_stored, uint32_t n_hashes) const {
         const uint32_t *ho32 = reinterpret_cast<const uint32_t *>(h + o_ho32);
         for (uint32_t i = 0; i < n_stored; i++) u->hash_offset[i] = ho32[i];
+        u->hash_offset[n_stored] = n_hashes;
     }
-    u->hash_offset[n_stored] = n_hashes;
+};
+
+// Gathers the records of `n_stored` stored nodes (ids on the device) into `u` (host, page-locked).
+static int32_t gather_and_copy(b200_ctx *c, const ForestDev &f, const uint32_t *d_stored_ids, uint32_t n_stored,
+                               uint32_t n_hashes, const uint32_t *d_prefix_by_node, const uint32_t *d_prefix_by_record,
+                               const uint64_t *d_seg_offsets, uint64_t n_segs, b200_updates *u, UpdatesOwner *owner) {
+    cudaStream_t st = c->stream;
+    const UpdatesLayout lay(n_stored, n_hashes);
+    CU(cudaMallocHost(&owner->host, lay.host_total ? lay.host_total : 16));
+    uint8_t *h = static_cast<uint8_t *>(owner->host);
+    lay.bind_host(u, h, n_stored);
+    if (n_stored) {
+        ENSURE(out_a, lay.dev_total);
+        uint8_t *d = static_cast<uint8_t *>(c->out_a.p);
+        CU(launch_gather_updates(f, d_stored_ids, n_stored, d_prefix_by_node, d_prefix_by_record, d_seg_offsets, n_segs,
+                                 lay.bind_dev(d), st));
+        c->launches++;
+        CU(cudaMemcpyAsync(h, d, lay.dev_total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    lay.finish_host(u, h, n_stored, n_hashes);
     return B200_OK;
 }
 
