@@ -372,6 +372,14 @@ B200_API int32_t b200_dstate_account_proofs(b200_dstate *, const uint8_t *acct_k
 B200_API int32_t b200_dstate_storage_proofs(b200_dstate *, const uint8_t *acct_key32, const uint8_t *slot_keys32, uint64_t n,
                                             uint8_t storage_root32[32] /* nullable */, b200_proofs *out);
 B200_API void b200_proofs_release(b200_proofs *);
+/* b200_dstate_apply with the block already in device memory (every input pointer and d_root32 are device pointers;
+ * n_entries = d_seg_offsets[m]); the update records, if wanted, still arrive in host memory. */
+B200_API int32_t b200_dstate_apply_dev(b200_dstate *, const void *d_acct_keys32, const void *d_accts, const void *d_acct_flags,
+                                       uint64_t m, const void *d_slot_keys32, const void *d_values32_be,
+                                       const void *d_seg_offsets, uint64_t n_entries, void *d_root32,
+                                       b200_updates *opt_acct_updated, b200_updates *opt_acct_removed,
+                                       b200_updates *opt_storage_updated, b200_updates *opt_storage_removed,
+                                       uint8_t *opt_storage_deleted, b200_stats *opt_stats);
 B200_API int32_t b200_dstate_root(b200_dstate *, uint8_t root32[32]);
 B200_API uint64_t b200_dstate_accounts(const b200_dstate *);
 B200_API uint64_t b200_dstate_slots(const b200_dstate *);

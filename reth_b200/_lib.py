@@ -168,6 +168,7 @@ def load():
     sig("b200_dstate_account_proofs", i32, vp, vp, u64, C.POINTER(Proofs))
     sig("b200_dstate_storage_proofs", i32, vp, vp, vp, u64, vp, C.POINTER(Proofs))
     sig("b200_proofs_release", None, C.POINTER(Proofs))
+    sig("b200_dstate_apply_dev", i32, vp, vp, vp, vp, u64, vp, vp, vp, u64, vp, PU, PU, PU, PU, vp, PS)
     sig("b200_dstate_root", i32, vp, vp)
     sig("b200_dstate_accounts", u64, vp)
     sig("b200_dstate_slots", u64, vp)

@@ -185,21 +185,24 @@ extern "C" B200_API int32_t b200_dstate_frontier(b200_dstate *t, b200_frontier_e
 // before the block's slots are applied (NULL = every entry is a plain upsert).  Storage entries of account entry i are
 // seg_offsets[i] .. seg_offsets[i+1]: slot keys ascending, zero value = delete.  Every account whose storage changes
 // must have an entry.  storage_* records carry trie_id = index i of the account entry.
-extern "C" B200_API int32_t b200_dstate_apply(b200_dstate *t, const uint8_t *acct_keys32, const b200_account *accts,
-                                              const uint8_t *acct_flags, uint64_t m, const uint8_t *slot_keys32,
-                                              const uint8_t *values32_be, const uint64_t *seg_offsets, uint8_t root32[32],
-                                              b200_updates *opt_acct_updated, b200_updates *opt_acct_removed,
-                                              b200_updates *opt_storage_updated, b200_updates *opt_storage_removed,
-                                              uint8_t *opt_storage_deleted /* [m] */, b200_stats *opt_stats) {
+// on_device: the block's arrays (and root32) are device memory, n_entries_dev = number of slot entries; the segment table
+// cannot be checked on the host then (a malformed one mis-routes slots but stays in bounds).
+static int32_t dstate_apply_impl(b200_dstate *t, const uint8_t *acct_keys32, const b200_account *accts,
+                                 const uint8_t *acct_flags, uint64_t m, const uint8_t *slot_keys32,
+                                 const uint8_t *values32_be, const uint64_t *seg_offsets, bool on_device, uint64_t n_entries_dev,
+                                 uint8_t *root32, b200_updates *opt_acct_updated, b200_updates *opt_acct_removed,
+                                 b200_updates *opt_storage_updated, b200_updates *opt_storage_removed,
+                                 uint8_t *opt_storage_deleted /* [m] */, b200_stats *opt_stats) {
     if (!t || !root32 || (m && (!acct_keys32 || !accts || !seg_offsets)))
         return fail(t ? t->c : nullptr, B200_ERR_INVALID_ARG, "bad argument");
     b200_ctx *c = t->c;
+    const cudaMemcpyKind in_kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     b200_updates *outs[] = {opt_acct_updated, opt_acct_removed, opt_storage_updated, opt_storage_removed};
     for (b200_updates *u : outs)
         if (u) memset(u, 0, sizeof *u);
     if (m >= (1ull << 28)) return fail(c, B200_ERR_INVALID_ARG, "at most 2^28-1 dirty accounts per apply");
-    if (m) TRY(check_offsets_host(c, seg_offsets, m));
-    const uint64_t n_entries = m ? seg_offsets[m] : 0;
+    if (m && !on_device) TRY(check_offsets_host(c, seg_offsets, m));
+    const uint64_t n_entries = m ? (on_device ? n_entries_dev : seg_offsets[m]) : 0;
     if (n_entries >= (1ull << 28)) return fail(c, B200_ERR_INVALID_ARG, "at most 2^28-1 dirty slots per apply");
     if (n_entries && (!slot_keys32 || !values32_be)) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
     std::lock_guard<std::mutex> lock(c->mu);
@@ -218,13 +221,13 @@ extern "C" B200_API int32_t b200_dstate_apply(b200_dstate *t, const uint8_t *acc
         TRY(da_resize(A, t->wipe_cnt, 16, 0, 0));
         TRY(da_scratch(A, t->trie_of_key, std::max<size_t>((size_t)m, (size_t)n_entries) * 4 + 16));
         if (t->sharded) TRY(da_scratch(A, t->acct_tries, m * 4));
-        TRY(h2d_into(A, t->in_akeys, acct_keys32, m * 32));
-        TRY(h2d_into(A, t->in_accts, accts, m * 72));
-        if (acct_flags) TRY(h2d_into(A, t->in_aflags, acct_flags, m));
-        TRY(h2d_into(A, t->in_offs, seg_offsets, (m + 1) * 8));
+        TRY(h2d_into(A, t->in_akeys, acct_keys32, m * 32, in_kind));
+        TRY(h2d_into(A, t->in_accts, accts, m * 72, in_kind));
+        if (acct_flags) TRY(h2d_into(A, t->in_aflags, acct_flags, m, in_kind));
+        TRY(h2d_into(A, t->in_offs, seg_offsets, (m + 1) * 8, in_kind));
         if (n_entries) {
-            TRY(h2d_into(S, t->in_skeys, slot_keys32, n_entries * 32));
-            TRY(h2d_into(S, t->in_svals, values32_be, n_entries * 32));
+            TRY(h2d_into(S, t->in_skeys, slot_keys32, n_entries * 32, in_kind));
+            TRY(h2d_into(S, t->in_svals, values32_be, n_entries * 32, in_kind));
         }
         const uint8_t *d_flags = acct_flags ? static_cast<const uint8_t *>(t->in_aflags.p) : nullptr;
         // ---- accounts: structure only (their leaves are re-hashed after the storage roots are known)
@@ -290,7 +293,7 @@ extern "C" B200_API int32_t b200_dstate_apply(b200_dstate *t, const uint8_t *acc
         TRY(da_pull_counters(A, ps + 256));
         TRY(da_pull_counters(S, ps + 256 + DG_WORDS));
     }
-    CU(cudaMemcpyAsync(root32, t->root.p, 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(root32, t->root.p, 32, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
     TRY(sync_and_status(c));
     if (m) {
         da_take_counters(A, ps + 256);
@@ -298,9 +301,17 @@ extern "C" B200_API int32_t b200_dstate_apply(b200_dstate *t, const uint8_t *acc
         if (!n_entries) S->n_built = S->n_removed = 0;  // the storage arena's per-apply lists were not reset this block
     }
     c->stats.branches_added = A->n_built + S->n_built;
-    if (opt_storage_deleted)
+    if (opt_storage_deleted) {
+        std::vector<uint8_t> h_flags;
+        const uint8_t *fl = acct_flags;
+        if (acct_flags && on_device && m) {  // the flags live on the device: bring them over
+            h_flags.resize(m);
+            CU(cudaMemcpy(h_flags.data(), acct_flags, m, cudaMemcpyDeviceToHost));
+            fl = h_flags.data();
+        }
         for (uint64_t i = 0; i < m; i++)
-            opt_storage_deleted[i] = (h_kind[i] == DK_DELETE || (acct_flags && (acct_flags[i] & 4) && (h_kind[i] == DK_UPDATE || h_kind[i] == DK_TOUCH))) ? 1 : 0;
+            opt_storage_deleted[i] = (h_kind[i] == DK_DELETE || (fl && (fl[i] & 4) && (h_kind[i] == DK_UPDATE || h_kind[i] == DK_TOUCH))) ? 1 : 0;
+    }
     auto release_all = [&] {
         for (b200_updates *u : outs)
             if (u) b200_updates_release(u);
@@ -336,3 +347,28 @@ extern "C" B200_API int32_t b200_dstate_apply(b200_dstate *t, const uint8_t *acc
     return B200_OK;
 }
 
+
+extern "C" B200_API int32_t b200_dstate_apply(b200_dstate *t, const uint8_t *acct_keys32, const b200_account *accts,
+                                              const uint8_t *acct_flags, uint64_t m, const uint8_t *slot_keys32,
+                                              const uint8_t *values32_be, const uint64_t *seg_offsets, uint8_t root32[32],
+                                              b200_updates *opt_acct_updated, b200_updates *opt_acct_removed,
+                                              b200_updates *opt_storage_updated, b200_updates *opt_storage_removed,
+                                              uint8_t *opt_storage_deleted /* [m] */, b200_stats *opt_stats) {
+    return dstate_apply_impl(t, acct_keys32, accts, acct_flags, m, slot_keys32, values32_be, seg_offsets, false, 0, root32,
+                             opt_acct_updated, opt_acct_removed, opt_storage_updated, opt_storage_removed, opt_storage_deleted,
+                             opt_stats);
+}
+// The block already in device memory (hashed and sorted there, e.g. by b200_hash_sort_*): every input pointer and d_root32
+// are device pointers, n_entries = d_seg_offsets[m].  The update records, if wanted, still arrive in host memory.
+extern "C" B200_API int32_t b200_dstate_apply_dev(b200_dstate *t, const void *d_acct_keys32, const void *d_accts,
+                                                  const void *d_acct_flags, uint64_t m, const void *d_slot_keys32,
+                                                  const void *d_values32_be, const void *d_seg_offsets, uint64_t n_entries,
+                                                  void *d_root32, b200_updates *opt_acct_updated, b200_updates *opt_acct_removed,
+                                                  b200_updates *opt_storage_updated, b200_updates *opt_storage_removed,
+                                                  uint8_t *opt_storage_deleted, b200_stats *opt_stats) {
+    return dstate_apply_impl(t, static_cast<const uint8_t *>(d_acct_keys32), static_cast<const b200_account *>(d_accts),
+                             static_cast<const uint8_t *>(d_acct_flags), m, static_cast<const uint8_t *>(d_slot_keys32),
+                             static_cast<const uint8_t *>(d_values32_be), static_cast<const uint64_t *>(d_seg_offsets), true,
+                             n_entries, static_cast<uint8_t *>(d_root32), opt_acct_updated, opt_acct_removed,
+                             opt_storage_updated, opt_storage_removed, opt_storage_deleted, opt_stats);
+}

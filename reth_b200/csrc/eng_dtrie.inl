@@ -89,10 +89,10 @@ extern "C" B200_API int32_t b200_dtrie_create_dev(b200_ctx *c, const void *d_acc
     return dtrie_create_common(c, d_acct_keys32, d_accts, d_storage_roots32, n, cudaMemcpyDeviceToDevice, out, d_root32);
 }
 
-static int32_t h2d_into(DArena *a, DevBuf &b, const void *src, size_t bytes) {
+static int32_t h2d_into(DArena *a, DevBuf &b, const void *src, size_t bytes, cudaMemcpyKind kind = cudaMemcpyHostToDevice) {
     b200_ctx *c = a->c;
     TRY(da_scratch(a, b, bytes));
-    if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, kind, c->stream));
     return B200_OK;
 }
 

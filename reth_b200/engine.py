@@ -533,6 +533,15 @@ class DynamicState:
         return (self._root, updates_to_records(au, lib), [r[1] for r in updates_to_records(ar, lib)],
                 updates_to_records(su, lib), [(r[0], r[1]) for r in updates_to_records(sr, lib)], deleted[:m].copy())
 
+    def apply_dev(self, p_acct_keys: int, p_accts: int, p_flags, m: int, p_slot_keys: int, p_values: int, p_seg_offsets: int,
+                  n_entries: int, p_root: int):
+        """The block given as raw device addresses (flags may be None); the root is written to the device buffer p_root."""
+        s = Stats()
+        self.engine._check(self.engine.lib.b200_dstate_apply_dev(self.handle, p_acct_keys, p_accts, p_flags, m, p_slot_keys,
+                                                                 p_values, p_seg_offsets, n_entries, p_root, None, None, None,
+                                                                 None, None, C.byref(s)))
+        return s.as_dict()
+
     def _take_proofs(self, p: Proofs, with_depths: bool = False) -> list:
         n, nn = int(p.n_targets), int(p.n_nodes)
         res = []

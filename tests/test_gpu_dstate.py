@@ -553,3 +553,53 @@ def test_bad_arguments_are_rejected_not_crashed(eng):
     assert ds.root() == root                                                                            # untouched by all of the above
     assert ds.apply(keys[:1], accs[:1], None, np.zeros((0, 32), np.uint8), np.zeros((0, 32), np.uint8), np.zeros(2, np.uint64)) == root
     ds.close()
+
+
+def test_device_resident_block(eng):
+    """b200_dstate_apply_dev: the block's arrays and the root buffer live in device memory; same result as the host-pointer
+    call on a twin state."""
+    from reth_b200 import DynamicState
+    rng = np.random.default_rng(66)
+    state = random_state(rng, 400)
+    _, keys, accs, skeys, svals, offs = flatten(state)
+    a = DynamicState.create(eng, keys, accs, skeys, svals, offs)
+    b = DynamicState.create(eng, keys, accs, skeys, svals, offs)
+    for step in range(3):
+        block = random_block(rng, state, 60, step + 1)
+        ks = sorted(block)
+        m = len(ks)
+        bk = np.frombuffer(b"".join(ks), np.uint8).reshape(m, 32)
+        ba = np.zeros(m, oracle.ACCOUNT_DTYPE)
+        bf = np.zeros(m, np.uint8)
+        sk, sv, so = [], [], [0]
+        for i, k in enumerate(ks):
+            bf[i], ba[i] = block[k][0], block[k][1]
+            for s in sorted(block[k][2]):
+                sk.append(s)
+                sv.append(int(block[k][2][s]).to_bytes(32, "big"))
+            so.append(len(sk))
+        bsk = np.frombuffer(b"".join(sk), np.uint8).reshape(-1, 32) if sk else np.zeros((1, 32), np.uint8)[:0]
+        bsv = np.frombuffer(b"".join(sv), np.uint8).reshape(-1, 32) if sv else np.zeros((1, 32), np.uint8)[:0]
+        so = np.array(so, np.uint64)
+        root_host = a.apply(bk, ba, bf, bsk, bsv, so)
+        pad = lambda x: x if len(x) else np.zeros((1, 32), np.uint8)            # a valid address even when empty
+        ptrs, hold = to_device_ptrs((bk, ba, bf, pad(bsk), pad(bsv), so, np.zeros(32, np.uint8)))
+        b.apply_dev(ptrs[0], ptrs[1], ptrs[2], m, ptrs[3], ptrs[4], ptrs[5], len(sk), ptrs[6])
+        assert b.root() == root_host
+        assert b.accounts() == a.accounts() and b.slots() == a.slots()
+        # (the host model only steers the block generator)
+        for k in ks:
+            fl, acc, slots = block[k]
+            if not (fl & EXISTS):
+                state.pop(k, None)
+            elif not (fl & UNCHANGED) or k in state:
+                cur_a, cur_s = (state[k] if (fl & UNCHANGED) else (acc, state[k][1] if k in state else {}))
+                cur_s = {} if (fl & WIPED) else dict(cur_s)
+                for s_, v in slots.items():
+                    if v == 0:
+                        cur_s.pop(s_, None)
+                    else:
+                        cur_s[s_] = v
+                state[k] = (cur_a, cur_s)
+    a.close()
+    b.close()
