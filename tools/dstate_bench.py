@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--slot-writes", type=int, default=10)
     ap.add_argument("--blocks", type=int, default=12)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--device-resident", action="store_true",
+                    help="also apply every block from device memory (b200_dstate_apply_dev) on a twin state and compare roots")
     args = ap.parse_args()
     from reth_b200 import ACCOUNT_DTYPE, KECCAK_EMPTY, DynamicState, Engine
     eng = Engine(0)
@@ -61,7 +63,8 @@ def main():
                  for i in range(n)}
     live = [keys[i].tobytes() for i in range(n)]
     slot_of = {}  # a few known slots per touched account, to zero / change later
-    lat, dev_ms, built, mism = [], [], [], 0
+    twin = DynamicState.create(eng, keys, accs, skeys, svals, offs) if args.device_resident else None
+    lat, dev_ms, built, mism, lat_dev, mism_twin = [], [], [], 0, [], 0
     EX, UN, WI = DynamicState.EXISTS, DynamicState.UNCHANGED, DynamicState.WIPED
     for b in range(args.blocks):
         block = {}
@@ -107,9 +110,25 @@ def main():
             so.append(len(sk))
         bsk = np.frombuffer(b"".join(sk), np.uint8).reshape(-1, 32) if sk else np.zeros((0, 32), np.uint8)
         bsv = np.frombuffer(b"".join(sv), np.uint8).reshape(-1, 32) if sv else np.zeros((0, 32), np.uint8)
+        so_arr = np.array(so, np.uint64)
+        if twin is not None:  # the same block from device memory on the twin state: "value" next to the e2e figure
+            import torch
+            pad = lambda x: x if len(x) else np.zeros((1, 32), np.uint8)
+            dev_in = [torch.from_numpy(np.ascontiguousarray(x).view(np.uint8).reshape(-1)).cuda()
+                      for x in (bk, ba, bf, pad(bsk), pad(bsv), so_arr)]
+            d_root = torch.zeros(32, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            twin.apply_dev(dev_in[0].data_ptr(), dev_in[1].data_ptr(), dev_in[2].data_ptr(), m, dev_in[3].data_ptr(),
+                           dev_in[4].data_ptr(), dev_in[5].data_ptr(), len(sk), d_root.data_ptr())
+            dev_wall = time.perf_counter() - t0
+            if b >= 2:
+                lat_dev.append(dev_wall * 1e6)
         t0 = time.perf_counter()
-        root = ds.apply(bk, ba, bf, bsk, bsv, np.array(so, np.uint64))
+        root = ds.apply(bk, ba, bf, bsk, bsv, so_arr)
         wall = time.perf_counter() - t0
+        if twin is not None:
+            mism_twin += bytes(d_root.cpu().numpy()) != root
         st = eng.last_stats()
         if b >= 2:
             lat.append(wall * 1e6)
@@ -152,7 +171,9 @@ def main():
                       "apply_wall_us_median": float(np.median(lat)), "apply_device_ms_median": float(np.median(dev_ms)),
                       "rehashed_nodes_median": float(np.median(built)), "seed_build_s": build_s,
                       "accounts_after": ds.accounts(), "slots_after": ds.slots(), "resident_bytes": ds.device_bytes(),
-                      "root_mismatches_vs_full_rebuild": mism if state is not None else None}))
+                      "root_mismatches_vs_full_rebuild": mism if state is not None else None,
+                      "apply_dev_wall_us_median": float(np.median(lat_dev)) if lat_dev else None,
+                      "root_mismatches_dev_vs_host": mism_twin if twin is not None else None}))
 
 
 if __name__ == "__main__":

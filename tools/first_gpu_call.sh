@@ -22,6 +22,6 @@ export B200_DTRIE_ON_GPU=1
   timeout 600 python tools/dtrie_bench.py --base 100000000 --dirty 10000 --mix 80,10,10 2>&1 | tail -2
   timeout 600 python tools/dtrie_bench.py --base 10000000 --dirty 10000 --mix 80,10,10 --compare 2>&1 | tail -2
   echo "== dynamic state (C3 shape, 2000 touched accounts per block)"
-  timeout 900 python tools/dstate_bench.py --accounts 1000000 --slots 16 --touch 2000 --slot-writes 10 2>&1 | tail -2
+  timeout 900 python tools/dstate_bench.py --accounts 1000000 --slots 16 --touch 2000 --slot-writes 10 --device-resident 2>&1 | tail -2
 } > gpurun_out/first_gpu_call.log 2>&1
 tail -60 gpurun_out/first_gpu_call.log
