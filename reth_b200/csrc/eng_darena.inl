@@ -216,6 +216,15 @@ static int32_t da_prepare(DArena *a, uint64_t m, uint64_t tries) {
     return B200_OK;
 }
 
+// Blocks of up to this many entries are restructured by one CTA in one launch (B200_DT_FUSED_MAX overrides; 0 = never).
+static uint64_t dt_fused_max() {
+    static const uint64_t v = [] {
+        const char *e = getenv("B200_DT_FUSED_MAX");
+        return e ? strtoull(e, nullptr, 10) : (uint64_t)8192;
+    }();
+    return v;
+}
+
 static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const uint8_t *d_keys, const uint8_t *d_vals,
                               const uint8_t *d_flags, const uint8_t *d_sroots, uint64_t m) {
     b200_ctx *c = a->c;
@@ -225,6 +234,15 @@ static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const ui
     uint8_t *kind = static_cast<uint8_t *>(a->kind.p);
     uint32_t *leaf_of = static_cast<uint32_t *>(a->leaf_of.p);
     CU(cudaMemsetAsync(d.g + DG_SEEDS, 0, (DG_WORDS - DG_SEEDS) * 4, st));  // the per-apply list lengths
+    if (m <= dt_fused_max()) {  // small block: one CTA does every phase below without coming back to the host
+        CU(launch_dt_restructure_fused(d, d_trie_of_key, d_keys, d_vals, d_flags, d_sroots, (uint32_t)m, kind, leaf_of,
+                                       static_cast<uint32_t *>(a->list_a.p), static_cast<uint32_t *>(a->list_b.p),
+                                       static_cast<uint8_t *>(a->flags.p), static_cast<uint32_t *>(a->ins_idx.p),
+                                       static_cast<uint32_t *>(a->sel.p), static_cast<uint64_t *>(a->attach.p),
+                                       static_cast<uint8_t *>(a->nh.p), 8, st));
+        c->launches++;
+        return B200_OK;
+    }
     // ---- locate, value updates, detach deleted leaves
     CU(launch_dt_locate(d, d_trie_of_key, d_keys, d_vals, d_flags, m, kind, leaf_of, st));
     uint32_t *list_cur = static_cast<uint32_t *>(a->list_a.p), *list_next = static_cast<uint32_t *>(a->list_b.p);

@@ -236,11 +236,10 @@ static __device__ __forceinline__ DtLoc dt_descend(const DTrieDev &t, uint32_t t
 // flags[i] (accounts): bit 0 = present (0 deletes), bit 1 = touch only (the leaf's data is unchanged but it must be
 // re-hashed: its storage root changes); nullptr = all present.  Storage slots: a zero value deletes.
 // trie_of_key (forest arenas): the trie each key belongs to, DT_NONE = skip the entry.
-__global__ void dt_locate_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_key, const uint8_t *__restrict__ keys,
-                                 const uint8_t *__restrict__ vals, const uint8_t *__restrict__ flags, uint64_t m,
-                                 uint8_t *__restrict__ kind, uint32_t *__restrict__ leaf_of) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
+static __device__ __forceinline__ void dt_locate_entry(const DTrieDev &t, const uint32_t *__restrict__ trie_of_key,
+                                                       const uint8_t *__restrict__ keys, const uint8_t *__restrict__ vals,
+                                                       const uint8_t *__restrict__ flags, uint64_t i, uint8_t *__restrict__ kind,
+                                                       uint32_t *__restrict__ leaf_of) {
     const uint32_t trie = trie_of_key ? trie_of_key[i] : 0;
     if (trie == DT_NONE) {
         kind[i] = DK_NOOP;
@@ -267,14 +266,18 @@ __global__ void dt_locate_kernel(DTrieDev t, const uint32_t *__restrict__ trie_o
     kind[i] = k;
     leaf_of[i] = loc.found ? (loc.child & ~DT_LEAF) : DT_NONE;
 }
+__global__ void dt_locate_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_key, const uint8_t *__restrict__ keys,
+                                 const uint8_t *__restrict__ vals, const uint8_t *__restrict__ flags, uint64_t m,
+                                 uint8_t *__restrict__ kind, uint32_t *__restrict__ leaf_of) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) dt_locate_entry(t, trie_of_key, keys, vals, flags, i, kind, leaf_of);
+}
 
 // value changes of existing leaves; deleted leaves leave their parent's slot
-__global__ void dt_update_detach_kernel(DTrieDev t, const uint8_t *__restrict__ vals, const uint8_t *__restrict__ sroots,
-                                        uint64_t m, const uint8_t *__restrict__ kind, const uint32_t *__restrict__ leaf_of,
-                                        uint32_t *__restrict__ touched) {
-    if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
+static __device__ __forceinline__ void dt_update_detach_entry(const DTrieDev &t, const uint8_t *__restrict__ vals,
+                                                              const uint8_t *__restrict__ sroots, uint64_t i,
+                                                              const uint8_t *__restrict__ kind, const uint32_t *__restrict__ leaf_of,
+                                                              uint32_t *__restrict__ touched) {
     uint32_t x = leaf_of[i];
     if (kind[i] == DK_UPDATE) {
         dt_copy_val(t, x, vals + (uint64_t)t.val_stride * i);
@@ -294,6 +297,13 @@ __global__ void dt_update_detach_kernel(DTrieDev t, const uint8_t *__restrict__ 
         t.leaf_free[atomicAdd(&t.g[DG_LEAF_FREE], 1u)] = x;
         atomicSub(&t.g[DG_NLEAVES], 1u);
     }
+}
+__global__ void dt_update_detach_kernel(DTrieDev t, const uint8_t *__restrict__ vals, const uint8_t *__restrict__ sroots,
+                                        uint64_t m, const uint8_t *__restrict__ kind, const uint32_t *__restrict__ leaf_of,
+                                        uint32_t *__restrict__ touched) {
+    if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) dt_update_detach_entry(t, vals, sroots, i, kind, leaf_of, touched);
 }
 
 // ------------------------------------------------------------------------------------------------ collapse rounds
@@ -324,11 +334,9 @@ __global__ void dt_round_end_kernel(DTrieDev t, const uint32_t *__restrict__ lis
 // One round over the nodes that lost children.  ncur marks the members of this round; a node whose parent was a
 // member when the round began waits for the next round, so two acting nodes are never parent and child and every
 // word has one writer.
-__global__ void dt_collapse_round_kernel(DTrieDev t, const uint32_t *__restrict__ list, const uint32_t *__restrict__ count_p,
-                                         const uint8_t *__restrict__ defer, uint32_t *__restrict__ next, uint32_t *next_count) {
-    if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *count_p) return;
+static __device__ __forceinline__ void dt_collapse_entry(const DTrieDev &t, const uint32_t *__restrict__ list, uint32_t i,
+                                                         const uint8_t *__restrict__ defer, uint32_t *__restrict__ next,
+                                                         uint32_t *next_count) {
     uint32_t v = list[i];
     if (t.ndepth[v] == DT_DEAD) return;
     uint32_t gp = t.nparent[v];
@@ -362,19 +370,29 @@ __global__ void dt_collapse_round_kernel(DTrieDev t, const uint32_t *__restrict_
     }
     dt_free_node(t, v);
 }
+__global__ void dt_collapse_round_kernel(DTrieDev t, const uint32_t *__restrict__ list, const uint32_t *__restrict__ count_p,
+                                         const uint8_t *__restrict__ defer, uint32_t *__restrict__ next, uint32_t *next_count) {
+    if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < *count_p) dt_collapse_entry(t, list, i, defer, next, next_count);
+}
 
 // ------------------------------------------------------------------------------------------------ insert
 // attach[j] identifies where insert key j hangs in the structure left by the deletes: (parent << 4 | slot), or, at a
 // trie's root word, (1 << 63 | trie).  Keys with equal attach words are consecutive (same trie, same leading prefix).
-__global__ void dt_insert_locate_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_key, const uint8_t *__restrict__ keys,
-                                        const uint32_t *__restrict__ ins_idx, const uint32_t *__restrict__ n_ins_p,
-                                        uint64_t *__restrict__ attach) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= *n_ins_p) return;
+static __device__ __forceinline__ void dt_insert_locate_entry(const DTrieDev &t, const uint32_t *__restrict__ trie_of_key,
+                                                              const uint8_t *__restrict__ keys, const uint32_t *__restrict__ ins_idx,
+                                                              uint32_t j, uint64_t *__restrict__ attach) {
     const uint32_t i = ins_idx[j];
     const uint32_t trie = trie_of_key ? trie_of_key[i] : 0;
     DtLoc loc = dt_descend(t, trie, keys + 32 * (uint64_t)i);
     attach[j] = loc.parent == DT_NONE ? ((1ull << 63) | trie) : (((uint64_t)loc.parent << 4) | loc.slot);
+}
+__global__ void dt_insert_locate_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_key, const uint8_t *__restrict__ keys,
+                                        const uint32_t *__restrict__ ins_idx, const uint32_t *__restrict__ n_ins_p,
+                                        uint64_t *__restrict__ attach) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < *n_ins_p) dt_insert_locate_entry(t, trie_of_key, keys, ins_idx, j, attach);
 }
 
 // returns the id of the new leaf
@@ -431,15 +449,12 @@ static __device__ __forceinline__ uint32_t dt_insert_one(const DTrieDev &t, uint
 // time the keys just inserted have fanned the attach point out into up to 16 deeper ones per level — a run of r keys
 // needs ~log(r) rounds instead of r serial inserts (a new contract with 100k slots, a bulk load into an empty trie).
 // pending[j] = 1 for every entry that is still to be inserted; *leftover counts them.
-__global__ void dt_insert_runs_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_key, const uint8_t *__restrict__ keys,
-                                      const uint8_t *__restrict__ vals, const uint8_t *__restrict__ sroots,
-                                      const uint32_t *__restrict__ ins_idx, const uint32_t *__restrict__ n_ins_p,
-                                      const uint64_t *__restrict__ attach, uint32_t *__restrict__ leaf_of, uint32_t max_per_run,
-                                      uint8_t *__restrict__ pending, uint32_t *__restrict__ leftover) {
-    if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
-    const uint32_t n_ins = *n_ins_p;
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_ins) return;
+static __device__ __forceinline__ void dt_insert_run_entry(const DTrieDev &t, const uint32_t *__restrict__ trie_of_key,
+                                                           const uint8_t *__restrict__ keys, const uint8_t *__restrict__ vals,
+                                                           const uint8_t *__restrict__ sroots, const uint32_t *__restrict__ ins_idx,
+                                                           uint32_t n_ins, uint32_t j, const uint64_t *__restrict__ attach,
+                                                           uint32_t *__restrict__ leaf_of, uint32_t max_per_run,
+                                                           uint8_t *__restrict__ pending, uint32_t *__restrict__ leftover) {
     uint64_t a = attach[j];
     if (j && attach[j - 1] == a) return;  // not the head of its run
     const bool at_root = (a >> 63) != 0;
@@ -459,6 +474,127 @@ __global__ void dt_insert_runs_kernel(DTrieDev t, const uint32_t *__restrict__ t
         done++;
     }
     if (left) atomicAdd(leftover, left);
+}
+__global__ void dt_insert_runs_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_key, const uint8_t *__restrict__ keys,
+                                      const uint8_t *__restrict__ vals, const uint8_t *__restrict__ sroots,
+                                      const uint32_t *__restrict__ ins_idx, const uint32_t *__restrict__ n_ins_p,
+                                      const uint64_t *__restrict__ attach, uint32_t *__restrict__ leaf_of, uint32_t max_per_run,
+                                      uint8_t *__restrict__ pending, uint32_t *__restrict__ leftover) {
+    if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
+    const uint32_t n_ins = *n_ins_p;
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_ins) dt_insert_run_entry(t, trie_of_key, keys, vals, sroots, ins_idx, n_ins, j, attach, leaf_of, max_per_run, pending, leftover);
+}
+
+// ------------------------------------------------------------------------------------------------ fused restructure
+// Small blocks (the live path: a few hundred accounts, a few thousand slots) are latency-bound by launches and host round
+// trips, not by work.  One CTA runs the whole restructure — locate, update / detach, every collapse round, every insert
+// round — with __syncthreads where the multi-launch form has kernel boundaries and host-driven loops; the phase bodies
+// are the same device functions.  Ordered compaction (the insert lists must stay sorted) is a block-wide scan.
+template <int BLOCK>
+static __device__ __forceinline__ uint32_t dt_block_exclusive_scan(uint32_t v, uint32_t *sh /* BLOCK/32 + 1 */, uint32_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < BLOCK / 32 ? sh[lane] : 0, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t up = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += up;
+        }
+        if (lane < BLOCK / 32) sh[lane] = wi - w;  // exclusive offset of every warp
+        if (lane == 31) sh[BLOCK / 32] = wi;      // grand total
+    }
+    __syncthreads();
+    uint32_t res = sh[warp] + incl - v;
+    total = sh[BLOCK / 32];
+    __syncthreads();  // sh is reused by the next call
+    return res;
+}
+// dst[0 .. count) = the src entries (positions 0 .. n) whose flag is set, order kept; returns count
+template <int BLOCK, class FlagOf>
+static __device__ __forceinline__ uint32_t dt_block_compact(const uint32_t *src, bool identity, uint32_t n, FlagOf flag_of,
+                                                            uint32_t *dst, uint32_t *sh) {
+    uint32_t base = 0;
+    for (uint32_t lo = 0; lo < n; lo += BLOCK) {
+        uint32_t j = lo + threadIdx.x;
+        uint32_t f = j < n && flag_of(j) ? 1u : 0u, total;
+        uint32_t pos = dt_block_exclusive_scan<BLOCK>(f, sh, total);
+        if (f) dst[base + pos] = identity ? j : src[j];
+        base += total;
+    }
+    __syncthreads();
+    return base;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) dt_restructure_fused_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_key,
+                                                                    const uint8_t *__restrict__ keys, const uint8_t *__restrict__ vals,
+                                                                    const uint8_t *__restrict__ flags, const uint8_t *__restrict__ sroots,
+                                                                    uint32_t m, uint8_t *__restrict__ kind, uint32_t *__restrict__ leaf_of,
+                                                                    uint32_t *list_a, uint32_t *list_b, uint8_t *__restrict__ defer,
+                                                                    uint32_t *idx_a, uint32_t *idx_b, uint64_t *__restrict__ attach,
+                                                                    uint8_t *__restrict__ pending, uint32_t max_per_run) {
+    __shared__ uint32_t sh[BLOCK / 32 + 1];
+    __shared__ uint32_t s_count;
+    const uint32_t tid = threadIdx.x;
+    // ---- locate
+    for (uint32_t i = tid; i < m; i += BLOCK) dt_locate_entry(t, trie_of_key, keys, vals, flags, i, kind, leaf_of);
+    __syncthreads();
+    if (*(volatile int *)t.err != B200_DEVERR_NONE) return;  // uniform: every thread reads the same word after the barrier
+    // ---- value updates, detach deleted leaves
+    for (uint32_t i = tid; i < m; i += BLOCK) dt_update_detach_entry(t, vals, sroots, i, kind, leaf_of, list_a);
+    __syncthreads();
+    // ---- collapse rounds
+    uint32_t *cur = list_a, *next = list_b;
+    uint32_t *cnt_cur = t.g + DG_LIST_A, *cnt_next = t.g + DG_LIST_B;
+    for (int round = 0; round < 256; round++) {
+        const uint32_t n = *(volatile uint32_t *)cnt_cur;
+        if (n == 0) break;
+        if (tid == 0) *cnt_next = 0;
+        for (uint32_t e = tid; e < n; e += BLOCK) {
+            uint32_t v = cur[e];
+            t.ncur[v] = 1;
+            t.nnext[v] = 0;
+        }
+        __syncthreads();
+        for (uint32_t e = tid; e < n; e += BLOCK) {
+            uint32_t v = cur[e];
+            uint32_t gp = t.ndepth[v] == DT_DEAD ? DT_NONE : t.nparent[v];
+            defer[e] = (gp != DT_NONE && t.ncur[gp]) ? 1 : 0;
+        }
+        __syncthreads();
+        for (uint32_t e = tid; e < n; e += BLOCK) dt_collapse_entry(t, cur, e, defer, next, cnt_next);
+        __syncthreads();
+        for (uint32_t e = tid; e < n; e += BLOCK) t.ncur[cur[e]] = 0;
+        __syncthreads();
+        uint32_t *tp = cur; cur = next; next = tp;
+        uint32_t *tc = cnt_cur; cnt_cur = cnt_next; cnt_next = tc;
+    }
+    __syncthreads();
+    if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
+    // ---- inserts, in rounds
+    uint32_t n_ins = dt_block_compact<BLOCK>(nullptr, true, m, [&](uint32_t j) { return kind[j] == DK_INSERT; }, idx_a, sh);
+    uint32_t *icur = idx_a, *inext = idx_b;
+    for (int round = 0; round < 128 && n_ins; round++) {
+        if (tid == 0) s_count = 0;
+        for (uint32_t j = tid; j < n_ins; j += BLOCK) dt_insert_locate_entry(t, trie_of_key, keys, icur, j, attach);
+        __syncthreads();
+        for (uint32_t j = tid; j < n_ins; j += BLOCK)
+            dt_insert_run_entry(t, trie_of_key, keys, vals, sroots, icur, n_ins, j, attach, leaf_of, max_per_run, pending, &s_count);
+        __syncthreads();
+        if (s_count == 0) break;
+        n_ins = dt_block_compact<BLOCK>(icur, false, n_ins, [&](uint32_t j) { return pending[j] != 0; }, inext, sh);
+        uint32_t *tp = icur; icur = inext; inext = tp;
+    }
+    if (tid == 0) t.g[DG_NINSERT] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ mark + wavefront

@@ -34,6 +34,15 @@ cudaError_t launch_dt_collapse_round(const DTrieDev &t, const uint32_t *list, co
     dt_round_end_kernel<<<blocks, 128, 0, st>>>(t, list, count_p);
     return cudaGetLastError();
 }
+// the whole restructure of a small block in one CTA (dt_restructure_fused_kernel)
+cudaError_t launch_dt_restructure_fused(const DTrieDev &t, const uint32_t *trie_of_key, const uint8_t *keys, const uint8_t *vals,
+                                        const uint8_t *flags, const uint8_t *sroots, uint32_t m, uint8_t *kind, uint32_t *leaf_of,
+                                        uint32_t *list_a, uint32_t *list_b, uint8_t *defer, uint32_t *idx_a, uint32_t *idx_b,
+                                        uint64_t *attach, uint8_t *pending, uint32_t max_per_run, cudaStream_t st) {
+    dt_restructure_fused_kernel<1024><<<1, 1024, 0, st>>>(t, trie_of_key, keys, vals, flags, sroots, m, kind, leaf_of, list_a, list_b,
+                                                         defer, idx_a, idx_b, attach, pending, max_per_run);
+    return cudaGetLastError();
+}
 // one insertion round: attach points of the (remaining) insert entries, then at most max_per_run keys per run
 cudaError_t launch_dt_insert(const DTrieDev &t, const uint32_t *trie_of_key, const uint8_t *keys, const uint8_t *vals,
                              const uint8_t *sroots, const uint32_t *ins_idx, const uint32_t *n_ins_p, uint64_t max_ins,

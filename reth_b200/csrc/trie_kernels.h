@@ -225,4 +225,9 @@ cudaError_t launch_dt_proof_write(const DTrieDev &t, const uint32_t *trie_of_tar
                                   uint8_t *node_depth, cudaStream_t st);
 cudaError_t launch_dt_find_leaf(const DTrieDev &t, const uint8_t *key, uint32_t *out, uint64_t n_copies, cudaStream_t st);
 
+cudaError_t launch_dt_restructure_fused(const DTrieDev &t, const uint32_t *trie_of_key, const uint8_t *keys, const uint8_t *vals,
+                                        const uint8_t *flags, const uint8_t *sroots, uint32_t m, uint8_t *kind, uint32_t *leaf_of,
+                                        uint32_t *list_a, uint32_t *list_b, uint8_t *defer, uint32_t *idx_a, uint32_t *idx_b,
+                                        uint64_t *attach, uint8_t *pending, uint32_t max_per_run, cudaStream_t st);
+
 }  // namespace b200

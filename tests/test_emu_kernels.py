@@ -25,12 +25,14 @@ def test_cuda_sources_pass_parity_under_cpu_emulation():
 
 
 def test_dynamic_tries_two_stage_rehash_under_cpu_emulation():
-    """The dynamic tries again with the thread-per-seed + warp-climb re-hash forced for every block size
-    (B200_DT_TWO_STAGE_MIN=0; by default only dirty sets above 4096 entries take it)."""
+    """The dynamic tries again on their large-block code paths, forced for every block size: the multi-launch restructure
+    (B200_DT_FUSED_MAX=0; by default blocks up to 8192 entries are restructured by one CTA) and the thread-per-seed +
+    warp-climb re-hash (B200_DT_TWO_STAGE_MIN=0; by default only dirty sets above 4096 entries take it)."""
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_dtrie.py", "tests/test_gpu_dstate.py", "-m", "gpu",
                         "--emu", "-q", "-x", "-p", "no:cacheprovider", "-k",
                         "random_blocks or shrink or clustered or sharded_state_matches or new_contract or lifecycle"],
-                       cwd=ROOT, capture_output=True, text=True, timeout=1500, env=dict(os.environ, B200_DT_TWO_STAGE_MIN="0"))
+                       cwd=ROOT, capture_output=True, text=True, timeout=1500,
+                       env=dict(os.environ, B200_DT_TWO_STAGE_MIN="0", B200_DT_FUSED_MAX="0"))
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout, tail

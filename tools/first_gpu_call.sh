@@ -9,8 +9,8 @@ export B200_DTRIE_ON_GPU=1
 {
   echo "== gated GPU tests"
   timeout 600 python -m pytest tests/test_gpu_dtrie.py tests/test_gpu_dstate.py tests/test_gpu_proofs.py -m gpu -q -x 2>&1 | tail -15
-  echo "== the same with the two-stage re-hash forced"
-  B200_DT_TWO_STAGE_MIN=0 timeout 600 python -m pytest tests/test_gpu_dtrie.py tests/test_gpu_dstate.py -m gpu -q -x 2>&1 | tail -5
+  echo "== the same on the large-block paths (multi-launch restructure, two-stage re-hash) forced"
+  B200_DT_TWO_STAGE_MIN=0 B200_DT_FUSED_MAX=0 timeout 600 python -m pytest tests/test_gpu_dtrie.py tests/test_gpu_dstate.py -m gpu -q -x 2>&1 | tail -5
   echo "== C++ host mirror incl. DynamicTrie"
   timeout 300 python -m pytest tests/test_cpp_host.py -m gpu -q 2>&1 | tail -3
   echo "== compute-sanitizer on the smallest dynamic test (racecheck is the point: emulation cannot see races)"
