@@ -26,6 +26,7 @@ struct DArena {
     DevBuf kind, leaf_of, list_a, list_b, ins_idx, attach, seeds, built, removed, freed_now, flags, nh, sel, prefix, pick, out;
     // outcome of the last apply
     uint32_t n_built = 0, n_removed = 0;
+    bool marked = false;  // the last restructure also marked the dirty paths (fused small-block form)
     uint32_t val_stride() const { return account ? 72u : 32u; }
 };
 
@@ -241,8 +242,10 @@ static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const ui
                                        static_cast<uint32_t *>(a->sel.p), static_cast<uint64_t *>(a->attach.p),
                                        static_cast<uint8_t *>(a->nh.p), 8, st));
         c->launches++;
+        a->marked = true;
         return B200_OK;
     }
+    a->marked = false;
     // ---- locate, value updates, detach deleted leaves
     CU(launch_dt_locate(d, d_trie_of_key, d_keys, d_vals, d_flags, m, kind, leaf_of, st));
     uint32_t *list_cur = static_cast<uint32_t *>(a->list_a.p), *list_next = static_cast<uint32_t *>(a->list_b.p);
@@ -330,7 +333,8 @@ static int32_t da_rehash(DArena *a, uint64_t m) {
         CU(cudaMemsetAsync(handoff_count, 0, 4, c->stream));
     }
     DTrieDev d = da_view(a);
-    CU(launch_dt_rehash(d, max_seeds, handoff, handoff_count, (a->forest && !a->account) ? 0 : 3, c->stream));
+    CU(launch_dt_rehash(d, max_seeds, handoff, handoff_count, (a->forest && !a->account) ? 0 : 3, a->marked, c->stream));
+    a->marked = false;
     CU(launch_dt_finish(d, (uint32_t)m + 16, c->stream));
     c->launches += 5;
     return B200_OK;

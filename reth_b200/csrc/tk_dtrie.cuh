@@ -486,11 +486,58 @@ __global__ void dt_insert_runs_kernel(DTrieDev t, const uint32_t *__restrict__ t
     if (j < n_ins) dt_insert_run_entry(t, trie_of_key, keys, vals, sroots, ins_idx, n_ins, j, attach, leaf_of, max_per_run, pending, leftover);
 }
 
+// ------------------------------------------------------------------------------------------------ mark + wavefront
+static __device__ __forceinline__ bool dt_alive(const DTrieDev &t, uint32_t word) {
+    return (word & DT_LEAF) ? t.lmeta[word & ~DT_LEAF] != DT_DEAD : t.ndepth[word] != DT_DEAD;
+}
+static __device__ __forceinline__ uint32_t dt_parent_of(const DTrieDev &t, uint32_t word) {
+    return (word & DT_LEAF) ? t.lparent[word & ~DT_LEAF] : t.nparent[word];
+}
+
+// pending[p] = number of dirty children of p.  A walk stops at the first ancestor somebody already reached, and at a
+// seed (which walks on its own behalf).
+static __device__ __forceinline__ void dt_mark_entry(const DTrieDev &t, uint32_t i) {
+    uint32_t s = t.seeds[i];
+    if (!dt_alive(t, s)) return;
+    uint32_t p = dt_parent_of(t, s);
+    for (int hops = 0; p != DT_NONE; hops++) {
+        if (hops > DT_MAX_HOPS) {
+            atomicExch(t.err, B200_DEVERR_CORRUPT);
+            break;
+        }
+        if (atomicAdd(&t.npending[p], 1u) != 0u) break;
+        if (t.nseed[p]) break;
+        p = t.nparent[p];
+    }
+}
+__global__ void dt_mark_kernel(DTrieDev t, const uint32_t *__restrict__ count_p) {
+    if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < *count_p) dt_mark_entry(t, i);
+}
+
+// After marking: clears the seed flags and keeps only the wavefront's starting points in the list — live leaves, and
+// live nodes without a dirty child (a seed node that has dirty children is re-hashed by the last of them to arrive).
+static __device__ __forceinline__ void dt_starts_entry(const DTrieDev &t, uint32_t i) {
+    uint32_t s = t.seeds[i];
+    if (s & DT_LEAF) {
+        t.lseed[s & ~DT_LEAF] = 0;
+        if (t.lmeta[s & ~DT_LEAF] == DT_DEAD) t.seeds[i] = DT_NONE;
+    } else {
+        t.nseed[s] = 0;
+        if (t.ndepth[s] == DT_DEAD || t.npending[s] != 0u) t.seeds[i] = DT_NONE;
+    }
+}
+__global__ void dt_starts_kernel(DTrieDev t, const uint32_t *__restrict__ count_p) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < *count_p) dt_starts_entry(t, i);
+}
+
 // ------------------------------------------------------------------------------------------------ fused restructure
 // Small blocks (the live path: a few hundred accounts, a few thousand slots) are latency-bound by launches and host round
 // trips, not by work.  One CTA runs the whole restructure — locate, update / detach, every collapse round, every insert
-// round — with __syncthreads where the multi-launch form has kernel boundaries and host-driven loops; the phase bodies
-// are the same device functions.  Ordered compaction (the insert lists must stay sorted) is a block-wide scan.
+// round, then mark / starts — with __syncthreads where the multi-launch form has kernel boundaries and host-driven
+// loops; the phase bodies are the same device functions.  Ordered compaction (the insert lists must stay sorted) is a block-wide scan.
 template <int BLOCK>
 static __device__ __forceinline__ uint32_t dt_block_exclusive_scan(uint32_t v, uint32_t *sh /* BLOCK/32 + 1 */, uint32_t &total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -594,50 +641,13 @@ __global__ void __launch_bounds__(BLOCK) dt_restructure_fused_kernel(DTrieDev t,
         n_ins = dt_block_compact<BLOCK>(icur, false, n_ins, [&](uint32_t j) { return pending[j] != 0; }, inext, sh);
         uint32_t *tp = icur; icur = inext; inext = tp;
     }
-    if (tid == 0) t.g[DG_NINSERT] = 0;
-}
-
-// ------------------------------------------------------------------------------------------------ mark + wavefront
-static __device__ __forceinline__ bool dt_alive(const DTrieDev &t, uint32_t word) {
-    return (word & DT_LEAF) ? t.lmeta[word & ~DT_LEAF] != DT_DEAD : t.ndepth[word] != DT_DEAD;
-}
-static __device__ __forceinline__ uint32_t dt_parent_of(const DTrieDev &t, uint32_t word) {
-    return (word & DT_LEAF) ? t.lparent[word & ~DT_LEAF] : t.nparent[word];
-}
-
-// pending[p] = number of dirty children of p.  A walk stops at the first ancestor somebody already reached, and at a
-// seed (which walks on its own behalf).
-__global__ void dt_mark_kernel(DTrieDev t, const uint32_t *__restrict__ count_p) {
+    __syncthreads();
+    // ---- mark the dirty paths and pick the wavefront's starting points (dt_mark_kernel / dt_starts_kernel)
     if (*(volatile int *)t.err != B200_DEVERR_NONE) return;
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *count_p) return;
-    uint32_t s = t.seeds[i];
-    if (!dt_alive(t, s)) return;
-    uint32_t p = dt_parent_of(t, s);
-    for (int hops = 0; p != DT_NONE; hops++) {
-        if (hops > DT_MAX_HOPS) {
-            atomicExch(t.err, B200_DEVERR_CORRUPT);
-            break;
-        }
-        if (atomicAdd(&t.npending[p], 1u) != 0u) break;
-        if (t.nseed[p]) break;
-        p = t.nparent[p];
-    }
-}
-
-// After marking: clears the seed flags and keeps only the wavefront's starting points in the list — live leaves, and
-// live nodes without a dirty child (a seed node that has dirty children is re-hashed by the last of them to arrive).
-__global__ void dt_starts_kernel(DTrieDev t, const uint32_t *__restrict__ count_p) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *count_p) return;
-    uint32_t s = t.seeds[i];
-    if (s & DT_LEAF) {
-        t.lseed[s & ~DT_LEAF] = 0;
-        if (t.lmeta[s & ~DT_LEAF] == DT_DEAD) t.seeds[i] = DT_NONE;
-    } else {
-        t.nseed[s] = 0;
-        if (t.ndepth[s] == DT_DEAD || t.npending[s] != 0u) t.seeds[i] = DT_NONE;
-    }
+    const uint32_t n_seeds = *(volatile uint32_t *)(t.g + DG_SEEDS);
+    for (uint32_t e = tid; e < n_seeds; e += BLOCK) dt_mark_entry(t, e);
+    __syncthreads();
+    for (uint32_t e = tid; e < n_seeds; e += BLOCK) dt_starts_entry(t, e);
 }
 
 // One warp builds node v from its 16 child slots (lane = nibble).  All 32 lanes must call.

@@ -61,12 +61,14 @@ __global__ void dt_finish_kernel(DTrieDev t) {
 }
 // handoff != nullptr selects the two-stage form (thread per seed below split_depth's levels, warps above)
 cudaError_t launch_dt_rehash(const DTrieDev &t, uint32_t max_seeds, uint32_t *handoff, uint32_t *handoff_count, int split_depth,
-                             cudaStream_t st) {
+                             bool already_marked, cudaStream_t st) {
     constexpr int WARPS = 4;
     const uint32_t *count_p = t.g + DG_SEEDS;
     unsigned blocks = blocks_for(max_seeds, 128);
-    dt_mark_kernel<<<blocks, 128, 0, st>>>(t, count_p);
-    dt_starts_kernel<<<blocks, 128, 0, st>>>(t, count_p);
+    if (!already_marked) {  // (the fused restructure of a small block has done both)
+        dt_mark_kernel<<<blocks, 128, 0, st>>>(t, count_p);
+        dt_starts_kernel<<<blocks, 128, 0, st>>>(t, count_p);
+    }
     unsigned cap = (unsigned)sms() * 16;
     if (handoff == nullptr) {
         unsigned wblocks = blocks_for(max_seeds, WARPS);
