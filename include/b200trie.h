@@ -244,6 +244,25 @@ B200_API int32_t b200_subtrie_frontier_dev(b200_ctx *, const void *d_acct_keys32
 B200_API int32_t b200_root_from_frontier(b200_ctx *, const b200_frontier_entry frontier[16], uint8_t root32[32]);
 B200_API int32_t b200_root_from_frontier_dev(b200_ctx *, const void *d_frontier, void *d_root32);
 
+/* ------------------------------------------------------------------------------------------------ ordered roots
+ * Transactions / receipts / withdrawals roots of a batch of lists in one call: what
+ * OrderedTrieRootEncodedBuilder::finalize (crates/trie/common/src/ordered_root.rs:240-257) and alloy's
+ * ordered_trie_root_with_encoder behind proofs::calculate_{transaction,receipt,withdrawals}_root
+ * (crates/ethereum/evm/src/build.rs:56-68, crates/ethereum/consensus/src/validation.rs:108,
+ * crates/consensus/common/src/validation.rs:59) return, for pre-encoded items.
+ * List l holds items seg_offsets[l] .. seg_offsets[l+1] in list (execution) order; item i is the byte string
+ * values[value_offsets[i] .. value_offsets[i+1]) — the EIP-2718 encoding the reference's encoder closure writes.
+ * Keys (rlp(index)) and their insertion order are derived on the device.  Empty list -> EMPTY_ROOT_HASH.
+ * roots32: n_lists*32.  At most 2^31-1 items per call, each below 2 GiB. */
+B200_API int32_t b200_ordered_roots(b200_ctx *, const uint8_t *values, const uint64_t *value_offsets,
+                                    const uint64_t *seg_offsets, uint64_t n_lists, uint8_t *roots32,
+                                    b200_stats *opt_stats);
+/* Device-resident variant (all pointers device pointers; d_values 8-byte aligned for the fast path, any alignment
+ * accepted; values_len = bytes readable at d_values).  Violations are reported by the next b200_sync. */
+B200_API int32_t b200_ordered_roots_dev(b200_ctx *, const void *d_values, uint64_t values_len,
+                                        const void *d_value_offsets, const void *d_seg_offsets, uint64_t n_lists,
+                                        uint64_t n_items, void *d_roots32);
+
 /* ------------------------------------------------------------------------------------------------ resident trie
  * Incremental state root (BASELINE config 5; reth: StateRoot::with_prefix_sets over stored branch nodes,
  * crates/trie/trie/src/walker.rs:172-202, node_iter.rs:205-300, DatabaseStateRoot::incremental_root_with_updates

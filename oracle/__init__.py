@@ -27,7 +27,7 @@ EMPTY_ROOT_HASH = bytes.fromhex("56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc
 
 def build(force: bool = False) -> str:
     """Compile liboracle.so with gcc (oracle/Makefile)."""
-    srcs = [os.path.join(_HERE, f) for f in ("keccak.c", "keccak_avx512.c", "hash_builder.c", "state_root.c", "oracle.h",
+    srcs = [os.path.join(_HERE, f) for f in ("keccak.c", "keccak_avx512.c", "hash_builder.c", "state_root.c", "ordered_root.c", "oracle.h",
                                              "Makefile")]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
@@ -109,6 +109,7 @@ def lib():
         L.orc_state_root_full.argtypes = [u8p, vp, C.c_uint64, u8p, u8p, u64p, u8p,
                                           C.POINTER(_Updates), C.POINTER(_Updates), C.c_int]
         L.orc_trie_root_recursive.argtypes = [u8p, u8p, u64p, C.c_uint64, u8p]
+        L.orc_ordered_roots.argtypes = [u8p, u64p, u64p, C.c_uint64, u8p]
         L.orc_stats_reset.argtypes = []
         L.orc_stats_get.argtypes = [C.POINTER(_Stats)]
         _lib = L
@@ -278,6 +279,33 @@ def storage_roots(slot_keys, values, seg_offsets, want_updates=False, threads=1)
     if rc:
         raise ValueError(f"orc_storage_roots rc={rc}")
     return (roots, _updates_to_py(u)) if want_updates else roots
+
+
+def pack_lists(lists):
+    """[[bytes, ...], ...] -> (values blob u8, value_offsets u64 [n+1], seg_offsets u64 [n_lists+1])."""
+    items = [it for l in lists for it in l]
+    value_offsets = np.zeros(len(items) + 1, np.uint64)
+    if items:
+        value_offsets[1:] = np.cumsum([len(it) for it in items], dtype=np.uint64)
+    seg_offsets = np.zeros(len(lists) + 1, np.uint64)
+    if lists:
+        seg_offsets[1:] = np.cumsum([len(l) for l in lists], dtype=np.uint64)
+    values = np.frombuffer(b"".join(items), np.uint8).copy() if items else np.zeros(0, np.uint8)
+    return values, value_offsets, seg_offsets
+
+
+def ordered_roots(values, value_offsets, seg_offsets) -> np.ndarray:
+    """Transactions / receipts / withdrawals roots of lists of pre-encoded items (ordered_root.rs:202-257)."""
+    values = _c(values)
+    value_offsets = _c(value_offsets, np.uint64)
+    seg_offsets = _c(seg_offsets, np.uint64)
+    m = len(seg_offsets) - 1
+    roots = np.empty((m, 32), np.uint8)
+    keep = values if len(values) else np.zeros(1, np.uint8)
+    rc = lib().orc_ordered_roots(_p(keep), _p(value_offsets), _p(seg_offsets), m, _p(roots))
+    if rc:
+        raise ValueError(f"orc_ordered_roots rc={rc}")
+    return roots
 
 
 def state_root(acct_keys, accounts, storage_roots32=None, want_updates=False):

@@ -120,6 +120,12 @@ int orc_state_root_full(const uint8_t *acct_keys32, const orc_account *accts, ui
 int orc_trie_root_recursive(const uint8_t *keys32, const uint8_t *values, const uint64_t *value_offsets,
                             uint64_t n, uint8_t root32[32]);
 
+/* Ordered (index-keyed) trie roots of n_lists lists of pre-encoded items: list l = items seg_offsets[l] ..
+ * seg_offsets[l+1] in list order, item i = values[value_offsets[i] .. value_offsets[i+1])
+ * (crates/trie/common/src/ordered_root.rs:202-257). */
+int orc_ordered_roots(const uint8_t *values, const uint64_t *value_offsets, const uint64_t *seg_offsets,
+                      uint64_t n_lists, uint8_t *roots32);
+
 /* Structure statistics of the last orc_state_root/orc_storage_roots call on this thread. */
 typedef struct {
     uint64_t leaves, branch_nodes, extension_nodes, hashed_nodes, keccak_f, rlp_bytes_hashed;

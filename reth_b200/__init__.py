@@ -13,3 +13,5 @@ from .trie import (BranchNodeCompact, DynamicStateRoot, ParallelStateRoot, Resid
                    StorageRoot, StorageTrieUpdates, TrieUpdates)
 from .sharded import ShardedDynamicStateRoot  # noqa: F401,E402
 from .verify import Verifier  # noqa: F401,E402
+from .ordered_root import (OrderedRootError, OrderedTrieRootEncodedBuilder, ordered_trie_root_encoded,  # noqa: F401,E402
+                           ordered_trie_roots)

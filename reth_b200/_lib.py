@@ -137,6 +137,8 @@ def load():
     sig("b200_storage_roots_dev", i32, vp, vp, vp, vp, u64, u64, vp)
     sig("b200_state_root_dev", i32, vp, vp, vp, vp, u64, vp)
     sig("b200_state_root_full_dev", i32, vp, vp, vp, u64, vp, vp, vp, u64, vp)
+    sig("b200_ordered_roots", i32, vp, vp, vp, vp, u64, vp, PS)
+    sig("b200_ordered_roots_dev", i32, vp, vp, u64, vp, vp, u64, u64, vp)
     sig("b200_dev_status", i32, vp)
     sig("b200_last_stats", i32, vp, PS)
     sig("b200_subtrie_frontier", i32, vp, vp, vp, u64, vp, vp, vp, C.POINTER(FrontierEntry), PS)

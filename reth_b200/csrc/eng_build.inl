@@ -15,10 +15,10 @@ struct Built {
 
 // Builds every trie of a forest over d_keys (n leaves).  d_seg_offsets == nullptr: one trie.
 // account: leaves are accounts (d_values = b200_account[n], d_sroots = storage roots or null); else storage
-// slots (d_values = U256 BE [n][32]).
+// slots (d_values = U256 BE [n][32]).  ordered != nullptr: leaves of index-keyed tries (eng_ordered.inl).
 static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, const uint64_t *d_seg_offsets,
                             uint64_t n_segs, bool account, const uint8_t *d_values, const uint8_t *d_sroots,
-                            bool retain_updates, Built &out) {
+                            bool retain_updates, Built &out, const OrderedLeavesDev *ordered = nullptr) {
     if (n >= (1ull << 31)) return fail(c, B200_ERR_INVALID_ARG, "at most 2^31-1 leaves per build");
     cudaStream_t st = c->stream;
     ForestDev &f = out.f;
@@ -50,7 +50,8 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
         c->launches++;
     }
     CU(launch_lcp(d_keys, n, f.Lp, f.nibs, f.err, st));
-    CU(launch_leaves(f, account, d_values, d_sroots, st));
+    if (ordered) CU(launch_ordered_leaves(f, *ordered, st));  // index-keyed tries: variable-length keys and values
+    else CU(launch_leaves(f, account, d_values, d_sroots, st));
     c->launches += 2;
     if (n < 2) return B200_OK;
 

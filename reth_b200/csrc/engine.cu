@@ -84,7 +84,8 @@ extern "C" B200_API void b200_destroy(b200_ctx *c) {
                       &c->upd_flags, &c->upd_nh, &c->upd_ids, &c->upd_prefix, &c->in_a, &c->in_b, &c->in_c,
                       &c->in_d, &c->in_e, &c->out_a, &c->chunk_in[0], &c->chunk_in[1], &c->chunk_in[2], &c->chunk_out[0],
                       &c->chunk_out[1], &c->chunk_out[2], &c->sort_ka, &c->sort_kb, &c->sort_ia, &c->sort_flag, &c->sort_perm,
-                      &c->sort_out, &c->node_key, &c->node_key2, &c->node_ids, &c->node_order};
+                      &c->sort_out, &c->node_key, &c->node_key2, &c->node_ids, &c->node_order, &c->ord_keys, &c->ord_knib,
+                      &c->ord_item};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->pinned_small) cudaFreeHost(c->pinned_small);
@@ -200,3 +201,4 @@ extern "C" B200_API uint64_t b200_launch_count(const b200_ctx *c) { return c ? c
 #include "eng_dtrie.inl"
 #include "eng_dstate.inl"
 #include "eng_proofs.inl"
+#include "eng_ordered.inl"

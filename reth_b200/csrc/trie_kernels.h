@@ -131,6 +131,18 @@ cudaError_t launch_stored_flags_subset(const ForestDev &f, const uint32_t *ids, 
 cudaError_t launch_pick_subset(const uint32_t *ids, const uint32_t *prefix, const uint32_t *sel_pos, uint32_t n_sel,
                                uint32_t *out_ids, uint32_t *out_prefix, cudaStream_t st);
 
+// ------------------------------------------------------------------------------------------------ ordered tries (tk_ordered.cuh)
+struct OrderedLeavesDev {
+    const uint8_t *key_nibs;  // [n] true key length in nibbles (the padded keys are ForestDev::keys)
+    const uint32_t *item;     // [n] item (in list order) carried by the leaf at this sorted position
+    const uint8_t *values;    // concatenated pre-encoded items
+    const uint64_t *val_off;  // [n+1] byte offsets of the items in `values`
+    uint64_t blob_len;
+};
+cudaError_t launch_ordered_keys(const uint64_t *d_seg_offsets, uint64_t n_segs, uint64_t n, uint8_t *keys, uint8_t *key_nibs,
+                                uint32_t *item, int *err, cudaStream_t st);
+cudaError_t launch_ordered_leaves(const ForestDev &f, const OrderedLeavesDev &o, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------------ dynamic trie (tk_dtrie.cuh)
 constexpr uint32_t DT_NONE = 0xFFFFFFFFu;
 constexpr uint32_t DT_LEAF = 0x80000000u;

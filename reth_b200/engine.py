@@ -192,6 +192,38 @@ class Engine:
             res.append(s.as_dict())
         return res[0] if len(res) == 1 else tuple(res)
 
+    def ordered_roots(self, values, value_offsets, seg_offsets, want_stats=False):
+        """Transactions / receipts / withdrawals roots of a batch of lists of pre-encoded items — what
+        OrderedTrieRootEncodedBuilder::finalize returns per list (crates/trie/common/src/ordered_root.rs:240-257).
+        List l = items seg_offsets[l] .. seg_offsets[l+1] in list order; item i = values[value_offsets[i] ..
+        value_offsets[i+1]).  -> roots [n_lists][32]."""
+        values = _np(values).reshape(-1)
+        value_offsets = _np(value_offsets, np.uint64)
+        seg_offsets = _np(seg_offsets, np.uint64)
+        m = len(seg_offsets) - 1
+        if m < 0 or len(value_offsets) < 1:
+            raise ValueError("seg_offsets / value_offsets need at least one entry")
+        if int(seg_offsets[-1]) != len(value_offsets) - 1:
+            raise ValueError("value_offsets must have seg_offsets[-1] + 1 entries")
+        if int(value_offsets[-1]) > len(values):
+            raise ValueError("value_offsets run past the end of values")
+        roots = np.empty((m, 32), np.uint8)
+        s = Stats()
+        self._check(self.lib.b200_ordered_roots(self.ctx, _ptr(values) if len(values) else None, _ptr(value_offsets),
+                                                _ptr(seg_offsets), m, _ptr(roots), C.byref(s)))
+        return (roots, s.as_dict()) if want_stats else roots
+
+    def ordered_root(self, items, want_stats=False):
+        """Root of one list of pre-encoded items (bytes objects) — calculate_transaction_root / calculate_receipt_root /
+        calculate_withdrawals_root over their EIP-2718 encodings."""
+        items = list(items)
+        value_offsets = np.zeros(len(items) + 1, np.uint64)
+        if items:
+            value_offsets[1:] = np.cumsum([len(it) for it in items], dtype=np.uint64)
+        values = np.frombuffer(b"".join(items), np.uint8) if items else np.zeros(0, np.uint8)
+        r = self.ordered_roots(values, value_offsets, np.array([0, len(items)], np.uint64), want_stats=want_stats)
+        return (r[0][0].tobytes(), r[1]) if want_stats else r[0].tobytes()
+
     def state_root(self, acct_keys, accounts, storage_roots32=None, want_updates=False, want_stats=False):
         acct_keys = _np(acct_keys).reshape(-1, 32)
         accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
@@ -277,6 +309,11 @@ class Engine:
     def storage_roots_dev(self, t_keys, t_vals, t_offs, n_accounts: int, n_slots: int, t_roots):
         self._check(self.lib.b200_storage_roots_dev(self.ctx, t_keys.data_ptr(), t_vals.data_ptr(), t_offs.data_ptr(),
                                                     n_accounts, n_slots, t_roots.data_ptr()))
+
+    def ordered_roots_dev(self, t_values, t_value_offsets, t_seg_offsets, n_lists: int, n_items: int, t_roots):
+        self._check(self.lib.b200_ordered_roots_dev(self.ctx, t_values.data_ptr(), t_values.numel() * t_values.element_size(),
+                                                    t_value_offsets.data_ptr(), t_seg_offsets.data_ptr(), n_lists, n_items,
+                                                    t_roots.data_ptr()))
 
     def state_root_dev(self, t_keys, t_accts, t_sroots, n: int, t_root):
         self._check(self.lib.b200_state_root_dev(self.ctx, t_keys.data_ptr(), t_accts.data_ptr(),

@@ -684,4 +684,86 @@ class ParallelStateRoot : public StateRoot {
     std::pair<B256, TrieUpdates> incremental_root_with_updates() const { return root_with_updates(); }
 };
 
+// ------------------------------------------------------------------------------------------------ ordered roots
+/// OrderedRootError — crates/trie/common/src/ordered_root.rs:9-80.
+struct OrderedRootError : std::runtime_error {
+    enum Kind { Incomplete, IndexOutOfBounds, DuplicateIndex } kind;
+    size_t expected = 0, received = 0, idx = 0, len = 0;
+    OrderedRootError(Kind k, std::string msg) : std::runtime_error(std::move(msg)), kind(k) {}
+    static OrderedRootError incomplete(size_t expected, size_t received) {
+        OrderedRootError e(Incomplete, "incomplete: expected " + std::to_string(expected) + " items, received " + std::to_string(received));
+        e.expected = expected;
+        e.received = received;
+        return e;
+    }
+    static OrderedRootError out_of_bounds(size_t index, size_t len) {
+        OrderedRootError e(IndexOutOfBounds, "index " + std::to_string(index) + " out of bounds for length " + std::to_string(len));
+        e.idx = index;
+        e.len = len;
+        return e;
+    }
+    static OrderedRootError duplicate(size_t index) {
+        OrderedRootError e(DuplicateIndex, "duplicate item at index " + std::to_string(index));
+        e.idx = index;
+        return e;
+    }
+    bool is_incomplete() const { return kind == Incomplete; }
+    bool is_index_out_of_bounds() const { return kind == IndexOutOfBounds; }
+    bool is_duplicate_index() const { return kind == DuplicateIndex; }
+    std::optional<size_t> index() const { return kind == Incomplete ? std::nullopt : std::optional<size_t>(idx); }
+};
+
+/// Roots of many lists of pre-encoded items in one device call — alloy_trie::root::ordered_trie_root_encoded per list
+/// (the transactions / receipts / withdrawals roots of a batch of blocks; b200_ordered_roots).
+inline std::vector<B256> ordered_trie_roots(const Engine &e, const std::vector<std::vector<std::vector<uint8_t>>> &lists) {
+    std::vector<uint64_t> seg{0}, off{0};
+    std::vector<uint8_t> blob;
+    for (const auto &l : lists) {
+        for (const auto &it : l) {
+            blob.insert(blob.end(), it.begin(), it.end());
+            off.push_back(blob.size());
+        }
+        seg.push_back(off.size() - 1);
+    }
+    std::vector<B256> roots(lists.size());
+    if (!lists.empty())
+        e.check(b200_ordered_roots(e.raw(), blob.data(), off.data(), seg.data(), lists.size(), roots[0].data(), nullptr));
+    return roots;
+}
+inline B256 ordered_trie_root_encoded(const Engine &e, const std::vector<std::vector<uint8_t>> &items) {
+    return ordered_trie_roots(e, {items})[0];
+}
+
+/// OrderedTrieRootEncodedBuilder — ordered_root.rs:131-257: same names, argument meaning and errors.  Items are buffered
+/// (the reference flushes into a HashBuilder as the key order allows); the trie is built on the device at finalize().
+class OrderedTrieRootEncodedBuilder {
+  public:
+    OrderedTrieRootEncodedBuilder(const Engine &e, size_t len) : e_(e), len_(len), pending_(len) {}
+    void push(size_t index, const std::vector<uint8_t> &bytes) {
+        if (index >= len_) throw OrderedRootError::out_of_bounds(index, len_);
+        if (pending_[index].has_value()) throw OrderedRootError::duplicate(index);
+        push_unchecked(index, bytes);
+    }
+    void push_unchecked(size_t index, const std::vector<uint8_t> &bytes) {
+        pending_[index] = bytes;
+        received_++;
+    }
+    bool is_complete() const { return received_ == len_; }
+    size_t pushed_count() const { return received_; }
+    size_t expected_count() const { return len_; }
+    B256 finalize() {
+        if (len_ == 0) return EMPTY_ROOT_HASH;
+        if (received_ != len_) throw OrderedRootError::incomplete(len_, received_);
+        std::vector<std::vector<uint8_t>> items;
+        items.reserve(len_);
+        for (auto &p : pending_) items.push_back(std::move(*p));
+        return ordered_trie_root_encoded(e_, items);
+    }
+
+  private:
+    const Engine &e_;
+    size_t len_, received_ = 0;
+    std::vector<std::optional<std::vector<uint8_t>>> pending_;
+};
+
 }  // namespace reth_b200

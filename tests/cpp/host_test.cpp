@@ -4,6 +4,7 @@
 //   from_bundle_state_with_rayon      crates/trie/db/src/state.rs:408-437
 //   storage_trie_around_extension_node crates/trie/db/tests/trie.rs:719-805
 //   prefix set semantics              crates/trie/common/src/prefix_set.rs:292-305
+//   ordered root builder              crates/trie/common/src/ordered_root.rs:263-353
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -400,6 +401,79 @@ static void table_rows_host_only() {
     CHECK(sp.size() == 3 && sp[2].value.size() == 33 + 70 && sp[2].value[0] == 0x24 && sp[2].value[32] == 2);
 }
 
+// crates/trie/common/src/ordered_root.rs:263-353 (equivalence, out of order, empty, incomplete, index errors)
+static void ordered_root_builder(const Engine &e) {
+    auto item = [](size_t i) {
+        std::string s = "item_" + std::to_string(i) + "_data";
+        return std::vector<uint8_t>(s.begin(), s.end());
+    };
+    auto oracle_root = [](const std::vector<std::vector<uint8_t>> &items) {
+        std::vector<uint8_t> blob(1);
+        std::vector<uint64_t> off{0};
+        blob.clear();
+        for (auto &it : items) {
+            blob.insert(blob.end(), it.begin(), it.end());
+            off.push_back(blob.size());
+        }
+        uint64_t seg[2] = {0, items.size()};
+        B256 r{};
+        blob.push_back(0);
+        CHECK(orc_ordered_roots(blob.data(), off.data(), seg, 1, r.data()) == 0);
+        return r;
+    };
+    for (size_t len : {0, 1, 2, 3, 10, 127, 128, 129, 130, 200}) {
+        std::vector<std::vector<uint8_t>> items;
+        for (size_t i = 0; i < len; i++) items.push_back(item(i));
+        B256 expected = oracle_root(items);
+        OrderedTrieRootEncodedBuilder b(e, len);
+        for (size_t i = 0; i < len; i++) b.push(i, items[i]);
+        CHECK(b.finalize() == expected);
+        OrderedTrieRootEncodedBuilder rev(e, len);
+        for (size_t i = len; i-- > 0;) rev.push(i, items[i]);
+        CHECK(rev.finalize() == expected);
+    }
+    {
+        OrderedTrieRootEncodedBuilder b(e, 0);
+        CHECK(b.is_complete() && b.finalize() == EMPTY_ROOT_HASH);
+    }
+    {
+        OrderedTrieRootEncodedBuilder b(e, 3);
+        b.push(0, item(0));
+        b.push(1, item(1));
+        CHECK(!b.is_complete());
+        bool threw = false;
+        try {
+            b.finalize();
+        } catch (const OrderedRootError &err) {
+            threw = err.is_incomplete() && err.expected == 3 && err.received == 2 && !err.index().has_value();
+        }
+        CHECK(threw);
+    }
+    {
+        OrderedTrieRootEncodedBuilder b(e, 2);
+        bool oob = false, dup = false;
+        try {
+            b.push(5, item(5));
+        } catch (const OrderedRootError &err) {
+            oob = err.is_index_out_of_bounds() && err.idx == 5 && err.len == 2;
+        }
+        b.push(0, item(0));
+        try {
+            b.push(0, item(9));
+        } catch (const OrderedRootError &err) {
+            dup = err.is_duplicate_index() && err.index() == std::optional<size_t>(0);
+        }
+        b.push(1, item(1));
+        CHECK(oob && dup && b.is_complete() && b.pushed_count() == 2 && b.expected_count() == 2);
+    }
+    // a batch with empty lists
+    std::vector<std::vector<std::vector<uint8_t>>> lists(5);
+    for (size_t i = 0; i < 140; i++) lists[1].push_back(std::vector<uint8_t>(1 + i * 3, (uint8_t)i));
+    lists[3].push_back(item(7));
+    auto roots = ordered_trie_roots(e, lists);
+    for (size_t l = 0; l < lists.size(); l++) CHECK(roots[l] == oracle_root(lists[l]));
+}
+
 int main() {
     table_rows_host_only();
     if (failures) {
@@ -416,6 +490,7 @@ int main() {
         if (std::getenv("B200_EMU") || std::getenv("B200_DTRIE_ON_GPU")) {
             dynamic_trie_blocks(e);
             dynamic_state_blocks(e);
+            ordered_root_builder(e);
         }
     } catch (const B200Error &err) {
         std::printf("B200Error: %s\n", err.what());
