@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# Round-2 opener: first B200 run of everything that was validated under tools/emu only (dynamic trie / state / proofs),
+# Round-2 opener: first B200 run of everything that was validated under tools/emu only (dynamic trie / state / proofs, ordered roots),
 # then their latency, all under timeouts so that a misbehaving kernel costs minutes, not the budget.
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/first_gpu_call.sh'
 set -u
@@ -16,6 +16,11 @@ export B200_DTRIE_ON_GPU=1
   echo "== compute-sanitizer on the smallest dynamic test (racecheck is the point: emulation cannot see races)"
   timeout 600 compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_dtrie.py -m gpu -q -x -k "n0-50 or 50-10-20" 2>&1 | tail -15
   timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_dstate.py -m gpu -q -x -k "3-6-5" 2>&1 | tail -15
+  echo "== ordered roots (ungated tests; memcheck on the leaf kernel's unaligned loads; throughput)"
+  timeout 600 python -m pytest tests/test_gpu_zz_ordered_roots.py -m gpu -q 2>&1 | tail -3
+  timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_zz_ordered_roots.py -m gpu -q -x -k "shapes or golden" 2>&1 | tail -8
+  timeout 600 python tools/ordered_bench.py --blocks 2000 --items 200 --shape receipts 2>&1 | tail -1
+  timeout 600 python tools/ordered_bench.py --blocks 2000 --items 200 --shape transactions 2>&1 | tail -1
   echo "== (afterwards: python bench.py --dynamic adds these legs to the official JSON line)"
   echo "== dynamic trie latency vs merge+rebuild (C5 shape)"
   timeout 600 python tools/dtrie_bench.py --base 100000000 --dirty 10000 --mix 100,0,0 2>&1 | tail -2
