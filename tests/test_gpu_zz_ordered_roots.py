@@ -9,6 +9,7 @@ pytestmark = pytest.mark.gpu
 
 import oracle
 from tests.test_ordered_root_oracle import golden_cases
+from tests.util import read_device, to_device_ptrs
 
 
 @pytest.fixture(scope="module")
@@ -150,3 +151,37 @@ def test_bad_offsets_are_rejected(eng):
         eng.ordered_roots(vals, np.array([0, 4, 8], np.uint64), np.array([0, 3], np.uint64))   # more items than offsets
     ok = oracle.pack_lists([[b"ab", b"cd"]])
     assert (eng.ordered_roots(*ok) == oracle.ordered_roots(*ok)).all()  # the context stays usable
+
+
+def _dev_roots(eng, values, value_offsets, seg_offsets, skew=0):
+    """b200_ordered_roots_dev with every buffer in device memory; `skew` shifts the items off 8-byte alignment"""
+    m, n = len(seg_offsets) - 1, len(value_offsets) - 1
+    blob = np.concatenate([np.zeros(skew, np.uint8), values, np.zeros(8, np.uint8)])
+    roots = np.zeros((max(m, 1), 32), np.uint8)
+    (p_blob, p_vo, p_so, p_roots), hold = to_device_ptrs([blob, value_offsets, seg_offsets, roots])
+    eng._check(eng.lib.b200_ordered_roots_dev(eng.ctx, p_blob + skew, len(values), p_vo, p_so, m, n, p_roots))
+    eng.sync()
+    return read_device(hold[3]).reshape(-1, 32)[:m]
+
+
+def test_device_resident_variant_any_alignment(eng):
+    rng = np.random.default_rng(14)
+    lists = [_random_items(rng, n, [1, 20, 33, 136, 137, 300, 1111]) for n in (0, 1, 40, 130, 3)]
+    packed = oracle.pack_lists(lists)
+    want = oracle.ordered_roots(*packed)
+    for skew in (0, 1, 3, 4, 7):
+        assert (_dev_roots(eng, *packed, skew=skew) == want).all(), skew
+
+
+def test_device_side_offset_validation(eng):
+    """the asynchronous variant reports violations through the sticky status (b200_sync), and the context recovers"""
+    from reth_b200 import B200Error
+    ok = oracle.pack_lists([[b"abcd" * 20, b"ef" * 50, b"g"]])
+    values, vo, so = ok
+    for bad_vo, bad_so in [(np.array([0, 90, 80, 181], np.uint64), so),          # value offsets not monotone
+                           (np.array([0, 80, 180, 9999], np.uint64), so),         # past the blob
+                           (vo, np.array([0, 5], np.uint64)),                     # list longer than the items
+                           (vo, np.array([2, 3], np.uint64))]:                    # does not start at 0
+        with pytest.raises(B200Error):
+            _dev_roots(eng, values, bad_vo, bad_so)
+    assert (_dev_roots(eng, *ok) == oracle.ordered_roots(*ok)).all()

@@ -134,3 +134,10 @@ def to_device_ptrs(arrays):
             hold = [torch.from_numpy(a.view(np.uint8).reshape(-1)).cuda() for a in arrays]
             return [t.data_ptr() for t in hold], hold
     return [a.ctypes.data for a in arrays], arrays
+
+
+def read_device(held, dtype=np.uint8):
+    """Host copy of one of the objects `to_device_ptrs` returned in its second list."""
+    if hasattr(held, "cpu"):
+        held = held.cpu().numpy()
+    return np.asarray(held).view(np.uint8).view(dtype).copy()
