@@ -161,3 +161,22 @@ pub fn hash_keys<const LEN: usize>(ctx: &B200Handle, keys: &[[u8; LEN]]) -> Prov
     let _ = (EMPTY_ROOT_HASH, U256::ZERO);
     Ok(out)
 }
+
+/// `proofs::calculate_transaction_root` for every block of a batch in one device call: the encoder
+/// is the one `ordered_trie_root_with_encoder` is given — `encode_2718` — so the trie sees the same bytes.
+pub fn transaction_roots<T: alloy_eips::eip2718::Encodable2718>(ctx: &B200Handle, blocks: &[&[T]]) -> ProviderResult<Vec<B256>> {
+    let (mut blob, mut offs, mut segs) = (Vec::<u8>::new(), vec![0u64], vec![0u64]);
+    for txs in blocks {
+        for tx in txs.iter() {
+            tx.encode_2718(&mut blob);
+            offs.push(blob.len() as u64);
+        }
+        segs.push(offs.len() as u64 - 1);
+    }
+    let mut roots = vec![B256::ZERO; blocks.len()];
+    ctx.check(unsafe {
+        sys::b200_ordered_roots(ctx.raw(), blob.as_ptr(), offs.as_ptr(), segs.as_ptr(), blocks.len() as u64,
+                                roots.as_mut_ptr().cast(), std::ptr::null_mut())
+    })?;
+    Ok(roots)
+}

@@ -128,4 +128,7 @@ unsafe extern "C" {
     pub fn b200_dstate_frontier(state: *mut b200_dstate, out16: *mut b200_frontier_entry) -> i32;
     pub fn b200_root_from_frontier(ctx: *mut b200_ctx, frontier16: *const b200_frontier_entry, root32: *mut u8) -> i32;
     pub fn b200_dstate_destroy(state: *mut b200_dstate);
+    /// transactions / receipts / withdrawals roots of a batch of lists (ordered_root.rs:240-257 per list)
+    pub fn b200_ordered_roots(ctx: *mut b200_ctx, values: *const u8, value_offsets: *const u64, seg_offsets: *const u64,
+                              n_lists: u64, roots32: *mut u8, opt_stats: *mut b200_stats) -> i32;
 }
