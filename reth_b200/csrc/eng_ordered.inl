@@ -14,12 +14,25 @@ static int32_t ordered_roots_on_device(b200_ctx *c, const uint8_t *d_values, uin
         ENSURE(ord_keys, n_items * 32);
         ENSURE(ord_knib, n_items);
         ENSURE(ord_item, n_items * 4);
+        ENSURE(ord_sched, n_items * 2);
+        ENSURE(ord_sched2, n_items * 2);
+        ENSURE(ord_pos, n_items * 4);
+        ENSURE(ord_order, n_items * 4);
         int *err = reinterpret_cast<int *>(small_u32(c) + SM_ERR);
-        CU(launch_ordered_keys(d_seg_offsets, n_lists, n_items, static_cast<uint8_t *>(c->ord_keys.p),
-                               static_cast<uint8_t *>(c->ord_knib.p), static_cast<uint32_t *>(c->ord_item.p), err, st));
-        c->launches++;
+        uint16_t *sched = static_cast<uint16_t *>(c->ord_sched.p), *sched2 = static_cast<uint16_t *>(c->ord_sched2.p);
+        uint32_t *pos = static_cast<uint32_t *>(c->ord_pos.p), *order = static_cast<uint32_t *>(c->ord_order.p);
+        CU(launch_ordered_keys(d_seg_offsets, n_lists, n_items, d_val_off, static_cast<uint8_t *>(c->ord_keys.p),
+                               static_cast<uint8_t *>(c->ord_knib.p), static_cast<uint32_t *>(c->ord_item.p), sched, pos, err,
+                               st));
+        // leaf visiting order: items of about equal length share a warp (stable: neighbours stay neighbours)
+        size_t t_sort = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, sched, sched2, pos, order, (int64_t)n_items, 0, 16, st));
+        ENSURE(cub_temp, t_sort);
+        CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_sort, sched, sched2, pos, order, (int64_t)n_items, 0, 16, st));
+        c->launches += 2;
         o.key_nibs = static_cast<const uint8_t *>(c->ord_knib.p);
         o.item = static_cast<const uint32_t *>(c->ord_item.p);
+        o.order = order;
         o.values = d_values;
         o.val_off = d_val_off;
         o.blob_len = blob_len;

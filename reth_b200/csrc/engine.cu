@@ -85,7 +85,7 @@ extern "C" B200_API void b200_destroy(b200_ctx *c) {
                       &c->in_d, &c->in_e, &c->out_a, &c->chunk_in[0], &c->chunk_in[1], &c->chunk_in[2], &c->chunk_out[0],
                       &c->chunk_out[1], &c->chunk_out[2], &c->sort_ka, &c->sort_kb, &c->sort_ia, &c->sort_flag, &c->sort_perm,
                       &c->sort_out, &c->node_key, &c->node_key2, &c->node_ids, &c->node_order, &c->ord_keys, &c->ord_knib,
-                      &c->ord_item};
+                      &c->ord_item, &c->ord_sched, &c->ord_sched2, &c->ord_pos, &c->ord_order};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->pinned_small) cudaFreeHost(c->pinned_small);

@@ -36,7 +36,7 @@ struct b200_ctx {
     DevBuf upd_flags, upd_nh, upd_ids, upd_prefix;
     DevBuf sort_ka, sort_kb, sort_ia, sort_flag, sort_perm, sort_out;
     DevBuf node_key, node_key2, node_ids, node_order;
-    DevBuf ord_keys, ord_knib, ord_item;  // ordered tries: synthesized rlp(index) keys
+    DevBuf ord_keys, ord_knib, ord_item, ord_sched, ord_sched2, ord_pos, ord_order;  // ordered tries (eng_ordered.inl)
     // staging for host-pointer entry points
     DevBuf in_a, in_b, in_c, in_d, in_e, out_a, chunk_in[3], chunk_out[3];
     void *pinned_small = nullptr;  // 4 KiB page-locked readback area

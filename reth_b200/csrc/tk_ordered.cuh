@@ -17,10 +17,12 @@ static __device__ __forceinline__ uint32_t ord_adjust_index(uint32_t j, uint32_t
     return j + 1;
 }
 
-// One thread per leaf position: the padded key, its true length in nibbles, and the item it carries.
+// One thread per leaf position: the padded key, its true length in nibbles, the item it carries, and a scheduling key
+// for the leaf pass (Keccak blocks of the item, longest first: threads of a warp then hash items of about equal length).
 __global__ void ordered_keys_kernel(const uint64_t *__restrict__ seg_offsets, uint64_t n_segs, uint64_t n,
-                                    uint8_t *__restrict__ keys, uint8_t *__restrict__ key_nibs,
-                                    uint32_t *__restrict__ item, int *err) {
+                                    const uint64_t *__restrict__ val_off, uint8_t *__restrict__ keys,
+                                    uint8_t *__restrict__ key_nibs, uint32_t *__restrict__ item,
+                                    uint16_t *__restrict__ sched_key, uint32_t *__restrict__ pos, int *err) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     // last segment starting at or before p (empty segments share a start: take the last of them)
@@ -60,6 +62,9 @@ __global__ void ordered_keys_kernel(const uint64_t *__restrict__ seg_offsets, ui
     q[1] = make_uint4(0, 0, 0, 0);
     key_nibs[p] = (uint8_t)(2 * nb);
     item[p] = (uint32_t)it;
+    uint64_t blocks = (val_off[it + 1] - val_off[it] + 17) / 136;  // (offsets are validated by the leaf pass)
+    sched_key[p] = (uint16_t)(65535u - (uint32_t)(blocks < 65535 ? blocks : 65535));
+    pos[p] = (uint32_t)p;
 }
 
 static __device__ __forceinline__ uint32_t ord_be_len(uint32_t x) { return x < 0x100 ? 1 : (x < 0x10000 ? 2 : (x < 0x1000000 ? 3 : 4)); }
@@ -95,12 +100,14 @@ static __device__ __forceinline__ uint64_t ord_load8(const uint8_t *p) {
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) ordered_leaf_kernel(ForestDev f, const uint8_t *__restrict__ key_nibs,
                                                              const uint32_t *__restrict__ item,
+                                                             const uint32_t *__restrict__ order,
                                                              const uint8_t *__restrict__ values,
                                                              const uint64_t *__restrict__ val_off, uint64_t blob_len) {
     if (*(volatile int *)f.err == B200_DEVERR_UNSORTED || *(volatile int *)f.err == B200_DEVERR_BAD_OFFSETS) return;
-    uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const uint64_t t = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
     uint32_t hashed = 0;
-    if (i < f.n) {
+    if (t < f.n) {
+        const uint64_t i = order[t];  // leaves in descending order of item length
         uint32_t k[8];
         load32_nc(f.keys + 32 * i, k);
         int pdl = depth_of(f.Lp[i]), pdr = depth_of(f.Lp[i + 1]);
@@ -201,16 +208,18 @@ __global__ void __launch_bounds__(BLOCK) ordered_leaf_kernel(ForestDev f, const 
     if ((threadIdx.x & 31) == 0 && hashed) atomicAdd(&f.counters[CNT_HASHED], (unsigned long long)hashed);
 }
 
-cudaError_t launch_ordered_keys(const uint64_t *d_seg_offsets, uint64_t n_segs, uint64_t n, uint8_t *keys, uint8_t *key_nibs,
-                                uint32_t *item, int *err, cudaStream_t st) {
+cudaError_t launch_ordered_keys(const uint64_t *d_seg_offsets, uint64_t n_segs, uint64_t n, const uint64_t *val_off,
+                                uint8_t *keys, uint8_t *key_nibs, uint32_t *item, uint16_t *sched_key, uint32_t *pos, int *err,
+                                cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    ordered_keys_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_seg_offsets, n_segs, n, keys, key_nibs, item, err);
+    ordered_keys_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_seg_offsets, n_segs, n, val_off, keys, key_nibs, item,
+                                                            sched_key, pos, err);
     return cudaGetLastError();
 }
 cudaError_t launch_ordered_leaves(const ForestDev &f, const OrderedLeavesDev &o, cudaStream_t st) {
     if (f.n == 0) return cudaSuccess;
     constexpr int BLOCK = 128;
-    ordered_leaf_kernel<BLOCK><<<blocks_for(f.n, BLOCK), BLOCK, 0, st>>>(f, o.key_nibs, o.item, o.values, o.val_off,
+    ordered_leaf_kernel<BLOCK><<<blocks_for(f.n, BLOCK), BLOCK, 0, st>>>(f, o.key_nibs, o.item, o.order, o.values, o.val_off,
                                                                          o.blob_len);
     return cudaGetLastError();
 }

@@ -135,12 +135,14 @@ cudaError_t launch_pick_subset(const uint32_t *ids, const uint32_t *prefix, cons
 struct OrderedLeavesDev {
     const uint8_t *key_nibs;  // [n] true key length in nibbles (the padded keys are ForestDev::keys)
     const uint32_t *item;     // [n] item (in list order) carried by the leaf at this sorted position
+    const uint32_t *order;    // [n] leaf positions in the order the leaf pass visits them (longest item first)
     const uint8_t *values;    // concatenated pre-encoded items
     const uint64_t *val_off;  // [n+1] byte offsets of the items in `values`
     uint64_t blob_len;
 };
-cudaError_t launch_ordered_keys(const uint64_t *d_seg_offsets, uint64_t n_segs, uint64_t n, uint8_t *keys, uint8_t *key_nibs,
-                                uint32_t *item, int *err, cudaStream_t st);
+cudaError_t launch_ordered_keys(const uint64_t *d_seg_offsets, uint64_t n_segs, uint64_t n, const uint64_t *val_off,
+                                uint8_t *keys, uint8_t *key_nibs, uint32_t *item, uint16_t *sched_key, uint32_t *pos, int *err,
+                                cudaStream_t st);
 cudaError_t launch_ordered_leaves(const ForestDev &f, const OrderedLeavesDev &o, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------ dynamic trie (tk_dtrie.cuh)
