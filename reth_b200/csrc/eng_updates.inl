@@ -124,8 +124,28 @@ static int32_t collect_updates(b200_ctx *c, const Built &b, const uint64_t *d_se
         n_stored = ps[200];
         n_hashes = ps[201] + ps[202];
     }
-    return gather_and_copy(c, b.f, static_cast<uint32_t *>(c->upd_ids.p), n_stored, n_hashes,
-                           static_cast<uint32_t *>(c->upd_prefix.p), nullptr, d_seg_offsets, n_segs, u, owner);
+    if (n_stored == 0)
+        return gather_and_copy(c, b.f, nullptr, 0, 0, nullptr, nullptr, d_seg_offsets, n_segs, u, owner);
+    // Records leave the device in table order (ascending trie, then path): the selected ids are in (depth, position)
+    // order, one radix sort by (leftmost leaf, depth) puts them in pre-order; the hash offsets are re-scanned in that
+    // order so that hashes follow their records.
+    ENSURE(upd_key, (size_t)n_stored * 8);
+    ENSURE(upd_key2, (size_t)n_stored * 8);
+    ENSURE(upd_ids2, (size_t)n_stored * 4);
+    uint32_t *ids = static_cast<uint32_t *>(c->upd_ids.p), *ids2 = static_cast<uint32_t *>(c->upd_ids2.p);
+    uint64_t *key = static_cast<uint64_t *>(c->upd_key.p), *key2 = static_cast<uint64_t *>(c->upd_key2.p);
+    uint8_t *flags = static_cast<uint8_t *>(c->upd_flags.p);
+    uint32_t *nh = static_cast<uint32_t *>(c->upd_nh.p), *prefix = static_cast<uint32_t *>(c->upd_prefix.p);
+    CU(launch_table_order_keys(b.f, ids, n_stored, key, st));
+    size_t t_sort = 0, t_scan = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, key, key2, ids, ids2, (int64_t)n_stored, 0, 40, st));
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, t_scan, nh, prefix, (int64_t)n_stored, st));
+    ENSURE(cub_temp, std::max(t_sort, t_scan));
+    CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_sort, key, key2, ids, ids2, (int64_t)n_stored, 0, 40, st));
+    CU(launch_stored_flags_subset(b.f, ids2, n_stored, flags, nh, st));  // (all flagged; nh in record order)
+    CU(cub::DeviceScan::ExclusiveSum(c->cub_temp.p, t_scan, nh, prefix, (int64_t)n_stored, st));
+    c->launches += 4;
+    return gather_and_copy(c, b.f, ids2, n_stored, n_hashes, nullptr, prefix, d_seg_offsets, n_segs, u, owner);
 }
 
 // Same for a subset of nodes given by id (the dirty nodes of an incremental update), in list order.

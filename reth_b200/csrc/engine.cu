@@ -81,7 +81,7 @@ extern "C" B200_API void b200_destroy(b200_ctx *c) {
     DevBuf *bufs[] = {&c->Lp, &c->nibs, &c->leaf_ref, &c->leaf_meta, &c->S, &c->E, &c->iota, &c->depth_sorted,
                       &c->gap_sorted, &c->bound_rank, &c->head, &c->node_start, &c->node_ref, &c->node_meta,
                       &c->node_l, &c->node_r, &c->node_masks, &c->cub_temp, &c->small, &c->sroots, &c->buckets,
-                      &c->upd_flags, &c->upd_nh, &c->upd_ids, &c->upd_prefix, &c->in_a, &c->in_b, &c->in_c,
+                      &c->upd_flags, &c->upd_nh, &c->upd_ids, &c->upd_prefix, &c->upd_key, &c->upd_key2, &c->upd_ids2, &c->in_a, &c->in_b, &c->in_c,
                       &c->in_d, &c->in_e, &c->out_a, &c->chunk_in[0], &c->chunk_in[1], &c->chunk_in[2], &c->chunk_out[0],
                       &c->chunk_out[1], &c->chunk_out[2], &c->sort_ka, &c->sort_kb, &c->sort_ia, &c->sort_flag, &c->sort_perm,
                       &c->sort_out, &c->node_key, &c->node_key2, &c->node_ids, &c->node_order, &c->ord_keys, &c->ord_knib,

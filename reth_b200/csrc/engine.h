@@ -33,7 +33,7 @@ struct b200_ctx {
     // scratch (grow-only)
     DevBuf Lp, nibs, leaf_ref, leaf_meta, S, E, iota, depth_sorted, gap_sorted, bound_rank, head, node_start,
         node_ref, node_meta, node_l, node_r, node_masks, cub_temp, small, sroots, buckets;
-    DevBuf upd_flags, upd_nh, upd_ids, upd_prefix;
+    DevBuf upd_flags, upd_nh, upd_ids, upd_prefix, upd_key, upd_key2, upd_ids2;
     DevBuf sort_ka, sort_kb, sort_ia, sort_flag, sort_perm, sort_out;
     DevBuf node_key, node_key2, node_ids, node_order;
     DevBuf ord_keys, ord_knib, ord_item, ord_sched, ord_sched2, ord_pos, ord_order;  // ordered tries (eng_ordered.inl)

@@ -91,7 +91,12 @@ int32_t encode(const b200_updates *u, const uint8_t *acct_keys32, uint64_t n_acc
         if (nh != (uint64_t)__builtin_popcount(u->hash_mask[i])) return B200_ERR_INVALID_ARG;
         total += (storage ? 32 : 0) + nibble_key_bytes(fmt, storage, len) + 6 + 32 * nh;
     }
-    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return row_less(keys[a], keys[b]); });
+    // records of a full build already arrive in table order (eng_updates.inl sorts them on the device); anything else
+    // (dirty subsets, hand-made updates) is ordered here
+    bool in_order = true;
+    for (uint64_t i = 1; i < n && in_order; i++) in_order = !row_less(keys[i], keys[i - 1]);
+    if (!in_order)
+        std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return row_less(keys[a], keys[b]); });
 
     // one block: [row_offset (n+1) u64][key_len n u32, padded to 8][bytes]
     size_t off_bytes = (n + 1) * sizeof(uint64_t), kl_bytes = ((n * sizeof(uint32_t)) + 7) & ~size_t(7);

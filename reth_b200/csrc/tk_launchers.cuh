@@ -167,6 +167,11 @@ cudaError_t launch_stored_flags(const ForestDev &f, uint32_t n_nodes, uint8_t *f
     stored_flags_kernel<<<blocks_for(n_nodes, 256), 256, 0, st>>>(f, n_nodes, flags, n_hashes);
     return cudaGetLastError();
 }
+cudaError_t launch_table_order_keys(const ForestDev &f, const uint32_t *ids, uint32_t count, uint64_t *keys, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    table_order_keys_kernel<<<blocks_for(count, 256), 256, 0, st>>>(f, ids, count, keys);
+    return cudaGetLastError();
+}
 cudaError_t launch_gather_updates(const ForestDev &f, const uint32_t *stored_ids, uint32_t n_stored,
                                   const uint32_t *hash_prefix, const uint32_t *prefix_by_record,
                                   const uint64_t *d_seg_offsets, uint64_t n_segs, const UpdatesDev &out,

@@ -56,6 +56,17 @@ __global__ void pick_subset_kernel(const uint32_t *__restrict__ ids, const uint3
     out_prefix[t] = prefix[p];
 }
 
+// Table-order key of a stored node: (leftmost leaf, depth) ascending is pre-order over the forest — ascending trie id,
+// then ascending path with a prefix before its extensions — the key order of AccountsTrie / StoragesTrie
+// (crates/trie/common/src/nibbles.rs StoredNibbles / StoredNibblesSubKey; MDBX memcmp order).
+__global__ void table_order_keys_kernel(ForestDev f, const uint32_t *__restrict__ ids, uint32_t count,
+                                        uint64_t *__restrict__ keys) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    uint32_t v = ids[t];
+    keys[t] = ((uint64_t)f.node_l[v] << 8) | (uint64_t)(f.node_masks[v].w & 0xff);
+}
+
 // One thread per stored node: path, masks and the child hashes under hash_mask, ascending nibble.
 __global__ void gather_updates_kernel(ForestDev f, const uint32_t *__restrict__ stored_ids, uint32_t n_stored,
                                       const uint32_t *__restrict__ hash_prefix /* exclusive, over all nodes */,

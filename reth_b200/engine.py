@@ -29,9 +29,10 @@ def _unpack_nibbles(packed: bytes, n: int) -> bytes:
     return bytes(x for b in packed for x in (b >> 4, b & 15))[:n]
 
 
-def updates_to_records(u: Updates, lib) -> list:
+def updates_to_records(u: Updates, lib, sort: bool = True) -> list:
     """-> [(trie_id, path_nibbles, state_mask, tree_mask, hash_mask, [hashes])] sorted by (trie_id, path);
-    releases the library-owned buffers."""
+    releases the library-owned buffers.  (sort=False keeps the library's order: full builds already deliver table
+    order, dirty subsets do not.)"""
     n = int(u.n_nodes)
     res = []
     if n:
@@ -48,7 +49,8 @@ def updates_to_records(u: Updates, lib) -> list:
             res.append((int(tid[i]), _unpack_nibbles(pp[i].tobytes(), int(pl[i])), int(sm[i]), int(tm[i]),
                         int(hm[i]), [hs[j].tobytes() for j in range(int(ho[i]), int(ho[i + 1]))]))
     lib.b200_updates_release(C.byref(u))
-    res.sort(key=lambda r: (r[0], r[1]))
+    if sort:
+        res.sort(key=lambda r: (r[0], r[1]))
     return res
 
 

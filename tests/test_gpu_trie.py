@@ -207,6 +207,31 @@ def test_full_state_table_rows(eng, packed):
     arows.release(); srows.release()
 
 
+def test_update_records_leave_the_device_in_table_order(eng):
+    """full builds: b200_updates records are already sorted by (trie id, path) — pre-order, the key order of the trie
+    tables — with hashes following their records; the row encoder then has nothing to sort"""
+    import ctypes as C
+    from reth_b200._lib import Updates
+    from reth_b200.engine import updates_to_records
+    n = 6000
+    akeys, accs = synth_accounts(31, n)
+    counts = np.where(np.arange(n) % 3 == 0, 40, 0) + np.where(np.arange(n) % 997 == 0, 1500, 0)
+    skeys, svals, offs = synth_storage(32, counts, value_mode="mixed")
+    root = np.empty(32, np.uint8)
+    au, su = Updates(), Updates()
+    eng._check(eng.lib.b200_state_root_full(eng.ctx, akeys.ctypes.data, accs.ctypes.data, n, skeys.ctypes.data,
+                                            svals.ctypes.data, offs.ctypes.data, root.ctypes.data, C.byref(au),
+                                            C.byref(su), None))
+    for u in (au, su):
+        ho = np.ctypeslib.as_array(u.hash_offset, (int(u.n_nodes) + 1,)).copy()
+        assert (np.diff(ho.astype(np.int64)) >= 0).all() and ho[0] == 0
+        recs = updates_to_records(u, eng.lib, sort=False)
+        assert len(recs) > 300
+        assert recs == sorted(recs, key=lambda r: (r[0], r[1]))
+    o_root, o_au, o_su = oracle.state_root_full(akeys, accs, skeys, svals, offs, want_updates=True, threads=4)
+    assert root.tobytes() == o_root
+
+
 def test_one_million_leaves(eng):
     """Size-independent check at scale: 1M-account trie root equals the oracle's."""
     keys, accs = synth_accounts(77, 1_000_000)
