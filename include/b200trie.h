@@ -159,6 +159,7 @@ B200_API int32_t b200_account_trie_rows(const b200_updates *account_updates, int
 B200_API int32_t b200_storage_trie_rows(const b200_updates *storage_updates, const uint8_t *acct_keys32,
                                         uint64_t n_accounts, int32_t key_format, b200_rows *out);
 B200_API void b200_rows_release(b200_rows *);
+/* (b200_state_root_full_rows, below, delivers the same rows straight from a build: encoded on the device.) */
 
 /* TrieStats / TrieRootMetrics (crates/trie/trie/src/stats.rs, metrics.rs:22-40) plus device timing. */
 typedef struct {
@@ -196,6 +197,16 @@ B200_API int32_t b200_state_root_full(b200_ctx *, const uint8_t *acct_keys32, co
                              const uint64_t *seg_offsets, uint8_t root32[32],
                              b200_updates *opt_account_updates, b200_updates *opt_storage_updates,
                              b200_stats *opt_stats);
+
+/* b200_state_root_full whose stored nodes arrive as finished table rows — MerkleStage's rebuild leg writing
+ * AccountsTrie / StoragesTrie (crates/stages/stages/src/stages/merkle.rs:216-253 → write_trie_updates,
+ * crates/storage/provider/src/providers/database/provider.rs:2545-2627): rows are sized, ordered and laid out on the
+ * device and cross in one copy; byte-identical to b200_account_trie_rows / b200_storage_trie_rows over the records.
+ * Release both with b200_rows_release. */
+B200_API int32_t b200_state_root_full_rows(b200_ctx *, const uint8_t *acct_keys32, const b200_account *accts,
+                                           uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
+                                           const uint64_t *seg_offsets, int32_t key_format, uint8_t root32[32],
+                                           b200_rows *account_rows, b200_rows *storage_rows, b200_stats *opt_stats);
 
 /* Device-resident variants: every pointer is a device pointer (seg_offsets included), results are written
  * to device memory, nothing is copied or synchronised.  d_root32 / d_roots32 are device buffers.

@@ -134,6 +134,7 @@ def load():
     sig("b200_storage_roots", i32, vp, vp, vp, vp, u64, vp, PU, PS)
     sig("b200_state_root", i32, vp, vp, vp, vp, u64, vp, PU, PS)
     sig("b200_state_root_full", i32, vp, vp, vp, u64, vp, vp, vp, vp, PU, PU, PS)
+    sig("b200_state_root_full_rows", i32, vp, vp, vp, u64, vp, vp, vp, i32, vp, C.POINTER(Rows), C.POINTER(Rows), PS)
     sig("b200_storage_roots_dev", i32, vp, vp, vp, vp, u64, u64, vp)
     sig("b200_state_root_dev", i32, vp, vp, vp, vp, u64, vp)
     sig("b200_state_root_full_dev", i32, vp, vp, vp, u64, vp, vp, vp, u64, vp)

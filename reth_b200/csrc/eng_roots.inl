@@ -231,19 +231,22 @@ static int32_t state_root_full_pipelined(b200_ctx *c, const uint8_t *acct_keys32
     return sync_and_status(c);
 }
 
-extern "C" B200_API int32_t b200_state_root_full(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
-                                        uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
-                                        const uint64_t *seg_offsets, uint8_t root32[32],
-                                        b200_updates *opt_account_updates, b200_updates *opt_storage_updates,
-                                        b200_stats *opt_stats) {
+// opt_*_rows: the stored nodes as finished table rows (encoded on the device) instead of / next to the records
+static int32_t state_root_full_impl(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
+                                    uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
+                                    const uint64_t *seg_offsets, uint8_t root32[32], b200_updates *opt_account_updates,
+                                    b200_updates *opt_storage_updates, int32_t key_format, b200_rows *opt_account_rows,
+                                    b200_rows *opt_storage_rows, b200_stats *opt_stats) {
     if (!c || !root32 || !seg_offsets || (n_accounts && (!acct_keys32 || !accts)))
         return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    if (opt_account_rows) memset(opt_account_rows, 0, sizeof *opt_account_rows);
+    if (opt_storage_rows) memset(opt_storage_rows, 0, sizeof *opt_storage_rows);
     TRY(check_offsets_host(c, seg_offsets, n_accounts));
     uint64_t n_slots = seg_offsets[n_accounts];
     if (n_slots && (!slot_keys32 || !values32_be)) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
     if (opt_account_updates) memset(opt_account_updates, 0, sizeof *opt_account_updates);
     if (opt_storage_updates) memset(opt_storage_updates, 0, sizeof *opt_storage_updates);
-    const bool retain = opt_account_updates || opt_storage_updates;
+    const bool retain = opt_account_updates || opt_storage_updates || opt_account_rows || opt_storage_rows;
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
     if (!retain && n_slots >= (2ull << 20) && n_accounts >= 16) {
@@ -266,10 +269,13 @@ extern "C" B200_API int32_t b200_state_root_full(b200_ctx *c, const uint8_t *acc
                                         static_cast<const uint64_t *>(c->in_c.p), n_accounts, n_slots,
                                         static_cast<uint8_t *>(c->sroots.p), retain, bs);
     // the storage forest's scratch is reused by the account build: gather its updates first
-    if (r == B200_OK && opt_storage_updates) {
+    if (r == B200_OK && (opt_storage_updates || opt_storage_rows)) {
         r = sync_and_status(c);
-        if (r == B200_OK)
+        if (r == B200_OK && opt_storage_updates)
             r = collect_updates(c, bs, static_cast<const uint64_t *>(c->in_c.p), n_accounts, opt_storage_updates);
+        if (r == B200_OK && opt_storage_rows)
+            r = collect_rows(c, bs, static_cast<const uint64_t *>(c->in_c.p), n_accounts,
+                             static_cast<const uint8_t *>(c->in_d.p), key_format, true, opt_storage_rows);
     }
     if (r == B200_OK)
         r = account_root_on_device(c, static_cast<const uint8_t *>(c->in_d.p), static_cast<const uint8_t *>(c->in_e.p),
@@ -281,10 +287,33 @@ extern "C" B200_API int32_t b200_state_root_full(b200_ctx *c, const uint8_t *acc
     }
     if (r == B200_OK) r = sync_and_status(c);
     if (r == B200_OK && opt_account_updates) r = collect_updates(c, ba, nullptr, 0, opt_account_updates);
+    if (r == B200_OK && opt_account_rows) r = collect_rows(c, ba, nullptr, 0, nullptr, key_format, false, opt_account_rows);
     if (r != B200_OK) {
         if (opt_account_updates) b200_updates_release(opt_account_updates);
         if (opt_storage_updates) b200_updates_release(opt_storage_updates);
+        if (opt_account_rows) b200_rows_release(opt_account_rows);
+        if (opt_storage_rows) b200_rows_release(opt_storage_rows);
     }
     if (opt_stats) *opt_stats = c->stats;
     return r;
+}
+
+extern "C" B200_API int32_t b200_state_root_full(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
+                                        uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
+                                        const uint64_t *seg_offsets, uint8_t root32[32],
+                                        b200_updates *opt_account_updates, b200_updates *opt_storage_updates,
+                                        b200_stats *opt_stats) {
+    return state_root_full_impl(c, acct_keys32, accts, n_accounts, slot_keys32, values32_be, seg_offsets, root32,
+                                opt_account_updates, opt_storage_updates, B200_KEYS_LEGACY, nullptr, nullptr, opt_stats);
+}
+
+extern "C" B200_API int32_t b200_state_root_full_rows(b200_ctx *c, const uint8_t *acct_keys32, const b200_account *accts,
+                                                      uint64_t n_accounts, const uint8_t *slot_keys32,
+                                                      const uint8_t *values32_be, const uint64_t *seg_offsets,
+                                                      int32_t key_format, uint8_t root32[32], b200_rows *account_rows,
+                                                      b200_rows *storage_rows, b200_stats *opt_stats) {
+    if (!account_rows || !storage_rows || (key_format != B200_KEYS_LEGACY && key_format != B200_KEYS_PACKED))
+        return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    return state_root_full_impl(c, acct_keys32, accts, n_accounts, slot_keys32, values32_be, seg_offsets, root32, nullptr,
+                                nullptr, key_format, account_rows, storage_rows, opt_stats);
 }

@@ -88,64 +88,131 @@ static int32_t gather_and_copy(b200_ctx *c, const ForestDev &f, const uint32_t *
     return B200_OK;
 }
 
-// Collects the stored BranchNodeCompact records of a finished build into `u` (host, page-locked).
+// The stored nodes of a finished build in table order (ascending trie, then path): selected in (depth, position) order,
+// then one radix sort by (leftmost leaf, depth) = pre-order.  *ids_out points into ctx scratch (upd_ids2).
+static int32_t stored_ids_in_table_order(b200_ctx *c, const Built &b, uint32_t *n_stored_out, uint32_t *n_hashes_out,
+                                         const uint32_t **ids_out) {
+    cudaStream_t st = c->stream;
+    const uint32_t B = b.n_nodes;
+    *n_stored_out = *n_hashes_out = 0;
+    *ids_out = nullptr;
+    if (!B) return B200_OK;
+    uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
+    ENSURE(upd_flags, B);
+    ENSURE(upd_nh, (size_t)B * 4);
+    ENSURE(upd_ids, (size_t)B * 4);
+    ENSURE(upd_prefix, (size_t)(B + 1) * 4);
+    uint8_t *flags = static_cast<uint8_t *>(c->upd_flags.p);
+    uint32_t *nh = static_cast<uint32_t *>(c->upd_nh.p);
+    uint32_t *ids = static_cast<uint32_t *>(c->upd_ids.p);
+    uint32_t *prefix = static_cast<uint32_t *>(c->upd_prefix.p);
+    uint32_t *n_stored_p = small_u32(c) + SM_NSTORED;
+    CU(launch_stored_flags(b.f, B, flags, nh, st));
+    size_t t_sel = 0, t_scan = 0, t_sort = 0;
+    thrust::counting_iterator<uint32_t> counting(0);
+    CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, flags, ids, n_stored_p, (int64_t)B, st));
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, t_scan, nh, prefix, (int64_t)B, st));
+    ENSURE(cub_temp, std::max(t_sel, t_scan));
+    CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, flags, ids, n_stored_p, (int64_t)B, st));
+    CU(cub::DeviceScan::ExclusiveSum(c->cub_temp.p, t_scan, nh, prefix, (int64_t)B, st));
+    c->launches += 3;
+    CU(cudaMemcpyAsync(ps + 200, n_stored_p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ps + 201, prefix + (B - 1), 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ps + 202, nh + (B - 1), 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint32_t n_stored = ps[200];
+    *n_stored_out = n_stored;
+    *n_hashes_out = ps[201] + ps[202];
+    if (!n_stored) return B200_OK;
+    ENSURE(upd_key, (size_t)n_stored * 8);
+    ENSURE(upd_key2, (size_t)n_stored * 8);
+    ENSURE(upd_ids2, (size_t)n_stored * 4);
+    uint32_t *ids2 = static_cast<uint32_t *>(c->upd_ids2.p);
+    uint64_t *key = static_cast<uint64_t *>(c->upd_key.p), *key2 = static_cast<uint64_t *>(c->upd_key2.p);
+    CU(launch_table_order_keys(b.f, ids, n_stored, key, st));
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, key, key2, ids, ids2, (int64_t)n_stored, 0, 40, st));
+    ENSURE(cub_temp, t_sort);
+    CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_sort, key, key2, ids, ids2, (int64_t)n_stored, 0, 40, st));
+    c->launches += 2;
+    *ids_out = ids2;
+    return B200_OK;
+}
+
+// Collects the stored BranchNodeCompact records of a finished build into `u` (host, page-locked), in table order; the
+// hash offsets are scanned in that order so that hashes follow their records.
 static int32_t collect_updates(b200_ctx *c, const Built &b, const uint64_t *d_seg_offsets, uint64_t n_segs,
                                b200_updates *u) {
     memset(u, 0, sizeof *u);
     UpdatesOwner *owner = new UpdatesOwner();
     u->_owner = owner;
     cudaStream_t st = c->stream;
-    const uint32_t B = b.n_nodes;
     uint32_t n_stored = 0, n_hashes = 0;
-    uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
-    if (B) {
-        ENSURE(upd_flags, B);
-        ENSURE(upd_nh, (size_t)B * 4);
-        ENSURE(upd_ids, (size_t)B * 4);
-        ENSURE(upd_prefix, (size_t)(B + 1) * 4);
-        uint8_t *flags = static_cast<uint8_t *>(c->upd_flags.p);
-        uint32_t *nh = static_cast<uint32_t *>(c->upd_nh.p);
-        uint32_t *ids = static_cast<uint32_t *>(c->upd_ids.p);
-        uint32_t *prefix = static_cast<uint32_t *>(c->upd_prefix.p);
-        uint32_t *n_stored_p = small_u32(c) + SM_NSTORED;
-        CU(launch_stored_flags(b.f, B, flags, nh, st));
-        size_t t_sel = 0, t_scan = 0;
-        thrust::counting_iterator<uint32_t> counting(0);
-        CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, flags, ids, n_stored_p, (int64_t)B, st));
-        CU(cub::DeviceScan::ExclusiveSum(nullptr, t_scan, nh, prefix, (int64_t)B, st));
-        ENSURE(cub_temp, std::max(t_sel, t_scan));
-        CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, flags, ids, n_stored_p, (int64_t)B, st));
-        CU(cub::DeviceScan::ExclusiveSum(c->cub_temp.p, t_scan, nh, prefix, (int64_t)B, st));
-        c->launches += 3;
-        CU(cudaMemcpyAsync(ps + 200, n_stored_p, 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(ps + 201, prefix + (B - 1), 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(ps + 202, nh + (B - 1), 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        n_stored = ps[200];
-        n_hashes = ps[201] + ps[202];
-    }
-    if (n_stored == 0)
-        return gather_and_copy(c, b.f, nullptr, 0, 0, nullptr, nullptr, d_seg_offsets, n_segs, u, owner);
-    // Records leave the device in table order (ascending trie, then path): the selected ids are in (depth, position)
-    // order, one radix sort by (leftmost leaf, depth) puts them in pre-order; the hash offsets are re-scanned in that
-    // order so that hashes follow their records.
-    ENSURE(upd_key, (size_t)n_stored * 8);
-    ENSURE(upd_key2, (size_t)n_stored * 8);
-    ENSURE(upd_ids2, (size_t)n_stored * 4);
-    uint32_t *ids = static_cast<uint32_t *>(c->upd_ids.p), *ids2 = static_cast<uint32_t *>(c->upd_ids2.p);
-    uint64_t *key = static_cast<uint64_t *>(c->upd_key.p), *key2 = static_cast<uint64_t *>(c->upd_key2.p);
+    const uint32_t *ids = nullptr;
+    TRY(stored_ids_in_table_order(c, b, &n_stored, &n_hashes, &ids));
+    if (n_stored == 0) return gather_and_copy(c, b.f, nullptr, 0, 0, nullptr, nullptr, d_seg_offsets, n_segs, u, owner);
     uint8_t *flags = static_cast<uint8_t *>(c->upd_flags.p);
     uint32_t *nh = static_cast<uint32_t *>(c->upd_nh.p), *prefix = static_cast<uint32_t *>(c->upd_prefix.p);
-    CU(launch_table_order_keys(b.f, ids, n_stored, key, st));
-    size_t t_sort = 0, t_scan = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, key, key2, ids, ids2, (int64_t)n_stored, 0, 40, st));
+    size_t t_scan = 0;
+    CU(launch_stored_flags_subset(b.f, ids, n_stored, flags, nh, st));  // (all flagged; nh in record order)
     CU(cub::DeviceScan::ExclusiveSum(nullptr, t_scan, nh, prefix, (int64_t)n_stored, st));
-    ENSURE(cub_temp, std::max(t_sort, t_scan));
-    CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_sort, key, key2, ids, ids2, (int64_t)n_stored, 0, 40, st));
-    CU(launch_stored_flags_subset(b.f, ids2, n_stored, flags, nh, st));  // (all flagged; nh in record order)
+    ENSURE(cub_temp, t_scan);
     CU(cub::DeviceScan::ExclusiveSum(c->cub_temp.p, t_scan, nh, prefix, (int64_t)n_stored, st));
-    c->launches += 4;
-    return gather_and_copy(c, b.f, ids2, n_stored, n_hashes, nullptr, prefix, d_seg_offsets, n_segs, u, owner);
+    c->launches += 2;
+    return gather_and_copy(c, b.f, ids, n_stored, n_hashes, nullptr, prefix, d_seg_offsets, n_segs, u, owner);
+}
+
+// The same stored nodes as finished AccountsTrie / StoragesTrie rows (b200_rows, page-locked host memory): sizes, one
+// scan, one warp per row writing table bytes, one D2H (tk_outputs.cuh; byte-identical to csrc/table_rows.cu's layout).
+struct RowsOwner {  // shared with table_rows.cu (b200_rows_release)
+    void *block;
+    int pinned;
+};
+static int32_t collect_rows(b200_ctx *c, const Built &b, const uint64_t *d_seg_offsets, uint64_t n_segs,
+                            const uint8_t *d_acct_keys, int32_t fmt, bool storage, b200_rows *rows) {
+    memset(rows, 0, sizeof *rows);
+    cudaStream_t st = c->stream;
+    uint32_t n_stored = 0, n_hashes = 0;
+    const uint32_t *ids = nullptr;
+    TRY(stored_ids_in_table_order(c, b, &n_stored, &n_hashes, &ids));
+    const int packed = fmt == B200_KEYS_PACKED ? 1 : 0;
+    const size_t n = n_stored;
+    // device: [size (n+1) u64][row_off (n+1) u64][key_len n u32]
+    ENSURE(upd_key, (n + 1) * 8);
+    ENSURE(upd_key2, (n + 1) * 8);
+    ENSURE(upd_nh, (n + 1) * 4);
+    uint64_t *size = static_cast<uint64_t *>(c->upd_key.p), *row_off = static_cast<uint64_t *>(c->upd_key2.p);
+    uint32_t *key_len = static_cast<uint32_t *>(c->upd_nh.p);
+    size_t t_scan = 0;
+    CU(launch_row_sizes(b.f, ids, n_stored, packed, storage ? 1 : 0, size, key_len, st));
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, t_scan, size, row_off, (int64_t)(n + 1), st));
+    ENSURE(cub_temp, t_scan);
+    CU(cub::DeviceScan::ExclusiveSum(c->cub_temp.p, t_scan, size, row_off, (int64_t)(n + 1), st));
+    c->launches += 2;
+    uint64_t *h_total = reinterpret_cast<uint64_t *>(static_cast<uint32_t *>(c->pinned_small) + 204);
+    CU(cudaMemcpyAsync(h_total, row_off + n, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint64_t total = *h_total;
+    const size_t off_bytes = (n + 1) * sizeof(uint64_t), kl_bytes = ((n * sizeof(uint32_t)) + 7) & ~size_t(7);
+    RowsOwner *owner = new RowsOwner{nullptr, 1};
+    rows->_owner = owner;
+    CU(cudaMallocHost(&owner->block, off_bytes + kl_bytes + (total ? total : 1)));
+    uint8_t *h = static_cast<uint8_t *>(owner->block);
+    rows->row_offset = reinterpret_cast<uint64_t *>(h);
+    rows->key_len = reinterpret_cast<uint32_t *>(h + off_bytes);
+    rows->bytes = h + off_bytes + kl_bytes;
+    rows->n_rows = n;
+    if (n) {
+        ENSURE(out_a, total);
+        uint8_t *d_bytes = static_cast<uint8_t *>(c->out_a.p);
+        CU(launch_encode_rows(b.f, ids, n_stored, packed, storage ? 1 : 0, d_seg_offsets, n_segs, d_acct_keys, row_off, d_bytes,
+                              st));
+        c->launches++;
+        CU(cudaMemcpyAsync(rows->key_len, key_len, n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(rows->bytes, d_bytes, total, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaMemcpyAsync(rows->row_offset, row_off, off_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return B200_OK;
 }
 
 // Same for a subset of nodes given by id (the dirty nodes of an incremental update), in list order.

@@ -16,12 +16,18 @@
 //                          (crates/storage/provider/src/providers/database/provider.rs:3125-3160,
 //                          crates/trie/db/src/trie_cursor.rs:280-312)
 #include "b200trie.h"
+#include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
+
+struct RowsOwner {  // == engine.cu's (eng_updates.inl)
+    void *block;
+    int pinned;
+};
 
 namespace {
 
@@ -102,7 +108,7 @@ int32_t encode(const b200_updates *u, const uint8_t *acct_keys32, uint64_t n_acc
     size_t off_bytes = (n + 1) * sizeof(uint64_t), kl_bytes = ((n * sizeof(uint32_t)) + 7) & ~size_t(7);
     uint8_t *block = (uint8_t *)malloc(off_bytes + kl_bytes + (total ? total : 1));
     if (!block) return B200_ERR_OOM;
-    out->_owner = block;
+    out->_owner = new RowsOwner{block, 0};
     out->row_offset = (uint64_t *)block;
     out->key_len = (uint32_t *)(block + off_bytes);
     out->bytes = block + off_bytes + kl_bytes;
@@ -148,7 +154,12 @@ B200_API int32_t b200_storage_trie_rows(const b200_updates *storage_updates, con
 
 B200_API void b200_rows_release(b200_rows *r) {
     if (!r) return;
-    free(r->_owner);
+    if (r->_owner) {
+        RowsOwner *o = static_cast<RowsOwner *>(r->_owner);
+        if (o->pinned) cudaFreeHost(o->block);  // rows encoded on the device (eng_updates.inl: collect_rows)
+        else free(o->block);
+        delete o;
+    }
     memset(r, 0, sizeof *r);
 }
 

@@ -172,6 +172,20 @@ cudaError_t launch_table_order_keys(const ForestDev &f, const uint32_t *ids, uin
     table_order_keys_kernel<<<blocks_for(count, 256), 256, 0, st>>>(f, ids, count, keys);
     return cudaGetLastError();
 }
+cudaError_t launch_row_sizes(const ForestDev &f, const uint32_t *ids, uint32_t count, int packed, int storage, uint64_t *size,
+                             uint32_t *key_len, cudaStream_t st) {
+    row_sizes_kernel<<<blocks_for((uint64_t)count + 1, 256), 256, 0, st>>>(f, ids, count, packed, storage, size, key_len);
+    return cudaGetLastError();
+}
+cudaError_t launch_encode_rows(const ForestDev &f, const uint32_t *ids, uint32_t count, int packed, int storage,
+                               const uint64_t *d_seg_offsets, uint64_t n_segs, const uint8_t *acct_keys,
+                               const uint64_t *row_off, uint8_t *out, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    constexpr int WARPS = 8;
+    encode_rows_kernel<WARPS><<<blocks_for(count, WARPS), WARPS * 32, 0, st>>>(f, ids, count, packed, storage, d_seg_offsets,
+                                                                              n_segs, acct_keys, row_off, out);
+    return cudaGetLastError();
+}
 cudaError_t launch_gather_updates(const ForestDev &f, const uint32_t *stored_ids, uint32_t n_stored,
                                   const uint32_t *hash_prefix, const uint32_t *prefix_by_record,
                                   const uint64_t *d_seg_offsets, uint64_t n_segs, const UpdatesDev &out,

@@ -115,3 +115,88 @@ __global__ void gather_updates_kernel(ForestDev f, const uint32_t *__restrict__ 
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------ table rows on the device
+// AccountsTrie / StoragesTrie rows of the stored nodes, byte for byte what csrc/table_rows.cu lays out on the host
+// (StoredNibbles / StoredNibblesSubKey / packed keys ‖ BranchNodeCompact: 3 × u16 BE masks ‖ hashes), encoded where the
+// nodes are: one D2H of finished table bytes instead of records + a host pass.
+__device__ __forceinline__ uint32_t row_key_bytes(int packed, int storage, uint32_t d) {
+    return packed ? 33u : (storage ? 65u : d);
+}
+
+__global__ void row_sizes_kernel(ForestDev f, const uint32_t *__restrict__ ids, uint32_t count, int packed, int storage,
+                                 uint64_t *__restrict__ size, uint32_t *__restrict__ key_len) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > count) return;
+    if (t == count) {  // the scan's last output is the total
+        size[t] = 0;
+        return;
+    }
+    ushort4 mk = f.node_masks[ids[t]];
+    uint32_t kb = row_key_bytes(packed, storage, mk.w);
+    size[t] = (storage ? 32u : 0u) + kb + 6u + 32u * (uint32_t)__popc((uint32_t)mk.z);
+    key_len[t] = storage ? 32u : kb;
+}
+
+// One warp per row; lanes stride over the row's bytes.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) encode_rows_kernel(ForestDev f, const uint32_t *__restrict__ ids, uint32_t count,
+                                                                 int packed, int storage,
+                                                                 const uint64_t *__restrict__ seg_offsets, uint64_t n_segs,
+                                                                 const uint8_t *__restrict__ acct_keys,
+                                                                 const uint64_t *__restrict__ row_off,
+                                                                 uint8_t *__restrict__ out) {
+    __shared__ uint32_t hashed_child[WARPS][16];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t t = blockIdx.x * WARPS + w;
+    if (t >= count) return;
+    const uint32_t v = ids[t];
+    const ushort4 mk = f.node_masks[v];
+    const uint32_t d = mk.w, l = f.node_l[v];
+    uint32_t tid = 0;
+    if (storage) {  // trie id = segment containing leaf l
+        uint64_t lo = 0, hi = n_segs;
+        while (lo + 1 < hi) {
+            uint64_t mid = (lo + hi) >> 1;
+            if (seg_offsets[mid] <= l) lo = mid;
+            else hi = mid;
+        }
+        tid = (uint32_t)lo;
+    }
+    // children under hash_mask, by rank: lane c looks at child c
+    const uint32_t j0 = f.node_start[v], k = f.node_start[v + 1] - j0;
+    if (lane <= k) {
+        ChildInfo ci = fetch_child(f, j0, lane);
+        if (mk.z & (1u << ci.nib)) hashed_child[w][__popc((uint32_t)mk.z & ((1u << ci.nib) - 1u))] = ci.id - (uint32_t)f.n;
+    }
+    __syncwarp();
+    const uint8_t *key = f.keys + 32 * (uint64_t)l;
+    const uint32_t a_len = storage ? 32u : 0u, kb = row_key_bytes(packed, storage, d);
+    const uint32_t m0 = a_len + kb, h0 = m0 + 6u, total = h0 + 32u * (uint32_t)__popc((uint32_t)mk.z);
+    uint8_t *row = out + row_off[t];
+    for (uint32_t j = lane; j < total; j += 32) {
+        uint32_t x;
+        if (j < a_len) {
+            x = acct_keys[32 * (uint64_t)tid + j];
+        } else if (j < m0) {
+            uint32_t jj = j - a_len;
+            if (jj == kb - 1 && (packed || storage)) {
+                x = d;  // trailing length byte of the packed key / of the subkey
+            } else if (packed) {
+                x = 0;
+                if (2 * jj < d) x = key[jj] & 0xF0;
+                if (2 * jj + 1 < d) x |= key[jj] & 0x0F;
+            } else {
+                x = jj < d ? ((jj & 1) ? (key[jj >> 1] & 15u) : (key[jj >> 1] >> 4)) : 0u;
+            }
+        } else if (j < h0) {
+            uint32_t q = j - m0;
+            uint32_t m = q < 2 ? mk.x : (q < 4 ? mk.y : mk.z);
+            x = (q & 1) ? (m & 0xff) : (m >> 8);
+        } else {
+            uint32_t q = j - h0;
+            x = f.node_ref[32 * (uint64_t)hashed_child[w][q >> 5] + (q & 31)];
+        }
+        row[j] = (uint8_t)x;
+    }
+}

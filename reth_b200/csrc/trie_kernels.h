@@ -93,6 +93,11 @@ cudaError_t launch_segment_roots(const ForestDev &f, const uint64_t *d_seg_offse
 cudaError_t launch_stored_flags(const ForestDev &f, uint32_t n_nodes, uint8_t *flags, uint32_t *n_hashes,
                                 cudaStream_t st);
 cudaError_t launch_table_order_keys(const ForestDev &f, const uint32_t *ids, uint32_t count, uint64_t *keys, cudaStream_t st);
+cudaError_t launch_row_sizes(const ForestDev &f, const uint32_t *ids, uint32_t count, int packed, int storage, uint64_t *size,
+                             uint32_t *key_len, cudaStream_t st);
+cudaError_t launch_encode_rows(const ForestDev &f, const uint32_t *ids, uint32_t count, int packed, int storage,
+                               const uint64_t *d_seg_offsets, uint64_t n_segs, const uint8_t *acct_keys,
+                               const uint64_t *row_off, uint8_t *out, cudaStream_t st);
 cudaError_t launch_gather_updates(const ForestDev &f, const uint32_t *stored_ids, uint32_t n_stored,
                                   const uint32_t *hash_prefix, const uint32_t *prefix_by_record,
                                   const uint64_t *d_seg_offsets, uint64_t n_segs, const UpdatesDev &out,

@@ -263,10 +263,13 @@ class Engine:
             res.append(s.as_dict())
         return res[0] if len(res) == 1 else tuple(res)
 
-    def state_root_full_rows(self, acct_keys, accounts, slot_keys, values, seg_offsets, key_format: int = 0):
+    def state_root_full_rows(self, acct_keys, accounts, slot_keys, values, seg_offsets, key_format: int = 0,
+                             encode_on_host: bool = False):
         """state_root_full, with the stored nodes returned as AccountsTrie / StoragesTrie table rows in MDBX key
         order (reth_b200.tables.TableRows; key_format 0 = legacy nibble keys, 1 = storage-v2 packed keys) — what
-        MerkleStage hands to write_trie_updates_sorted (crates/stages/stages/src/stages/merkle.rs:184-366)."""
+        MerkleStage hands to write_trie_updates_sorted (crates/stages/stages/src/stages/merkle.rs:184-366).
+        Rows are encoded on the device (b200_state_root_full_rows); encode_on_host=True takes the records and lays the
+        rows out with b200_account_trie_rows / b200_storage_trie_rows instead (same bytes)."""
         from . import tables
         acct_keys = _np(acct_keys).reshape(-1, 32)
         accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
@@ -276,6 +279,12 @@ class Engine:
         if len(seg_offsets) != len(acct_keys) + 1:
             raise ValueError("seg_offsets must have n_accounts+1 entries")
         root = np.empty(32, np.uint8)
+        if not encode_on_host:
+            ra, rs = _lib.Rows(), _lib.Rows()
+            self._check(self.lib.b200_state_root_full_rows(
+                self.ctx, _ptr(acct_keys), _ptr(accounts), len(acct_keys), _ptr(slot_keys), _ptr(values),
+                _ptr(seg_offsets), key_format, _ptr(root), C.byref(ra), C.byref(rs), None))
+            return root.tobytes(), tables.TableRows(ra, self.lib), tables.TableRows(rs, self.lib)
         ua, us, s = Updates(), Updates(), Stats()
         self._check(self.lib.b200_state_root_full(
             self.ctx, _ptr(acct_keys), _ptr(accounts), len(acct_keys), _ptr(slot_keys), _ptr(values),

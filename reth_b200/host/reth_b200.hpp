@@ -495,6 +495,22 @@ class StateRoot {
         return {p.root, std::move(p.updates)};
     }
     StateRootProgress root_with_progress() const { return calculate(true); }
+    /// The rebuild leg of MerkleStage in one call (merkle.rs:216-253 → write_trie_updates): the root and the stored nodes
+    /// as AccountsTrie / StoragesTrie rows in table order, laid out on the device (b200_state_root_full_rows).
+    struct RootWithTables {
+        B256 root;
+        std::vector<TableRow> accounts_trie, storages_trie;
+    };
+    RootWithTables root_with_table_rows(b200_key_format fmt = B200_KEYS_LEGACY) const {
+        FlatState f = state_.to_flat();
+        RootWithTables out;
+        b200_rows ar{}, sr{};
+        e_.check(b200_state_root_full_rows(e_.raw(), f.acct_keys.data(), f.accts.data(), f.n_accounts(), f.slot_keys.data(),
+                                           f.slot_values.data(), f.seg_offsets.data(), fmt, out.root.data(), &ar, &sr, nullptr));
+        out.accounts_trie = detail::take_rows(ar);
+        out.storages_trie = detail::take_rows(sr);
+        return out;
+    }
 
   protected:
     StateRootProgress calculate(bool retain_updates) const {

@@ -197,6 +197,17 @@ static void random_state_vs_oracle(const Engine &e) {
     CHECK(storage_nodes == os.n_nodes);
     orc_updates_free(&oa);
     orc_updates_free(&os);
+    // rows laid out on the device == rows the host encoder makes of the same build's TrieUpdates (first validated under
+    // tools/emu: opt-in on a GPU like the dynamic tries)
+    if (std::getenv("B200_EMU") || std::getenv("B200_DTRIE_ON_GPU")) {
+        for (b200_key_format fmt : {B200_KEYS_LEGACY, B200_KEYS_PACKED}) {
+            auto t = StateRoot(e, sorted).root_with_table_rows(fmt);
+            CHECK(t.root == oroot);
+            CHECK(t.accounts_trie == account_trie_rows(upd, fmt));
+            CHECK(t.storages_trie == storage_trie_rows(upd, fmt));
+            CHECK(!t.accounts_trie.empty() && !t.storages_trie.empty());
+        }
+    }
 }
 
 // DynamicTrie: blocks of inserts / deletes / updates applied in place == oracle root over the merged state, and the

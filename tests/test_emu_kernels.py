@@ -17,7 +17,7 @@ FAST = ("not one_million and not pipelined and not reentrancy and not frontier_s
 def test_cuda_sources_pass_parity_under_cpu_emulation():
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_trie.py", "tests/test_gpu_keccak.py",
                         "tests/test_gpu_host_mirror.py", "tests/test_gpu_dtrie.py", "tests/test_gpu_dstate.py", "tests/test_gpu_proofs.py",
-                        "tests/test_gpu_zz_ordered_roots.py", "-m", "gpu", "--emu", "-q", "-x", "-k", FAST,
+                        "tests/test_gpu_zz_ordered_roots.py", "tests/test_gpu_zz_table_rows_device.py", "-m", "gpu", "--emu", "-q", "-x", "-k", FAST,
                         "-p", "no:cacheprovider"],
                        cwd=ROOT, capture_output=True, text=True, timeout=1500)
     tail = (r.stdout + r.stderr)[-3000:]

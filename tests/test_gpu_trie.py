@@ -198,7 +198,7 @@ def test_full_state_table_rows(eng, packed):
     akeys, accs = synth_accounts(21, n)
     counts = np.where(np.arange(n) % 4 == 0, 24, 0) + np.where(np.arange(n) % 1999 == 0, 2500, 0)
     skeys, svals, offs = synth_storage(22, counts, value_mode="mixed")
-    root, arows, srows = eng.state_root_full_rows(akeys, accs, skeys, svals, offs, key_format=packed)
+    root, arows, srows = eng.state_root_full_rows(akeys, accs, skeys, svals, offs, key_format=packed, encode_on_host=True)
     o_root, o_au, o_su = oracle.state_root_full(akeys, accs, skeys, svals, offs, want_updates=True, threads=4)
     assert root == o_root
     assert arows.to_list() == expected_account_rows(o_au, bool(packed))
