@@ -21,6 +21,10 @@ export B200_DTRIE_ON_GPU=1
   timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_zz_ordered_roots.py -m gpu -q -x -k "shapes or golden" 2>&1 | tail -8
   timeout 600 python tools/ordered_bench.py --blocks 2000 --items 200 --shape receipts 2>&1 | tail -1
   timeout 600 python tools/ordered_bench.py --blocks 2000 --items 200 --shape transactions 2>&1 | tail -1
+  echo "== table rows laid out on the device"
+  timeout 600 python -m pytest tests/test_gpu_zz_table_rows_device.py -m gpu -q 2>&1 | tail -3
+  timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_zz_table_rows_device.py -m gpu -q -x -k "degenerate or genesis" 2>&1 | tail -8
+  timeout 600 python tools/rows_bench.py --accounts 1000000 --slots 16 2>&1 | tail -1
   echo "== (afterwards: python bench.py --dynamic adds these legs to the official JSON line)"
   echo "== dynamic trie latency vs merge+rebuild (C5 shape)"
   timeout 600 python tools/dtrie_bench.py --base 100000000 --dirty 10000 --mix 100,0,0 2>&1 | tail -2
