@@ -705,7 +705,8 @@ def bench_incremental(args, eng, dev):
 
 
 def bench_dynamic(args):
-    """--dynamic: the emulation-validated dynamic trie / state, each in its own process (its own CUDA context and a
+    """--dynamic: the emulation-validated parts (dynamic trie / state, ordered roots, device table rows), each in its own
+    process (its own CUDA context and a
     timeout), so that whatever happens there cannot touch the numbers above."""
     import subprocess
     root = os.path.dirname(os.path.abspath(__file__))
@@ -714,6 +715,9 @@ def bench_dynamic(args):
         "dtrie_value_updates": ["tools/dtrie_bench.py", "--base", str(args.base_accounts), "--dirty", str(args.dirty), "--mix", "100,0,0"],
         "dtrie_mixed_block": ["tools/dtrie_bench.py", "--base", str(args.base_accounts), "--dirty", str(args.dirty), "--mix", "80,10,10"],
         "dstate_c3_shape": ["tools/dstate_bench.py", "--accounts", "1000000", "--slots", "16", "--touch", "2000", "--slot-writes", "10"],
+        "ordered_roots_receipts": ["tools/ordered_bench.py", "--blocks", "2000", "--items", "200", "--shape", "receipts"],
+        "ordered_roots_transactions": ["tools/ordered_bench.py", "--blocks", "2000", "--items", "200", "--shape", "transactions"],
+        "table_rows_c3_shape": ["tools/rows_bench.py", "--accounts", "1000000", "--slots", "16"],
     }
     for name, cmd in runs.items():
         try:
