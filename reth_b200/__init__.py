@@ -11,7 +11,7 @@ from .hashed_state import (Account, HashedPostState, HashedPostStateSorted, Hash
 from .stages import AccountHashingStage, MerkleStage, StageError, StorageHashingStage, Tables  # noqa: F401,E402
 from .trie import (BranchNodeCompact, DynamicStateRoot, ParallelStateRoot, ResidentStateRoot, StateRoot, StateRootError, StateRootProgress,  # noqa: F401,E402
                    StorageRoot, StorageTrieUpdates, TrieUpdates)
-from .sharded import ShardedDynamicStateRoot  # noqa: F401,E402
+from .sharded import ShardedDynamicStateRoot, sharded_ordered_trie_roots  # noqa: F401,E402
 from .verify import Verifier  # noqa: F401,E402
 from .ordered_root import (OrderedRootError, OrderedTrieRootEncodedBuilder, ordered_trie_root_encoded,  # noqa: F401,E402
                            ordered_trie_roots)

@@ -60,3 +60,37 @@ class ShardedDynamicStateRoot:
 
     def close(self):
         self.local.close()
+
+
+def list_range_of(rank: int, world: int, n_lists: int) -> Tuple[int, int]:
+    """Contiguous share of a batch of lists (blocks) for a rank."""
+    return rank * n_lists // world, (rank + 1) * n_lists // world
+
+
+def sharded_ordered_trie_roots(engine: Engine, lists, rank: int, world: int, group=None):
+    """Ordered (transactions / receipts / withdrawals) roots of a batch of lists over `world` ranks: the lists are
+    independent tries, so rank r folds lists [r·n/world, (r+1)·n/world) with b200_ordered_roots — no data-path
+    collective — and only the 32-byte roots are all-gathered.  `lists` may be the full batch on every rank (only the
+    rank's share is read).  -> all roots, in list order, on every rank."""
+    from .ordered_root import ordered_trie_roots
+    n = len(lists)
+    lo, hi = list_range_of(rank, world, n)
+    mine = ordered_trie_roots(engine, lists[lo:hi])
+    if world == 1:
+        return mine
+    import torch
+    import torch.distributed as dist
+    width = (n + world - 1) // world                                   # every rank contributes a fixed-size block
+    buf = np.zeros((width, 32), np.uint8)
+    if mine:
+        buf[:len(mine)] = np.frombuffer(b"".join(mine), np.uint8).reshape(-1, 32)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.from_numpy(buf.reshape(-1)).to(dev)
+    gathered = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t, group=group)
+    out = []
+    for r in range(world):
+        r_lo, r_hi = list_range_of(r, world, n)
+        rows = gathered[r].cpu().numpy().reshape(width, 32)
+        out += [rows[i].tobytes() for i in range(r_hi - r_lo)]
+    return out
