@@ -52,7 +52,9 @@ extern "C" B200_API int32_t b200_ordered_roots_dev(b200_ctx *c, const void *d_va
                                                    uint64_t n_items, void *d_roots32) {
     if (!c || !d_seg_offsets || (n_lists && !d_roots32) || (n_items && !d_value_offsets) || (values_len && !d_values))
         return fail(c, B200_ERR_INVALID_ARG, "bad argument");
-    if (!aligned16(d_roots32) || (reinterpret_cast<uintptr_t>(d_value_offsets) & 7) || (reinterpret_cast<uintptr_t>(d_seg_offsets) & 7))
+    const bool offsets_aligned =
+        !(reinterpret_cast<uintptr_t>(d_value_offsets) & 7) && !(reinterpret_cast<uintptr_t>(d_seg_offsets) & 7);
+    if (!aligned16(d_roots32) || !offsets_aligned)
         return fail(c, B200_ERR_INVALID_ARG, "device buffers must be aligned (roots 16, offsets 8)");
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));

@@ -67,7 +67,10 @@ __global__ void ordered_keys_kernel(const uint64_t *__restrict__ seg_offsets, ui
     pos[p] = (uint32_t)p;
 }
 
-static __device__ __forceinline__ uint32_t ord_be_len(uint32_t x) { return x < 0x100 ? 1 : (x < 0x10000 ? 2 : (x < 0x1000000 ? 3 : 4)); }
+// bytes of the big-endian representation of a length
+static __device__ __forceinline__ uint32_t ord_be_len(uint32_t x) {
+    return x < 0x100 ? 1 : (x < 0x10000 ? 2 : (x < 0x1000000 ? 3 : 4));
+}
 
 struct OrdPrefix {  // the bytes of a leaf in front of its value: list header, hex-prefix path, string header
     uint8_t b[24];
