@@ -33,6 +33,8 @@ static int32_t ordered_roots_on_device(b200_ctx *c, const uint8_t *d_values, uin
         o.key_nibs = static_cast<const uint8_t *>(c->ord_knib.p);
         o.item = static_cast<const uint32_t *>(c->ord_item.p);
         o.order = order;
+        o.sched_sorted = sched2;
+        o.n_long = small_u32(c) + SM_ORD_NLONG;
         o.values = d_values;
         o.val_off = d_val_off;
         o.blob_len = blob_len;

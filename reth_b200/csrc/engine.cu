@@ -28,7 +28,7 @@ static thread_local int g_create_status = 0;
 static constexpr uint32_t WARP_LEVEL_MAX = 4096;
 
 // layout of the `small` device buffer (uint32 units)
-enum : int { SM_BUCKET_OFF = 0, SM_LEVEL_LO = 80, SM_NNODES = 160, SM_ERR = 164, SM_NSTORED = 168, SM_COUNTERS = 176 /* 4 x u64 */, SM_HIST = 256 /* 256 x u32 */, SM_WORDS = 512 };
+enum : int { SM_BUCKET_OFF = 0, SM_LEVEL_LO = 80, SM_NNODES = 160, SM_ERR = 164, SM_NSTORED = 168, SM_ORD_NLONG = 170, SM_COUNTERS = 176 /* 4 x u64 */, SM_HIST = 256 /* 256 x u32 */, SM_WORDS = 512 };
 
 static uint32_t *small_u32(b200_ctx *c) { return static_cast<uint32_t *>(c->small.p); }
 

@@ -142,6 +142,8 @@ struct OrderedLeavesDev {
     const uint8_t *key_nibs;  // [n] true key length in nibbles (the padded keys are ForestDev::keys)
     const uint32_t *item;     // [n] item (in list order) carried by the leaf at this sorted position
     const uint32_t *order;    // [n] leaf positions in the order the leaf pass visits them (longest item first)
+    const uint16_t *sched_sorted;  // [n] the sorted scheduling keys (65535 - Keccak blocks of the item)
+    uint32_t *n_long;         // device word: leading entries of `order` that get a warp each
     const uint8_t *values;    // concatenated pre-encoded items
     const uint64_t *val_off;  // [n+1] byte offsets of the items in `values`
     uint64_t blob_len;

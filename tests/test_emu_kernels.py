@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FAST = ("not one_million and not pipelined and not reentrancy and not frontier_sharding and not commits_blocks "
-        "and not 200000 and not three_byte_index")
+        "and not 200000 and not receipt_and_transaction_shaped")
 
 
 def test_cuda_sources_pass_parity_under_cpu_emulation():

@@ -140,6 +140,20 @@ def test_receipt_and_transaction_shaped_batch(eng):
     assert (eng.ordered_roots(*packed) == oracle.ordered_roots(*packed)).all()
 
 
+def test_long_items_take_the_warp_path(eng):
+    """items of >= 32 rate blocks (≈4.3 KB) are hashed by a warp each: lengths either side of that switch, block
+    multiples, and a maximum-size (128 KiB) calldata transaction, mixed with short items in the same lists"""
+    rng = np.random.default_rng(15)
+    lens = [4300, 4334, 4335, 4336, 4351, 4352, 4353, 8192, 13600 - 9, 13600, 40000, 131072]
+    big = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
+    small = _random_items(rng, 150, [1, 40, 110, 300])
+    lists = [big[:4] + small[:50], small[50:100], [big[11]], small[100:] + big[4:]]
+    packed = oracle.pack_lists(lists)
+    assert (eng.ordered_roots(*packed) == oracle.ordered_roots(*packed)).all()
+    for skew in (1, 5):
+        assert (_dev_roots(eng, *packed, skew=skew) == oracle.ordered_roots(*packed)).all()
+
+
 def test_bad_offsets_are_rejected(eng):
     from reth_b200 import B200Error
     vals = np.zeros(10, np.uint8)
