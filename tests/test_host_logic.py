@@ -99,3 +99,41 @@ def test_storage_trie_updates_semantics():
 def test_empty_state_flat():
     keys, accts, skeys, svals, offs = HashedPostStateSorted().to_flat()
     assert keys.shape == (0, 32) and skeys.shape == (0, 32) and list(offs) == [0]
+
+
+# ---------------------------------------------------------------- ordered roots: host side (no device needed)
+def test_ordered_root_builder_bookkeeping_and_errors():
+    """crates/trie/common/src/ordered_root.rs:315-353 — the parts that never reach the device"""
+    import pytest
+    from reth_b200 import EMPTY_ROOT_HASH, OrderedRootError, OrderedTrieRootEncodedBuilder
+    b = OrderedTrieRootEncodedBuilder.new(None, 0)
+    assert b.is_complete() and b.finalize() == EMPTY_ROOT_HASH          # :241-243, no engine involved
+    b = OrderedTrieRootEncodedBuilder.new(None, 3)
+    b.push(2, b"c")
+    b.push(0, b"a")
+    assert (b.pushed_count(), b.expected_count(), b.is_complete()) == (2, 3, False)
+    with pytest.raises(OrderedRootError) as e:
+        b.finalize()
+    assert e.value.is_incomplete() and e.value.index() is None
+    assert str(e.value) == "incomplete: expected 3 items, received 2"     # Display impl :66-80
+    with pytest.raises(OrderedRootError) as e:
+        b.push(3, b"x")
+    assert e.value.is_index_out_of_bounds() and str(e.value) == "index 3 out of bounds for length 3"
+    with pytest.raises(OrderedRootError) as e:
+        b.push(2, b"again")
+    assert e.value.is_duplicate_index() and str(e.value) == "duplicate item at index 2" and e.value.index() == 2
+
+
+def test_ordered_root_pack_lists_and_rank_shares():
+    from reth_b200.ordered_root import pack_lists
+    from reth_b200.sharded import list_range_of
+    values, vo, so = pack_lists([[b"ab", b""], [], [b"cde"]])
+    assert values.tobytes() == b"abcde" and list(vo) == [0, 2, 2, 5] and list(so) == [0, 2, 2, 3]
+    values, vo, so = pack_lists([])
+    assert len(values) == 0 and list(vo) == [0] and list(so) == [0]
+    for n in (0, 1, 7, 16, 1000):
+        for world in (1, 2, 3, 8):
+            shares = [list_range_of(r, world, n) for r in range(world)]
+            assert shares[0][0] == 0 and shares[-1][1] == n
+            assert all(shares[r][1] == shares[r + 1][0] for r in range(world - 1))
+            assert max(hi - lo for lo, hi in shares) - min(hi - lo for lo, hi in shares) <= 1
