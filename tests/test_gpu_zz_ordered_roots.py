@@ -5,7 +5,8 @@ Bit-exact.  (Named to run last: first validated under tools/emu, see DESIGN.md Â
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+# first hardware run happens at round end: bound a hang (method=thread ends the process even inside a blocked CUDA sync)
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]
 
 import oracle
 from tests.test_ordered_root_oracle import golden_cases

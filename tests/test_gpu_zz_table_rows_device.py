@@ -5,7 +5,8 @@ b200_storage_trie_rows).  Byte-exact.  (Named to run last: first validated under
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+# first hardware run happens at round end: bound a hang (method=thread ends the process even inside a blocked CUDA sync)
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]
 
 import oracle
 from tests.test_table_rows import expected_account_rows, expected_storage_rows
