@@ -58,6 +58,7 @@ extern "C" B200_API int32_t b200_ordered_roots_dev(b200_ctx *c, const void *d_va
         !(reinterpret_cast<uintptr_t>(d_value_offsets) & 7) && !(reinterpret_cast<uintptr_t>(d_seg_offsets) & 7);
     if (!aligned16(d_roots32) || !offsets_aligned)
         return fail(c, B200_ERR_INVALID_ARG, "device buffers must be aligned (roots 16, offsets 8)");
+    if (n_items && !n_lists) return fail(c, B200_ERR_INVALID_ARG, "items without a list");  // (the key pass reads seg_offsets[1])
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
     TRY(reset_build_state(c));

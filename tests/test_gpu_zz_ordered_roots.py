@@ -199,4 +199,6 @@ def test_device_side_offset_validation(eng):
                            (vo, np.array([2, 3], np.uint64))]:                    # does not start at 0
         with pytest.raises(B200Error):
             _dev_roots(eng, values, bad_vo, bad_so)
+    with pytest.raises(B200Error):   # items but no list: refused on the host, before any launch
+        _dev_roots(eng, values, vo, np.array([0], np.uint64))
     assert (_dev_roots(eng, *ok) == oracle.ordered_roots(*ok)).all()
