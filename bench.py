@@ -58,11 +58,32 @@ def effective_cpus() -> int:
     return n
 
 
+OUT_FD = [None]  # the real stdout when fd 1 is parked on stderr (multi-rank runs)
+
+
+def emit(line: dict) -> None:
+    """The one JSON line of the run, on the real stdout."""
+    txt = json.dumps(line) + "\n"
+    if OUT_FD[0] is None:
+        sys.stdout.write(txt)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(OUT_FD[0], txt.encode())
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
     except ValueError:
         return default
+
+
+def c2_config(n_keys: int, world: int) -> dict:
+    """`config` of the headline line: the same dict on both arms (the driver compares them)."""
+    return {"workload": "C2: batch keccak256 of 10M 32-byte keys per GPU (AccountHashing/StorageHashing inner loop)",
+            "keys_per_gpu": n_keys, "msg_len": 32, "parallelism": f"keys sharded over {world} GPU(s), no collective",
+            "l2": "input 320 MB + output 320 MB per step exceed the 126 MB L2; no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------------ synthetic data
@@ -183,6 +204,42 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+# ------------------------------------------------------------------------------------------------ roofline
+ALU_INSTR_PER_KECCAK_F = 4150.0  # LOP3 + SHF per permutation of the register sponge (cuobjdump of keccak256_fixed32_kernel:
+                                 # 24 rounds x (122 LOP3 + 58 SHF) minus what the peeled first / last rounds fold away)
+ALU_LANES_PER_CLK_PER_SM = 64.0  # measured: profiles/r01_pipe_microbench.txt
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return json.load(open(peaks_path))["hbm_gbs"], "of measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def traffic_of(key):
+    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(prof):
+        return json.load(open(prof)).get(key)
+    return None
+
+
+def make_roofline(algo_bytes: float, seconds: float, keccak_f: float, sm_mhz, traffic_key: str, kernel: str, n_sms: int = 148):
+    """roofline object of one leg: `achieved` = algorithmic bytes / device time against the HBM peak (the
+    contract figure), `alu_frac` = Keccak-f executed / device time against the measured ALU-pipe ceiling (the binding one)."""
+    peak, src = hbm_peak()
+    achieved = algo_bytes / seconds / 1e9
+    r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+         "traffic": traffic_of(traffic_key), "kernel": kernel, "peak_source": src,
+         "algorithmic_bytes_per_launch": algo_bytes, "keccak_f_per_launch": keccak_f, "alu_frac": None,
+         "note": "Keccak-f is ALU-bound (~4150 LOP3/SHF per permutation on the 64-lane/clk/SM ALU pipe): alu_frac is the binding roofline"}
+    if sm_mhz:
+        alu_peak = n_sms * ALU_LANES_PER_CLK_PER_SM * sm_mhz * 1e6 / ALU_INSTR_PER_KECCAK_F
+        r["alu_peak_keccak_f_per_s"] = alu_peak
+        r["alu_frac"] = (keccak_f / seconds) / alu_peak
+    return r
+
+
 # ------------------------------------------------------------------------------------------------ CPU baseline
 def cpu_keccak_baseline(target_seconds: float = 12.0):
     """oracle keccak over 32-byte keys on all host cores; bounded sample of the C2 workload."""
@@ -242,29 +299,30 @@ def run_reference(args, rank, world):
     import oracle
     from tests.util import random_keys
     cores = effective_cpus()
-    n = 1_000_000
+    n = args.keys  # the same batch as the GPU arm: one step = one pass over all 10M keys
     keys = random_keys(2, n)
     for _ in range(args.warmup):
-        oracle.keccak256_fixed(keys[:200_000], threads=cores)
+        oracle.keccak256_fixed(keys, threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         oracle.keccak256_fixed(keys, threads=cores)
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
-    sample = f"each step hashes {n} of the 10M 32-byte keys on {cores} host threads (scalar C keccak, chunks of 100)"
+    sample = f"each step hashes all {n} 32-byte keys on {cores} host threads (scalar C keccak, chunks of 100)"
     simd_val = None
     if oracle.keccak256_fixed_simd(keys[:1024], threads=1) is not None:
         t1 = time.perf_counter()
-        for _ in range(args.steps):
+        reps = max(1, min(args.steps, 5))
+        for _ in range(reps):
             oracle.keccak256_fixed_simd(keys, threads=cores)
-        simd_val = n * args.steps / (time.perf_counter() - t1)
+        simd_val = n * reps / (time.perf_counter() - t1)
     sr = cpu_state_root_baseline()
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "C2: batch keccak256 of 10M 32-byte keys per GPU (AccountHashing/StorageHashing inner loop)",
-                   "reference": "CPU restatement of reth's algorithm (oracle/); reth cannot be built here (no Rust toolchain)"},
+        "config": c2_config(n, args.gpus),
+        "reference": "CPU restatement of reth's algorithm (oracle/); reth cannot be built here (no Rust toolchain)",
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "simd_value": simd_val,
                          "simd_note": "8-way AVX-512 multi-buffer Keccak, best-effort figure; reth hashes one key at a time "
@@ -291,7 +349,8 @@ def main():
     ap.add_argument("--dirty", type=int, default=10_000, help="dirty accounts per incremental update")
     ap.add_argument("--skip-incremental", action="store_true")
     ap.add_argument("--c4", action="store_true", help="also run the mainnet-shape leg (BASELINE config 4): per GPU "
-                    "--c4-leaves leaves, 80%% EOAs, Zipf(1.2) storage sizes")
+                    "--c4-leaves leaves, 80%% EOAs, Zipf(1.2) storage sizes (on by default at N>1: 250M leaves over 8 GPUs)")
+    ap.add_argument("--skip-c4", action="store_true")
     ap.add_argument("--c4-leaves", type=int, default=31_250_000, help="leaves per GPU (250M over 8 GPUs)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--dynamic", action="store_true", help="also time the dynamic resident trie / state (tools/dtrie_bench.py, "
@@ -313,20 +372,16 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "WARN")  # NCCL prints its version banner to stdout
-        # stdout carries exactly one JSON line: park fd 1 on stderr while NCCL initialises (it writes to fd 1 directly)
+        # NCCL_DEBUG is left as the caller set it (the driver reads the communicator's rank count from that log).
+        # stdout carries exactly one JSON line, and NCCL logs to fd 1 directly (at init, at the first use of a
+        # collective, at destroy): fd 1 stays parked on stderr for the whole run, the line goes to the saved fd.
         sys.stdout.flush()
-        saved_fd = os.dup(1)
+        OUT_FD[0] = os.dup(1)
         os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            warm = torch.zeros(1, device=dev)
-            dist.all_reduce(warm)
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_fd, 1)
-            os.close(saved_fd)
+        dist.init_process_group("nccl", device_id=dev)
+        warm = torch.zeros(1, device=dev)
+        dist.all_reduce(warm)
+        torch.cuda.synchronize()
     eng = Engine(local_rank)
     # a dedicated (non-default) stream: torch events, NCCL and the engine's kernels are all ordered on it
     stream = torch.cuda.Stream(device=dev)
@@ -392,40 +447,23 @@ def main():
     eng.use_torch_stream()
 
     # ---------------------------------------------------------------- roofline of the dominant kernel
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "of measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
-    algo_bytes = 64 * n  # 32 B key read + 32 B digest written per digest
-    achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(prof):
-        traffic = json.load(open(prof)).get("keccak256_fixed32_kernel_dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "keccak256_fixed32_kernel", "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo_bytes,
-                "note": "Keccak-f is ALU-bound (~4.3k LOP3/SHF per digest on the 64-lane/clk/SM ALU pipe): "
-                        "see alu_frac for the binding roofline",
-                "alu_frac": None}
-    if clk.summary()["sm_mhz"]:
-        alu_peak = 148 * 64 * clk.summary()["sm_mhz"] * 1e6 / 4150.0  # measured 64 lanes/clk/SM ALU pipe, ~4150 ALU instr/digest
-        roofline["alu_frac"] = (n / (ms_per_step * 1e-3)) / alu_peak
-        roofline["alu_peak_digests_per_s"] = alu_peak
+    # 32 B key read + 32 B digest written per digest; one Keccak-f per digest
+    roofline = make_roofline(64.0 * n, ms_per_step * 1e-3, float(n), clk.summary()["sm_mhz"],
+                             "keccak256_fixed32_kernel_dram_bytes_per_launch", "keccak256_fixed32_kernel")
+    sm_mhz = clk.summary()["sm_mhz"]
 
     # ---------------------------------------------------------------- C3: state root
     state_root = None
     if not args.skip_state_root:
-        state_root = bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks)
+        state_root = bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks, sm_mhz)
 
     c4 = None
-    if args.c4:
+    if (args.c4 or world > 1) and not args.skip_c4:
         c4 = bench_c4(args, eng, dev, rank, world, barrier, max_over_ranks)
 
     incremental = None
     if not args.skip_incremental and world == 1:
-        incremental = bench_incremental(args, eng, dev)
+        incremental = bench_incremental(args, eng, dev, sm_mhz, skip_cpu=args.skip_cpu)
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -442,21 +480,19 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "C2: batch keccak256 of 10M 32-byte keys per GPU (AccountHashing/StorageHashing inner loop)",
-                       "keys_per_gpu": n, "msg_len": 32, "parallelism": f"keys sharded over {world} GPU(s), no collective",
-                       "l2": "input 320 MB + output 320 MB per step exceed the 126 MB L2; no flush needed"},
+            "config": c2_config(n, world),
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
             "cpu_baseline": cpu, "state_root": state_root, "mainnet_shape": c4, "incremental": incremental,
             "parity_spot_check": parity_ok,
         }
         if dynamic is not None:
             line["dynamic"] = dynamic
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-def bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks):
+def bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks, sm_mhz=None):
     import torch
     import torch.distributed as dist
     n_acc = args.accounts
@@ -508,6 +544,11 @@ def bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks):
            "node_digests_per_sec": world * stats["hashed_nodes"] / (ms * 1e-3) if world == 1 else None,
            "stats": stats,
            "algorithmic_gb_per_s": world * (n_acc * C3_SLOTS * 64 + n_acc * 104) / (ms * 1e-3) / 1e9}
+    # per GPU: 64 B per storage leaf + 104 B per account leaf; Keccak-f = rate blocks absorbed, counted on
+    # the device (stats.keccak_f)
+    kf = float(stats.get("keccak_f") or 0) or 1.494 * leaves
+    res["roofline"] = make_roofline(float(n_acc * C3_SLOTS * 64 + n_acc * 104), ms * 1e-3, kf, sm_mhz,
+                                    "state_root_c3_dram_bytes_per_step", "state_root_full (leaf + branch kernels of one build)")
     if world == 1:
         # e2e: host (page-locked) buffers through b200_state_root_full
         h = {k: eng.pinned_empty(tuple(v.shape), np.uint8 if v.dtype == torch.uint8 else np.int64)
@@ -627,7 +668,7 @@ def bench_c4(args, eng, dev, rank, world, barrier, max_over_ranks):
     return res
 
 
-def bench_incremental(args, eng, dev):
+def bench_incremental(args, eng, dev, sm_mhz=None, skip_cpu=False):
     """BASELINE config 5: a resident base trie of --base-accounts accounts (no storage), then updates of --dirty random
     existing accounts (new balance + nonce).  Reports the root latency of one update (device-resident dirty set) and
     the same through the host-pointer C ABI."""
@@ -658,6 +699,7 @@ def bench_incremental(args, eng, dev):
     g.manual_seed(55)
     lat = []
     d_new_root = torch.zeros(32, dtype=torch.uint8, device=dev)
+    accts_now = accts  # updated in place as the updates are committed (the base tensor is not needed afterwards)
     reps = 12
     for it in range(reps):
         idx = torch.randperm(n, generator=g, device=dev)[:m] if n < 50_000_000 else \
@@ -676,6 +718,7 @@ def bench_incremental(args, eng, dev):
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
+        accts_now[idx] = da.view(mm, 72)
         if it >= 2:
             lat.append((e0.elapsed_time(e1) * 1e3, wall * 1e6))
     stats = eng.last_stats()
@@ -691,13 +734,49 @@ def bench_incremental(args, eng, dev):
         root = trie.update(hk, ha)
     e2e_us = (time.perf_counter() - t0) / 5 * 1e6
     eng.use_torch_stream()
+    # in-bench parity: the incremental root must equal a from-scratch device build of the updated state (the from-scratch
+    # path is the one the tests pin against the oracle and reth's golden roots); `accts_now` tracks what was committed
+    root_inc = bytes(trie.root())
+    d_chk = torch.zeros(32, dtype=torch.uint8, device=dev)
+    eng.state_root_dev(keys.view(torch.uint8).view(-1), accts_now.view(-1), None, n, d_chk)
+    torch.cuda.synchronize()
+    eng.dev_status()
+    root_scratch = bytes(d_chk.cpu().numpy())
+    if root_inc != root_scratch or root_inc != root:
+        raise SystemExit(f"C5 parity: incremental root {root_inc.hex()} / {root.hex()} != from-scratch root {root_scratch.hex()}")
+    # Keccak-f of one update: dirty leaves (account leaf RLP 104..148 B -> 1 or 2 rate blocks; these are ~112 B = 1) +
+    # re-hashed branch nodes (1..4 blocks by child count); counted on the device when the library reports it
+    kf = float(stats.get("keccak_f") or 0) or float(mm + 2.6 * stats["branches_added"])
+    # algorithmic bytes: the dirty set in (32 B key + 72 B account) + per re-hashed node its <=16 child refs read and its ref written
+    algo = mm * 104.0 + stats["branches_added"] * (16 * 33 + 33)
     res = {"metric": "incremental_root_latency_us", "value": wall_us, "unit": "us", "device_us": dev_us,
            "e2e_us": e2e_us, "base_leaves": n, "dirty_accounts": mm, "dirty_leaves_per_sec": mm / (wall_us * 1e-6),
            "base_build_ms": build_s * 1e3, "base_root": base_root, "root_after": root.hex(),
+           "root_check": "incremental root == from-scratch device build of the updated 100M-leaf state: ok",
            "rehashed_branch_nodes": stats["branches_added"], "levels": stats["levels"],
            "resident_bytes": trie.device_bytes(),
+           "roofline": make_roofline(algo, dev_us * 1e-6, kf, sm_mhz, "incremental_c5_dram_bytes_per_step",
+                                     "b200_trie_update (locate + mark + wavefront)"),
            "config": {"workload": f"C5: {mm}-account dirty set against a resident {n}-leaf base trie, "
                                   "value changes of existing accounts, root path re-hash only"}}
+    res["roofline"]["note"] = ("latency-bound: the critical path is ~27 dependent Keccak-f (7 levels x <=4 blocks); "
+                               "frac / alu_frac are reported for completeness")
+    if not skip_cpu:
+        # the CPU restatement has no incremental walk (reth's needs its database); its figure is the from-scratch
+        # account-trie fold (StateRoot shape, serial like reth's) on a bounded sample, scaled to the base size
+        import oracle
+        from tests.util import synth_accounts
+        ns = 1_000_000
+        ak, ac = synth_accounts(5, ns)
+        t0 = time.perf_counter()
+        oracle.state_root(ak, ac)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": ns / dt, "unit": "leaves/s", "cores": 1, "kind": "port",
+                               "sample": f"from-scratch account-trie fold over {ns} accounts, single thread (the fold is serial in reth); "
+                                         "no incremental CPU path exists outside reth's database walker",
+                               "equivalent_full_rebuild_s": n / (ns / dt),
+                               "note": "an incremental update on the CPU would touch the same ~46k nodes: at the oracle's "
+                                       "~0.55 us per Keccak-f that is ~60 ms single-threaded"}
     trie.close()
     del keys, accts
     torch.cuda.empty_cache()

@@ -23,7 +23,7 @@ struct DArena {
     DevBuf nchild, ndepth, nparent, nref, nmeta, nmasks, nkey, npending, ntrie, nseed, ncur, nnext;
     DevBuf troot, leaf_free, node_free, g;
     // per-apply scratch
-    DevBuf kind, leaf_of, list_a, list_b, ins_idx, attach, seeds, built, removed, freed_now, flags, nh, sel, prefix, pick, out;
+    DevBuf kind, leaf_of, list_a, list_b, ins_idx, attach, unlock, seeds, built, removed, freed_now, flags, nh, sel, prefix, pick, out;
     // outcome of the last apply
     uint32_t n_built = 0, n_removed = 0;
     bool marked = false;  // the last restructure also marked the dirty paths (fused small-block form)
@@ -128,6 +128,7 @@ static DTrieDev da_view(DArena *a) {
     d.built = static_cast<uint32_t *>(a->built.p);
     d.removed = static_cast<uint32_t *>(a->removed.p);
     d.freed_now = static_cast<uint32_t *>(a->freed_now.p);
+    d.unlock = static_cast<uint32_t *>(a->unlock.p);
     d.g = static_cast<uint32_t *>(a->g.p);
     d.err = reinterpret_cast<int *>(small_u32(c) + SM_ERR);
     d.counters = reinterpret_cast<unsigned long long *>(small_u32(c) + SM_COUNTERS);
@@ -140,7 +141,7 @@ static void da_free(DArena *a) {
     DevBuf *bufs[] = {&a->lkey, &a->lval, &a->lsroot, &a->lref, &a->lmeta, &a->lparent, &a->ltrie, &a->lseed, &a->nchild,
                       &a->ndepth, &a->nparent, &a->nref, &a->nmeta, &a->nmasks, &a->nkey, &a->npending, &a->ntrie, &a->nseed,
                       &a->ncur, &a->nnext, &a->troot, &a->leaf_free, &a->node_free, &a->g, &a->kind, &a->leaf_of, &a->list_a,
-                      &a->list_b, &a->ins_idx, &a->attach, &a->seeds, &a->built, &a->removed, &a->freed_now, &a->flags, &a->nh,
+                      &a->list_b, &a->ins_idx, &a->attach, &a->unlock, &a->seeds, &a->built, &a->removed, &a->freed_now, &a->flags, &a->nh,
                       &a->sel, &a->prefix, &a->pick, &a->out};
     for (DevBuf *b : bufs)
         if (b->p) {
@@ -207,6 +208,7 @@ static int32_t da_prepare(DArena *a, uint64_t m, uint64_t tries) {
     TRY(da_scratch(a, a->list_b, (size_t)max_list * 4));
     TRY(da_scratch(a, a->ins_idx, m * 4));
     TRY(da_scratch(a, a->attach, m * 8));
+    TRY(da_scratch(a, a->unlock, m * 4));
     TRY(da_scratch(a, a->seeds, (size_t)max_seeds * 4));
     TRY(da_scratch(a, a->built, (size_t)max_built * 4));
     TRY(da_scratch(a, a->removed, ((size_t)max_built + max_list) * 4));
@@ -287,7 +289,7 @@ static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const ui
         CU(cudaMemsetAsync(leftover, 0, 4, st));
         CU(launch_dt_insert(d, d_trie_of_key, d_keys, d_vals, d_sroots, idx_cur, d.g + DG_NINSERT, bound,
                             static_cast<uint64_t *>(a->attach.p), leaf_of, DT_KEYS_PER_RUN, pending, leftover, st));
-        c->launches += 2;
+        c->launches += 3;
         CU(cudaMemcpyAsync(ps + 200, leftover, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(ps + 201, small_u32(c) + SM_ERR, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(ps + 202, d.g + DG_NINSERT, 4, cudaMemcpyDeviceToHost, st));

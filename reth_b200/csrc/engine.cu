@@ -28,7 +28,7 @@ static thread_local int g_create_status = 0;
 static constexpr uint32_t WARP_LEVEL_MAX = 4096;
 
 // layout of the `small` device buffer (uint32 units)
-enum : int { SM_BUCKET_OFF = 0, SM_LEVEL_LO = 80, SM_NNODES = 160, SM_ERR = 164, SM_NSTORED = 168, SM_ORD_NLONG = 170, SM_COUNTERS = 176 /* 4 x u64 */, SM_HIST = 256 /* 256 x u32 */, SM_WORDS = 512 };
+enum : int { SM_BUCKET_OFF = 0, SM_LEVEL_LO = 80, SM_NNODES = 160, SM_ERR = 164, SM_ERR_STICKY = 165, SM_NSTORED = 168, SM_ORD_NLONG = 170, SM_COUNTERS = 176 /* 4 x u64 */, SM_HIST = 256 /* 256 x u32 */, SM_WORDS = 512 };
 
 static uint32_t *small_u32(b200_ctx *c) { return static_cast<uint32_t *>(c->small.p); }
 
@@ -142,7 +142,7 @@ static int32_t map_dev_error(b200_ctx *c, int code) {
 static int32_t sync_and_status(b200_ctx *c) {
     CU(cudaStreamSynchronize(c->stream));
     uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
-    CU(cudaMemcpyAsync(ps, small_u32(c) + SM_ERR, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(ps, small_u32(c) + SM_ERR, 8, cudaMemcpyDeviceToHost, c->stream));  // current + sticky word
     CU(cudaMemcpyAsync(ps + 8, small_u32(c) + SM_COUNTERS, 32, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(ps + 4, small_u32(c) + SM_NSTORED, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -156,12 +156,17 @@ static int32_t sync_and_status(b200_ctx *c) {
         c->stats.extension_nodes = cnt[CNT_EXT];
         c->stats_pending = false;
     }
-    return map_dev_error(c, (int)ps[0]);
+    // the oldest unreported violation wins; reporting clears both words (a later b200_sync returns OK again)
+    int code = ps[1] ? (int)ps[1] : (int)ps[0];
+    if (code) CU(cudaMemsetAsync(small_u32(c) + SM_ERR, 0, 8, c->stream));
+    return map_dev_error(c, code);
 }
 
 static int32_t reset_build_state(b200_ctx *c) {
-    CU(cudaMemsetAsync(small_u32(c) + SM_ERR, 0, 4, c->stream));
-    CU(cudaMemsetAsync(small_u32(c) + SM_COUNTERS, 0, 32, c->stream));
+    // latches a still unreported error of the previous async build into the sticky word, then clears the error word
+    // and the counters for this build
+    CU(launch_latch_error(reinterpret_cast<int *>(small_u32(c) + SM_ERR), reinterpret_cast<int *>(small_u32(c) + SM_ERR_STICKY),
+                          reinterpret_cast<unsigned long long *>(small_u32(c) + SM_COUNTERS), c->stream));
     c->stats = b200_stats{};
     c->stats_wavefront = false;
     CU(cudaEventRecord(c->ev0, c->stream));

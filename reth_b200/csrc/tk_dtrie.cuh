@@ -395,11 +395,14 @@ __global__ void dt_insert_locate_kernel(DTrieDev t, const uint32_t *__restrict__
     if (j < *n_ins_p) dt_insert_locate_entry(t, trie_of_key, keys, ins_idx, j, attach);
 }
 
-// returns the id of the new leaf
+// returns the id of the new leaf.  `top` is the value of the attach word (the child word at (parent, slot), or the trie's
+// root word): the run that owns the attach point keeps it in a register — the word in memory holds DT_LOCKED for the
+// whole round — and stores the final value afterwards (dt_insert_unlock_entry).
 static __device__ __forceinline__ uint32_t dt_insert_one(const DTrieDev &t, uint32_t trie, const uint8_t *key, const uint8_t *val,
-                                                         const uint8_t *sroot, uint32_t parent, uint32_t slot) {
+                                                         const uint8_t *sroot, uint32_t parent, uint32_t slot, uint32_t &top) {
     uint32_t matched = parent == DT_NONE ? 0 : (uint32_t)t.ndepth[parent] + 1;
-    uint32_t cur = parent == DT_NONE ? t.troot[trie] : t.nchild[16 * (uint64_t)parent + slot];
+    uint32_t cur = top;
+    bool at_top = true;  // `cur` is the attach word itself: updates go to `top`, not to memory
     // the new leaf
     uint32_t x = dt_alloc_leaf(t);
     dt_copy32(t.lkey + 32 * (uint64_t)x, key);
@@ -417,7 +420,8 @@ static __device__ __forceinline__ uint32_t dt_insert_one(const DTrieDev &t, uint
             break;
         }
         if (cur == DT_NONE) {
-            dt_set_child(t, trie, parent, slot, x | DT_LEAF);
+            if (at_top) top = x | DT_LEAF;
+            else dt_set_child(t, trie, parent, slot, x | DT_LEAF);
             t.lparent[x] = parent;
             break;
         }
@@ -430,7 +434,8 @@ static __device__ __forceinline__ uint32_t dt_insert_one(const DTrieDev &t, uint
             t.nchild[16 * (uint64_t)b + dt_nib(other, l)] = cur;
             t.lparent[x] = b;
             dt_set_parent(t, cur, b);
-            dt_set_child(t, trie, parent, slot, b);
+            if (at_top) top = b;
+            else dt_set_child(t, trie, parent, slot, b);
             dt_seed(t, b);
             dt_seed(t, cur);  // parent depth changed
             break;
@@ -440,6 +445,7 @@ static __device__ __forceinline__ uint32_t dt_insert_one(const DTrieDev &t, uint
         slot = dt_nib(key, limit);
         matched = limit + 1;
         cur = t.nchild[16 * (uint64_t)cur + slot];
+        at_top = false;
     }
     dt_seed(t, x | DT_LEAF);
     return x;
@@ -449,19 +455,33 @@ static __device__ __forceinline__ uint32_t dt_insert_one(const DTrieDev &t, uint
 // time the keys just inserted have fanned the attach point out into up to 16 deeper ones per level — a run of r keys
 // needs ~log(r) rounds instead of r serial inserts (a new contract with 100k slots, a bulk load into an empty trie).
 // pending[j] = 1 for every entry that is still to be inserted; *leftover counts them.
+//
+// The keys of one attach point are NOT always neighbours in the sorted list: with K1 < K2 < K3, K1 and K3 can both diverge
+// inside the edge above a node N (same attach word) while K2 matches that edge and attaches below N — long edges (clustered
+// keys, small storage tries) make that common.  Two heads with the same attach word must not work concurrently, so a head
+// takes the attach word itself as the lock: atomicExch(word, DT_LOCKED).  The winner keeps the word's value in a register
+// and leaves DT_LOCKED in memory until the round is over (t.unlock[j] = the final value, stored by dt_insert_unlock_entry
+// after the barrier / kernel boundary); a head that finds DT_LOCKED leaves its keys for the next round.  Nothing else reads
+// an attach word during this phase: descents happen in the locate phase, and runs below N start from their own attach word.
+static __device__ __forceinline__ uint32_t *dt_attach_word(const DTrieDev &t, uint64_t a) {
+    return (a >> 63) ? t.troot + (uint32_t)a : t.nchild + a;  // (parent << 4 | slot) == 16 * parent + slot
+}
 static __device__ __forceinline__ void dt_insert_run_entry(const DTrieDev &t, const uint32_t *__restrict__ trie_of_key,
                                                            const uint8_t *__restrict__ keys, const uint8_t *__restrict__ vals,
                                                            const uint8_t *__restrict__ sroots, const uint32_t *__restrict__ ins_idx,
                                                            uint32_t n_ins, uint32_t j, const uint64_t *__restrict__ attach,
                                                            uint32_t *__restrict__ leaf_of, uint32_t max_per_run,
                                                            uint8_t *__restrict__ pending, uint32_t *__restrict__ leftover) {
+    t.unlock[j] = DT_LOCKED;  // nothing to store back for this entry (unless it turns out to own an attach word)
     uint64_t a = attach[j];
     if (j && attach[j - 1] == a) return;  // not the head of its run
     const bool at_root = (a >> 63) != 0;
     uint32_t parent = at_root ? DT_NONE : (uint32_t)(a >> 4), slot = at_root ? 0u : (uint32_t)(a & 15);
+    uint32_t top = atomicExch(dt_attach_word(t, a), DT_LOCKED);
+    const bool owner = top != DT_LOCKED;
     uint32_t done = 0, left = 0;
     for (uint32_t q = j; q < n_ins && attach[q] == a; q++) {
-        if (done == max_per_run) {
+        if (!owner || done == max_per_run) {
             pending[q] = 1;
             left++;
             continue;
@@ -469,11 +489,17 @@ static __device__ __forceinline__ void dt_insert_run_entry(const DTrieDev &t, co
         uint64_t i = ins_idx[q];
         uint32_t trie = trie_of_key ? trie_of_key[i] : 0;
         leaf_of[i] = dt_insert_one(t, trie, keys + 32 * i, vals + (uint64_t)t.val_stride * i, sroots ? sroots + 32 * i : nullptr,
-                                   parent, slot);
+                                   parent, slot, top);
         pending[q] = 0;
         done++;
     }
+    if (owner) t.unlock[j] = top;
     if (left) atomicAdd(leftover, left);
+}
+// after every head of the round has run: the owners store the final value of their attach word (never DT_LOCKED)
+static __device__ __forceinline__ void dt_insert_unlock_entry(const DTrieDev &t, uint32_t j, const uint64_t *__restrict__ attach) {
+    uint32_t v = t.unlock[j];
+    if (v != DT_LOCKED) *dt_attach_word(t, attach[j]) = v;
 }
 __global__ void dt_insert_runs_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_key, const uint8_t *__restrict__ keys,
                                       const uint8_t *__restrict__ vals, const uint8_t *__restrict__ sroots,
@@ -484,6 +510,10 @@ __global__ void dt_insert_runs_kernel(DTrieDev t, const uint32_t *__restrict__ t
     const uint32_t n_ins = *n_ins_p;
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n_ins) dt_insert_run_entry(t, trie_of_key, keys, vals, sroots, ins_idx, n_ins, j, attach, leaf_of, max_per_run, pending, leftover);
+}
+__global__ void dt_insert_unlock_kernel(DTrieDev t, const uint32_t *__restrict__ n_ins_p, const uint64_t *__restrict__ attach) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < *n_ins_p) dt_insert_unlock_entry(t, j, attach);
 }
 
 // ------------------------------------------------------------------------------------------------ mark + wavefront
@@ -636,6 +666,8 @@ __global__ void __launch_bounds__(BLOCK) dt_restructure_fused_kernel(DTrieDev t,
         __syncthreads();
         for (uint32_t j = tid; j < n_ins; j += BLOCK)
             dt_insert_run_entry(t, trie_of_key, keys, vals, sroots, icur, n_ins, j, attach, leaf_of, max_per_run, pending, &s_count);
+        __syncthreads();
+        for (uint32_t j = tid; j < n_ins; j += BLOCK) dt_insert_unlock_entry(t, j, attach);
         __syncthreads();
         if (s_count == 0) break;
         n_ins = dt_block_compact<BLOCK>(icur, false, n_ins, [&](uint32_t j) { return pending[j] != 0; }, inext, sh);

@@ -52,6 +52,7 @@ cudaError_t launch_dt_insert(const DTrieDev &t, const uint32_t *trie_of_key, con
     dt_insert_locate_kernel<<<blocks, 128, 0, st>>>(t, trie_of_key, keys, ins_idx, n_ins_p, attach);
     dt_insert_runs_kernel<<<blocks, 128, 0, st>>>(t, trie_of_key, keys, vals, sroots, ins_idx, n_ins_p, attach, leaf_of, max_per_run,
                                                   pending, leftover);
+    dt_insert_unlock_kernel<<<blocks, 128, 0, st>>>(t, n_ins_p, attach);
     return cudaGetLastError();
 }
 // mark -> starts -> wavefront -> finish (empty-trie root, recycling of this apply's freed nodes)

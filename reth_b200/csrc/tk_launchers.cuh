@@ -40,6 +40,10 @@ static unsigned persistent_grid(K kernel, int block, size_t smem, uint64_t work_
     return (unsigned)(want < cap ? (want ? want : 1) : cap);
 }
 
+cudaError_t launch_latch_error(int *err, int *sticky, unsigned long long *counters, cudaStream_t st) {
+    latch_error_kernel<<<1, 1, 0, st>>>(err, sticky, counters);
+    return cudaGetLastError();
+}
 cudaError_t launch_mark_boundaries(const uint64_t *d_seg_offsets, uint64_t n_segs, uint64_t n, uint8_t *Lp, int *err,
                                    cudaStream_t st) {
     mark_boundaries_kernel<<<blocks_for(n_segs + 1, 256), 256, 0, st>>>(d_seg_offsets, n_segs, n, Lp, err);

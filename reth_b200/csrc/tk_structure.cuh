@@ -51,6 +51,16 @@ __global__ void mark_boundaries_kernel(const uint64_t *__restrict__ seg_offsets,
     if (o > 0 && o < n) Lp[o] = 0xFF;
 }
 
+// Start of a build: the error word of the previous (possibly still unreported) build is latched into the sticky word —
+// first error wins — and cleared, together with the build counters, so that this build starts clean without erasing
+// what b200_sync / b200_dev_status still has to report (include/b200trie.h: violations of async calls are sticky).
+__global__ void latch_error_kernel(int *__restrict__ err, int *__restrict__ sticky, unsigned long long *__restrict__ counters) {
+    int e = *err;
+    if (e != B200_DEVERR_NONE && *sticky == B200_DEVERR_NONE) *sticky = e;
+    *err = B200_DEVERR_NONE;
+    for (int i = 0; i < CNT_COUNT; i++) counters[i] = 0;
+}
+
 __global__ void iota_kernel(uint32_t *__restrict__ out, uint64_t n, uint32_t first) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = first + (uint32_t)i;

@@ -72,6 +72,7 @@ struct UpdatesDev {
     uint8_t *hashes;
 };
 
+cudaError_t launch_latch_error(int *err, int *sticky, unsigned long long *counters, cudaStream_t st);
 cudaError_t launch_mark_boundaries(const uint64_t *d_seg_offsets, uint64_t n_segs, uint64_t n, uint8_t *Lp, int *err,
                                    cudaStream_t st);
 cudaError_t launch_lcp(const uint8_t *keys, uint64_t n, uint8_t *Lp, uint8_t *nibs, int *err, cudaStream_t st);
@@ -156,6 +157,7 @@ cudaError_t launch_ordered_leaves(const ForestDev &f, const OrderedLeavesDev &o,
 // ------------------------------------------------------------------------------------------------ dynamic trie (tk_dtrie.cuh)
 constexpr uint32_t DT_NONE = 0xFFFFFFFFu;
 constexpr uint32_t DT_LEAF = 0x80000000u;
+constexpr uint32_t DT_LOCKED = 0xFFFFFFFEu;  // an attach word owned by an insert run for the duration of a round (never a valid id: ids < 2^31 - 2)
 constexpr uint8_t DT_DEAD = 0xFF;  // ndepth / lmeta of a freed slot
 constexpr int DT_MAX_HOPS = 66;
 
@@ -199,6 +201,7 @@ struct DTrieDev {
     // free stacks, lists, globals
     uint32_t *leaf_free, *node_free;
     uint32_t *seeds, *built, *removed, *freed_now;
+    uint32_t *unlock;  // [insert entries of the round] final value of the attach word a run owned, DT_LOCKED = none
     uint32_t *g;
     int *err;
     unsigned long long *counters;

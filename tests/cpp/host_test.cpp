@@ -197,9 +197,8 @@ static void random_state_vs_oracle(const Engine &e) {
     CHECK(storage_nodes == os.n_nodes);
     orc_updates_free(&oa);
     orc_updates_free(&os);
-    // rows laid out on the device == rows the host encoder makes of the same build's TrieUpdates (first validated under
-    // tools/emu: opt-in on a GPU like the dynamic tries)
-    if (std::getenv("B200_EMU") || std::getenv("B200_DTRIE_ON_GPU")) {
+    // rows laid out on the device == rows the host encoder makes of the same build's TrieUpdates
+    {
         for (b200_key_format fmt : {B200_KEYS_LEGACY, B200_KEYS_PACKED}) {
             auto t = StateRoot(e, sorted).root_with_table_rows(fmt);
             CHECK(t.root == oroot);
@@ -498,7 +497,7 @@ int main() {
         extension_node_storage_trie(e);
         prefix_sets_and_destroyed(e);
         random_state_vs_oracle(e);
-        if (std::getenv("B200_EMU") || std::getenv("B200_DTRIE_ON_GPU")) {
+        {
             dynamic_trie_blocks(e);
             dynamic_state_blocks(e);
             ordered_root_builder(e);

@@ -2,9 +2,7 @@
 upserts / destructions and slot upserts / deletions / wipes applied in place.  After every block the root equals the
 oracle's from-scratch StateRoot over the merged state, and the account / storage TrieUpdates applied to a model of
 AccountsTrie / StoragesTrie reproduce the oracle's full node sets (reth's incremental == full criterion,
-crates/trie/db/tests/trie.rs:680-717, crates/trie/parallel/src/root.rs:287-400).
-
-Gate: emulation-validated only so far (`pytest -m gpu --emu`); opt-in on a GPU with B200_DTRIE_ON_GPU=1."""
+crates/trie/db/tests/trie.rs:680-717, crates/trie/parallel/src/root.rs:287-400)."""
 import os
 
 import numpy as np
@@ -13,11 +11,7 @@ import pytest
 import oracle
 from tests.util import to_device_ptrs
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(not (os.environ.get("B200_EMU") or os.environ.get("B200_DTRIE_ON_GPU")),
-                       reason="dynamic state: validated under tools/emu only; set B200_DTRIE_ON_GPU=1 to run on a GPU"),
-]
+pytestmark = [pytest.mark.gpu]
 
 EXISTS, UNCHANGED, WIPED = 1, 2, 4
 

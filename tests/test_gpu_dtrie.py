@@ -1,10 +1,7 @@
 """Dynamic resident trie (b200_dtrie_*): inserts, deletes and value updates applied in place,
 checked after every block against a from-scratch oracle build — the root, and the stored-node set a database would hold
 after applying the block's TrieUpdates (updated nodes written, removed paths deleted).  Modelled on reth's
-fuzz_in_memory_account_nodes / incremental-vs-full tests (crates/trie/db/tests/trie.rs, fuzz_in_memory_nodes.rs).
-
-Gate: these kernels have so far run under tools/emu only (`pytest -m gpu --emu`); on a real GPU they are opt-in
-(B200_DTRIE_ON_GPU=1) until their first validated B200 run."""
+fuzz_in_memory_account_nodes / incremental-vs-full tests (crates/trie/db/tests/trie.rs, fuzz_in_memory_nodes.rs)."""
 import os
 
 import numpy as np
@@ -13,11 +10,7 @@ import pytest
 import oracle
 from tests.util import synth_accounts
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(not (os.environ.get("B200_EMU") or os.environ.get("B200_DTRIE_ON_GPU")),
-                       reason="dynamic trie: validated under tools/emu only; set B200_DTRIE_ON_GPU=1 to run on a GPU"),
-]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")
@@ -222,6 +215,37 @@ def test_rejects_unsorted_or_duplicate_keys_and_stays_consistent(eng):
         h.trie.apply(dup, np.zeros(2, oracle.ACCOUNT_DTYPE))
     assert h.trie.root() == before
     h.commit({ks[0]: (0, acct(0))})      # still usable
+    h.trie.close()
+
+
+def test_split_runs_share_an_attach_point(eng):
+    """K1 < K2 < K3 where K1 and K3 diverge inside the (long) edge above a node N and K2 passes through it: K1 and K3 have the
+    same attach point without being neighbours in the sorted insert list.  The first B200 run caught this shape (two threads
+    inserting at one attach word concurrently; sequential emulation could not see it): many such triples per block here."""
+    rng = np.random.default_rng(31)
+    state0 = {}
+    stems = []
+    for _ in range(64):                                   # 64 deep two-leaf subtries: root -> long edge -> N -> {a, b}
+        stem = rng.integers(0, 256, 20, dtype=np.uint8).tobytes()
+        stems.append(stem)
+        for last in (0x10, 0xE0):
+            state0[stem + bytes([last]) + rng.integers(0, 256, 11, dtype=np.uint8).tobytes()] = acct(1)
+    h = Harness(eng, 0, seed=32)
+    h.commit({k: (1, a) for k, a in state0.items()})
+    for step in range(3):
+        dirty = {}
+        for stem in stems:
+            cut = int(rng.integers(2 + step, 19))         # diverge inside the edge at byte `cut`, below and above
+            lo, hi = bytearray(stem), bytearray(stem)
+            if lo[cut] == 0 or hi[cut] == 255:
+                continue
+            lo[cut] -= 1
+            hi[cut] += 1
+            tail = lambda n: rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+            dirty[bytes(lo[:cut + 1]) + tail(31 - cut)] = (1, acct(2))          # K1: below the edge
+            dirty[stem + bytes([0x70 + step]) + tail(11)] = (1, acct(3))        # K2: through the edge, into N
+            dirty[bytes(hi[:cut + 1]) + tail(31 - cut)] = (1, acct(4))          # K3: above the edge
+        h.commit(dirty)
     h.trie.close()
 
 

@@ -126,8 +126,6 @@ def test_resident_state_root_commits_blocks(eng, dynamic):
     StateRoot over the merged state — the reference's incremental == full criterion
     (crates/trie/db/tests/trie.rs:680-717, crates/trie/parallel/src/root.rs:287-400)."""
     from reth_b200 import ResidentStateRoot
-    if dynamic and not (os.environ.get("B200_EMU") or os.environ.get("B200_DTRIE_ON_GPU")):
-        pytest.skip("dynamic trie: validated under tools/emu only so far (tests/test_gpu_dtrie.py)")
     rng = np.random.default_rng(77)
     rk = lambda: bytes(rng.integers(0, 256, 32, dtype=np.uint8))
     base = HashedPostState()

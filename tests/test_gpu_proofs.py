@@ -1,9 +1,7 @@
 """Merkle proofs from the dynamic resident state (b200_dstate_account_proofs / _storage_proofs) against the
 reference's own vectors — crates/trie/db/tests/proof.rs: testspec_proofs (:44-115), testspec_empty_storage_proof
 (:117-140), mainnet_genesis_account_proof (:142-165) — and, for random states, against a verifier that walks the proof
-from the state root exactly like `AccountProof::verify` (hash of node k+1 must sit in node k at the key's next nibble).
-
-Gate: emulation-validated only so far (`pytest -m gpu --emu`); opt-in on a GPU with B200_DTRIE_ON_GPU=1."""
+from the state root exactly like `AccountProof::verify` (hash of node k+1 must sit in node k at the key's next nibble)."""
 import os
 
 import numpy as np
@@ -12,11 +10,7 @@ import pytest
 import oracle
 from tests.util import alloc_to_flat
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(not (os.environ.get("B200_EMU") or os.environ.get("B200_DTRIE_ON_GPU")),
-                       reason="dynamic state: validated under tools/emu only; set B200_DTRIE_ON_GPU=1 to run on a GPU"),
-]
+pytestmark = [pytest.mark.gpu]
 
 H = bytes.fromhex
 TESTSPEC = {  # address -> proof, crates/trie/db/tests/proof.rs:50-98

@@ -325,6 +325,35 @@ def test_device_resident_full_state(eng):
     assert d_root.cpu().numpy().tobytes() == oracle.state_root_full(akeys, accs, skeys, svals, offs, threads=4)
 
 
+def test_async_error_is_sticky_across_back_to_back_dev_calls(eng):
+    """include/b200trie.h: a violation of an async (*_dev) call is reported by the next b200_sync / b200_dev_status —
+    also when another, well-formed *_dev build was enqueued after it (the later build must not erase it)."""
+    import torch
+    from reth_b200 import B200Error, _lib
+    n = 2000
+    keys, accs = synth_accounts(63, n)
+    bad = keys.copy()
+    bad[[100, 101]] = bad[[101, 100]]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
+    d_bad, d_good, d_accs = t(bad), t(keys), t(accs)
+    r1 = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    r2 = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    eng.use_torch_stream()
+    try:
+        eng.state_root_dev(d_bad, d_accs, None, n, r1)    # unsorted: flags the error on the device
+        eng.state_root_dev(d_good, d_accs, None, n, r2)   # fine on its own
+        with pytest.raises(B200Error) as e:
+            eng.dev_status()
+        assert e.value.status == _lib.ERR_UNSORTED
+        eng.dev_status()                                   # reported once; the context is clean again
+        assert r2.cpu().numpy().tobytes() == oracle.state_root(keys, accs)  # the second build was not disturbed
+        eng.state_root_dev(d_good, d_accs, None, n, r1)
+        eng.dev_status()
+        assert r1.cpu().numpy().tobytes() == oracle.state_root(keys, accs)
+    finally:
+        eng.set_stream(None)
+
+
 # ---------------------------------------------------------------- resident trie / incremental root (BASELINE config 5)
 def _mutate(accs, idx, seed):
     rng = np.random.default_rng(seed)
