@@ -50,9 +50,19 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
         c->launches++;
     }
     CU(launch_lcp(d_keys, n, f.Lp, f.nibs, f.err, st));
+    c->launches++;
+    // The leaf pass (ALU-bound, the longest kernel of a build) and the structure pass (sorts / scans / flags: memory- and
+    // latency-bound, one host read-back at its end) both need only Lp: they run side by side, the structure pass on the
+    // high-priority aux stream; the branch levels join them again.  A single leaf has no structure pass.
+    cudaStream_t sa = n >= 2 ? c->aux_stream : st;
+    if (n >= 2) {
+        CU(cudaEventRecord(c->ev_fork, st));
+        CU(cudaStreamWaitEvent(sa, c->ev_fork, 0));
+    }
     if (ordered) CU(launch_ordered_leaves(f, *ordered, st));  // index-keyed tries: variable-length keys and values
     else CU(launch_leaves(f, account, d_values, d_sroots, st));
-    c->launches += 2;
+    c->launches++;
+    phase_mark(c, account ? "lcp+leaves(acct)" : "lcp+leaves");
     if (n < 2) return B200_OK;
 
     // ---- gaps sorted by depth (stable: position order inside a depth) -> branch nodes in CSR form
@@ -70,50 +80,54 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
     uint8_t *head = static_cast<uint8_t *>(c->head.p);
     uint32_t *node_start = static_cast<uint32_t *>(c->node_start.p);
 
-    CU(launch_iota(static_cast<uint32_t *>(c->iota.p), G, 1, st));
+    CU(launch_iota(static_cast<uint32_t *>(c->iota.p), G, 1, sa));
     c->launches++;
     size_t t_sort = 0, t_sel = 0, t_scan = 0;
     CU(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, f.Lp + 1, depth_sorted, static_cast<uint32_t *>(c->iota.p),
-                                       gap_sorted, (int64_t)G, 0, 8, st));
+                                       gap_sorted, (int64_t)G, 0, 8, sa));
     thrust::counting_iterator<uint32_t> counting(0);
-    CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, head, node_start, n_nodes_p, (int64_t)G, st));
+    CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, head, node_start, n_nodes_p, (int64_t)G, sa));
     auto bflags = thrust::make_transform_iterator(static_cast<const uint8_t *>(f.Lp), IsBoundary());
     uint32_t *bound_rank = nullptr;
     if (d_seg_offsets) {
         ENSURE(bound_rank, (n + 1) * 4);
         bound_rank = static_cast<uint32_t *>(c->bound_rank.p);
-        CU(cub::DeviceScan::InclusiveSum(nullptr, t_scan, bflags, bound_rank, (int64_t)(n + 1), st));
+        CU(cub::DeviceScan::InclusiveSum(nullptr, t_scan, bflags, bound_rank, (int64_t)(n + 1), sa));
     }
     size_t t_max = std::max(t_sort, std::max(t_sel, t_scan));
     ENSURE(cub_temp, t_max);
     CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_sort, f.Lp + 1, depth_sorted,
-                                       static_cast<uint32_t *>(c->iota.p), gap_sorted, (int64_t)G, 0, 8, st));
-    CU(launch_bucket_offsets(depth_sorted, G, bucket_off, st));
+                                       static_cast<uint32_t *>(c->iota.p), gap_sorted, (int64_t)G, 0, 8, sa));
+    CU(launch_bucket_offsets(depth_sorted, G, bucket_off, sa));
     if (d_seg_offsets)
-        CU(cub::DeviceScan::InclusiveSum(c->cub_temp.p, t_scan, bflags, bound_rank, (int64_t)(n + 1), st));
-    CU(cudaMemsetAsync(head, 0, G, st));
-    CU(launch_head_flags(d_keys, depth_sorted, gap_sorted, bound_rank, bucket_off + 64, G, head, st));
-    CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, head, node_start, n_nodes_p, (int64_t)G, st));
-    CU(launch_level_ranges(node_start, n_nodes_p, bucket_off, level_lo, st));
+        CU(cub::DeviceScan::InclusiveSum(c->cub_temp.p, t_scan, bflags, bound_rank, (int64_t)(n + 1), sa));
+    CU(cudaMemsetAsync(head, 0, G, sa));
+    CU(launch_head_flags(d_keys, depth_sorted, gap_sorted, bound_rank, bucket_off + 64, G, head, sa));
+    CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, head, node_start, n_nodes_p, (int64_t)G, sa));
+    CU(launch_level_ranges(node_start, n_nodes_p, bucket_off, level_lo, sa));
     // (depth, child-count class) of every node + histogram, still without knowing the node count on the host
     ENSURE(node_key, G);
     ENSURE(node_ids, G * 4);
     uint8_t *nk = static_cast<uint8_t *>(c->node_key.p);
     uint32_t *nids = static_cast<uint32_t *>(c->node_ids.p);
     uint32_t *hist = small_u32(c) + SM_HIST;
-    CU(cudaMemsetAsync(hist, 0, 256 * 4, st));
-    CU(launch_node_class_keys(node_start, depth_sorted, n_nodes_p, G, nk, nids, hist, st));
+    CU(cudaMemsetAsync(hist, 0, 256 * 4, sa));
+    CU(launch_node_class_keys(node_start, depth_sorted, n_nodes_p, G, nk, nids, hist, sa));
     c->launches += 9;
     uint32_t *h_level = static_cast<uint32_t *>(c->pinned_small) + 64;
     uint32_t *h_hist = static_cast<uint32_t *>(c->pinned_small) + 256;
-    CU(cudaMemcpyAsync(h_level, level_lo, 66 * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h_hist, hist, 256 * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));  // the only host round trip of a build: 322 integers
+    CU(cudaMemcpyAsync(h_level, level_lo, 66 * 4, cudaMemcpyDeviceToHost, sa));
+    CU(cudaMemcpyAsync(h_hist, hist, 256 * 4, cudaMemcpyDeviceToHost, sa));
+    CU(cudaStreamSynchronize(sa));  // the only host round trip of a build: 322 integers (the leaf pass keeps running)
     const uint32_t B = h_level[65];
     out.n_nodes = B;
     f.gap_sorted = gap_sorted;
     f.node_start = node_start;
-    if (B == 0) return B200_OK;  // every trie has at most one leaf
+    if (B == 0) {  // every trie has at most one leaf
+        CU(cudaEventRecord(c->ev_join, sa));
+        CU(cudaStreamWaitEvent(st, c->ev_join, 0));
+        return B200_OK;
+    }
 
     ENSURE(node_ref, (size_t)B * 32);
     ENSURE(node_meta, B);
@@ -132,10 +146,13 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
     uint8_t *nk2 = static_cast<uint8_t *>(c->node_key2.p);
     uint32_t *norder = static_cast<uint32_t *>(c->node_order.p);
     size_t t_ns = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, t_ns, nk, nk2, nids, norder, (int64_t)B, 0, 8, st));
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, t_ns, nk, nk2, nids, norder, (int64_t)B, 0, 8, sa));
     ENSURE(cub_temp, t_ns);
-    CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_ns, nk, nk2, nids, norder, (int64_t)B, 0, 8, st));
+    CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_ns, nk, nk2, nids, norder, (int64_t)B, 0, 8, sa));
     c->launches += 1;
+    CU(cudaEventRecord(c->ev_join, sa));
+    CU(cudaStreamWaitEvent(st, c->ev_join, 0));  // the branch levels need the leaves (st) and the structure (sa)
+    phase_mark(c, "leaves||structure");
 
     // ---- deepest level first; the per-level frontier stays in HBM.  Big levels get one launch per child-count
     // class (strip size and unrolling fit the class), small ones a single launch.
@@ -150,6 +167,7 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
             CU(launch_branch_level(f, norder, pos, pos + cnt, d, -1, st));
             c->launches++;
             pos += cnt;
+            phase_mark(c, "small-level");
         } else {
             for (int cls = 0; cls < 4; cls++) {
                 if (!hc[cls]) continue;
@@ -157,6 +175,7 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
                 CU(launch_branch_level(f, norder, pos, pos + hc[cls], d, hc[cls] <= WARP_LEVEL_MAX / 4 ? -1 : cls, st));
                 c->launches++;
                 pos += hc[cls];
+                phase_mark(c, hc[cls] <= WARP_LEVEL_MAX / 4 ? "small-class" : (cls == 0 ? "big<=3" : cls == 1 ? "big<=7" : cls == 2 ? "big<=12" : "big<=16"));
             }
         }
     }

@@ -260,7 +260,7 @@ static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const ui
         CU(cudaMemcpyAsync(ps + 200, cnt_cur, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(ps + 201, small_u32(c) + SM_ERR, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        if (ps[201] != B200_DEVERR_NONE) return map_dev_error(c, (int)ps[201]);
+        if (ps[201] != B200_DEVERR_NONE) return report_dev_error_now(c, (int)ps[201]);
         if (ps[200] == 0) break;
         if (round > 200) return fail(c, B200_ERR_CUDA, "collapse rounds do not converge");
         CU(cudaMemsetAsync(cnt_next, 0, 4, st));
@@ -294,7 +294,7 @@ static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const ui
         CU(cudaMemcpyAsync(ps + 201, small_u32(c) + SM_ERR, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(ps + 202, d.g + DG_NINSERT, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        if (ps[201] != B200_DEVERR_NONE) return map_dev_error(c, (int)ps[201]);
+        if (ps[201] != B200_DEVERR_NONE) return report_dev_error_now(c, (int)ps[201]);
         if (ps[200] == 0) break;
         if (round > 80) return fail(c, B200_ERR_CUDA, "insert rounds do not converge");
         if (!idx_next) {

@@ -403,7 +403,7 @@ extern "C" B200_API int32_t b200_trie_apply(b200_trie *t, const uint8_t *keys32,
     CU(cudaMemcpyAsync(ps + 300, counts, 16, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(ps, small_u32(c) + SM_ERR, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (ps[0] != B200_DEVERR_NONE) return map_dev_error(c, (int)ps[0]);
+    if (ps[0] != B200_DEVERR_NONE) return report_dev_error_now(c, (int)ps[0]);
     const uint64_t n_ins = ps[300], n_del = ps[301], n_upd = ps[302];
     int32_t r = B200_OK;
     if (n_ins == 0 && n_del == 0 && n_upd == m) {

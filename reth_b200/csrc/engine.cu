@@ -63,6 +63,13 @@ extern "C" B200_API b200_ctx *b200_create(int32_t device_ordinal) {
     c->stream = c->own_stream;
     for (int i = 0; i < 3; i++)
         if ((e = cudaStreamCreateWithFlags(&c->copy_streams[i], cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = greatest priority
+        if ((e = cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail(e);
+    }
+    if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail(e);
     if ((e = cudaMallocHost(&c->pinned_small, 4096)) != cudaSuccess) return bail(e);
@@ -70,6 +77,7 @@ extern "C" B200_API b200_ctx *b200_create(int32_t device_ordinal) {
     c->small.cap = SM_WORDS * 4;
     c->dev_bytes += c->small.cap;
     if ((e = cudaMemset(c->small.p, 0, SM_WORDS * 4)) != cudaSuccess) return bail(e);
+    c->phase_timing = getenv("B200_PHASE_TIMING") != nullptr;
     g_create_status = B200_OK;
     return c;
 }
@@ -89,9 +97,14 @@ extern "C" B200_API void b200_destroy(b200_ctx *c) {
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->pinned_small) cudaFreeHost(c->pinned_small);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->chunk_events) cudaEventDestroy(e);
+    for (auto &p : c->phases) cudaEventDestroy(p.second);
+    for (cudaEvent_t e : c->phase_pool) cudaEventDestroy(e);
     for (int i = 0; i < 3; i++)
         if (c->copy_streams[i]) cudaStreamDestroy(c->copy_streams[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -138,9 +151,17 @@ static int32_t map_dev_error(b200_ctx *c, int code) {
     }
 }
 
+// an error word read back and reported right away (mid-call read-backs of the resident / dynamic paths): the word is
+// cleared, otherwise the next build would latch it as a still unreported violation of an async call
+static int32_t report_dev_error_now(b200_ctx *c, int code) {
+    cudaMemsetAsync(small_u32(c) + SM_ERR, 0, 4, c->stream);
+    return map_dev_error(c, code);
+}
+
 // waits for the stream, folds the timing / counters of the last build into stats, returns the sticky status
 static int32_t sync_and_status(b200_ctx *c) {
     CU(cudaStreamSynchronize(c->stream));
+    if (c->phase_timing) phase_report(c);
     uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
     CU(cudaMemcpyAsync(ps, small_u32(c) + SM_ERR, 8, cudaMemcpyDeviceToHost, c->stream));  // current + sticky word
     CU(cudaMemcpyAsync(ps + 8, small_u32(c) + SM_COUNTERS, 32, cudaMemcpyDeviceToHost, c->stream));
@@ -170,9 +191,11 @@ static int32_t reset_build_state(b200_ctx *c) {
     c->stats = b200_stats{};
     c->stats_wavefront = false;
     CU(cudaEventRecord(c->ev0, c->stream));
+    phase_mark(c, "start");
     return B200_OK;
 }
 static int32_t finish_build_state(b200_ctx *c) {
+    phase_mark(c, "end");
     CU(cudaEventRecord(c->ev1, c->stream));
     c->stats_pending = true;
     return B200_OK;

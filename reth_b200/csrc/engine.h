@@ -21,6 +21,10 @@ struct b200_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr};
+    // structure pass of a build (sorts, scans, flags: memory / latency bound) runs here, next to the ALU-bound leaf pass
+    // on `stream`; highest priority, so that its short kernels get the SM slots the leaf pass frees
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> chunk_events;
     std::mutex mu;
@@ -40,7 +44,39 @@ struct b200_ctx {
     // staging for host-pointer entry points
     DevBuf in_a, in_b, in_c, in_d, in_e, out_a, chunk_in[3], chunk_out[3];
     void *pinned_small = nullptr;  // 4 KiB page-locked readback area
+    // B200_PHASE_TIMING=1 (development aid): CUDA events at the phase boundaries of a build, reported by b200_sync on stderr
+    bool phase_timing = false;
+    std::vector<std::pair<const char *, cudaEvent_t>> phases;
+    std::vector<cudaEvent_t> phase_pool;
 };
+
+inline void phase_mark(b200_ctx *c, const char *name) {
+    if (!c->phase_timing) return;
+    cudaEvent_t ev = nullptr;
+    if (!c->phase_pool.empty()) {
+        ev = c->phase_pool.back();
+        c->phase_pool.pop_back();
+    } else if (cudaEventCreate(&ev) != cudaSuccess) {
+        return;
+    }
+    cudaEventRecord(ev, c->stream);
+    c->phases.emplace_back(name, ev);
+}
+inline void phase_report(b200_ctx *c) {  // after a stream synchronize
+    if (c->phases.size() > 1) {
+        float total = 0;
+        cudaEventElapsedTime(&total, c->phases.front().second, c->phases.back().second);
+        fprintf(stderr, "[b200 phases] total %.3f ms:", total);
+        for (size_t i = 1; i < c->phases.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->phases[i - 1].second, c->phases[i].second);
+            fprintf(stderr, " %s %.3f", c->phases[i].first, ms);
+        }
+        fprintf(stderr, "\n");
+    }
+    for (auto &p : c->phases) c->phase_pool.push_back(p.second);
+    c->phases.clear();
+}
 
 inline int32_t fail(b200_ctx *c, int32_t code, const char *fmt, ...) {
     char buf[512];

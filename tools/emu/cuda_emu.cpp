@@ -334,6 +334,8 @@ cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cu
 cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { if (n) memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new emuStream{0}; return cudaSuccess; }
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { *s = new emuStream{0}; return cudaSuccess; }
+cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { if (lo) *lo = 0; if (hi) *hi = -5; return cudaSuccess; }
 cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = new emuStream{0}; return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { if (s != cudaStreamLegacy) delete s; return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }

@@ -224,6 +224,8 @@ cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cu
 cudaError_t cudaMemset(void *d, int v, size_t n);
 cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *, unsigned);
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *, unsigned, int);
+cudaError_t cudaDeviceGetStreamPriorityRange(int *, int *);
 cudaError_t cudaStreamCreate(cudaStream_t *);
 cudaError_t cudaStreamDestroy(cudaStream_t);
 cudaError_t cudaStreamSynchronize(cudaStream_t);
