@@ -353,9 +353,8 @@ def main():
     ap.add_argument("--skip-c4", action="store_true")
     ap.add_argument("--c4-leaves", type=int, default=31_250_000, help="leaves per GPU (250M over 8 GPUs)")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--dynamic", action="store_true", help="also time the dynamic resident trie / state (tools/dtrie_bench.py, "
-                    "tools/dstate_bench.py) in subprocesses and attach their JSON under \"dynamic\" (off by default: those "
-                    "paths are emulation-validated only until their first B200 run)")
+    ap.add_argument("--skip-dynamic", action="store_true", help="skip the in-place block-update legs (dynamic resident trie / "
+                    "state: tools/dtrie_bench.py, tools/dstate_bench.py, each in its own process) and the f2/f3/f4 throughput legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -370,6 +369,10 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one process per GPU: this rank's CPUs and its page-locked staging buffers on the GPU's own socket (SCALE_r01: GPUs 0-3
+    # hang off NUMA node 0, 4-7 off node 1; the e2e leg moves 640 MB per step and GPU through host memory)
+    from reth_b200 import numa_bind_thread
+    numa_node = numa_bind_thread(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL_DEBUG is left as the caller set it (the driver reads the communicator's rank count from that log).
@@ -442,7 +445,7 @@ def main():
     dt = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e = {"value": world * n * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * 32,
-           "d2h_bytes_per_step": n * 32, "steps": e2e_steps,
+           "d2h_bytes_per_step": n * 32, "steps": e2e_steps, "numa_node_bound": numa_node,
            "api": "b200_keccak256_fixed (host pointers, page-locked, chunked double-buffered H2D/kernel/D2H)"}
     eng.use_torch_stream()
 
@@ -472,7 +475,7 @@ def main():
             state_root["cpu_baseline"] = cpu_state_root_baseline()
 
     dynamic = None
-    if args.dynamic and rank == 0 and world == 1:
+    if not args.skip_dynamic and rank == 0 and world == 1:
         dynamic = bench_dynamic(args)
 
     if rank == 0:
@@ -784,27 +787,35 @@ def bench_incremental(args, eng, dev, sm_mhz=None, skip_cpu=False):
 
 
 def bench_dynamic(args):
-    """--dynamic: the emulation-validated parts (dynamic trie / state, ordered roots, device table rows), each in its own
-    process (its own CUDA context and a
-    timeout), so that whatever happens there cannot touch the numbers above."""
+    """The in-place block-update path (the role reth's sparse trie plays on the live path) and the
+    f2/f3/f4 throughput legs, each in its own process (its own CUDA context and a timeout) so that whatever happens there
+    cannot touch the numbers above.  Every leg checks itself: the dynamic legs compare every block's root with the static
+    merge + from-scratch rebuild path (dtrie) / a device-resident twin (dstate) and finally undo all blocks in one block,
+    which must restore the root of the from-scratch build the state was created from."""
     import subprocess
     root = os.path.dirname(os.path.abspath(__file__))
     out = {}
     runs = {
-        "dtrie_value_updates": ["tools/dtrie_bench.py", "--base", str(args.base_accounts), "--dirty", str(args.dirty), "--mix", "100,0,0"],
-        "dtrie_mixed_block": ["tools/dtrie_bench.py", "--base", str(args.base_accounts), "--dirty", str(args.dirty), "--mix", "80,10,10"],
-        "dstate_c3_shape": ["tools/dstate_bench.py", "--accounts", "1000000", "--slots", "16", "--touch", "2000", "--slot-writes", "10"],
+        "dtrie_apply_mixed_block": ["tools/dtrie_bench.py", "--base", str(args.base_accounts), "--dirty", str(args.dirty),
+                                    "--mix", "80,10,10", "--compare", "--cpu-sample", "1000000"],
+        "dstate_apply_c3_shape": ["tools/dstate_bench.py", "--accounts", "1000000", "--slots", "16", "--touch", "2000",
+                                  "--slot-writes", "10", "--device-resident", "--cpu-sample", "40000"],
+        "hash_sort_keys": ["tools/hash_sort_bench.py", "--keys", "10000000"],
         "ordered_roots_receipts": ["tools/ordered_bench.py", "--blocks", "2000", "--items", "200", "--shape", "receipts"],
-        "ordered_roots_transactions": ["tools/ordered_bench.py", "--blocks", "2000", "--items", "200", "--shape", "transactions"],
         "table_rows_c3_shape": ["tools/rows_bench.py", "--accounts", "1000000", "--slots", "16"],
     }
     for name, cmd in runs.items():
+        if not os.path.exists(os.path.join(root, cmd[0])):
+            continue
         try:
-            r = subprocess.run([sys.executable] + cmd, cwd=root, capture_output=True, text=True, timeout=900)
+            r = subprocess.run([sys.executable] + cmd, cwd=root, capture_output=True, text=True, timeout=600)
             last = [l for l in r.stdout.splitlines() if l.startswith("{")]
             out[name] = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-300:]}
         except Exception as e:  # noqa: BLE001
             out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    d = out.get("dtrie_apply_mixed_block", {})
+    if d.get("merge_rebuild_wall_us_median") and d.get("apply_wall_us_median"):
+        d["speedup_over_merge_rebuild"] = d["merge_rebuild_wall_us_median"] / d["apply_wall_us_median"]
     return out
 
 

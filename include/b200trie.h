@@ -65,6 +65,12 @@ B200_API const char *b200_version(void);
 B200_API int32_t b200_set_stream(b200_ctx *, void *cuda_stream);
 B200_API int32_t b200_sync(b200_ctx *);
 /* Page-locked host buffers for the host-pointer entry points (pageable memory works too, but is slower). */
+/* Binds the CALLING thread to the host NUMA node the GPU hangs off (its CPUs and, as preferred memory policy, its DRAM),
+ * so that page-locked staging buffers allocated afterwards (b200_host_alloc, or the caller's own) and the copies out of them
+ * stay on the GPU's socket — the placement a one-process-per-GPU host wants before it allocates (reth's stage pipeline
+ * drains cursors into such buffers, hashing_account.rs:176-238).  Returns the node (>= 0), -1 when the platform exposes no
+ * NUMA topology for the device (nothing is changed then).  Never fails hard; needs no context. */
+B200_API int32_t b200_numa_bind_thread(int32_t device_ordinal);
 B200_API void *b200_host_alloc(size_t bytes);
 B200_API void b200_host_free(void *);
 /* Scratch the context currently holds on the device, bytes. */

@@ -115,6 +115,7 @@ def load():
     sig("b200_version", C.c_char_p)
     sig("b200_set_stream", i32, vp, vp)
     sig("b200_sync", i32, vp)
+    sig("b200_numa_bind_thread", C.c_int32, C.c_int32)
     sig("b200_host_alloc", vp, C.c_size_t)
     sig("b200_host_free", None, vp)
     sig("b200_device_bytes", u64, vp)

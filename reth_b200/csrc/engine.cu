@@ -4,7 +4,17 @@
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 
+#if defined(__linux__)
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+#endif
+
 #include <algorithm>
+#include <cctype>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -123,6 +133,62 @@ extern "C" B200_API int32_t b200_set_stream(b200_ctx *c, void *cuda_stream) {
                 : cuda_stream == nullptr                    ? cudaStreamLegacy
                                                             : static_cast<cudaStream_t>(cuda_stream);
     return B200_OK;
+}
+
+extern "C" B200_API int32_t b200_numa_bind_thread(int32_t device_ordinal) {
+#if defined(__linux__)
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device_ordinal) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char *p = bus; *p; p++) *p = (char)tolower((unsigned char)*p);
+    char path[160];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0 || node >= 1024) return -1;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return -1;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int a = 0, b = 0, any = 0;
+    for (;;) {  // "0-31,64-95"
+        if (fscanf(f, "%d", &a) != 1) break;
+        b = a;
+        int ch = fgetc(f);
+        if (ch == '-') {
+            if (fscanf(f, "%d", &b) != 1) break;
+            ch = fgetc(f);
+        }
+        for (int cpu = a; cpu <= b && cpu < CPU_SETSIZE; cpu++) {
+            CPU_SET(cpu, &set);
+            any = 1;
+        }
+        if (ch != ',') break;
+    }
+    fclose(f);
+    if (!any) return -1;
+    // keep only CPUs the process may use at all (cgroup / taskset), then bind; an empty intersection changes nothing
+    cpu_set_t cur, both;
+    if (sched_getaffinity(0, sizeof cur, &cur) == 0) {
+        CPU_AND(&both, &set, &cur);
+        if (CPU_COUNT(&both) == 0) return -1;
+        set = both;
+    }
+    if (sched_setaffinity(0, sizeof set, &set) != 0) return -1;
+    unsigned long mask[16] = {0};  // MPOL_PREFERRED: fall back to other nodes rather than fail an allocation
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, (unsigned long)(8 * sizeof mask));
+    return node;
+#else
+    (void)device_ordinal;
+    return -1;
+#endif
 }
 
 extern "C" B200_API void *b200_host_alloc(size_t bytes) {

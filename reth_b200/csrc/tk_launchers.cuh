@@ -89,9 +89,9 @@ cudaError_t launch_leaves(const ForestDev &f, bool account, const uint8_t *value
         size_t smem = (size_t)LEAF_WORDS_ACCOUNT * LEAF_BLOCK * 4;
         k<<<persistent_grid(k, LEAF_BLOCK, smem, f.n), LEAF_BLOCK, smem, st>>>(f, values, storage_roots);
     } else {
-        auto k = leaf_kernel<LEAF_BLOCK, false>;
-        size_t smem = (size_t)LEAF_WORDS_STORAGE * LEAF_BLOCK * 4;
-        k<<<persistent_grid(k, LEAF_BLOCK, smem, f.n), LEAF_BLOCK, smem, st>>>(f, values, nullptr);
+        auto k = leaf_storage_kernel<LEAF_BLOCK>;
+        size_t smem = (size_t)LEAF_WORDS_STORAGE * LEAF_BLOCK * 4;  // the strip of the rare leaves outside the register path
+        k<<<blocks_for(f.n, LEAF_BLOCK), LEAF_BLOCK, smem, st>>>(f, values);
     }
     return cudaGetLastError();
 }

@@ -349,6 +349,11 @@ class Engine:
         self._check(self.lib.b200_dev_status(self.ctx))
 
 
+def numa_bind_thread(device: int = 0) -> int:
+    """b200_numa_bind_thread: bind the calling thread (CPUs + preferred memory) to the GPU's NUMA node; -1 = no topology."""
+    return int(_lib.load().b200_numa_bind_thread(int(device)))
+
+
 class ResidentTrie:
     """Handle on a b200_trie: the account trie of a whole state kept in HBM for incremental roots (BASELINE config 5).
     `update` commits value changes of existing accounts by re-hashing only their root paths."""

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--slot-writes", type=int, default=10)
     ap.add_argument("--blocks", type=int, default=12)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="accounts of the oracle's from-scratch build timed as the CPU baseline (0 = skip)")
     ap.add_argument("--device-resident", action="store_true",
                     help="also apply every block from device memory (b200_dstate_apply_dev) on a twin state and compare roots")
     args = ap.parse_args()
@@ -62,9 +63,13 @@ def main():
         state = {keys[i].tobytes(): (accs[i].copy(), {skeys[j].tobytes(): svals[j].tobytes() for j in range(int(offs[i]), int(offs[i + 1]))})
                  for i in range(n)}
     live = [keys[i].tobytes() for i in range(n)]
+    live_base = {k: i for i, k in enumerate(live)}   # base account -> row
     slot_of = {}  # a few known slots per touched account, to zero / change later
     twin = DynamicState.create(eng, keys, accs, skeys, svals, offs) if args.device_resident else None
-    lat, dev_ms, built, mism, lat_dev, mism_twin = [], [], [], 0, [], 0
+    lat, dev_ms, built, mism, lat_dev, mism_twin, launches = [], [], [], 0, [], 0, []
+    seed_root = ds.root()
+    touched_existing, inserted_accounts = set(), set()
+    base_set = None
     EX, UN, WI = DynamicState.EXISTS, DynamicState.UNCHANGED, DynamicState.WIPED
     for b in range(args.blocks):
         block = {}
@@ -124,9 +129,14 @@ def main():
             dev_wall = time.perf_counter() - t0
             if b >= 2:
                 lat_dev.append(dev_wall * 1e6)
+        l0 = eng.launch_count()
         t0 = time.perf_counter()
         root = ds.apply(bk, ba, bf, bsk, bsv, so_arr)
         wall = time.perf_counter() - t0
+        if b >= 2:
+            launches.append(eng.launch_count() - l0)
+        for k in ks:
+            (touched_existing if k in live_base else inserted_accounts).add(k)
         if twin is not None:
             mism_twin += bytes(d_root.cpu().numpy()) != root
         st = eng.last_stats()
@@ -166,7 +176,43 @@ def main():
             full = eng.state_root_full(fk, fa, np.frombuffer(b"".join(fsk), np.uint8).reshape(-1, 32),
                                        np.frombuffer(b"".join(fsv), np.uint8).reshape(-1, 32), np.array(fo, np.uint64))
             mism += full != root
-    print(json.dumps({"accounts": n, "slots_per_account": args.slots, "touched_accounts_per_block": args.touch,
+    # ---- undo everything in one block: every touched base account gets its base value and (wipe +) its base slots back,
+    # every account the blocks created is destroyed.  The root must return to the seed root — the root of the from-scratch
+    # build the state was created from — without any model of the 17M-leaf state on the host.
+    undo_keys = sorted(touched_existing | inserted_accounts)
+    m = len(undo_keys)
+    bk = np.frombuffer(b"".join(undo_keys), np.uint8).reshape(m, 32)
+    ba = np.zeros(m, ACCOUNT_DTYPE)
+    bf = np.zeros(m, np.uint8)
+    rows, so = [], [0]
+    for i, k in enumerate(undo_keys):
+        r = live_base.get(k)
+        if r is not None:
+            ba[i] = accs[r]
+            bf[i] = EX | WI
+            rows.append(np.arange(int(offs[r]), int(offs[r + 1])))
+            so.append(so[-1] + int(offs[r + 1] - offs[r]))
+        else:
+            so.append(so[-1])
+    rr = np.concatenate(rows) if rows else np.zeros(0, np.int64)
+    undo_root = ds.apply(bk, ba, bf, skeys[rr], svals[rr], np.array(so, np.uint64))
+    undo_ok = bool(undo_root == seed_root and ds.accounts() == n and ds.slots() == total)
+    cpu = None
+    if args.cpu_sample:
+        import oracle
+        cs = args.cpu_sample
+        threads = len(os.sched_getaffinity(0))
+        t0 = time.perf_counter()
+        oracle.state_root_full(keys[:cs], accs[:cs], skeys[:int(offs[cs])], svals[:int(offs[cs])], offs[:cs + 1], threads=threads)
+        dt = time.perf_counter() - t0
+        leaves = cs + int(offs[cs])
+        cpu = {"value": leaves / dt, "unit": "leaves/s", "cores": threads, "kind": "port",
+               "sample": f"from-scratch ParallelStateRoot-shaped build of {cs} accounts x {args.slots} slots "
+                         "(the CPU restatement has no in-place update path)",
+               "equivalent_rebuild_s_at_state_size": (n + total) / (leaves / dt)}
+    print(json.dumps({"undo_block_restores_seed_root": undo_ok, "launches_per_block": float(np.median(launches)) if launches else None,
+                      "cpu_baseline": cpu,
+                      "accounts": n, "slots_per_account": args.slots, "touched_accounts_per_block": args.touch,
                       "slot_writes_per_storage_touch": args.slot_writes, "blocks": args.blocks,
                       "apply_wall_us_median": float(np.median(lat)), "apply_device_ms_median": float(np.median(dev_ms)),
                       "rehashed_nodes_median": float(np.median(built)), "seed_build_s": build_s,

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--dirty", type=int, default=10_000)
     ap.add_argument("--mix", default="80,10,10", help="update,insert,delete percent")
     ap.add_argument("--blocks", type=int, default=12)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="accounts of the oracle's from-scratch fold timed as the CPU baseline (0 = skip)")
     ap.add_argument("--compare", action="store_true", help="also run every block through b200_trie_apply and compare roots")
     args = ap.parse_args()
     import torch
@@ -52,7 +53,11 @@ def main():
     rng = np.random.default_rng(55)
     live = keys.view(torch.uint8).view(n, 32).cpu().numpy()   # host copy of the key set, kept in step with the trie
     live_set = None
-    lat, dev_ms, built, mismatches = [], [], [], 0
+    lat, dev_ms, built, mismatches, lat_rebuild, launches = [], [], [], 0, [], []
+    base_root = trie.root()
+    base_index = {}          # key -> row in the base arrays, for every key a block touched (the final undo block needs the base value)
+    inserted_total = set()
+    h_accts = accts.cpu().numpy().view(ACCOUNT_DTYPE).reshape(-1)
     for b in range(args.blocks):
         n_upd, n_ins, n_del = m * pu // 100, m * pi // 100, m * pd // 100
         pick = rng.choice(len(live), n_upd + n_del, replace=False)
@@ -66,6 +71,7 @@ def main():
         da["nonce"] = b + 1
         da["balance"][:, 24:] = rng.integers(0, 256, (len(dk), 8), dtype=np.uint8)
         da["code_hash"] = np.frombuffer(bytes.fromhex("c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"), np.uint8)
+        l0 = eng.launch_count()
         t0 = time.perf_counter()
         root, stats = trie.apply(dk, da, present, want_stats=True)
         wall = time.perf_counter() - t0
@@ -73,13 +79,66 @@ def main():
             lat.append(wall * 1e6)
             dev_ms.append(stats["device_ms"])
             built.append(stats["branches_added"])
-        if ref is not None:
+            launches.append(eng.launch_count() - l0)
+        if ref is not None:  # the same block through merge + from-scratch rebuild (the static, oracle-pinned path)
+            t0 = time.perf_counter()
             r2 = ref.apply(dk, da, present)[0]
+            if b >= 2:
+                lat_rebuild.append((time.perf_counter() - t0) * 1e6)
             mismatches += r2 != root
+        for kk in ins_keys:
+            inserted_total.add(kk.tobytes())
+        for kk in list(upd_keys) + list(del_keys):
+            base_index.setdefault(kk.tobytes(), None)
         mask = np.ones(len(live), bool)
         mask[pick[n_upd:]] = False
         live = np.concatenate([live[mask], ins_keys])
-    print(json.dumps({"base_leaves": n, "dirty": m, "mix_update_insert_delete": [pu, pi, pd], "blocks": args.blocks,
+    # ---- undo everything in one block: base values back, deleted base keys re-inserted, inserted keys deleted.  The root must
+    # return to the root of the from-scratch build the trie was created from (independent of any model of the state).
+    base_keys_np = keys.view(torch.uint8).view(n, 32).cpu().numpy()
+    prefix = np.ascontiguousarray(base_keys_np[:, :8]).view(">u8").reshape(-1)   # sorted with the keys (big-endian)
+
+    def find_row(kb):
+        want = int.from_bytes(kb[:8], "big")
+        row = int(np.searchsorted(prefix, want))
+        while row < n and int(prefix[row]) == want:
+            if base_keys_np[row].tobytes() == kb:
+                return row
+            row += 1
+        return -1
+    undo = {}
+    for kb in base_index:
+        if kb in inserted_total:
+            continue
+        row = find_row(kb)
+        if row >= 0:
+            undo[kb] = (1, h_accts[row])
+    for kb in inserted_total:
+        if kb not in undo:
+            undo[kb] = (0, h_accts[0])
+    uk = sorted(undo)
+    dk = np.frombuffer(b"".join(uk), np.uint8).reshape(-1, 32)
+    da = np.zeros(len(uk), ACCOUNT_DTYPE)
+    present = np.zeros(len(uk), np.uint8)
+    for i, kb in enumerate(uk):
+        present[i], da[i] = undo[kb]
+    undo_root = trie.apply(dk, da, present)
+    undo_ok = bool(undo_root == base_root and len(trie) == n)
+    cpu = None
+    if args.cpu_sample:
+        import oracle
+        from tests.util import synth_accounts
+        ak, ac = synth_accounts(5, args.cpu_sample)
+        t0 = time.perf_counter()
+        oracle.state_root(ak, ac)
+        dt = time.perf_counter() - t0
+        cpu = {"value": args.cpu_sample / dt, "unit": "leaves/s", "cores": 1, "kind": "port",
+               "sample": f"from-scratch account-trie fold over {args.cpu_sample} accounts (the CPU restatement has no in-place update path)",
+               "equivalent_rebuild_s_at_base_size": n / (args.cpu_sample / dt)}
+    print(json.dumps({"undo_block_restores_base_root": undo_ok, "launches_per_block": float(np.median(launches)) if launches else None,
+                      "merge_rebuild_wall_us_median": float(np.median(lat_rebuild)) if lat_rebuild else None,
+                      "cpu_baseline": cpu,
+                      "base_leaves": n, "dirty": m, "mix_update_insert_delete": [pu, pi, pd], "blocks": args.blocks,
                       "apply_wall_us_median": float(np.median(lat)), "apply_device_ms_median": float(np.median(dev_ms)),
                       "rehashed_nodes_median": float(np.median(built)), "base_build_ms": build_s * 1e3,
                       "leaves_after": len(trie), "resident_bytes": trie.device_bytes(),
