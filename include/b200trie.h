@@ -261,6 +261,43 @@ B200_API int32_t b200_subtrie_frontier_dev(b200_ctx *, const void *d_acct_keys32
 B200_API int32_t b200_root_from_frontier(b200_ctx *, const b200_frontier_entry frontier[16], uint8_t root32[32]);
 B200_API int32_t b200_root_from_frontier_dev(b200_ctx *, const void *d_frontier, void *d_root32);
 
+/* ------------------------------------------------------------------------------------------------ streamed / resumable root
+ * StateRoot::with_threshold / root_with_progress / with_intermediate_state (crates/trie/trie/src/trie.rs:73-85,156-330;
+ * progress.rs) and MerkleStage's chunked rebuild with its MerkleCheckpoint (crates/stages/stages/src/stages/merkle.rs:
+ * 118-148,184-366): the state is committed in ascending account-key ranges, e.g. when it does not fit HBM or host memory
+ * at once.  Each push carries a range of accounts (strictly after every key pushed before) with their complete storage, in
+ * the layout of b200_state_root_full.  A push builds the storage tries of its accounts and every top-nibble bucket of the
+ * account trie that the range closes; closed buckets survive as 68-byte frontier entries (the entries of the multi-GPU
+ * path), the accounts of the still open bucket (at most 1/16 of the state, 136 bytes each) stay on the device.  Stored
+ * nodes leave with the push that closes them (account nodes: trie_id = top nibble; storage nodes: trie_id = index of the
+ * account inside that push), like the per-chunk TrieUpdates of StateRootProgress::Progress.  finish closes the last bucket
+ * and folds the frontier.  k pushes give exactly the root and the union of updates of one b200_state_root_full call. */
+typedef struct b200_root_stream b200_root_stream;
+typedef struct {
+    uint64_t accounts;         /* pushed so far */
+    uint64_t slots;
+    uint64_t open_accounts;    /* carried in HBM: the accounts of the open bucket */
+    uint32_t closed_buckets;   /* bit i: top nibble i is finished */
+} b200_stream_progress;
+/* What survives a restart (the role of MerkleCheckpoint): frontier of the closed buckets + where to resume.  After
+ * b200_root_stream_resume the caller pushes again from the first key whose top nibble is resume_nibble (16: nothing left). */
+typedef struct {
+    b200_frontier_entry frontier[16];
+    uint32_t closed_mask;
+    uint32_t resume_nibble;
+    uint32_t retain_updates;
+    uint32_t _reserved;
+} b200_stream_checkpoint;
+B200_API int32_t b200_root_stream_begin(b200_ctx *, int32_t retain_updates, b200_root_stream **out);
+B200_API int32_t b200_root_stream_push(b200_root_stream *, const uint8_t *acct_keys32, const b200_account *accts,
+                                       uint64_t n_accounts, const uint8_t *slot_keys32, const uint8_t *values32_be,
+                                       const uint64_t *seg_offsets, b200_updates *opt_account_updates,
+                                       b200_updates *opt_storage_updates, b200_stream_progress *opt_progress);
+B200_API int32_t b200_root_stream_finish(b200_root_stream *, uint8_t root32[32], b200_updates *opt_account_updates);
+B200_API int32_t b200_root_stream_checkpoint(const b200_root_stream *, b200_stream_checkpoint *out);
+B200_API int32_t b200_root_stream_resume(b200_ctx *, const b200_stream_checkpoint *, b200_root_stream **out);
+B200_API void b200_root_stream_free(b200_root_stream *);
+
 /* ------------------------------------------------------------------------------------------------ ordered roots
  * Transactions / receipts / withdrawals roots of a batch of lists in one call: what
  * OrderedTrieRootEncodedBuilder::finalize (crates/trie/common/src/ordered_root.rs:240-257) and alloy's

@@ -86,6 +86,18 @@ class FrontierEntry(C.Structure):
 
 assert C.sizeof(FrontierEntry) == 68
 
+
+class StreamProgress(C.Structure):
+    _fields_ = [("accounts", C.c_uint64), ("slots", C.c_uint64), ("open_accounts", C.c_uint64), ("closed_buckets", C.c_uint32)]
+
+
+class StreamCheckpoint(C.Structure):
+    _fields_ = [("frontier", FrontierEntry * 16), ("closed_mask", C.c_uint32), ("resume_nibble", C.c_uint32),
+                ("retain_updates", C.c_uint32), ("_reserved", C.c_uint32)]
+
+
+assert C.sizeof(StreamCheckpoint) == 16 * 68 + 16
+
 _lib = None
 
 
@@ -147,6 +159,12 @@ def load():
     sig("b200_subtrie_frontier_dev", i32, vp, vp, vp, u64, vp, vp, vp, u64, vp)
     sig("b200_root_from_frontier", i32, vp, C.POINTER(FrontierEntry), vp)
     sig("b200_root_from_frontier_dev", i32, vp, vp, vp)
+    sig("b200_root_stream_begin", i32, vp, i32, C.POINTER(vp))
+    sig("b200_root_stream_push", i32, vp, vp, vp, u64, vp, vp, vp, PU, PU, C.POINTER(StreamProgress))
+    sig("b200_root_stream_finish", i32, vp, vp, PU)
+    sig("b200_root_stream_checkpoint", i32, vp, C.POINTER(StreamCheckpoint))
+    sig("b200_root_stream_resume", i32, vp, C.POINTER(StreamCheckpoint), C.POINTER(vp))
+    sig("b200_root_stream_free", None, vp)
     sig("b200_trie_create", i32, vp, vp, vp, vp, u64, C.POINTER(vp), vp)
     sig("b200_trie_create_dev", i32, vp, vp, vp, vp, u64, C.POINTER(vp), vp)
     sig("b200_trie_update", i32, vp, vp, vp, vp, u64, vp, PU, PS)

@@ -290,6 +290,7 @@ extern "C" B200_API uint64_t b200_launch_count(const b200_ctx *c) { return c ? c
 #include "eng_updates.inl"
 #include "eng_roots.inl"
 #include "eng_frontier.inl"
+#include "eng_stream.inl"
 #include "eng_resident.inl"
 #include "eng_darena.inl"
 #include "eng_dtrie.inl"

@@ -349,6 +349,85 @@ class Engine:
         self._check(self.lib.b200_dev_status(self.ctx))
 
 
+class RootStream:
+    """b200_root_stream_*: a state root committed in ascending account-key ranges (StateRoot::with_threshold /
+    root_with_progress / with_intermediate_state, trie.rs:73-85,156; MerkleStage's chunked rebuild, merkle.rs:184-366).
+    push() returns the progress and, with retain_updates, the stored nodes the range closed; finish() the root."""
+
+    def __init__(self, engine: Engine, retain_updates: bool = False, _handle=None):
+        self.engine = engine
+        if _handle is None:
+            h = C.c_void_p()
+            engine._check(engine.lib.b200_root_stream_begin(engine.ctx, 1 if retain_updates else 0, C.byref(h)))
+            _handle = h
+        self.handle = _handle
+        self.retain = retain_updates
+
+    def push(self, acct_keys, accounts, slot_keys, values, seg_offsets):
+        """-> progress dict [, account records (trie_id = top nibble), storage records (trie_id = account index in this push)]"""
+        acct_keys = _np(acct_keys).reshape(-1, 32)
+        accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
+        slot_keys = _np(slot_keys).reshape(-1, 32)
+        values = _np(values).reshape(-1, 32)
+        seg_offsets = _np(seg_offsets, np.uint64)
+        n = len(acct_keys)
+        if len(seg_offsets) != n + 1 or len(accounts) != n:
+            raise ValueError("seg_offsets must have n_accounts + 1 entries, accounts n_accounts")
+        if int(seg_offsets[0]) != 0 or int(seg_offsets[n]) != len(slot_keys) or len(values) != len(slot_keys):
+            raise ValueError("seg_offsets must start at 0 and end at the number of slot rows (keys and values)")
+        from ._lib import StreamProgress
+        ua, us, pr = Updates(), Updates(), StreamProgress()
+        w = self.retain
+        self.engine._check(self.engine.lib.b200_root_stream_push(
+            self.handle, _ptr(acct_keys), _ptr(accounts), n, _ptr(slot_keys), _ptr(values), _ptr(seg_offsets),
+            C.byref(ua) if w else None, C.byref(us) if w else None, C.byref(pr)))
+        prog = {"accounts": int(pr.accounts), "slots": int(pr.slots), "open_accounts": int(pr.open_accounts),
+                "closed_buckets": int(pr.closed_buckets)}
+        if not w:
+            return prog
+        return prog, updates_to_records(ua, self.engine.lib), updates_to_records(us, self.engine.lib)
+
+    def finish(self):
+        """-> root [, account records of the last bucket]"""
+        root = np.empty(32, np.uint8)
+        ua = Updates()
+        self.engine._check(self.engine.lib.b200_root_stream_finish(self.handle, _ptr(root), C.byref(ua) if self.retain else None))
+        if self.retain:
+            return root.tobytes(), updates_to_records(ua, self.engine.lib)
+        return root.tobytes()
+
+    def checkpoint(self) -> bytes:
+        """The resumable part (1104 bytes): frontier of the closed buckets + the nibble to resume from (byte 1092)."""
+        from ._lib import StreamCheckpoint
+        cp = StreamCheckpoint()
+        self.engine._check(self.engine.lib.b200_root_stream_checkpoint(self.handle, C.byref(cp)))
+        return bytes(cp)
+
+    @staticmethod
+    def resume_nibble(checkpoint: bytes) -> int:
+        from ._lib import StreamCheckpoint
+        return int(StreamCheckpoint.from_buffer_copy(checkpoint).resume_nibble)
+
+    @classmethod
+    def resume(cls, engine: Engine, checkpoint: bytes) -> "RootStream":
+        from ._lib import StreamCheckpoint
+        cp = StreamCheckpoint.from_buffer_copy(checkpoint)
+        h = C.c_void_p()
+        engine._check(engine.lib.b200_root_stream_resume(engine.ctx, C.byref(cp), C.byref(h)))
+        return cls(engine, bool(cp.retain_updates), _handle=h)
+
+    def close(self):
+        if self.handle:
+            self.engine.lib.b200_root_stream_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 def numa_bind_thread(device: int = 0) -> int:
     """b200_numa_bind_thread: bind the calling thread (CPUs + preferred memory) to the GPU's NUMA node; -1 = no topology."""
     return int(_lib.load().b200_numa_bind_thread(int(device)))

@@ -35,6 +35,8 @@ class Tables:
     hashed_accounts: List[Tuple[bytes, Account]] = field(default_factory=list)          # HashedAccounts, key order
     hashed_storages: Dict[bytes, List[Tuple[bytes, int]]] = field(default_factory=dict)  # HashedStorages, key order
     trie_updates: Optional[TrieUpdates] = None                                # AccountsTrie + StoragesTrie rows
+    merkle_checkpoint: Optional[Tuple[bytes, bytes]] = None   # (last_account_key, stream checkpoint): MerkleCheckpoint
+    merkle_inner_state: Optional[object] = None               # the live IntermediateStateRootState between execute() calls
 
 
 class AccountHashingStage:
@@ -95,16 +97,45 @@ class MerkleStage:
         self.engine = engine
         self.resident: Optional[DynamicStateRoot] = None   # seeded by the first incremental execution
 
-    def execute(self, t: Tables, expected_state_root: Optional[bytes] = None) -> bytes:
+    def execute(self, t: Tables, expected_state_root: Optional[bytes] = None, threshold: Optional[int] = None,
+                max_steps: Optional[int] = None) -> Optional[bytes]:
+        """Rebuild leg (merkle.rs:210-310).  With `threshold` the build runs in ranges of at least that many hashed entries:
+        every step's TrieUpdates are written to the trie tables and the inner checkpoint (`t.merkle_checkpoint`, the role of
+        MerkleCheckpoint / save_execution_checkpoint, merkle.rs:118-148,255-275) is saved, exactly the loop the pipeline
+        drives by calling execute() until it reports done.  `max_steps` stops after that many ranges and returns None
+        (ExecOutput{done: false}); the next execute() continues from the saved checkpoint."""
         self.close()  # a rebuild invalidates the resident state
         state = HashedPostStateSorted(list(t.hashed_accounts),
                                       {k: HashedStorageSorted(list(v)) for k, v in t.hashed_storages.items()})
-        root, updates = StateRoot(self.engine, state).root_with_updates()
-        if expected_state_root is not None and root != expected_state_root:
-            # merkle.rs:437-453 -> StageError::Block{BodyStateRootDiff}
-            raise StageError(f"state root mismatch: got {root.hex()}, expected {expected_state_root.hex()}")
-        t.trie_updates = updates
-        return root
+        if threshold is None:
+            root, updates = StateRoot(self.engine, state).root_with_updates()
+            if expected_state_root is not None and root != expected_state_root:
+                # merkle.rs:437-453 -> StageError::Block{BodyStateRootDiff}
+                raise StageError(f"state root mismatch: got {root.hex()}, expected {expected_state_root.hex()}")
+            t.trie_updates = updates
+            t.merkle_checkpoint = None
+            return root
+        inter = getattr(t, "merkle_inner_state", None)
+        if inter is None:  # "Rebuilding trie": reset the checkpoint and clear the trie tables (merkle.rs:229-237)
+            t.trie_updates = TrieUpdates()
+            t.merkle_checkpoint = None
+        steps = 0
+        while True:
+            progress = StateRoot(self.engine, state).with_threshold(threshold).with_intermediate_state(inter) \
+                .root_with_progress()
+            self.write_trie_updates(t.trie_updates, progress.updates)
+            steps += 1
+            if progress.complete:
+                t.merkle_inner_state = None
+                t.merkle_checkpoint = None
+                if expected_state_root is not None and progress.root != expected_state_root:
+                    raise StageError(f"state root mismatch: got {progress.root.hex()}, expected {expected_state_root.hex()}")
+                return progress.root
+            inter = progress.state
+            t.merkle_inner_state = inter
+            t.merkle_checkpoint = (inter.last_hashed_key, inter.checkpoint())   # what would be persisted
+            if max_steps is not None and steps >= max_steps:
+                return None
 
     # ------------------------------------------------------------------ incremental leg
     def execute_incremental(self, t: Tables, changed_accounts: Dict[bytes, Optional[Account]],
@@ -131,22 +162,26 @@ class MerkleStage:
             post.accounts[ha[a]] = acc
         for a in set(changed_storage) | set(wiped):
             post.storages[ha[a]] = HashedStorage(a in wiped, {hs[int(s)]: int(v) for s, v in changed_storage.get(a, {}).items()})
-        # 2. plain + hashed tables
+        # 2. plain + hashed tables, built aside: they replace the live ones only after the root has been validated
+        # (merkle.rs:437-453 validates before the transaction commits; a mismatch drops it)
+        plain_accounts = dict(t.plain_accounts)
+        plain_storage = dict(t.plain_storage)
+        hashed_storages = dict(t.hashed_storages)
         hashed_accounts = dict(t.hashed_accounts)
         for a, acc in changed_accounts.items():
             if acc is None:
-                t.plain_accounts.pop(a, None)
-                t.plain_storage.pop(a, None)
+                plain_accounts.pop(a, None)
+                plain_storage.pop(a, None)
                 hashed_accounts.pop(ha[a], None)
-                t.hashed_storages.pop(ha[a], None)
+                hashed_storages.pop(ha[a], None)
             else:
-                t.plain_accounts[a] = acc
+                plain_accounts[a] = acc
                 hashed_accounts[ha[a]] = acc
         for a in set(changed_storage) | set(wiped):
             if changed_accounts.get(a, 0) is None:
                 continue
-            plain = {} if a in wiped else dict(t.plain_storage.get(a, {}))
-            hashed = {} if a in wiped else dict(t.hashed_storages.get(ha[a], []))
+            plain = {} if a in wiped else dict(plain_storage.get(a, {}))
+            hashed = {} if a in wiped else dict(hashed_storages.get(ha[a], []))
             for s, v in changed_storage.get(a, {}).items():
                 if v == 0:
                     plain.pop(int(s), None)
@@ -154,16 +189,20 @@ class MerkleStage:
                 else:
                     plain[int(s)] = int(v)
                     hashed[hs[int(s)]] = int(v)
-            t.plain_storage[a] = plain
+            plain_storage[a] = plain
             if hashed:
-                t.hashed_storages[ha[a]] = sorted(hashed.items())
+                hashed_storages[ha[a]] = sorted(hashed.items())
             else:
-                t.hashed_storages.pop(ha[a], None)
-        t.hashed_accounts = sorted(hashed_accounts.items())
-        # 3. commit on the device, validate, write the trie tables
+                hashed_storages.pop(ha[a], None)
+        # 3. commit on the device, validate, then publish the tables and write the trie tables
         root, upd = self.resident.commit(post)
         if expected_state_root is not None and root != expected_state_root:
+            # the device state has advanced past what the tables hold: drop it, the next execution re-seeds from the tables
+            self.close()
             raise StageError(f"state root mismatch: got {root.hex()}, expected {expected_state_root.hex()}")
+        t.plain_accounts, t.plain_storage = plain_accounts, plain_storage
+        t.hashed_storages = hashed_storages
+        t.hashed_accounts = sorted(hashed_accounts.items())
         self.write_trie_updates(t.trie_updates, upd)
         return root
 

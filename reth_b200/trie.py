@@ -66,12 +66,28 @@ class TrieUpdates:
 
 
 @dataclass
+class IntermediateStateRootState:
+    """crates/trie/trie/src/progress.rs:24-30.  reth keeps the HashBuilder stack and the walker position; here the open
+    right edge of the build is a b200_root_stream (frontier of the closed top-nibble buckets + the accounts of the open
+    bucket in HBM) and the position is the index of the next account of the sorted state."""
+    stream: object            # engine.RootStream
+    next_account: int
+    last_hashed_key: bytes
+
+    def checkpoint(self) -> bytes:
+        """What MerkleStage persists between runs (MerkleCheckpoint, merkle.rs:118-148): 1104 bytes."""
+        return self.stream.checkpoint()
+
+
+@dataclass
 class StateRootProgress:
-    """crates/trie/trie/src/progress.rs:12-21.  A device build never pauses: always `Complete`."""
-    root: bytes
+    """crates/trie/trie/src/progress.rs:12-21: `Complete(root, walked, updates)` (complete = True, state = None) or
+    `Progress(state, walked, updates)` (complete = False, root = None; `updates` are the nodes finished so far by this call)."""
+    root: Optional[bytes]
     hashed_entries_walked: int
     updates: TrieUpdates
     complete: bool = True
+    state: Optional[IntermediateStateRootState] = None
 
 
 class StateRootError(RuntimeError):
@@ -94,10 +110,16 @@ class StorageRoot:
         self.threshold = 100_000
 
     def with_prefix_set(self, prefix_set):
+        """Kept for interface parity (trie.rs:512-516).  This calculator is given every slot of the trie and hashes all of
+        them, so a changed-key set cannot alter its result; the skipping that prefix sets drive in reth happens in
+        IncrementalStateRoot (stored nodes + prefix sets) and in the resident paths."""
         self.prefix_set = prefix_set
         return self
 
     def with_threshold(self, threshold: int):
+        """trie.rs:523-527.  One storage trie is one device build (a 10M-slot trie takes milliseconds): `calculate`
+        always returns the Complete variant, whatever the threshold — the thresholded, resumable build is StateRoot's
+        (account ranges; every storage trie of a range is finished inside its push)."""
         self.threshold = threshold
         return self
 
@@ -136,14 +158,24 @@ class StorageRoot:
 
 
 class StateRoot:
-    """StateRoot::{root, root_with_updates, root_with_progress} — crates/trie/trie/src/trie.rs:54-158."""
+    """StateRoot::{root, root_with_updates, root_with_progress} — crates/trie/trie/src/trie.rs:54-158.
+
+    with_threshold(t) + root_with_progress(): the build stops after a range of accounts holding at least `t` hashed
+    entries (accounts + slots; reth counts retained trie updates, trie.rs:296-306 — a device build knows the entries of a
+    range before it runs, the updates only afterwards) and returns StateRootProgress(complete=False, state=...); feeding the
+    state back through with_intermediate_state() continues where it stopped.  root() / root_with_updates() ignore the
+    threshold like the reference (trie.rs:126-140)."""
 
     def __init__(self, engine: Engine, hashed_state: HashedPostStateSorted):
         self.engine, self.state = engine, hashed_state
         self.prefix_sets = TriePrefixSets()
         self.threshold = 100_000  # DEFAULT_INTERMEDIATE_THRESHOLD, trie.rs:25
+        self.previous_state: Optional[IntermediateStateRootState] = None
 
     def with_prefix_sets(self, prefix_sets: TriePrefixSets):
+        """A from-scratch build hashes every leaf it is given, so the changed-key sets have nothing to skip; only
+        `destroyed_accounts` is consumed (TrieUpdates::finalize).  The skip logic lives in IncrementalStateRoot (stored
+        nodes + prefix sets) and in the resident paths."""
         self.prefix_sets = prefix_sets
         return self
 
@@ -155,6 +187,10 @@ class StateRoot:
         self.threshold = 2**64 - 1
         return self
 
+    def with_intermediate_state(self, state: Optional[IntermediateStateRootState]):
+        self.previous_state = state
+        return self
+
     def root(self) -> bytes:
         return self._calculate(False).root
 
@@ -163,7 +199,14 @@ class StateRoot:
         return p.root, p.updates
 
     def root_with_progress(self) -> StateRootProgress:
-        return self._calculate(True)
+        if self.threshold >= 2**64 - 1 and self.previous_state is None:
+            return self._calculate(True)
+        return self._calculate_range()
+
+    def _finalize(self, updates: TrieUpdates):
+        # TrieUpdates::finalize (updates.rs:140-158): destroyed accounts -> is_deleted
+        for destroyed in self.prefix_sets.destroyed_accounts:
+            updates.storage_tries.setdefault(destroyed, StorageTrieUpdates()).is_deleted = True
 
     def _calculate(self, retain_updates: bool) -> StateRootProgress:
         keys, accts, skeys, svals, offs = self.state.to_flat()
@@ -187,11 +230,54 @@ class StateRoot:
                     updates.insert_storage_updates(addr, StorageTrieUpdates.deleted())
                 else:
                     updates.insert_storage_updates(addr, StorageTrieUpdates(storage_nodes=per_trie.get(i, {})))
-            # TrieUpdates::finalize (updates.rs:140-158): destroyed accounts -> is_deleted
-            for destroyed in self.prefix_sets.destroyed_accounts:
-                updates.storage_tries.setdefault(destroyed, StorageTrieUpdates()).is_deleted = True
+            self._finalize(updates)
         walked = int(len(keys) + len(skeys))
         return StateRootProgress(root, walked, updates)
+
+    def _calculate_range(self) -> StateRootProgress:
+        """One step of the thresholded build: push the next range of accounts into the stream; Complete when none is left."""
+        from .engine import RootStream
+        keys, accts, skeys, svals, offs = self.state.to_flat()
+        n = len(keys)
+        st = self.previous_state
+        try:
+            if st is None:
+                st = IntermediateStateRootState(RootStream(self.engine, retain_updates=True), 0, b"")
+            a0 = st.next_account
+            # the range: accounts a0 .. a1 holding >= threshold hashed entries (at least one account)
+            target = int(offs[a0]) + a0 + min(self.threshold, 2**62) if a0 < n else 0
+            entries = offs[a0:n + 1].astype(np.int64) + np.arange(a0, n + 1)      # entries before account i
+            a1 = min(n, max(a0 + 1, int(np.searchsorted(entries, target, side="left")))) if a0 < n else n
+            updates = TrieUpdates()
+            walked = 0
+            if a1 > a0:
+                s0, s1 = int(offs[a0]), int(offs[a1])
+                _, acct_recs, stor_recs = st.stream.push(keys[a0:a1], accts[a0:a1], skeys[s0:s1], svals[s0:s1],
+                                                         (offs[a0:a1 + 1] - offs[a0]).astype(np.uint64))
+                for _, path, sm, tm, hm, hashes in acct_recs:
+                    updates.account_nodes[bytes(path)] = BranchNodeCompact(sm, tm, hm, tuple(hashes))
+                per_trie = _records_to_nodes(stor_recs)
+                for i in range(a0, a1):
+                    addr = keys[i].tobytes()
+                    if offs[i + 1] == offs[i]:
+                        updates.insert_storage_updates(addr, StorageTrieUpdates.deleted())
+                    else:
+                        updates.insert_storage_updates(addr, StorageTrieUpdates(storage_nodes=per_trie.get(i - a0, {})))
+                walked = (a1 - a0) + (s1 - s0)
+                st.next_account = a1
+                st.last_hashed_key = keys[a1 - 1].tobytes()
+            if a1 < n:
+                return StateRootProgress(None, walked, updates, complete=False, state=st)
+            root, acct_recs = st.stream.finish()
+            st.stream.close()
+            for _, path, sm, tm, hm, hashes in acct_recs:
+                updates.account_nodes[bytes(path)] = BranchNodeCompact(sm, tm, hm, tuple(hashes))
+            self._finalize(updates)
+            return StateRootProgress(root, walked, updates)
+        except StateRootError:
+            raise
+        except Exception as e:  # noqa: BLE001
+            raise StateRootError(str(e)) from e
 
 
 class ParallelStateRoot(StateRoot):

@@ -335,6 +335,7 @@ cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); retur
 cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { if (n) memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new emuStream{0}; return cudaSuccess; }
 cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { *s = new emuStream{0}; return cudaSuccess; }
+cudaError_t cudaDeviceGetPCIBusId(char *b, int n, int) { if (n > 0) b[0] = 0; return cudaErrorInvalidValue; }
 cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { if (lo) *lo = 0; if (hi) *hi = -5; return cudaSuccess; }
 cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = new emuStream{0}; return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { if (s != cudaStreamLegacy) delete s; return cudaSuccess; }

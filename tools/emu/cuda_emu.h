@@ -226,6 +226,7 @@ cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *, unsigned);
 cudaError_t cudaStreamCreateWithPriority(cudaStream_t *, unsigned, int);
 cudaError_t cudaDeviceGetStreamPriorityRange(int *, int *);
+cudaError_t cudaDeviceGetPCIBusId(char *, int, int);
 cudaError_t cudaStreamCreate(cudaStream_t *);
 cudaError_t cudaStreamDestroy(cudaStream_t);
 cudaError_t cudaStreamSynchronize(cudaStream_t);
