@@ -261,6 +261,38 @@ B200_API int32_t b200_subtrie_frontier_dev(b200_ctx *, const void *d_acct_keys32
 B200_API int32_t b200_root_from_frontier(b200_ctx *, const b200_frontier_entry frontier[16], uint8_t root32[32]);
 B200_API int32_t b200_root_from_frontier_dev(b200_ctx *, const void *d_frontier, void *d_root32);
 
+/* ------------------------------------------------------------------------------------------------ changesets -> dirty set
+ * Incremental hashing of a block range in one call: what HashedPostStateSorted::from_reverts (crates/trie/db/src/state.rs:
+ * 289-347), load_prefix_sets_with_provider (crates/trie/db/src/prefix_set.rs:22-60) and insert_account_for_hashing /
+ * insert_storage_for_hashing (crates/storage/provider/src/providers/database/provider.rs:3206-3280) do with HashSets and
+ * sort_unstable: keccak every changed address and slot, keep the FIRST (oldest) changeset entry of every address and of every
+ * (address, slot) pair, sort.  Input: the account changeset addresses and the storage changeset (address, slot) rows of the
+ * range, in changeset order (block, address).  Output (page-locked, released with b200_changeset_hashes_release):
+ *   accounts  : unique keccak(address) ascending + index of the first entry of each (the caller picks AccountBeforeTx there)
+ *   storages  : unique (keccak(address), keccak(slot)) pairs as a CSR — addresses ascending, slot keys ascending inside a
+ *               segment, index of the first entry of each pair — i.e. HashedStorageSorted per address, and at the same
+ *               time the storage prefix sets (sorted, deduplicated changed keys; prefix_set.rs:165-177)
+ *   prefix set: the account prefix set — union of both address key sets, ascending, deduplicated.
+ * destroyed_accounts needs the HashedAccounts table (prefix_set.rs:40-42) and stays with the caller. */
+typedef struct {
+    uint64_t n_accounts;
+    uint8_t *account_keys32;
+    uint32_t *account_first;
+    uint64_t n_storage_accounts;
+    uint8_t *storage_account_keys32;
+    uint64_t *storage_seg_offsets; /* [n_storage_accounts + 1] */
+    uint64_t n_slots;
+    uint8_t *slot_keys32;
+    uint32_t *slot_first;
+    uint64_t n_prefix;
+    uint8_t *account_prefix_keys32;
+    void *_owner;
+} b200_changeset_hashes;
+B200_API int32_t b200_hash_changesets(b200_ctx *, const uint8_t *acct_addresses20, uint64_t n_acct_entries,
+                                      const uint8_t *storage_addresses20, const uint8_t *storage_slots32,
+                                      uint64_t n_storage_entries, b200_changeset_hashes *out);
+B200_API void b200_changeset_hashes_release(b200_changeset_hashes *);
+
 /* ------------------------------------------------------------------------------------------------ streamed / resumable root
  * StateRoot::with_threshold / root_with_progress / with_intermediate_state (crates/trie/trie/src/trie.rs:73-85,156-330;
  * progress.rs) and MerkleStage's chunked rebuild with its MerkleCheckpoint (crates/stages/stages/src/stages/merkle.rs:

@@ -87,6 +87,14 @@ class FrontierEntry(C.Structure):
 assert C.sizeof(FrontierEntry) == 68
 
 
+class ChangesetHashes(C.Structure):
+    _fields_ = [("n_accounts", C.c_uint64), ("account_keys32", C.POINTER(C.c_uint8)), ("account_first", C.POINTER(C.c_uint32)),
+                ("n_storage_accounts", C.c_uint64), ("storage_account_keys32", C.POINTER(C.c_uint8)),
+                ("storage_seg_offsets", C.POINTER(C.c_uint64)), ("n_slots", C.c_uint64), ("slot_keys32", C.POINTER(C.c_uint8)),
+                ("slot_first", C.POINTER(C.c_uint32)), ("n_prefix", C.c_uint64), ("account_prefix_keys32", C.POINTER(C.c_uint8)),
+                ("_owner", C.c_void_p)]
+
+
 class StreamProgress(C.Structure):
     _fields_ = [("accounts", C.c_uint64), ("slots", C.c_uint64), ("open_accounts", C.c_uint64), ("closed_buckets", C.c_uint32)]
 
@@ -159,6 +167,8 @@ def load():
     sig("b200_subtrie_frontier_dev", i32, vp, vp, vp, u64, vp, vp, vp, u64, vp)
     sig("b200_root_from_frontier", i32, vp, C.POINTER(FrontierEntry), vp)
     sig("b200_root_from_frontier_dev", i32, vp, vp, vp)
+    sig("b200_hash_changesets", i32, vp, vp, u64, vp, vp, u64, C.POINTER(ChangesetHashes))
+    sig("b200_changeset_hashes_release", None, C.POINTER(ChangesetHashes))
     sig("b200_root_stream_begin", i32, vp, i32, C.POINTER(vp))
     sig("b200_root_stream_push", i32, vp, vp, vp, u64, vp, vp, vp, PU, PU, C.POINTER(StreamProgress))
     sig("b200_root_stream_finish", i32, vp, vp, PU)

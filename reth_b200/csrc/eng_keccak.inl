@@ -83,7 +83,7 @@ extern "C" B200_API int32_t b200_keccak256_var(b200_ctx *c, const uint8_t *data,
 
 // ------------------------------------------------------------------------------------------------ hash + sort
 int32_t sort_digests_on_device(b200_ctx *c, const void *d_digests, uint64_t n, void *d_sorted, uint32_t *d_perm,
-                               DevBuf &keys_a, DevBuf &keys_b, DevBuf &idx_a, DevBuf &flag);
+                               DevBuf &keys_a, DevBuf &keys_b, DevBuf &idx_a, DevBuf &flag, bool allow_equal = false);
 
 // Device-resident: d_in -> d_sorted32 (n x 32), d_perm (n x u32).  Synchronises once (tie check).
 extern "C" B200_API int32_t b200_hash_sort_keys_dev(b200_ctx *c, const void *d_in, uint32_t msg_len, uint32_t stride,
@@ -132,7 +132,7 @@ extern "C" B200_API int32_t b200_hash_sort_keys(b200_ctx *c, const uint8_t *in, 
 
 int32_t sort_composite_on_device(b200_ctx *c, const void *d_ha, uint32_t n_addr, const uint32_t *d_addr_index,
                                  const void *d_hs, uint64_t n, void *d_sorted, uint32_t *d_perm, DevBuf &keys_a,
-                                 DevBuf &keys_b, DevBuf &idx_a, DevBuf &flag);
+                                 DevBuf &keys_b, DevBuf &idx_a, DevBuf &flag, bool allow_equal = false);
 
 // StorageHashingStage full pass: hash n_addr addresses once, n slot keys, sort entries by keccak(address) || keccak(slot).
 extern "C" B200_API int32_t b200_hash_sort_storage(b200_ctx *c, const uint8_t *addresses20, uint32_t n_addr,

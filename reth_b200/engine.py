@@ -166,6 +166,32 @@ class Engine:
                                                     _ptr(slots), n, _ptr(out), _ptr(perm)))
         return out, perm
 
+    def hash_changesets(self, acct_addresses, storage_addresses, storage_slots) -> dict:
+        """b200_hash_changesets: the account / storage changesets of a block range (addresses uint8[na,20]; rows
+        (address uint8[ns,20], slot uint8[ns,32]) in changeset order) -> the range's dirty set: unique hashed keys sorted,
+        the index of the first (oldest) entry of each, the storage CSR and the account prefix set."""
+        from ._lib import ChangesetHashes
+        a = _np(acct_addresses).reshape(-1, 20)
+        sa = _np(storage_addresses).reshape(-1, 20)
+        ss = _np(storage_slots).reshape(-1, 32)
+        if len(sa) != len(ss):
+            raise ValueError("storage changeset rows need one address and one slot each")
+        o = ChangesetHashes()
+        self._check(self.lib.b200_hash_changesets(self.ctx, _ptr(a), len(a), _ptr(sa), _ptr(ss), len(ss), C.byref(o)))
+        arr = lambda p, shape, n: np.ctypeslib.as_array(p, shape).copy() if n else np.zeros(shape, np.uint8 if len(shape) == 2 else None)
+        na, nsa, nl, npx = int(o.n_accounts), int(o.n_storage_accounts), int(o.n_slots), int(o.n_prefix)
+        res = {
+            "account_keys": arr(o.account_keys32, (na, 32), na),
+            "account_first": np.ctypeslib.as_array(o.account_first, (na,)).copy() if na else np.zeros(0, np.uint32),
+            "storage_account_keys": arr(o.storage_account_keys32, (nsa, 32), nsa),
+            "storage_seg_offsets": np.ctypeslib.as_array(o.storage_seg_offsets, (nsa + 1,)).copy(),
+            "slot_keys": arr(o.slot_keys32, (nl, 32), nl),
+            "slot_first": np.ctypeslib.as_array(o.slot_first, (nl,)).copy() if nl else np.zeros(0, np.uint32),
+            "account_prefix_keys": arr(o.account_prefix_keys32, (npx, 32), npx),
+        }
+        self.lib.b200_changeset_hashes_release(C.byref(o))
+        return res
+
     # device-resident (torch) variants ------------------------------------------------------------
     def keccak256_fixed_dev(self, t_in, msg_len: int, stride: int, n: int, t_out):
         self._check(self.lib.b200_keccak256_fixed_dev(self.ctx, t_in.data_ptr(), msg_len, stride, n, t_out.data_ptr()))

@@ -28,6 +28,10 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="accounts of the oracle's from-scratch fold timed as the CPU baseline (0 = skip)")
     ap.add_argument("--compare", action="store_true", help="also run every block through b200_trie_apply and compare roots")
     args = ap.parse_args()
+    T0 = time.perf_counter()
+
+    def note(msg):  # progress on stderr: where the wall time of a 100M-key run goes
+        print(f"[dtrie_bench {time.perf_counter() - T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
     import torch
     from bench import be_sort_key, random_keys_torch, splitmix64_torch
     from reth_b200 import ACCOUNT_DTYPE, DynamicTrie, Engine, ResidentTrie
@@ -47,6 +51,7 @@ def main():
     trie = DynamicTrie.create_dev(eng, keys.view(torch.uint8).view(-1), accts.view(-1), None, n)
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
+    note("dynamic trie created")
     ref = ResidentTrie.create_dev(eng, keys.view(torch.uint8).view(-1), accts.view(-1), None, n) if args.compare else None
     assert ref is None or trie.root() == ref.root()
     eng.set_stream(None)
@@ -58,7 +63,9 @@ def main():
     base_index = {}          # key -> row in the base arrays, for every key a block touched (the final undo block needs the base value)
     inserted_total = set()
     h_accts = accts.cpu().numpy().view(ACCOUNT_DTYPE).reshape(-1)
+    note("host copies ready")
     for b in range(args.blocks):
+        note(f"block {b}")
         n_upd, n_ins, n_del = m * pu // 100, m * pi // 100, m * pd // 100
         pick = rng.choice(len(live), n_upd + n_del, replace=False)
         upd_keys, del_keys = live[pick[:n_upd]], live[pick[n_upd:]]
@@ -93,6 +100,7 @@ def main():
         mask = np.ones(len(live), bool)
         mask[pick[n_upd:]] = False
         live = np.concatenate([live[mask], ins_keys])
+    note("blocks done")
     # ---- undo everything in one block: base values back, deleted base keys re-inserted, inserted keys deleted.  The root must
     # return to the root of the from-scratch build the trie was created from (independent of any model of the state).
     base_keys_np = keys.view(torch.uint8).view(n, 32).cpu().numpy()
@@ -122,7 +130,9 @@ def main():
     present = np.zeros(len(uk), np.uint8)
     for i, kb in enumerate(uk):
         present[i], da[i] = undo[kb]
+    note(f"undo block of {len(uk)} entries")
     undo_root = trie.apply(dk, da, present)
+    note("undo applied")
     undo_ok = bool(undo_root == base_root and len(trie) == n)
     cpu = None
     if args.cpu_sample:
