@@ -261,6 +261,27 @@ B200_API int32_t b200_subtrie_frontier_dev(b200_ctx *, const void *d_acct_keys32
 B200_API int32_t b200_root_from_frontier(b200_ctx *, const b200_frontier_entry frontier[16], uint8_t root32[32]);
 B200_API int32_t b200_root_from_frontier_dev(b200_ctx *, const void *d_frontier, void *d_root32);
 
+/* ------------------------------------------------------------------------------------------------ incremental root, trie not resident
+ * The fold of an incremental HashBuilder run over the element stream reth's TrieWalker + TrieNodeIter produce from the
+ * stored trie nodes and the prefix sets (crates/trie/trie/src/walker.rs:161-388, node_iter.rs:200-304; PrefixSet::contains,
+ * crates/trie/common/src/prefix_set.rs:205-231; StateRoot::calculate, trie.rs:247-309; StorageRoot::calculate, :659-698):
+ * item i is either a leaf (key_nibbles[i] == 64: HashBuilder::add_leaf) or the stored hash of an unchanged subtree
+ * (key_nibbles[i] = length of its path in nibbles, 0..63: HashBuilder::add_branch(path, hash, children_are_in_trie)).
+ *   keys32      : leaf key, or the path left-aligned (two nibbles per byte) and zero-padded; strictly ascending inside a
+ *                 trie and prefix-free (the walker never yields anything below a hash it yields)
+ *   item_flags  : bit 0 = children_are_in_trie of a hash item (sets the parent's tree-mask bit)
+ *   values      : rows of 72 bytes (account != 0: b200_account; storage_roots32 gives their storage roots, NULL = empty)
+ *                 or 32 bytes (U256 big-endian slot values, non-zero); a hash item's row starts with its 32-byte hash
+ *   seg_offsets : a forest of storage tries in one call (n_segs + 1 entries), or NULL for one trie (n_segs ignored)
+ * roots32: one root per trie (an empty segment gives EMPTY_ROOT_HASH; a lone hash at the empty path is returned as is).
+ * opt_updates: the branch nodes built by THIS fold that the tables must store (TrieUpdates::account_nodes /
+ * storage_nodes; trie_id = segment) — the removed_nodes of the walk are the walker's (every stored node it descended into
+ * and that is not among the updated ones, walker.rs:336-344). */
+B200_API int32_t b200_root_from_items(b200_ctx *, const uint8_t *keys32, const uint8_t *key_nibbles, const uint8_t *item_flags,
+                                      const uint8_t *values, const uint8_t *storage_roots32, const uint64_t *seg_offsets,
+                                      uint64_t n_segs, uint64_t n_items, int32_t account, uint8_t *roots32,
+                                      b200_updates *opt_updates, b200_stats *opt_stats);
+
 /* ------------------------------------------------------------------------------------------------ changesets -> dirty set
  * Incremental hashing of a block range in one call: what HashedPostStateSorted::from_reverts (crates/trie/db/src/state.rs:
  * 289-347), load_prefix_sets_with_provider (crates/trie/db/src/prefix_set.rs:22-60) and insert_account_for_hashing /

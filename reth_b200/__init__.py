@@ -15,3 +15,4 @@ from .sharded import ShardedDynamicStateRoot, sharded_ordered_trie_roots  # noqa
 from .verify import Verifier  # noqa: F401,E402
 from .ordered_root import (OrderedRootError, OrderedTrieRootEncodedBuilder, ordered_trie_root_encoded,  # noqa: F401,E402
                            ordered_trie_roots)
+from .walker import IncrementalStateRoot, TrieElement, walk  # noqa: F401,E402

@@ -167,6 +167,7 @@ def load():
     sig("b200_subtrie_frontier_dev", i32, vp, vp, vp, u64, vp, vp, vp, u64, vp)
     sig("b200_root_from_frontier", i32, vp, C.POINTER(FrontierEntry), vp)
     sig("b200_root_from_frontier_dev", i32, vp, vp, vp)
+    sig("b200_root_from_items", i32, vp, vp, vp, vp, vp, vp, vp, u64, u64, i32, vp, PU, PS)
     sig("b200_hash_changesets", i32, vp, vp, u64, vp, vp, u64, C.POINTER(ChangesetHashes))
     sig("b200_changeset_hashes_release", None, C.POINTER(ChangesetHashes))
     sig("b200_root_stream_begin", i32, vp, i32, C.POINTER(vp))

@@ -15,10 +15,12 @@ struct Built {
 
 // Builds every trie of a forest over d_keys (n leaves).  d_seg_offsets == nullptr: one trie.
 // account: leaves are accounts (d_values = b200_account[n], d_sroots = storage roots or null); else storage
-// slots (d_values = U256 BE [n][32]).  ordered != nullptr: leaves of index-keyed tries (eng_ordered.inl).
+// slots (d_values = U256 BE [n][32]).  ordered != nullptr: leaves of index-keyed tries (eng_ordered.inl); items != nullptr:
+// leaves mixed with stored hashes of unchanged subtrees (eng_items.inl).
 static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, const uint64_t *d_seg_offsets,
                             uint64_t n_segs, bool account, const uint8_t *d_values, const uint8_t *d_sroots,
-                            bool retain_updates, Built &out, const OrderedLeavesDev *ordered = nullptr) {
+                            bool retain_updates, Built &out, const OrderedLeavesDev *ordered = nullptr,
+                            const ItemLeavesDev *items = nullptr) {
     if (n >= (1ull << 31)) return fail(c, B200_ERR_INVALID_ARG, "at most 2^31-1 leaves per build");
     cudaStream_t st = c->stream;
     ForestDev &f = out.f;
@@ -60,6 +62,7 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
         CU(cudaStreamWaitEvent(sa, c->ev_fork, 0));
     }
     if (ordered) CU(launch_ordered_leaves(f, *ordered, st));  // index-keyed tries: variable-length keys and values
+    else if (items) CU(launch_item_leaves(f, *items, d_values, d_sroots, st));  // leaves + hashes of unchanged subtrees
     else CU(launch_leaves(f, account, d_values, d_sroots, st));
     c->launches++;
     phase_mark(c, account ? "lcp+leaves(acct)" : "lcp+leaves");

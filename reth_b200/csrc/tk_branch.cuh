@@ -55,7 +55,7 @@ __device__ __forceinline__ uint32_t encode_branch(Strip<BLOCK> &s, const ForestD
         payload += clen - 1;
         uint32_t bit = 1u << ci.nib;
         state_mask |= bit;
-        if (ci.id >= f.n) {
+        if (ci.id >= f.n || (ci.meta & META_ISNODE)) {
             if (!(ci.meta & META_EXT)) {
                 hash_mask |= bit;
                 if ((ci.meta & META_LEN) && f.retain_updates) atomicExch(f.err, B200_DEVERR_INLINE_HASH_CHILD);
@@ -148,7 +148,7 @@ __device__ __forceinline__ uint32_t encode_branch_u(Strip<BLOCK> &s, const Fores
             payload += ((meta & META_LEN) ? (meta & META_LEN) : 33u) - 1;
             uint32_t bit = 1u << (nm[c] & 15);
             state_mask |= bit;
-            if (id[c] >= n) {
+            if (id[c] >= n || (meta & META_ISNODE)) {
                 if (!(meta & META_EXT)) {
                     hash_mask |= bit;
                     if ((meta & META_LEN) && f.retain_updates) atomicExch(f.err, B200_DEVERR_INLINE_HASH_CHILD);

@@ -109,7 +109,8 @@ __global__ void gather_updates_kernel(ForestDev f, const uint32_t *__restrict__ 
         ChildInfo ci = fetch_child(f, j0, c);
         if (mk.z & (1u << ci.nib)) {
             uint32_t ref[8];
-            load32_nc(f.node_ref + 32 * (uint64_t)(ci.id - (uint32_t)f.n), ref);
+            // (a hash child is a node of this build or, in an items build, the stored hash of an unchanged subtree)
+            load32_nc(ci.id < f.n ? f.leaf_ref + 32 * (uint64_t)ci.id : f.node_ref + 32 * (uint64_t)(ci.id - (uint32_t)f.n), ref);
             store32(out.hashes + 32 * (uint64_t)ho, ref);
             ho++;
         }

@@ -188,7 +188,7 @@ __device__ __forceinline__ void warp_build_node(const ForestDev &f, uint32_t v, 
     }
     uint32_t clen = has ? ((ci.meta & META_LEN) ? (ci.meta & META_LEN) : 33u) : 0u;
     uint32_t bit = has ? (1u << ci.nib) : 0u;
-    bool is_branch = has && ci.id >= n;
+    bool is_branch = has && (ci.id >= n || (ci.meta & META_ISNODE));
     uint32_t hbit = (is_branch && !(ci.meta & META_EXT)) ? bit : 0u;
     uint32_t tbit = (is_branch && (ci.meta & META_STORED)) ? bit : 0u;
     if (hbit && (ci.meta & META_LEN) && f.retain_updates) atomicExch(f.err, B200_DEVERR_INLINE_HASH_CHILD);

@@ -33,6 +33,7 @@ namespace b200 {
 #include "tk_frontier.cuh"
 #include "tk_launchers.cuh"
 #include "tk_ordered.cuh"
+#include "tk_items.cuh"
 #include "tk_dtrie.cuh"
 #include "tk_dstate.cuh"
 #include "tk_proofs.cuh"

@@ -18,7 +18,9 @@ enum : int {
 };
 
 // node / leaf meta byte
-enum : uint32_t { META_LEN = 31u, META_EXT = 32u, META_STORED = 64u };
+// META_ISNODE (leaf_meta only): the position holds the hash of a whole unchanged subtree (HashBuilder::add_branch,
+// tk_items.cuh), which its parent treats like a branch child (hash / tree mask bits)
+enum : uint32_t { META_LEN = 31u, META_EXT = 32u, META_STORED = 64u, META_ISNODE = 128u };
 
 enum : int { CNT_HASHED = 0, CNT_EXT = 1, CNT_COUNT = 4 };
 
@@ -153,6 +155,17 @@ cudaError_t launch_ordered_keys(const uint64_t *d_seg_offsets, uint64_t n_segs, 
                                 uint8_t *keys, uint8_t *key_nibs, uint32_t *item, uint16_t *sched_key, uint32_t *pos, int *err,
                                 cudaStream_t st);
 cudaError_t launch_ordered_leaves(const ForestDev &f, const OrderedLeavesDev &o, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------ mixed items (tk_items.cuh)
+// The input stream of an incremental HashBuilder run (TrieNodeIter, crates/trie/trie/src/node_iter.rs:200-304): changed /
+// uncovered leaves and the stored hashes of unchanged subtrees, in key order.
+struct ItemLeavesDev {
+    const uint8_t *key_nibs;  // [n] 64 = a leaf; 0..63 = hash of the subtree rooted at the path of that many nibbles
+    const uint8_t *flags;     // [n] bit 0: the subtree's nodes are in the trie tables (children_are_in_trie -> tree mask)
+    int account;              // leaf values: b200_account (72-byte rows) | U256 BE (32-byte rows); hashes: first 32 bytes of the row
+};
+cudaError_t launch_item_leaves(const ForestDev &f, const ItemLeavesDev &it, const uint8_t *values, const uint8_t *storage_roots,
+                               cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------ dynamic trie (tk_dtrie.cuh)
 constexpr uint32_t DT_NONE = 0xFFFFFFFFu;

@@ -166,6 +166,31 @@ class Engine:
                                                     _ptr(slots), n, _ptr(out), _ptr(perm)))
         return out, perm
 
+    def root_from_items(self, keys, key_nibbles, item_flags, values, storage_roots32, seg_offsets, account: bool,
+                        want_updates: bool = False):
+        """b200_root_from_items: the fold of an incremental run over leaves (key_nibbles == 64) and stored hashes of unchanged
+        subtrees (key_nibbles = path length).  -> roots uint8[tries, 32] [, records]."""
+        keys = _np(keys).reshape(-1, 32)
+        n = len(keys)
+        key_nibbles, item_flags = _np(key_nibbles), _np(item_flags)
+        values = _np(values).reshape(n, 72 if account else 32)
+        sr = None if storage_roots32 is None else _np(storage_roots32).reshape(n, 32)
+        so = None if seg_offsets is None else _np(seg_offsets, np.uint64)
+        if len(key_nibbles) != n or len(item_flags) != n:
+            raise ValueError("one key_nibbles / item_flags entry per item")
+        if so is not None and (int(so[0]) != 0 or int(so[-1]) != n):
+            raise ValueError("seg_offsets must start at 0 and end at the number of items")
+        tries = 1 if so is None else len(so) - 1
+        roots = np.empty((max(tries, 1), 32), np.uint8)
+        u, s = Updates(), Stats()
+        self._check(self.lib.b200_root_from_items(self.ctx, _ptr(keys), _ptr(key_nibbles), _ptr(item_flags), _ptr(values), _ptr(sr),
+                                                  _ptr(so), tries if so is not None else 0, n, 1 if account else 0, _ptr(roots),
+                                                  C.byref(u) if want_updates else None, C.byref(s)))
+        roots = roots[:tries]
+        if want_updates:
+            return roots, updates_to_records(u, self.lib)
+        return roots
+
     def hash_changesets(self, acct_addresses, storage_addresses, storage_slots) -> dict:
         """b200_hash_changesets: the account / storage changesets of a block range (addresses uint8[na,20]; rows
         (address uint8[ns,20], slot uint8[ns,32]) in changeset order) -> the range's dirty set: unique hashed keys sorted,
