@@ -386,6 +386,16 @@ def main():
         dist.all_reduce(warm)
         torch.cuda.synchronize()
     eng = Engine(local_rank)
+    comm = None
+    if world > 1:
+        # the library's own communicator (b200_comm_*): the frontier all-gather runs inside b200_state_root_sharded_dev on the
+        # engine's stream; torch.distributed only carries the 128-byte NCCL id and the max-over-ranks of the timings
+        from reth_b200 import Comm
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        comm = Comm(eng, bytes(uid.cpu().numpy()), world, rank)
     # a dedicated (non-default) stream: torch events, NCCL and the engine's kernels are all ordered on it
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -458,11 +468,15 @@ def main():
     # ---------------------------------------------------------------- C3: state root
     state_root = None
     if not args.skip_state_root:
-        state_root = bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks, sm_mhz)
+        state_root = bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks, sm_mhz, comm)
 
     c4 = None
     if (args.c4 or world > 1) and not args.skip_c4:
-        c4 = bench_c4(args, eng, dev, rank, world, barrier, max_over_ranks)
+        c4 = bench_c4(args, eng, dev, rank, world, barrier, max_over_ranks, comm)
+
+    hash_part = None
+    if comm is not None and not args.skip_state_root:
+        hash_part = bench_hash_partition(args, eng, comm, dev, rank, world, barrier, max_over_ranks)
 
     incremental = None
     if not args.skip_incremental and world == 1:
@@ -485,17 +499,20 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": c2_config(n, world),
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
-            "cpu_baseline": cpu, "state_root": state_root, "mainnet_shape": c4, "incremental": incremental,
+            "cpu_baseline": cpu, "state_root": state_root, "mainnet_shape": c4, "hash_partition": hash_part,
+            "incremental": incremental,
             "parity_spot_check": parity_ok,
         }
         if dynamic is not None:
             line["dynamic"] = dynamic
         emit(line)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks, sm_mhz=None):
+def bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks, sm_mhz=None, comm=None):
     import torch
     import torch.distributed as dist
     n_acc = args.accounts
@@ -513,14 +530,8 @@ def bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks, sm_mh
             eng.state_root_full_dev(sh["akeys"], sh["accts"], n_acc, sh["skeys"], sh["svals"], sh["offs"],
                                     sh["n_slots"], d_root)
         else:
-            eng.subtrie_frontier_dev(sh["akeys"], sh["accts"], n_acc, sh["skeys"], sh["svals"], sh["offs"],
-                                     sh["n_slots"], d_front)
-            dist.all_gather(gathered, d_front)  # 16 x 68 B per rank: the one collective of the path
-            merged = torch.stack(gathered).view(world, 16, 68)
-            pick = torch.arange(16, device=dev) * world // 16  # owner rank of each top nibble
-            front = merged[pick, torch.arange(16, device=dev)].contiguous().view(-1)
-            eng.root_from_frontier_dev(front, d_root)
-            step.front = front  # keep alive until the stream has consumed it
+            # frontier -> ncclAllGather (16 x 68 B per rank: the one collective of the path) -> root, one C call
+            comm.state_root_sharded_dev(sh["akeys"], sh["accts"], n_acc, sh["skeys"], sh["svals"], sh["offs"], sh["n_slots"], d_root)
 
     for _ in range(max(2, args.warmup - 1)):
         step()
@@ -542,7 +553,8 @@ def bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks, sm_mh
            "config": {"workload": f"C3: StateRoot over {n_acc} accounts x {C3_SLOTS} storage slots per GPU, "
                                   "level-by-level node-hash frontier", "leaves_per_gpu": leaves,
                       "parallelism": "single GPU" if world == 1 else
-                      f"accounts sharded by top key nibble over {world} GPUs, one NCCL all-gather of 16 frontier entries"},
+                      f"accounts sharded by top key nibble over {world} GPUs, one ncclAllGather of 16 frontier entries inside "
+                      "b200_state_root_sharded_dev"},
            "root": bytes(d_root.cpu().numpy()).hex(),
            "node_digests_per_sec": world * stats["hashed_nodes"] / (ms * 1e-3) if world == 1 else None,
            "stats": stats,
@@ -573,6 +585,37 @@ def bench_state_root(args, eng, dev, rank, world, barrier, max_over_ranks, sm_mh
                       "root_matches_device_run": root.hex() == res["root"],
                       "api": "b200_state_root_full (host pointers, page-locked)"}
     return res
+
+
+def bench_hash_partition(args, eng, comm, dev, rank, world, barrier, max_over_ranks):
+    """AccountHashing at N > 1: every rank holds an arbitrary slice of the plain table (20-byte addresses with a
+    72-byte account row each); b200_hash_partition_dev hashes, all-to-alls (digest, row) by owner rank over NVLink and sorts."""
+    import torch
+    n = args.keys // 2
+    t_in = random_keys_torch(11 + 1000 * rank, n, dev).view(torch.uint8).view(n, 32)[:, :20].contiguous().view(-1)
+    t_val = splitmix64_torch(13 + 1000 * rank, 9 * n, dev).view(torch.uint8).view(-1)
+    cap = n + n // 2 + 1024
+    t_k = torch.empty(cap * 32, dtype=torch.uint8, device=dev)
+    t_v = torch.empty(cap * 72, dtype=torch.uint8, device=dev)
+    got = 0
+    for _ in range(2):
+        got = comm.hash_partition_dev(t_in, 20, 20, n, t_val, 72, cap, t_k, t_v)
+    barrier()
+    steps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        got = comm.hash_partition_dev(t_in, 20, 20, n, t_val, 72, cap, t_k, t_v)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    k = t_k.view(cap, 32)[:got]
+    pre = be_sort_key(k.contiguous().view(torch.int64).view(got, 4))
+    ok = bool((pre[1:] >= pre[:-1]).all().item()) and bool(((k[:, 0] >> 4).to(torch.int64) * world // 16 == rank).all().item())
+    return {"metric": "hash_partition_keys_per_sec", "value": world * n / (ms * 1e-3), "unit": "keys/s", "ms_per_step": ms,
+            "keys_per_gpu": n, "row_bytes": 72, "rows_received_rank0": got, "sorted_and_owned_rank0": ok,
+            "exchange_bytes_per_gpu": int(n * (world - 1) / world * (32 + 72)),
+            "config": {"workload": f"{n} addresses + 72-byte rows per GPU: keccak, all-to-all by top nibble over {world} GPUs, sort"}}
 
 
 def make_c4_shard(seed: int, leaves: int, nibble_lo: int, nibble_hi: int, device):
@@ -622,7 +665,7 @@ def make_c4_shard(seed: int, leaves: int, nibble_lo: int, nibble_hi: int, device
                 contracts=n_contracts)
 
 
-def bench_c4(args, eng, dev, rank, world, barrier, max_over_ranks):
+def bench_c4(args, eng, dev, rank, world, barrier, max_over_ranks, comm=None):
     """BASELINE config 4: MerkleExecute-style full build of a mainnet-shaped state, subtries sharded over the GPUs."""
     import torch
     import torch.distributed as dist
@@ -637,12 +680,7 @@ def bench_c4(args, eng, dev, rank, world, barrier, max_over_ranks):
         if world == 1:
             eng.state_root_full_dev(sh["akeys"], sh["accts"], n_acc, sh["skeys"], sh["svals"], sh["offs"], sh["n_slots"], d_root)
         else:
-            eng.subtrie_frontier_dev(sh["akeys"], sh["accts"], n_acc, sh["skeys"], sh["svals"], sh["offs"], sh["n_slots"], d_front)
-            dist.all_gather(gathered, d_front)
-            merged = torch.stack(gathered).view(world, 16, 68)
-            pick = torch.arange(16, device=dev) * world // 16
-            step.front = merged[pick, torch.arange(16, device=dev)].contiguous().view(-1)
-            eng.root_from_frontier_dev(step.front, d_root)
+            comm.state_root_sharded_dev(sh["akeys"], sh["accts"], n_acc, sh["skeys"], sh["svals"], sh["offs"], sh["n_slots"], d_root)
 
     for _ in range(2):
         step()

@@ -351,6 +351,37 @@ B200_API int32_t b200_root_stream_checkpoint(const b200_root_stream *, b200_stre
 B200_API int32_t b200_root_stream_resume(b200_ctx *, const b200_stream_checkpoint *, b200_root_stream **out);
 B200_API void b200_root_stream_free(b200_root_stream *);
 
+/* Communicator: the two exchange steps of the path behind the C ABI (SURVEY.md §8b `b200_create(device, n_devices)`, §8e).
+ * One process (or thread) per GPU, each with its own b200_ctx; rank 0 makes the id (b200_comm_unique_id = ncclGetUniqueId),
+ * the host ships its 128 bytes to the other ranks over whatever channel it has, every rank calls b200_comm_create
+ * (ncclCommInitRank: collective, blocks until all ranks joined).  NCCL is loaded at run time (libnccl.so.2; B200_NCCL_LIB
+ * overrides), so a host that never creates a communicator needs no NCCL.  At most 16 ranks (one top-nibble bucket each). */
+#define B200_COMM_ID_BYTES 128
+typedef struct b200_comm b200_comm;
+B200_API int32_t b200_comm_unique_id(uint8_t id[B200_COMM_ID_BYTES]);
+B200_API int32_t b200_comm_create(b200_ctx *, const uint8_t id[B200_COMM_ID_BYTES], int32_t n_ranks, int32_t rank, b200_comm **out);
+B200_API void b200_comm_destroy(b200_comm *);
+B200_API int32_t b200_comm_rank(const b200_comm *);
+B200_API int32_t b200_comm_size(const b200_comm *);
+/* b200_subtrie_frontier -> ncclAllGather of the 16 x 68-byte frontier -> b200_root_from_frontier in ONE call on the ctx
+ * stream: every rank passes its own shard (whole top-nibble buckets, any subset) and receives the state root.  The _dev form
+ * takes device pointers and returns without synchronising (d_root32: device). */
+B200_API int32_t b200_state_root_sharded(b200_comm *, const uint8_t *acct_keys32, const b200_account *accts, uint64_t n_accounts,
+                                         const uint8_t *slot_keys32, const uint8_t *values32_be, const uint64_t *seg_offsets,
+                                         uint8_t root32[32], b200_stats *opt_stats);
+B200_API int32_t b200_state_root_sharded_dev(b200_comm *, const void *d_acct_keys32, const void *d_accts, uint64_t n_accounts,
+                                             const void *d_slot_keys32, const void *d_values32_be, const void *d_seg_offsets,
+                                             uint64_t n_slots, void *d_root32);
+/* AccountHashingStage / StorageHashingStage at N > 1 (hashing_account.rs:176-238, hashing_storage.rs:106-178; SURVEY.md §8e
+ * last sentence): every rank holds an arbitrary slice of the plain table — n messages (msg_len 20 | 32) with one
+ * value_bytes-wide row each (the account, the slot value; may be 0).  One call hashes them, sends every (digest, row) to the
+ * rank that owns the digest's top nibble (rank = nibble * n_ranks / 16; one grouped all-to-all over NVLink) and sorts what
+ * arrives by digest: the rank's shard of HashedAccounts in table order, ready for b200_state_root_sharded.  Device pointers;
+ * the outputs hold `capacity` rows, *n_out receives the rows this rank owns (error if it exceeds capacity). Synchronises. */
+B200_API int32_t b200_hash_partition_dev(b200_comm *, const void *d_in, uint32_t msg_len, uint32_t stride, uint64_t n,
+                                         const void *d_values, uint32_t value_bytes, uint64_t capacity, void *d_sorted_keys32,
+                                         void *d_sorted_values, uint64_t *n_out);
+
 /* ------------------------------------------------------------------------------------------------ ordered roots
  * Transactions / receipts / withdrawals roots of a batch of lists in one call: what
  * OrderedTrieRootEncodedBuilder::finalize (crates/trie/common/src/ordered_root.rs:240-257) and alloy's
@@ -497,6 +528,15 @@ typedef struct {
 B200_API int32_t b200_dstate_account_proofs(b200_dstate *, const uint8_t *acct_keys32, uint64_t n, b200_proofs *out);
 B200_API int32_t b200_dstate_storage_proofs(b200_dstate *, const uint8_t *acct_key32, const uint8_t *slot_keys32, uint64_t n,
                                             uint8_t storage_root32[32] /* nullable */, b200_proofs *out);
+/* Multiproof batch (Proof::multiproof over MultiProofTargets, crates/trie/trie/src/proof/mod.rs:143-193; the unit of work of
+ * the proof workers in crates/trie/parallel/src/proof_task.rs): n target accounts, account i with the hashed slot targets
+ * slot_seg_offsets[i] .. slot_seg_offsets[i+1] of slot_keys32.  One call returns the account proofs (target i = account i),
+ * storage_roots32[i] (EMPTY_ROOT_HASH for an absent account) and the proofs of all slot targets (target j = slot j; an
+ * absent account's slots prove with the single node 0x80).  MultiProof::account_subtree = { key[..node_depth] -> rlp } over
+ * account_proofs; StorageMultiProof{root, subtree} per account the same over its slot targets. */
+B200_API int32_t b200_dstate_multiproof(b200_dstate *, const uint8_t *acct_keys32, uint64_t n_accounts,
+                                        const uint64_t *slot_seg_offsets, const uint8_t *slot_keys32, b200_proofs *account_proofs,
+                                        uint8_t *storage_roots32, b200_proofs *storage_proofs);
 B200_API void b200_proofs_release(b200_proofs *);
 /* b200_dstate_apply with the block already in device memory (every input pointer and d_root32 are device pointers;
  * n_entries = d_seg_offsets[m]); the update records, if wanted, still arrive in host memory. */

@@ -4,7 +4,7 @@ The product is libb200trie.so (hand-written sm_100a CUDA behind the C ABI of inc
 package is the host-side mirror of the reference interface used by tests and benchmarks.
 """
 from ._lib import B200Error, LIB_PATH  # noqa: F401
-from .engine import ACCOUNT_DTYPE, EMPTY_ROOT_HASH, KECCAK_EMPTY, DynamicState, DynamicTrie, Engine, ResidentTrie, RootStream, numa_bind_thread  # noqa: F401
+from .engine import ACCOUNT_DTYPE, EMPTY_ROOT_HASH, KECCAK_EMPTY, DynamicState, DynamicTrie, Comm, Engine, ResidentTrie, RootStream, numa_bind_thread  # noqa: F401
 from .hashed_state import (Account, HashedPostState, HashedPostStateSorted, HashedStorage,  # noqa: F401,E402
                            HashedStorageSorted, KeccakKeyHasher, PrefixSet, PrefixSetMut, TriePrefixSets,
                            TriePrefixSetsMut, unpack_nibbles)

@@ -167,6 +167,14 @@ def load():
     sig("b200_subtrie_frontier_dev", i32, vp, vp, vp, u64, vp, vp, vp, u64, vp)
     sig("b200_root_from_frontier", i32, vp, C.POINTER(FrontierEntry), vp)
     sig("b200_root_from_frontier_dev", i32, vp, vp, vp)
+    sig("b200_comm_unique_id", i32, vp)
+    sig("b200_comm_create", i32, vp, vp, i32, i32, C.POINTER(vp))
+    sig("b200_comm_destroy", None, vp)
+    sig("b200_comm_rank", i32, vp)
+    sig("b200_comm_size", i32, vp)
+    sig("b200_state_root_sharded", i32, vp, vp, vp, u64, vp, vp, vp, vp, PS)
+    sig("b200_state_root_sharded_dev", i32, vp, vp, vp, u64, vp, vp, vp, u64, vp)
+    sig("b200_hash_partition_dev", i32, vp, vp, C.c_uint32, C.c_uint32, u64, vp, C.c_uint32, u64, vp, vp, C.POINTER(C.c_uint64))
     sig("b200_root_from_items", i32, vp, vp, vp, vp, vp, vp, vp, u64, u64, i32, vp, PU, PS)
     sig("b200_hash_changesets", i32, vp, vp, u64, vp, vp, u64, C.POINTER(ChangesetHashes))
     sig("b200_changeset_hashes_release", None, C.POINTER(ChangesetHashes))
@@ -200,6 +208,7 @@ def load():
     sig("b200_dstate_apply", i32, vp, vp, vp, vp, u64, vp, vp, vp, vp, PU, PU, PU, PU, vp, PS)
     sig("b200_dstate_account_proofs", i32, vp, vp, u64, C.POINTER(Proofs))
     sig("b200_dstate_storage_proofs", i32, vp, vp, vp, u64, vp, C.POINTER(Proofs))
+    sig("b200_dstate_multiproof", i32, vp, vp, u64, vp, vp, C.POINTER(Proofs), vp, C.POINTER(Proofs))
     sig("b200_proofs_release", None, C.POINTER(Proofs))
     sig("b200_dstate_apply_dev", i32, vp, vp, vp, vp, u64, vp, vp, vp, u64, vp, PU, PU, PU, PU, vp, PS)
     sig("b200_dstate_root", i32, vp, vp)

@@ -136,3 +136,51 @@ extern "C" B200_API int32_t b200_dstate_storage_proofs(b200_dstate *t, const uin
     return r;
 }
 
+
+// Multiproof batch (Proof::multiproof over MultiProofTargets, crates/trie/trie/src/proof/mod.rs:143-193; the unit of work of
+// the proof workers, crates/trie/parallel/src/proof_task.rs): n target accounts, account i with the slot targets
+// slot_seg_offsets[i] .. [i+1].  One call: the account proofs, every account's storage root, and the proofs of all slot
+// targets of all accounts (one pass over the storage forest).  Every proof node carries its depth, so
+// MultiProof::account_subtree is { target[..node_depth] -> rlp } over account_proofs and StorageMultiProof::subtree the same
+// over the slot targets of one account.
+extern "C" B200_API int32_t b200_dstate_multiproof(b200_dstate *t, const uint8_t *acct_keys32, uint64_t n_accounts,
+                                                   const uint64_t *slot_seg_offsets, const uint8_t *slot_keys32,
+                                                   b200_proofs *account_proofs, uint8_t *storage_roots32, b200_proofs *storage_proofs) {
+    if (!t || !account_proofs || !storage_proofs || !slot_seg_offsets || (n_accounts && (!acct_keys32 || !storage_roots32)))
+        return fail(t ? t->c : nullptr, B200_ERR_INVALID_ARG, "bad argument");
+    b200_ctx *c = t->c;
+    memset(account_proofs, 0, sizeof *account_proofs);
+    memset(storage_proofs, 0, sizeof *storage_proofs);
+    if (t->sharded) return fail(c, B200_ERR_INVALID_ARG, "proofs of a sharded state start at the virtual root branch: not supported");
+    TRY(check_offsets_host(c, slot_seg_offsets, n_accounts));
+    const uint64_t m = slot_seg_offsets[n_accounts];
+    if (m && !slot_keys32) return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    if (n_accounts >= (1ull << 24) || m >= (1ull << 24)) return fail(c, B200_ERR_INVALID_ARG, "at most 2^24-1 proof targets per call");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    TRY(reset_build_state(c));
+    TRY(h2d_into(&t->acc, t->in_akeys, acct_keys32, n_accounts * 32));
+    TRY(h2d_into(&t->sto, t->in_skeys, slot_keys32, m * 32));
+    TRY(h2d_into(&t->acc, t->in_offs, slot_seg_offsets, (n_accounts + 1) * 8));
+    int32_t r = da_proofs(&t->acc, nullptr, static_cast<const uint8_t *>(t->in_akeys.p), n_accounts, account_proofs);
+    if (r == B200_OK) {
+        // leaf (= storage trie id) and storage root of every target account, then the trie of every slot target
+        TRY(da_scratch(&t->acc, t->trie_of_key, (n_accounts + m + 1) * 4));
+        TRY(da_scratch(&t->acc, t->in_svals, (n_accounts ? n_accounts : 1) * 32));
+        uint32_t *d_leaf = static_cast<uint32_t *>(t->trie_of_key.p), *d_tries = d_leaf + n_accounts;
+        DTrieDev da = da_view(&t->acc);
+        CU(launch_dt_find_leaves(da, static_cast<const uint8_t *>(t->in_akeys.p), n_accounts, d_leaf, static_cast<uint8_t *>(t->in_svals.p), st));
+        CU(launch_dt_target_tries(static_cast<const uint64_t *>(t->in_offs.p), n_accounts, d_leaf, m, d_tries, st));
+        c->launches += 2;
+        if (n_accounts) CU(cudaMemcpyAsync(storage_roots32, t->in_svals.p, n_accounts * 32, cudaMemcpyDeviceToHost, st));
+        t->sto.top_out = static_cast<uint8_t *>(t->acc.lsroot.p);
+        t->sto.top_stride = 32;
+        r = da_proofs(&t->sto, d_tries, static_cast<const uint8_t *>(t->in_skeys.p), m, storage_proofs);
+    }
+    if (r != B200_OK) {
+        b200_proofs_release(account_proofs);
+        b200_proofs_release(storage_proofs);
+    }
+    return r;
+}

@@ -298,3 +298,4 @@ extern "C" B200_API uint64_t b200_launch_count(const b200_ctx *c) { return c ? c
 #include "eng_proofs.inl"
 #include "eng_ordered.inl"
 #include "eng_items.inl"
+#include "eng_comm.inl"

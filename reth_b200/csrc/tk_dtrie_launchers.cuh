@@ -148,6 +148,15 @@ cudaError_t launch_dt_proof_write(const DTrieDev &t, const uint32_t *trie_of_tar
     if (n) dt_proof_write_kernel<<<blocks_for(n, 64), 64, 0, st>>>(t, trie_of_target, keys, n, node_base, byte_base, rlp, rlp_offset, node_depth);
     return cudaGetLastError();
 }
+cudaError_t launch_dt_find_leaves(const DTrieDev &t, const uint8_t *keys, uint64_t n, uint32_t *leaf_out, uint8_t *sroot_out, cudaStream_t st) {
+    if (n) dt_find_leaves_kernel<<<blocks_for(n, 128), 128, 0, st>>>(t, keys, n, leaf_out, sroot_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_dt_target_tries(const uint64_t *seg_offsets, uint64_t n_accounts, const uint32_t *leaf_of, uint64_t n_targets,
+                                   uint32_t *trie_of_target, cudaStream_t st) {
+    if (n_targets) dt_target_tries_kernel<<<blocks_for(n_targets, 256), 256, 0, st>>>(seg_offsets, n_accounts, leaf_of, n_targets, trie_of_target);
+    return cudaGetLastError();
+}
 cudaError_t launch_dt_find_leaf(const DTrieDev &t, const uint8_t *key, uint32_t *out, uint64_t n_copies, cudaStream_t st) {
     if (n_copies) dt_find_leaf_kernel<<<blocks_for(n_copies, 128), 128, 0, st>>>(t, key, out, n_copies);
     return cudaGetLastError();

@@ -111,3 +111,62 @@ __global__ void nibble_buckets_kernel(const uint8_t *__restrict__ keys, uint64_t
     }
     offs[b] = lo;
 }
+
+// Multi-GPU: out[i] = the one non-empty entry of nibble i among the gathered frontiers of all ranks (rank r's 16 entries at
+// all[16 * r ..]); two ranks claiming the same nibble is an input error (a rank owns whole top-nibble buckets).
+__global__ void merge_frontiers_kernel(const FrontierEntryDev *__restrict__ all, int world, FrontierEntryDev *__restrict__ out,
+                                       int *__restrict__ err) {
+    int i = threadIdx.x;
+    if (i >= 16) return;
+    FrontierEntryDev e;
+    e.as_child_len = 0;
+    e.as_root_len = 0;
+    int owners = 0;
+    for (int r = 0; r < world; r++) {
+        const FrontierEntryDev &c = all[16 * r + i];
+        if (c.as_child_len || c.as_root_len) {
+            if (!owners) e = c;
+            owners++;
+        }
+    }
+    if (owners > 1) atomicExch(err, B200_DEVERR_BAD_OFFSETS);
+    if (!owners)
+        for (int b = 0; b < 33; b++) e.as_child[b] = e.as_root[b] = 0;
+    out[i] = e;
+}
+
+// Hash-partition (AccountHashing / StorageHashing at N > 1): owner rank of every digest by top nibble, histogram per rank
+__global__ void partition_owner_kernel(const uint8_t *__restrict__ digests, uint64_t n, int world, uint8_t *__restrict__ owner,
+                                       unsigned long long *__restrict__ counts) {
+    __shared__ unsigned int sh[16];
+    if (threadIdx.x < 16) sh[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        uint32_t r = (uint32_t)(digests[32 * i] >> 4) * (uint32_t)world / 16u;
+        owner[i] = (uint8_t)r;
+        atomicAdd(&sh[r], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+// rows (digest 32 B, value vb B) gathered in destination order
+__global__ void partition_gather_kernel(const uint8_t *__restrict__ digests, const uint8_t *__restrict__ values, uint32_t vb,
+                                        const uint32_t *__restrict__ perm, uint64_t n, uint8_t *__restrict__ out_d,
+                                        uint8_t *__restrict__ out_v) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s = perm[i];
+    const uint4 *q = reinterpret_cast<const uint4 *>(digests + 32 * s);
+    uint4 *o = reinterpret_cast<uint4 *>(out_d + 32 * i);
+    o[0] = q[0];
+    o[1] = q[1];
+    for (uint32_t b = 0; b < vb; b++) out_v[(uint64_t)vb * i + b] = values[(uint64_t)vb * s + b];
+}
+__global__ void gather_values_kernel(const uint8_t *__restrict__ values, uint32_t vb, const uint32_t *__restrict__ perm, uint64_t n,
+                                     uint8_t *__restrict__ out_v) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s = perm[i];
+    for (uint32_t b = 0; b < vb; b++) out_v[(uint64_t)vb * i + b] = values[(uint64_t)vb * s + b];
+}

@@ -213,6 +213,24 @@ cudaError_t launch_frontier(const ForestDev &f, const uint64_t *bucket_offsets, 
     k<<<1, B, smem, st>>>(f, bucket_offsets, values, storage_roots, out);
     return cudaGetLastError();
 }
+cudaError_t launch_merge_frontiers(const FrontierEntryDev *all, int world, FrontierEntryDev *out, int *err, cudaStream_t st) {
+    merge_frontiers_kernel<<<1, 32, 0, st>>>(all, world, out, err);
+    return cudaGetLastError();
+}
+cudaError_t launch_partition_owner(const uint8_t *digests, uint64_t n, int world, uint8_t *owner, unsigned long long *counts,
+                                   cudaStream_t st) {
+    if (n) partition_owner_kernel<<<blocks_for(n, 256), 256, 0, st>>>(digests, n, world, owner, counts);
+    return cudaGetLastError();
+}
+cudaError_t launch_partition_gather(const uint8_t *digests, const uint8_t *values, uint32_t vb, const uint32_t *perm, uint64_t n,
+                                    uint8_t *out_d, uint8_t *out_v, cudaStream_t st) {
+    if (n) partition_gather_kernel<<<blocks_for(n, 256), 256, 0, st>>>(digests, values, vb, perm, n, out_d, out_v);
+    return cudaGetLastError();
+}
+cudaError_t launch_gather_values(const uint8_t *values, uint32_t vb, const uint32_t *perm, uint64_t n, uint8_t *out_v, cudaStream_t st) {
+    if (n && vb) gather_values_kernel<<<blocks_for(n, 256), 256, 0, st>>>(values, vb, perm, n, out_v);
+    return cudaGetLastError();
+}
 cudaError_t launch_root_from_frontier(const FrontierEntryDev *fr, uint8_t *root, cudaStream_t st) {
     constexpr int B = 32;
     auto k = root_from_frontier_kernel<B>;

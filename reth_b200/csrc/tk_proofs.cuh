@@ -205,3 +205,31 @@ __global__ void dt_find_leaf_kernel(DTrieDev t, const uint8_t *__restrict__ key,
     out[i] = loc.found ? (loc.child & ~DT_LEAF) : DT_NONE;
 }
 
+
+// ---- multiproof batch (MultiProofTargets: accounts with their slot targets)
+// leaf_out[i] = the account leaf (= storage trie id) of account key i, DT_NONE when the account does not exist; its storage
+// root goes to sroot_out (EMPTY_ROOT_HASH for a missing account)
+__global__ void dt_find_leaves_kernel(DTrieDev t, const uint8_t *__restrict__ keys, uint64_t n, uint32_t *__restrict__ leaf_out,
+                                      uint8_t *__restrict__ sroot_out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *key = keys + 32 * i;
+    DtLoc loc = dt_descend(t, t.ltrie ? (uint32_t)(key[0] >> 4) : 0u, key);
+    uint32_t leaf = loc.found ? (loc.child & ~DT_LEAF) : DT_NONE;
+    leaf_out[i] = leaf;
+    if (leaf != DT_NONE && t.lsroot) dt_copy32(sroot_out + 32 * i, t.lsroot + 32 * (uint64_t)leaf);
+    else dt_put_empty_root(sroot_out + 32 * i);
+}
+// trie_of_target[j] = leaf of the account whose slot-target segment holds j
+__global__ void dt_target_tries_kernel(const uint64_t *__restrict__ seg_offsets, uint64_t n_accounts, const uint32_t *__restrict__ leaf_of,
+                                       uint64_t n_targets, uint32_t *__restrict__ trie_of_target) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_targets) return;
+    uint64_t lo = 0, hi = n_accounts;  // last account with offset <= j
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (seg_offsets[mid] <= j) lo = mid;
+        else hi = mid;
+    }
+    trie_of_target[j] = leaf_of[lo];
+}

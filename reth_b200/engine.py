@@ -400,6 +400,57 @@ class Engine:
         self._check(self.lib.b200_dev_status(self.ctx))
 
 
+class Comm:
+    """b200_comm_*: the NCCL communicator behind the C ABI (one rank per GPU).  `Comm.unique_id()` on rank 0, ship the 128 bytes
+    to the other ranks, `Comm(engine, id, n_ranks, rank)` on every rank (collective)."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = np.zeros(128, np.uint8)
+        rc = _lib.load().b200_comm_unique_id(_ptr(buf))
+        if rc != 0:
+            raise B200Error(rc, "b200_comm_unique_id: NCCL not available")
+        return buf.tobytes()
+
+    def __init__(self, engine: Engine, unique_id: bytes, n_ranks: int, rank: int):
+        self.engine = engine
+        h = C.c_void_p()
+        idb = np.frombuffer(unique_id, np.uint8).copy()
+        engine._check(engine.lib.b200_comm_create(engine.ctx, _ptr(idb), n_ranks, rank, C.byref(h)))
+        self.handle, self.n_ranks, self.rank = h, n_ranks, rank
+
+    def state_root_sharded(self, acct_keys, accounts, slot_keys, values, seg_offsets) -> bytes:
+        """This rank's shard (whole top-nibble buckets) in, the state root out — on every rank."""
+        acct_keys = _np(acct_keys).reshape(-1, 32)
+        accounts = np.ascontiguousarray(accounts, ACCOUNT_DTYPE)
+        slot_keys = _np(slot_keys).reshape(-1, 32)
+        values = _np(values).reshape(-1, 32)
+        seg_offsets = _np(seg_offsets, np.uint64)
+        root = np.empty(32, np.uint8)
+        s = Stats()
+        self.engine._check(self.engine.lib.b200_state_root_sharded(self.handle, _ptr(acct_keys), _ptr(accounts), len(acct_keys),
+                                                                   _ptr(slot_keys), _ptr(values), _ptr(seg_offsets), _ptr(root), C.byref(s)))
+        return root.tobytes()
+
+    def state_root_sharded_dev(self, t_akeys, t_accts, n_accounts: int, t_skeys, t_svals, t_offs, n_slots: int, t_root):
+        self.engine._check(self.engine.lib.b200_state_root_sharded_dev(self.handle, t_akeys.data_ptr(), t_accts.data_ptr(), n_accounts,
+                                                                       t_skeys.data_ptr(), t_svals.data_ptr(), t_offs.data_ptr(),
+                                                                       n_slots, t_root.data_ptr()))
+
+    def hash_partition_dev(self, t_in, msg_len: int, stride: int, n: int, t_values, value_bytes: int, capacity: int, t_keys_out,
+                           t_values_out) -> int:
+        n_out = C.c_uint64(0)
+        self.engine._check(self.engine.lib.b200_hash_partition_dev(
+            self.handle, t_in.data_ptr(), msg_len, stride, n, t_values.data_ptr() if t_values is not None else None, value_bytes,
+            capacity, t_keys_out.data_ptr(), t_values_out.data_ptr() if t_values_out is not None else None, C.byref(n_out)))
+        return int(n_out.value)
+
+    def close(self):
+        if self.handle:
+            self.engine.lib.b200_comm_destroy(self.handle)
+            self.handle = None
+
+
 class RootStream:
     """b200_root_stream_*: a state root committed in ascending account-key ranges (StateRoot::with_threshold /
     root_with_progress / with_intermediate_state, trie.rs:73-85,156; MerkleStage's chunked rebuild, merkle.rs:184-366).
@@ -753,6 +804,41 @@ class DynamicState:
             nib = bytes(x for b in key.tobytes() for x in (b >> 4, b & 15))
             for depth, rlp in nodes:
                 out[nib[:depth]] = rlp
+        return out
+
+    def multiproof(self, targets: dict) -> dict:
+        """Proof::multiproof(MultiProofTargets) in one device call.  targets: {hashed address: iterable of hashed slots}.
+        -> {"account_subtree": {path: rlp}, "storages": {address: {"root": bytes, "subtree": {path: rlp}}}} — the maps of
+        MultiProof / StorageMultiProof (crates/trie/common/src/proofs.rs:180-188,594-602; branch_node_masks are not
+        produced)."""
+        addrs = sorted(targets)
+        n = len(addrs)
+        ak = np.frombuffer(b"".join(addrs), np.uint8).reshape(n, 32) if n else np.zeros((0, 32), np.uint8)
+        slots, offs = [], [0]
+        for a in addrs:
+            sl = sorted(set(bytes(x) for x in targets[a]))
+            slots.extend(sl)
+            offs.append(len(slots))
+        sk = np.frombuffer(b"".join(slots), np.uint8).reshape(len(slots), 32) if slots else np.zeros((0, 32), np.uint8)
+        so = np.array(offs, np.uint64)
+        sroots = np.zeros((max(n, 1), 32), np.uint8)
+        pa, ps = Proofs(), Proofs()
+        self.engine._check(self.engine.lib.b200_dstate_multiproof(self.handle, _ptr(ak), n, _ptr(so), _ptr(sk), C.byref(pa), _ptr(sroots),
+                                                                  C.byref(ps)))
+        nib = lambda k: bytes(x for b in k for x in (b >> 4, b & 15))
+        out = {"account_subtree": {}, "storages": {}}
+        for key, nodes in zip(addrs, self._take_proofs(pa, with_depths=True)):
+            kn = nib(key)
+            for depth, rlp in nodes:
+                out["account_subtree"][kn[:depth]] = rlp
+        sp = self._take_proofs(ps, with_depths=True)
+        for i, a in enumerate(addrs):
+            sub = {}
+            for j in range(offs[i], offs[i + 1]):
+                kn = nib(slots[j])
+                for depth, rlp in sp[j]:
+                    sub[kn[:depth]] = rlp
+            out["storages"][a] = {"root": sroots[i].tobytes(), "subtree": sub}
         return out
 
     def account_proofs(self, acct_keys) -> list:

@@ -243,3 +243,48 @@ def test_account_multiproof_is_the_union_of_the_proofs(eng, golden_allocs):
     # the extension 'a7' (2 nibbles) puts the first branch at path [a, 7]
     assert bytes([0xa, 0x7]) in mp and len(rlp_items(mp[bytes([0xa, 0x7])])) == 17
     ds.close()
+
+
+def test_multiproof_batch_equals_the_single_proofs(eng):
+    """b200_dstate_multiproof (Proof::multiproof over MultiProofTargets, proof/mod.rs:143-193): accounts with their slot targets
+    in one call == the union of the per-target account proofs and per-account storage proofs, storage roots included; absent
+    accounts and accounts without storage behave as in testspec_empty_storage_proof (proof.rs:117-140)."""
+    from reth_b200 import DynamicState
+    from tests.util import synth_accounts, synth_storage
+    n = 2000
+    keys, accs = synth_accounts(71, n)
+    counts = np.where(np.arange(n) % 5 == 0, 1 + (np.arange(n) % 40), 0)
+    skeys, svals, offs = synth_storage(72, counts, "mixed")
+    ds = DynamicState.create(eng, keys, accs, skeys, svals, offs)
+    rng = np.random.default_rng(8)
+    targets = {}
+    for a in rng.choice(n, 25, replace=False):
+        lo, hi = int(offs[a]), int(offs[a + 1])
+        have = [skeys[j].tobytes() for j in range(lo, min(hi, lo + 6))]
+        targets[keys[a].tobytes()] = have + [bytes(rng.integers(0, 256, 32, dtype=np.uint8)) for _ in range(2)]
+    targets[bytes(rng.integers(0, 256, 32, dtype=np.uint8))] = [bytes(32)]        # an account that does not exist
+    targets[keys[1].tobytes()] = []                                               # an account target without slot targets
+    mp = ds.multiproof(targets)
+    addrs = sorted(targets)
+    assert mp["account_subtree"] == ds.account_multiproof(np.frombuffer(b"".join(addrs), np.uint8).reshape(-1, 32))
+    nib = lambda k: bytes(x for b in k for x in (b >> 4, b & 15))
+    for a in addrs:
+        sl = sorted(set(targets[a]))
+        tgt = np.frombuffer(b"".join(sl), np.uint8).reshape(-1, 32) if sl else np.zeros((0, 32), np.uint8)
+        sroot, sproofs = ds.storage_proofs(a, tgt)
+        assert mp["storages"][a]["root"] == sroot
+        want = {}
+        for k, proof in zip(sl, sproofs):
+            # node k of a proof sits at the path consumed so far: recompute it by walking the proof
+            path = b""
+            for node in proof:
+                want[path] = node
+                items = rlp_items(node) if node != b"\x80" else []
+                if len(items) == 17:
+                    path = path + nib(k)[len(path):len(path) + 1]
+                elif len(items) == 2 and not (items[0][0] & 0x20):
+                    enc = items[0]
+                    ext = list(nib(enc))[1:] if enc[0] & 0x10 else list(nib(enc))[2:]
+                    path = path + bytes(ext)
+        assert mp["storages"][a]["subtree"] == want
+    ds.close()

@@ -104,7 +104,8 @@ def main():
     # ---- undo everything in one block: base values back, deleted base keys re-inserted, inserted keys deleted.  The root must
     # return to the root of the from-scratch build the trie was created from (independent of any model of the state).
     base_keys_np = keys.view(torch.uint8).view(n, 32).cpu().numpy()
-    prefix = np.ascontiguousarray(base_keys_np[:, :8]).view(">u8").reshape(-1)   # sorted with the keys (big-endian)
+    # sorted with the keys; NATIVE byte order (searchsorted on a non-native array converts the whole array on every call)
+    prefix = np.ascontiguousarray(base_keys_np[:, :8]).view(">u8").reshape(-1).astype(np.uint64)
 
     def find_row(kb):
         want = int.from_bytes(kb[:8], "big")
