@@ -56,8 +56,12 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
     // The leaf pass (ALU-bound, the longest kernel of a build) and the structure pass (sorts / scans / flags: memory- and
     // latency-bound, one host read-back at its end) both need only Lp: they run side by side, the structure pass on the
     // high-priority aux stream; the branch levels join them again.  A single leaf has no structure pass.
-    cudaStream_t sa = n >= 2 ? c->aux_stream : st;
-    if (n >= 2) {
+    static const bool overlap = [] {  // B200_OVERLAP_STRUCTURE=0: one stream (measurement aid)
+        const char *e = getenv("B200_OVERLAP_STRUCTURE");
+        return !e || atoi(e) != 0;
+    }();
+    cudaStream_t sa = (n >= 2 && overlap) ? c->aux_stream : st;
+    if (sa != st) {
         CU(cudaEventRecord(c->ev_fork, st));
         CU(cudaStreamWaitEvent(sa, c->ev_fork, 0));
     }
@@ -127,8 +131,10 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
     f.gap_sorted = gap_sorted;
     f.node_start = node_start;
     if (B == 0) {  // every trie has at most one leaf
-        CU(cudaEventRecord(c->ev_join, sa));
-        CU(cudaStreamWaitEvent(st, c->ev_join, 0));
+        if (sa != st) {
+            CU(cudaEventRecord(c->ev_join, sa));
+            CU(cudaStreamWaitEvent(st, c->ev_join, 0));
+        }
         return B200_OK;
     }
 
@@ -153,8 +159,10 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
     ENSURE(cub_temp, t_ns);
     CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_ns, nk, nk2, nids, norder, (int64_t)B, 0, 8, sa));
     c->launches += 1;
-    CU(cudaEventRecord(c->ev_join, sa));
-    CU(cudaStreamWaitEvent(st, c->ev_join, 0));  // the branch levels need the leaves (st) and the structure (sa)
+    if (sa != st) {
+        CU(cudaEventRecord(c->ev_join, sa));
+        CU(cudaStreamWaitEvent(st, c->ev_join, 0));  // the branch levels need the leaves (st) and the structure (sa)
+    }
     phase_mark(c, "leaves||structure");
 
     // ---- deepest level first; the per-level frontier stays in HBM.  Big levels get one launch per child-count
