@@ -101,6 +101,8 @@ def main():
         mask[pick[n_upd:]] = False
         live = np.concatenate([live[mask], ins_keys])
     note("blocks done")
+    import faulthandler
+    faulthandler.dump_traceback_later(240, exit=True)   # a hang below says where
     # ---- undo everything in one block: base values back, deleted base keys re-inserted, inserted keys deleted.  The root must
     # return to the root of the from-scratch build the trie was created from (independent of any model of the state).
     base_keys_np = keys.view(torch.uint8).view(n, 32).cpu().numpy()
@@ -109,12 +111,13 @@ def main():
 
     def find_row(kb):
         want = int.from_bytes(kb[:8], "big")
-        row = int(np.searchsorted(prefix, want))
+        row = int(np.searchsorted(prefix, np.uint64(want)))   # (a Python int would promote the whole array on every call)
         while row < n and int(prefix[row]) == want:
             if base_keys_np[row].tobytes() == kb:
                 return row
             row += 1
         return -1
+    note("base key prefixes ready")
     undo = {}
     for kb in base_index:
         if kb in inserted_total:
@@ -125,6 +128,7 @@ def main():
     for kb in inserted_total:
         if kb not in undo:
             undo[kb] = (0, h_accts[0])
+    note("undo entries looked up")
     uk = sorted(undo)
     dk = np.frombuffer(b"".join(uk), np.uint8).reshape(-1, 32)
     da = np.zeros(len(uk), ACCOUNT_DTYPE)
@@ -135,6 +139,7 @@ def main():
     undo_root = trie.apply(dk, da, present)
     note("undo applied")
     undo_ok = bool(undo_root == base_root and len(trie) == n)
+    faulthandler.cancel_dump_traceback_later()
     cpu = None
     if args.cpu_sample:
         import oracle

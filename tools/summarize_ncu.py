@@ -58,6 +58,51 @@ def launches(src, dst):
             f.write(f"| {v:.3f} | {100 * v / To:.1f}% | {cnt[k]} | `{k[:110]}` |\n")
 
 
+def trie(src, dst):
+    """`ncu -i rep --page raw --csv` of the node kernels of one C3 build -> one row per launch."""
+    rows = list(csv.reader(open(src)))
+    hdr, data = rows[0], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    cols = [("Kernel Name", "kernel"), ("launch__grid_size", "grid"), ("gpu__time_duration.sum", "ms"),
+            ("launch__registers_per_thread", "regs"), ("launch__shared_mem_per_block_dynamic", "dyn smem KB"),
+            ("smsp__inst_executed.sum", "warp inst"), ("smsp__thread_inst_executed_per_inst_executed.ratio", "active thr/warp"),
+            ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
+            ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
+            ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe %"),
+            ("dram__bytes_read.sum", "DRAM rd"), ("dram__bytes_write.sum", "DRAM wr"),
+            ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall: long scoreboard"),
+            ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall: math pipe")]
+    units = rows[1]
+    out = ["# ncu --set full, node kernels of one C3 build (1M accounts x 16 slots), round 2", "",
+           "One row per launch in launch order (storage forest, then the account trie).  Durations are ncu replays (cold caches,",
+           "serialised).  `leaf_storage_kernel` is the register-path storage leaf kernel (no shared-memory strip).", "",
+           "| " + " | ".join(n for _, n in cols) + " |", "|" + "---|" * len(cols)]
+    total = 0.0
+    for r in data:
+        vals = []
+        for h, _ in cols:
+            v = r[col[h]] if h in col else ""
+            if h == "Kernel Name":
+                v = "`" + v.split("(")[0].replace("void ", "") + "`"
+            elif h == "launch__shared_mem_per_block_dynamic":
+                v = f"{float(v) / 1024:.1f}" if units[col[h]] == "byte/block" else v
+            elif h in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                u = units[col[h]]
+                f = float(v) * {"Gbyte": 1000, "Mbyte": 1, "Kbyte": 1e-3, "byte": 1e-6}.get(u, 1)
+                v = f"{f:.1f} MB"
+            else:
+                try:
+                    fv = float(v)
+                    v = f"{fv:.3f}" if h == "gpu__time_duration.sum" else (f"{fv:.0f}" if fv > 1000 else f"{fv:.1f}")
+                except ValueError:
+                    pass
+            vals.append(v)
+        total += float(r[col["gpu__time_duration.sum"]])
+        out.append("| " + " | ".join(vals) + " |")
+    out += ["", f"sum of the node kernels above: {total:.3f} ms"]
+    open(dst, "w").write("\n".join(out) + "\n")
+
+
 def report(src, dst):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -76,4 +121,4 @@ def report(src, dst):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "report": report, "trie": trie}[sys.argv[1]](sys.argv[2], sys.argv[3])
