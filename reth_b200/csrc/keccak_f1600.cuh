@@ -3,8 +3,9 @@
 // Why thread-per-message and not a warp-cooperative layout: the permutation is ~122 LOP3 + ~58 SHF per round
 // on 32-bit halves (all on the ALU pipe: 64 lanes/clk/SM).  Spreading one state over 25 lanes of a warp turns
 // every theta/pi/chi dependency into SHFL traffic (32 lanes/clk/SM, two SHFL per 64-bit lane) and idles 7/32
-// lanes; it is ~5x slower than keeping the 25 lanes in registers.  A warp-shuffle variant is kept in
-// keccak_batch.cu (keccak256_fixed32_warp_kernel) for the measured comparison DESIGN.md reports.
+// lanes; it is ~5x slower than keeping the 25 lanes in registers.  The warp-shuffle formulation survives where latency, not
+// throughput, is the bound: WarpKeccak in tk_warp.cuh (one warp per node for the sparse top levels of a trie and the dirty
+// paths of an incremental update), measured against this one in DESIGN.md §5.
 //
 // What it computes: alloy-primitives `keccak256` (Keccak-256, rate 136, pad 0x01..0x80) as called from
 // reth's KeccakKeyHasher (crates/trie/common/src/key.rs:4-18) and alloy-trie's RlpNode::from_rlp.
@@ -115,6 +116,13 @@ __device__ __forceinline__ void keccak_f1600_final(uint64_t (&a)[25]) {
 #pragma unroll 1
     for (int r = 0; r < 23; r++) keccak_round(a, KECCAK_RC[r]);
     keccak_round(a, 0x8000000080008008ULL);
+}
+
+// Rounds [R0, R1) of the permutation: lets a kernel interleave other work (the loads of its next item) between segments.
+template <int R0, int R1>
+__device__ __forceinline__ void keccak_rounds(uint64_t (&a)[25]) {
+#pragma unroll 1
+    for (int r = R0; r < R1; r++) keccak_round(a, KECCAK_RC[r]);
 }
 
 // Single-block message whose state is mostly compile-time zeros (a 20/32-byte key): round 0 is peeled too, so

@@ -336,6 +336,156 @@ __device__ __forceinline__ void thread_build_node(Strip<BLOCK> &s, uint32_t *sme
     f.E[r] = (uint32_t)f.n + v;
 }
 
+// ------------------------------------------------------------------------------------------------ class 0, software-pipelined
+// The thread-per-node kernels gather through four dependent loads (node -> gap -> S/E -> meta/ref); ncu shows them stalled
+// on exactly that (long scoreboard 1.6 warps per issue slot at 3.5 resident warps per scheduler, ALU pipe 82 %).  For the
+// class that holds most nodes (2 / 3 children, register path) the gather of node i+1 is therefore spread over the
+// permutation of node i: one level of the chain is issued after every six rounds, so every load has ~2 us of ALU work of
+// the same thread (and of its neighbours) in front of its first use.
+struct PrefetchedNode3 {
+    uint32_t v, j0, k;      // node, first gap (sorted order), number of gaps (children - 1)
+    uint32_t g0, g1;        // gap positions
+    uint32_t id[3], nb[3], mt[3];
+    uint32_t rr[3][8];
+    uint32_t nl, nr;        // node_l / node_r of the first / last child when those are nodes
+    bool valid;
+};
+
+template <int BLOCK>
+__device__ __forceinline__ void pf3_stage_a(const ForestDev &f, const uint32_t *__restrict__ node_order, uint64_t p, uint32_t pos_hi,
+                                            PrefetchedNode3 &x) {
+    x.valid = p < pos_hi;
+    if (x.valid) {
+        x.v = __ldg(node_order + p);
+        x.j0 = f.node_start[x.v];
+        x.k = f.node_start[x.v + 1] - x.j0;
+    }
+}
+__device__ __forceinline__ void pf3_stage_b(const ForestDev &f, PrefetchedNode3 &x) {
+    if (x.valid) {
+        x.g0 = f.gap_sorted[x.j0];
+        x.g1 = x.k >= 2 ? f.gap_sorted[x.j0 + 1] : x.g0;
+    }
+}
+__device__ __forceinline__ void pf3_stage_c(const ForestDev &f, PrefetchedNode3 &x) {
+    if (x.valid) {
+        const uint32_t nib0 = f.nibs[x.g0], nib1 = f.nibs[x.g1];
+        x.id[0] = f.E[x.g0 - 1];
+        x.id[1] = f.S[x.g0];
+        x.id[2] = x.k >= 2 ? f.S[x.g1] : x.id[1];
+        x.nb[0] = nib0 >> 4;
+        x.nb[1] = nib0 & 15;
+        x.nb[2] = x.k >= 2 ? (nib1 & 15) : 15u;
+    }
+}
+__device__ __forceinline__ void pf3_stage_d(const ForestDev &f, PrefetchedNode3 &x) {
+    if (x.valid) {
+        const uint32_t n = (uint32_t)f.n;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            x.mt[c] = x.id[c] < n ? f.leaf_meta[x.id[c]] : f.node_meta[x.id[c] - n];
+            load32_nc(x.id[c] < n ? f.leaf_ref + 32 * (uint64_t)x.id[c] : f.node_ref + 32 * (uint64_t)(x.id[c] - n), x.rr[c]);
+        }
+        const uint32_t last = x.k >= 2 ? x.id[2] : x.id[1];
+        x.nl = x.id[0] < n ? x.id[0] : f.node_l[x.id[0] - n];
+        x.nr = last < n ? last : f.node_r[last - n];
+    }
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 4) branch3_pipelined_kernel(ForestDev f, const uint32_t *__restrict__ node_order,
+                                                                  uint32_t pos_lo, uint32_t pos_hi, int d) {
+    extern __shared__ uint32_t smem[];
+    if (*(volatile int *)f.err != B200_DEVERR_NONE) return;
+    Strip<BLOCK> s;
+    uint32_t hashed = 0, exts = 0;
+    const uint32_t step = gridDim.x * BLOCK;
+    const uint32_t n = (uint32_t)f.n;
+    uint64_t p = (uint64_t)pos_lo + blockIdx.x * BLOCK + threadIdx.x;
+    PrefetchedNode3 cur;
+    pf3_stage_a<BLOCK>(f, node_order, p, pos_hi, cur);
+    pf3_stage_b(f, cur);
+    pf3_stage_c(f, cur);
+    pf3_stage_d(f, cur);
+    while (cur.valid) {
+        PrefetchedNode3 nx;
+        pf3_stage_a<BLOCK>(f, node_order, p + step, pos_hi, nx);
+        const uint32_t v = cur.v, l = cur.nl, r = cur.nr;
+        const bool three = cur.k >= 2;
+        const bool fast = cur.k >= 1 && cur.k <= 2 && ((cur.mt[0] | cur.mt[1] | (three ? cur.mt[2] : 0u)) & META_LEN) == 0;
+        const uint8_t lpl = f.Lp[l], lpr = f.Lp[(uint64_t)r + 1];  // consumed after the permutation
+        uint32_t ref[8], meta = 0, state_mask = 0, tree_mask = 0, hash_mask = 0;
+        if (fast) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                if (c < 2 || three) {
+                    const uint32_t bit = 1u << cur.nb[c];
+                    state_mask |= bit;
+                    if (cur.id[c] >= n || (cur.mt[c] & META_ISNODE)) {
+                        if (!(cur.mt[c] & META_EXT)) hash_mask |= bit;
+                        if (cur.mt[c] & META_STORED) tree_mask |= bit;
+                    }
+                }
+            }
+            uint64_t a[25];
+            {
+                uint32_t m[34];
+                branch23_words(cur.rr[0], cur.rr[1], cur.rr[2], cur.nb[0], cur.nb[1], cur.nb[2], three, m);
+#pragma unroll
+                for (int q = 0; q < 17; q++) a[q] = ((uint64_t)m[2 * q + 1] << 32) | m[2 * q];
+#pragma unroll
+                for (int q = 17; q < 25; q++) a[q] = 0;
+            }
+            keccak_rounds<0, 6>(a);
+            pf3_stage_b(f, nx);
+            keccak_rounds<6, 12>(a);
+            pf3_stage_c(f, nx);
+            keccak_rounds<12, 17>(a);
+            pf3_stage_d(f, nx);
+            keccak_rounds<17, 23>(a);
+            keccak_round(a, 0x8000000080008008ULL);  // last round: only lanes 0..3 are consumed
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                ref[2 * q] = (uint32_t)a[q];
+                ref[2 * q + 1] = (uint32_t)(a[q] >> 32);
+            }
+            hashed++;
+            int pdl = depth_of(lpl), pdr = depth_of(lpr);
+            int pd = pdl > pdr ? pdl : pdr;
+            if (pd + 1 < d) {  // extension node above the branch (rare for hashed keys): through the strip
+                s.init(smem);
+                uint32_t elen = encode_extension(s, f.keys + 32 * (uint64_t)l, (uint32_t)(pd + 1), (uint32_t)d, ref, 0u);
+                meta = strip_to_ref(s, elen, pd < 0, ref, hashed) | META_EXT;
+                exts++;
+            }
+            if ((tree_mask | hash_mask) != 0) meta |= META_STORED;
+            store32(f.node_ref + 32 * (uint64_t)v, ref);
+            f.node_meta[v] = (uint8_t)meta;
+            f.node_l[v] = l;
+            f.node_r[v] = r;
+            f.node_masks[v] = make_ushort4((unsigned short)state_mask, (unsigned short)tree_mask, (unsigned short)hash_mask,
+                                           (unsigned short)d);
+            f.S[l] = n + v;
+            f.E[r] = n + v;
+        } else {  // an inline (< 32 byte) child, or a node outside the class: the general builder (loads everything again)
+            pf3_stage_b(f, nx);
+            pf3_stage_c(f, nx);
+            pf3_stage_d(f, nx);
+            thread_build_node<BLOCK, 3, false>(s, smem, f, v, d, hashed, exts, ref);
+        }
+        cur = nx;
+        p += step;
+    }
+    for (int o = 16; o; o >>= 1) {
+        hashed += __shfl_xor_sync(0xffffffffu, hashed, o);
+        exts += __shfl_xor_sync(0xffffffffu, exts, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (hashed) atomicAdd(&f.counters[CNT_HASHED], (unsigned long long)hashed);
+        if (exts) atomicAdd(&f.counters[CNT_EXT], (unsigned long long)exts);
+    }
+}
+
 // One thread per branch node of depth d.  MAXC bounds the children of every node in [pos_lo, pos_hi) (the level's
 // nodes are grouped by child-count class); the strip is sized for that class, which is what sets the occupancy.
 template <int BLOCK, int MAXC>

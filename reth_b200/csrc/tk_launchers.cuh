@@ -120,7 +120,12 @@ cudaError_t launch_branch_level(const ForestDev &f, const uint32_t *node_order, 
         return cudaGetLastError();
     }
     switch (cls) {
-        case 0: return launch_branch_class<3, 34>(f, node_order, pos_lo, pos_hi, d, st);
+        case 0: {  // 2 / 3 children: register path, gather of the next node pipelined under the permutation of this one
+            auto k = branch3_pipelined_kernel<BRANCH_BLOCK>;
+            size_t smem = (size_t)34 * BRANCH_BLOCK * 4;  // the strip of the rare extension / inline-child nodes
+            k<<<persistent_grid(k, BRANCH_BLOCK, smem, pos_hi - pos_lo), BRANCH_BLOCK, smem, st>>>(f, node_order, pos_lo, pos_hi, d);
+            return cudaGetLastError();
+        }
         case 1: return launch_branch_class<7, 68>(f, node_order, pos_lo, pos_hi, d, st);
         case 2: return launch_branch_class<12, 102>(f, node_order, pos_lo, pos_hi, d, st);
         default: return launch_branch_class<16, BRANCH_WORDS>(f, node_order, pos_lo, pos_hi, d, st);
