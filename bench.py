@@ -8,15 +8,22 @@ Headline workload (BASELINE.json configs[1], "C2"): batch keccak256 of 10M 32-by
 AccountHashing / StorageHashing inner loop.  One step = one pass over the batch.
   value : digests/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
   e2e   : same metric through the C-ABI with HOST (page-locked) buffers, H2D + hash + D2H inside the region
-Secondary object "state_root" (BASELINE.json configs[2], "C3"): StateRoot over 1M accounts x 16 slots per GPU,
-leaves/s; at N>1 the accounts are sharded by top key nibble and the 16-entry subtrie frontier is all-gathered
-over NCCL (the only collective of the path).
-Also printed in the same JSON line: roofline (dominant kernel vs measured HBM peak), cpu_baseline (the oracle's
-keccak on the host cores, bounded sample), clocks, gpu_launches.
+Objects in the same JSON line (each with its own `roofline`: HBM fraction from the algorithmic bytes of SURVEY.md §8d,
+`alu_frac` against the measured ALU-pipe ceiling, `traffic` from the committed ncu sums in profiles/roofline_traffic.json):
+  state_root    C3 (configs[2]): StateRoot over 1M accounts x 16 slots per GPU, leaves/s; at N>1 the accounts are sharded by
+                top key nibble and the 16-entry frontier is all-gathered inside b200_state_root_sharded_dev (NCCL behind the
+                C ABI) — the only collective of the path; e2e through b200_state_root_full with host buffers
+  mainnet_shape C4 (configs[3]; on by default at N>1): 31.25M-leaf mainnet-shaped shard per GPU = 250M leaves on 8 GPUs
+  hash_partition (N>1): AccountHashing at N>1 — keccak + all-to-all of (digest, row) by owner rank + sort
+  incremental   C5 (configs[4]): 10k dirty accounts against a resident 100M-leaf trie, latency; the incremental root is
+                checked against a from-scratch device build of the updated state inside the run
+  dynamic       the in-place block-update path (b200_dtrie_apply at 100M leaves, mixed blocks; b200_dstate_apply on the C3
+                state) and the f2/f3/f4 legs (hash+sort, ordered roots, table rows), each in its own process and each
+                checking itself (per-block roots against the static path / a twin, and an undo block back to the seed root)
+  cpu_baseline  the oracle's keccak on the host cores, bounded sample; clocks; gpu_launches; parity_spot_check.
 
---impl reference times the CPU restatement of reth's algorithm (oracle/, all host threads) on a bounded sample
-of the same workload: reth itself cannot be built in this image (no Rust toolchain; its keccak/HashBuilder live
-in external crates), see DESIGN.md.
+--impl reference times the CPU restatement of reth's algorithm (oracle/, all host threads) on the SAME 10M keys and config:
+reth itself cannot be built in this image (no Rust toolchain; its keccak/HashBuilder live in external crates), see DESIGN.md.
 """
 from __future__ import annotations
 
