@@ -13,8 +13,11 @@
  *   - a b200_ctx is internally locked: calls on one ctx are serialised, different ctxs run concurrently
  *     (ParallelStateRoot calls StorageRoot from many threads: crates/trie/parallel/src/root.rs:111-125)
  *   - host-pointer entry points copy inputs to the device and results back (these are what the e2e
- *     benchmark times); *_dev entry points take device pointers, enqueue on the ctx stream and return
- *     without synchronising (b200_sync to wait)
+ *     benchmark times); *_dev entry points take device pointers (inputs and outputs) and leave their results in
+ *     device memory without a final synchronisation (b200_sync to wait, or order later work on the ctx stream).
+ *     They are not fire-and-forget: a trie build reads its level histogram back once (322 integers, on an internal
+ *     stream while the leaf pass keeps running on the ctx stream), and a scratch buffer that has to grow
+ *     synchronises before it is replaced
  *   - hashed keys are 32-byte big-endian strings exactly as reth's B256; sorted means ascending bytewise
  */
 #ifndef B200TRIE_H
@@ -215,7 +218,8 @@ B200_API int32_t b200_state_root_full_rows(b200_ctx *, const uint8_t *acct_keys3
                                            b200_rows *account_rows, b200_rows *storage_rows, b200_stats *opt_stats);
 
 /* Device-resident variants: every pointer is a device pointer (seg_offsets included), results are written
- * to device memory, nothing is copied or synchronised.  d_root32 / d_roots32 are device buffers.
+ * to device memory and no host buffer is touched (one internal read-back of the level histogram per build, see the
+ * conventions above).  d_root32 / d_roots32 are device buffers.
  * Input violations (unsorted keys, zero values) are reported by the next b200_sync / b200_dev_status. */
 B200_API int32_t b200_storage_roots_dev(b200_ctx *, const void *d_slot_keys32, const void *d_values32_be,
                                const void *d_seg_offsets, uint64_t n_accounts, uint64_t n_slots,
@@ -365,7 +369,7 @@ B200_API int32_t b200_comm_rank(const b200_comm *);
 B200_API int32_t b200_comm_size(const b200_comm *);
 /* b200_subtrie_frontier -> ncclAllGather of the 16 x 68-byte frontier -> b200_root_from_frontier in ONE call on the ctx
  * stream: every rank passes its own shard (whole top-nibble buckets, any subset) and receives the state root.  The _dev form
- * takes device pointers and returns without synchronising (d_root32: device). */
+ * takes device pointers and leaves the root in device memory without a final synchronisation (d_root32: device). */
 B200_API int32_t b200_state_root_sharded(b200_comm *, const uint8_t *acct_keys32, const b200_account *accts, uint64_t n_accounts,
                                          const uint8_t *slot_keys32, const uint8_t *values32_be, const uint64_t *seg_offsets,
                                          uint8_t root32[32], b200_stats *opt_stats);

@@ -121,7 +121,16 @@ extern "C" B200_API void b200_destroy(b200_ctx *c) {
     delete c;
 }
 
-extern "C" B200_API const char *b200_last_error(const b200_ctx *c) { return c ? c->err.c_str() : "null context"; }
+extern "C" B200_API const char *b200_last_error(const b200_ctx *c) {
+    if (!c) return "null context";
+    // a copy per calling thread: another thread's failing call may rewrite the context's string at any time
+    static thread_local std::string mine;
+    {
+        std::lock_guard<std::mutex> g(const_cast<b200_ctx *>(c)->err_mu);
+        mine = c->err;
+    }
+    return mine.c_str();
+}
 extern "C" B200_API const char *b200_version(void) { return B200_VERSION_STR; }
 extern "C" B200_API uint64_t b200_device_bytes(const b200_ctx *c) { return c ? c->dev_bytes : 0; }
 

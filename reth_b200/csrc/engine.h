@@ -28,6 +28,7 @@ struct b200_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> chunk_events;
     std::mutex mu;
+    std::mutex err_mu;  // guards err: argument checks report errors before they take `mu`
     std::string err;
     uint64_t dev_bytes = 0;
     unsigned launches = 0;
@@ -84,7 +85,10 @@ inline int32_t fail(b200_ctx *c, int32_t code, const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    if (c) c->err = buf;
+    if (c) {
+        std::lock_guard<std::mutex> g(c->err_mu);
+        c->err = buf;
+    }
     return code;
 }
 

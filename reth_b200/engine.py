@@ -233,6 +233,7 @@ class Engine:
         slot_keys = _np(slot_keys).reshape(-1, 32)
         values = _np(values).reshape(-1, 32)
         seg_offsets = _np(seg_offsets, np.uint64)
+        _check_segments(seg_offsets, len(slot_keys), len(values))
         m = len(seg_offsets) - 1
         roots = np.empty((m, 32), np.uint8)
         u, s = Updates(), Stats()
@@ -301,6 +302,7 @@ class Engine:
         seg_offsets = _np(seg_offsets, np.uint64)
         if len(seg_offsets) != len(acct_keys) + 1:
             raise ValueError("seg_offsets must have n_accounts+1 entries")
+        _check_segments(seg_offsets, len(slot_keys), len(values))
         root = np.empty(32, np.uint8)
         ua, us, s = Updates(), Updates(), Stats()
         self._check(self.lib.b200_state_root_full(
@@ -400,12 +402,32 @@ class Engine:
         self._check(self.lib.b200_dev_status(self.ctx))
 
 
+def _prefer_bundled_nccl():
+    """The library dlopens "libnccl.so.2".  In a Python host that also imports torch AFTERWARDS the system copy loaded first
+    would shadow the newer one torch is linked against (same soname): point the library at the copy bundled with torch
+    (nvidia-nccl wheel) when there is one and the caller has not chosen (B200_NCCL_LIB)."""
+    import importlib.util
+    import os
+    if os.environ.get("B200_NCCL_LIB"):
+        return
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations or []) if spec else []:
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["B200_NCCL_LIB"] = cand
+                return
+    except Exception:  # noqa: BLE001 - no bundled copy: the system library is used
+        pass
+
+
 class Comm:
     """b200_comm_*: the NCCL communicator behind the C ABI (one rank per GPU).  `Comm.unique_id()` on rank 0, ship the 128 bytes
     to the other ranks, `Comm(engine, id, n_ranks, rank)` on every rank (collective)."""
 
     @staticmethod
     def unique_id() -> bytes:
+        _prefer_bundled_nccl()
         buf = np.zeros(128, np.uint8)
         rc = _lib.load().b200_comm_unique_id(_ptr(buf))
         if rc != 0:
@@ -413,6 +435,7 @@ class Comm:
         return buf.tobytes()
 
     def __init__(self, engine: Engine, unique_id: bytes, n_ranks: int, rank: int):
+        _prefer_bundled_nccl()
         self.engine = engine
         h = C.c_void_p()
         idb = np.frombuffer(unique_id, np.uint8).copy()
@@ -528,6 +551,15 @@ class RootStream:
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+
+def _check_segments(seg_offsets, n_rows_keys: int, n_rows_values: int):
+    """The C ABI takes the row count from seg_offsets[-1] and copies that many rows out of the caller's buffers: an
+    inconsistent offsets array must fail here, not read past a numpy buffer."""
+    if len(seg_offsets) == 0 or int(seg_offsets[0]) != 0:
+        raise B200Error(_lib.ERR_INVALID_ARG, "seg_offsets must start at 0")
+    if int(seg_offsets[-1]) != n_rows_keys or n_rows_values != n_rows_keys:
+        raise B200Error(_lib.ERR_INVALID_ARG, "seg_offsets[-1] must equal the number of slot rows (keys and values)")
 
 
 def numa_bind_thread(device: int = 0) -> int:

@@ -63,7 +63,7 @@ def test_state_root_sharded_two_ranks():
 
 @pytest.mark.skipif(not _two_gpus(), reason="needs 2 GPUs")
 def test_hash_partition_two_ranks():
-    import torch
+    import torch  # (before the communicator: the library then shares torch's NCCL instead of loading the system copy first)
     n = 50_000
     rng = np.random.default_rng(5)
     addrs = rng.integers(0, 256, (n, 20), dtype=np.uint8)
