@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <optional>
 #include <set>
 #include <stdexcept>
@@ -429,11 +430,32 @@ inline std::vector<TableRow> storage_trie_rows(const TrieUpdates &u, b200_key_fo
     return detail::take_rows(rows);
 }
 
-/// crates/trie/trie/src/progress.rs:12-21 — a device build never pauses: always Complete.
+/// crates/trie/trie/src/progress.rs:24-30.  reth keeps the HashBuilder stack and the walker position; here the open right edge
+/// of the build is a b200_root_stream (frontier of the closed top-nibble buckets + the accounts of the open bucket in HBM) and
+/// the position is the index of the next account of the sorted state.
+struct IntermediateStateRootState {
+    b200_root_stream *stream = nullptr;
+    uint64_t next_account = 0;
+    B256 last_hashed_key{};
+    ~IntermediateStateRootState() {
+        if (stream) b200_root_stream_free(stream);
+    }
+    /// what MerkleStage persists between runs (MerkleCheckpoint, merkle.rs:118-148)
+    b200_stream_checkpoint checkpoint() const {
+        b200_stream_checkpoint cp{};
+        if (b200_root_stream_checkpoint(stream, &cp) != B200_OK) throw B200Error(B200_ERR_INVALID_ARG, "stream checkpoint");
+        return cp;
+    }
+};
+
+/// crates/trie/trie/src/progress.rs:12-21: Complete(root, walked, updates) (complete, no state) or
+/// Progress(state, walked, updates) (not complete; `updates` = the nodes this call finished).
 struct StateRootProgress {
-    B256 root;
-    size_t hashed_entries_walked;
+    B256 root{};
+    size_t hashed_entries_walked = 0;
     TrieUpdates updates;
+    bool complete = true;
+    std::shared_ptr<IntermediateStateRootState> state;
 };
 
 /// StorageRoot::{root, root_with_updates, calculate} — trie.rs:479-721
@@ -489,12 +511,23 @@ class StateRoot {
         threshold_ = UINT64_MAX;
         return *this;
     }
+    /// trie.rs:85-88: continue a thresholded build where root_with_progress stopped
+    StateRoot &with_intermediate_state(std::shared_ptr<IntermediateStateRootState> st) {
+        previous_state_ = std::move(st);
+        return *this;
+    }
+    /// root() / root_with_updates() ignore the threshold like the reference (trie.rs:126-140)
     B256 root() const { return calculate(false).root; }
     std::pair<B256, TrieUpdates> root_with_updates() const {
         auto p = calculate(true);
         return {p.root, std::move(p.updates)};
     }
-    StateRootProgress root_with_progress() const { return calculate(true); }
+    /// With a threshold the build stops after a range of accounts holding at least that many hashed entries (accounts +
+    /// slots) and returns Progress; feeding `state` back through with_intermediate_state continues (b200_root_stream_*).
+    StateRootProgress root_with_progress() const {
+        if (threshold_ == UINT64_MAX && !previous_state_) return calculate(true);
+        return calculate_range();
+    }
     /// The rebuild leg of MerkleStage in one call (merkle.rs:216-253 → write_trie_updates): the root and the stored nodes
     /// as AccountsTrie / StoragesTrie rows in table order, laid out on the device (b200_state_root_full_rows).
     struct RootWithTables {
@@ -513,6 +546,58 @@ class StateRoot {
     }
 
   protected:
+    StateRootProgress calculate_range() const {
+        FlatState f = state_.to_flat();
+        const uint64_t n = f.n_accounts();
+        auto st = previous_state_;
+        if (!st) {
+            st = std::make_shared<IntermediateStateRootState>();
+            e_.check(b200_root_stream_begin(e_.raw(), 1, &st->stream));
+        }
+        StateRootProgress out;
+        const uint64_t a0 = st->next_account;
+        uint64_t a1 = a0;
+        // the range: accounts a0 .. a1 holding >= threshold hashed entries (at least one account)
+        while (a1 < n && (a1 == a0 || (a1 - a0) + (f.seg_offsets[a1] - f.seg_offsets[a0]) < threshold_)) a1++;
+        auto take = [&](b200_updates &u, bool storage) {
+            std::map<uint32_t, StorageTrieUpdates> per_trie;
+            for (uint64_t i = 0; i < u.n_nodes; i++) {
+                if (storage) per_trie[u.trie_id[i]].storage_nodes.insert(detail::branch_node(u, i));
+                else out.updates.account_nodes.insert(detail::branch_node(u, i));
+            }
+            b200_updates_release(&u);
+            return per_trie;
+        };
+        if (a1 > a0) {
+            const uint64_t s0 = f.seg_offsets[a0], s1 = f.seg_offsets[a1];
+            std::vector<uint64_t> rel(a1 - a0 + 1);
+            for (uint64_t a = a0; a <= a1; a++) rel[a - a0] = f.seg_offsets[a] - s0;
+            b200_updates au{}, su{};
+            e_.check(b200_root_stream_push(st->stream, f.acct_keys.data() + 32 * a0, f.accts.data() + a0, a1 - a0,
+                                           f.slot_keys.data() + 32 * s0, f.slot_values.data() + 32 * s0, rel.data(), &au, &su, nullptr));
+            take(au, false);
+            auto per_trie = take(su, true);
+            for (uint64_t a = a0; a < a1; a++) {
+                B256 addr;
+                std::memcpy(addr.data(), f.acct_keys.data() + 32 * a, 32);
+                if (f.seg_offsets[a + 1] == f.seg_offsets[a]) out.updates.insert_storage_updates(addr, StorageTrieUpdates::deleted());
+                else out.updates.insert_storage_updates(addr, per_trie[(uint32_t)(a - a0)]);
+            }
+            out.hashed_entries_walked = (a1 - a0) + (s1 - s0);
+            st->next_account = a1;
+            std::memcpy(st->last_hashed_key.data(), f.acct_keys.data() + 32 * (a1 - 1), 32);
+        }
+        if (a1 < n) {
+            out.complete = false;
+            out.state = st;
+            return out;
+        }
+        b200_updates au{};
+        e_.check(b200_root_stream_finish(st->stream, out.root.data(), &au));
+        take(au, false);
+        for (auto &d : prefix_sets_.destroyed_accounts) out.updates.storage_tries[d].is_deleted = true;  // updates.rs:153-157
+        return out;
+    }
     StateRootProgress calculate(bool retain_updates) const {
         FlatState f = state_.to_flat();
         StateRootProgress out;
@@ -543,6 +628,7 @@ class StateRoot {
     HashedPostStateSorted state_;
     TriePrefixSets prefix_sets_;
     uint64_t threshold_ = 100000;  // DEFAULT_INTERMEDIATE_THRESHOLD, trie.rs:25
+    std::shared_ptr<IntermediateStateRootState> previous_state_;
 };
 
 /// The account trie resident in HBM as an arena of 16-slot branch nodes (b200_dtrie_*): a block's upserts and deletes

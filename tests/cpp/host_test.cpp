@@ -197,6 +197,32 @@ static void random_state_vs_oracle(const Engine &e) {
     CHECK(storage_nodes == os.n_nodes);
     orc_updates_free(&oa);
     orc_updates_free(&os);
+    // thresholded build (StateRoot::with_threshold / with_intermediate_state / root_with_progress, trie.rs:73-88,156):
+    // looped until Complete == the one-shot root and updates (reth: arbitrary_state_root_with_progress)
+    for (uint64_t threshold : {uint64_t(1), uint64_t(700), uint64_t(1) << 40}) {
+        std::shared_ptr<IntermediateStateRootState> inter;
+        TrieUpdates acc;
+        size_t steps = 0, walked = 0;
+        for (;;) {
+            auto p = StateRoot(e, sorted).with_threshold(threshold).with_intermediate_state(inter).root_with_progress();
+            steps++;
+            walked += p.hashed_entries_walked;
+            for (auto &kv : p.updates.account_nodes) acc.account_nodes[kv.first] = kv.second;
+            for (auto &kv : p.updates.storage_tries) acc.storage_tries[kv.first] = kv.second;
+            if (p.complete) {
+                CHECK(!p.state && p.root == oroot);
+                break;
+            }
+            CHECK(p.state != nullptr);
+            CHECK(p.state->checkpoint().resume_nibble <= 16);
+            inter = p.state;
+        }
+        CHECK(walked == f.n_accounts() + f.slot_keys.size() / 32);
+        CHECK(acc.account_nodes == upd.account_nodes);
+        CHECK(acc.storage_tries.size() == upd.storage_tries.size());
+        for (auto &kv : upd.storage_tries) CHECK(acc.storage_tries.at(kv.first).storage_nodes == kv.second.storage_nodes);
+        CHECK((steps == 1) == (threshold >= walked));
+    }
     // rows laid out on the device == rows the host encoder makes of the same build's TrieUpdates
     {
         for (b200_key_format fmt : {B200_KEYS_LEGACY, B200_KEYS_PACKED}) {
@@ -211,7 +237,7 @@ static void random_state_vs_oracle(const Engine &e) {
 
 // DynamicTrie: blocks of inserts / deletes / updates applied in place == oracle root over the merged state, and the
 // node set {previous - removed + updated} == the oracle's stored nodes (the incremental == full criterion of
-// crates/trie/db/tests/trie.rs:680-717).  Opt-in on a GPU until the first validated B200 run (tests/test_gpu_dtrie.py).
+// crates/trie/db/tests/trie.rs:680-717).
 static void dynamic_trie_blocks(const Engine &e) {
     std::mt19937_64 rng(7);
     std::map<B256, b200_account> state;

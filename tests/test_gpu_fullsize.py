@@ -150,3 +150,50 @@ def test_c4_mainnet_shape_small_vs_oracle(eng):
     root, au, su = eng.state_root_full(*args, want_updates=True)
     o_root, o_au, o_su = oracle.state_root_full(*args, want_updates=True, threads=8)
     assert root == o_root and au == o_au and su == o_su
+
+
+def test_c3_streamed_pushes_equal_one_shot_with_updates(eng):
+    """a14 at the C3 shape (1M accounts x 16 slots): the state pushed in 11 account-key ranges through b200_root_stream_* ==
+    one b200_state_root_full call — the root, and the stored nodes (TrieUpdates) as multisets of records."""
+    import hashlib
+
+    import torch
+
+    from bench import make_c3_shard
+    from reth_b200 import ACCOUNT_DTYPE, RootStream
+    dev = torch.device("cuda", 0)
+    n_acc, slots = 1_000_000, 16
+    sh = make_c3_shard(3, n_acc, slots, 0, 16, dev)
+    akeys = sh["akeys"].view(n_acc, 32).cpu().numpy()
+    accts = sh["accts"].view(n_acc, 72).cpu().numpy().view(ACCOUNT_DTYPE).reshape(-1)
+    skeys = sh["skeys"].view(-1, 32).cpu().numpy()
+    svals = sh["svals"].view(-1, 32).cpu().numpy()
+    offs = sh["offs"].cpu().numpy().astype(np.uint64)
+    del sh
+    eng.set_stream(None)
+    root, au, su = eng.state_root_full(akeys, accts, skeys, svals, offs, want_updates=True)
+
+    def digest(acct_recs, stor_recs):
+        # order-independent fingerprint of the record sets (storage records keyed by the owning account's key)
+        ha, hs = 0, 0
+        for r in acct_recs:
+            ha ^= int.from_bytes(hashlib.blake2b(repr((bytes(r[1]), r[2], r[3], r[4], r[5])).encode(), digest_size=16).digest(), "big")
+        for key, r in stor_recs:
+            hs ^= int.from_bytes(hashlib.blake2b(repr((key, bytes(r[1]), r[2], r[3], r[4], r[5])).encode(), digest_size=16).digest(), "big")
+        return ha, hs, len(acct_recs), len(stor_recs)
+
+    want = digest(au, [(akeys[r[0]].tobytes(), r) for r in su])
+    cuts = [0, 1, 90_000, 250_000, 250_001, 400_000, 555_555, 700_000, 812_345, 950_000, 999_999, n_acc]
+    s = RootStream(eng, retain_updates=True)
+    acct_recs, stor_recs = [], []
+    for a0, a1 in zip(cuts[:-1], cuts[1:]):
+        s0, s1 = int(offs[a0]), int(offs[a1])
+        prog, a_r, s_r = s.push(akeys[a0:a1], accts[a0:a1], skeys[s0:s1], svals[s0:s1], (offs[a0:a1 + 1] - offs[a0]).astype(np.uint64))
+        assert prog["accounts"] == a1 and prog["open_accounts"] <= n_acc // 8
+        acct_recs += a_r
+        stor_recs += [(akeys[a0 + r[0]].tobytes(), r) for r in s_r]
+    s_root, a_r = s.finish()
+    acct_recs += a_r
+    s.close()
+    assert s_root == root
+    assert digest(acct_recs, stor_recs) == want
