@@ -87,8 +87,12 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
     uint8_t *head = static_cast<uint8_t *>(c->head.p);
     uint32_t *node_start = static_cast<uint32_t *>(c->node_start.p);
 
+    auto mark = [&](const char *name) {  // phase marks of the structure pass (serial mode only: they record on c->stream)
+        if (c->phase_timing && sa == st) phase_mark(c, name);
+    };
     CU(launch_iota(static_cast<uint32_t *>(c->iota.p), G, 1, sa));
     c->launches++;
+    mark("s:iota");
     size_t t_sort = 0, t_sel = 0, t_scan = 0;
     CU(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, f.Lp + 1, depth_sorted, static_cast<uint32_t *>(c->iota.p),
                                        gap_sorted, (int64_t)G, 0, 8, sa));
@@ -105,13 +109,17 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
     ENSURE(cub_temp, t_max);
     CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_sort, f.Lp + 1, depth_sorted,
                                        static_cast<uint32_t *>(c->iota.p), gap_sorted, (int64_t)G, 0, 8, sa));
+    mark("s:gap-sort");
     CU(launch_bucket_offsets(depth_sorted, G, bucket_off, sa));
     if (d_seg_offsets)
         CU(cub::DeviceScan::InclusiveSum(c->cub_temp.p, t_scan, bflags, bound_rank, (int64_t)(n + 1), sa));
     CU(cudaMemsetAsync(head, 0, G, sa));
-    CU(launch_head_flags(d_keys, depth_sorted, gap_sorted, bound_rank, bucket_off + 64, G, head, sa));
+    mark("s:offsets+scan");
+    CU(launch_head_flags(d_keys, f.Lp, depth_sorted, gap_sorted, bound_rank, bucket_off + 64, G, head, sa));
+    mark("s:head-flags");
     CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, head, node_start, n_nodes_p, (int64_t)G, sa));
     CU(launch_level_ranges(node_start, n_nodes_p, bucket_off, level_lo, sa));
+    mark("s:select+ranges");
     // (depth, child-count class) of every node + histogram, still without knowing the node count on the host
     ENSURE(node_key, G);
     ENSURE(node_ids, G * 4);
@@ -121,11 +129,13 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
     CU(cudaMemsetAsync(hist, 0, 256 * 4, sa));
     CU(launch_node_class_keys(node_start, depth_sorted, n_nodes_p, G, nk, nids, hist, sa));
     c->launches += 9;
+    mark("s:class-keys");
     uint32_t *h_level = static_cast<uint32_t *>(c->pinned_small) + 64;
     uint32_t *h_hist = static_cast<uint32_t *>(c->pinned_small) + 256;
     CU(cudaMemcpyAsync(h_level, level_lo, 66 * 4, cudaMemcpyDeviceToHost, sa));
     CU(cudaMemcpyAsync(h_hist, hist, 256 * 4, cudaMemcpyDeviceToHost, sa));
     CU(cudaStreamSynchronize(sa));  // the only host round trip of a build: 322 integers (the leaf pass keeps running)
+    mark("s:readback");
     const uint32_t B = h_level[65];
     out.n_nodes = B;
     f.gap_sorted = gap_sorted;

@@ -62,11 +62,11 @@ cudaError_t launch_bucket_offsets(const uint8_t *depth_sorted, uint64_t G, uint3
     bucket_offsets_kernel<<<1, 96, 0, st>>>(depth_sorted, G, bucket_off);
     return cudaGetLastError();
 }
-cudaError_t launch_head_flags(const uint8_t *keys, const uint8_t *depth_sorted, const uint32_t *gap_sorted,
+cudaError_t launch_head_flags(const uint8_t *keys, const uint8_t *Lp, const uint8_t *depth_sorted, const uint32_t *gap_sorted,
                               const uint32_t *bound_rank, const uint32_t *G_real_p, uint64_t G, uint8_t *head,
                               cudaStream_t st) {
     if (G == 0) return cudaSuccess;
-    head_flags_kernel<<<blocks_for(G, 256), 256, 0, st>>>(keys, depth_sorted, gap_sorted, bound_rank, G_real_p, G, head);
+    head_flags_kernel<<<blocks_for(G, 256), 256, 0, st>>>(keys, Lp, depth_sorted, gap_sorted, bound_rank, G_real_p, G, head);
     return cudaGetLastError();
 }
 cudaError_t launch_level_ranges(uint32_t *node_start, const uint32_t *n_nodes_p, const uint32_t *bucket_off,

@@ -81,7 +81,7 @@ __global__ void bucket_offsets_kernel(const uint8_t *__restrict__ depth_sorted, 
 }
 
 // head[j] = 1 iff sorted gap j starts a new branch node
-__global__ void head_flags_kernel(const uint8_t *__restrict__ keys, const uint8_t *__restrict__ depth_sorted,
+__global__ void head_flags_kernel(const uint8_t *__restrict__ keys, const uint8_t *__restrict__ Lp, const uint8_t *__restrict__ depth_sorted,
                                   const uint32_t *__restrict__ gap_sorted, const uint32_t *__restrict__ bound_rank,
                                   const uint32_t *__restrict__ G_real_p, uint64_t G, uint8_t *__restrict__ head) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,6 +94,12 @@ __global__ void head_flags_kernel(const uint8_t *__restrict__ keys, const uint8_
         if (same_seg) {
             if (gp + 1 == g) {
                 h = false;  // the single leaf gp is a child between the two gaps
+            } else if (g - gp <= 33) {
+                // short span (the rule in forests of small tries): leaves gp .. g-1 share > d nibbles iff every gap between
+                // them is deeper than d — a few consecutive bytes of Lp (L2-resident) instead of two random 32-byte key rows
+                bool deeper = true;
+                for (uint32_t q = gp + 1; q < g; q++) deeper = deeper && Lp[q] > d;
+                h = !deeper;
             } else {
                 // leaves gp .. g-1 form one child iff they share > d nibbles
                 uint32_t a[8], b[8];

@@ -80,7 +80,7 @@ cudaError_t launch_mark_boundaries(const uint64_t *d_seg_offsets, uint64_t n_seg
 cudaError_t launch_lcp(const uint8_t *keys, uint64_t n, uint8_t *Lp, uint8_t *nibs, int *err, cudaStream_t st);
 cudaError_t launch_iota(uint32_t *out, uint64_t n, uint32_t first, cudaStream_t st);
 cudaError_t launch_bucket_offsets(const uint8_t *depth_sorted, uint64_t G, uint32_t *bucket_off, cudaStream_t st);
-cudaError_t launch_head_flags(const uint8_t *keys, const uint8_t *depth_sorted, const uint32_t *gap_sorted,
+cudaError_t launch_head_flags(const uint8_t *keys, const uint8_t *Lp, const uint8_t *depth_sorted, const uint32_t *gap_sorted,
                               const uint32_t *bound_rank, const uint32_t *G_real_p, uint64_t G, uint8_t *head,
                               cudaStream_t st);
 cudaError_t launch_level_ranges(uint32_t *node_start, const uint32_t *n_nodes_p, const uint32_t *bucket_off,
