@@ -376,6 +376,11 @@ B200_API int32_t b200_state_root_sharded(b200_comm *, const uint8_t *acct_keys32
 B200_API int32_t b200_state_root_sharded_dev(b200_comm *, const void *d_acct_keys32, const void *d_accts, uint64_t n_accounts,
                                              const void *d_slot_keys32, const void *d_values32_be, const void *d_seg_offsets,
                                              uint64_t n_slots, void *d_root32);
+/* The live path at N > 1: every rank has applied its part of the block to its shard (b200_dstate_create_sharded +
+ * b200_dstate_apply); this gathers the resident 16-entry frontiers of all ranks (one ncclAllGather) and returns the state root
+ * on every rank.  (b200_dstate is declared further down.) */
+struct b200_dstate;
+B200_API int32_t b200_dstate_root_sharded(b200_comm *, struct b200_dstate *, uint8_t root32[32]);
 /* AccountHashingStage / StorageHashingStage at N > 1 (hashing_account.rs:176-238, hashing_storage.rs:106-178; SURVEY.md §8e
  * last sentence): every rank holds an arbitrary slice of the plain table — n messages (msg_len 20 | 32) with one
  * value_bytes-wide row each (the account, the slot value; may be 0).  One call hashes them, sends every (digest, row) to the

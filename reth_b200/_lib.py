@@ -174,6 +174,7 @@ def load():
     sig("b200_comm_size", i32, vp)
     sig("b200_state_root_sharded", i32, vp, vp, vp, u64, vp, vp, vp, vp, PS)
     sig("b200_state_root_sharded_dev", i32, vp, vp, vp, u64, vp, vp, vp, u64, vp)
+    sig("b200_dstate_root_sharded", i32, vp, vp, vp)
     sig("b200_hash_partition_dev", i32, vp, vp, C.c_uint32, C.c_uint32, u64, vp, C.c_uint32, u64, vp, vp, C.POINTER(C.c_uint64))
     sig("b200_root_from_items", i32, vp, vp, vp, vp, vp, vp, vp, u64, u64, i32, vp, PU, PS)
     sig("b200_hash_changesets", i32, vp, vp, u64, vp, vp, u64, C.POINTER(ChangesetHashes))

@@ -191,6 +191,28 @@ extern "C" B200_API int32_t b200_state_root_sharded(b200_comm *m, const uint8_t 
     return r;
 }
 
+// The sharded dynamic state (b200_dstate_create_sharded): after every rank has applied its part of a block, one all-gather of
+// the resident frontiers and the root — the per-block exchange of the live path at N > 1.
+extern "C" B200_API int32_t b200_dstate_root_sharded(b200_comm *m, b200_dstate *t, uint8_t root32[32]) {
+    if (!m || !t || !root32) return B200_ERR_INVALID_ARG;
+    b200_ctx *c = m->c;
+    if (t->c != c) return fail(c, B200_ERR_INVALID_ARG, "the state and the communicator belong to different contexts");
+    if (!t->sharded) return fail(c, B200_ERR_INVALID_ARG, "not a sharded state (b200_dstate_create_sharded)");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    const size_t fb = 16 * sizeof(FrontierEntryDev);
+    TRY(ensure(c, m->all, fb * m->world));
+    TRY(ensure(c, m->merged, fb + 64));
+    NC(nccl_api().AllGather(t->frontier.p, m->all.p, fb, ncclChar, m->comm, c->stream));
+    CU(launch_merge_frontiers(static_cast<const FrontierEntryDev *>(m->all.p), m->world, static_cast<FrontierEntryDev *>(m->merged.p),
+                              reinterpret_cast<int *>(small_u32(c) + SM_ERR), c->stream));
+    uint8_t *d_root = static_cast<uint8_t *>(m->merged.p) + align_up(fb, 16);
+    CU(launch_root_from_frontier(static_cast<const FrontierEntryDev *>(m->merged.p), d_root, c->stream));
+    c->launches += 2;
+    CU(cudaMemcpyAsync(root32, d_root, 32, cudaMemcpyDeviceToHost, c->stream));
+    return sync_and_status(c);
+}
+
 // keccak of this rank's n messages, every (digest, row) sent to the rank that owns the digest's top nibble, what arrives
 // sorted by digest.  d_sorted_keys32 / d_sorted_values must hold `capacity` rows; *n_out = rows this rank now owns.
 extern "C" B200_API int32_t b200_hash_partition_dev(b200_comm *m, const void *d_in, uint32_t msg_len, uint32_t stride, uint64_t n,
@@ -297,4 +319,5 @@ extern "C" B200_API int32_t b200_state_root_sharded(b200_comm *, const uint8_t *
                                                     const uint8_t *, const uint64_t *, uint8_t *, b200_stats *) { return B200_ERR_CUDA; }
 extern "C" B200_API int32_t b200_hash_partition_dev(b200_comm *, const void *, uint32_t, uint32_t, uint64_t, const void *, uint32_t,
                                                     uint64_t, void *, void *, uint64_t *) { return B200_ERR_CUDA; }
+extern "C" B200_API int32_t b200_dstate_root_sharded(b200_comm *, b200_dstate *, uint8_t *) { return B200_ERR_CUDA; }
 #endif

@@ -460,6 +460,12 @@ class Comm:
                                                                        t_skeys.data_ptr(), t_svals.data_ptr(), t_offs.data_ptr(),
                                                                        n_slots, t_root.data_ptr()))
 
+    def dstate_root_sharded(self, dstate) -> bytes:
+        """b200_dstate_root_sharded: after every rank applied its part of a block to its shard, the state root (all ranks)."""
+        root = np.empty(32, np.uint8)
+        self.engine._check(self.engine.lib.b200_dstate_root_sharded(self.handle, dstate.handle, _ptr(root)))
+        return root.tobytes()
+
     def hash_partition_dev(self, t_in, msg_len: int, stride: int, n: int, t_values, value_bytes: int, capacity: int, t_keys_out,
                            t_values_out) -> int:
         n_out = C.c_uint64(0)

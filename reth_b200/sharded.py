@@ -22,12 +22,13 @@ def owner_of(key: bytes, world: int) -> int:
 
 
 class ShardedDynamicStateRoot:
-    def __init__(self, engine: Engine, state: HashedPostState, rank: int, world: int, group=None):
+    def __init__(self, engine: Engine, state: HashedPostState, rank: int, world: int, group=None, comm=None):
         """state: the full initial hashed state (every rank may pass the same object; only its buckets are kept) or
-        already just this rank's part."""
+        already just this rank's part.  comm: a reth_b200.Comm — the frontier exchange then runs inside the library
+        (b200_dstate_root_sharded, NCCL) instead of through torch.distributed."""
         if 16 % world and world > 16:
             raise ValueError("at most 16 ranks (one top-nibble bucket each)")
-        self.engine, self.rank, self.world, self.group = engine, rank, world, group
+        self.engine, self.rank, self.world, self.group, self.comm = engine, rank, world, group, comm
         mine = HashedPostState({k: a for k, a in state.accounts.items() if owner_of(k, world) == rank},
                                {k: s for k, s in state.storages.items() if owner_of(k, world) == rank})
         self.local = DynamicStateRoot(engine, mine.into_sorted(), sharded=True)
@@ -37,6 +38,8 @@ class ShardedDynamicStateRoot:
         return self._root
 
     def _gather_root(self) -> bytes:
+        if self.comm is not None:
+            return self.comm.dstate_root_sharded(self.local.ds)
         import torch
         import torch.distributed as dist
         fr = self.local.ds.frontier()                                  # (16, 68) uint8, empty outside this rank's buckets

@@ -89,3 +89,53 @@ def test_hash_partition_two_ranks():
         idx = order[owner[order] == r]                                # the whole table hashed + sorted, this rank's buckets
         assert (res[r][0] == dig[idx]).all()
         assert (res[r][1] == rows[idx]).all()
+
+
+@pytest.mark.skipif(not _two_gpus(), reason="needs 2 GPUs")
+def test_sharded_dynamic_state_two_ranks():
+    """The live path at N = 2: every rank keeps its top-nibble buckets resident (b200_dstate_create_sharded), applies its part
+    of each block in place and b200_dstate_root_sharded gathers the frontiers (NCCL inside the library): the root equals the
+    oracle's from-scratch StateRoot over the merged state after every block."""
+    from reth_b200 import Account, HashedPostState, HashedStorage, ShardedDynamicStateRoot
+    rng = np.random.default_rng(44)
+    rk = lambda: bytes(rng.integers(0, 256, 32, dtype=np.uint8))
+    base = HashedPostState()
+    for _ in range(1500):
+        k = rk()
+        base.accounts[k] = Account(int(rng.integers(0, 9)), int(rng.integers(0, 2**60)), None)
+        if rng.random() < 0.3:
+            base.storages[k] = HashedStorage(False, {rk(): int(rng.integers(1, 2**62)) for _ in range(int(rng.integers(1, 12)))})
+    blocks = []
+    live = sorted(base.accounts)
+    for step in range(3):
+        b = HashedPostState()
+        for k in [live[int(i)] for i in rng.choice(len(live), 40, replace=False)]:
+            r = rng.random()
+            if r < 0.5:
+                b.accounts[k] = Account(step + 10, int(rng.integers(0, 2**60)), None)
+            elif r < 0.7:
+                b.accounts[k] = None
+                b.storages[k] = HashedStorage(True, {})
+            else:
+                b.storages[k] = HashedStorage(False, {rk(): int(rng.integers(1, 2**62)) for _ in range(4)})
+        for _ in range(10):
+            b.accounts[rk()] = Account(0, 7, None)
+        blocks.append(b)
+    # expected roots: from-scratch oracle StateRoot over the merged state after every block
+    merged = HashedPostState(dict(base.accounts), {k: HashedStorage(False, dict(s.storage)) for k, s in base.storages.items()})
+    want = []
+    for b in blocks:
+        merged.extend(b)
+        post = HashedPostState({k: a for k, a in merged.accounts.items() if a is not None},
+                               {k: HashedStorage(False, {s: v for s, v in st.storage.items() if v != 0})
+                                for k, st in merged.storages.items() if merged.accounts.get(k) is not None})
+        want.append(oracle.state_root_full(*post.into_sorted().to_flat(), threads=4))
+
+    def rank_main(r, eng, comm):
+        sh = ShardedDynamicStateRoot(eng, base, r, 2, comm=comm)
+        roots = [sh.commit(b)[0] for b in blocks]
+        sh.close()
+        return roots
+
+    res = _run_ranks(2, rank_main)
+    assert res[0] == want and res[1] == want

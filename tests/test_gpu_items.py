@@ -185,3 +185,32 @@ def test_state_incremental_equals_full(eng):
         assert tables.account_nodes == full_tables.account_nodes
         rows = lambda t: {k: v.storage_nodes for k, v in t.storage_tries.items() if v.storage_nodes}
         assert rows(tables) == rows(full_tables)
+
+
+def test_malformed_streams_are_rejected(eng):
+    """A leaf below a hash item (the walker never yields that), descending keys, key_nibbles > 64: errors, not garbage."""
+    from reth_b200 import B200Error, _lib
+    h = oracle.keccak256(b"x")
+    keys = np.zeros((2, 32), np.uint8)
+    keys[0, 0] = 0xA0                      # hash item at path [a]
+    keys[1, 0] = 0xA5                      # a leaf below it
+    nib = np.array([1, 64], np.uint8)
+    fl = np.zeros(2, np.uint8)
+    vals = np.zeros((2, 32), np.uint8)
+    vals[0] = np.frombuffer(h, np.uint8)
+    vals[1, 31] = 7
+    with pytest.raises(B200Error) as e:
+        eng.root_from_items(keys, nib, fl, vals, None, None, account=False)
+    assert e.value.status == _lib.ERR_UNSORTED
+    with pytest.raises(B200Error) as e:
+        eng.root_from_items(keys[::-1].copy(), nib[::-1].copy(), fl, vals[::-1].copy(), None, None, account=False)
+    assert e.value.status == _lib.ERR_UNSORTED
+    with pytest.raises(B200Error) as e:
+        eng.root_from_items(keys, np.array([1, 65], np.uint8), fl, vals, None, None, account=False)
+    assert e.value.status == _lib.ERR_INVALID_ARG
+    # the context stays usable: a lone hash at the empty path is the root itself, a lone hash deeper hangs under an extension
+    k1 = np.zeros((1, 32), np.uint8)
+    assert eng.root_from_items(k1, np.array([0], np.uint8), fl[:1], vals[:1], None, None, account=False)[0].tobytes() == h
+    hb = oracle.HashBuilder()
+    hb.add_branch(bytes([0xA]), h, False)
+    assert eng.root_from_items(keys[:1], nib[:1], fl[:1], vals[:1], None, None, account=False)[0].tobytes() == hb.root()

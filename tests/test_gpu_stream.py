@@ -223,3 +223,24 @@ def test_merkle_stage_chunked_rebuild(eng):
     # applies every step to the tables: compare the rows)
     rows = lambda tu: {k: v.storage_nodes for k, v in tu.storage_tries.items() if v.storage_nodes}
     assert rows(t2.trie_updates) == rows(t1.trie_updates)
+
+
+def test_stream_misuse_is_an_error(eng):
+    from reth_b200 import B200Error, RootStream, _lib
+    akeys, accs = synth_accounts(12, 10)
+    z = np.zeros((0, 32), np.uint8)
+    offs = np.zeros(11, np.uint64)
+    s = RootStream(eng)
+    s.push(akeys, accs, z, z, offs)
+    root = s.finish()
+    assert root == oracle.state_root(akeys, accs)
+    for call in (lambda: s.finish(), lambda: s.push(akeys, accs, z, z, offs)):
+        with pytest.raises(B200Error) as e:
+            call()
+        assert e.value.status == _lib.ERR_INVALID_ARG
+    s.close()
+    with pytest.raises(B200Error):                      # a checkpoint that claims a closed bucket at or after the resume point
+        cp = bytearray(RootStream(eng).checkpoint())
+        cp[1088:1092] = (1 << 5).to_bytes(4, "little")   # closed_mask: bucket 5
+        cp[1092:1096] = (3).to_bytes(4, "little")        # resume_nibble 3
+        RootStream.resume(eng, bytes(cp))
