@@ -144,3 +144,66 @@ def storage_trie_rows(records, acct_keys, key_format: int = KEYS_LEGACY) -> list
     if rc:
         raise B200Error(rc, "b200_storage_trie_rows")
     return _slice_rows(rows, lib)
+
+
+# ------------------------------------------------------------------------------------------------ checkpoint codecs (host)
+def branch_node_compact_to_bytes(node) -> bytes:
+    """`Compact for BranchNodeCompact` (alloy-trie; the value bytes of an AccountsTrie / StoragesTrie row): the three masks
+    as big-endian u16, the root hash if present, then the child hashes."""
+    out = bytearray()
+    for m in (node.state_mask, node.tree_mask, node.hash_mask):
+        out += int(m).to_bytes(2, "big")
+    if getattr(node, "root_hash", None):
+        out += node.root_hash
+    for h in node.hashes:
+        out += h
+    return bytes(out)
+
+
+def branch_node_compact_from_bytes(buf: bytes):
+    """Inverse; the root hash is present iff there is one more 32-byte word than hash_mask has bits (alloy-trie's rule)."""
+    from .trie import BranchNodeCompact
+    if len(buf) < 6 or (len(buf) - 6) % 32:
+        raise ValueError("BranchNodeCompact: 6 bytes of masks followed by 32-byte hashes")
+    sm, tm, hm = (int.from_bytes(buf[i:i + 2], "big") for i in (0, 2, 4))
+    words = [buf[6 + 32 * i:38 + 32 * i] for i in range((len(buf) - 6) // 32)]
+    n = bin(hm).count("1")
+    if len(words) == n + 1:
+        return BranchNodeCompact(sm, tm, hm, tuple(words[1:]), words[0])
+    if len(words) != n:
+        raise ValueError("BranchNodeCompact: hash count does not match hash_mask")
+    return BranchNodeCompact(sm, tm, hm, tuple(words), None)
+
+
+class StoredSubNode:
+    """crates/trie/common/src/subnode.rs:5-14 — one element of the walker stack inside reth's MerkleCheckpoint, with its
+    Compact codec (:16-67): u16 key length, key, option flag + nibble, option flag + BranchNodeCompact.  This engine's own
+    checkpoint is b200_stream_checkpoint; the codec is here so that a host can read and write reth's rows."""
+
+    def __init__(self, key: bytes = b"", nibble=None, node=None):
+        self.key, self.nibble, self.node = bytes(key), nibble, node
+
+    def __eq__(self, o):
+        return (self.key, self.nibble, self.node) == (o.key, o.nibble, o.node)
+
+    def to_compact(self) -> bytes:
+        out = bytearray(len(self.key).to_bytes(2, "big")) + self.key
+        out += bytes([1, self.nibble]) if self.nibble is not None else b"\x00"
+        if self.node is not None:
+            out += b"\x01" + branch_node_compact_to_bytes(self.node)
+        else:
+            out += b"\x00"
+        return bytes(out)
+
+    @classmethod
+    def from_compact(cls, buf: bytes) -> "StoredSubNode":
+        n = int.from_bytes(buf[:2], "big")
+        key, p = buf[2:2 + n], 2 + n
+        nibble = None
+        if buf[p]:
+            nibble = buf[p + 1]
+            p += 2
+        else:
+            p += 1
+        node = branch_node_compact_from_bytes(buf[p + 1:]) if buf[p] else None
+        return cls(key, nibble, node)
