@@ -212,8 +212,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ roofline
-ALU_INSTR_PER_KECCAK_F = 4150.0  # LOP3 + SHF per permutation of the register sponge (cuobjdump of keccak256_fixed32_kernel:
-                                 # 24 rounds x (122 LOP3 + 58 SHF) minus what the peeled first / last rounds fold away)
+ALU_INSTR_PER_KECCAK_F = 4220.0  # ALU-pipe instructions per digest of keccak256_fixed32_kernel counted from its SASS
+                                 # (tools/sass_count.py -> profiles/r02_keccak_sass_count.txt: 132 + 22 x 183 + 62; ncu
+                                 # counts 4286 instructions of all kinds per digest, profiles/r02_keccak32.md)
 ALU_LANES_PER_CLK_PER_SM = 64.0  # measured: profiles/r01_pipe_microbench.txt
 
 
@@ -239,7 +240,7 @@ def make_roofline(algo_bytes: float, seconds: float, keccak_f: float, sm_mhz, tr
     r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
          "traffic": traffic_of(traffic_key), "kernel": kernel, "peak_source": src,
          "algorithmic_bytes_per_launch": algo_bytes, "keccak_f_per_launch": keccak_f, "alu_frac": None,
-         "note": "Keccak-f is ALU-bound (~4150 LOP3/SHF per permutation on the 64-lane/clk/SM ALU pipe): alu_frac is the binding roofline"}
+         "note": "Keccak-f is ALU-bound (~4220 ALU-pipe instructions per permutation on the 64-lane/clk/SM ALU pipe): alu_frac is the binding roofline"}
     if sm_mhz:
         alu_peak = n_sms * ALU_LANES_PER_CLK_PER_SM * sm_mhz * 1e6 / ALU_INSTR_PER_KECCAK_F
         r["alu_peak_keccak_f_per_s"] = alu_peak
