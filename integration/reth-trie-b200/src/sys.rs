@@ -72,6 +72,29 @@ pub struct b200_rows {
 pub const B200_KEYS_LEGACY: i32 = 0;
 pub const B200_KEYS_PACKED: i32 = 1;
 
+// ---- round-2 entry points (include/b200trie.h): stream, items, changesets, communicator, multiproof
+#[repr(C)] pub struct b200_root_stream { _p: [u8; 0] }
+#[repr(C)] pub struct b200_comm { _p: [u8; 0] }
+#[repr(C)] #[derive(Default, Clone, Copy)]
+pub struct b200_stream_progress { pub accounts: u64, pub slots: u64, pub open_accounts: u64, pub closed_buckets: u32 }
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct b200_stream_checkpoint {
+    pub frontier: [b200_frontier_entry; 16], pub closed_mask: u32, pub resume_nibble: u32, pub retain_updates: u32, pub _reserved: u32,
+}
+#[repr(C)]
+pub struct b200_changeset_hashes {
+    pub n_accounts: u64, pub account_keys32: *mut u8, pub account_first: *mut u32,
+    pub n_storage_accounts: u64, pub storage_account_keys32: *mut u8, pub storage_seg_offsets: *mut u64,
+    pub n_slots: u64, pub slot_keys32: *mut u8, pub slot_first: *mut u32,
+    pub n_prefix: u64, pub account_prefix_keys32: *mut u8, pub _owner: *mut c_void,
+}
+#[repr(C)]
+pub struct b200_proofs {
+    pub n_targets: u64, pub node_offset: *mut u64, pub n_nodes: u64, pub rlp_offset: *mut u64, pub rlp: *mut u8,
+    pub node_depth: *mut u8, pub _owner: *mut c_void,
+}
+pub const B200_COMM_ID_BYTES: usize = 128;
+
 pub const B200_OK: i32 = 0;
 pub const B200_ERR_NOT_FOUND: i32 = -8;
 
@@ -131,4 +154,41 @@ unsafe extern "C" {
     /// transactions / receipts / withdrawals roots of a batch of lists (ordered_root.rs:240-257 per list)
     pub fn b200_ordered_roots(ctx: *mut b200_ctx, values: *const u8, value_offsets: *const u64, seg_offsets: *const u64,
                               n_lists: u64, roots32: *mut u8, opt_stats: *mut b200_stats) -> i32;
+
+    /// StateRoot::with_threshold / root_with_progress / with_intermediate_state; MerkleStage's chunked rebuild + MerkleCheckpoint
+    pub fn b200_root_stream_begin(ctx: *mut b200_ctx, retain_updates: i32, out: *mut *mut b200_root_stream) -> i32;
+    pub fn b200_root_stream_push(s: *mut b200_root_stream, acct_keys32: *const u8, accts: *const b200_account, n_accounts: u64,
+                                 slot_keys32: *const u8, values32_be: *const u8, seg_offsets: *const u64,
+                                 account_updates: *mut b200_updates, storage_updates: *mut b200_updates,
+                                 progress: *mut b200_stream_progress) -> i32;
+    pub fn b200_root_stream_finish(s: *mut b200_root_stream, root32: *mut u8, account_updates: *mut b200_updates) -> i32;
+    pub fn b200_root_stream_checkpoint(s: *const b200_root_stream, out: *mut b200_stream_checkpoint) -> i32;
+    pub fn b200_root_stream_resume(ctx: *mut b200_ctx, cp: *const b200_stream_checkpoint, out: *mut *mut b200_root_stream) -> i32;
+    pub fn b200_root_stream_free(s: *mut b200_root_stream);
+    /// the fold of TrieNodeIter's element stream: HashBuilder::add_leaf / add_branch (trie.rs:247-309,659-698)
+    pub fn b200_root_from_items(ctx: *mut b200_ctx, keys32: *const u8, key_nibbles: *const u8, item_flags: *const u8,
+                                values: *const u8, storage_roots32: *const u8, seg_offsets: *const u64, n_segs: u64,
+                                n_items: u64, account: i32, roots32: *mut u8, updates: *mut b200_updates, stats: *mut b200_stats) -> i32;
+    /// HashedPostStateSorted::from_reverts + load_prefix_sets_with_provider over the changesets of a block range
+    pub fn b200_hash_changesets(ctx: *mut b200_ctx, acct_addresses20: *const u8, n_acct: u64, storage_addresses20: *const u8,
+                                storage_slots32: *const u8, n_storage: u64, out: *mut b200_changeset_hashes) -> i32;
+    pub fn b200_changeset_hashes_release(o: *mut b200_changeset_hashes);
+    /// the two exchange steps of the path (NCCL behind the C ABI)
+    pub fn b200_comm_unique_id(id: *mut u8) -> i32;
+    pub fn b200_comm_create(ctx: *mut b200_ctx, id: *const u8, n_ranks: i32, rank: i32, out: *mut *mut b200_comm) -> i32;
+    pub fn b200_comm_destroy(comm: *mut b200_comm);
+    pub fn b200_state_root_sharded(comm: *mut b200_comm, acct_keys32: *const u8, accts: *const b200_account, n_accounts: u64,
+                                   slot_keys32: *const u8, values32_be: *const u8, seg_offsets: *const u64, root32: *mut u8,
+                                   stats: *mut b200_stats) -> i32;
+    pub fn b200_dstate_root_sharded(comm: *mut b200_comm, state: *mut b200_dstate, root32: *mut u8) -> i32;
+    pub fn b200_hash_partition_dev(comm: *mut b200_comm, d_in: *const c_void, msg_len: u32, stride: u32, n: u64,
+                                   d_values: *const c_void, value_bytes: u32, capacity: u64, d_sorted_keys32: *mut c_void,
+                                   d_sorted_values: *mut c_void, n_out: *mut u64) -> i32;
+    /// Proof::multiproof(MultiProofTargets) from the resident state
+    pub fn b200_dstate_multiproof(state: *mut b200_dstate, acct_keys32: *const u8, n_accounts: u64, slot_seg_offsets: *const u64,
+                                  slot_keys32: *const u8, account_proofs: *mut b200_proofs, storage_roots32: *mut u8,
+                                  storage_proofs: *mut b200_proofs) -> i32;
+    pub fn b200_proofs_release(p: *mut b200_proofs);
+    /// CPUs + preferred memory of the calling thread on the GPU's NUMA node (before allocating staging buffers)
+    pub fn b200_numa_bind_thread(device_ordinal: i32) -> i32;
 }
