@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Round-2 measurement aid for the dynamic resident state (b200_dstate_*).
 
-    B200_DTRIE_ON_GPU=1 python -m pytest tests/test_gpu_dstate.py tests/test_gpu_dtrie.py -m gpu -q   # correctness first
+    python -m pytest tests/test_gpu_dstate.py tests/test_gpu_dtrie.py -m gpu -q   # correctness first
     python tools/dstate_bench.py --accounts 1000000 --slots 16 --touch 2000 --slot-writes 10
 
 Seeds a state of --accounts accounts x --slots slots (the C3 shape), then commits blocks that touch --touch accounts:

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
-"""Round-2 measurement aid for the dynamic resident trie (b200_dtrie_*): first B200 validation + latency.
+"""Latency of the dynamic resident trie (b200_dtrie_*) on a B200 (a leg of bench.py).
 
-    B200_DTRIE_ON_GPU=1 python -m pytest tests/test_gpu_dtrie.py -m gpu -q      # correctness first
+    python -m pytest tests/test_gpu_dtrie.py -m gpu -q      # correctness first
     python tools/dtrie_bench.py --base 100000000 --dirty 10000 --mix 80,10,10   # then latency
 
 Builds a base trie of --base accounts on the device, then applies blocks of --dirty keys with the given

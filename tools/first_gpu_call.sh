@@ -1,11 +1,10 @@
 #!/usr/bin/env bash
-# First B200 run of the dynamic trie / state / proofs (validated under tools/emu only until now), then racecheck /
+# The run that first put the dynamic trie / state / proofs on a B200 (profiles/r02_first_gpu_call.log): tests, racecheck /
 # memcheck on them and their latency; everything under timeouts so a misbehaving kernel costs minutes, not the budget.
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/first_gpu_call.sh'
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-export B200_DTRIE_ON_GPU=1
 {
   echo "== gated GPU tests"
   timeout 600 python -m pytest tests/test_gpu_dtrie.py tests/test_gpu_dstate.py tests/test_gpu_proofs.py tests/test_gpu_host_mirror.py -m gpu -q 2>&1 | tail -25
