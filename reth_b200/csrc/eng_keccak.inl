@@ -20,6 +20,15 @@ extern "C" B200_API int32_t b200_keccak256_var_dev(b200_ctx *c, const void *d_da
     return B200_OK;
 }
 
+static uint64_t keccak_host_chunk() {  // messages per chunk of the host-pointer paths (B200_KECCAK_CHUNK overrides: tuning, tests)
+    static const uint64_t CHUNK = [] {
+        const char *e = getenv("B200_KECCAK_CHUNK");
+        uint64_t v = e ? strtoull(e, nullptr, 10) : 0;
+        return v >= 1024 ? v : (1ull << 19);
+    }();
+    return CHUNK;
+}
+
 // Host buffers: chunked over three streams so that the H2D copy of chunk k+2, the hashing of chunk k+1 and the D2H
 // copy of chunk k overlap (both DMA directions stay busy; fully asynchronous when the caller's buffers are
 // page-locked, see b200_host_alloc).
@@ -29,11 +38,7 @@ extern "C" B200_API int32_t b200_keccak256_fixed(b200_ctx *c, const uint8_t *in,
     if (n == 0) return B200_OK;
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
-    static const uint64_t CHUNK = [] {  // messages per chunk (B200_KECCAK_CHUNK overrides, for tuning)
-        const char *e = getenv("B200_KECCAK_CHUNK");
-        uint64_t v = e ? strtoull(e, nullptr, 10) : 0;
-        return v >= 1024 ? v : (1ull << 19);
-    }();
+    const uint64_t CHUNK = keccak_host_chunk();
     uint64_t chunk = n < CHUNK ? n : CHUNK;
     for (int i = 0; i < 3; i++) {
         TRY(ensure(c, c->chunk_in[i], chunk * stride));
@@ -108,6 +113,36 @@ extern "C" B200_API int32_t b200_sort_keys32_dev(b200_ctx *c, const void *d_keys
                                   c->sort_kb, c->sort_ia, c->sort_flag);
 }
 
+// Host messages -> device digests (n x 32, d_digests) with the H2D copy of chunk k+1 under the hashing of chunk k: the
+// hashing stages' inputs never sit in HBM as a whole, and the copy engine is busy from the first byte on.  The copy streams
+// start after whatever is queued on c->stream and c->stream continues after the last chunk.
+static int32_t hash_from_host(b200_ctx *c, const uint8_t *in, uint32_t msg_len, uint32_t stride, uint64_t n,
+                              uint8_t *d_digests) {
+    if (n == 0) return B200_OK;
+    const uint64_t chunk = n < keccak_host_chunk() ? n : keccak_host_chunk();
+    for (int i = 0; i < 3; i++) TRY(ensure(c, c->chunk_in[i], chunk * stride));
+    while (c->chunk_events.size() < 4) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->chunk_events.push_back(e);
+    }
+    CU(cudaEventRecord(c->chunk_events[3], c->stream));
+    for (int i = 0; i < 3; i++) CU(cudaStreamWaitEvent(c->copy_streams[i], c->chunk_events[3], 0));
+    int slot = 0;
+    for (uint64_t lo = 0; lo < n; lo += chunk, slot = (slot + 1) % 3) {
+        uint64_t m = n - lo < chunk ? n - lo : chunk;
+        cudaStream_t st = c->copy_streams[slot];
+        CU(cudaMemcpyAsync(c->chunk_in[slot].p, in + lo * stride, (m - 1) * (size_t)stride + msg_len, cudaMemcpyHostToDevice,
+                           st));
+        CU(launch_keccak256_fixed(c->chunk_in[slot].p, msg_len, stride, m, d_digests + lo * 32, st, &c->launches));
+    }
+    for (int i = 0; i < 3; i++) {
+        CU(cudaEventRecord(c->chunk_events[i], c->copy_streams[i]));
+        CU(cudaStreamWaitEvent(c->stream, c->chunk_events[i], 0));
+    }
+    return B200_OK;
+}
+
 extern "C" B200_API int32_t b200_hash_sort_keys(b200_ctx *c, const uint8_t *in, uint32_t msg_len, uint32_t stride, uint64_t n,
                                        uint8_t *out_sorted32, uint32_t *out_perm) {
     if (!c || (n && (!in || !out_sorted32 || !out_perm)) || stride < msg_len)
@@ -115,13 +150,10 @@ extern "C" B200_API int32_t b200_hash_sort_keys(b200_ctx *c, const uint8_t *in, 
     if (n == 0) return B200_OK;
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
-    size_t in_bytes = (n - 1) * (size_t)stride + msg_len;
-    ENSURE(in_a, in_bytes);
     ENSURE(out_a, n * 32);
     ENSURE(sort_out, n * 32);
     ENSURE(sort_perm, n * 4);
-    CU(cudaMemcpyAsync(c->in_a.p, in, in_bytes, cudaMemcpyHostToDevice, c->stream));
-    CU(launch_keccak256_fixed(c->in_a.p, msg_len, stride, n, c->out_a.p, c->stream, &c->launches));
+    TRY(hash_from_host(c, in, msg_len, stride, n, static_cast<uint8_t *>(c->out_a.p)));
     TRY(sort_digests_on_device(c, c->out_a.p, n, c->sort_out.p, static_cast<uint32_t *>(c->sort_perm.p), c->sort_ka,
                                c->sort_kb, c->sort_ia, c->sort_flag));
     CU(cudaMemcpyAsync(out_sorted32, c->sort_out.p, n * 32, cudaMemcpyDeviceToHost, c->stream));
@@ -144,17 +176,15 @@ extern "C" B200_API int32_t b200_hash_sort_storage(b200_ctx *c, const uint8_t *a
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
     ENSURE(in_a, (size_t)n_addr * 20);
-    ENSURE(in_b, n * 32);
     ENSURE(in_c, n * 4);
     ENSURE(in_d, (size_t)n_addr * 32);  // address digests
     ENSURE(out_a, n * 32);              // slot digests
     ENSURE(sort_out, n * 64);
     ENSURE(sort_perm, n * 4);
     CU(cudaMemcpyAsync(c->in_a.p, addresses20, (size_t)n_addr * 20, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->in_b.p, slots32, n * 32, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->in_c.p, addr_index, n * 4, cudaMemcpyHostToDevice, c->stream));
     CU(launch_keccak256_fixed(c->in_a.p, 20, 20, n_addr, c->in_d.p, c->stream, &c->launches));
-    CU(launch_keccak256_fixed(c->in_b.p, 32, 32, n, c->out_a.p, c->stream, &c->launches));
+    TRY(hash_from_host(c, slots32, 32, 32, n, static_cast<uint8_t *>(c->out_a.p)));
     TRY(sort_composite_on_device(c, c->in_d.p, n_addr, static_cast<const uint32_t *>(c->in_c.p), c->out_a.p, n,
                                  c->sort_out.p, static_cast<uint32_t *>(c->sort_perm.p), c->sort_ka, c->sort_kb,
                                  c->sort_ia, c->sort_flag));

@@ -25,6 +25,16 @@ def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
+def _out_array(a, shape, dtype):
+    """A result array: the caller's (checked: shape, dtype, C-contiguous, writeable) or a fresh one."""
+    if a is None:
+        return np.empty(shape, dtype)
+    if not isinstance(a, np.ndarray) or a.shape != tuple(shape) or a.dtype != np.dtype(dtype) \
+            or not a.flags.c_contiguous or not a.flags.writeable:
+        raise B200Error(_lib.ERR_INVALID_ARG, f"result array must be a writeable C-contiguous {np.dtype(dtype)}{tuple(shape)}")
+    return a
+
+
 def _unpack_nibbles(packed: bytes, n: int) -> bytes:
     return bytes(x for b in packed for x in (b >> 4, b & 15))[:n]
 
@@ -144,24 +154,25 @@ class Engine:
         d = np.frombuffer(bytes(data) or b"\0", np.uint8)
         return self.keccak256_var(d, np.array([0, len(data)], np.uint64))[0].tobytes()
 
-    def hash_sort_keys(self, msgs: np.ndarray, msg_len: int | None = None):
-        """-> (sorted digests uint8[n,32], perm uint32[n]): digest[perm[i]] is the i-th smallest."""
+    def hash_sort_keys(self, msgs: np.ndarray, msg_len: int | None = None, out=None, perm=None):
+        """-> (sorted digests uint8[n,32], perm uint32[n]): digest[perm[i]] is the i-th smallest.  `out` / `perm`: the
+        caller's result arrays (page-locked ones from pinned_empty make the read-back a plain DMA)."""
         msgs = _np(msgs)
         n, stride = msgs.shape
-        out = np.empty((n, 32), np.uint8)
-        perm = np.empty(n, np.uint32)
+        out = _out_array(out, (n, 32), np.uint8)
+        perm = _out_array(perm, (n,), np.uint32)
         self._check(self.lib.b200_hash_sort_keys(self.ctx, _ptr(msgs), msg_len or stride, stride, n, _ptr(out), _ptr(perm)))
         return out, perm
 
-    def hash_sort_storage(self, addresses: np.ndarray, addr_index: np.ndarray, slots: np.ndarray):
+    def hash_sort_storage(self, addresses: np.ndarray, addr_index: np.ndarray, slots: np.ndarray, out=None, perm=None):
         """StorageHashing full pass: entry i = (addresses[addr_index[i]], slots[i]) -> (composite keys uint8[n,64]
-        sorted ascending, perm uint32[n])."""
+        sorted ascending, perm uint32[n]).  `out` / `perm` as in hash_sort_keys."""
         addresses = _np(addresses).reshape(-1, 20)
         addr_index = _np(addr_index, np.uint32)
         slots = _np(slots).reshape(-1, 32)
         n = len(slots)
-        out = np.empty((n, 64), np.uint8)
-        perm = np.empty(n, np.uint32)
+        out = _out_array(out, (n, 64), np.uint8)
+        perm = _out_array(perm, (n,), np.uint32)
         self._check(self.lib.b200_hash_sort_storage(self.ctx, _ptr(addresses), len(addresses), _ptr(addr_index),
                                                     _ptr(slots), n, _ptr(out), _ptr(perm)))
         return out, perm

@@ -152,3 +152,53 @@ def test_hash_sort_storage_rejects_duplicates_and_bad_index(eng):
     with pytest.raises(B200Error) as e:
         eng.hash_sort_storage(addrs, owner, random_keys(7, 8))
     assert e.value.status == _lib.ERR_INVALID_ARG
+
+
+@pytest.mark.gpu
+def test_hash_sort_host_paths_in_chunks():
+    """The host-pointer hash+sort entry points copy and hash in chunks on the copy streams (eng_keccak.inl hash_from_host):
+    several chunks incl. a ragged last one, results in the caller's page-locked arrays, against the oracle.  Own process:
+    the chunk size is read once per process (B200_KECCAK_CHUNK)."""
+    import subprocess
+    import sys
+    from reth_b200 import _lib
+    code = "from reth_b200 import _lib\n_lib.LIB_PATH = %r   # (the emulation build under --emu)\n" % _lib.LIB_PATH + r"""
+import numpy as np, oracle
+from reth_b200 import Engine, B200Error
+from tests.util import random_keys, sort_rows
+eng = Engine(0)
+n = 5 * 1024 + 77
+addrs = random_keys(21, n)[:, :20].copy()
+out, perm = eng.pinned_empty((n, 32)), eng.pinned_empty((n,), np.uint32)
+r_out, r_perm = eng.hash_sort_keys(addrs, out=out, perm=perm)
+assert r_out is out and r_perm is perm
+dig = oracle.keccak256_fixed(addrs)
+assert (out == dig[sort_rows(dig)]).all() and (dig[perm] == out).all()
+# strided input: 20-byte messages at a 32-byte stride
+wide = random_keys(22, n)
+out2, perm2 = eng.hash_sort_keys(wide, 20)
+dig2 = oracle.keccak256_fixed(np.ascontiguousarray(wide[:, :20]))
+assert (out2 == dig2[sort_rows(dig2)]).all() and (dig2[perm2] == out2).all()
+# storage: composite keys, slots hashed in chunks
+n_addr = 9
+a20 = random_keys(23, n_addr)[:, :20].copy()
+owner = np.sort(np.random.default_rng(5).integers(0, n_addr, n)).astype(np.uint32)
+slots = random_keys(24, n)
+keys, sperm = eng.hash_sort_storage(a20, owner, slots)
+comp = np.concatenate([oracle.keccak256_fixed(a20)[owner], oracle.keccak256_fixed(slots)], axis=1)
+v = comp.view(">u8")
+order = np.lexsort(tuple(v[:, i] for i in range(7, -1, -1)))
+assert (keys == comp[order]).all() and (sperm == order).all()
+try:
+    eng.hash_sort_keys(addrs, out=np.empty((n, 31), np.uint8))
+    raise SystemExit("a mis-shaped result array was accepted")
+except B200Error:
+    pass
+eng.close()
+print("ok")
+"""
+    import os
+    env = dict(os.environ, B200_KECCAK_CHUNK="1024")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
