@@ -4,7 +4,9 @@
 // A rotate by r of the pair (lo, hi) is also  lo' = lo*2^r + hi32(hi*2^r),  hi' = hi*2^r + hi32(lo*2^r)  (the
 // two summands never share a bit), i.e. IMAD.HI + IMAD + IMAD.WIDE (with a 64-bit addend) on the FMA pipe.  The multipliers come from
 // constant memory so that ptxas cannot turn them back into shifts.  This bench times N permutations per thread
-// with K of the 29 rotates of every round moved over (K = 0: the shipping code).
+// with K of the 29 rotates of every round moved over (K = 0: the shipping code).  Result (profiles/r02_rot_pipes.md): no gain,
+// the register-file operand bandwidth is shared by the two pipes.
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o rot_pipes rot_pipes.cu && ./rot_pipes 64
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
