@@ -2,8 +2,8 @@
 // Part of the single translation unit engine.cu (textually included, in this order).
 
 // ------------------------------------------------------------------------------------------------ forest build
-struct IsBoundary {
-    __host__ __device__ uint32_t operator()(uint8_t v) const { return v == 0xFF ? 1u : 0u; }
+struct IsHead {  // sorted gap key (depth | flags << 8, tk_structure.cuh): the gap starts a branch node
+    __host__ __device__ uint8_t operator()(uint16_t k) const { return (uint8_t)((k >> 8) & 1u); }
 };
 
 struct Built {
@@ -75,48 +75,41 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
     // ---- gaps sorted by depth (stable: position order inside a depth) -> branch nodes in CSR form
     const uint64_t G = n - 1;
     ENSURE(iota, G * 4);
-    ENSURE(depth_sorted, G);
+    ENSURE(head, G * 2);          // sort keys in position order (depth | flags << 8)
+    ENSURE(depth_sorted, G * 2);  // the same, sorted
     ENSURE(gap_sorted, G * 4);
-    ENSURE(head, G);
     ENSURE(node_start, (G + 1) * 4);
     uint32_t *bucket_off = small_u32(c) + SM_BUCKET_OFF;
     uint32_t *level_lo = small_u32(c) + SM_LEVEL_LO;
     uint32_t *n_nodes_p = small_u32(c) + SM_NNODES;
-    uint8_t *depth_sorted = static_cast<uint8_t *>(c->depth_sorted.p);
+    uint32_t *unresolved = small_u32(c) + SM_UNRESOLVED;
+    uint16_t *gap_key = static_cast<uint16_t *>(c->head.p);
+    uint16_t *key_sorted = static_cast<uint16_t *>(c->depth_sorted.p);
     uint32_t *gap_sorted = static_cast<uint32_t *>(c->gap_sorted.p);
-    uint8_t *head = static_cast<uint8_t *>(c->head.p);
     uint32_t *node_start = static_cast<uint32_t *>(c->node_start.p);
 
     auto mark = [&](const char *name) {  // phase marks of the structure pass (serial mode only: they record on c->stream)
         if (c->phase_timing && sa == st) phase_mark(c, name);
     };
-    CU(launch_iota(static_cast<uint32_t *>(c->iota.p), G, 1, sa));
+    // sort input in position order; most gaps learn here whether they start a node (tk_structure.cuh gap_keys_kernel)
+    CU(cudaMemsetAsync(unresolved, 0, 4, sa));
+    CU(launch_gap_keys(f.Lp, G, gap_key, static_cast<uint32_t *>(c->iota.p), unresolved, sa));
     c->launches++;
-    mark("s:iota");
-    size_t t_sort = 0, t_sel = 0, t_scan = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, f.Lp + 1, depth_sorted, static_cast<uint32_t *>(c->iota.p),
-                                       gap_sorted, (int64_t)G, 0, 8, sa));
+    mark("s:gap-keys");
+    size_t t_sort = 0, t_sel = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, gap_key, key_sorted, static_cast<uint32_t *>(c->iota.p), gap_sorted,
+                                       (int64_t)G, 0, 8, sa));
     thrust::counting_iterator<uint32_t> counting(0);
+    auto head = thrust::make_transform_iterator(static_cast<const uint16_t *>(key_sorted), IsHead());
     CU(cub::DeviceSelect::Flagged(nullptr, t_sel, counting, head, node_start, n_nodes_p, (int64_t)G, sa));
-    auto bflags = thrust::make_transform_iterator(static_cast<const uint8_t *>(f.Lp), IsBoundary());
-    uint32_t *bound_rank = nullptr;
-    if (d_seg_offsets) {
-        ENSURE(bound_rank, (n + 1) * 4);
-        bound_rank = static_cast<uint32_t *>(c->bound_rank.p);
-        CU(cub::DeviceScan::InclusiveSum(nullptr, t_scan, bflags, bound_rank, (int64_t)(n + 1), sa));
-    }
-    size_t t_max = std::max(t_sort, std::max(t_sel, t_scan));
+    size_t t_max = std::max(t_sort, t_sel);
     ENSURE(cub_temp, t_max);
-    CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_sort, f.Lp + 1, depth_sorted,
-                                       static_cast<uint32_t *>(c->iota.p), gap_sorted, (int64_t)G, 0, 8, sa));
+    CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t_sort, gap_key, key_sorted, static_cast<uint32_t *>(c->iota.p),
+                                       gap_sorted, (int64_t)G, 0, 8, sa));
     mark("s:gap-sort");
-    CU(launch_bucket_offsets(depth_sorted, G, bucket_off, sa));
-    if (d_seg_offsets)
-        CU(cub::DeviceScan::InclusiveSum(c->cub_temp.p, t_scan, bflags, bound_rank, (int64_t)(n + 1), sa));
-    CU(cudaMemsetAsync(head, 0, G, sa));
-    mark("s:offsets+scan");
-    CU(launch_head_flags(d_keys, f.Lp, depth_sorted, gap_sorted, bound_rank, bucket_off + 64, G, head, sa));
-    mark("s:head-flags");
+    CU(launch_bucket_offsets(key_sorted, G, bucket_off, sa));
+    CU(launch_head_fix(d_keys, key_sorted, gap_sorted, d_seg_offsets, n_segs, unresolved, G, sa));
+    mark("s:offsets+head-fix");
     CU(cub::DeviceSelect::Flagged(c->cub_temp.p, t_sel, counting, head, node_start, n_nodes_p, (int64_t)G, sa));
     CU(launch_level_ranges(node_start, n_nodes_p, bucket_off, level_lo, sa));
     mark("s:select+ranges");
@@ -127,8 +120,8 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
     uint32_t *nids = static_cast<uint32_t *>(c->node_ids.p);
     uint32_t *hist = small_u32(c) + SM_HIST;
     CU(cudaMemsetAsync(hist, 0, 256 * 4, sa));
-    CU(launch_node_class_keys(node_start, depth_sorted, n_nodes_p, G, nk, nids, hist, sa));
-    c->launches += 9;
+    CU(launch_node_class_keys(node_start, key_sorted, n_nodes_p, G, nk, nids, hist, sa));
+    c->launches += 7;
     mark("s:class-keys");
     uint32_t *h_level = static_cast<uint32_t *>(c->pinned_small) + 64;
     uint32_t *h_hist = static_cast<uint32_t *>(c->pinned_small) + 256;

@@ -254,6 +254,7 @@ static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const ui
     uint32_t *cnt_cur = d.g + DG_LIST_A, *cnt_next = d.g + DG_LIST_B;
     CU(launch_dt_update_detach(d, d_vals, d_sroots, m, kind, leaf_of, list_cur, st));
     c->launches += 2;
+    phase_mark(c, "r:locate+detach");
     // ---- collapse rounds until no node is left that lost children
     uint32_t *ps = static_cast<uint32_t *>(c->pinned_small);
     for (int round = 0;; round++) {
@@ -261,6 +262,7 @@ static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const ui
         CU(cudaMemcpyAsync(ps + 201, small_u32(c) + SM_ERR, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (ps[201] != B200_DEVERR_NONE) return report_dev_error_now(c, (int)ps[201]);
+        phase_mark(c, "r:collapse-sync");
         if (ps[200] == 0) break;
         if (round > 200) return fail(c, B200_ERR_CUDA, "collapse rounds do not converge");
         CU(cudaMemsetAsync(cnt_next, 0, 4, st));
@@ -295,6 +297,7 @@ static int32_t da_restructure(DArena *a, const uint32_t *d_trie_of_key, const ui
         CU(cudaMemcpyAsync(ps + 202, d.g + DG_NINSERT, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (ps[201] != B200_DEVERR_NONE) return report_dev_error_now(c, (int)ps[201]);
+        phase_mark(c, "r:insert-round");
         if (ps[200] == 0) break;
         if (round > 80) return fail(c, B200_ERR_CUDA, "insert rounds do not converge");
         if (!idx_next) {

@@ -230,6 +230,7 @@ static int32_t dstate_apply_impl(b200_dstate *t, const uint8_t *acct_keys32, con
             TRY(h2d_into(S, t->in_svals, values32_be, n_entries * 32, in_kind));
         }
         const uint8_t *d_flags = acct_flags ? static_cast<const uint8_t *>(t->in_aflags.p) : nullptr;
+        phase_mark(c, "block-in");
         // ---- accounts: structure only (their leaves are re-hashed after the storage roots are known)
         const uint32_t *d_acct_tries = nullptr;
         if (t->sharded) {  // bucket trie of every account entry = its top key nibble
@@ -241,6 +242,7 @@ static int32_t dstate_apply_impl(b200_dstate *t, const uint8_t *acct_keys32, con
                            d_flags, nullptr, m));
         const uint8_t *a_kind = static_cast<const uint8_t *>(A->kind.p);
         const uint32_t *a_leaf = static_cast<const uint32_t *>(A->leaf_of.p);
+        phase_mark(c, "acct-restructure");
         // ---- storage tries of destroyed / wiped accounts
         S->top_out = static_cast<uint8_t *>(A->lsroot.p);  // the account arena may have been re-allocated
         S->top_stride = 32;
@@ -268,6 +270,7 @@ static int32_t dstate_apply_impl(b200_dstate *t, const uint8_t *acct_keys32, con
                 hi = ps[201];
             }
         }
+        phase_mark(c, "wipes");
         // ---- storage slots of the surviving accounts
         if (n_entries) {
             uint32_t *trie_of_key = static_cast<uint32_t *>(t->trie_of_key.p);
@@ -275,12 +278,15 @@ static int32_t dstate_apply_impl(b200_dstate *t, const uint8_t *acct_keys32, con
             c->launches++;
             TRY(da_restructure(S, trie_of_key, static_cast<const uint8_t *>(t->in_skeys.p),
                                static_cast<const uint8_t *>(t->in_svals.p), nullptr, nullptr, n_entries));
+            phase_mark(c, "storage-restructure");
             TRY(da_rehash(S, n_entries));  // roots land in the account leaves' storage-root fields
+            phase_mark(c, "storage-rehash");
             c->stats.leaves_added += n_entries;
         }
         // ---- accounts: re-hash
         TRY(da_rehash(A, m));
         if (t->sharded) TRY(dstate_frontier_on_device(t));
+        phase_mark(c, "acct-rehash");
         c->stats.leaves_added += m;
         // what the host needs to label the storage records
         h_kind.resize(m);

@@ -38,7 +38,7 @@ static thread_local int g_create_status = 0;
 static constexpr uint32_t WARP_LEVEL_MAX = 4096;
 
 // layout of the `small` device buffer (uint32 units)
-enum : int { SM_BUCKET_OFF = 0, SM_LEVEL_LO = 80, SM_NNODES = 160, SM_ERR = 164, SM_ERR_STICKY = 165, SM_NSTORED = 168, SM_ORD_NLONG = 170, SM_COUNTERS = 176 /* 4 x u64 */, SM_HIST = 256 /* 256 x u32 */, SM_WORDS = 512 };
+enum : int { SM_BUCKET_OFF = 0, SM_LEVEL_LO = 80, SM_NNODES = 160, SM_ERR = 164, SM_ERR_STICKY = 165, SM_NSTORED = 168, SM_ORD_NLONG = 170, SM_UNRESOLVED = 172, SM_COUNTERS = 176 /* 4 x u64 */, SM_HIST = 256 /* 256 x u32 */, SM_WORDS = 512 };
 
 static uint32_t *small_u32(b200_ctx *c) { return static_cast<uint32_t *>(c->small.p); }
 
@@ -97,7 +97,7 @@ extern "C" B200_API void b200_destroy(b200_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf *bufs[] = {&c->Lp, &c->nibs, &c->leaf_ref, &c->leaf_meta, &c->S, &c->E, &c->iota, &c->depth_sorted,
-                      &c->gap_sorted, &c->bound_rank, &c->head, &c->node_start, &c->node_ref, &c->node_meta,
+                      &c->gap_sorted, &c->head, &c->node_start, &c->node_ref, &c->node_meta,
                       &c->node_l, &c->node_r, &c->node_masks, &c->cub_temp, &c->small, &c->sroots, &c->buckets,
                       &c->upd_flags, &c->upd_nh, &c->upd_ids, &c->upd_prefix, &c->upd_key, &c->upd_key2, &c->upd_ids2, &c->in_a, &c->in_b, &c->in_c,
                       &c->in_d, &c->in_e, &c->out_a, &c->chunk_in[0], &c->chunk_in[1], &c->chunk_in[2], &c->chunk_out[0],

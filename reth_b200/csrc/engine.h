@@ -36,7 +36,7 @@ struct b200_ctx {
     bool stats_pending = false;
     bool stats_wavefront = false;  // branches_added of the last build comes from the wavefront's node counter
     // scratch (grow-only)
-    DevBuf Lp, nibs, leaf_ref, leaf_meta, S, E, iota, depth_sorted, gap_sorted, bound_rank, head, node_start,
+    DevBuf Lp, nibs, leaf_ref, leaf_meta, S, E, iota, depth_sorted, gap_sorted, head, node_start,
         node_ref, node_meta, node_l, node_r, node_masks, cub_temp, small, sroots, buckets;
     DevBuf upd_flags, upd_nh, upd_ids, upd_prefix, upd_key, upd_key2, upd_ids2;
     DevBuf sort_ka, sort_kb, sort_ia, sort_flag, sort_perm, sort_out;

@@ -58,15 +58,19 @@ cudaError_t launch_iota(uint32_t *out, uint64_t n, uint32_t first, cudaStream_t 
     iota_kernel<<<blocks_for(n, 256), 256, 0, st>>>(out, n, first);
     return cudaGetLastError();
 }
-cudaError_t launch_bucket_offsets(const uint8_t *depth_sorted, uint64_t G, uint32_t *bucket_off, cudaStream_t st) {
-    bucket_offsets_kernel<<<1, 96, 0, st>>>(depth_sorted, G, bucket_off);
+cudaError_t launch_gap_keys(const uint8_t *Lp, uint64_t G, uint16_t *key, uint32_t *val, uint32_t *unresolved, cudaStream_t st) {
+    if (G == 0) return cudaSuccess;
+    gap_keys_kernel<<<blocks_for(G, 256), 256, 0, st>>>(Lp, G, key, val, unresolved);
     return cudaGetLastError();
 }
-cudaError_t launch_head_flags(const uint8_t *keys, const uint8_t *Lp, const uint8_t *depth_sorted, const uint32_t *gap_sorted,
-                              const uint32_t *bound_rank, const uint32_t *G_real_p, uint64_t G, uint8_t *head,
-                              cudaStream_t st) {
+cudaError_t launch_bucket_offsets(const uint16_t *key_sorted, uint64_t G, uint32_t *bucket_off, cudaStream_t st) {
+    bucket_offsets_kernel<<<1, 96, 0, st>>>(key_sorted, G, bucket_off);
+    return cudaGetLastError();
+}
+cudaError_t launch_head_fix(const uint8_t *keys, uint16_t *key_sorted, const uint32_t *gap_sorted, const uint64_t *seg_offsets,
+                            uint64_t n_segs, const uint32_t *unresolved, uint64_t G, cudaStream_t st) {
     if (G == 0) return cudaSuccess;
-    head_flags_kernel<<<blocks_for(G, 256), 256, 0, st>>>(keys, Lp, depth_sorted, gap_sorted, bound_rank, G_real_p, G, head);
+    head_fix_kernel<<<blocks_for(G, 256), 256, 0, st>>>(keys, key_sorted, gap_sorted, seg_offsets, n_segs, unresolved, G);
     return cudaGetLastError();
 }
 cudaError_t launch_level_ranges(uint32_t *node_start, const uint32_t *n_nodes_p, const uint32_t *bucket_off,
@@ -136,7 +140,7 @@ cudaError_t launch_branch_level(const ForestDev &f, const uint32_t *node_order, 
 // is a 33-byte hash reference (children <= 3 -> 1 block, <= 7 -> 2, <= 12 -> 3, else 4)
 // hist[key] counts the nodes of every (depth, class); runs before the host knows the node count, hence the
 // device-side bound.
-__global__ void node_class_keys_kernel(const uint32_t *__restrict__ node_start, const uint8_t *__restrict__ depth_sorted,
+__global__ void node_class_keys_kernel(const uint32_t *__restrict__ node_start, const uint16_t *__restrict__ key_sorted,
                                        const uint32_t *__restrict__ n_nodes_p, uint8_t *__restrict__ keys,
                                        uint32_t *__restrict__ ids, uint32_t *__restrict__ hist) {
     __shared__ uint32_t sh[256];
@@ -146,7 +150,7 @@ __global__ void node_class_keys_kernel(const uint32_t *__restrict__ node_start, 
     for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_nodes; v += gridDim.x * blockDim.x) {
         uint32_t j0 = node_start[v], children = node_start[v + 1] - j0 + 1;
         uint32_t cls = children <= 3 ? 0 : (children <= 7 ? 1 : (children <= 12 ? 2 : 3));
-        uint32_t key = ((63u - depth_sorted[j0]) << 2) | cls;
+        uint32_t key = ((63u - (key_sorted[j0] & 0xFFu)) << 2) | cls;
         keys[v] = (uint8_t)key;
         ids[v] = v;
         atomicAdd(&sh[key], 1u);
@@ -154,12 +158,12 @@ __global__ void node_class_keys_kernel(const uint32_t *__restrict__ node_start, 
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
-cudaError_t launch_node_class_keys(const uint32_t *node_start, const uint8_t *depth_sorted, const uint32_t *n_nodes_p,
+cudaError_t launch_node_class_keys(const uint32_t *node_start, const uint16_t *key_sorted, const uint32_t *n_nodes_p,
                                    uint64_t max_nodes, uint8_t *keys, uint32_t *ids, uint32_t *hist, cudaStream_t st) {
     if (max_nodes == 0) return cudaSuccess;
     unsigned blocks = blocks_for(max_nodes, 256);
     if (blocks > (unsigned)sms() * 8) blocks = (unsigned)sms() * 8;
-    node_class_keys_kernel<<<blocks, 256, 0, st>>>(node_start, depth_sorted, n_nodes_p, keys, ids, hist);
+    node_class_keys_kernel<<<blocks, 256, 0, st>>>(node_start, key_sorted, n_nodes_p, keys, ids, hist);
     return cudaGetLastError();
 }
 

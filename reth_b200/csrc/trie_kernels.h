@@ -43,7 +43,7 @@ static_assert(sizeof(FrontierEntryDev) == 68, "frontier layout");
 // frontier of every level is exactly node_ref/leaf_ref).
 //
 //   per leaf  (n)    : keys 32 B (input) | Lp 1 | nibs 1 | leaf_ref 32 | leaf_meta 1 | S 4 | E 4
-//   per gap   (n-1)  : depth_sorted 1 | gap_sorted 4            (gaps ordered by (depth, position))
+//   per gap   (n-1)  : key_sorted 2 (depth | head flag << 8) | gap_sorted 4   (gaps ordered by (depth, position))
 //   per branch (B)   : node_start 4 (CSR into gap_sorted) | node_ref 32 | node_meta 1 | node_l 4 | node_r 4 |
 //                      node_masks 8 (state, tree, hash, depth)
 struct ForestDev {
@@ -79,17 +79,17 @@ cudaError_t launch_mark_boundaries(const uint64_t *d_seg_offsets, uint64_t n_seg
                                    cudaStream_t st);
 cudaError_t launch_lcp(const uint8_t *keys, uint64_t n, uint8_t *Lp, uint8_t *nibs, int *err, cudaStream_t st);
 cudaError_t launch_iota(uint32_t *out, uint64_t n, uint32_t first, cudaStream_t st);
-cudaError_t launch_bucket_offsets(const uint8_t *depth_sorted, uint64_t G, uint32_t *bucket_off, cudaStream_t st);
-cudaError_t launch_head_flags(const uint8_t *keys, const uint8_t *Lp, const uint8_t *depth_sorted, const uint32_t *gap_sorted,
-                              const uint32_t *bound_rank, const uint32_t *G_real_p, uint64_t G, uint8_t *head,
-                              cudaStream_t st);
+cudaError_t launch_gap_keys(const uint8_t *Lp, uint64_t G, uint16_t *key, uint32_t *val, uint32_t *unresolved, cudaStream_t st);
+cudaError_t launch_bucket_offsets(const uint16_t *key_sorted, uint64_t G, uint32_t *bucket_off, cudaStream_t st);
+cudaError_t launch_head_fix(const uint8_t *keys, uint16_t *key_sorted, const uint32_t *gap_sorted, const uint64_t *seg_offsets,
+                            uint64_t n_segs, const uint32_t *unresolved, uint64_t G, cudaStream_t st);
 cudaError_t launch_level_ranges(uint32_t *node_start, const uint32_t *n_nodes_p, const uint32_t *bucket_off,
                                 uint32_t *level_lo, cudaStream_t st);
 cudaError_t launch_leaves(const ForestDev &f, bool account, const uint8_t *values, const uint8_t *storage_roots,
                           cudaStream_t st);
 cudaError_t launch_branch_level(const ForestDev &f, const uint32_t *node_order, uint32_t pos_lo, uint32_t pos_hi,
                                 int d, int cls, cudaStream_t st);
-cudaError_t launch_node_class_keys(const uint32_t *node_start, const uint8_t *depth_sorted, const uint32_t *n_nodes_p,
+cudaError_t launch_node_class_keys(const uint32_t *node_start, const uint16_t *key_sorted, const uint32_t *n_nodes_p,
                                    uint64_t max_nodes, uint8_t *keys, uint32_t *ids, uint32_t *hist, cudaStream_t st);
 cudaError_t launch_segment_roots(const ForestDev &f, const uint64_t *d_seg_offsets, uint64_t n_segs, uint8_t *roots,
                                  cudaStream_t st);

@@ -135,6 +135,39 @@ def test_forest_with_deep_shared_prefixes(eng, seed):
     assert (got == exp).all()
 
 
+def test_node_heads_across_trie_boundaries_and_long_spans(eng):
+    """Which gaps start a branch node (tk_structure.cuh): most learn it from the 32 gaps to their left (gap_keys_kernel), the
+    others after the sort from the keys (head_fix_kernel) — which must not join two tries.  Trie A ends in a large top-nibble-7
+    group, trie B starts with one: the previous depth-0 gap of B's first depth-0 gap lies in A, more than 32 gaps away, and
+    the leaves between them all share nibble 7.  Then: tries whose spans straddle exactly 31 / 32 / 33 / 34 gaps; empty and
+    one-leaf tries in between."""
+    rng = np.random.default_rng(77)
+
+    def keys_with_top(nibbles, n):
+        k = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        k[:, 0] = (rng.choice(nibbles, n).astype(np.uint8) << 4) | (k[:, 0] & 0x0F)
+        k = np.unique(k, axis=0)
+        return k[sort_rows(k)]
+
+    def span_trie(span):
+        # two depth-0 gaps with `span` leaves of one top nibble between them (their gaps are all deeper)
+        k = np.concatenate([keys_with_top([1], 1), keys_with_top([2], span), keys_with_top([3], 1)])
+        return k[sort_rows(k)]
+
+    segs = [keys_with_top(list(range(0, 8)), 3000), keys_with_top(list(range(7, 16)), 1500), np.zeros((0, 32), np.uint8),
+            keys_with_top([4], 1)]
+    segs += [span_trie(sp) for sp in (30, 31, 32, 33, 34, 35, 64, 65)]
+    segs += [keys_with_top([7], 700), keys_with_top([7, 8], 900)]
+    offs = np.zeros(len(segs) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(x) for x in segs])
+    keys = np.concatenate(segs)
+    vals = u256_be(rng.integers(1, 1 << 62, len(keys)))
+    roots, upd = eng.storage_roots(keys, vals, offs, want_updates=True)
+    o_roots, o_upd = oracle.storage_roots(keys, vals, offs, want_updates=True, threads=4)
+    assert (roots == o_roots).all()
+    assert upd == o_upd
+
+
 @pytest.mark.parametrize("mode", ["u64", "mixed"])
 def test_storage_forest_random(eng, mode):
     rng = np.random.default_rng(4)
