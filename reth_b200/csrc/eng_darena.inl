@@ -35,6 +35,7 @@ static int32_t da_resize(DArena *a, DevBuf &b, size_t new_bytes, size_t keep_byt
     if (new_bytes <= b.cap) return B200_OK;
     void *p = nullptr;
     size_t want = new_bytes + 256;
+    if (c->phase_timing) fprintf(stderr, "[b200 grow] %zu -> %zu bytes (keep %zu)\n", b.cap, want, keep_bytes);
     CU(cudaMalloc(&p, want));
     if (fill >= 0) CU(cudaMemsetAsync(p, fill, want, c->stream));
     if (b.p && keep_bytes) CU(cudaMemcpyAsync(p, b.p, keep_bytes, cudaMemcpyDeviceToDevice, c->stream));
@@ -48,7 +49,12 @@ static int32_t da_resize(DArena *a, DevBuf &b, size_t new_bytes, size_t keep_byt
     *a->bytes += want;
     return B200_OK;
 }
-static int32_t da_scratch(DArena *a, DevBuf &b, size_t bytes) { return da_resize(a, b, bytes ? bytes : 16, 0, -1); }
+// Per-block scratch: grows by half again, so that blocks of slowly rising size do not pay a cudaMalloc + cudaFree (each an
+// implicit device synchronisation: 0.5 - 100 ms measured on a B200 with a few GB resident) every time one is the largest so far.
+static int32_t da_scratch(DArena *a, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return B200_OK;
+    return da_resize(a, b, bytes + bytes / 2 + 4096, 0, -1);
+}
 
 // capacity for `leaves` leaf slots, `nodes` node slots and `tries` root words, keeping what is allocated so far
 static int32_t da_reserve(DArena *a, uint64_t leaves, uint64_t nodes, uint64_t tries) {
