@@ -207,3 +207,114 @@ class StoredSubNode:
             p += 1
         node = branch_node_compact_from_bytes(buf[p + 1:]) if buf[p] else None
         return cls(key, nibble, node)
+
+
+def _varuint(n: int) -> bytes:
+    """reth-codecs `encode_varuint`: LEB128, low 7 bits first."""
+    out = bytearray()
+    while n >= 0x80:
+        out.append(0x80 | (n & 0x7F))
+        n >>= 7
+    out.append(n)
+    return bytes(out)
+
+
+def _read_varuint(buf: bytes, p: int):
+    n = shift = 0
+    while True:
+        b = buf[p]
+        p += 1
+        n |= (b & 0x7F) << shift
+        if not b & 0x80:
+            return n, p
+        shift += 7
+
+
+def _vec_u8_to_compact(v: bytes) -> bytes:
+    """reth-codecs `Vec<T>::to_compact` instantiated at T = u8: varuint element count, then per element a varuint length
+    and the element's own Compact bytes — a u8 drops its leading zero byte, so 0 is (length 0, no byte)."""
+    out = bytearray(_varuint(len(v)))
+    for x in v:
+        out += b"\x00" if x == 0 else bytes([1, x])
+    return bytes(out)
+
+
+def _vec_u8_from_compact(buf: bytes, p: int):
+    n, p = _read_varuint(buf, p)
+    v = bytearray()
+    for _ in range(n):
+        ln, p = _read_varuint(buf, p)
+        v.append(int.from_bytes(buf[p:p + ln], "big") if ln else 0)
+        p += ln
+    return bytes(v), p
+
+
+class HashBuilderState:
+    """crates/trie/common/src/hash_builder/state.rs:15-32 — alloy-trie's HashBuilder between two `add_leaf` calls, the form
+    reth's MerkleCheckpoint stores — with its Compact codec (:66-140): key (nibbles, one per byte) as a Vec<u8>, u16 stack
+    length + (u16 length, RlpNode bytes) per entry, the pending value (tag 0 + 32-byte hash | tag 1 + Vec<u8> of a leaf
+    value), three u16-counted lists of big-endian u16 masks (groups, tree, hash), one byte stored_in_database.
+
+    The element codecs (Vec<u8>, HashBuilderValue, TrieMask) live in the external crate reth-codecs 0.3.1 (Cargo.toml:328; not
+    vendored under the reference) and are restated here from its published source: parity of this codec is unpinned — the
+    reference tree holds no byte vector for it (state.rs:149-170 round-trips only), and so does tests/test_table_rows.py.
+    This engine's resumable state is the frontier checkpoint (b200_root_stream_checkpoint), which a
+    HashBuilder stack cannot express at a bucket boundary (the builder folds a key only when the next one arrives); the
+    codec lets a host read and write the rows reth itself left in `StageCheckpoints`."""
+
+    def __init__(self, key: bytes = b"", value=("bytes", b""), stack=(), groups=(), tree_masks=(), hash_masks=(),
+                 stored_in_database: bool = False):
+        self.key, self.value, self.stack = bytes(key), (value[0], bytes(value[1])), [bytes(s) for s in stack]
+        self.groups, self.tree_masks, self.hash_masks = list(groups), list(tree_masks), list(hash_masks)
+        self.stored_in_database = bool(stored_in_database)
+        if any(n > 15 for n in self.key):
+            raise ValueError("key holds one nibble per byte")
+        if self.value[0] not in ("hash", "bytes") or (self.value[0] == "hash" and len(self.value[1]) != 32):
+            raise ValueError("value is ('hash', 32 bytes) or ('bytes', leaf value)")
+
+    def _tuple(self):
+        return (self.key, self.value, self.stack, self.groups, self.tree_masks, self.hash_masks, self.stored_in_database)
+
+    def __eq__(self, o):
+        return self._tuple() == o._tuple()
+
+    def to_compact(self) -> bytes:
+        out = bytearray(_vec_u8_to_compact(self.key))
+        out += len(self.stack).to_bytes(2, "big")
+        for item in self.stack:
+            out += len(item).to_bytes(2, "big") + item
+        out += (b"\x00" + self.value[1]) if self.value[0] == "hash" else (b"\x01" + _vec_u8_to_compact(self.value[1]))
+        for masks in (self.groups, self.tree_masks, self.hash_masks):
+            out += len(masks).to_bytes(2, "big")
+            for m in masks:
+                out += int(m).to_bytes(2, "big")
+        out.append(1 if self.stored_in_database else 0)
+        return bytes(out)
+
+    @classmethod
+    def from_compact(cls, buf: bytes) -> "HashBuilderState":
+        key, p = _vec_u8_from_compact(buf, 0)
+        n = int.from_bytes(buf[p:p + 2], "big")
+        p += 2
+        stack = []
+        for _ in range(n):
+            ln = int.from_bytes(buf[p:p + 2], "big")
+            stack.append(buf[p + 2:p + 2 + ln])
+            p += 2 + ln
+        tag = buf[p]
+        p += 1
+        if tag == 0:
+            value = ("hash", buf[p:p + 32])
+            p += 32
+        elif tag == 1:
+            v, p = _vec_u8_from_compact(buf, p)
+            value = ("bytes", v)
+        else:
+            raise ValueError("HashBuilderValue tag %d" % tag)
+        lists = []
+        for _ in range(3):
+            n = int.from_bytes(buf[p:p + 2], "big")
+            p += 2
+            lists.append([int.from_bytes(buf[p + 2 * i:p + 2 * i + 2], "big") for i in range(n)])
+            p += 2 * n
+        return cls(key, value, stack, lists[0], lists[1], lists[2], buf[p] != 0)
