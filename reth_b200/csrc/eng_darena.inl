@@ -409,7 +409,7 @@ static int32_t da_collect_updates(DArena *a, b200_updates *u) {
         pick_prefix = pref;
     }
     const UpdatesLayout lay(n_stored, n_hashes);
-    CU(cudaMallocHost(&owner->host, lay.host_total ? lay.host_total : 16));
+    if (!(owner->host = pinned_block_alloc(lay.host_total ? lay.host_total : 16))) return fail(c, B200_ERR_OOM, "page-locked result block");
     uint8_t *h = static_cast<uint8_t *>(owner->host);
     lay.bind_host(u, h, n_stored);
     if (n_stored) {
@@ -436,7 +436,7 @@ static int32_t da_collect_removed(DArena *a, const b200_updates *updated, b200_u
     const size_t n = a->n_removed;
     size_t o_len = 0, o_path = align_up(n, 16), o_tid = align_up(o_path + n * 32, 16), o_masks = align_up(o_tid + n * 4, 16),
            o_ho = align_up(o_masks + n * 2, 16), total = o_ho + (n + 1) * 8;
-    CU(cudaMallocHost(&owner->host, total));
+    if (!(owner->host = pinned_block_alloc(total))) return fail(c, B200_ERR_OOM, "page-locked result block");
     uint8_t *h = static_cast<uint8_t *>(owner->host);
     memset(h, 0, total);
     if (n) {

@@ -9,7 +9,7 @@ extern "C" B200_API void b200_proofs_release(b200_proofs *p) {
     if (!p) return;
     if (p->_owner) {
         ProofsOwner *o = static_cast<ProofsOwner *>(p->_owner);
-        if (o->host) cudaFreeHost(o->host);
+        pinned_block_free(o->host);
         delete o;
     }
     memset(p, 0, sizeof *p);
@@ -57,7 +57,7 @@ static int32_t da_proofs(DArena *a, const uint32_t *d_trie_of_target, const uint
     // host block: node_offset u64[n+1] | rlp_offset u64[n_nodes+1] | node_depth u8[n_nodes] | rlp bytes
     size_t o_no = 0, o_ro = (n + 1) * 8, o_nd = o_ro + (n_nodes + 1) * 8, o_rlp = align_up(o_nd + n_nodes, 16),
            total = o_rlp + n_bytes + 16;
-    CU(cudaMallocHost(&owner->host, total));
+    if (!(owner->host = pinned_block_alloc(total))) return fail(c, B200_ERR_OOM, "page-locked result block");
     uint8_t *h = static_cast<uint8_t *>(owner->host);
     out->node_offset = reinterpret_cast<uint64_t *>(h + o_no);
     out->rlp_offset = reinterpret_cast<uint64_t *>(h + o_ro);

@@ -10,7 +10,7 @@ extern "C" B200_API void b200_updates_release(b200_updates *u) {
     if (!u) return;
     if (u->_owner) {
         UpdatesOwner *o = static_cast<UpdatesOwner *>(u->_owner);
-        if (o->host) cudaFreeHost(o->host);
+        pinned_block_free(o->host);
         delete o;
     }
     memset(u, 0, sizeof *u);
@@ -72,7 +72,7 @@ static int32_t gather_and_copy(b200_ctx *c, const ForestDev &f, const uint32_t *
                                const uint64_t *d_seg_offsets, uint64_t n_segs, b200_updates *u, UpdatesOwner *owner) {
     cudaStream_t st = c->stream;
     const UpdatesLayout lay(n_stored, n_hashes);
-    CU(cudaMallocHost(&owner->host, lay.host_total ? lay.host_total : 16));
+    if (!(owner->host = pinned_block_alloc(lay.host_total ? lay.host_total : 16))) return fail(c, B200_ERR_OOM, "page-locked result block");
     uint8_t *h = static_cast<uint8_t *>(owner->host);
     lay.bind_host(u, h, n_stored);
     if (n_stored) {
@@ -195,7 +195,7 @@ static int32_t collect_rows(b200_ctx *c, const Built &b, const uint64_t *d_seg_o
     const size_t off_bytes = (n + 1) * sizeof(uint64_t), kl_bytes = ((n * sizeof(uint32_t)) + 7) & ~size_t(7);
     RowsOwner *owner = new RowsOwner{nullptr, 1};
     rows->_owner = owner;
-    CU(cudaMallocHost(&owner->block, off_bytes + kl_bytes + (total ? total : 1)));
+    if (!(owner->block = pinned_block_alloc(off_bytes + kl_bytes + (total ? total : 1)))) return fail(c, B200_ERR_OOM, "page-locked result block");
     uint8_t *h = static_cast<uint8_t *>(owner->block);
     rows->row_offset = reinterpret_cast<uint64_t *>(h);
     rows->key_len = reinterpret_cast<uint32_t *>(h + off_bytes);

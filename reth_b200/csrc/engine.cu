@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -198,6 +199,85 @@ extern "C" B200_API int32_t b200_numa_bind_thread(int32_t device_ordinal) {
     (void)device_ordinal;
     return -1;
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------ pinned result blocks
+namespace {
+struct PinnedPool {
+    std::mutex mu;
+    std::multimap<size_t, void *> idle;          // capacity -> block
+    std::unordered_map<void *, size_t> capacity;  // every block this pool has handed out or holds
+    size_t idle_bytes = 0;
+    size_t limit = [] {
+        const char *e = getenv("B200_PINNED_POOL_MB");
+        return (size_t)(e ? strtoull(e, nullptr, 10) : 1024) << 20;
+    }();
+};
+PinnedPool &pinned_pool() {
+    static PinnedPool *p = new PinnedPool();  // never destroyed: blocks may be released after static destruction began
+    return *p;
+}
+size_t pinned_size_class(size_t bytes) {  // next multiple of an eighth of the enclosing power of two, at least 4 KiB
+    if (bytes <= 4096) return 4096;
+    size_t pow2 = 4096;
+    while (pow2 < bytes) pow2 <<= 1;
+    size_t step = pow2 >> 4;  // (pow2 / 2) / 8
+    return (bytes + step - 1) / step * step;
+}
+}  // namespace
+
+void *pinned_block_alloc(size_t bytes) {
+    const size_t want = pinned_size_class(bytes);
+    PinnedPool &pp = pinned_pool();
+    {
+        std::lock_guard<std::mutex> g(pp.mu);
+        auto it = pp.idle.lower_bound(want);
+        if (it != pp.idle.end() && it->first <= 2 * want) {
+            void *p = it->second;
+            pp.idle_bytes -= it->first;
+            pp.idle.erase(it);
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaMallocHost(&p, want) != cudaSuccess) {
+        cudaGetLastError();
+        // pinned memory is exhausted: give the idle blocks back and try once more
+        std::vector<void *> drop;
+        {
+            std::lock_guard<std::mutex> g(pp.mu);
+            for (auto &kv : pp.idle) {
+                drop.push_back(kv.second);
+                pp.capacity.erase(kv.second);
+            }
+            pp.idle.clear();
+            pp.idle_bytes = 0;
+        }
+        for (void *q : drop) cudaFreeHost(q);
+        if (cudaMallocHost(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+    }
+    std::lock_guard<std::mutex> g(pp.mu);
+    pp.capacity[p] = want;
+    return p;
+}
+
+void pinned_block_free(void *p) {
+    if (!p) return;
+    PinnedPool &pp = pinned_pool();
+    {
+        std::lock_guard<std::mutex> g(pp.mu);
+        auto it = pp.capacity.find(p);
+        if (it != pp.capacity.end() && pp.idle_bytes + it->second <= pp.limit) {
+            pp.idle.emplace(it->second, p);
+            pp.idle_bytes += it->second;
+            return;
+        }
+        if (it != pp.capacity.end()) pp.capacity.erase(it);
+    }
+    cudaFreeHost(p);
 }
 
 extern "C" B200_API void *b200_host_alloc(size_t bytes) {

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/b200trie.h"
+#include "pinned_pool.h"
 
 // ------------------------------------------------------------------------------------------------ context
 struct DevBuf {

@@ -327,7 +327,7 @@ extern "C" B200_API void b200_changeset_hashes_release(b200_changeset_hashes *o)
     if (!o) return;
     if (o->_owner) {
         ChangesetOwner *w = static_cast<ChangesetOwner *>(o->_owner);
-        if (w->host) cudaFreeHost(w->host);
+        pinned_block_free(w->host);
         delete w;
     }
     memset(o, 0, sizeof *o);
@@ -451,7 +451,7 @@ extern "C" B200_API int32_t b200_hash_changesets(b200_ctx *c, const uint8_t *acc
                  h_pk = htake((size_t)uu * 32);
     ChangesetOwner *owner = new ChangesetOwner();
     out->_owner = owner;
-    CU(cudaMallocHost(&owner->host, h ? h : 16));
+    if (!(owner->host = pinned_block_alloc(h ? h : 16))) return fail(c, B200_ERR_OOM, "page-locked result block");
     uint8_t *H = static_cast<uint8_t *>(owner->host);
     out->n_accounts = ua;
     out->account_keys32 = H + h_ak;

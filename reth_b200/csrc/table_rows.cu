@@ -16,6 +16,7 @@
 //                          (crates/storage/provider/src/providers/database/provider.rs:3125-3160,
 //                          crates/trie/db/src/trie_cursor.rs:280-312)
 #include "b200trie.h"
+#include "pinned_pool.h"
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -156,7 +157,7 @@ B200_API void b200_rows_release(b200_rows *r) {
     if (!r) return;
     if (r->_owner) {
         RowsOwner *o = static_cast<RowsOwner *>(r->_owner);
-        if (o->pinned) cudaFreeHost(o->block);  // rows encoded on the device (eng_updates.inl: collect_rows)
+        if (o->pinned) pinned_block_free(o->block);  // rows encoded on the device (eng_updates.inl: collect_rows)
         else free(o->block);
         delete o;
     }

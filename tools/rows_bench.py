@@ -44,7 +44,7 @@ def main():
         for _ in range(args.reps + 1):
             t0 = time.perf_counter()
             root, ar, sr = eng.state_root_full_rows(akeys, accs, skeys, svals, offs, key_format=args.packed, encode_on_host=host)
-            ts.append((time.perf_counter() - t0) * 1e3)
+            ts.append((time.perf_counter() - t0) * 1e3)   # (the rows live in page-locked library memory until release())
             cur = (root, ar.bytes.copy(), sr.bytes.copy(), ar.row_offset.copy(), sr.row_offset.copy())
             rows, nbytes = len(ar) + len(sr), int(ar.row_offset[-1]) + int(sr.row_offset[-1])
             ar.release(); sr.release()
