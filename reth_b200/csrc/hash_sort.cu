@@ -2,10 +2,11 @@
 // collector (crates/stages/stages/src/stages/hashing_account.rs:192-230, crates/etl/src/lib.rs:31-60), done on
 // the device: keccak of every key, then a radix sort of the 32-byte digests.
 //
-// Digests are keccak outputs, so their leading 64 bits are distinct with overwhelming probability: sort
-// (prefix64, index) pairs with one 64-bit radix sort, then verify strict order of the full 32-byte keys.
-// Only if the verification finds an unordered neighbour pair (adversarial / equal-prefix input) the keys are
-// re-sorted by a stable LSD over all four 64-bit words.
+// Digests are keccak outputs: uniform.  (top 32 bits, index) pairs go through a four-pass radix sort; the few rows that
+// agree in those bits (n^2 / 2^33 pairs) sit next to each other afterwards and the head of each such run orders it by the
+// full 32 bytes, in place (fix_runs_kernel).  A last pass verifies the order of the full keys; only if it finds an unordered
+// neighbour pair (runs longer than SORT_RUN_MAX: adversarial / equal-prefix input, not digests) the keys are re-sorted by a
+// stable LSD over all four 64-bit words.  The composite 64-byte keys of the storage stage sort by 64-bit words (below).
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -60,6 +61,64 @@ __global__ void check_sorted_kernel(const uint64_t *__restrict__ sorted, uint64_
     if (!less && !(allow_equal && !decided)) *flag = 1;  // equal keys also land here; harmless (the fallback is stable)
 }
 
+// keys32[i] = the four most significant bytes of digest i, idx[i] = i
+__global__ void extract_top32_kernel(const uint32_t *__restrict__ digests, uint64_t n, uint32_t *__restrict__ keys32,
+                                     uint32_t *__restrict__ idx_out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys32[i] = __byte_perm(digests[8 * i], 0, 0x0123);
+    idx_out[i] = (uint32_t)i;
+}
+
+// After a stable sort on the top 32 bits: rows that agree in those bits form short runs (n^2 / 2^33 pairs among n uniform
+// digests: 12 thousand at 10M, one row in a hundred at 100M).  The thread at the head of a run orders it by the full 32
+// bytes, stably, rows and permutation entries alike.  Runs longer than SORT_RUN_MAX are left alone — check_sorted_kernel
+// then sends the whole batch to the four-word LSD sort (keys with long common prefixes: not digests).
+constexpr int SORT_RUN_MAX = 16;
+__device__ __forceinline__ bool row_less(const uint32_t (&a)[8], const uint32_t (&b)[8]) {  // big-endian byte strings
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        uint32_t x = __byte_perm(a[w], 0, 0x0123), y = __byte_perm(b[w], 0, 0x0123);
+        if (x != y) return x < y;
+    }
+    return false;
+}
+__global__ void fix_runs_kernel(uint32_t *__restrict__ sorted /* [n][8] */, uint32_t *__restrict__ perm, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    const uint32_t top = sorted[8 * i];
+    if (sorted[8 * (i + 1)] != top || (i > 0 && sorted[8 * (i - 1)] == top)) return;  // not the head of a run of >= 2
+    int len = 2;
+    while (len <= SORT_RUN_MAX && i + len < n && sorted[8 * (i + len)] == top) len++;
+    if (len > SORT_RUN_MAX) return;
+    uint32_t row[SORT_RUN_MAX][8], src[SORT_RUN_MAX];
+    for (int k = 0; k < len; k++) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) row[k][w] = sorted[8 * (i + k) + w];
+        src[k] = perm[i + k];
+    }
+    for (int k = 1; k < len; k++) {  // insertion sort: stable
+        uint32_t r[8], sidx = src[k];
+#pragma unroll
+        for (int w = 0; w < 8; w++) r[w] = row[k][w];
+        int j = k;
+        while (j > 0 && row_less(r, row[j - 1])) {
+#pragma unroll
+            for (int w = 0; w < 8; w++) row[j][w] = row[j - 1][w];
+            src[j] = src[j - 1];
+            j--;
+        }
+#pragma unroll
+        for (int w = 0; w < 8; w++) row[j][w] = r[w];
+        src[j] = sidx;
+    }
+    for (int k = 0; k < len; k++) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) sorted[8 * (i + k) + w] = row[k][w];
+        perm[i + k] = src[k];
+    }
+}
+
 inline unsigned nblk(uint64_t n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
@@ -77,17 +136,21 @@ int32_t sort_digests_on_device(b200_ctx *c, const void *d_digests, uint64_t n, v
     uint64_t *ka = static_cast<uint64_t *>(keys_a.p), *kb = static_cast<uint64_t *>(keys_b.p);
     uint32_t *ia = static_cast<uint32_t *>(idx_a.p);
     const uint64_t *dig = static_cast<const uint64_t *>(d_digests);
-    size_t temp = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, temp, ka, kb, ia, d_perm, (int64_t)n, 0, 64, st));
-    TRY(ensure(c, c->cub_temp, temp));
-    extract_word_kernel<<<nblk(n), 256, 0, st>>>(dig, nullptr, 0, n, ka, ia);
-    CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, temp, ka, kb, ia, d_perm, (int64_t)n, 0, 64, st));
+    // fast path: four radix passes over the top 32 bits of every digest, then the short runs of equal tops ordered in place
+    size_t temp = 0, temp32 = 0;
+    uint32_t *ka32 = reinterpret_cast<uint32_t *>(ka), *kb32 = reinterpret_cast<uint32_t *>(kb);
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, temp, ka, kb, ia, d_perm, (int64_t)n, 0, 64, st));  // (the fallback's need)
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, temp32, ka32, kb32, ia, d_perm, (int64_t)n, 0, 32, st));
+    TRY(ensure(c, c->cub_temp, std::max(temp, temp32)));
+    extract_top32_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const uint32_t *>(d_digests), n, ka32, ia);
+    CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, temp32, ka32, kb32, ia, d_perm, (int64_t)n, 0, 32, st));
     gather32_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const uint4 *>(d_digests), d_perm, n,
                                              static_cast<uint4 *>(d_sorted));
+    fix_runs_kernel<<<nblk(n), 256, 0, st>>>(static_cast<uint32_t *>(d_sorted), d_perm, n);
     CU(cudaMemsetAsync(flag.p, 0, 4, st));
     check_sorted_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const uint64_t *>(d_sorted), n, static_cast<int *>(flag.p),
                                                  allow_equal ? 1 : 0);
-    c->launches += 4;
+    c->launches += 5;
     int *h_flag = reinterpret_cast<int *>(static_cast<uint8_t *>(c->pinned_small) + 3072);
     CU(cudaMemcpyAsync(h_flag, flag.p, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

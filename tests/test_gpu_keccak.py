@@ -108,6 +108,68 @@ def test_sort_keys32_equal_prefix_fallback(eng):
     assert (perm.cpu().numpy().astype(np.int64) == order).all()
 
 
+class _HostAsDevice:
+    """--emu only: the emulation treats host memory as device memory, so a numpy array can stand in for a CUDA tensor."""
+
+    def __init__(self, a):
+        self.a = a
+
+    def data_ptr(self):
+        return self.a.ctypes.data
+
+
+def _sort_keys32(eng, keys):
+    """b200_sort_keys32_dev over `keys`: CUDA tensors on a GPU, the arrays themselves under --emu."""
+    import os
+    n = len(keys)
+    if os.environ.get("B200_EMU"):
+        out, perm = np.empty_like(keys), np.empty(n, np.uint32)
+        eng.sort_keys32_dev(_HostAsDevice(keys), n, _HostAsDevice(out), _HostAsDevice(perm))
+        eng.sync()
+        return out, perm
+    import torch as th
+    t = th.from_numpy(keys).cuda()
+    d_out, d_perm = th.empty_like(t), th.empty(n, dtype=th.int32, device="cuda")
+    eng.sort_keys32_dev(t, n, d_out, d_perm)
+    eng.sync()
+    return d_out.cpu().numpy(), d_perm.cpu().numpy()
+
+
+def test_sort_keys32_runs_of_equal_leading_bytes(eng):
+    """The sort orders by the top 32 bits, then the head of every run of equal tops orders its run by all 32 bytes
+    (hash_sort.cu fix_runs_kernel): runs of 2 .. 16 rows (in place), 17 and more (left to the full four-word sort), runs at
+    both ends of the batch, rows that differ only in their last byte, and a crowd of ordinary rows around them."""
+    rng = np.random.default_rng(41)
+    groups = []
+    for ln in list(range(2, 20)) + [40, 2, 16, 17]:
+        g = rng.integers(0, 256, (ln, 32), dtype=np.uint8)
+        g[:, :4] = rng.integers(0, 256, 4, dtype=np.uint8)
+        if ln % 3 == 0:
+            g[:, 4:31] = g[0, 4:31]                      # equal up to the last byte
+            g[:, 31] = rng.permutation(256)[:ln].astype(np.uint8)
+        groups.append(g)
+    lo = np.zeros((3, 32), np.uint8)
+    lo[:, 31] = [3, 1, 2]                                 # a run at the very start of the sorted order
+    hi = np.full((2, 32), 255, np.uint8)
+    hi[:, 31] = [254, 9]                                  # and one at the very end
+    keys = np.concatenate(groups + [lo, hi, rng.integers(0, 256, (20_000, 32), dtype=np.uint8)])
+    keys = np.unique(keys, axis=0)
+    rng.shuffle(keys)
+    order = sort_rows(keys)
+    out, perm = _sort_keys32(eng, keys)
+    assert (out == keys[order]).all()
+    assert (perm.astype(np.int64) == order).all()
+    # without the long runs the in-place path alone must get it right (no fallback: the launch count tells)
+    short = np.concatenate([g for g in groups if len(g) <= 16] + [lo, hi, rng.integers(0, 256, (5_000, 32), dtype=np.uint8)])
+    short = np.unique(short, axis=0)
+    rng.shuffle(short)
+    l0 = eng.launch_count()
+    out, perm = _sort_keys32(eng, short)
+    assert eng.launch_count() - l0 == 5, "the four-word fallback ran"
+    order = sort_rows(short)
+    assert (out == short[order]).all() and (perm.astype(np.int64) == order).all()
+
+
 def test_device_resident_path(eng):
     import torch
     n = 100_000
