@@ -238,9 +238,11 @@ extern "C" B200_API int32_t b200_hash_partition_dev(b200_comm *m, const void *d_
     TRY(ensure(c, m->p_counts, 16 * 8));
     TRY(ensure(c, m->p_allcounts, 16 * 8 * (size_t)W));
     // 1. hash, owner rank of every digest, rows in destination order (stable: the order inside a destination is the input order)
+    phase_mark(c, "start");
     CU(cudaMemsetAsync(m->p_counts.p, 0, 16 * 8, st));
     if (n) {
         CU(launch_keccak256_fixed(d_in, msg_len, stride, n, m->p_dig.p, st, &c->launches));
+        phase_mark(c, "p:hash");
         CU(launch_partition_owner(static_cast<const uint8_t *>(m->p_dig.p), n, W, static_cast<uint8_t *>(m->p_owner.p),
                                   static_cast<unsigned long long *>(m->p_counts.p), st));
         CU(launch_iota(static_cast<uint32_t *>(m->p_iota.p), n, 0, st));
@@ -254,6 +256,7 @@ extern "C" B200_API int32_t b200_hash_partition_dev(b200_comm *m, const void *d_
                                    static_cast<const uint32_t *>(m->p_perm.p), n, static_cast<uint8_t *>(m->p_send_d.p),
                                    static_cast<uint8_t *>(m->p_send_v.p), st));
         c->launches += 4;
+        phase_mark(c, "p:owner+order+gather");
     }
     // 2. everybody learns everybody's per-destination counts (16 x u64 per rank)
     NC(nccl_api().AllGather(m->p_counts.p, m->p_allcounts.p, 16 * 8, ncclChar, m->comm, st));
@@ -265,6 +268,7 @@ extern "C" B200_API int32_t b200_hash_partition_dev(b200_comm *m, const void *d_
         send_off[r + 1] = send_off[r] + hc[16 * m->rank + r];
         recv_off[r + 1] = recv_off[r] + hc[16 * r + m->rank];
     }
+    phase_mark(c, "p:counts");
     const uint64_t n_recv = recv_off[W];
     *n_out = n_recv;
     if (n_recv > capacity) return fail(c, B200_ERR_INVALID_ARG, "hash_partition: %llu rows arrive, capacity is %llu",
@@ -291,6 +295,7 @@ extern "C" B200_API int32_t b200_hash_partition_dev(b200_comm *m, const void *d_
         }
     }
     NC(nccl_api().GroupEnd());
+    phase_mark(c, "p:exchange");
     // 4. sort what arrived by digest (the ETL collector's job), rows follow their keys
     if (n_recv) {
         TRY(sort_digests_on_device(c, m->p_recv_d.p, n_recv, d_sorted_keys32, static_cast<uint32_t *>(m->p_sortperm.p), c->sort_ka,
@@ -299,7 +304,9 @@ extern "C" B200_API int32_t b200_hash_partition_dev(b200_comm *m, const void *d_
                                 n_recv, static_cast<uint8_t *>(d_sorted_values), st));
         c->launches++;
     }
+    phase_mark(c, "p:sort");
     CU(cudaStreamSynchronize(st));
+    if (c->phase_timing) phase_report(c);
     return B200_OK;
 }
 

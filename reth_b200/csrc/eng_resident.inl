@@ -263,9 +263,13 @@ static int32_t trie_update_on_device(b200_trie *t, const uint8_t *d_keys, const 
     // Populous deep levels (more dirty nodes than a wave of warps can absorb cheaply) are climbed by one thread per
     // leaf with the register-resident sponge; the sparse levels above by one warp per node (shuffle sponge).
     int split = 65;  // 65: everything warp-cooperative
-    if (m > WARP_LEVEL_MAX)
+    static const uint64_t two_stage_min = [] {  // B200_WAVEFRONT_TWO_STAGE_MIN overrides the switch-over (tuning)
+        const char *e = getenv("B200_WAVEFRONT_TWO_STAGE_MIN");
+        return e ? strtoull(e, nullptr, 10) : (uint64_t)WARP_LEVEL_MAX;
+    }();
+    if (m > two_stage_min)
         for (int d = 0; d < 64; d++)
-            if (std::min<uint64_t>(m, t->level_count[d]) > WARP_LEVEL_MAX) {
+            if (std::min<uint64_t>(m, t->level_count[d]) > two_stage_min) {
                 split = d;
                 break;
             }

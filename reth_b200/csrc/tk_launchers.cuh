@@ -231,14 +231,26 @@ cudaError_t launch_partition_owner(const uint8_t *digests, uint64_t n, int world
     if (n) partition_owner_kernel<<<blocks_for(n, 256), 256, 0, st>>>(digests, n, world, owner, counts);
     return cudaGetLastError();
 }
-cudaError_t launch_partition_gather(const uint8_t *digests, const uint8_t *values, uint32_t vb, const uint32_t *perm, uint64_t n,
-                                    uint8_t *out_d, uint8_t *out_v, cudaStream_t st) {
-    if (n) partition_gather_kernel<<<blocks_for(n, 256), 256, 0, st>>>(digests, values, vb, perm, n, out_d, out_v);
+cudaError_t launch_gather_values(const uint8_t *values, uint32_t vb, const uint32_t *perm, uint64_t n, uint8_t *out_v, cudaStream_t st) {
+    if (!n || !vb) return cudaSuccess;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(values) | reinterpret_cast<uintptr_t>(out_v) | vb;
+    if (!(al & 7)) {
+        gather_rows_kernel<uint64_t><<<blocks_for(n * (vb / 8), 256), 256, 0, st>>>(reinterpret_cast<const uint64_t *>(values), vb / 8, perm, n,
+                                                                                 reinterpret_cast<uint64_t *>(out_v));
+    } else if (!(al & 3)) {
+        gather_rows_kernel<uint32_t><<<blocks_for(n * (vb / 4), 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(values), vb / 4, perm, n,
+                                                                                 reinterpret_cast<uint32_t *>(out_v));
+    } else {
+        gather_rows_kernel<uint8_t><<<blocks_for(n * vb, 256), 256, 0, st>>>(values, vb, perm, n, out_v);
+    }
     return cudaGetLastError();
 }
-cudaError_t launch_gather_values(const uint8_t *values, uint32_t vb, const uint32_t *perm, uint64_t n, uint8_t *out_v, cudaStream_t st) {
-    if (n && vb) gather_values_kernel<<<blocks_for(n, 256), 256, 0, st>>>(values, vb, perm, n, out_v);
-    return cudaGetLastError();
+cudaError_t launch_partition_gather(const uint8_t *digests, const uint8_t *values, uint32_t vb, const uint32_t *perm, uint64_t n,
+                                    uint8_t *out_d, uint8_t *out_v, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    partition_gather_kernel<<<blocks_for(n, 256), 256, 0, st>>>(digests, perm, n, out_d);
+    cudaError_t e = cudaGetLastError();
+    return e != cudaSuccess ? e : launch_gather_values(values, vb, perm, n, out_v, st);
 }
 cudaError_t launch_root_from_frontier(const FrontierEntryDev *fr, uint8_t *root, cudaStream_t st) {
     constexpr int B = 32;
