@@ -532,6 +532,11 @@ typedef struct {
     uint8_t *rlp;
     uint8_t *node_depth;   /* [n_nodes] nibbles of the target key that lead to the node: its path in a ProofNodes /
                               MultiProof map (crates/trie/common/src/proofs.rs) is target[..node_depth] */
+    uint32_t *node_masks;  /* [n_nodes] hash_mask << 16 | tree_mask of a branch node that reth stores in its trie tables (either
+                              mask non-empty), 0 otherwise (leaves, extensions, unstored branches): the entries of
+                              MultiProof::branch_node_masks / StorageMultiProof::branch_node_masks (proofs.rs:185,601;
+                              BranchNodeMasks, crates/trie/common/src/trie.rs:13-18) that Proof::with_branch_node_masks(true)
+                              collects from the hash builder's updated_branch_nodes (proof/mod.rs) */
     void *_owner;
 } b200_proofs;
 B200_API int32_t b200_dstate_account_proofs(b200_dstate *, const uint8_t *acct_keys32, uint64_t n, b200_proofs *out);

@@ -91,7 +91,7 @@ pub struct b200_changeset_hashes {
 #[repr(C)]
 pub struct b200_proofs {
     pub n_targets: u64, pub node_offset: *mut u64, pub n_nodes: u64, pub rlp_offset: *mut u64, pub rlp: *mut u8,
-    pub node_depth: *mut u8, pub _owner: *mut c_void,
+    pub node_depth: *mut u8, pub node_masks: *mut u32, pub _owner: *mut c_void,
 }
 pub const B200_COMM_ID_BYTES: usize = 128;
 

@@ -57,6 +57,7 @@ class Proofs(C.Structure):
         ("rlp_offset", C.POINTER(C.c_uint64)),
         ("rlp", C.POINTER(C.c_uint8)),
         ("node_depth", C.POINTER(C.c_uint8)),
+        ("node_masks", C.POINTER(C.c_uint32)),
         ("_owner", C.c_void_p),
     ]
 

@@ -54,27 +54,30 @@ static int32_t da_proofs(DArena *a, const uint32_t *d_trie_of_target, const uint
         n_nodes = ps[0] + ps32[0];
         n_bytes = ps[1] + ps[2];
     }
-    // host block: node_offset u64[n+1] | rlp_offset u64[n_nodes+1] | node_depth u8[n_nodes] | rlp bytes
-    size_t o_no = 0, o_ro = (n + 1) * 8, o_nd = o_ro + (n_nodes + 1) * 8, o_rlp = align_up(o_nd + n_nodes, 16),
-           total = o_rlp + n_bytes + 16;
+    // host block: node_offset u64[n+1] | rlp_offset u64[n_nodes+1] | node_masks u32[n_nodes] | node_depth u8[n_nodes] | rlp bytes
+    size_t o_no = 0, o_ro = (n + 1) * 8, o_nm = o_ro + (n_nodes + 1) * 8, o_nd = o_nm + n_nodes * 4,
+           o_rlp = align_up(o_nd + n_nodes, 16), total = o_rlp + n_bytes + 16;
     if (!(owner->host = pinned_block_alloc(total))) return fail(c, B200_ERR_OOM, "page-locked result block");
     uint8_t *h = static_cast<uint8_t *>(owner->host);
     out->node_offset = reinterpret_cast<uint64_t *>(h + o_no);
     out->rlp_offset = reinterpret_cast<uint64_t *>(h + o_ro);
     out->rlp = h + o_rlp;
     out->node_depth = h + o_nd;
+    out->node_masks = reinterpret_cast<uint32_t *>(h + o_nm);
     out->n_nodes = n_nodes;
     if (n) {
-        TRY(da_scratch(a, a->out, (n_nodes + 1) * 8 + n_nodes + n_bytes + 32));
+        TRY(da_scratch(a, a->out, (n_nodes + 1) * 8 + n_nodes * 5 + n_bytes + 32));
         uint64_t *d_ro = static_cast<uint64_t *>(a->out.p);
-        uint8_t *d_nd = reinterpret_cast<uint8_t *>(d_ro + n_nodes + 1);
+        uint32_t *d_nm = reinterpret_cast<uint32_t *>(d_ro + n_nodes + 1);
+        uint8_t *d_nd = reinterpret_cast<uint8_t *>(d_nm + n_nodes);
         uint8_t *d_rlp = d_nd + n_nodes;
-        CU(launch_dt_proof_write(d, d_trie_of_target, d_keys, n, node_base, byte_base, d_rlp, d_ro, d_nd, st));
+        CU(launch_dt_proof_write(d, d_trie_of_target, d_keys, n, node_base, byte_base, d_rlp, d_ro, d_nd, d_nm, st));
         c->launches++;
         CU(cudaMemcpyAsync(out->node_offset, node_base, n * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(out->rlp_offset, d_ro, n_nodes * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(out->rlp, d_rlp, n_bytes, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(out->node_depth, d_nd, n_nodes, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out->node_masks, d_nm, n_nodes * 4, cudaMemcpyDeviceToHost, st));
         TRY(sync_and_status(c));
     }
     out->node_offset[n] = n_nodes;

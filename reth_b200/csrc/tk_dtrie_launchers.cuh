@@ -144,8 +144,9 @@ cudaError_t launch_dt_proof_sizes(const DTrieDev &t, const uint32_t *trie_of_tar
 }
 cudaError_t launch_dt_proof_write(const DTrieDev &t, const uint32_t *trie_of_target, const uint8_t *keys, uint64_t n,
                                   const uint64_t *node_base, const uint64_t *byte_base, uint8_t *rlp, uint64_t *rlp_offset,
-                                  uint8_t *node_depth, cudaStream_t st) {
-    if (n) dt_proof_write_kernel<<<blocks_for(n, 64), 64, 0, st>>>(t, trie_of_target, keys, n, node_base, byte_base, rlp, rlp_offset, node_depth);
+                                  uint8_t *node_depth, uint32_t *node_masks, cudaStream_t st) {
+    if (n) dt_proof_write_kernel<<<blocks_for(n, 64), 64, 0, st>>>(t, trie_of_target, keys, n, node_base, byte_base, rlp, rlp_offset, node_depth,
+                                                                  node_masks);
     return cudaGetLastError();
 }
 cudaError_t launch_dt_find_leaves(const DTrieDev &t, const uint8_t *keys, uint64_t n, uint32_t *leaf_out, uint8_t *sroot_out, cudaStream_t st) {

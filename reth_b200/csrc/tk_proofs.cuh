@@ -88,16 +88,19 @@ static __device__ void dt_write_branch_rlp(const DTrieDev &t, uint32_t v, uint32
 // rlp + byte_base and their start offsets at rlp_offset[node_base ..].
 template <bool WRITE>
 static __device__ void dt_proof_walk(const DTrieDev &t, uint32_t trie, const uint8_t *key, uint32_t &n_nodes, uint64_t &n_bytes,
-                                     uint8_t *rlp, uint64_t byte_base, uint64_t *rlp_offset, uint8_t *node_depth, uint64_t node_base) {
+                                     uint8_t *rlp, uint64_t byte_base, uint64_t *rlp_offset, uint8_t *node_depth, uint32_t *node_masks,
+                                     uint64_t node_base) {
     n_nodes = 0;
     n_bytes = 0;
     uint32_t cur = t.troot[trie];
     int pd = -1;
     // depth = number of key nibbles that lead to the node: its path in a ProofNodes / MultiProof map is key[..depth]
-    auto begin_node = [&](uint32_t len, int depth) {
+    // masks: hash_mask << 16 | tree_mask of a branch node reth would store (BranchNodeMasks), 0 for everything else
+    auto begin_node = [&](uint32_t len, int depth, uint32_t masks = 0) {
         if (WRITE) {
             rlp_offset[node_base + n_nodes] = byte_base + n_bytes;
             node_depth[node_base + n_nodes] = (uint8_t)depth;
+            node_masks[node_base + n_nodes] = masks;
         }
         n_nodes++;
         n_bytes += len;
@@ -129,6 +132,8 @@ static __device__ void dt_proof_walk(const DTrieDev &t, uint32_t trie, const uin
         const uint8_t *nk = t.nkey + 32 * (uint64_t)v;
         uint32_t payload;
         const uint32_t blen = dt_branch_rlp_len(t, v, payload);
+        const ushort4 mk = t.nmasks[v];
+        const uint32_t masks = ((uint32_t)mk.z << 16) | mk.y;
         const bool ext = pd + 1 < d;
         const bool matches = dt_lcp(key, nk, (uint32_t)(pd + 1), (uint32_t)d) == (uint32_t)d;
         if (ext) {  // the extension node sits at a prefix of the key (we got here); the branch only if its nibbles match
@@ -152,10 +157,10 @@ static __device__ void dt_proof_walk(const DTrieDev &t, uint32_t trie, const uin
             }
             begin_node(elen, pd + 1);
             if (!matches) return;
-            begin_node(blen, d);
+            begin_node(blen, d, masks);
         } else {
             if (WRITE) dt_write_branch_rlp(t, v, payload, rlp + byte_base + n_bytes);
-            begin_node(blen, d);
+            begin_node(blen, d, masks);
         }
         pd = d;
         cur = t.nchild[16 * (uint64_t)v + dt_nib(key, (uint32_t)d)];
@@ -176,14 +181,15 @@ __global__ void dt_proof_size_kernel(DTrieDev t, const uint32_t *__restrict__ tr
         nn = 1;
         nb = 1;
     } else {
-        dt_proof_walk<false>(t, trie, keys + 32 * i, nn, nb, nullptr, 0, nullptr, nullptr, 0);
+        dt_proof_walk<false>(t, trie, keys + 32 * i, nn, nb, nullptr, 0, nullptr, nullptr, nullptr, 0);
     }
     node_count[i] = nn;
     byte_count[i] = nb;
 }
 __global__ void dt_proof_write_kernel(DTrieDev t, const uint32_t *__restrict__ trie_of_target, const uint8_t *__restrict__ keys,
                                       uint64_t n, const uint64_t *__restrict__ node_base, const uint64_t *__restrict__ byte_base,
-                                      uint8_t *__restrict__ rlp, uint64_t *__restrict__ rlp_offset, uint8_t *__restrict__ node_depth) {
+                                      uint8_t *__restrict__ rlp, uint64_t *__restrict__ rlp_offset, uint8_t *__restrict__ node_depth,
+                                      uint32_t *__restrict__ node_masks) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t trie = trie_of_target ? trie_of_target[i] : 0;
@@ -193,8 +199,9 @@ __global__ void dt_proof_write_kernel(DTrieDev t, const uint32_t *__restrict__ t
         rlp[byte_base[i]] = 0x80;
         rlp_offset[node_base[i]] = byte_base[i];
         node_depth[node_base[i]] = 0;
+        node_masks[node_base[i]] = 0;
     } else {
-        dt_proof_walk<true>(t, trie, keys + 32 * i, nn, nb, rlp, byte_base[i], rlp_offset, node_depth, node_base[i]);
+        dt_proof_walk<true>(t, trie, keys + 32 * i, nn, nb, rlp, byte_base[i], rlp_offset, node_depth, node_masks, node_base[i]);
     }
 }
 // the account leaf (= storage trie id) of one account key, DT_NONE when the account does not exist

@@ -266,7 +266,7 @@ cudaError_t launch_dt_proof_sizes(const DTrieDev &t, const uint32_t *trie_of_tar
                                   uint32_t *node_count, uint64_t *byte_count, cudaStream_t st);
 cudaError_t launch_dt_proof_write(const DTrieDev &t, const uint32_t *trie_of_target, const uint8_t *keys, uint64_t n,
                                   const uint64_t *node_base, const uint64_t *byte_base, uint8_t *rlp, uint64_t *rlp_offset,
-                                  uint8_t *node_depth, cudaStream_t st);
+                                  uint8_t *node_depth, uint32_t *node_masks, cudaStream_t st);
 cudaError_t launch_dt_find_leaves(const DTrieDev &t, const uint8_t *keys, uint64_t n, uint32_t *leaf_out, uint8_t *sroot_out, cudaStream_t st);
 cudaError_t launch_dt_target_tries(const uint64_t *seg_offsets, uint64_t n_accounts, const uint32_t *leaf_of, uint64_t n_targets,
                                    uint32_t *trie_of_target, cudaStream_t st);

@@ -825,17 +825,20 @@ class DynamicState:
                                                                  None, None, C.byref(s)))
         return s.as_dict()
 
-    def _take_proofs(self, p: Proofs, with_depths: bool = False) -> list:
+    def _take_proofs(self, p: Proofs, with_depths: bool = False, with_masks: bool = False) -> list:
         n, nn = int(p.n_targets), int(p.n_nodes)
         res = []
         if n:
             no = np.ctypeslib.as_array(p.node_offset, (n + 1,))
             ro = np.ctypeslib.as_array(p.rlp_offset, (nn + 1,))
             nd = np.ctypeslib.as_array(p.node_depth, (max(nn, 1),))
+            nm = np.ctypeslib.as_array(p.node_masks, (max(nn, 1),))
             blob = np.ctypeslib.as_array(p.rlp, (max(int(ro[nn]), 1),)).tobytes()
             for t in range(n):
                 rng_ = range(int(no[t]), int(no[t + 1]))
-                if with_depths:
+                if with_masks:
+                    res.append([(int(nd[k]), blob[int(ro[k]):int(ro[k + 1])], int(nm[k])) for k in rng_])
+                elif with_depths:
                     res.append([(int(nd[k]), blob[int(ro[k]):int(ro[k + 1])]) for k in rng_])
                 else:
                     res.append([blob[int(ro[k]):int(ro[k + 1])] for k in rng_])
@@ -857,9 +860,10 @@ class DynamicState:
 
     def multiproof(self, targets: dict) -> dict:
         """Proof::multiproof(MultiProofTargets) in one device call.  targets: {hashed address: iterable of hashed slots}.
-        -> {"account_subtree": {path: rlp}, "storages": {address: {"root": bytes, "subtree": {path: rlp}}}} — the maps of
-        MultiProof / StorageMultiProof (crates/trie/common/src/proofs.rs:180-188,594-602; branch_node_masks are not
-        produced)."""
+        -> {"account_subtree": {path: rlp}, "branch_node_masks": {path: (hash_mask, tree_mask)},
+            "storages": {address: {"root": bytes, "subtree": {path: rlp}, "branch_node_masks": {...}}}} — the maps of
+        MultiProof / StorageMultiProof (crates/trie/common/src/proofs.rs:180-188,594-602); branch_node_masks holds the
+        branch nodes of the proof that reth stores in its trie tables (what Proof::with_branch_node_masks(true) collects)."""
         addrs = sorted(targets)
         n = len(addrs)
         ak = np.frombuffer(b"".join(addrs), np.uint8).reshape(n, 32) if n else np.zeros((0, 32), np.uint8)
@@ -875,19 +879,23 @@ class DynamicState:
         self.engine._check(self.engine.lib.b200_dstate_multiproof(self.handle, _ptr(ak), n, _ptr(so), _ptr(sk), C.byref(pa), _ptr(sroots),
                                                                   C.byref(ps)))
         nib = lambda k: bytes(x for b in k for x in (b >> 4, b & 15))
-        out = {"account_subtree": {}, "storages": {}}
-        for key, nodes in zip(addrs, self._take_proofs(pa, with_depths=True)):
+        out = {"account_subtree": {}, "branch_node_masks": {}, "storages": {}}
+        for key, nodes in zip(addrs, self._take_proofs(pa, with_masks=True)):
             kn = nib(key)
-            for depth, rlp in nodes:
+            for depth, rlp, masks in nodes:
                 out["account_subtree"][kn[:depth]] = rlp
-        sp = self._take_proofs(ps, with_depths=True)
+                if masks:
+                    out["branch_node_masks"][kn[:depth]] = (masks >> 16, masks & 0xFFFF)
+        sp = self._take_proofs(ps, with_masks=True)
         for i, a in enumerate(addrs):
-            sub = {}
+            sub, bm = {}, {}
             for j in range(offs[i], offs[i + 1]):
                 kn = nib(slots[j])
-                for depth, rlp in sp[j]:
+                for depth, rlp, masks in sp[j]:
                     sub[kn[:depth]] = rlp
-            out["storages"][a] = {"root": sroots[i].tobytes(), "subtree": sub}
+                    if masks:
+                        bm[kn[:depth]] = (masks >> 16, masks & 0xFFFF)
+            out["storages"][a] = {"root": sroots[i].tobytes(), "subtree": sub, "branch_node_masks": bm}
         return out
 
     def account_proofs(self, acct_keys) -> list:

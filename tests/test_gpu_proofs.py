@@ -287,4 +287,26 @@ def test_multiproof_batch_equals_the_single_proofs(eng):
                     ext = list(nib(enc))[1:] if enc[0] & 0x10 else list(nib(enc))[2:]
                     path = path + bytes(ext)
         assert mp["storages"][a]["subtree"] == want
+    # branch_node_masks (Proof::with_branch_node_masks): exactly the branch nodes of the proof that the hash builder stores —
+    # the oracle's updated_branch_nodes of a full build, restricted to the proof's paths (the root path is left aside:
+    # TrieUpdates drops it, the proof may carry it)
+    sroots = oracle.storage_roots(skeys, svals, offs)
+    _, acct_upd = oracle.state_root(keys, accs, sroots, want_updates=True)
+    stored = {bytes(r[1]): (r[4], r[3]) for r in acct_upd}                       # path -> (hash_mask, tree_mask)
+    got = {pth: m for pth, m in mp["branch_node_masks"].items() if pth}
+    on_proof = {pth for pth in mp["account_subtree"] if pth}
+    assert got == {pth: m for pth, m in stored.items() if pth in on_proof} and got
+    _, sto_upd = oracle.storage_roots(skeys, svals, offs, want_updates=True)
+    index_of = {keys[i].tobytes(): i for i in range(n)}
+    checked = 0
+    for a in addrs:
+        if a not in index_of:
+            assert mp["storages"][a]["branch_node_masks"] == {}
+            continue
+        stored = {bytes(r[1]): (r[4], r[3]) for r in sto_upd if r[0] == index_of[a]}
+        sub = mp["storages"][a]
+        got = {pth: m for pth, m in sub["branch_node_masks"].items() if pth}
+        assert got == {pth: m for pth, m in stored.items() if pth in sub["subtree"]}
+        checked += len(got)
+    assert checked > 0
     ds.close()
