@@ -168,6 +168,31 @@ def test_node_heads_across_trie_boundaries_and_long_spans(eng):
     assert upd == o_upd
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_node_heads_at_block_boundaries_of_the_gap_pass(eng, seed):
+    """gap_keys_kernel works on 256 gaps per CTA behind a 32-gap window of the previous block: tries whose sizes put trie
+    boundaries, first gaps and long same-nibble spans on and around multiples of 256 (and of 32), random and clustered keys."""
+    rng = np.random.default_rng(500 + seed)
+    sizes = [255, 1, 256, 257, 31, 33, 32, 512, 513, 2, 254, 0, 258, 1023, 1, 1025, 224, 288, 16, 240]
+    rng.shuffle(sizes)
+    segs = []
+    for n in sizes:
+        k = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        if n and rng.random() < 0.5:                      # clustered: few top nibbles, long runs of deeper gaps
+            k[:, 0] = (rng.choice([3, 3, 3, 9], n).astype(np.uint8) << 4) | (k[:, 0] & 0x0F)
+            k[: n // 2, 1] = 0x55
+        k = np.unique(k, axis=0)
+        segs.append(k[sort_rows(k)] if len(k) else k)
+    offs = np.zeros(len(segs) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(x) for x in segs])
+    keys = np.concatenate(segs)
+    vals = u256_be(rng.integers(1, 1 << 62, len(keys)))
+    roots, upd = eng.storage_roots(keys, vals, offs, want_updates=True)
+    o_roots, o_upd = oracle.storage_roots(keys, vals, offs, want_updates=True, threads=4)
+    assert (roots == o_roots).all()
+    assert upd == o_upd
+
+
 @pytest.mark.parametrize("mode", ["u64", "mixed"])
 def test_storage_forest_random(eng, mode):
     rng = np.random.default_rng(4)
