@@ -178,6 +178,10 @@ typedef struct {
     uint64_t hashed_nodes;     /* keccak digests produced (node RLP >= 32 bytes, plus roots) */
     uint64_t levels;           /* populated trie levels processed */
     double device_ms;          /* stream time of the build, measured with CUDA events */
+    uint64_t keccak_f;         /* Keccak-f[1600] permutations of a from-scratch build: hashed_nodes + the second .. fourth rate
+                                  block of every branch node by its child-count class (4-7 children: 2 blocks, 8-12: 3, 13-16: 4;
+                                  exact when no child of such a node is inlined, i.e. for hashed keys).  0 where it is not
+                                  counted (ordered roots, resident / dynamic updates). */
 } b200_stats;
 
 /* ------------------------------------------------------------------------------------------------ roots

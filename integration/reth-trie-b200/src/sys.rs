@@ -59,6 +59,7 @@ pub struct b200_stats {
     pub hashed_nodes: u64,
     pub levels: u64,
     pub device_ms: f64,
+    pub keccak_f: u64,
 }
 
 #[repr(C)]

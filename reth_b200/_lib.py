@@ -70,6 +70,7 @@ class Stats(C.Structure):
         ("hashed_nodes", C.c_uint64),
         ("levels", C.c_uint64),
         ("device_ms", C.c_double),
+        ("keccak_f", C.c_uint64),
     ]
 
     def as_dict(self):

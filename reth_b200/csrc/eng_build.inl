@@ -32,6 +32,7 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
     out.n_nodes = 0;
     out.levels = 0;
     if (n == 0) return B200_OK;
+    c->extra_blocks_valid = !ordered;  // (items of an ordered trie span several rate blocks themselves: not counted)
 
     ENSURE(Lp, n + 1);
     ENSURE(nibs, n + 1);
@@ -177,6 +178,7 @@ static int32_t build_forest(b200_ctx *c, const uint8_t *d_keys, uint64_t n, cons
         if (!cnt) continue;
         out.levels++;
         out.level_count[d] = cnt;
+        c->extra_blocks += (uint64_t)hc[1] + 2ull * hc[2] + 3ull * hc[3];
         if (cnt <= WARP_LEVEL_MAX) {  // about one wave of warps: latency-bound, one warp per node
             CU(launch_branch_level(f, norder, pos, pos + cnt, d, -1, st));
             c->launches++;

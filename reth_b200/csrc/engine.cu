@@ -330,6 +330,7 @@ static int32_t sync_and_status(b200_ctx *c) {
         const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(ps + 8);
         c->stats.hashed_nodes = cnt[CNT_HASHED];
         c->stats.extension_nodes = cnt[CNT_EXT];
+        c->stats.keccak_f = c->extra_blocks_valid ? c->stats.hashed_nodes + c->extra_blocks : 0;
         c->stats_pending = false;
     }
     // the oldest unreported violation wins; reporting clears both words (a later b200_sync returns OK again)
@@ -345,6 +346,8 @@ static int32_t reset_build_state(b200_ctx *c) {
                           reinterpret_cast<unsigned long long *>(small_u32(c) + SM_COUNTERS), c->stream));
     c->stats = b200_stats{};
     c->stats_wavefront = false;
+    c->extra_blocks = 0;
+    c->extra_blocks_valid = false;
     CU(cudaEventRecord(c->ev0, c->stream));
     phase_mark(c, "start");
     return B200_OK;

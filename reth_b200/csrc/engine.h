@@ -36,6 +36,8 @@ struct b200_ctx {
     b200_stats stats{};
     bool stats_pending = false;
     bool stats_wavefront = false;  // branches_added of the last build comes from the wavefront's node counter
+    uint64_t extra_blocks = 0;     // rate blocks beyond the first of the branch nodes built since reset_build_state
+    bool extra_blocks_valid = false;  // every node of this call went through build_forest's class histogram
     // scratch (grow-only)
     DevBuf Lp, nibs, leaf_ref, leaf_meta, S, E, iota, depth_sorted, gap_sorted, head, node_start,
         node_ref, node_meta, node_l, node_r, node_masks, cub_temp, small, sroots, buckets;

@@ -43,7 +43,7 @@ def test_struct_layouts_match_header():
     from reth_b200._lib import FrontierEntry, Stats, Updates
     assert ACCOUNT_DTYPE.itemsize == 72
     assert ctypes.sizeof(FrontierEntry) == 68
-    assert ctypes.sizeof(Stats) == 48
+    assert ctypes.sizeof(Stats) == 56
     assert ctypes.sizeof(Updates) == 8 * 10
 
 

@@ -235,6 +235,32 @@ def test_c1_config(eng):
     assert root == oracle.state_root(hashed[order], accs)
 
 
+def test_stats_count_the_keccak_permutations(eng):
+    """b200_stats.keccak_f (the numerator of bench.py's alu_frac) == the permutations the oracle's HashBuilder executes for the
+    same state: digests plus the extra rate blocks of the 4..16-child branch nodes; hashed_nodes == the oracle's digests."""
+    n = 20_000
+    akeys, accs = synth_accounts(52, n)
+    counts = np.where(np.arange(n) % 3 == 0, 16, 0) + np.where(np.arange(n) % 499 == 0, 700, 0)
+    skeys, svals, offs = synth_storage(53, counts, value_mode="u64")
+    oracle.stats_reset()
+    o_root = oracle.state_root_full(akeys, accs, skeys, svals, offs)
+    want = oracle.stats()
+    root, st = eng.state_root_full(akeys, accs, skeys, svals, offs, want_stats=True)
+    assert root == o_root
+    assert st["hashed_nodes"] == want["hashed_nodes"]
+    assert st["keccak_f"] == want["keccak_f"] > st["hashed_nodes"]
+    # not counted where the child-count classes do not apply
+    assert eng.ordered_roots(*pack_lists_for_stats(), want_stats=True)[1]["keccak_f"] == 0
+
+
+def pack_lists_for_stats():
+    items = [bytes([i]) * (40 + 7 * i) for i in range(20)]
+    values = np.frombuffer(b"".join(items), np.uint8)
+    vo = np.zeros(len(items) + 1, np.uint64)
+    vo[1:] = np.cumsum([len(x) for x in items])
+    return values, vo, np.array([0, len(items)], np.uint64)
+
+
 def test_full_state_random(eng):
     n = 30_000
     akeys, accs = synth_accounts(12, n)
