@@ -111,6 +111,10 @@ B200_API int32_t b200_hash_sort_keys_dev(b200_ctx *, const void *d_in, uint32_t 
  * came from.  A duplicate (address, slot) pair yields B200_ERR_UNSORTED. */
 B200_API int32_t b200_hash_sort_storage(b200_ctx *, const uint8_t *addresses20, uint32_t n_addr, const uint32_t *addr_index,
                                         const uint8_t *slots32, uint64_t n, uint8_t *out_sorted64, uint32_t *out_perm);
+/* The same with every array in device memory (d_sorted64: n x 64 bytes, d_perm_u32: n x u32); synchronises once for the
+ * verification of the order, like b200_hash_sort_keys_dev. */
+B200_API int32_t b200_hash_sort_storage_dev(b200_ctx *, const void *d_addresses20, uint32_t n_addr, const void *d_addr_index_u32,
+                                            const void *d_slots32, uint64_t n, void *d_sorted64, void *d_perm_u32);
 /* The sort half alone: n 32-byte keys (already digests) -> ascending order + permutation. */
 B200_API int32_t b200_sort_keys32_dev(b200_ctx *, const void *d_keys32, uint64_t n, void *d_sorted32, void *d_perm_u32);
 

@@ -109,6 +109,8 @@ unsafe extern "C" {
     pub fn b200_keccak256_fixed(ctx: *mut b200_ctx, input: *const u8, msg_len: u32, stride: u32, n: u64, out32: *mut u8) -> i32;
     pub fn b200_hash_sort_keys(ctx: *mut b200_ctx, input: *const u8, msg_len: u32, stride: u32, n: u64,
                                out_sorted32: *mut u8, out_perm: *mut u32) -> i32;
+    pub fn b200_hash_sort_storage_dev(ctx: *mut b200_ctx, d_addresses20: *const c_void, n_addr: u32, d_addr_index: *const c_void,
+                                      d_slots32: *const c_void, n: u64, d_sorted64: *mut c_void, d_perm: *mut c_void) -> i32;
     pub fn b200_hash_sort_storage(ctx: *mut b200_ctx, addresses20: *const u8, n_addr: u32, addr_index: *const u32,
                                   slots32: *const u8, n: u64, out_sorted64: *mut u8, out_perm: *mut u32) -> i32;
 

@@ -150,6 +150,7 @@ def load():
     sig("b200_hash_sort_keys_dev", i32, vp, vp, u32, u32, u64, vp, vp)
     sig("b200_sort_keys32_dev", i32, vp, vp, u64, vp, vp)
     sig("b200_hash_sort_storage", i32, vp, vp, u32, vp, vp, u64, vp, vp)
+    sig("b200_hash_sort_storage_dev", i32, vp, vp, u32, vp, vp, u64, vp, vp)
     sig("b200_updates_release", None, PU)
     sig("b200_account_trie_rows", i32, PU, i32, C.POINTER(Rows))
     sig("b200_storage_trie_rows", i32, PU, vp, u64, i32, C.POINTER(Rows))

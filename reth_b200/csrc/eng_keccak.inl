@@ -166,6 +166,23 @@ int32_t sort_composite_on_device(b200_ctx *c, const void *d_ha, uint32_t n_addr,
                                  const void *d_hs, uint64_t n, void *d_sorted, uint32_t *d_perm, DevBuf &keys_a,
                                  DevBuf &keys_b, DevBuf &idx_a, DevBuf &flag, bool allow_equal = false);
 
+// The same entirely on the device (inputs and outputs in HBM).
+extern "C" B200_API int32_t b200_hash_sort_storage_dev(b200_ctx *c, const void *d_addresses20, uint32_t n_addr,
+                                                       const void *d_addr_index, const void *d_slots32, uint64_t n,
+                                                       void *d_sorted64, void *d_perm) {
+    if (!c || (n && (!d_addresses20 || !d_addr_index || !d_slots32 || !d_sorted64 || !d_perm)) || (n && !n_addr))
+        return fail(c, B200_ERR_INVALID_ARG, "bad argument");
+    if (n == 0) return B200_OK;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ENSURE(in_d, (size_t)n_addr * 32);  // address digests
+    ENSURE(out_a, n * 32);              // slot digests
+    CU(launch_keccak256_fixed(d_addresses20, 20, 20, n_addr, c->in_d.p, c->stream, &c->launches));
+    CU(launch_keccak256_fixed(d_slots32, 32, 32, n, c->out_a.p, c->stream, &c->launches));
+    return sort_composite_on_device(c, c->in_d.p, n_addr, static_cast<const uint32_t *>(d_addr_index), c->out_a.p, n, d_sorted64,
+                                    static_cast<uint32_t *>(d_perm), c->sort_ka, c->sort_kb, c->sort_ia, c->sort_flag);
+}
+
 // StorageHashingStage full pass: hash n_addr addresses once, n slot keys, sort entries by keccak(address) || keccak(slot).
 extern "C" B200_API int32_t b200_hash_sort_storage(b200_ctx *c, const uint8_t *addresses20, uint32_t n_addr,
                                                    const uint32_t *addr_index, const uint8_t *slots32, uint64_t n,

@@ -103,7 +103,7 @@ extern "C" B200_API void b200_destroy(b200_ctx *c) {
                       &c->upd_flags, &c->upd_nh, &c->upd_ids, &c->upd_prefix, &c->upd_key, &c->upd_key2, &c->upd_ids2, &c->in_a, &c->in_b, &c->in_c,
                       &c->in_d, &c->in_e, &c->out_a, &c->chunk_in[0], &c->chunk_in[1], &c->chunk_in[2], &c->chunk_out[0],
                       &c->chunk_out[1], &c->chunk_out[2], &c->sort_ka, &c->sort_kb, &c->sort_ia, &c->sort_flag, &c->sort_perm,
-                      &c->sort_out, &c->node_key, &c->node_key2, &c->node_ids, &c->node_order, &c->ord_keys, &c->ord_knib,
+                      &c->sort_out, &c->sort_aux[0], &c->sort_aux[1], &c->sort_aux[2], &c->sort_aux[3], &c->node_key, &c->node_key2, &c->node_ids, &c->node_order, &c->ord_keys, &c->ord_knib,
                       &c->ord_item, &c->ord_sched, &c->ord_sched2, &c->ord_pos, &c->ord_order};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);

@@ -43,6 +43,7 @@ struct b200_ctx {
         node_ref, node_meta, node_l, node_r, node_masks, cub_temp, small, sroots, buckets;
     DevBuf upd_flags, upd_nh, upd_ids, upd_prefix, upd_key, upd_key2, upd_ids2;
     DevBuf sort_ka, sort_kb, sort_ia, sort_flag, sort_perm, sort_out;
+    DevBuf sort_aux[4];  // composite sort: sorted address digests, their permutation, head flags / dense ranks, rank by address
     DevBuf node_key, node_key2, node_ids, node_order;
     DevBuf ord_keys, ord_knib, ord_item, ord_sched, ord_sched2, ord_pos, ord_order;  // ordered tries (eng_ordered.inl)
     // staging for host-pointer entry points

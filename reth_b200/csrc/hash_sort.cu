@@ -6,7 +6,9 @@
 // agree in those bits (n^2 / 2^33 pairs) sit next to each other afterwards and the head of each such run orders it by the
 // full 32 bytes, in place (fix_runs_kernel).  A last pass verifies the order of the full keys; only if it finds an unordered
 // neighbour pair (runs longer than SORT_RUN_MAX: adversarial / equal-prefix input, not digests) the keys are re-sorted by a
-// stable LSD over all four 64-bit words.  The composite 64-byte keys of the storage stage sort by 64-bit words (below).
+// stable LSD over all four 64-bit words.  The composite 64-byte keys of the storage stage: the (few) address digests are sorted
+// on their own, every entry takes the dense rank of its address, and the entries go through four passes over the top 32 bits
+// of the slot digest plus ceil(log2(ranks)) bits of the rank (below).
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -229,6 +231,76 @@ __global__ void check_sorted_composite_kernel(const uint64_t *__restrict__ sorte
     else if (!less) atomicMax(flag, 1);     // out of order: the prefix passes were not enough
 }
 
+// ---- fast path of the composite sort: (dense rank of the address digest, top 32 bits of the slot digest)
+// head[j] = 1 iff sorted address digest j differs from its predecessor (j = 0: 0), so that the inclusive sum is the dense rank
+__global__ void addr_heads_kernel(const uint64_t *__restrict__ sorted_ha, uint32_t n_addr, uint32_t *__restrict__ head) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_addr) return;
+    bool h = false;
+    if (j > 0)
+        for (int w = 0; w < 4; w++) h = h || sorted_ha[4 * (uint64_t)j + w] != sorted_ha[4 * (uint64_t)(j - 1) + w];
+    head[j] = h ? 1u : 0u;
+}
+__global__ void addr_rank_scatter_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ dense, uint32_t n_addr,
+                                         uint32_t *__restrict__ rank) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_addr) rank[perm[j]] = dense[j];
+}
+__global__ void extract_slot_top32_kernel(const uint32_t *__restrict__ hs, uint64_t n, uint32_t *__restrict__ keys32,
+                                          uint32_t *__restrict__ idx_out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys32[i] = __byte_perm(hs[8 * i], 0, 0x0123);
+    idx_out[i] = (uint32_t)i;
+}
+__global__ void extract_addr_rank_kernel(const uint32_t *__restrict__ addr_index, const uint32_t *__restrict__ rank,
+                                         const uint32_t *__restrict__ order, uint64_t n, uint32_t *__restrict__ keys32) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys32[i] = rank[addr_index[order[i]]];
+}
+// rows of 64 bytes that agree in the address digest and in the top 32 bits of the slot digest: ordered by the slot digest,
+// in place, by the head of the run (fix_runs_kernel's job for the composite keys; longer runs are left to the fallback)
+__global__ void fix_runs_composite_kernel(uint32_t *__restrict__ sorted /* [n][16] */, uint32_t *__restrict__ perm, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    auto same = [&](uint64_t x, uint64_t y) {  // address digest and slot top equal
+        bool e = true;
+#pragma unroll
+        for (int w = 0; w < 9; w++) e = e && sorted[16 * x + w] == sorted[16 * y + w];
+        return e;
+    };
+    if (!same(i, i + 1) || (i > 0 && same(i - 1, i))) return;
+    int len = 2;
+    while (len <= SORT_RUN_MAX && i + len < n && same(i, i + len)) len++;
+    if (len > SORT_RUN_MAX) return;
+    uint32_t row[SORT_RUN_MAX][8], src[SORT_RUN_MAX];  // the slot digests (the address part of the run is one value)
+    for (int k = 0; k < len; k++) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) row[k][w] = sorted[16 * (i + k) + 8 + w];
+        src[k] = perm[i + k];
+    }
+    for (int k = 1; k < len; k++) {
+        uint32_t r[8], sidx = src[k];
+#pragma unroll
+        for (int w = 0; w < 8; w++) r[w] = row[k][w];
+        int j = k;
+        while (j > 0 && row_less(r, row[j - 1])) {
+#pragma unroll
+            for (int w = 0; w < 8; w++) row[j][w] = row[j - 1][w];
+            src[j] = src[j - 1];
+            j--;
+        }
+#pragma unroll
+        for (int w = 0; w < 8; w++) row[j][w] = r[w];
+        src[j] = sidx;
+    }
+    for (int k = 0; k < len; k++) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) sorted[16 * (i + k) + 8 + w] = row[k][w];
+        perm[i + k] = src[k];
+    }
+}
+
 __global__ void check_index_kernel(const uint32_t *__restrict__ addr_index, uint64_t n, uint32_t n_addr, int *__restrict__ flag) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && addr_index[i] >= n_addr) *flag = 3;
@@ -283,8 +355,41 @@ int32_t sort_composite_on_device(b200_ctx *c, const void *d_ha, uint32_t n_addr,
         CU(cudaStreamSynchronize(st));
         return B200_OK;
     };
-    const int fast[2] = {4, 0};  // slot-digest prefix, then (stable) address-digest prefix
-    TRY(lsd(fast, 2));
+    // fast path: the addresses are few — sort their digests on their own and give every entry the dense rank of its
+    // address; then four radix passes over the top 32 bits of the slot digests and ceil(log2(ranks)) bits of the rank
+    // (stable: slot order survives inside an address), the rare rows that agree in both ordered in place, verification.
+    {
+        for (int k = 0; k < 4; k++) TRY(ensure(c, c->sort_aux[k], (size_t)n_addr * (k == 0 ? 32 : 4) + 16));
+        uint8_t *sorted_ha = static_cast<uint8_t *>(c->sort_aux[0].p);
+        uint32_t *perm_ha = static_cast<uint32_t *>(c->sort_aux[1].p), *dense = static_cast<uint32_t *>(c->sort_aux[2].p),
+                 *rank = static_cast<uint32_t *>(c->sort_aux[3].p);
+        TRY(sort_digests_on_device(c, d_ha, n_addr, sorted_ha, perm_ha, keys_a, keys_b, idx_a, flag, true));
+        addr_heads_kernel<<<nblk(n_addr), 256, 0, st>>>(reinterpret_cast<const uint64_t *>(sorted_ha), n_addr, dense);
+        size_t t_scan = 0, t32 = 0;
+        CU(cub::DeviceScan::InclusiveSum(nullptr, t_scan, dense, dense, (int64_t)n_addr, st));
+        uint32_t *ka32 = reinterpret_cast<uint32_t *>(ka), *kb32 = reinterpret_cast<uint32_t *>(kb);
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, t32, ka32, kb32, ia, d_perm, (int64_t)n, 0, 32, st));
+        TRY(ensure(c, c->cub_temp, std::max(temp, std::max(t_scan, t32))));
+        CU(cub::DeviceScan::InclusiveSum(c->cub_temp.p, t_scan, dense, dense, (int64_t)n_addr, st));
+        addr_rank_scatter_kernel<<<nblk(n_addr), 256, 0, st>>>(perm_ha, dense, n_addr, rank);
+        extract_slot_top32_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const uint32_t *>(d_hs), n, ka32, ia);
+        CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t32, ka32, kb32, ia, d_perm, (int64_t)n, 0, 32, st));
+        extract_addr_rank_kernel<<<nblk(n), 256, 0, st>>>(d_addr_index, rank, d_perm, n, ka32);
+        int rank_bits = 1;
+        while (rank_bits < 32 && (1ull << rank_bits) < (uint64_t)n_addr) rank_bits++;
+        CU(cub::DeviceRadixSort::SortPairs(c->cub_temp.p, t32, ka32, kb32, d_perm, ia, (int64_t)n, 0, rank_bits, st));
+        CU(cudaMemcpyAsync(d_perm, ia, n * 4, cudaMemcpyDeviceToDevice, st));
+        gather_composite_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const uint4 *>(d_ha), d_addr_index,
+                                                        static_cast<const uint4 *>(d_hs), d_perm, n,
+                                                        static_cast<uint4 *>(d_sorted));
+        fix_runs_composite_kernel<<<nblk(n), 256, 0, st>>>(static_cast<uint32_t *>(d_sorted), d_perm, n);
+        CU(cudaMemsetAsync(flag.p, 0, 4, st));
+        check_sorted_composite_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const uint64_t *>(d_sorted), n,
+                                                              static_cast<int *>(flag.p), allow_equal ? 1 : 0);
+        c->launches += 11;
+        CU(cudaMemcpyAsync(h_flag, flag.p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
     if (*h_flag == 1) {
         const int full[8] = {7, 6, 5, 4, 3, 2, 1, 0};
         TRY(lsd(full, 8));

@@ -236,6 +236,10 @@ class Engine:
         self._check(self.lib.b200_hash_sort_keys_dev(self.ctx, t_in.data_ptr(), msg_len, stride, n,
                                                      t_sorted.data_ptr(), t_perm.data_ptr()))
 
+    def hash_sort_storage_dev(self, t_addresses, n_addr: int, t_addr_index, t_slots, n: int, t_sorted64, t_perm):
+        self._check(self.lib.b200_hash_sort_storage_dev(self.ctx, t_addresses.data_ptr(), n_addr, t_addr_index.data_ptr(),
+                                                        t_slots.data_ptr(), n, t_sorted64.data_ptr(), t_perm.data_ptr()))
+
     def sort_keys32_dev(self, t_keys, n: int, t_sorted, t_perm):
         self._check(self.lib.b200_sort_keys32_dev(self.ctx, t_keys.data_ptr(), n, t_sorted.data_ptr(), t_perm.data_ptr()))
 

@@ -201,6 +201,32 @@ def test_hash_sort_storage_composite(eng):
     assert (perm.astype(np.int64) == order).all()
 
 
+def test_hash_sort_storage_large_storage_and_repeated_addresses(eng):
+    """The composite sort orders by (dense rank of the address digest, top 32 bits of the slot digest) and then orders the rows
+    that agree in both in place (hash_sort.cu fix_runs_composite_kernel): one contract with 400k slots has ~18 pairs of slot
+    digests with equal top 32 bits; the address table lists one address twice (equal digests share a rank) and holds
+    addresses no entry refers to."""
+    rng = np.random.default_rng(12)
+    n_addr, n = 300, 420_000
+    addrs = random_keys(31, n_addr)[:, :20].copy()
+    addrs[17] = addrs[5]                                    # the same address under two indices
+    owner = rng.integers(100, 200, n).astype(np.uint32)     # indices 0..99 and 200..299 are never used
+    owner[:400_000] = 150
+    owner[400_000:400_500] = 5
+    owner[400_500:401_000] = 17
+    slots = random_keys(32, n)
+    keys, perm = eng.hash_sort_storage(addrs, owner, slots)
+    ha = oracle.keccak256_fixed(addrs, threads=4)
+    hs = oracle.keccak256_fixed(slots, threads=4)
+    comp = np.concatenate([ha[owner], hs], axis=1)
+    v = comp.view(">u8")
+    order = np.lexsort(tuple(v[:, i] for i in range(7, -1, -1)))
+    top = comp[order][:, :36]
+    assert (np.all(top[1:] == top[:-1], axis=1)).sum() >= 5, "the input was meant to hold rows with equal (address, slot top)"
+    assert (keys == comp[order]).all()
+    assert (perm.astype(np.int64) == order).all()
+
+
 def test_hash_sort_storage_rejects_duplicates_and_bad_index(eng):
     from reth_b200 import B200Error, _lib
     addrs = random_keys(5, 4)[:, :20].copy()
