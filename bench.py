@@ -847,6 +847,7 @@ def bench_dynamic(args):
         "dstate_apply_c3_shape": ["tools/dstate_bench.py", "--accounts", "1000000", "--slots", "16", "--touch", "2000",
                                   "--slot-writes", "10", "--device-resident", "--cpu-sample", "40000"],
         "hash_sort_keys": ["tools/hash_sort_bench.py", "--keys", "10000000"],
+        "hash_sort_storage": ["tools/hash_sort_storage_bench.py", "--slots", "10000000", "--accounts", "200000"],
         "ordered_roots_receipts": ["tools/ordered_bench.py", "--blocks", "2000", "--items", "200", "--shape", "receipts"],
         "table_rows_c3_shape": ["tools/rows_bench.py", "--accounts", "1000000", "--slots", "16"],
     }
