@@ -7,10 +7,18 @@ out of scope; what is mirrored is each stage's full-pass data tr
   MerkleStage         : HashedAccounts + HashedStorages      -> state root (+ AccountsTrie/StoragesTrie updates),
                         validated against the header's state root (merkle.rs:437-453)
 
-and the incremental leg the pipeline takes for short block ranges (merkle.rs:255-300 with the incremental hashing of
-crates/storage/provider/src/providers/database/provider.rs:3206-3221,3266-3280): the changed plain accounts / slots of the
-range are hashed in one device batch, folded into the hashed tables and committed to a state kept resident on the device
-(`DynamicStateRoot`); the returned TrieUpdates are applied to the trie tables the way write_trie_updates does.
+and the incremental legs the pipeline takes for short block ranges (merkle.rs:255-300 with the incremental hashing of
+crates/storage/provider/src/providers/database/provider.rs:3206-3221,3266-3280), in two forms:
+
+  * nothing resident — the pipeline's own shape: `AccountHashingStage.execute_incremental` / `StorageHashingStage.
+    execute_incremental` take the range's changeset rows (b200_hash_changesets: every address and slot hashed once, first
+    occurrence kept) and bring the hashed tables up to date; `MerkleStage.execute_incremental_from_changesets` turns the same
+    rows into prefix sets (load_prefix_sets_with_provider) and folds the changed leaves with the stored hashes of every
+    untouched subtree (IncrementalStateRoot over b200_root_from_items);
+  * state resident on the device — `MerkleStage.execute_incremental`: the changed plain accounts / slots of the range are
+    hashed in one device batch, folded into the hashed tables and committed to a `DynamicStateRoot`.
+
+Either way the root is validated before the trie tables are written, the way write_trie_updates does it.
 """
 from __future__ import annotations
 
@@ -20,7 +28,8 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from .engine import Engine
-from .hashed_state import Account, HashedPostState, HashedPostStateSorted, HashedStorage, HashedStorageSorted, KeccakKeyHasher
+from .hashed_state import (Account, HashedPostState, HashedPostStateSorted, HashedStorage, HashedStorageSorted, KeccakKeyHasher,
+                           PrefixSet, TriePrefixSets, unpack_nibbles)
 from .trie import DynamicStateRoot, StateRoot, StorageTrieUpdates, TrieUpdates
 
 
@@ -57,6 +66,26 @@ class AccountHashingStage:
         return len(addrs)
 
 
+    def execute_incremental(self, t: Tables, changed_addresses) -> int:
+        """The stage's changeset leg (hashing_account.rs:240-262 -> insert_account_for_hashing, provider.rs:3206-3221):
+        `changed_addresses` are the addresses of the range's AccountChangeSets rows (repeats allowed); every distinct one is
+        hashed once on the device and HashedAccounts takes the account's CURRENT plain value — or loses the row."""
+        addrs = [bytes(a) for a in changed_addresses]
+        if not addrs:
+            return 0
+        cs = self.engine.hash_changesets(np.frombuffer(b"".join(addrs), np.uint8).reshape(-1, 20),
+                                         np.zeros((0, 20), np.uint8), np.zeros((0, 32), np.uint8))
+        hashed = dict(t.hashed_accounts)
+        for k, first in zip(cs["account_keys"], cs["account_first"]):
+            acc = t.plain_accounts.get(addrs[int(first)])
+            if acc is None:
+                hashed.pop(k.tobytes(), None)
+            else:
+                hashed[k.tobytes()] = acc
+        t.hashed_accounts = sorted(hashed.items())
+        return len(cs["account_keys"])
+
+
 class StorageHashingStage:
     """Full pass of hashing_storage.rs:106-178: composite key keccak(address) ‖ keccak(slot); the address digest
     is computed once per address (the reference caches it across consecutive entries, :129-134)."""
@@ -87,6 +116,34 @@ class StorageHashingStage:
                 t.hashed_storages.setdefault(keys[i, :32].tobytes(), []).append(
                     (keys[i, 32:].tobytes(), values[int(perm[i])]))
         return total
+
+
+    def execute_incremental(self, t: Tables, changed_rows) -> int:
+        """The changeset leg (hashing_storage.rs:180-206 -> insert_storage_for_hashing, provider.rs:3266-3280): `changed_rows` =
+        (address, slot) of the range's StorageChangeSets rows in changeset order (repeats allowed; a destroyed account lists
+        every slot it had).  One device call hashes each address once per run and each slot once and returns the unique pairs
+        as a CSR; HashedStorages takes every pair's CURRENT plain value, zero / absent = the row goes."""
+        rows = [(bytes(a), int(s)) for a, s in changed_rows]
+        if not rows:
+            return 0
+        sa = np.frombuffer(b"".join(a for a, _ in rows), np.uint8).reshape(-1, 20)
+        ss = np.frombuffer(b"".join(s.to_bytes(32, "big") for _, s in rows), np.uint8).reshape(-1, 32)
+        cs = self.engine.hash_changesets(np.zeros((0, 20), np.uint8), sa, ss)
+        offs = cs["storage_seg_offsets"]
+        for i, hk in enumerate(cs["storage_account_keys"]):
+            cur = dict(t.hashed_storages.get(hk.tobytes(), []))
+            for j in range(int(offs[i]), int(offs[i + 1])):
+                addr, slot = rows[int(cs["slot_first"][j])]
+                val = t.plain_storage.get(addr, {}).get(slot, 0)
+                if val:
+                    cur[cs["slot_keys"][j].tobytes()] = val
+                else:
+                    cur.pop(cs["slot_keys"][j].tobytes(), None)
+            if cur:
+                t.hashed_storages[hk.tobytes()] = sorted(cur.items())
+            else:
+                t.hashed_storages.pop(hk.tobytes(), None)
+        return len(cs["slot_keys"])
 
 
 class MerkleStage:
@@ -203,6 +260,41 @@ class MerkleStage:
         t.plain_accounts, t.plain_storage = plain_accounts, plain_storage
         t.hashed_storages = hashed_storages
         t.hashed_accounts = sorted(hashed_accounts.items())
+        self.write_trie_updates(t.trie_updates, upd)
+        return root
+
+    def execute_incremental_from_changesets(self, t: Tables, changed_addresses, changed_rows,
+                                            expected_state_root: Optional[bytes] = None) -> bytes:
+        """The incremental leg as the pipeline runs it (merkle.rs:255-300): nothing resident on the device.  The range's
+        changesets become prefix sets in one device call (load_prefix_sets_with_provider, crates/trie/db/src/prefix_set.rs:
+        22-60 -> b200_hash_changesets), the hashed tables — already brought up to date by the two hashing stages — supply the
+        leaves, the trie tables the hashes of every subtree the prefix sets do not touch (StateRoot::incremental_root_with_
+        updates -> IncrementalStateRoot over b200_root_from_items).  The root is validated before the trie tables are
+        written."""
+        from .walker import IncrementalStateRoot
+        if t.trie_updates is None:
+            raise StageError("no trie tables: run the rebuild (execute) once before incremental executions")
+        self.close()
+        addrs = [bytes(a) for a in changed_addresses]
+        rows = [(bytes(a), int(sl)) for a, sl in changed_rows]
+        cs = self.engine.hash_changesets(
+            np.frombuffer(b"".join(addrs), np.uint8).reshape(-1, 20) if addrs else np.zeros((0, 20), np.uint8),
+            np.frombuffer(b"".join(a for a, _ in rows), np.uint8).reshape(-1, 20) if rows else np.zeros((0, 20), np.uint8),
+            np.frombuffer(b"".join(sl.to_bytes(32, "big") for _, sl in rows), np.uint8).reshape(-1, 32) if rows
+            else np.zeros((0, 32), np.uint8))
+        live = dict(t.hashed_accounts)
+        offs = cs["storage_seg_offsets"]
+        prefix_sets = TriePrefixSets(
+            PrefixSet([unpack_nibbles(k.tobytes()) for k in cs["account_prefix_keys"]]),
+            {hk.tobytes(): PrefixSet([unpack_nibbles(cs["slot_keys"][j].tobytes()) for j in range(int(offs[i]), int(offs[i + 1]))])
+             for i, hk in enumerate(cs["storage_account_keys"])},
+            # destroyed_accounts: changed addresses that have no HashedAccounts row any more (prefix_set.rs:44-51)
+            {k.tobytes() for k in cs["account_keys"] if k.tobytes() not in live})
+        state = HashedPostStateSorted(list(t.hashed_accounts),
+                                      {k: HashedStorageSorted(list(v)) for k, v in t.hashed_storages.items()})
+        root, upd = IncrementalStateRoot(self.engine, t.trie_updates, state, prefix_sets).root_with_updates()
+        if expected_state_root is not None and root != expected_state_root:
+            raise StageError(f"state root mismatch: got {root.hex()}, expected {expected_state_root.hex()}")
         self.write_trie_updates(t.trie_updates, upd)
         return root
 

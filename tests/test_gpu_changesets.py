@@ -88,3 +88,79 @@ def test_empty_sides(eng):
     check(eng, acct, z20, z32)
     check(eng, z20, acct[:10], rng.integers(0, 256, (10, 32), dtype=np.uint8))
     check(eng, z20, z20, z32)
+
+
+def test_pipeline_incremental_from_changesets_equals_rebuild(eng):
+    """The three stages on their changeset legs, as the pipeline runs a short block range (hashing_account.rs:240-262,
+    hashing_storage.rs:180-206, merkle.rs:255-300 with load_prefix_sets_with_provider): the range's AccountChangeSets /
+    StorageChangeSets rows -> b200_hash_changesets -> hashed tables updated, prefix sets, incremental root over the trie
+    tables (b200_root_from_items) — hashed tables, root and trie tables equal a from-scratch run of the full-pass stages over
+    the same plain state.  Nothing is resident on the device between the ranges."""
+    from reth_b200 import Account, AccountHashingStage, MerkleStage, StorageHashingStage
+    from reth_b200.stages import Tables
+    rng = np.random.default_rng(61)
+    addr = lambda: bytes(rng.integers(0, 256, 20, dtype=np.uint8))
+    t = Tables()
+    for _ in range(700):
+        a = addr()
+        t.plain_accounts[a] = Account(int(rng.integers(0, 9)), int(rng.integers(1, 2**60)), None)
+        if rng.random() < 0.3:
+            t.plain_storage[a] = {int(rng.integers(0, 2**40)): int(rng.integers(1, 2**62)) for _ in range(int(rng.integers(1, 30)))}
+    AccountHashingStage(eng).execute(t)
+    StorageHashingStage(eng).execute(t)
+    ms = MerkleStage(eng)
+    ms.execute(t)
+    rows = lambda tu: {k: v.storage_nodes for k, v in tu.storage_tries.items() if v.storage_nodes}
+    for _range in range(3):
+        acct_cs, stor_cs = [], []
+        for _block in range(4):
+            live = sorted(t.plain_accounts)
+            picks = sorted({live[int(i)] for i in rng.choice(len(live), 25, replace=False)} | {addr() for _ in range(5)})
+            for a in picks:                                   # changeset order inside a block: by address
+                r = rng.random()
+                if a not in t.plain_accounts:                 # created (with storage, sometimes)
+                    acct_cs.append(a)
+                    t.plain_accounts[a] = Account(0, int(rng.integers(1, 2**60)), None)
+                    if rng.random() < 0.5:
+                        t.plain_storage[a] = {}
+                        for _ in range(4):
+                            sl = int(rng.integers(0, 2**40))
+                            stor_cs.append((a, sl))
+                            t.plain_storage[a][sl] = int(rng.integers(1, 2**62))
+                elif r < 0.35:                                # balance / nonce change
+                    acct_cs.append(a)
+                    old = t.plain_accounts[a]
+                    t.plain_accounts[a] = Account(old.nonce + 1, int(rng.integers(1, 2**60)), None)
+                elif r < 0.5:                                 # destroyed: the changesets list the account and every slot it had
+                    acct_cs.append(a)
+                    for sl in sorted(t.plain_storage.get(a, {})):
+                        stor_cs.append((a, sl))
+                    t.plain_accounts.pop(a)
+                    t.plain_storage.pop(a, None)
+                else:                                         # storage writes: new slots, changed slots, cleared slots
+                    st = t.plain_storage.setdefault(a, {})
+                    for sl in list(st)[:3]:
+                        stor_cs.append((a, sl))
+                        if rng.random() < 0.5:
+                            st.pop(sl)
+                        else:
+                            st[sl] = int(rng.integers(1, 2**62))
+                    for _ in range(3):
+                        sl = int(rng.integers(0, 2**40))
+                        stor_cs.append((a, sl))
+                        st[sl] = int(rng.integers(1, 2**62))
+        assert len(acct_cs) > len(set(acct_cs)) or len(stor_cs) > len(set(stor_cs)) or _range    # repeats across blocks do occur
+        AccountHashingStage(eng).execute_incremental(t, acct_cs)
+        StorageHashingStage(eng).execute_incremental(t, stor_cs)
+        root = ms.execute_incremental_from_changesets(t, acct_cs, stor_cs)
+        ref = Tables(plain_accounts=dict(t.plain_accounts), plain_storage={a: dict(s) for a, s in t.plain_storage.items()})
+        AccountHashingStage(eng).execute(ref)
+        StorageHashingStage(eng).execute(ref)
+        ref_root = MerkleStage(eng).execute(ref)
+        assert t.hashed_accounts == ref.hashed_accounts
+        assert t.hashed_storages == ref.hashed_storages
+        assert root == ref_root
+        assert t.trie_updates.account_nodes == ref.trie_updates.account_nodes
+        assert rows(t.trie_updates) == rows(ref.trie_updates)
+    with pytest.raises(Exception):
+        ms.execute_incremental_from_changesets(t, acct_cs[:1], [], expected_state_root=bytes(32))
