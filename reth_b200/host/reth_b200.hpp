@@ -760,6 +760,58 @@ class DynamicStateRoot {
         return {sroot, std::move(out)};
     }
 
+    /// MultiProof / StorageMultiProof of crates/trie/common/src/proofs.rs:180-188,594-602: node path -> RLP, with the hash / tree
+    /// masks of the stored branch nodes among them (branch_node_masks, what Proof::with_branch_node_masks(true) collects).
+    struct StorageMultiProof {
+        B256 root{};
+        std::map<Nibbles, std::vector<uint8_t>> subtree;
+        std::map<Nibbles, std::pair<uint16_t, uint16_t>> branch_node_masks;  // path -> (hash_mask, tree_mask)
+    };
+    struct MultiProof {
+        std::map<Nibbles, std::vector<uint8_t>> account_subtree;
+        std::map<Nibbles, std::pair<uint16_t, uint16_t>> branch_node_masks;
+        std::map<B256, StorageMultiProof> storages;
+    };
+    /// Proof::multiproof(MultiProofTargets) in one device call (crates/trie/trie/src/proof/mod.rs:143-193): hashed address ->
+    /// hashed slot targets.
+    MultiProof multiproof(const std::map<B256, std::vector<B256>> &targets) const {
+        std::vector<uint8_t> ak, sk;
+        std::vector<uint64_t> offs{0};
+        std::vector<std::vector<B256>> slots_of;
+        for (auto &kv : targets) {
+            ak.insert(ak.end(), kv.first.begin(), kv.first.end());
+            std::set<B256> uniq(kv.second.begin(), kv.second.end());
+            slots_of.emplace_back(uniq.begin(), uniq.end());
+            for (auto &s : slots_of.back()) sk.insert(sk.end(), s.begin(), s.end());
+            offs.push_back(sk.size() / 32);
+        }
+        const uint64_t n = targets.size();
+        std::vector<uint8_t> sroots(32 * (n ? n : 1));
+        b200_proofs pa{}, ps{};
+        e_.check(b200_dstate_multiproof(s_, ak.data(), n, offs.data(), sk.data(), &pa, sroots.data(), &ps));
+        MultiProof out;
+        auto fold = [](const b200_proofs &p, uint64_t t, const B256 &key, std::map<Nibbles, std::vector<uint8_t>> &subtree,
+                       std::map<Nibbles, std::pair<uint16_t, uint16_t>> &masks) {
+            Nibbles nib = unpack_nibbles(key);
+            for (uint64_t k = p.node_offset[t]; k < p.node_offset[t + 1]; k++) {
+                Nibbles path(nib.begin(), nib.begin() + p.node_depth[k]);
+                subtree[path] = std::vector<uint8_t>(p.rlp + p.rlp_offset[k], p.rlp + p.rlp_offset[k + 1]);
+                if (p.node_masks[k]) masks[path] = {(uint16_t)(p.node_masks[k] >> 16), (uint16_t)(p.node_masks[k] & 0xFFFF)};
+            }
+        };
+        uint64_t i = 0;
+        for (auto &kv : targets) {
+            fold(pa, i, kv.first, out.account_subtree, out.branch_node_masks);
+            StorageMultiProof &st = out.storages[kv.first];
+            std::memcpy(st.root.data(), sroots.data() + 32 * i, 32);
+            for (uint64_t j = offs[i]; j < offs[i + 1]; j++) fold(ps, j, slots_of[i][j - offs[i]], st.subtree, st.branch_node_masks);
+            i++;
+        }
+        b200_proofs_release(&pa);
+        b200_proofs_release(&ps);
+        return out;
+    }
+
   private:
     static std::vector<std::vector<uint8_t>> nodes_of(const b200_proofs &p, uint64_t t) {
         std::vector<std::vector<uint8_t>> out;

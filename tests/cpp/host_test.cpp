@@ -390,6 +390,32 @@ static void dynamic_state_blocks(const Engine &e) {
         B256 h;
         orc_keccak256(proof[0].data(), proof[0].size(), h.data());
         CHECK(h == root);
+        // the multiproof of a few accounts with slot targets == the union of their single proofs; storage roots included
+        std::map<B256, std::vector<B256>> targets;
+        int picked = 0;
+        for (auto &ks : merged.storages) {
+            if (!merged.accounts.count(ks.first) || ks.second.storage.empty() || ++picked > 4) continue;
+            targets[ks.first] = {ks.second.storage.begin()->first, rand_key()};
+        }
+        targets[rand_key()] = {rand_key()};  // an account that does not exist
+        auto mp = ds.multiproof(targets);
+        CHECK(mp.storages.size() == targets.size());
+        CHECK(mp.account_subtree.count(Nibbles{}) == 1);
+        size_t union_nodes = 0;
+        std::set<std::vector<uint8_t>> seen;
+        for (auto &kv : targets) {
+            for (auto &node : ds.account_proof(kv.first))
+                if (seen.insert(node).second) union_nodes++;
+            auto sp = ds.storage_proofs(kv.first, kv.second);
+            CHECK(sp.first == mp.storages[kv.first].root);
+            std::set<std::vector<uint8_t>> snodes;
+            for (auto &pr : sp.second) snodes.insert(pr.begin(), pr.end());
+            std::set<std::vector<uint8_t>> got;
+            for (auto &pn : mp.storages[kv.first].subtree) got.insert(pn.second);
+            CHECK(got == snodes);
+        }
+        CHECK(mp.account_subtree.size() == union_nodes);
+        for (auto &bm : mp.branch_node_masks) CHECK(mp.account_subtree.count(bm.first) == 1 && (bm.second.first | bm.second.second));
     }
 }
 
