@@ -1,3 +1,5 @@
+"""cuobjdump -sass <binary> | python sassmix.py : opcode histogram per kernel (IMAD split by its .WIDE / .HI / .MOV ... forms),
+used to check which pipe the rotates of rot_pipes.cu ended up on."""
 import sys,re,collections
 fn=None; cnt=collections.defaultdict(collections.Counter)
 for l in sys.stdin:
