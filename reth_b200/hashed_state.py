@@ -241,6 +241,28 @@ class HashedPostStateSorted:
     accounts: List[Tuple[B256, Optional[Account]]] = field(default_factory=list)
     storages: Dict[B256, HashedStorageSorted] = field(default_factory=dict)
 
+    @classmethod
+    def from_reverts(cls, engine: Engine, account_changesets, storage_changesets) -> "HashedPostStateSorted":
+        """DatabaseHashedPostState::from_reverts (crates/trie/db/src/state.rs:289-347): the state to go back to when the blocks
+        of a range are unwound.  account_changesets: (address20, Account-before or None) rows in changeset order (block, then
+        address); storage_changesets: (address20, slot (int or 32 bytes), value-before) rows likewise.  The value before the
+        FIRST change of every address / (address, slot) pair is kept, addresses and slots are keccak-hashed, everything comes
+        back in trie order — one b200_hash_changesets call instead of the HashSets and the sorts on one core."""
+        acct = [(bytes(a), info) for a, info in account_changesets]
+        stor = [(bytes(a), sl if isinstance(sl, (bytes, bytearray)) else int(sl).to_bytes(32, "big"), int(v))
+                for a, sl, v in storage_changesets]
+        blob = lambda rows, w: np.frombuffer(b"".join(rows), np.uint8).reshape(-1, w) if rows else np.zeros((0, w), np.uint8)
+        cs = engine.hash_changesets(blob([a for a, _ in acct], 20), blob([a for a, _, _ in stor], 20),
+                                    blob([bytes(sl) for _, sl, _ in stor], 32))
+        accounts = [(k.tobytes(), acct[int(i)][1]) for k, i in zip(cs["account_keys"], cs["account_first"])]
+        offs = cs["storage_seg_offsets"]
+        storages = {}
+        for t, hk in enumerate(cs["storage_account_keys"]):
+            seg = range(int(offs[t]), int(offs[t + 1]))
+            storages[hk.tobytes()] = HashedStorageSorted([(cs["slot_keys"][j].tobytes(), stor[int(cs["slot_first"][j])][2]) for j in seg],
+                                                         False)
+        return cls(accounts, storages)
+
     def to_flat(self):
         """The flat layout of include/b200trie.h for a state that IS the whole state (no database underneath):
         destroyed accounts (None) and zero-valued slots are dropped exactly where the reference's cursors skip

@@ -164,3 +164,38 @@ def test_pipeline_incremental_from_changesets_equals_rebuild(eng):
         assert rows(t.trie_updates) == rows(ref.trie_updates)
     with pytest.raises(Exception):
         ms.execute_incremental_from_changesets(t, acct_cs[:1], [], expected_state_root=bytes(32))
+
+
+def test_from_reverts_mirror(eng):
+    """crates/trie/db/src/state.rs:439-517 `from_reverts_keeps_first_occurrence_and_ordering` and :519-541
+    `from_reverts_empty_range`, through HashedPostStateSorted.from_reverts (one b200_hash_changesets call)."""
+    from reth_b200 import Account, HashedPostStateSorted
+    a1, a2 = bytes(19) + b"\x01", bytes(19) + b"\x02"
+    acct = [(a1, Account(1, 0, None)), (a1, Account(2, 0, None)), (a2, None)]        # blocks 1, 2, 3
+    stor = [(a1, 22, 200), (a1, 11, 100), (a1, 11, 999)]                              # the last row must be ignored
+    st = HashedPostStateSorted.from_reverts(eng, acct, stor)
+    h1, h2 = oracle.keccak256(a1), oracle.keccak256(a2)
+    assert len(st.accounts) == 2
+    assert dict(st.accounts)[h1].nonce == 1 and dict(st.accounts)[h2] is None
+    assert [k for k, _ in st.accounts] == sorted([h1, h2])
+    slots = st.storages[h1].storage_slots
+    assert slots == sorted([(oracle.keccak256((11).to_bytes(32, "big")), 100), (oracle.keccak256((22).to_bytes(32, "big")), 200)])
+    assert st.storages[h1].wiped is False and set(st.storages) == {h1}
+    empty = HashedPostStateSorted.from_reverts(eng, [], [])
+    assert empty.accounts == [] and empty.storages == {}
+    # random ranges against the host restatement above
+    rng = np.random.default_rng(17)
+    addrs = [bytes(rng.integers(0, 256, 20, dtype=np.uint8)) for _ in range(40)]
+    acct = [(addrs[int(rng.integers(0, 40))], Account(int(i), 0, None) if rng.random() < 0.8 else None) for i in range(300)]
+    stor = [(addrs[int(rng.integers(0, 40))], int(rng.integers(0, 25)), int(i) + 1) for i in range(900)]
+    st = HashedPostStateSorted.from_reverts(eng, acct, stor)
+    first_a, first_s = {}, {}
+    for a, info in acct:
+        first_a.setdefault(a, info)
+    for a, sl, v in stor:
+        first_s.setdefault((a, sl), v)
+    assert st.accounts == sorted((oracle.keccak256(a), info) for a, info in first_a.items())
+    want = {}
+    for (a, sl), v in first_s.items():
+        want.setdefault(oracle.keccak256(a), []).append((oracle.keccak256(sl.to_bytes(32, "big")), v))
+    assert {k: v.storage_slots for k, v in st.storages.items()} == {k: sorted(v) for k, v in want.items()}
